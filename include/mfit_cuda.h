@@ -1,0 +1,193 @@
+/* mfit_cuda.h -- C ABI of libmfit_cuda.so, the B200 (sm_100a) backend for the
+ * Metropolis-Hastings hot path of afranson/Lisp-MCMC.
+ *
+ * Every entry point names the reference interface it stands in for; citations are
+ * into /root/reference/mcmc-fitting.lisp unless another file is named.  The host
+ * (SBCL through CFFI -- lisp_mcmc_b200/lisp/mfit-cuda.lisp -- or the Python mirror in
+ * lisp_mcmc_b200/walker.py through ctypes) owns every host pointer only for the
+ * duration of a call; the library copies.  The library owns device memory, its
+ * stream, the NVRTC cache and the NCCL communicator.  No callbacks into the host.
+ *
+ * All functions return 0 on success or a negative mfit_status; the message is
+ * available from mfit_last_error().  NaN/Inf in likelihoods are returned, never
+ * raised.  A context is single-owner: one host thread at a time.
+ *
+ * There is no CPU fallback: without a CUDA device mfit_ctx_create fails with
+ * MFIT_ERR_CUDA.
+ */
+#ifndef MFIT_CUDA_H
+#define MFIT_CUDA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFIT_ABI_VERSION 1
+
+typedef enum {
+  MFIT_OK = 0,
+  MFIT_ERR_ARG = -1,      /* bad argument (reference: Lisp `error` in clean-data :819,:825) */
+  MFIT_ERR_CUDA = -2,     /* CUDA runtime / driver failure, or no device */
+  MFIT_ERR_SEXPR = -3,    /* s-expression could not be parsed or lowered */
+  MFIT_ERR_NVRTC = -4,    /* NVRTC unavailable or compilation failed (log in mfit_last_error) */
+  MFIT_ERR_STATE = -5,    /* call made in the wrong order (e.g. run before chains_init) */
+  MFIT_ERR_STREAM = -6,   /* injected z/u stream shorter than the steps requested */
+  MFIT_ERR_NCCL = -7,
+  MFIT_ERR_NOMEM = -8
+} mfit_status;
+
+/* Model families (the reference ships none -- README.md:11 tells users to write them; SURVEY.md 8(d)
+ * defines these).  theta order:
+ *   POLY (degree D): c0..cD            f = c0 + x(c1 + x(c2 + ...))
+ *   EXPO:      a b c                   f = a exp(b x) + c
+ *   SINUS:     a omega phi c           f = a sin(omega x + phi) + c
+ *   LORENTZ:   a x0 gamma c            f = a gamma^2 / ((x-x0)^2 + gamma^2) + c
+ *   GAUSS_LIN: a mu s b0 b1            f = a exp(-((x-mu)/s)^2 / 2) + b0 + b1 x
+ *   NV_MULTI (K dips, `degree` = K): scale_1..K mu_1..K sigma bg0  (names: nv-specific.lisp:25-30)
+ *                                      f = bg0 - sum_k scale_k sigma^2 / ((x-mu_k)^2 + sigma^2)
+ *   SEXPR: user lambda lowered to CUDA C and compiled by NVRTC for sm_100a */
+enum { MFIT_FAM_POLY = 0, MFIT_FAM_EXPO = 1, MFIT_FAM_SINUS = 2, MFIT_FAM_LORENTZ = 3,
+       MFIT_FAM_GAUSS_LIN = 4, MFIT_FAM_NV_MULTI = 5, MFIT_FAM_SEXPR = 100 };
+
+/* :log-liklihood slot values.  NORMAL = log-liklihood-normal :393-400, NORMAL_CUTOFF =
+ * log-liklihood-normal-cutoff :419-427, POISSON = (create-log-liklihood-function
+ * (lambda (y model error) (log-poisson model y))) :402-417 with log-poisson :382-383. */
+enum { MFIT_LL_NORMAL = 0, MFIT_LL_NORMAL_CUTOFF = 1, MFIT_LL_POISSON = 2 };
+
+enum { MFIT_AUTO_NONE = 0, MFIT_AUTO_PROB_SETTLE = 1 };      /* :auto, :862 */
+enum { MFIT_OPT_COVARIANCE = 0, MFIT_OPT_BEST_VALUE = 1 };   /* :sampling-optimization, :862 */
+
+typedef struct mfit_ctx mfit_ctx;
+
+/* keyword arguments of walker-adaptive-steps-full, :862 */
+typedef struct {
+  int64_t n;                    /* :n (default 100000); walker-adaptive-steps :946 passes 30000 */
+  double temperature;           /* :temperature (default 1d3; walker-adaptive-steps passes 10) */
+  int32_t auto_mode;            /* :auto  MFIT_AUTO_* (:slope-settle is not supported) */
+  int32_t sampling_optimization;/* :sampling-optimization MFIT_OPT_* */
+  int64_t max_walker_length;    /* :max-walker-length, 0 = nil */
+  int32_t greedy;               /* 1 = accept only uphill (walker-pretend-take-step :1117) */
+  int32_t reserved;
+} mfit_adapt_cfg;
+
+/* per-chain summary, filled by mfit_stats_read (struct walker :467-479 scalar slots) */
+typedef struct {
+  int64_t length;          /* walker-length */
+  int64_t age;             /* walker-age */
+  int64_t steps_this_run;  /* take-step calls made by the last run */
+  double last_prob;        /* (walker-step-prob (walker-last-step w)) */
+  double best_prob;        /* (walker-step-prob (walker-most-likely-step w)) */
+  double temperature;      /* temperature at exit of the last run */
+  double accept_200;       /* walker-get :acceptance :take 200, :506-508 */
+  int32_t shutting_down;   /* shutting-down-p at exit */
+  int32_t l_updates;       /* number of l-matrix updates (rescale or re-estimate) in the last run */
+} mfit_chain_stats;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int mfit_abi_version(void);
+/* `stream` is a cudaStream_t (NULL = the library creates its own non-blocking stream). */
+int mfit_ctx_create(int device, void* stream, mfit_ctx** out);
+void mfit_ctx_destroy(mfit_ctx* ctx);
+const char* mfit_last_error(mfit_ctx* ctx);     /* ctx may be NULL: last create error */
+int mfit_synchronize(mfit_ctx* ctx);
+int64_t mfit_launch_count(mfit_ctx* ctx);       /* kernels launched by this ctx so far */
+
+/* ---- walker-create :1132-1163: problem definition -------------------------------------------
+ * D datasets (length of the :function list), P shared parameters (length of the :params plist). */
+int mfit_problem_define(mfit_ctx* ctx, int n_datasets, int n_params);
+/* :data (list x y) and :data-error of dataset d.  sigma==NULL means data-error 1 (:1144).
+ * Stands in for clean-data / clean-data-error / to-double-floats :774-835 (the host flattens). */
+int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, const double* sigma, int64_t n);
+/* :function slot of dataset d = built-in family; param_index maps family theta slots to the
+ * shared parameter vector (global fits share keys across datasets, README.md "Global Parameter Fitting"). */
+int mfit_model_builtin(mfit_ctx* ctx, int d, int family, int degree, const int32_t* param_index, int n_idx);
+/* :function slot = user lambda text, e.g. "(lambda (x &key a b &allow-other-keys) (+ b (* a x)))";
+ * key_names are the P keys of the :params plist in order.  Lowered to CUDA C, NVRTC -> sm_100a. */
+int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* const* key_names, int n_keys);
+int mfit_likelihood_set(mfit_ctx* ctx, int d, int kind);
+/* :log-prior slot.  flat = log-prior-flat :340-343; bounds = (prior-bounds-let ((k lo hi)...) bounds-total)
+ * :346-369 with constant bounds (idx<0 means the key is absent: getf default 0d0); sexpr = any
+ * (lambda (params data) ...) body, prior-bounds-let included. */
+int mfit_prior_flat(mfit_ctx* ctx, int d);
+int mfit_prior_bounds(mfit_ctx* ctx, int d, int n, const int32_t* idx, const double* lo, const double* hi);
+int mfit_prior_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* const* key_names, int n_keys);
+
+/* s-expression -> CUDA C lowering, exposed so it can be inspected and tested without a GPU.
+ * kind 0 = model lambda, 1 = prior lambda.  Returns bytes needed (incl. NUL) or a negative status. */
+int mfit_lower_sexpr(const char* lambda_text, const char* const* key_names, int n_keys, int kind,
+                     char* out, int out_len, char* err, int err_len);
+
+/* ---- walker-make-step :1067-1070 over a batch of parameter vectors ------------------------------
+ * theta: W x P row-major.  ll, lp: W x D row-major per-dataset terms (either may be NULL);
+ * prob: W totals = (sum_d ll) + (sum_d lp) in dataset order. */
+int mfit_eval_logp(mfit_ctx* ctx, const double* theta, int64_t W, double* prob, double* ll, double* lp);
+
+/* ---- chains: W independent walkers sharing the problem ------------------------------------------
+ * theta0: W x P.  Evaluates the first step like walker-create :1148-1162 (length = age = 1).
+ * chain_id_base: global id of chain 0 (Philox streams are keyed by global chain id, so a sharded run
+ * draws the same numbers as a single-GPU run).  trace_capacity: rows of history kept per chain
+ * (0 = as many as the next run needs, bounded by free memory; always >= max(1000, 10*max(50,P)) + 1). */
+int mfit_chains_init(mfit_ctx* ctx, const double* theta0, int64_t W, uint64_t seed, int64_t chain_id_base,
+                     int64_t trace_capacity);
+/* walker-adaptive-steps-full :862-942.  l_matrix: NULL, or P x P row-major shared by all chains
+ * (:l-matrix).  z: W x nstream x P normals and u: W x nstream uniforms, indexed by the count of
+ * take-step calls in this run (NULL = on-device Philox4x32-10).  steps_launched (may be NULL)
+ * receives the number of MH steps enqueued (the longest chain). */
+int mfit_run_adaptive(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, const double* l_matrix,
+                      const double* z, const double* u, int64_t nstream, int64_t* steps_launched);
+/* walker-many-steps :849-853: n steps, constant l-matrix (required), temperature 1 */
+int mfit_run_many_steps(mfit_ctx* ctx, int64_t n, const double* l_matrix, const double* z, const double* u,
+                        int64_t nstream);
+/* walker-sample-region :949-969 */
+int mfit_run_sample_region(mfit_ctx* ctx, double initial_scale, const double* z, int64_t nstream);
+/* walker-force-take-step :1124-1129 */
+int mfit_force_take_step(mfit_ctx* ctx);
+/* mfit-walker-estop :860: asynchronous stop request, polled between launches */
+int mfit_request_stop(mfit_ctx* ctx);
+
+/* walker-get :steps / :log-liklihoods :take, newest first.  theta: W x take x P, prob: W x take,
+ * n_valid: W (rows filled per chain; the rest is NaN).  Any output may be NULL. */
+int mfit_trace_read(mfit_ctx* ctx, int64_t take, double* theta, double* prob, int64_t* n_valid);
+int mfit_stats_read(mfit_ctx* ctx, mfit_chain_stats* stats /* W */);
+/* most-likely-step :474 and last-step :475.  theta outputs W x P. */
+int mfit_best_read(mfit_ctx* ctx, double* theta, double* prob);
+int mfit_last_read(mfit_ctx* ctx, double* theta, double* prob);
+/* l-matrix in use at the end of the last run, W x P x P */
+int mfit_l_matrix_read(mfit_ctx* ctx, double* l);
+/* walker-modify :keep-walks :568-569 applied to every chain */
+int mfit_keep_walks(mfit_ctx* ctx, int64_t keep);
+
+/* normals / uniforms the on-device Philox stream yields for (seed, global chain id, step index):
+ * lets a test replay a Philox run through the injected-stream path of another implementation. */
+int mfit_philox_stream(mfit_ctx* ctx, uint64_t seed, int64_t chain_id_base, int64_t W, int64_t first_step,
+                       int64_t nsteps, int P, double* z /* W x nsteps x P */, double* u /* W x nsteps */);
+
+/* ---- multi-GPU (one process per GPU) --------------------------------------------------------------
+ * Chain-sharded runs need no collective on the data path.  Dataset-sharded global fits
+ * (walker-make-step's sum over datasets, :1068-1069, split across ranks) exchange per-dataset
+ * ll/lp every step with ncclAllGather and sum them in dataset order on every rank. */
+int mfit_nccl_unique_id(void* id_out /* 128 bytes */);
+int mfit_nccl_attach(mfit_ctx* ctx, const void* unique_id, int rank, int n_ranks);
+/* owner[d] = rank that evaluates dataset d (others skip it). Requires mfit_nccl_attach. */
+int mfit_dataset_owners(mfit_ctx* ctx, const int32_t* owner);
+/* gather chain-sharded traces on every rank: local (W_local x take x (P+1)) -> out (n_ranks x ...) */
+int mfit_nccl_allgather_f64(mfit_ctx* ctx, const double* local_host, int64_t count, double* out_host);
+
+/* ---- measurement helpers ----------------------------------------------------------------------------
+ * FP64 DFMA issue peak of the device this ctx is bound to, measured live (FLOP/s, 2 per DFMA), and the
+ * DFMA-equivalent cost of the FP64 transcendentals used by the model families. */
+int mfit_measure_fp64(mfit_ctx* ctx, double* dfma_flops, double* cost_exp, double* cost_log, double* cost_sin,
+                      double* cost_div);
+/* device time of the eval kernels of the last run / eval call, seconds (CUDA events on the ctx stream),
+ * and how many eval launches it covered */
+int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches);
+/* write > L2 bytes on the ctx stream (bench hygiene between timed steps) */
+int mfit_flush_l2(mfit_ctx* ctx);
+/* run exactly `n_steps` more MH steps with the adaptive driver state left by mfit_run_adaptive
+ * re-armed for n = n_steps (used by bench.py to time step by step) */
+int mfit_stream_handle(mfit_ctx* ctx, void** stream_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

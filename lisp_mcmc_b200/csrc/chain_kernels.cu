@@ -1,0 +1,707 @@
+// chain_kernels.cu -- per-chain side of the Metropolis-Hastings step, one thread per chain.
+//
+// Device form of hot loop #1 of the reference (mcmc-fitting.lisp:902-942): proposal theta' = theta + L.z
+// (get-covariant-sample :679-700), the accept test of walker-take-step (:1091-1094), walker-modify
+// :add-step (:549-555), the temperature schedule, auto-stop and acceptance-window l-matrix update of
+// walker-adaptive-steps-full (:905-942) and the forward-step covariance + Cholesky re-estimate
+// (:497-502, :263-280, :614-643, :583-598, :888-895).
+//
+// This translation unit is compiled with -fmad=false and keeps the reference's operation order
+// (sequential sums, separate multiply and add) so that, given the same injected normals/uniforms and the
+// same log-probabilities, proposals, l-matrices and decisions are bit-identical to the CPU oracle.
+#include <cuda_runtime.h>
+#include <math.h>
+#include "mfit_chain.h"
+#include "mfit_internal.h"
+
+namespace {
+
+// ------------------------------------------------------------------ Philox4x32-10 (counter based)
+struct U4 { unsigned x, y, z, w; };
+__device__ __forceinline__ U4 philox4x32_10(U4 c, unsigned k0, unsigned k1) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    U4 n;
+    n.x = hi1 ^ c.y ^ k0;
+    n.y = lo1;
+    n.z = hi0 ^ c.w ^ k1;
+    n.w = lo0;
+    c = n;
+    k0 += W0;
+    k1 += W1;
+  }
+  return c;
+}
+__device__ __forceinline__ double u01(unsigned hi, unsigned lo) {  // (0,1), 53 bits
+  unsigned long long v = ((unsigned long long)hi << 32) | lo;
+  return ((double)(v >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+// stream layout: counter = (step_lo, step_hi, chain_lo, chain_hi16 | lane << 16); lane 0xFFFF = accept uniform,
+// lane m < 0xFFFF = normals 2m, 2m+1 (Box-Muller)
+__device__ __forceinline__ void philox_pair(unsigned long long seed, long long gchain, long long step, unsigned lane,
+                                            double* a, double* b) {
+  U4 c;
+  c.x = (unsigned)step;
+  c.y = (unsigned)((unsigned long long)step >> 32);
+  c.z = (unsigned)gchain;
+  c.w = ((unsigned)((unsigned long long)gchain >> 32) & 0xFFFFu) | (lane << 16);
+  U4 r = philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
+  *a = u01(r.x, r.y);
+  *b = u01(r.z, r.w);
+}
+__device__ __forceinline__ void philox_normals(unsigned long long seed, long long gchain, long long step, int P,
+                                               double* z) {
+  for (int m = 0; 2 * m < P; m++) {
+    double u1, u2, s, c;
+    philox_pair(seed, gchain, step, (unsigned)m, &u1, &u2);
+    double rad = sqrt(-2.0 * log(u1));
+    sincospi(2.0 * u2, &s, &c);
+    z[2 * m] = rad * c;
+    if (2 * m + 1 < P) z[2 * m + 1] = rad * s;
+  }
+}
+__device__ __forceinline__ double philox_uniform(unsigned long long seed, long long gchain, long long step) {
+  double a, b;
+  philox_pair(seed, gchain, step, 0xFFFFu, &a, &b);
+  return a;
+}
+
+// ------------------------------------------------------------------ trace ring access
+__device__ __forceinline__ double tprob(const MfitChains& c, long long row, long long w) {
+  return c.trace_prob[(size_t)(row % c.cap) * c.stride + w];
+}
+__device__ __forceinline__ double ttheta(const MfitChains& c, long long row, int i, long long w) {
+  return c.trace_theta[((size_t)(row % c.cap) * c.P + i) * c.stride + w];
+}
+// (walker-get w :get :steps :take take): the newest min(length, take) rows
+__device__ __forceinline__ long long wlen(const MfitChains& c, long long w, long long take) {
+  long long m = c.length[w] < take ? c.length[w] : take;
+  if (m > c.rows[w]) m = c.rows[w];
+  if (m > c.cap) m = c.cap;
+  return m;
+}
+// walker-get :acceptance :506-508 -> exact count / len
+__device__ void acc_window(const MfitChains& c, long long w, long long take, long long* cnt, long long* len) {
+  long long m = wlen(c, w, take);
+  long long r = c.rows[w] - 1;
+  long long n = 1;  // the oldest element of the window is always kept
+  unsigned long long prev = (unsigned long long)__double_as_longlong(tprob(c, r, w));
+  for (long long k = 1; k < m; k++) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(tprob(c, r - k, w));
+    if (b != prev) n++;
+    prev = b;
+  }
+  *cnt = m > 0 ? n : 0;
+  *len = m;
+}
+// (< acc thr) / (> acc thr) with thr a single-float literal compared exactly against the rational count/len
+__device__ __forceinline__ bool acc_lt(long long cnt, long long len, float thr) {
+  return (double)cnt < (double)thr * (double)len;
+}
+__device__ __forceinline__ bool acc_gt(long long cnt, long long len, float thr) {
+  return (double)cnt > (double)thr * (double)len;
+}
+// stable-probs-p :880-885
+__device__ bool stable_probs(const MfitChains& c, long long w, long long S) {
+  long long m = wlen(c, w, S);
+  if (m < 200) return false;
+  long long hi = c.rows[w] - 1, lo = c.rows[w] - m;
+  double early = tprob(c, hi, w);
+  for (long long j = hi - 199; j <= hi; j++) early = fmax(early, tprob(c, j, w));
+  double late = tprob(c, lo, w);
+  for (long long j = lo; j < lo + 200; j++) late = fmax(late, tprob(c, j, w));
+  double mn = tprob(c, lo, w);
+  for (long long j = lo; j <= hi; j++) mn = fmin(mn, tprob(c, j, w));
+  double spread = early - mn;
+  return (fabs(early - late) < 0.5) && (4.0 < spread && spread < 9.0);
+}
+
+__device__ __forceinline__ double* ll_ptr(const MfitChains& c, int d) {
+  if (c.xch) {
+    const MfitDsDev& s = c.ds[d];
+    return const_cast<double*>(c.xch) + ((size_t)(s.xrank * c.xslots + s.xslot) * 2 + 0) * c.stride;
+  }
+  return c.lld + (size_t)d * c.stride;
+}
+__device__ __forceinline__ double* lp_ptr(const MfitChains& c, int d) {
+  if (c.xch) {
+    const MfitDsDev& s = c.ds[d];
+    return const_cast<double*>(c.xch) + ((size_t)(s.xrank * c.xslots + s.xslot) * 2 + 1) * c.stride;
+  }
+  return c.lpd + (size_t)d * c.stride;
+}
+
+// per-segment partial sums -> dataset log-likelihood (segments added in order)
+__device__ double finalize_ll(const MfitChains& c, int d, long long w) {
+  const MfitDsDev& s = c.ds[d];
+  double sum = 0.0;
+  if (s.n_seg > 0) {
+    sum = s.partial[w];
+    for (int k = 1; k < s.n_seg; k++) sum = sum + s.partial[(size_t)k * c.stride + w];
+  }
+  switch (s.ll_kind) {
+    case MFIT_LL_NORMAL: return s.cst + (-0.5 * sum);
+    case MFIT_LL_NORMAL_CUTOFF: return sum;
+    default: return s.cst + sum;
+  }
+}
+
+// prior-bounds-let with constant bounds, body = bounds-total (:346-369); flat = 0d0 (:340-343)
+__device__ double builtin_prior(const MfitChains& c, const MfitDsDev& s, const double* theta, long long w) {
+  if (s.prior_kind != 1) return 0.0;
+  double total = 0.0;
+  for (int k = 0; k < s.nb; k++) {
+    int id = s.b_idx[k];
+    double p = id >= 0 ? theta[(size_t)id * c.stride + w] : 0.0;
+    double lo = s.b_lo[k], hi = s.b_hi[k], b;
+    if (lo < p && p < hi)
+      b = 0.0;
+    else {
+      double a1 = fabs(p - hi), a2 = fabs(p - lo);
+      double m = a1;
+      if (a2 < a1) m = a2;
+      b = -1e10 * (exp(m * 1e-5) - 1.0);
+    }
+    total = k == 0 ? b : total + b;
+  }
+  return total;
+}
+
+__device__ void scale_L(const MfitChains& c, long long w, double s) {  // scale-array :605-611
+  const int PP = c.P * c.P;
+  for (int e = 0; e < PP; e++) {
+    double* p = c.L + (size_t)e * c.stride + w;
+    *p = s * *p;
+  }
+}
+
+// ------------------------------------------------------------------ top of loop iteration: shutdown test + proposal
+__device__ void pre_body(const MfitChains& c, const MfitRunCfg& r, long long w) {
+  if (c.done[w]) return;
+  const int P = c.P;
+  if (r.mode == MFIT_MODE_ADAPTIVE) {  // :905-917
+    long long i = c.loop_i[w];
+    bool sh = c.shutting[w] != 0;
+    bool trig = (!sh && (r.n - i) < r.tail);
+    if (!trig && r.auto_mode != MFIT_AUTO_NONE && !sh && i > 2 * r.S && (i % 1000 == 0)) {
+      long long cnt, len;
+      acc_window(c, w, 1000, &cnt, &len);
+      if (acc_gt(cnt, len, 0.2f) && (double)cnt < 0.5 * (double)len) trig = stable_probs(c, w, r.S);
+    }
+    if (trig) {
+      c.temperature[w] = 1.0;
+      c.shutting[w] = 1;
+      c.loop_i[w] = r.n - r.tail;
+    }
+  }
+  // get-covariant-sample :679-700
+  double z[MFIT_MAX_P];
+  if (r.z) {
+    const double* zp = r.z + ((size_t)w * r.nstream + r.t) * P;
+    for (int j = 0; j < P; j++) z[j] = zp[j];
+  } else
+    philox_normals(r.seed, r.chain_base + w, c.age[w], P, z);
+  for (int i = 0; i < P; i++) {
+    double s = 0.0;
+    for (int j = 0; j < P; j++) s = s + c.L[(size_t)(i * P + j) * c.stride + w] * z[j];
+    c.prop_theta[(size_t)i * c.stride + w] = s + c.cur_theta[(size_t)i * c.stride + w];
+  }
+  for (int d = 0; d < c.D; d++) {
+    const MfitDsDev& s = c.ds[d];
+    if (s.owned && s.prior_kind != 2) lp_ptr(c, d)[w] = builtin_prior(c, s, c.prop_theta, w);
+  }
+}
+
+// ------------------------------------------------------------------ after the likelihood: accept, push, adapt
+template <bool FIN>
+__device__ void post_body(const MfitChains& c, const MfitRunCfg& r, long long w) {
+  if (c.done[w]) return;
+  const int P = c.P;
+  // walker-make-step :1067-1070
+  double ll = 0.0, lp = 0.0;
+  for (int d = 0; d < c.D; d++) {
+    double v = FIN ? finalize_ll(c, d, w) : ll_ptr(c, d)[w];
+    ll = d == 0 ? v : ll + v;
+  }
+  for (int d = 0; d < c.D; d++) {
+    double v = lp_ptr(c, d)[w];
+    lp = d == 0 ? v : lp + v;
+  }
+  const double p1 = ll + lp;
+  const double p0 = c.cur_prob[w];
+  const double T = c.temperature[w];
+  bool acc = p1 > p0;  // :1091
+  if (!acc && !r.greedy) {
+    double u = r.u ? r.u[(size_t)w * r.nstream + r.t] : philox_uniform(r.seed, r.chain_base + w, c.age[w]);
+    acc = (p1 - p0) / T > log(u);  // :1092
+  }
+  if (acc) {
+    for (int i = 0; i < P; i++) c.cur_theta[(size_t)i * c.stride + w] = c.prop_theta[(size_t)i * c.stride + w];
+    c.cur_prob[w] = p1;
+    if (p1 > c.best_prob[w]) {  // :553-555
+      for (int i = 0; i < P; i++) c.best_theta[(size_t)i * c.stride + w] = c.prop_theta[(size_t)i * c.stride + w];
+      c.best_prob[w] = p1;
+    }
+  }
+  // walker-modify :add-step :549-552
+  {
+    const long long row = c.rows[w];
+    const size_t slot = (size_t)(row % c.cap);
+    for (int i = 0; i < P; i++)
+      c.trace_theta[(slot * P + i) * c.stride + w] = c.cur_theta[(size_t)i * c.stride + w];
+    c.trace_prob[slot * c.stride + w] = c.cur_prob[w];
+    c.rows[w] = row + 1;
+    c.length[w] += 1;
+    c.age[w] += 1;
+    c.steps_run[w] += 1;
+  }
+  long long i = c.loop_i[w];
+  if (r.mode == MFIT_MODE_ADAPTIVE) {
+    const bool sh = c.shutting[w] != 0;
+    if (!sh && i < r.Tn) c.temperature[w] = r.temps[i];  // :920-921
+    if (r.mwl && i == c.reset_index[w]) {                 // :923-927
+      if (c.length[w] > r.mwl) {
+        c.length[w] = r.mwl;
+        c.reset_index[w] += 1 + r.mwl;
+      } else
+        c.reset_index[w] += 1 + (r.mwl - c.length[w]);
+    }
+    if (i > 0) {  // :929-942
+      bool enter = false, have = false;
+      long long cnt = 0, len = 1;
+      if (i % 200 == 0) {
+        acc_window(c, w, 200, &cnt, &len);
+        have = true;
+        if (acc_lt(cnt, len, 0.2f) || acc_gt(cnt, len, 0.4f)) enter = true;
+      }
+      if (!enter && !sh && (i % (2 * r.S) == 0)) enter = true;
+      if (enter) {
+        if (!have) acc_window(c, w, 200, &cnt, &len);
+        if (acc_gt(cnt, len, 0.2f) && acc_lt(cnt, len, 0.4f))
+          c.need_reest[w] = 1;
+        else if (acc_lt(cnt, len, 0.2f)) {
+          scale_L(c, w, 0.1);
+          c.l_updates[w] += 1;
+        } else if (acc_gt(cnt, len, 0.4f)) {
+          scale_L(c, w, 1.9);
+          c.l_updates[w] += 1;
+        }
+      }
+    }
+    i++;
+    if (i >= r.n) c.done[w] = 1;
+  } else if (r.mode == MFIT_MODE_MANY) {
+    i++;
+    if (i >= r.n) c.done[w] = 1;
+  } else {  // walker-sample-region :960-969
+    if (i > 0 && i % 20 == 0) {
+      long long cnt, len;
+      acc_window(c, w, 50, &cnt, &len);
+      if (cnt * 50 == len) { scale_L(c, w, 0.25); c.l_updates[w] += 1; }
+      else if (cnt * 50 > 4 * len) { scale_L(c, w, 1.7); c.l_updates[w] += 1; }
+    }
+    i++;
+    if (i >= 3000) c.done[w] = 1;
+  }
+  c.loop_i[w] = i;
+}
+
+__global__ void k_pre(const MfitChains c, const MfitRunCfg r) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < c.W) pre_body(c, r, w);
+}
+template <bool FIN, bool FUSE>
+__global__ void k_post(const MfitChains c, MfitRunCfg r) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  post_body<FIN>(c, r, w);
+  if (FUSE) {
+    r.t += 1;
+    pre_body(c, r, w);
+  }
+}
+__global__ void k_finalize(const MfitChains c) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  for (int d = 0; d < c.D; d++)
+    if (c.ds[d].owned) ll_ptr(c, d)[w] = finalize_ll(c, d, w);
+}
+
+// ------------------------------------------------------------------ run set-up (:866-901)
+__global__ void k_init_run(const MfitChains c, const MfitRunCfg r, const double* l_shared) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  const int P = c.P, PP = P * P;
+  c.shutting[w] = 0;
+  c.need_reest[w] = 0;
+  c.steps_run[w] = 0;
+  c.l_updates[w] = 0;
+  c.reset_index[w] = 10000;
+  if (r.mode == MFIT_MODE_ADAPTIVE) {
+    c.loop_i[w] = 1;
+    c.done[w] = (1 >= r.n) ? 1 : 0;
+    c.temperature[w] = r.temperature0;
+    if (l_shared) {
+      for (int e = 0; e < PP; e++) c.L[(size_t)e * c.stride + w] = l_shared[e];
+    } else {
+      for (int e = 0; e < PP; e++) {  // diagonal-covariance of the most likely params :899-900
+        int i = e / P, j = e % P;
+        c.L[(size_t)e * c.stride + w] = (i == j) ? c.best_theta[(size_t)i * c.stride + w] : 0.0;
+      }
+      long long cnt, len;
+      acc_window(c, w, 100, &cnt, &len);
+      if (!(c.length[w] < r.S || acc_lt(cnt, len, 0.1f))) c.need_reest[w] = 1;  // :897-901
+    }
+  } else if (r.mode == MFIT_MODE_MANY) {
+    c.loop_i[w] = 0;
+    c.done[w] = (0 >= r.n) ? 1 : 0;
+    c.temperature[w] = 1.0;
+    for (int e = 0; e < PP; e++) c.L[(size_t)e * c.stride + w] = l_shared[e];
+  } else {
+    c.loop_i[w] = 1;
+    c.done[w] = 0;
+    c.temperature[w] = 1.0;
+    for (int e = 0; e < PP; e++) {  // :959
+      int i = e / P, j = e % P;
+      double v = (i == j) ? c.best_theta[(size_t)i * c.stride + w] : 0.0;
+      c.L[(size_t)e * c.stride + w] = r.sr_scale * v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ get-optimal-mcmc-l-matrix :888-895, one CTA per chain
+__global__ void k_reest(const MfitChains c, const MfitRunCfg r) {
+  const long long w = blockIdx.x;
+  if (w >= c.W || !c.need_reest[w]) return;
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int P = c.P, PP = P * P;
+  double* avg = reinterpret_cast<double*>(sm);
+  double* cov = avg + P;
+  double* Ln = cov + PP;
+  int* fwd = reinterpret_cast<int*>(Ln + PP);
+  __shared__ int m_sh, ok_sh;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const double scale = (2.38 * 2.38) / (double)P;  // (/ (expt 2.38d0 2) num-params)
+
+  if (r.sampling_opt == MFIT_OPT_BEST_VALUE) {  // :895
+    for (int e = tid; e < PP; e += nth) {
+      int i = e / P, j = e % P;
+      double v = (i == j) ? c.best_theta[(size_t)i * c.stride + w] : 0.0;
+      c.L[(size_t)e * c.stride + w] = 1e-5 * v;
+    }
+    if (tid == 0) { c.need_reest[w] = 0; c.l_updates[w] += 1; }
+    return;
+  }
+  const long long mwin = wlen(c, w, r.S);
+  const long long hi = c.rows[w] - 1, lo = c.rows[w] - mwin;
+  if (tid == 0) {  // walker-get :forward-steps :497-502, newest first
+    int m = 0;
+    for (long long j = hi; j >= lo + 1; j--)
+      if (tprob(c, j, w) > tprob(c, j - 1, w)) fwd[m++] = (int)(j - lo);
+    m_sh = m;
+  }
+  __syncthreads();
+  const int m = m_sh;
+  if (m == 1) {  // 0x0 result fails the dimension check :936 -> l-matrix kept
+    if (tid == 0) c.need_reest[w] = 0;
+    return;
+  }
+  if (m == 0) {  // (elt nil 0) -> type-error handler returns l-matrix, scaled in place
+    for (int e = tid; e < PP; e += nth) {
+      double* p = c.L + (size_t)e * c.stride + w;
+      *p = scale * *p;
+    }
+    if (tid == 0) { c.need_reest[w] = 0; c.l_updates[w] += 1; }
+    return;
+  }
+  const int n = m - 1;  // number of differences (older - newer), :263-275
+#define MFIT_DIFF(k, i) (ttheta(c, lo + fwd[(k) + 1], (i), w) - ttheta(c, lo + fwd[(k)], (i), w))
+  for (int i = tid; i < P; i += nth) {  // :626
+    double s = MFIT_DIFF(0, i);
+    for (int k = 1; k < n; k++) s = s + MFIT_DIFF(k, i);
+    avg[i] = s / (double)n;
+  }
+  __syncthreads();
+  for (int e = tid; e < PP; e += nth) {  // :636-643
+    const int i = e / P, j = e % P;
+    const double ai = avg[i], aj = avg[j];
+    double s = 0.0;
+    for (int k = 0; k < n; k++) s = s + ((MFIT_DIFF(k, i) - ai) * (MFIT_DIFF(k, j) - aj)) / (double)n;
+    cov[e] = s;
+  }
+#undef MFIT_DIFF
+  for (int e = tid; e < PP; e += nth) Ln[e] = 0.0;
+  __syncthreads();
+  if (tid == 0) {  // cholesky-decomp :583-598
+    int ok = 1;
+    for (int i = 0; i < P; i++)
+      for (int k = 0; k <= i; k++) {
+        double tmp = 0.0;
+        for (int j = 0; j < k; j++) tmp = tmp + Ln[i * P + j] * Ln[k * P + j];
+        double v;
+        if (i == k) {
+          double d = cov[i * P + k] - tmp;
+          v = sqrt(d > 0.0 ? d : (d != d ? d : 0.0));
+        } else
+          v = (cov[i * P + k] - tmp) / Ln[k * P + k];
+        Ln[i * P + k] = v;
+        if (!isfinite(v)) ok = 0;
+      }
+    ok_sh = ok;
+  }
+  __syncthreads();
+  if (ok_sh) {
+    for (int e = tid; e < PP; e += nth) c.L[(size_t)e * c.stride + w] = scale * Ln[e];
+  } else {  // FPO / DB0 handlers :892-893
+    for (int e = tid; e < PP; e += nth) {
+      double* p = c.L + (size_t)e * c.stride + w;
+      *p = scale * *p;
+    }
+  }
+  if (tid == 0) { c.need_reest[w] = 0; c.l_updates[w] += 1; }
+}
+
+// ------------------------------------------------------------------ walker-create first step / force-take-step
+__global__ void k_first_step(const MfitChains c) {  // :1148-1162; prop_theta = theta0, lld/lpd evaluated
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  const int P = c.P;
+  double ll = 0.0, lp = 0.0;
+  for (int d = 0; d < c.D; d++) { double v = ll_ptr(c, d)[w]; ll = d == 0 ? v : ll + v; }
+  for (int d = 0; d < c.D; d++) { double v = lp_ptr(c, d)[w]; lp = d == 0 ? v : lp + v; }
+  const double p = ll + lp;
+  for (int i = 0; i < P; i++) {
+    double v = c.prop_theta[(size_t)i * c.stride + w];
+    c.cur_theta[(size_t)i * c.stride + w] = v;
+    c.best_theta[(size_t)i * c.stride + w] = v;
+    c.trace_theta[(size_t)i * c.stride + w] = v;
+  }
+  c.cur_prob[w] = p;
+  c.best_prob[w] = p;
+  c.trace_prob[w] = p;
+  c.rows[w] = 1;
+  c.length[w] = 1;
+  c.age[w] = 1;
+  c.done[w] = 0;
+  c.shutting[w] = 0;
+  c.need_reest[w] = 0;
+  c.steps_run[w] = 0;
+  c.l_updates[w] = 0;
+  c.loop_i[w] = 0;
+  c.temperature[w] = 1.0;
+  c.reset_index[w] = 10000;
+}
+__global__ void k_force_step(const MfitChains c) {  // :1124-1129; prop_theta = cur_theta re-evaluated
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  const int P = c.P;
+  double ll = 0.0, lp = 0.0;
+  for (int d = 0; d < c.D; d++) { double v = ll_ptr(c, d)[w]; ll = d == 0 ? v : ll + v; }
+  for (int d = 0; d < c.D; d++) { double v = lp_ptr(c, d)[w]; lp = d == 0 ? v : lp + v; }
+  const double p = ll + lp;
+  c.cur_prob[w] = p;
+  if (p > c.best_prob[w]) {
+    for (int i = 0; i < P; i++) c.best_theta[(size_t)i * c.stride + w] = c.cur_theta[(size_t)i * c.stride + w];
+    c.best_prob[w] = p;
+  }
+  const long long row = c.rows[w];
+  const size_t slot = (size_t)(row % c.cap);
+  for (int i = 0; i < P; i++) c.trace_theta[(slot * P + i) * c.stride + w] = c.cur_theta[(size_t)i * c.stride + w];
+  c.trace_prob[slot * c.stride + w] = p;
+  c.rows[w] = row + 1;
+  c.length[w] += 1;
+  c.age[w] += 1;
+}
+// priors of an arbitrary theta batch (eval_logp, first step): built-in kinds only
+__global__ void k_priors(const MfitChains c, const double* theta) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  for (int d = 0; d < c.D; d++) {
+    const MfitDsDev& s = c.ds[d];
+    if (s.owned && s.prior_kind != 2) lp_ptr(c, d)[w] = builtin_prior(c, s, theta, w);
+  }
+}
+__global__ void k_eval_finalize(const MfitChains c, double* prob, double* ll_out, double* lp_out) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  double ll = 0.0, lp = 0.0;
+  for (int d = 0; d < c.D; d++) {
+    double v = ll_ptr(c, d)[w];
+    if (ll_out) ll_out[(size_t)w * c.D + d] = v;
+    ll = d == 0 ? v : ll + v;
+  }
+  for (int d = 0; d < c.D; d++) {
+    double v = lp_ptr(c, d)[w];
+    if (lp_out) lp_out[(size_t)w * c.D + d] = v;
+    lp = d == 0 ? v : lp + v;
+  }
+  if (prob) prob[w] = ll + lp;
+}
+
+__global__ void k_count_active(const MfitChains c, int* out) {
+  __shared__ int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  int local = 0;
+  for (long long w = threadIdx.x; w < c.W; w += blockDim.x) local += c.done[w] ? 0 : 1;
+  atomicAdd(&s, local);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = s;
+}
+__global__ void k_keep_walks(const MfitChains c, long long keep) {  // :568-569
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < c.W) c.length[w] = keep;
+}
+__global__ void k_stats(const MfitChains c, mfit_chain_stats* out) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  mfit_chain_stats s;
+  s.length = c.length[w];
+  s.age = c.age[w];
+  s.steps_this_run = c.steps_run[w];
+  s.last_prob = c.cur_prob[w];
+  s.best_prob = c.best_prob[w];
+  s.temperature = c.temperature[w];
+  long long cnt, len;
+  acc_window(c, w, 200, &cnt, &len);
+  s.accept_200 = len > 0 ? (double)cnt / (double)len : 0.0;
+  s.shutting_down = c.shutting[w];
+  s.l_updates = c.l_updates[w];
+  out[w] = s;
+}
+// newest-first gather of the trace: theta [W][take][P], prob [W][take]
+__global__ void k_trace_gather(const MfitChains c, long long take, double* theta, double* prob, long long* nvalid) {
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (long long)c.W * take) return;
+  const long long r = id / c.W, w = id % c.W;  // adjacent threads = adjacent chains (coalesced ring reads)
+  const long long m = wlen(c, w, take);
+  if (r == 0 && nvalid) nvalid[w] = m;
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  if (r < m) {
+    const long long row = c.rows[w] - 1 - r;
+    if (theta)
+      for (int i = 0; i < c.P; i++) theta[((size_t)w * take + r) * c.P + i] = ttheta(c, row, i, w);
+    if (prob) prob[(size_t)w * take + r] = tprob(c, row, w);
+  } else {
+    if (theta)
+      for (int i = 0; i < c.P; i++) theta[((size_t)w * take + r) * c.P + i] = nanv;
+    if (prob) prob[(size_t)w * take + r] = nanv;
+  }
+}
+__global__ void k_philox_stream(unsigned long long seed, long long chain_base, long long W, long long first,
+                                long long nsteps, int P, double* z, double* u) {
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= W * nsteps) return;
+  const long long w = id / nsteps, t = id % nsteps;
+  double zz[MFIT_MAX_P];
+  philox_normals(seed, chain_base + w, first + t, P, zz);
+  for (int j = 0; j < P; j++) z[(size_t)id * P + j] = zz[j];
+  u[id] = philox_uniform(seed, chain_base + w, first + t);
+}
+__global__ void k_transpose_in(const double* src, double* dst, long long W, int P, long long stride) {
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= W * P) return;
+  const long long w = id % W;
+  const int i = (int)(id / W);
+  dst[(size_t)i * stride + w] = src[(size_t)w * P + i];
+}
+__global__ void k_transpose_out(const double* src, double* dst, long long W, int P, long long stride) {
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= W * P) return;
+  const long long w = id % W;
+  const int i = (int)(id / W);
+  dst[(size_t)w * P + i] = src[(size_t)i * stride + w];
+}
+__global__ void k_l_read(const MfitChains c, double* out) {
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int PP = c.P * c.P;
+  if (id >= (long long)c.W * PP) return;
+  const long long w = id % c.W;
+  const int e = (int)(id / c.W);
+  out[(size_t)w * PP + e] = c.L[(size_t)e * c.stride + w];
+}
+__global__ void k_flush(double* buf, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) buf[i] = (double)i;
+}
+
+inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+// ------------------------------------------------------------------ launchers
+void mfit_launch_init_run(const MfitChains& c, const MfitRunCfg& r, const double* l_shared, cudaStream_t st) {
+  k_init_run<<<blocks_for(c.W, 128), 128, 0, st>>>(c, r, l_shared);
+}
+void mfit_launch_reest(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st) {
+  const int P = c.P;
+  size_t smem = sizeof(double) * (P + 2 * (size_t)P * P) + sizeof(int) * (size_t)(r.S + 1);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(k_reest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  k_reest<<<(unsigned)c.W, 128, smem, st>>>(c, r);
+}
+void mfit_launch_pre(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st) {
+  k_pre<<<blocks_for(c.W, 128), 128, 0, st>>>(c, r);
+}
+void mfit_launch_post(const MfitChains& c, const MfitRunCfg& r, bool fuse_pre, cudaStream_t st) {
+  const bool fin = c.xch == nullptr;
+  const unsigned g = blocks_for(c.W, 128);
+  if (fin) {
+    if (fuse_pre) k_post<true, true><<<g, 128, 0, st>>>(c, r);
+    else k_post<true, false><<<g, 128, 0, st>>>(c, r);
+  } else {
+    if (fuse_pre) k_post<false, true><<<g, 128, 0, st>>>(c, r);
+    else k_post<false, false><<<g, 128, 0, st>>>(c, r);
+  }
+}
+void mfit_launch_finalize(const MfitChains& c, cudaStream_t st) {
+  k_finalize<<<blocks_for(c.W, 128), 128, 0, st>>>(c);
+}
+void mfit_launch_first_step(const MfitChains& c, cudaStream_t st) {
+  k_first_step<<<blocks_for(c.W, 128), 128, 0, st>>>(c);
+}
+void mfit_launch_force_step(const MfitChains& c, cudaStream_t st) {
+  k_force_step<<<blocks_for(c.W, 128), 128, 0, st>>>(c);
+}
+void mfit_launch_priors(const MfitChains& c, const double* theta, cudaStream_t st) {
+  k_priors<<<blocks_for(c.W, 128), 128, 0, st>>>(c, theta);
+}
+void mfit_launch_count_active(const MfitChains& c, int* out, cudaStream_t st) {
+  k_count_active<<<1, 1024, 0, st>>>(c, out);
+}
+void mfit_launch_keep_walks(const MfitChains& c, long long keep, cudaStream_t st) {
+  k_keep_walks<<<blocks_for(c.W, 128), 128, 0, st>>>(c, keep);
+}
+void mfit_launch_stats(const MfitChains& c, void* stats_dev, cudaStream_t st) {
+  k_stats<<<blocks_for(c.W, 128), 128, 0, st>>>(c, (mfit_chain_stats*)stats_dev);
+}
+void mfit_launch_trace_gather(const MfitChains& c, long long take, double* theta, double* prob, long long* nvalid,
+                              cudaStream_t st) {
+  k_trace_gather<<<blocks_for((long long)c.W * take, 256), 256, 0, st>>>(c, take, theta, prob, nvalid);
+}
+void mfit_launch_philox_stream(unsigned long long seed, long long chain_base, long long W, long long first,
+                               long long nsteps, int P, double* z, double* u, cudaStream_t st) {
+  k_philox_stream<<<blocks_for(W * nsteps, 128), 128, 0, st>>>(seed, chain_base, W, first, nsteps, P, z, u);
+}
+void mfit_launch_transpose_in(const double* src, double* dst, long long W, int P, long long stride, cudaStream_t st) {
+  k_transpose_in<<<blocks_for(W * P, 256), 256, 0, st>>>(src, dst, W, P, stride);
+}
+void mfit_launch_transpose_out(const double* src, double* dst, long long W, int P, long long stride, cudaStream_t st) {
+  k_transpose_out<<<blocks_for(W * P, 256), 256, 0, st>>>(src, dst, W, P, stride);
+}
+void mfit_launch_eval_finalize(const MfitChains& c, double* prob, double* ll, double* lp, cudaStream_t st) {
+  k_eval_finalize<<<blocks_for(c.W, 128), 128, 0, st>>>(c, prob, ll, lp);
+}
+void mfit_launch_l_read(const MfitChains& c, double* out, cudaStream_t st) {
+  k_l_read<<<blocks_for((long long)c.W * c.P * c.P, 256), 256, 0, st>>>(c, out);
+}
+void mfit_launch_flush(void* buf, size_t bytes, cudaStream_t st) {
+  k_flush<<<148 * 8, 256, 0, st>>>((double*)buf, bytes / 8);
+}

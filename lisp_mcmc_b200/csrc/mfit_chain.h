@@ -1,0 +1,98 @@
+// mfit_chain.h -- device-side chain state shared by chain_kernels.cu and api.cu
+#ifndef MFIT_CHAIN_H
+#define MFIT_CHAIN_H
+#include <stdint.h>
+
+#define MFIT_MAX_P 96
+#define MFIT_MODE_ADAPTIVE 0      /* walker-adaptive-steps-full :862-942 */
+#define MFIT_MODE_MANY 1          /* walker-many-steps :849-853 */
+#define MFIT_MODE_SAMPLE_REGION 2 /* walker-sample-region :949-969 */
+
+// one dataset as the chain kernels see it
+struct MfitDsDev {
+  const double* partial;  // [n_seg][stride] per-segment sums written by the eval kernel
+  int n_seg;
+  int ll_kind;
+  double cst;             // theta-independent part of the log-likelihood
+  int owned;              // this rank evaluates the dataset
+  int prior_kind;         // 0 flat, 1 bounds, 2 user kernel (lp written by an NVRTC kernel)
+  int nb;
+  const int* b_idx;
+  const double* b_lo;
+  const double* b_hi;
+  int xrank, xslot;       // exchange location when datasets are sharded over ranks
+};
+
+// struct-of-arrays chain state; every per-chain array has `stride` (W rounded up to 128) entries
+struct MfitChains {
+  int W, P, D;
+  long long stride;
+  double* cur_theta;    // [P][stride]   (walker-last-step params)
+  double* cur_prob;     // [stride]
+  double* prop_theta;   // [P][stride]   proposal under evaluation
+  double* best_theta;   // [P][stride]   (walker-most-likely-step)
+  double* best_prob;
+  double* L;            // [P*P][stride] per-chain l-matrix, row-major entries
+  long long* loop_i;    // reference loop variable i
+  unsigned char* shutting;
+  unsigned char* done;  // also the eval kernel's skip mask
+  unsigned char* need_reest;
+  double* temperature;
+  long long* length;    // walker-length
+  long long* age;       // walker-age
+  long long* rows;      // rows ever pushed to the trace ring (slot = row % cap)
+  long long* reset_index;
+  long long* steps_run;
+  int* l_updates;
+  double* trace_theta;  // [cap][P][stride]
+  double* trace_prob;   // [cap][stride]
+  long long cap;
+  double* lld;          // [D][stride] per-dataset log-likelihood of the proposal
+  double* lpd;          // [D][stride] per-dataset log-prior of the proposal
+  const double* xch;    // exchange buffer [R][slots][2][stride] when datasets are sharded (else null)
+  int xslots;
+  const MfitDsDev* ds;  // [D] device array
+};
+
+struct MfitRunCfg {
+  int mode;
+  long long n, Tn, S, tail, mwl;
+  int auto_mode, sampling_opt, greedy;
+  double temperature0;
+  const double* temps;  // [Tn]
+  const double* z;      // [W][nstream][P] or null
+  const double* u;      // [W][nstream] or null
+  long long nstream;
+  long long t;          // take-step index inside this run
+  unsigned long long seed;
+  long long chain_base;
+  double sr_scale;      // sample-region initial scale
+};
+
+#ifdef __CUDACC__
+void mfit_launch_init_run(const MfitChains& c, const MfitRunCfg& r, const double* l_shared, cudaStream_t st);
+void mfit_launch_reest(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st);
+void mfit_launch_pre(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st);
+void mfit_launch_post(const MfitChains& c, const MfitRunCfg& r, bool fuse_pre, cudaStream_t st);
+void mfit_launch_finalize(const MfitChains& c, cudaStream_t st);
+void mfit_launch_first_step(const MfitChains& c, cudaStream_t st);
+void mfit_launch_force_step(const MfitChains& c, cudaStream_t st);
+void mfit_launch_priors(const MfitChains& c, const double* theta, cudaStream_t st);
+void mfit_launch_count_active(const MfitChains& c, int* out, cudaStream_t st);
+void mfit_launch_keep_walks(const MfitChains& c, long long keep, cudaStream_t st);
+void mfit_launch_stats(const MfitChains& c, void* stats_dev, cudaStream_t st);
+void mfit_launch_trace_gather(const MfitChains& c, long long take, double* theta, double* prob, long long* nvalid,
+                              cudaStream_t st);
+void mfit_launch_philox_stream(unsigned long long seed, long long chain_base, long long W, long long first,
+                               long long nsteps, int P, double* z, double* u, cudaStream_t st);
+void mfit_launch_transpose_in(const double* src_rowmajor, double* dst, long long W, int P, long long stride,
+                              cudaStream_t st);
+void mfit_launch_transpose_out(const double* src, double* dst_rowmajor, long long W, int P, long long stride,
+                               cudaStream_t st);
+void mfit_launch_eval_finalize(const MfitChains& c, double* prob, double* ll, double* lp, cudaStream_t st);
+void mfit_launch_l_read(const MfitChains& c, double* out, cudaStream_t st);
+int mfit_measure_fp64_dev(cudaStream_t st, double* dfma_flops, double* cost_exp, double* cost_log, double* cost_sin,
+                          double* cost_div);
+void mfit_launch_flush(void* buf, size_t bytes, cudaStream_t st);
+#endif
+#endif

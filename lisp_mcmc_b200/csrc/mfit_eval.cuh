@@ -1,0 +1,218 @@
+// mfit_eval.cuh -- the batched log-likelihood kernel (sm_100a).
+//
+// This is the GPU form of hot loop #2 of the reference: log-liklihood-normal
+// (mcmc-fitting.lisp:393-400), log-liklihood-normal-cutoff (:419-427) and the
+// create-log-liklihood-function closure (:402-417) over log-poisson (:382-383), i.e.
+//     ll_d(theta) = sum_i  density(y_i, f(x_i; theta), sigma_i)
+// evaluated for W parameter vectors (chains) at once against shared (x, y, sigma).
+//
+// Work decomposition: one CTA = one chain-block (MFIT_CB chains, one chain per thread) x one
+// segment of the data (tiles_per_seg tiles of MFIT_TILE points).  The data tile is moved
+// global -> shared by the TMA engine (cp.async.bulk, 1-D) through an MFIT_STAGES-deep
+// mbarrier ring and is read back as warp-uniform (broadcast) 128-bit LDS; theta lives in
+// registers, one chain per lane, so the FP64 pipe sees no cross-lane traffic at all and
+// each fetched point is reused by 128 chains.  Per-chain sums are sequential inside a
+// segment (two interleaved accumulators, fixed order) and the per-segment partials are
+// added in segment order by the chain kernel, so results do not depend on grid size, SM
+// count or GPU count.
+//
+// The file is freestanding (no #include) because the very same text is embedded in
+// libmfit_cuda.so and handed to NVRTC together with a model struct generated from a user
+// s-expression (csrc/lower.cpp).
+#ifndef MFIT_EVAL_CUH
+#define MFIT_EVAL_CUH
+
+#define MFIT_TILE 512    /* points per shared-memory stage */
+#define MFIT_STAGES 3    /* TMA ring depth */
+#define MFIT_CB 128      /* chains per CTA = threads per CTA */
+#define MFIT_MAXK 16     /* parameters a built-in family may gather */
+
+#define MFITK_NORMAL 0
+#define MFITK_CUTOFF 1
+#define MFITK_POISSON 2
+
+struct MfitEvalArgs {
+  const double* x;      /* [n_pad] */
+  const double* y;      /* [n_pad] */
+  const double* w;      /* [n_pad] 1/sigma_i            (normal, cutoff) */
+  const double* c;      /* [n_pad] -ln(2pi)/2 - ln sigma_i  (cutoff only) */
+  long long n;          /* valid points */
+  int tiles_per_seg;
+  int n_seg;
+  int n_cb;             /* chain blocks */
+  int W;                /* chains */
+  long long stride;     /* chain stride of theta / partial (W rounded up to MFIT_CB) */
+  const double* theta;  /* [P][stride] parameter vectors to evaluate */
+  const unsigned char* skip; /* [stride] 1 = chain finished, nothing to do (may be null) */
+  double* partial;      /* [n_seg][stride] per-segment sums */
+  int idx[MFIT_MAXK];   /* built-in families: family slot -> shared parameter index */
+  int degree;
+};
+
+// ---------------------------------------------------------------- PTX helpers (mbarrier + TMA bulk copy)
+__device__ __forceinline__ unsigned mfit_smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mfit_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mfit_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mfit_fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mfit_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mfit_smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mfit_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mfit_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mfit_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MFIT_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MFIT_DONE;\n"
+      "bra MFIT_WAIT;\n"
+      "MFIT_DONE:\n"
+      "}\n" ::"r"(mfit_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA: global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void mfit_tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   mfit_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(mfit_smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------- per-point terms
+template <int LL>
+struct MfitTerm;
+
+// log-normal :372-377 with the theta-independent part hoisted: the kernel accumulates
+// sum r^2, r = (y - f)/sigma; the chain kernel forms  C_d - sum/2.
+template <>
+struct MfitTerm<MFITK_NORMAL> {
+  static constexpr int NARR = 3;
+  __device__ __forceinline__ static double add(double acc, double f, double y, double w, double) {
+    double r = (y - f) * w;
+    return fma(r, r, acc);
+  }
+};
+// log-liklihood-normal-cutoff :426: (max -5000d0 (log-normal y f sigma)) cannot be hoisted
+template <>
+struct MfitTerm<MFITK_CUTOFF> {
+  static constexpr int NARR = 4;
+  __device__ __forceinline__ static double add(double acc, double f, double y, double w, double c) {
+    double r = (y - f) * w;
+    double t = fma(-0.5 * r, r, c);
+    t = (t > -5000.0) ? t : ((t != t) ? t : -5000.0);
+    return acc + t;
+  }
+};
+// log-poisson :382-383 with sum_i log k_i! hoisted:  k ln(lambda) - lambda
+template <>
+struct MfitTerm<MFITK_POISSON> {
+  static constexpr int NARR = 2;
+  __device__ __forceinline__ static double add(double acc, double f, double y, double, double) {
+    return acc + fma(y, log(f), -f);
+  }
+};
+
+// ---------------------------------------------------------------- the kernel body
+template <class Model, int LL>
+__device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
+  constexpr int NARR = MfitTerm<LL>::NARR;
+  constexpr unsigned STAGE_BYTES = NARR * MFIT_TILE * 8u;
+  extern __shared__ __align__(128) unsigned char mfit_smem[];
+  double* buf = reinterpret_cast<double*>(mfit_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(mfit_smem + MFIT_STAGES * STAGE_BYTES);
+  unsigned long long* empty = full + MFIT_STAGES;
+
+  const int tid = threadIdx.x;
+  const int cb = blockIdx.x % a.n_cb;   // chain-block fastest: CTAs launched together share a data segment in L2
+  const int seg = blockIdx.x / a.n_cb;
+  const long long chain = (long long)cb * MFIT_CB + tid;
+  const bool valid = chain < a.W;
+  const long long cl = valid ? chain : (long long)a.W - 1;
+  const bool live = valid && !(a.skip != nullptr && a.skip[cl] != 0);
+  if (__syncthreads_or(live ? 1 : 0) == 0) return;  // every chain of this block has finished
+
+  const long long n_tiles = (a.n + MFIT_TILE - 1) / MFIT_TILE;
+  const long long t0 = (long long)seg * a.tiles_per_seg;
+  long long t1 = t0 + a.tiles_per_seg;
+  if (t1 > n_tiles) t1 = n_tiles;
+  const int nt = (int)(t1 - t0);
+
+  if (tid == 0) {
+    for (int s = 0; s < MFIT_STAGES; s++) {
+      mfit_mbar_init(&full[s], 1);
+      mfit_mbar_init(&empty[s], MFIT_CB / 32);
+    }
+    mfit_fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int k) {  // tile t0+k -> stage k % STAGES   (thread 0 only)
+    const int s = k % MFIT_STAGES;
+    const long long off = (t0 + k) * (long long)MFIT_TILE;
+    double* dst = buf + (size_t)s * NARR * MFIT_TILE;
+    mfit_mbar_expect_tx(&full[s], STAGE_BYTES);
+    mfit_tma_load_1d(dst, a.x + off, MFIT_TILE * 8u, &full[s]);
+    mfit_tma_load_1d(dst + MFIT_TILE, a.y + off, MFIT_TILE * 8u, &full[s]);
+    if (NARR > 2) mfit_tma_load_1d(dst + 2 * MFIT_TILE, a.w + off, MFIT_TILE * 8u, &full[s]);
+    if (NARR > 3) mfit_tma_load_1d(dst + 3 * MFIT_TILE, a.c + off, MFIT_TILE * 8u, &full[s]);
+  };
+  if (tid == 0) {
+    const int pre = nt < MFIT_STAGES ? nt : MFIT_STAGES;
+    for (int k = 0; k < pre; k++) issue(k);
+  }
+
+  // theta -> registers while the first tiles are in flight
+  Model m;
+  m.load(a, cl);
+
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int k = 0; k < nt; k++) {
+    const int s = k % MFIT_STAGES;
+    const unsigned ph = (unsigned)(k / MFIT_STAGES) & 1u;
+    // refill the stage freed one tile ago (gives the other warps a tile of slack)
+    if (tid == 0 && k >= 1 && k - 1 + MFIT_STAGES < nt) {
+      const int sp = (k - 1) % MFIT_STAGES;
+      mfit_mbar_wait(&empty[sp], (unsigned)((k - 1) / MFIT_STAGES) & 1u);
+      issue(k - 1 + MFIT_STAGES);
+    }
+    mfit_mbar_wait(&full[s], ph);
+
+    const double* xs = buf + (size_t)s * NARR * MFIT_TILE;
+    const double* ys = xs + MFIT_TILE;
+    const double* ws = xs + (NARR > 2 ? 2 : 0) * MFIT_TILE;
+    const double* cs = xs + (NARR > 3 ? 3 : 0) * MFIT_TILE;
+    long long rem = a.n - (t0 + k) * (long long)MFIT_TILE;
+    const int cnt = rem < MFIT_TILE ? (int)rem : MFIT_TILE;
+    const int pairs = cnt >> 1;
+    const double2* x2 = reinterpret_cast<const double2*>(xs);
+    const double2* y2 = reinterpret_cast<const double2*>(ys);
+    const double2* w2 = reinterpret_cast<const double2*>(ws);
+    const double2* c2 = reinterpret_cast<const double2*>(cs);
+#pragma unroll 2
+    for (int i = 0; i < pairs; i++) {
+      const double2 xv = x2[i], yv = y2[i], wv = w2[i], cv = c2[i];
+      const double f0 = m.eval(xv.x);
+      const double f1 = m.eval(xv.y);
+      acc0 = MfitTerm<LL>::add(acc0, f0, yv.x, wv.x, cv.x);
+      acc1 = MfitTerm<LL>::add(acc1, f1, yv.y, wv.y, cv.y);
+    }
+    if (cnt & 1) {
+      const int i = cnt - 1;
+      acc0 = MfitTerm<LL>::add(acc0, m.eval(xs[i]), ys[i], ws[i], cs[i]);
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mfit_mbar_arrive(&empty[s]);
+  }
+  if (live) a.partial[(size_t)seg * a.stride + chain] = acc0 + acc1;
+}
+
+#endif  // MFIT_EVAL_CUH
