@@ -117,6 +117,13 @@ int mfit_prior_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* 
 int mfit_lower_sexpr(const char* lambda_text, const char* const* key_names, int n_keys, int kind,
                      char* out, int out_len, char* err, int err_len);
 
+/* lower + NVRTC-compile (sm_100a cubin) without touching a GPU; returns the cubin size or a negative status */
+int mfit_compile_sexpr(const char* lambda_text, const char* const* key_names, int n_keys, int kind,
+                       char* err, int err_len);
+/* points per reduction segment = 512 * tiles (0 = default: a function of the point count only, so that
+ * log-likelihood bits do not depend on chain count or GPU count) */
+int mfit_set_segment_tiles(mfit_ctx* ctx, int tiles_per_segment);
+
 /* ---- walker-make-step :1067-1070 over a batch of parameter vectors ------------------------------
  * theta: W x P row-major.  ll, lp: W x D row-major per-dataset terms (either may be NULL);
  * prob: W totals = (sum_d ll) + (sum_d lp) in dataset order. */
@@ -178,13 +185,14 @@ int mfit_nccl_allgather_f64(mfit_ctx* ctx, const double* local_host, int64_t cou
  * DFMA-equivalent cost of the FP64 transcendentals used by the model families. */
 int mfit_measure_fp64(mfit_ctx* ctx, double* dfma_flops, double* cost_exp, double* cost_log, double* cost_sin,
                       double* cost_div);
+/* record CUDA events around the likelihood kernels of subsequent runs (off by default) */
+int mfit_set_timing(mfit_ctx* ctx, int on);
 /* device time of the eval kernels of the last run / eval call, seconds (CUDA events on the ctx stream),
  * and how many eval launches it covered */
 int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches);
 /* write > L2 bytes on the ctx stream (bench hygiene between timed steps) */
 int mfit_flush_l2(mfit_ctx* ctx);
-/* run exactly `n_steps` more MH steps with the adaptive driver state left by mfit_run_adaptive
- * re-armed for n = n_steps (used by bench.py to time step by step) */
+/* the cudaStream_t the context enqueues on */
 int mfit_stream_handle(mfit_ctx* ctx, void** stream_out);
 
 #ifdef __cplusplus

@@ -1,0 +1,1177 @@
+// api.cu -- host side of libmfit_cuda.so: the C ABI of include/mfit_cuda.h.
+//
+// What the reference does with Lisp lists inside one SBCL image (walker-create :1132-1163,
+// walker-make-step :1067-1070, walker-adaptive-steps-full :862-942) is here a context that owns
+// flat FP64 device arrays and enqueues kernels on one CUDA stream:
+//
+//   per MH step:   eval kernel per dataset (mfit_eval.cuh)      -- hot loop #2, >99 % of the time
+//                  [ncclAllGather of ll/lp when datasets are sharded over ranks]
+//                  k_post  (accept, push, adapt; + next proposal)   \  hot loop #1,
+//                  k_reest (forward-step covariance + Cholesky)     /  chain_kernels.cu
+//
+// The host never looks at chain state inside a run except for a lagging, non-blocking poll of
+// "how many chains are still active" (auto-stop) and the stop flag (mfit-walker-estop :860).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "mfit_chain.h"
+#include "mfit_eval.cuh"
+#include "mfit_internal.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct Dataset {
+  long long n = -1, n_pad = 0;
+  double *x = nullptr, *y = nullptr, *w = nullptr, *c = nullptr;
+  double cst_normal = 0.0, cst_poisson = 0.0;
+  bool poisson_ok = false;
+  int family = -1, degree = 0;
+  int idx[MFIT_MAXK];
+  int ll_kind = MFIT_LL_NORMAL;
+  int prior_kind = 0;
+  int nb = 0;
+  int* b_idx = nullptr;
+  double *b_lo = nullptr, *b_hi = nullptr;
+  cudaLibrary_t lib_model = nullptr, lib_prior = nullptr;
+  cudaKernel_t k_user[3] = {nullptr, nullptr, nullptr};
+  cudaKernel_t k_prior = nullptr;
+  int owner = 0, xslot = 0;
+  bool owned = true;
+  int tiles_per_seg = 1, n_seg = 0;
+};
+
+// buffers needed to evaluate W parameter vectors against every dataset
+struct Workspace {
+  long long W = 0, stride = 0;
+  double *lld = nullptr, *lpd = nullptr;
+  std::vector<double*> partial;
+  MfitDsDev* ds_dev = nullptr;
+  double* xch = nullptr;
+  int xslots = 0;
+};
+
+struct EventPair { cudaEvent_t a, b; };
+
+}  // namespace
+
+struct mfit_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  long long launches = 0;
+  int D = 0, P = 0;
+  std::vector<Dataset> ds;
+  int seg_tiles_override = 0;
+
+  // chains
+  bool have_chains = false;
+  MfitChains ch;
+  Workspace ws;
+  std::vector<void*> chain_allocs;
+  unsigned long long seed = 0;
+  long long chain_base = 0;
+  bool cap_fixed = false;
+  long long rows_upper = 0;  // no chain has pushed more trace rows than this
+  double* temps_dev = nullptr;
+  long long temps_len = 0;
+  double *z_dev = nullptr, *u_dev = nullptr;
+  size_t z_bytes = 0, u_bytes = 0;
+  double* lshared_dev = nullptr;
+  int* active_dev = nullptr;
+  int* active_host = nullptr;  // pinned [4]
+  cudaEvent_t poll_ev[4];
+  bool poll_ev_made = false;
+
+  // multi-GPU
+  void* comm = nullptr;
+  int rank = 0, n_ranks = 1;
+  bool sharded = false;
+  int xslots = 0;
+
+  std::atomic<int> stop{0};
+
+  // measurement
+  bool timing = false;
+  std::vector<EventPair> ev;
+  size_t ev_used = 0;
+  double eval_seconds = 0.0;
+  long long eval_launches = 0;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+};
+
+namespace {
+
+int fail(mfit_ctx* c, int code, const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess)                                                                                    \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? MFIT_ERR_NOMEM : MFIT_ERR_CUDA, "%s: %s", #call,     \
+                  cudaGetErrorString(e_));                                                                    \
+  } while (0)
+
+long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+void free_dev(void* p) { if (p) cudaFree(p); }
+
+void dataset_free_data(Dataset& d) {
+  free_dev(d.x); free_dev(d.y); free_dev(d.w); free_dev(d.c);
+  d.x = d.y = d.w = d.c = nullptr;
+  d.n = -1;
+}
+void dataset_free_prior(Dataset& d) {
+  free_dev(d.b_idx); free_dev(d.b_lo); free_dev(d.b_hi);
+  d.b_idx = nullptr; d.b_lo = d.b_hi = nullptr;
+  d.nb = 0;
+  if (d.lib_prior) { cudaLibraryUnload(d.lib_prior); d.lib_prior = nullptr; d.k_prior = nullptr; }
+}
+void dataset_free_model(Dataset& d) {
+  if (d.lib_model) { cudaLibraryUnload(d.lib_model); d.lib_model = nullptr; }
+  d.k_user[0] = d.k_user[1] = d.k_user[2] = nullptr;
+}
+
+void workspace_free(Workspace& w) {
+  free_dev(w.lld); free_dev(w.lpd); free_dev(w.ds_dev); free_dev(w.xch);
+  for (double* p : w.partial) free_dev(p);
+  w = Workspace();
+}
+
+void chains_free(mfit_ctx* ctx) {
+  for (void* p : ctx->chain_allocs) free_dev(p);
+  ctx->chain_allocs.clear();
+  workspace_free(ctx->ws);
+  ctx->have_chains = false;
+}
+
+// log-factorial :379-380 -- (reduce (lambda (x y) (+ x (log y))) (up-to n)): single-float accumulation
+double log_factorial_ref(long long n, std::vector<float>& memo) {
+  if (n < (long long)memo.size()) return (double)memo[(size_t)n];
+  if (memo.empty()) memo.push_back(0.0f);
+  for (long long j = (long long)memo.size(); j <= n; j++) memo.push_back(memo[(size_t)j - 1] + (float)std::log((double)j));
+  return (double)memo[(size_t)n];
+}
+
+// segment geometry is a function of the point count alone, so that partial sums -- and therefore
+// every log-likelihood bit -- do not depend on chain count, SM count or the number of GPUs
+void plan_segments(mfit_ctx* ctx, Dataset& d) {
+  const long long n_tiles = (d.n + MFIT_TILE - 1) / MFIT_TILE;
+  long long tps = ctx->seg_tiles_override > 0 ? ctx->seg_tiles_override : (n_tiles + 255) / 256;
+  if (tps < 1) tps = 1;
+  d.tiles_per_seg = (int)tps;
+  d.n_seg = (int)((n_tiles + tps - 1) / tps);
+}
+
+int workspace_make(mfit_ctx* ctx, Workspace& w, long long W) {
+  workspace_free(w);
+  w.W = W;
+  w.stride = round_up(W > 0 ? W : 1, MFIT_CB);
+  const int D = ctx->D;
+  CU(cudaMalloc(&w.lld, sizeof(double) * D * w.stride));
+  CU(cudaMalloc(&w.lpd, sizeof(double) * D * w.stride));
+  CU(cudaMemsetAsync(w.lld, 0, sizeof(double) * D * w.stride, ctx->stream));
+  CU(cudaMemsetAsync(w.lpd, 0, sizeof(double) * D * w.stride, ctx->stream));
+  w.partial.assign(D, nullptr);
+  if (ctx->sharded) {
+    w.xslots = ctx->xslots;
+    const size_t cnt = (size_t)ctx->n_ranks * w.xslots * 2 * w.stride;
+    CU(cudaMalloc(&w.xch, sizeof(double) * cnt));
+    CU(cudaMemsetAsync(w.xch, 0, sizeof(double) * cnt, ctx->stream));
+  }
+  std::vector<MfitDsDev> host(D);
+  for (int d = 0; d < D; d++) {
+    Dataset& s = ctx->ds[d];
+    MfitDsDev& h = host[d];
+    memset(&h, 0, sizeof h);
+    h.owned = s.owned ? 1 : 0;
+    h.ll_kind = s.ll_kind;
+    h.prior_kind = s.prior_kind;
+    h.nb = s.nb;
+    h.b_idx = s.b_idx;
+    h.b_lo = s.b_lo;
+    h.b_hi = s.b_hi;
+    h.xrank = s.owner;
+    h.xslot = s.xslot;
+    if (s.owned) {
+      plan_segments(ctx, s);
+      h.n_seg = s.n_seg;
+      h.cst = s.ll_kind == MFIT_LL_NORMAL ? s.cst_normal : s.ll_kind == MFIT_LL_POISSON ? s.cst_poisson : 0.0;
+      if (s.n_seg > 0) CU(cudaMalloc(&w.partial[d], sizeof(double) * (size_t)s.n_seg * w.stride));
+      h.partial = w.partial[d];
+    }
+  }
+  CU(cudaMalloc(&w.ds_dev, sizeof(MfitDsDev) * (D > 0 ? D : 1)));
+  CU(cudaMemcpyAsync(w.ds_dev, host.data(), sizeof(MfitDsDev) * D, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // `host` dies with this frame
+  return 0;
+}
+
+int check_problem_ready(mfit_ctx* ctx) {
+  if (ctx->D <= 0) return fail(ctx, MFIT_ERR_STATE, "mfit_problem_define has not been called");
+  for (int d = 0; d < ctx->D; d++) {
+    Dataset& s = ctx->ds[d];
+    if (!s.owned) continue;
+    if (s.n < 0) return fail(ctx, MFIT_ERR_STATE, "dataset %d has no data", d);
+    if (s.family < 0) return fail(ctx, MFIT_ERR_STATE, "dataset %d has no model (:function)", d);
+    if (s.ll_kind == MFIT_LL_POISSON && !s.poisson_ok)
+      return fail(ctx, MFIT_ERR_ARG, "dataset %d: log-poisson needs non-negative integer-valued y (log-factorial :379-380)", d);
+  }
+  return 0;
+}
+
+int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const double* theta, const unsigned char* skip) {
+  if (s.n == 0 || s.n_seg == 0) return 0;
+  MfitEvalArgs a;
+  memset(&a, 0, sizeof a);
+  a.x = s.x; a.y = s.y; a.w = s.w; a.c = s.c;
+  a.n = s.n;
+  a.tiles_per_seg = s.tiles_per_seg;
+  a.n_seg = s.n_seg;
+  a.n_cb = (int)(w.stride / MFIT_CB);
+  a.W = (int)w.W;
+  a.stride = w.stride;
+  a.theta = theta;
+  a.skip = skip;
+  a.partial = w.partial[d];
+  for (int k = 0; k < MFIT_MAXK; k++) a.idx[k] = s.idx[k];
+  a.degree = s.degree;
+  const void* fn = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user[s.ll_kind]
+                                              : mfit_builtin_eval_kernel(s.family, s.degree, s.ll_kind);
+  if (!fn) return fail(ctx, MFIT_ERR_STATE, "no kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
+  const size_t smem = mfit_eval_smem_bytes(s.ll_kind);
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {&a};
+  const unsigned grid = (unsigned)((long long)a.n_cb * a.n_seg);
+  CU(cudaLaunchKernel(fn, dim3(grid), dim3(MFIT_CB), args, smem, ctx->stream));
+  ctx->launches++;
+  return 0;
+}
+
+// all owned datasets: per-segment partial sums (+ user priors).  Built-in priors are written by the chain kernels.
+int eval_all(mfit_ctx* ctx, Workspace& w, const MfitChains& view, const double* theta, const unsigned char* skip) {
+  const bool timed = ctx->timing && ctx->ev_used < ctx->ev.size();
+  if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_used].a, ctx->stream));
+  int n_eval = 0;
+  for (int d = 0; d < ctx->D; d++) {
+    Dataset& s = ctx->ds[d];
+    if (!s.owned) continue;
+    int rc = launch_eval(ctx, s, w, d, theta, skip);
+    if (rc) return rc;
+    if (s.n > 0) n_eval++;
+  }
+  if (timed) {
+    CU(cudaEventRecord(ctx->ev[ctx->ev_used].b, ctx->stream));
+    ctx->ev_used++;
+    ctx->eval_launches += n_eval;
+  }
+  for (int d = 0; d < ctx->D; d++) {
+    Dataset& s = ctx->ds[d];
+    if (!s.owned || s.prior_kind != 2) continue;
+    double* out = view.xch ? const_cast<double*>(view.xch) + ((size_t)(s.owner * view.xslots + s.xslot) * 2 + 1) * view.stride
+                           : view.lpd + (size_t)d * view.stride;
+    long long stride = w.stride, W = w.W;
+    void* args[] = {(void*)&theta, &stride, &W, (void*)&skip, &out};
+    CU(cudaLaunchKernel((const void*)s.k_prior, dim3((unsigned)((W + 127) / 128)), dim3(128), args, 0, ctx->stream));
+    ctx->launches++;
+  }
+  return 0;
+}
+
+int exchange(mfit_ctx* ctx, Workspace& w) {
+  if (!ctx->sharded) return 0;
+  const size_t per_rank = sizeof(double) * (size_t)w.xslots * 2 * w.stride;
+  std::string e;
+  int rc = mfit_nccl_allgather_bytes(ctx->comm, (const char*)w.xch + per_rank * ctx->rank, w.xch, per_rank, ctx->stream, e);
+  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  return 0;
+}
+
+MfitChains view_of(mfit_ctx* ctx, Workspace& w) {
+  MfitChains v;
+  memset(&v, 0, sizeof v);
+  v.W = (int)w.W;
+  v.P = ctx->P;
+  v.D = ctx->D;
+  v.stride = w.stride;
+  v.lld = w.lld;
+  v.lpd = w.lpd;
+  v.xch = w.xch;
+  v.xslots = w.xslots;
+  v.ds = w.ds_dev;
+  return v;
+}
+
+void collect_timing(mfit_ctx* ctx) {
+  for (size_t i = 0; i < ctx->ev_used; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[i].a, ctx->ev[i].b) == cudaSuccess) ctx->eval_seconds += ms * 1e-3;
+  }
+  ctx->ev_used = 0;
+}
+
+template <class T>
+int chain_alloc(mfit_ctx* ctx, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  CU(cudaMalloc(&p, sizeof(T) * (count ? count : 1)));
+  if (zero) CU(cudaMemsetAsync(p, 0, sizeof(T) * (count ? count : 1), ctx->stream));
+  ctx->chain_allocs.push_back(p);
+  *out = (T*)p;
+  return 0;
+}
+
+long long min_trace_cap(int P) {
+  long long S = 10LL * (P > 50 ? P : 50);
+  return (S > 1000 ? S : 1000) + 1;
+}
+
+int grow_trace(mfit_ctx* ctx, long long need_rows) {
+  MfitChains& c = ctx->ch;
+  if (need_rows <= c.cap || ctx->cap_fixed) return 0;
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t row_bytes = sizeof(double) * (size_t)(c.P + 1) * c.stride;
+  long long afford = (long long)((free_b * 0.8) / row_bytes);
+  long long new_cap = need_rows < afford ? need_rows : afford;
+  if (new_cap <= c.cap) return 0;  // keep the ring: the oldest rows are overwritten, like :max-walker-length
+  double *nt = nullptr, *np = nullptr;
+  CU(cudaMalloc(&nt, sizeof(double) * (size_t)new_cap * c.P * c.stride));
+  CU(cudaMalloc(&np, sizeof(double) * (size_t)new_cap * c.stride));
+  mfit_launch_trace_regrow(c, nt, np, new_cap, ctx->stream);
+  ctx->launches++;
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->chain_allocs) {
+    if (p == c.trace_theta) { cudaFree(p); p = nt; }
+    else if (p == c.trace_prob) { cudaFree(p); p = np; }
+  }
+  c.trace_theta = nt;
+  c.trace_prob = np;
+  c.cap = new_cap;
+  return 0;
+}
+
+int upload_opt(mfit_ctx* ctx, const double* host, size_t count, double** dev, size_t* dev_bytes) {
+  const size_t bytes = sizeof(double) * count;
+  if (*dev_bytes < bytes) {
+    free_dev(*dev);
+    *dev = nullptr;
+    *dev_bytes = 0;
+    CU(cudaMalloc(dev, bytes));
+    *dev_bytes = bytes;
+  }
+  CU(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+// the step loop shared by the three run modes
+int run_loop(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long long max_steps, long long* steps_launched) {
+  MfitChains& c = ctx->ch;
+  int rc = check_problem_ready(ctx);
+  if (rc) return rc;
+  ctx->stop.store(0);
+  ctx->eval_seconds = 0.0;
+  ctx->eval_launches = 0;
+  ctx->ev_used = 0;
+  if (max_steps < 0) max_steps = 0;
+  rc = grow_trace(ctx, ctx->rows_upper + max_steps + 1);
+  if (rc) return rc;
+  const double* l_dev = nullptr;
+  if (l_shared_host) {
+    if (!ctx->lshared_dev) CU(cudaMalloc(&ctx->lshared_dev, sizeof(double) * MFIT_MAX_P * MFIT_MAX_P));
+    CU(cudaMemcpyAsync(ctx->lshared_dev, l_shared_host, sizeof(double) * c.P * c.P, cudaMemcpyHostToDevice, ctx->stream));
+    l_dev = ctx->lshared_dev;
+  }
+  r.seed = ctx->seed;
+  r.chain_base = ctx->chain_base;
+  r.t = 0;
+  mfit_launch_init_run(c, r, l_dev, ctx->stream);
+  mfit_launch_pre(c, r, ctx->stream);    // proposals of chains that keep their l-matrix
+  mfit_launch_reest(c, r, ctx->stream);  // chains resuming a long walk re-estimate first (:897-901)
+  ctx->launches += 3;
+  if (!ctx->poll_ev_made) {
+    for (auto& e : ctx->poll_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaMallocHost(&ctx->active_host, sizeof(int) * 4));
+    CU(cudaMalloc(&ctx->active_dev, sizeof(int) * 4));
+    ctx->poll_ev_made = true;
+  }
+  const long long poll_every = 64;
+  bool poll_pending[4] = {false, false, false, false};
+  int poll_slot = 0;
+  long long t = 0;
+  bool all_done = false;
+  for (; t < max_steps && !all_done; t++) {
+    if (ctx->stop.load()) break;  // mfit-walker-estop, :904
+    r.t = t;
+    rc = eval_all(ctx, ctx->ws, c, c.prop_theta, c.done);
+    if (rc) return rc;
+    if (ctx->sharded) {
+      mfit_launch_finalize(c, ctx->stream);
+      ctx->launches++;
+      rc = exchange(ctx, ctx->ws);
+      if (rc) return rc;
+    }
+    mfit_launch_post(c, r, true, ctx->stream);  // accept/push/adapt of step t, proposal of step t+1
+    MfitRunCfg rn = r;
+    rn.t = t + 1;
+    mfit_launch_reest(c, rn, ctx->stream);
+    ctx->launches += 2;
+    if ((t + 1) % poll_every == 0) {
+      // lagging poll: look at the answer of an earlier query if it has arrived; never block
+      for (int s = 0; s < 4; s++)
+        if (poll_pending[s] && cudaEventQuery(ctx->poll_ev[s]) == cudaSuccess) {
+          poll_pending[s] = false;
+          if (ctx->active_host[s] == 0) all_done = true;
+        }
+      if (!poll_pending[poll_slot]) {
+        mfit_launch_count_active(c, ctx->active_dev + poll_slot, ctx->stream);
+        ctx->launches++;
+        CU(cudaMemcpyAsync(ctx->active_host + poll_slot, ctx->active_dev + poll_slot, sizeof(int),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaEventRecord(ctx->poll_ev[poll_slot], ctx->stream));
+        poll_pending[poll_slot] = true;
+        poll_slot = (poll_slot + 1) & 3;
+      }
+    }
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  collect_timing(ctx);
+  ctx->rows_upper += t;
+  if (steps_launched) *steps_launched = t;
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+int mfit_abi_version(void) { return MFIT_ABI_VERSION; }
+
+int mfit_ctx_create(int device, void* stream, mfit_ctx** out) {
+  if (!out) return fail(nullptr, MFIT_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, MFIT_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= n) return fail(nullptr, MFIT_ERR_ARG, "device %d out of range (have %d)", device, n);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, MFIT_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10)
+    return fail(nullptr, MFIT_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                prop.minor);
+  mfit_ctx* c = new mfit_ctx();
+  c->device = device;
+  if (stream) c->stream = (cudaStream_t)stream;
+  else {
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(nullptr, MFIT_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    c->own_stream = true;
+  }
+  *out = c;
+  return 0;
+}
+
+void mfit_ctx_destroy(mfit_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  chains_free(ctx);
+  for (auto& d : ctx->ds) { dataset_free_data(d); dataset_free_prior(d); dataset_free_model(d); }
+  free_dev(ctx->temps_dev); free_dev(ctx->z_dev); free_dev(ctx->u_dev); free_dev(ctx->lshared_dev);
+  free_dev(ctx->active_dev); free_dev(ctx->flush_buf);
+  if (ctx->active_host) cudaFreeHost(ctx->active_host);
+  if (ctx->poll_ev_made) for (auto& e : ctx->poll_ev) cudaEventDestroy(e);
+  for (auto& p : ctx->ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  if (ctx->comm) mfit_nccl_comm_destroy(ctx->comm);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* mfit_last_error(mfit_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int mfit_synchronize(mfit_ctx* ctx) {
+  if (!ctx) return MFIT_ERR_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int64_t mfit_launch_count(mfit_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int mfit_stream_handle(mfit_ctx* ctx, void** stream_out) {
+  if (!ctx || !stream_out) return MFIT_ERR_ARG;
+  *stream_out = (void*)ctx->stream;
+  return 0;
+}
+
+int mfit_problem_define(mfit_ctx* ctx, int n_datasets, int n_params) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (n_datasets < 1 || n_params < 1 || n_params > MFIT_MAX_P)
+    return fail(ctx, MFIT_ERR_ARG, "need 1 <= datasets and 1 <= params <= %d", MFIT_MAX_P);
+  CU(cudaSetDevice(ctx->device));
+  chains_free(ctx);
+  for (auto& d : ctx->ds) { dataset_free_data(d); dataset_free_prior(d); dataset_free_model(d); }
+  ctx->ds.assign(n_datasets, Dataset());
+  for (auto& d : ctx->ds) memset(d.idx, 0, sizeof d.idx);
+  ctx->D = n_datasets;
+  ctx->P = n_params;
+  ctx->sharded = false;
+  return 0;
+}
+
+#define NEED_DS(d)                                                                       \
+  if (!ctx) return MFIT_ERR_ARG;                                                          \
+  if (ctx->D <= 0) return fail(ctx, MFIT_ERR_STATE, "mfit_problem_define has not been called"); \
+  if ((d) < 0 || (d) >= ctx->D) return fail(ctx, MFIT_ERR_ARG, "dataset index %d out of range", (d))
+
+int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, const double* sigma, int64_t n) {
+  NEED_DS(d);
+  if (n < 0 || (n > 0 && (!x || !y))) return fail(ctx, MFIT_ERR_ARG, "dataset %d: bad x/y/n", d);
+  CU(cudaSetDevice(ctx->device));
+  Dataset& s = ctx->ds[d];
+  dataset_free_data(s);
+  s.n = n;
+  s.n_pad = round_up(n > 0 ? n : 1, MFIT_TILE);
+  std::vector<double> w((size_t)s.n_pad, 0.0), cc((size_t)s.n_pad, 0.0), xx((size_t)s.n_pad, 0.0), yy((size_t)s.n_pad, 0.0);
+  const double a = -0.5 * std::log(2.0 * 3.141592653589793);  // (* -1/2 (log (* 2 pi))) :377
+  double cst = 0.0;
+  bool pois_ok = true;
+  std::vector<float> memo;
+  double pcst = 0.0;
+  for (long long i = 0; i < n; i++) {
+    const double sg = sigma ? sigma[i] : 1.0;  // (if data-error data-error 1) :1144
+    xx[i] = x[i];
+    yy[i] = y[i];
+    w[i] = 1.0 / sg;
+    const double ci = a + (-1.0 * std::log(sg));
+    cc[i] = ci;
+    cst = i == 0 ? ci : cst + ci;
+    const double k = y[i];
+    if (pois_ok) {
+      if (!(k >= 0.0) || k != std::floor(k) || k > 5e6) pois_ok = false;
+      else {
+        const double lf = log_factorial_ref((long long)k, memo);
+        pcst = i == 0 ? -lf : pcst - lf;
+      }
+    }
+  }
+  s.cst_normal = cst;
+  s.cst_poisson = pcst;
+  s.poisson_ok = pois_ok;
+  const size_t bytes = sizeof(double) * (size_t)s.n_pad;
+  CU(cudaMalloc(&s.x, bytes)); CU(cudaMalloc(&s.y, bytes)); CU(cudaMalloc(&s.w, bytes)); CU(cudaMalloc(&s.c, bytes));
+  CU(cudaMemcpyAsync(s.x, xx.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.y, yy.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.w, w.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.c, cc.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->have_chains) chains_free(ctx);  // segment geometry changed: chains must be re-initialised
+  return 0;
+}
+
+int mfit_model_builtin(mfit_ctx* ctx, int d, int family, int degree, const int32_t* param_index, int n_idx) {
+  NEED_DS(d);
+  const int need = mfit_family_nparams(family, degree);
+  if (need < 0 || !mfit_builtin_eval_kernel(family, degree, 0))
+    return fail(ctx, MFIT_ERR_ARG, "unknown family %d / degree %d", family, degree);
+  if (n_idx != need || need > MFIT_MAXK) return fail(ctx, MFIT_ERR_ARG, "family %d takes %d parameters, got %d", family, need, n_idx);
+  Dataset& s = ctx->ds[d];
+  for (int k = 0; k < n_idx; k++) {
+    if (param_index[k] < 0 || param_index[k] >= ctx->P) return fail(ctx, MFIT_ERR_ARG, "param_index[%d]=%d out of range", k, param_index[k]);
+    s.idx[k] = param_index[k];
+  }
+  dataset_free_model(s);
+  s.family = family;
+  s.degree = degree;
+  return 0;
+}
+
+static int load_cubin(mfit_ctx* ctx, const std::vector<char>& cubin, cudaLibrary_t* lib) {
+  CU(cudaLibraryLoadData(lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  return 0;
+}
+
+int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* const* key_names, int n_keys) {
+  NEED_DS(d);
+  if (!lambda_text || n_keys != ctx->P) return fail(ctx, MFIT_ERR_ARG, "need the lambda text and exactly P=%d key names", ctx->P);
+  CU(cudaSetDevice(ctx->device));
+  std::string code, e;
+  int rc = mfit_lower_to_string(lambda_text, key_names, n_keys, 0, code, e);
+  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  std::vector<char> cubin;
+  rc = mfit_nvrtc_compile(mfit_user_model_source(code), cubin, e);
+  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  Dataset& s = ctx->ds[d];
+  dataset_free_model(s);
+  rc = load_cubin(ctx, cubin, &s.lib_model);
+  if (rc) return rc;
+  CU(cudaLibraryGetKernel(&s.k_user[0], s.lib_model, "mfit_user_eval_normal"));
+  CU(cudaLibraryGetKernel(&s.k_user[1], s.lib_model, "mfit_user_eval_cutoff"));
+  CU(cudaLibraryGetKernel(&s.k_user[2], s.lib_model, "mfit_user_eval_poisson"));
+  s.family = MFIT_FAM_SEXPR;
+  s.degree = 0;
+  return 0;
+}
+
+int mfit_likelihood_set(mfit_ctx* ctx, int d, int kind) {
+  NEED_DS(d);
+  if (kind < 0 || kind > 2) return fail(ctx, MFIT_ERR_ARG, "unknown likelihood kind %d", kind);
+  if (ctx->ds[d].ll_kind != kind && ctx->have_chains) chains_free(ctx);
+  ctx->ds[d].ll_kind = kind;
+  return 0;
+}
+
+int mfit_prior_flat(mfit_ctx* ctx, int d) {
+  NEED_DS(d);
+  if (ctx->have_chains) chains_free(ctx);
+  dataset_free_prior(ctx->ds[d]);
+  ctx->ds[d].prior_kind = 0;
+  return 0;
+}
+
+int mfit_prior_bounds(mfit_ctx* ctx, int d, int n, const int32_t* idx, const double* lo, const double* hi) {
+  NEED_DS(d);
+  if (n < 0 || (n > 0 && (!idx || !lo || !hi))) return fail(ctx, MFIT_ERR_ARG, "bad bounds arrays");
+  for (int k = 0; k < n; k++)
+    if (idx[k] >= ctx->P) return fail(ctx, MFIT_ERR_ARG, "bounds idx[%d]=%d out of range", k, idx[k]);
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->have_chains) chains_free(ctx);
+  Dataset& s = ctx->ds[d];
+  dataset_free_prior(s);
+  s.prior_kind = 1;
+  s.nb = n;
+  if (n > 0) {
+    CU(cudaMalloc(&s.b_idx, sizeof(int) * n));
+    CU(cudaMalloc(&s.b_lo, sizeof(double) * n));
+    CU(cudaMalloc(&s.b_hi, sizeof(double) * n));
+    CU(cudaMemcpy(s.b_idx, idx, sizeof(int) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s.b_lo, lo, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(s.b_hi, hi, sizeof(double) * n, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int mfit_prior_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* const* key_names, int n_keys) {
+  NEED_DS(d);
+  if (!lambda_text || n_keys != ctx->P) return fail(ctx, MFIT_ERR_ARG, "need the lambda text and exactly P=%d key names", ctx->P);
+  CU(cudaSetDevice(ctx->device));
+  std::string code, e;
+  int rc = mfit_lower_to_string(lambda_text, key_names, n_keys, 1, code, e);
+  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  std::vector<char> cubin;
+  rc = mfit_nvrtc_compile(mfit_user_prior_source(code), cubin, e);
+  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  if (ctx->have_chains) chains_free(ctx);
+  Dataset& s = ctx->ds[d];
+  dataset_free_prior(s);
+  rc = load_cubin(ctx, cubin, &s.lib_prior);
+  if (rc) return rc;
+  CU(cudaLibraryGetKernel(&s.k_prior, s.lib_prior, "mfit_user_prior_kernel"));
+  s.prior_kind = 2;
+  return 0;
+}
+
+int mfit_set_segment_tiles(mfit_ctx* ctx, int tiles_per_segment) {
+  if (!ctx || tiles_per_segment < 0) return MFIT_ERR_ARG;
+  if (ctx->have_chains) chains_free(ctx);
+  ctx->seg_tiles_override = tiles_per_segment;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ walker-make-step on a batch
+int mfit_eval_logp(mfit_ctx* ctx, const double* theta, int64_t W, double* prob, double* ll, double* lp) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (W < 0 || (W > 0 && !theta)) return fail(ctx, MFIT_ERR_ARG, "bad theta/W");
+  int rc = check_problem_ready(ctx);
+  if (rc) return rc;
+  if (W == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  Workspace w;
+  rc = workspace_make(ctx, w, W);
+  if (rc) { workspace_free(w); return rc; }
+  const int P = ctx->P, D = ctx->D;
+  double *th_rm = nullptr, *th = nullptr, *o_prob = nullptr, *o_ll = nullptr, *o_lp = nullptr;
+  auto cleanup = [&]() { free_dev(th_rm); free_dev(th); free_dev(o_prob); free_dev(o_ll); free_dev(o_lp); workspace_free(w); };
+#define CUX(call)                                                                          \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) { cleanup(); return fail(ctx, MFIT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } \
+  } while (0)
+  CUX(cudaMalloc(&th_rm, sizeof(double) * W * P));
+  CUX(cudaMalloc(&th, sizeof(double) * P * w.stride));
+  CUX(cudaMemsetAsync(th, 0, sizeof(double) * P * w.stride, ctx->stream));
+  CUX(cudaMalloc(&o_prob, sizeof(double) * W));
+  CUX(cudaMalloc(&o_ll, sizeof(double) * W * D));
+  CUX(cudaMalloc(&o_lp, sizeof(double) * W * D));
+  CUX(cudaMemcpyAsync(th_rm, theta, sizeof(double) * W * P, cudaMemcpyHostToDevice, ctx->stream));
+  mfit_launch_transpose_in(th_rm, th, W, P, w.stride, ctx->stream);
+  MfitChains v = view_of(ctx, w);
+  mfit_launch_priors(v, th, ctx->stream);
+  ctx->launches += 2;
+  ctx->eval_seconds = 0.0;
+  ctx->eval_launches = 0;
+  ctx->ev_used = 0;
+  rc = eval_all(ctx, w, v, th, nullptr);
+  if (rc) { cleanup(); return rc; }
+  mfit_launch_finalize(v, ctx->stream);
+  ctx->launches++;
+  rc = exchange(ctx, w);
+  if (rc) { cleanup(); return rc; }
+  mfit_launch_eval_finalize(v, o_prob, o_ll, o_lp, ctx->stream);
+  ctx->launches++;
+  if (prob) CUX(cudaMemcpyAsync(prob, o_prob, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ll) CUX(cudaMemcpyAsync(ll, o_ll, sizeof(double) * W * D, cudaMemcpyDeviceToHost, ctx->stream));
+  if (lp) CUX(cudaMemcpyAsync(lp, o_lp, sizeof(double) * W * D, cudaMemcpyDeviceToHost, ctx->stream));
+  CUX(cudaStreamSynchronize(ctx->stream));
+  CUX(cudaGetLastError());
+  collect_timing(ctx);
+  cleanup();
+#undef CUX
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ chains
+int mfit_chains_init(mfit_ctx* ctx, const double* theta0, int64_t W, uint64_t seed, int64_t chain_id_base,
+                     int64_t trace_capacity) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (W < 1 || !theta0) return fail(ctx, MFIT_ERR_ARG, "need W >= 1 and theta0");
+  if (W > 2000000000LL) return fail(ctx, MFIT_ERR_ARG, "W too large");
+  int rc = check_problem_ready(ctx);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  chains_free(ctx);
+  rc = workspace_make(ctx, ctx->ws, W);
+  if (rc) return rc;
+  const int P = ctx->P, D = ctx->D;
+  MfitChains& c = ctx->ch;
+  c = view_of(ctx, ctx->ws);
+  const size_t st = (size_t)c.stride;
+#define CA(field, count) if ((rc = chain_alloc(ctx, &c.field, (count))) != 0) { chains_free(ctx); return rc; }
+  CA(cur_theta, P * st) CA(cur_prob, st) CA(prop_theta, P * st) CA(best_theta, P * st) CA(best_prob, st)
+  CA(L, (size_t)P * P * st) CA(loop_i, st) CA(shutting, st) CA(done, st) CA(need_reest, st) CA(temperature, st)
+  CA(length, st) CA(age, st) CA(rows, st) CA(reset_index, st) CA(steps_run, st) CA(l_updates, st)
+  (void)D;
+  long long cap = trace_capacity;
+  ctx->cap_fixed = trace_capacity > 0;
+  const long long mincap = min_trace_cap(P);
+  if (cap < mincap) cap = mincap;
+  c.cap = cap;
+  if ((rc = chain_alloc(ctx, &c.trace_theta, (size_t)cap * P * st, false)) != 0) { chains_free(ctx); return rc; }
+  if ((rc = chain_alloc(ctx, &c.trace_prob, (size_t)cap * st, false)) != 0) { chains_free(ctx); return rc; }
+#undef CA
+  ctx->seed = seed;
+  ctx->chain_base = chain_id_base;
+  ctx->have_chains = true;
+  // first step, walker-create :1148-1162
+  double* th_rm = nullptr;
+  CU(cudaMalloc(&th_rm, sizeof(double) * W * P));
+  CU(cudaMemcpyAsync(th_rm, theta0, sizeof(double) * W * P, cudaMemcpyHostToDevice, ctx->stream));
+  mfit_launch_transpose_in(th_rm, c.prop_theta, W, P, c.stride, ctx->stream);
+  mfit_launch_priors(c, c.prop_theta, ctx->stream);
+  ctx->launches += 2;
+  rc = eval_all(ctx, ctx->ws, c, c.prop_theta, nullptr);
+  if (rc) { cudaFree(th_rm); return rc; }
+  mfit_launch_finalize(c, ctx->stream);
+  ctx->launches++;
+  rc = exchange(ctx, ctx->ws);
+  if (rc) { cudaFree(th_rm); return rc; }
+  mfit_launch_first_step(c, ctx->stream);
+  ctx->rows_upper = 1;
+  ctx->launches++;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(th_rm);
+  if (e != cudaSuccess) return fail(ctx, MFIT_ERR_CUDA, "chains_init: %s", cudaGetErrorString(e));
+  CU(cudaGetLastError());
+  collect_timing(ctx);
+  return 0;
+}
+
+static int make_cfg(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, MfitRunCfg& r) {
+  memset(&r, 0, sizeof r);
+  const int P = ctx->P;
+  r.mode = MFIT_MODE_ADAPTIVE;
+  r.n = cfg->n;                                   // (floor n) :866 -- the ABI takes an integer
+  r.S = 10LL * (P > 50 ? P : 50);                 // steps-to-settle :873
+  r.Tn = r.n > 10 * r.S ? r.n : 10 * r.S;         // temp-steps :875
+  r.tail = r.S > 2000 ? r.S : 2000;               // (max 2000 steps-to-settle) :906
+  r.mwl = cfg->max_walker_length > 0 ? cfg->max_walker_length / 2 : 0;  // :868
+  r.auto_mode = cfg->auto_mode;
+  r.sampling_opt = cfg->sampling_optimization;
+  r.greedy = cfg->greedy;
+  r.temperature0 = cfg->temperature;
+  // temps :878  (max 1 (* (cos (* x pi (+ 1 (* 2 (floor temp-steps 5000))) (/ (* 2 temp-steps)))) temperature))
+  std::vector<double> temps((size_t)r.Tn);
+  const double pi = 3.141592653589793;
+  const double k = (double)(1 + 2 * (r.Tn / 5000));
+  const double inv = 1.0 / (double)(2 * r.Tn);
+  for (long long x = 0; x < r.Tn; x++) {
+    const double a = (((double)x * pi) * k) * inv;
+    const double t = std::cos(a) * cfg->temperature;
+    temps[(size_t)x] = t > 1.0 ? t : 1.0;
+  }
+  if (ctx->temps_len < r.Tn) {
+    free_dev(ctx->temps_dev);
+    ctx->temps_dev = nullptr;
+    ctx->temps_len = 0;
+    CU(cudaMalloc(&ctx->temps_dev, sizeof(double) * (size_t)r.Tn));
+    ctx->temps_len = r.Tn;
+  }
+  CU(cudaMemcpyAsync(ctx->temps_dev, temps.data(), sizeof(double) * (size_t)r.Tn, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  r.temps = ctx->temps_dev;
+  return 0;
+}
+
+static int attach_streams(mfit_ctx* ctx, MfitRunCfg& r, const double* z, const double* u, int64_t nstream,
+                          long long need, bool need_u) {
+  r.z = nullptr;
+  r.u = nullptr;
+  r.nstream = nstream;
+  if (!z && !u) return 0;
+  if (!z) return fail(ctx, MFIT_ERR_ARG, "u without z");
+  if (nstream < need) return fail(ctx, MFIT_ERR_STREAM, "injected stream holds %lld steps, the run may take %lld", (long long)nstream, need);
+  const size_t W = (size_t)ctx->ch.W;
+  int rc = upload_opt(ctx, z, W * nstream * ctx->P, &ctx->z_dev, &ctx->z_bytes);
+  if (rc) return rc;
+  r.z = ctx->z_dev;
+  if (u) {
+    rc = upload_opt(ctx, u, W * nstream, &ctx->u_dev, &ctx->u_bytes);
+    if (rc) return rc;
+    r.u = ctx->u_dev;
+  } else if (need_u)
+    return fail(ctx, MFIT_ERR_ARG, "z injected without u");
+  return 0;
+}
+
+int mfit_run_adaptive(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, const double* l_matrix, const double* z,
+                      const double* u, int64_t nstream, int64_t* steps_launched) {
+  if (!ctx || !cfg) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (cfg->n < 0) return fail(ctx, MFIT_ERR_ARG, "n < 0");
+  CU(cudaSetDevice(ctx->device));
+  MfitRunCfg r;
+  int rc = make_cfg(ctx, cfg, r);
+  if (rc) return rc;
+  const long long max_steps = r.n > 1 ? r.n - 1 : 0;
+  rc = attach_streams(ctx, r, z, u, nstream, max_steps, !cfg->greedy);
+  if (rc) return rc;
+  long long launched = 0;
+  rc = run_loop(ctx, r, l_matrix, max_steps, &launched);
+  if (steps_launched) *steps_launched = launched;
+  return rc;
+}
+
+int mfit_run_many_steps(mfit_ctx* ctx, int64_t n, const double* l_matrix, const double* z, const double* u,
+                        int64_t nstream) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (!l_matrix) return fail(ctx, MFIT_ERR_ARG, "walker-many-steps needs an l-matrix here (the :median-params default is post-processing)");
+  if (n < 0) return fail(ctx, MFIT_ERR_ARG, "n < 0");
+  CU(cudaSetDevice(ctx->device));
+  MfitRunCfg r;
+  memset(&r, 0, sizeof r);
+  r.mode = MFIT_MODE_MANY;
+  r.n = n;
+  r.S = 10LL * (ctx->P > 50 ? ctx->P : 50);
+  r.temperature0 = 1.0;
+  int rc = attach_streams(ctx, r, z, u, nstream, n, true);
+  if (rc) return rc;
+  return run_loop(ctx, r, l_matrix, n, nullptr);
+}
+
+int mfit_run_sample_region(mfit_ctx* ctx, double initial_scale, const double* z, int64_t nstream) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  CU(cudaSetDevice(ctx->device));
+  MfitRunCfg r;
+  memset(&r, 0, sizeof r);
+  r.mode = MFIT_MODE_SAMPLE_REGION;
+  r.n = 3000;
+  r.S = 10LL * (ctx->P > 50 ? ctx->P : 50);
+  r.greedy = 1;
+  r.temperature0 = 1.0;
+  r.sr_scale = initial_scale;
+  int rc = attach_streams(ctx, r, z, nullptr, nstream, 2999, false);
+  if (rc) return rc;
+  return run_loop(ctx, r, nullptr, 2999, nullptr);
+}
+
+int mfit_force_take_step(mfit_ctx* ctx) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  CU(cudaSetDevice(ctx->device));
+  MfitChains& c = ctx->ch;
+  int rc = grow_trace(ctx, ctx->rows_upper + 2);
+  if (rc) return rc;
+  ctx->rows_upper += 1;
+  mfit_launch_priors(c, c.cur_theta, ctx->stream);
+  ctx->launches++;
+  rc = eval_all(ctx, ctx->ws, c, c.cur_theta, nullptr);
+  if (rc) return rc;
+  mfit_launch_finalize(c, ctx->stream);
+  ctx->launches++;
+  rc = exchange(ctx, ctx->ws);
+  if (rc) return rc;
+  mfit_launch_force_step(c, ctx->stream);
+  ctx->launches++;
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  collect_timing(ctx);
+  return 0;
+}
+
+int mfit_request_stop(mfit_ctx* ctx) {
+  if (!ctx) return MFIT_ERR_ARG;
+  ctx->stop.store(1);
+  return 0;
+}
+
+int mfit_trace_read(mfit_ctx* ctx, int64_t take, double* theta, double* prob, int64_t* n_valid) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (take < 1) return fail(ctx, MFIT_ERR_ARG, "take < 1");
+  CU(cudaSetDevice(ctx->device));
+  MfitChains& c = ctx->ch;
+  const size_t W = (size_t)c.W;
+  double *dt = nullptr, *dp = nullptr;
+  long long* dn = nullptr;
+  int rc = 0;
+  cudaError_t e = cudaSuccess;
+  if (theta) e = cudaMalloc(&dt, sizeof(double) * W * take * c.P);
+  if (e == cudaSuccess && prob) e = cudaMalloc(&dp, sizeof(double) * W * take);
+  if (e == cudaSuccess && n_valid) e = cudaMalloc(&dn, sizeof(long long) * W);
+  if (e == cudaSuccess) {
+    mfit_launch_trace_gather(c, take, dt, dp, dn, ctx->stream);
+    ctx->launches++;
+    if (theta) e = cudaMemcpyAsync(theta, dt, sizeof(double) * W * take * c.P, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && prob) e = cudaMemcpyAsync(prob, dp, sizeof(double) * W * take, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && n_valid) e = cudaMemcpyAsync(n_valid, dn, sizeof(long long) * W, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (e != cudaSuccess) rc = fail(ctx, e == cudaErrorMemoryAllocation ? MFIT_ERR_NOMEM : MFIT_ERR_CUDA, "trace_read: %s", cudaGetErrorString(e));
+  free_dev(dt); free_dev(dp); free_dev(dn);
+  return rc;
+}
+
+int mfit_stats_read(mfit_ctx* ctx, mfit_chain_stats* stats) {
+  if (!ctx || !stats) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  CU(cudaSetDevice(ctx->device));
+  MfitChains& c = ctx->ch;
+  mfit_chain_stats* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(mfit_chain_stats) * c.W));
+  mfit_launch_stats(c, d, ctx->stream);
+  ctx->launches++;
+  cudaError_t e = cudaMemcpyAsync(stats, d, sizeof(mfit_chain_stats) * c.W, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, MFIT_ERR_CUDA, "stats_read: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int read_soa(mfit_ctx* ctx, const double* src_theta, const double* src_prob, double* theta, double* prob) {
+  MfitChains& c = ctx->ch;
+  if (theta) {
+    double* tmp = nullptr;
+    CU(cudaMalloc(&tmp, sizeof(double) * (size_t)c.W * c.P));
+    mfit_launch_transpose_out(src_theta, tmp, c.W, c.P, c.stride, ctx->stream);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(theta, tmp, sizeof(double) * (size_t)c.W * c.P, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(ctx, MFIT_ERR_CUDA, "read: %s", cudaGetErrorString(e));
+  }
+  if (prob) {
+    CU(cudaMemcpyAsync(prob, src_prob, sizeof(double) * (size_t)c.W, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+int mfit_best_read(mfit_ctx* ctx, double* theta, double* prob) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  CU(cudaSetDevice(ctx->device));
+  return read_soa(ctx, ctx->ch.best_theta, ctx->ch.best_prob, theta, prob);
+}
+int mfit_last_read(mfit_ctx* ctx, double* theta, double* prob) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  CU(cudaSetDevice(ctx->device));
+  return read_soa(ctx, ctx->ch.cur_theta, ctx->ch.cur_prob, theta, prob);
+}
+
+int mfit_l_matrix_read(mfit_ctx* ctx, double* l) {
+  if (!ctx || !l) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  CU(cudaSetDevice(ctx->device));
+  MfitChains& c = ctx->ch;
+  const size_t cnt = (size_t)c.W * c.P * c.P;
+  double* tmp = nullptr;
+  CU(cudaMalloc(&tmp, sizeof(double) * cnt));
+  mfit_launch_l_read(c, tmp, ctx->stream);
+  ctx->launches++;
+  cudaError_t e = cudaMemcpyAsync(l, tmp, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(ctx, MFIT_ERR_CUDA, "l_matrix_read: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int mfit_keep_walks(mfit_ctx* ctx, int64_t keep) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (keep < 1) return fail(ctx, MFIT_ERR_ARG, "keep < 1");
+  CU(cudaSetDevice(ctx->device));
+  mfit_launch_keep_walks(ctx->ch, keep, ctx->stream);
+  ctx->launches++;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int mfit_philox_stream(mfit_ctx* ctx, uint64_t seed, int64_t chain_id_base, int64_t W, int64_t first_step,
+                       int64_t nsteps, int P, double* z, double* u) {
+  if (!ctx || !z || !u || W < 1 || nsteps < 1 || P < 1 || P > MFIT_MAX_P) return MFIT_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  double *dz = nullptr, *du = nullptr;
+  CU(cudaMalloc(&dz, sizeof(double) * W * nsteps * P));
+  cudaError_t e = cudaMalloc(&du, sizeof(double) * W * nsteps);
+  if (e == cudaSuccess) {
+    mfit_launch_philox_stream(seed, chain_id_base, W, first_step, nsteps, P, dz, du, ctx->stream);
+    ctx->launches++;
+    e = cudaMemcpyAsync(z, dz, sizeof(double) * W * nsteps * P, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(u, du, sizeof(double) * W * nsteps, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  free_dev(dz); free_dev(du);
+  if (e != cudaSuccess) return fail(ctx, MFIT_ERR_CUDA, "philox_stream: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ multi-GPU
+int mfit_nccl_unique_id(void* id_out) {
+  if (!id_out) return MFIT_ERR_ARG;
+  std::string e;
+  int rc = mfit_nccl_get_unique_id(id_out, e);
+  if (rc) return fail(nullptr, rc, "%s", e.c_str());
+  return 0;
+}
+
+int mfit_nccl_attach(mfit_ctx* ctx, const void* unique_id, int rank, int n_ranks) {
+  if (!ctx || !unique_id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return MFIT_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->comm) { mfit_nccl_comm_destroy(ctx->comm); ctx->comm = nullptr; }
+  std::string e;
+  int rc = mfit_nccl_comm_init(&ctx->comm, n_ranks, unique_id, rank, e);
+  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  ctx->rank = rank;
+  ctx->n_ranks = n_ranks;
+  return 0;
+}
+
+int mfit_dataset_owners(mfit_ctx* ctx, const int32_t* owner) {
+  if (!ctx || !owner) return MFIT_ERR_ARG;
+  if (ctx->D <= 0) return fail(ctx, MFIT_ERR_STATE, "mfit_problem_define has not been called");
+  if (!ctx->comm) return fail(ctx, MFIT_ERR_STATE, "mfit_nccl_attach has not been called");
+  std::vector<int> per_rank(ctx->n_ranks, 0);
+  for (int d = 0; d < ctx->D; d++) {
+    if (owner[d] < 0 || owner[d] >= ctx->n_ranks) return fail(ctx, MFIT_ERR_ARG, "owner[%d]=%d out of range", d, owner[d]);
+    ctx->ds[d].owner = owner[d];
+    ctx->ds[d].xslot = per_rank[owner[d]]++;
+    ctx->ds[d].owned = owner[d] == ctx->rank;
+  }
+  int slots = 1;
+  for (int v : per_rank) slots = v > slots ? v : slots;
+  ctx->xslots = slots;
+  ctx->sharded = true;
+  if (ctx->have_chains) chains_free(ctx);
+  return 0;
+}
+
+int mfit_nccl_allgather_f64(mfit_ctx* ctx, const double* local_host, int64_t count, double* out_host) {
+  if (!ctx || !local_host || !out_host || count < 0) return MFIT_ERR_ARG;
+  if (!ctx->comm) return fail(ctx, MFIT_ERR_STATE, "mfit_nccl_attach has not been called");
+  if (count == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  double* buf = nullptr;
+  const size_t per = sizeof(double) * (size_t)count;
+  CU(cudaMalloc(&buf, per * ctx->n_ranks));
+  int rc = 0;
+  cudaError_t e = cudaMemcpyAsync((char*)buf + per * ctx->rank, local_host, per, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    std::string er;
+    rc = mfit_nccl_allgather_bytes(ctx->comm, (char*)buf + per * ctx->rank, buf, per, ctx->stream, er);
+    if (rc) fail(ctx, rc, "%s", er.c_str());
+  }
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(out_host, buf, per * ctx->n_ranks, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(buf);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, MFIT_ERR_CUDA, "allgather: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ measurement
+int mfit_measure_fp64(mfit_ctx* ctx, double* dfma_flops, double* cost_exp, double* cost_log, double* cost_sin,
+                      double* cost_div) {
+  if (!ctx) return MFIT_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (mfit_measure_fp64_dev(ctx->stream, dfma_flops, cost_exp, cost_log, cost_sin, cost_div) != 0)
+    return fail(ctx, MFIT_ERR_CUDA, "fp64 micro-benchmark failed: %s", cudaGetErrorString(cudaGetLastError()));
+  ctx->launches += 5 * 4;
+  return 0;
+}
+
+int mfit_set_timing(mfit_ctx* ctx, int on) {
+  if (!ctx) return MFIT_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  ctx->timing = on != 0;
+  if (ctx->timing && ctx->ev.empty()) {
+    ctx->ev.resize(4096);
+    for (auto& p : ctx->ev) { CU(cudaEventCreate(&p.a)); CU(cudaEventCreate(&p.b)); }
+  }
+  return 0;
+}
+
+int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (seconds) *seconds = ctx->eval_seconds;
+  if (launches) *launches = ctx->eval_launches;
+  return 0;
+}
+
+int mfit_flush_l2(mfit_ctx* ctx) {
+  if (!ctx) return MFIT_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->flush_buf) {
+    ctx->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+    CU(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+  }
+  mfit_launch_flush(ctx->flush_buf, ctx->flush_bytes, ctx->stream);
+  ctx->launches++;
+  return 0;
+}
+
+}  // extern "C"

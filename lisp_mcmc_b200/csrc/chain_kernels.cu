@@ -179,8 +179,9 @@ __device__ void scale_L(const MfitChains& c, long long w, double s) {  // scale-
 }
 
 // ------------------------------------------------------------------ top of loop iteration: shutdown test + proposal
+// Chains flagged need_reest are skipped here: k_reest rebuilds their l-matrix first and then runs this body itself.
 __device__ void pre_body(const MfitChains& c, const MfitRunCfg& r, long long w) {
-  if (c.done[w]) return;
+  if (c.done[w] || c.need_reest[w]) return;
   const int P = c.P;
   if (r.mode == MFIT_MODE_ADAPTIVE) {  // :905-917
     long long i = c.loop_i[w];
@@ -373,10 +374,8 @@ __global__ void k_init_run(const MfitChains c, const MfitRunCfg r, const double*
 }
 
 // ------------------------------------------------------------------ get-optimal-mcmc-l-matrix :888-895, one CTA per chain
-__global__ void k_reest(const MfitChains c, const MfitRunCfg r) {
-  const long long w = blockIdx.x;
-  if (w >= c.W || !c.need_reest[w]) return;
-  extern __shared__ __align__(16) unsigned char sm[];
+// returns 1 when the l-matrix was replaced or rescaled (counts as an update)
+__device__ int reest_body(const MfitChains& c, const MfitRunCfg& r, long long w, unsigned char* sm) {
   const int P = c.P, PP = P * P;
   double* avg = reinterpret_cast<double*>(sm);
   double* cov = avg + P;
@@ -392,8 +391,7 @@ __global__ void k_reest(const MfitChains c, const MfitRunCfg r) {
       double v = (i == j) ? c.best_theta[(size_t)i * c.stride + w] : 0.0;
       c.L[(size_t)e * c.stride + w] = 1e-5 * v;
     }
-    if (tid == 0) { c.need_reest[w] = 0; c.l_updates[w] += 1; }
-    return;
+    return 1;
   }
   const long long mwin = wlen(c, w, r.S);
   const long long hi = c.rows[w] - 1, lo = c.rows[w] - mwin;
@@ -405,17 +403,13 @@ __global__ void k_reest(const MfitChains c, const MfitRunCfg r) {
   }
   __syncthreads();
   const int m = m_sh;
-  if (m == 1) {  // 0x0 result fails the dimension check :936 -> l-matrix kept
-    if (tid == 0) c.need_reest[w] = 0;
-    return;
-  }
-  if (m == 0) {  // (elt nil 0) -> type-error handler returns l-matrix, scaled in place
+  if (m == 1) return 0;  // 0x0 result fails the dimension check :936 -> l-matrix kept
+  if (m == 0) {          // (elt nil 0) -> type-error handler returns l-matrix, scaled in place
     for (int e = tid; e < PP; e += nth) {
       double* p = c.L + (size_t)e * c.stride + w;
       *p = scale * *p;
     }
-    if (tid == 0) { c.need_reest[w] = 0; c.l_updates[w] += 1; }
-    return;
+    return 1;
   }
   const int n = m - 1;  // number of differences (older - newer), :263-275
 #define MFIT_DIFF(k, i) (ttheta(c, lo + fwd[(k) + 1], (i), w) - ttheta(c, lo + fwd[(k)], (i), w))
@@ -461,7 +455,34 @@ __global__ void k_reest(const MfitChains c, const MfitRunCfg r) {
       *p = scale * *p;
     }
   }
-  if (tid == 0) { c.need_reest[w] = 0; c.l_updates[w] += 1; }
+  return 1;
+}
+
+// r.t is the take-step index of the step that FOLLOWS the re-estimate; the chain's proposal for it is made here
+__global__ void k_reest(const MfitChains c, const MfitRunCfg r) {
+  const long long w = blockIdx.x;
+  if (w >= c.W || !c.need_reest[w]) return;
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int upd = reest_body(c, r, w, sm);
+  __syncthreads();  // l-matrix writes of every thread are visible to thread 0
+  if (threadIdx.x == 0) {
+    c.need_reest[w] = 0;
+    c.l_updates[w] += upd;
+    pre_body(c, r, w);
+  }
+}
+
+// re-map a trace ring to a larger capacity (slot = row % cap changes with cap)
+__global__ void k_trace_regrow(const MfitChains c, double* new_theta, double* new_prob, long long new_cap) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  long long m = c.rows[w] < c.cap ? c.rows[w] : c.cap;
+  for (long long k = 0; k < m; k++) {
+    const long long row = c.rows[w] - 1 - k;
+    const size_t so = (size_t)(row % c.cap), sn = (size_t)(row % new_cap);
+    for (int i = 0; i < c.P; i++) new_theta[(sn * c.P + i) * c.stride + w] = c.trace_theta[(so * c.P + i) * c.stride + w];
+    new_prob[sn * c.stride + w] = c.trace_prob[so * c.stride + w];
+  }
 }
 
 // ------------------------------------------------------------------ walker-create first step / force-take-step
@@ -701,6 +722,10 @@ void mfit_launch_eval_finalize(const MfitChains& c, double* prob, double* ll, do
 }
 void mfit_launch_l_read(const MfitChains& c, double* out, cudaStream_t st) {
   k_l_read<<<blocks_for((long long)c.W * c.P * c.P, 256), 256, 0, st>>>(c, out);
+}
+void mfit_launch_trace_regrow(const MfitChains& c, double* new_theta, double* new_prob, long long new_cap,
+                              cudaStream_t st) {
+  k_trace_regrow<<<blocks_for(c.W, 128), 128, 0, st>>>(c, new_theta, new_prob, new_cap);
 }
 void mfit_launch_flush(void* buf, size_t bytes, cudaStream_t st) {
   k_flush<<<148 * 8, 256, 0, st>>>((double*)buf, bytes / 8);

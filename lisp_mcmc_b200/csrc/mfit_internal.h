@@ -5,8 +5,28 @@
 #include <stdint.h>
 #include "../../include/mfit_cuda.h"
 
+#ifdef __cplusplus
+#include <string>
+#include <vector>
+
+// eval_builtin.cu
 const void* mfit_builtin_eval_kernel(int family, int degree, int ll);
 int mfit_family_nparams(int family, int degree);
 size_t mfit_eval_smem_bytes(int ll);
 
+// lower.cpp
+int mfit_lower_to_string(const char* text, const char* const* keys, int n_keys, int kind, std::string& out,
+                         std::string& err);
+// nvrtc_glue.cpp
+std::string mfit_user_model_source(const std::string& model_struct);
+std::string mfit_user_prior_source(const std::string& prior_fn);
+int mfit_nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string& err);
+
+// nccl_glue.cpp (libnccl is dlopen'ed on first use)
+int mfit_nccl_get_unique_id(void* id128, std::string& err);
+int mfit_nccl_comm_init(void** comm, int n_ranks, const void* id128, int rank, std::string& err);
+int mfit_nccl_allgather_bytes(void* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream,
+                              std::string& err);
+void mfit_nccl_comm_destroy(void* comm);
+#endif
 #endif

@@ -1,0 +1,508 @@
+"""Host-side mirror of the reference's walker API for the GPU path.
+
+Same names, argument meaning and error behaviour as mcmc-fitting.lisp: walker-create (:1132-1163),
+walker-adaptive-steps(-full) (:862-947), walker-many-steps (:849-853), walker-sample-region (:949-969),
+walker-force-take-step (:1124-1129), walker-get (:487-543), walker-modify :keep-walks (:568-569),
+walker-save / walker-load (:971-1001, dead code in the reference), mcmc-fit (:1165-1175).  The SBCL
+version of this file is lisp/mfit-cuda.lisp; both sit on the same C ABI (include/mfit_cuda.h).
+
+One `Walker` here is a *walker set* in the reference's vocabulary (nv-specific.lisp:58-66): W independent
+chains sharing :function / :data / :log-liklihood / :log-prior, advanced together on the GPU.  W = 1 is
+exactly one reference walker.
+
+Plugin slot values are descriptors instead of closures (nothing calls back into the host):
+  :function       `builtin("gauss_lin", keys)` | Lisp lambda text (lowered to CUDA C, compiled by NVRTC)
+  :log-liklihood  "log-liklihood-normal" | "log-liklihood-normal-cutoff" | "log-poisson"
+  :log-prior      "log-prior-flat" | [(key, lo, hi), ...] (prior-bounds-let with body bounds-total)
+                  | Lisp lambda text `(lambda (params data) ...)`
+"""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+from . import _lib, families
+
+_dp = C.POINTER(C.c_double)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Builtin:
+    """:function slot value selecting a hand-written family; `keys` maps the family's theta slots to parameter keys."""
+
+    def __init__(self, name, keys=None, degree=0):
+        self.name, self.degree = name, int(degree)
+        self.keys = [k.lstrip(":").lower() for k in (keys if keys is not None else families.slots(name, degree))]
+        if len(self.keys) != len(families.slots(name, self.degree)):
+            raise ValueError("family %s takes %d parameters" % (name, len(families.slots(name, self.degree))))
+
+    def lisp_text(self):
+        return families.lisp_text(self.name, self.degree, self.keys)
+
+    def __repr__(self):
+        return "(builtin %s %d (%s))" % (self.name, self.degree, " ".join(self.keys))
+
+
+def builtin(name, keys=None, degree=0):
+    return Builtin(name, keys, degree)
+
+
+_LL = {"log-liklihood-normal": _lib.LL_NORMAL, "log-liklihood-normal-cutoff": _lib.LL_NORMAL_CUTOFF,
+       "log-poisson": _lib.LL_POISSON, None: _lib.LL_NORMAL}
+_AUTO = {None: _lib.AUTO_NONE, False: _lib.AUTO_NONE, "prob-settle": _lib.AUTO_PROB_SETTLE, ":prob-settle": _lib.AUTO_PROB_SETTLE}
+_OPT = {None: _lib.OPT_COVARIANCE, "covariance": _lib.OPT_COVARIANCE, ":covariance": _lib.OPT_COVARIANCE,
+        "best-value": _lib.OPT_BEST_VALUE, ":best-value": _lib.OPT_BEST_VALUE}
+
+
+# ------------------------------------------------------------------ input normalisation (walker-create :1142-1147)
+def force_list(item):
+    """force-list :755-759"""
+    return list(item) if isinstance(item, (list, tuple)) else [item]
+
+
+def get_depth(tree):
+    """get-depth :761-771: nesting depth of a list tree (a flat list is 1)"""
+    if isinstance(tree, np.ndarray):
+        return tree.ndim
+    if not isinstance(tree, (list, tuple)):
+        return 0
+    return 1 + (max([get_depth(t) for t in tree]) if len(tree) else 0)
+
+
+def clean_data(data, n_functions):
+    """clean-data :807-825: -> list of n_functions datasets, each (x, y) as float64 vectors.
+    Accepts one dataset `(x y)` for a single function or a list of datasets; raises like the reference's
+    `error` when the shape does not match the number of functions."""
+    depth = get_depth(data)
+    if depth == 2:
+        sets = [data]
+    elif depth == 3:
+        sets = list(data)
+    else:
+        raise ValueError("data must be (x y) or a list of (x y) sets, got depth %d" % depth)
+    if len(sets) != n_functions:
+        raise ValueError("number of data sets (%d) does not match number of functions (%d)" % (len(sets), n_functions))
+    out = []
+    for s in sets:
+        if len(s) < 2:
+            raise ValueError("each data set needs x and y")
+        x, y = _f64(s[0]), _f64(s[1])
+        if x.ndim != 1 or x.shape != y.shape:
+            raise ValueError("x and y must be flat and of equal length")
+        out.append((x, y))
+    return out
+
+
+def clean_data_error(err, data):
+    """clean-data-error :774-805: a scalar, or a short list, is broadcast to the shape of each y using the FIRST
+    value found; a full per-point list is kept.  nil means 1 (:1144)."""
+    if err is None:
+        err = 1.0
+    out = []
+    per_set = None
+    if isinstance(err, (list, tuple, np.ndarray)) and get_depth(err) >= 2 and len(err) == len(data):
+        per_set = list(err)
+    for d, (x, y) in enumerate(data):
+        e = per_set[d] if per_set is not None else err
+        if np.ndim(e) == 0:
+            out.append(np.full(y.shape, float(e)))
+        else:
+            e = _f64(e).ravel()
+            if e.shape == y.shape:
+                out.append(e)
+            elif per_set is None and len(data) > 1 and len(e) == len(data):
+                out.append(np.full(y.shape, float(e[d])))
+            else:
+                out.append(np.full(y.shape, float(e[0])))
+    return out
+
+
+def plist(params):
+    """(:a 1 :b 2) / dict / [(k, v)] -> (keys, values) with to-double-floats :833-835 applied"""
+    if isinstance(params, dict):
+        items = list(params.items())
+    else:
+        p = list(params)
+        if p and isinstance(p[0], (tuple, list)):
+            items = [(k, v) for k, v in p]
+        else:
+            if len(p) % 2:
+                raise ValueError("params must be a property list")
+            items = [(p[i], p[i + 1]) for i in range(0, len(p), 2)]
+    keys = [str(k).lstrip(":").lower() for k, _ in items]
+    if len(set(keys)) != len(keys):
+        raise ValueError("duplicate parameter keys")
+    return keys, np.array([float(v) for _, v in items], dtype=np.float64)
+
+
+# ------------------------------------------------------------------ sharding plans (one process per GPU)
+def shard_chains(W, rank, world):
+    """Contiguous, balanced partition of W chains over `world` ranks -> (first global chain id, count)."""
+    base, rem = divmod(W, world)
+    lo = rank * base + min(rank, rem)
+    return lo, base + (1 if rank < rem else 0)
+
+
+def shard_datasets(D, world):
+    """owner[d] for D datasets over `world` ranks, round-robin (C4: dataset d on GPU d)."""
+    return [d % world for d in range(D)]
+
+
+class Walker:
+    """W chains on one GPU behind the reference's walker interface."""
+
+    def __init__(self, function, data, params, data_error=None, log_liklihood=None, log_prior=None,
+                 n_walkers=None, theta0=None, seed=0, device=0, chain_id_base=0, trace_capacity=0,
+                 nccl=None, dataset_owners=None, stream=None):
+        L = _lib.lib()
+        self._L = L
+        self.function = force_list(function)                        # :1142
+        D = len(self.function)
+        self.param_keys, p0 = plist(params)                         # :1145
+        P = len(self.param_keys)
+        self.data = clean_data(data, D)                             # :1143
+        self.data_error = clean_data_error(data_error, self.data)   # :1144
+        ll = log_liklihood if isinstance(log_liklihood, (list, tuple)) else [log_liklihood] * D
+        self.log_liklihood = [x if x is not None else "log-liklihood-normal" for x in ll]
+        if isinstance(log_prior, (list, tuple)) and log_prior and not isinstance(log_prior[0], (tuple, list)):
+            lp = list(log_prior)
+        elif isinstance(log_prior, (list, tuple)) and log_prior and isinstance(log_prior[0], (list, tuple)) \
+                and log_prior[0] and isinstance(log_prior[0][0], (list, tuple)):
+            lp = list(log_prior)            # list of bounds lists, one per dataset
+        else:
+            lp = [log_prior] * D
+        self.log_prior = [x if x is not None else "log-prior-flat" for x in lp]
+        if len(self.log_liklihood) != D or len(self.log_prior) != D:
+            raise ValueError(":log-liklihood / :log-prior lists must match the :function list")
+        self.param_style = "multiple-kwargs"
+        self.device, self.seed, self.chain_id_base = device, int(seed), int(chain_id_base)
+        self._keys_c = _lib.keys_array(self.param_keys)
+
+        h = C.c_void_p()
+        rc = L.mfit_ctx_create(device, stream, C.byref(h))
+        if rc != 0:
+            raise _lib.MfitError(rc, L.mfit_last_error(None).decode())
+        self._h = h
+        self._chk(L.mfit_problem_define(h, D, P))
+        if nccl is not None:
+            uid, rank, world = nccl
+            self._chk(L.mfit_nccl_attach(h, uid, rank, world))
+            self.rank, self.world = rank, world
+        else:
+            self.rank, self.world = 0, 1
+        self.dataset_owners = None
+        if dataset_owners is not None:
+            own = np.ascontiguousarray(dataset_owners, dtype=np.int32)
+            self._chk(L.mfit_dataset_owners(h, own.ctypes.data_as(C.POINTER(C.c_int32))))
+            self.dataset_owners = list(own)
+        for d in range(D):
+            if self.dataset_owners is None or self.dataset_owners[d] == self.rank:
+                x, y = self.data[d]
+                e = self.data_error[d]
+                self._chk(L.mfit_dataset_upload(h, d, _ptr(x), _ptr(y), _ptr(e), len(x)))
+            self._set_function(d, self.function[d])
+            kind = _LL.get(self.log_liklihood[d])
+            if kind is None:
+                raise ValueError("unknown :log-liklihood %r" % (self.log_liklihood[d],))
+            self._chk(L.mfit_likelihood_set(h, d, kind))
+            self._set_prior(d, self.log_prior[d])
+
+        if theta0 is None:
+            W = int(n_walkers or 1)
+            theta0 = np.tile(p0, (W, 1))
+        else:
+            theta0 = _f64(theta0)
+            if theta0.ndim == 1:
+                theta0 = theta0[None, :]
+            if theta0.shape[1] != P:
+                raise ValueError("theta0 must be W x P")
+        self.W, self.P, self.D = theta0.shape[0], P, D
+        self._chk(L.mfit_chains_init(h, _ptr(_f64(theta0)), self.W, self.seed, self.chain_id_base, int(trace_capacity)))
+        self.last_steps_launched = 0
+
+    # -------------------------------------------------------------- plumbing
+    def _chk(self, rc):
+        if rc != 0:
+            raise _lib.MfitError(rc, self._L.mfit_last_error(self._h).decode())
+
+    def _set_function(self, d, f):
+        L, h = self._L, self._h
+        if isinstance(f, Builtin):
+            try:
+                idx = np.array([self.param_keys.index(k) for k in f.keys], dtype=np.int32)
+            except ValueError as e:
+                raise ValueError("function %d uses a key that is not in :params: %s" % (d, e))
+            self._chk(L.mfit_model_builtin(h, d, families.family_id(f.name), f.degree,
+                                           idx.ctypes.data_as(C.POINTER(C.c_int32)), len(idx)))
+        elif isinstance(f, str):
+            self._chk(L.mfit_model_sexpr(h, d, f.encode(), self._keys_c, self.P))
+        else:
+            raise TypeError(":function must be builtin(...) or Lisp lambda text; host closures cannot run on the GPU")
+
+    def _set_prior(self, d, p):
+        L, h = self._L, self._h
+        if p in ("log-prior-flat", None):
+            self._chk(L.mfit_prior_flat(h, d))
+        elif isinstance(p, str):
+            self._chk(L.mfit_prior_sexpr(h, d, p.encode(), self._keys_c, self.P))
+        else:
+            idx = np.array([self.param_keys.index(str(k).lstrip(":").lower()) if str(k).lstrip(":").lower() in self.param_keys
+                            else -1 for k, _, _ in p], dtype=np.int32)
+            lo = _f64([b[1] for b in p])
+            hi = _f64([b[2] for b in p])
+            self._chk(L.mfit_prior_bounds(h, d, len(idx), idx.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(lo), _ptr(hi)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mfit_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------- walker-make-step on a batch (:1067-1070)
+    def make_step(self, theta):
+        """prob, ll[W,D], lp[W,D] for a batch of parameter vectors (W x P)."""
+        theta = _f64(theta)
+        if theta.ndim == 1:
+            theta = theta[None, :]
+        W = theta.shape[0]
+        prob, ll, lp = np.empty(W), np.empty((W, self.D)), np.empty((W, self.D))
+        self._chk(self._L.mfit_eval_logp(self._h, _ptr(theta), W, _ptr(prob), _ptr(ll), _ptr(lp)))
+        return prob, ll, lp
+
+    # -------------------------------------------------------------- drivers
+    def _streams(self, z, u):
+        nstream = 0
+        if z is not None:
+            z = _f64(z)
+            if z.ndim == 2:
+                z = z[None, :, :]
+            if z.shape[0] != self.W or z.shape[2] != self.P:
+                raise ValueError("z must be W x nstream x P")
+            nstream = z.shape[1]
+        if u is not None:
+            u = _f64(u)
+            if u.ndim == 1:
+                u = u[None, :]
+            if z is None or u.shape != z.shape[:2]:
+                raise ValueError("u must be W x nstream and come with z")
+        return z, u, nstream
+
+    def adaptive_steps_full(self, n=100000, temperature=1e3, auto=None, sampling_optimization=None,
+                            max_walker_length=None, l_matrix=None, z=None, u=None, greedy=False):
+        """walker-adaptive-steps-full :862-942.  `auto` = "prob-settle" or None (:slope-settle is not supported)."""
+        if auto in ("slope-settle", ":slope-settle"):
+            raise NotImplementedError(":slope-settle runs a nested mcmc-fit on the host (:886-887); use :prob-settle")
+        cfg = _lib.AdaptCfg(int(np.floor(n)), float(temperature), _AUTO[auto], _OPT[sampling_optimization],
+                            int(max_walker_length or 0), int(bool(greedy)), 0)
+        z, u, nstream = self._streams(z, u)
+        lm = _f64(l_matrix) if l_matrix is not None else None
+        if lm is not None and lm.shape != (self.P, self.P):
+            raise ValueError(":l-matrix must be P x P")
+        launched = C.c_int64()
+        self._chk(self._L.mfit_run_adaptive(self._h, C.byref(cfg), _ptr(lm), _ptr(z), _ptr(u), nstream, C.byref(launched)))
+        self.last_steps_launched = launched.value
+        return self
+
+    def adaptive_steps(self, n=30000, **kw):
+        """walker-adaptive-steps :946-947"""
+        return self.adaptive_steps_full(n=n, temperature=10, auto="prob-settle", **kw)
+
+    def many_steps(self, n, l_matrix, z=None, u=None):
+        """walker-many-steps :849-853 (the :median-params default l-matrix is host post-processing: pass one)"""
+        z, u, nstream = self._streams(z, u)
+        lm = _f64(l_matrix)
+        self._chk(self._L.mfit_run_many_steps(self._h, int(n), _ptr(lm), _ptr(z), _ptr(u), nstream))
+        return self
+
+    def sample_region(self, initial_scale=1e-3, z=None):
+        """walker-sample-region :949-969"""
+        z, _, nstream = self._streams(z, None)
+        self._chk(self._L.mfit_run_sample_region(self._h, float(initial_scale), _ptr(z), nstream))
+        return self
+
+    def force_take_step(self):
+        """walker-force-take-step :1124-1129"""
+        self._chk(self._L.mfit_force_take_step(self._h))
+        return self
+
+    def request_stop(self):
+        """(setf mfit-walker-estop t) :860"""
+        self._L.mfit_request_stop(self._h)
+
+    def keep_walks(self, keep):
+        """walker-modify :keep-walks :568-569"""
+        self._chk(self._L.mfit_keep_walks(self._h, int(keep)))
+
+    # -------------------------------------------------------------- readers
+    def stats(self):
+        arr = (_lib.ChainStats * self.W)()
+        self._chk(self._L.mfit_stats_read(self._h, arr))
+        return np.frombuffer(arr, dtype=[("length", "i8"), ("age", "i8"), ("steps_this_run", "i8"), ("last_prob", "f8"),
+                                         ("best_prob", "f8"), ("temperature", "f8"), ("accept_200", "f8"),
+                                         ("shutting_down", "i4"), ("l_updates", "i4")]).copy()
+
+    def trace(self, take):
+        """newest-first (theta[W,take,P], prob[W,take], n_valid[W]) like walker-get :steps :take"""
+        take = int(take)
+        th = np.empty((self.W, take, self.P))
+        pr = np.empty((self.W, take))
+        nv = np.empty(self.W, dtype=np.int64)
+        self._chk(self._L.mfit_trace_read(self._h, take, _ptr(th), _ptr(pr), nv.ctypes.data_as(C.POINTER(C.c_int64))))
+        return th, pr, nv
+
+    def most_likely(self):
+        th, pr = np.empty((self.W, self.P)), np.empty(self.W)
+        self._chk(self._L.mfit_best_read(self._h, _ptr(th), _ptr(pr)))
+        return th, pr
+
+    def last_step(self):
+        th, pr = np.empty((self.W, self.P)), np.empty(self.W)
+        self._chk(self._L.mfit_last_read(self._h, _ptr(th), _ptr(pr)))
+        return th, pr
+
+    def l_matrix(self):
+        out = np.empty((self.W, self.P, self.P))
+        self._chk(self._L.mfit_l_matrix_read(self._h, _ptr(out)))
+        return out
+
+    def philox_stream(self, first_step, nsteps):
+        """The normals z[W,nsteps,P] and uniforms u[W,nsteps] the device draws for take-step calls made at walker
+        age first_step, first_step+1, ... (for replaying a Philox run through an injected-stream implementation)."""
+        z, u = np.empty((self.W, nsteps, self.P)), np.empty((self.W, nsteps))
+        self._chk(self._L.mfit_philox_stream(self._h, self.seed, self.chain_id_base, self.W, int(first_step), int(nsteps),
+                                             self.P, _ptr(z), _ptr(u)))
+        return z, u
+
+    def get(self, get, take=None, param=None, chain=None):
+        """walker-get :487-543 for the modes that read the trace (the list-walking analytics are host post-processing).
+        Results carry a leading chain axis unless `chain` selects one."""
+        g = str(get).lstrip(":").lower()
+        st = self.stats()
+        n = int(st["length"].max()) if take is None else int(take)
+        sel = (lambda a: a if chain is None else a[chain])
+        if g in ("most-likely-params", "most-likely-step"):
+            th, pr = self.most_likely()
+            return sel(th) if g == "most-likely-params" else (sel(th), sel(pr))
+        if g == "last-step":
+            th, pr = self.last_step()
+            return sel(th), sel(pr)
+        th, pr, nv = self.trace(max(n, 1))
+        if g == "steps":
+            return sel(th), sel(pr), sel(nv)
+        if g == "params":
+            return sel(th)
+        if g == "log-liklihoods":
+            return sel(pr)
+        if g == "param":
+            return sel(th[:, :, self.param_keys.index(str(param).lstrip(":").lower())])
+        if g == "acceptance":      # :506-508: runs of distinct consecutive probs / window
+            acc = np.empty(self.W)
+            for w in range(self.W):
+                p = pr[w, :nv[w]]
+                acc[w] = (1 + np.count_nonzero(p[1:].view(np.int64) != p[:-1].view(np.int64))) / float(len(p))
+            return sel(acc)
+        if g == "median-params":   # :516-523 with `median` = nth-percentile 50 (:1499-1513, midpoint form)
+            med = np.empty((self.W, self.P))
+            for w in range(self.W):
+                med[w] = np.median(th[w, :nv[w]], axis=0)
+            return sel(med)
+        raise NotImplementedError("walker-get :%s" % g)
+
+    # -------------------------------------------------------------- walker-save / walker-load (:971-1001)
+    def save(self, path, take=None):
+        """s-expression header in the layout of the reference's (commented-out) walker-save, followed by a binary
+        FP64 blob: W x rows x (P+1) doubles (prob first), newest step first."""
+        st = self.stats()
+        rows = int(st["length"].max()) if take is None else int(take)
+        th, pr, nv = self.trace(rows)
+        fn_names = " ".join('"%s"' % (repr(f) if isinstance(f, Builtin) else f).replace('"', '\\"') for f in self.function)
+        hdr = ("(:mfit-walker 1 :fn (%s) :param-keys (%s) :log-liklihood (%s) :log-prior (%s) :n-walkers %d :rows %d "
+               ":n-params %d :seed %d :lengths (%s))\n") % (
+            fn_names, " ".join(":" + k for k in self.param_keys),
+            " ".join('"%s"' % x for x in self.log_liklihood),
+            " ".join('"%s"' % (x if isinstance(x, str) else repr(list(x))).replace('"', '\\"') for x in self.log_prior),
+            self.W, rows, self.P, self.seed, " ".join(str(int(v)) for v in nv))
+        blob = np.concatenate([pr[:, :, None], th], axis=2).astype("<f8")
+        with open(path, "wb") as f:
+            f.write(hdr.encode())
+            f.write(struct.pack("<q", blob.size))
+            f.write(blob.tobytes())
+        return path
+
+
+def walker_load(path):
+    """Read a file written by Walker.save -> dict(header text, param_keys, prob[W,rows], theta[W,rows,P], n_valid[W])."""
+    with open(path, "rb") as f:
+        hdr = f.readline().decode()
+        (cnt,) = struct.unpack("<q", f.read(8))
+        blob = np.frombuffer(f.read(cnt * 8), dtype="<f8")
+    import re
+    W = int(re.search(r":n-walkers (\d+)", hdr).group(1))
+    rows = int(re.search(r":rows (\d+)", hdr).group(1))
+    P = int(re.search(r":n-params (\d+)", hdr).group(1))
+    keys = re.search(r":param-keys \(([^)]*)\)", hdr).group(1).split()
+    lens = [int(v) for v in re.search(r":lengths \(([^)]*)\)", hdr).group(1).split()]
+    blob = blob.reshape(W, rows, P + 1)
+    return {"header": hdr, "param_keys": [k.lstrip(":") for k in keys], "prob": blob[:, :, 0].copy(),
+            "theta": blob[:, :, 1:].copy(), "n_valid": np.array(lens, dtype=np.int64)}
+
+
+# ------------------------------------------------------------------ the reference's function names
+def walker_create(function=None, data=None, params=None, data_error=None, log_liklihood=None, log_prior=None,
+                  param_bounds=None, **gpu):
+    """walker-create :1132-1163 (param-bounds is ignorable in the reference too, :1141).  Extra keywords select the
+    GPU-side batch: n_walkers / theta0, seed, device, chain_id_base, trace_capacity, nccl, dataset_owners."""
+    return Walker(function, data, params, data_error, log_liklihood, log_prior, **gpu)
+
+
+def walker_adaptive_steps_full(walker, **kw):
+    return walker.adaptive_steps_full(**kw)
+
+
+def walker_adaptive_steps(walker, n=30000):
+    return walker.adaptive_steps(n)
+
+
+def walker_many_steps(walker, n, l_matrix=None):
+    if l_matrix is None:   # :851 (diagonal-covariance (scale-plist 1e-2 median-params)); 1e-2 is a single-float literal
+        med = walker.get("median-params")
+        if not np.allclose(med, med[0]):
+            raise ValueError("chains disagree on :median-params; pass an l-matrix")
+        l_matrix = np.diag(np.float64(np.float32(1e-2)) * med[0])
+    return walker.many_steps(n, l_matrix)
+
+
+def walker_sample_region(walker, initial_scale=1e-3):
+    return walker.sample_region(initial_scale)
+
+
+def walker_force_take_step(walker):
+    return walker.force_take_step()
+
+
+def walker_get(walker, get, take=None, param=None, chain=None):
+    return walker.get(get, take=take, param=param, chain=chain)
+
+
+def walker_save(walker, path, take=None):
+    return walker.save(path, take)
+
+
+def mcmc_fit(**kw):
+    """mcmc-fit :1165-1175"""
+    w = walker_create(**kw)
+    walker_adaptive_steps(w)
+    return w

@@ -1,0 +1,357 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (walker.py -> libmfit_cuda.so), against the
+CPU oracle on the same seeded inputs.  Tolerances are BASELINE.json's: log-likelihoods within 1e-12 relative
+(FP64), identical accept/reject sequences under the same injected normal/uniform streams."""
+import numpy as np
+import pytest
+
+from lisp_mcmc_b200 import builtin, families, walker_create, workloads
+from lisp_mcmc_b200 import _lib
+from helpers import oracle_walker, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12  # relative, north_star
+
+
+def _family_cfg(name, N, W, ll="log-liklihood-normal", degree=0, seed=0):
+    rng = np.random.default_rng(100 + seed)
+    if name == "poly":
+        keys = families.slots("poly", degree)
+        th = rng.uniform(-1, 1, degree + 1)
+        x = np.linspace(-1.5, 1.5, N)
+    elif name == "expo":
+        keys, th, x = families.slots(name), np.array([2.0, -0.7, 0.5]), np.linspace(0, 4, N)
+    elif name == "sinus":
+        keys, th, x = families.slots(name), np.array([20.0, 0.7, 0.3, 50.0]), np.linspace(0, 100, N)
+    elif name == "lorentz":
+        keys, th, x = families.slots(name), np.array([5.0, 2500.0, 60.0, -1.0]), 2000.0 + np.linspace(0, 1000, N)
+    elif name == "gauss_lin":
+        keys, th, x = families.slots(name), np.array([10.0, 0.5, 1.5, 2.0, 0.1]), np.linspace(-10, 10, N)
+    else:
+        keys = families.slots("nv_multi", degree)
+        th = np.array([1e-2 * (1 + 0.1 * k) for k in range(degree)] + [2860.0 + 15 * k for k in range(degree)] + [12.0, 5e-3])
+        x = np.linspace(2800, 2940, N)
+    fam = builtin(name, keys, degree)
+    from oracle import oracle as orc
+    f = np.array([orc.model_builtin(families.family_id(name), degree, th, xi) for xi in x]) if N else np.zeros(0)
+    if ll == "log-poisson":
+        y = rng.poisson(np.maximum(f, 0.1)).astype(np.float64)
+        sig = 1.0
+    else:
+        sig = rng.uniform(0.05, 0.15, N) * (np.abs(th[0]) if name != "nv_multi" else 1e-3)
+        y = f + sig * rng.standard_normal(N)
+    theta0 = th[None, :] * (1 + 0.01 * rng.standard_normal((W, len(th))))
+    return dict(function=[fam], data=[[x, y]], data_error=[sig] if np.ndim(sig) else sig, keys=keys, theta_star=th,
+                theta0=theta0, log_liklihood=ll, log_prior="log-prior-flat")
+
+
+FAMILIES = [("poly", 0), ("poly", 1), ("poly", 3), ("poly", 5), ("poly", 7), ("expo", 0), ("sinus", 0), ("lorentz", 0),
+            ("gauss_lin", 0), ("nv_multi", 1), ("nv_multi", 2), ("nv_multi", 4)]
+
+
+@pytest.mark.parametrize("name,degree", FAMILIES)
+@pytest.mark.parametrize("ll", ["log-liklihood-normal", "log-liklihood-normal-cutoff"])
+def test_builtin_family_loglik_matches_oracle(orc, name, degree, ll):
+    cfg = _family_cfg(name, 1537, 70, ll, degree)   # ragged: 3 tiles + 1 point, 70 chains (not a multiple of 128)
+    w = workloads.make_walker(cfg)
+    prob, llv, lpv = w.make_step(cfg["theta0"])
+    ow = oracle_walker(orc, cfg)
+    ref = np.array([ow.logp(t)[0] for t in cfg["theta0"]])
+    assert rel_err(prob, ref) < TOL
+    assert rel_err(llv[:, 0], ref) < TOL
+    assert np.all(lpv == 0.0)
+    w.close()
+
+
+@pytest.mark.parametrize("name", ["sinus", "expo", "gauss_lin"])
+def test_log_poisson_matches_oracle(orc, name):
+    cfg = _family_cfg(name, 2100, 33, "log-poisson")
+    if name != "sinus":   # keep lambda positive
+        cfg["theta0"] = np.abs(cfg["theta0"])
+        cfg["theta0"][:, -1 if name == "expo" else 3] += 3.0
+    w = workloads.make_walker(cfg)
+    prob, _, _ = w.make_step(cfg["theta0"])
+    ow = oracle_walker(orc, cfg)
+    ref = np.array([ow.logp(t)[0] for t in cfg["theta0"]])
+    assert rel_err(prob, ref) < TOL
+    w.close()
+
+
+@pytest.mark.parametrize("N", [0, 1, 2, 511, 512, 513, 1024, 4097])
+@pytest.mark.parametrize("W", [1, 128, 129])
+def test_ragged_sizes(orc, N, W):
+    cfg = _family_cfg("gauss_lin", N, W, seed=N + W)
+    w = workloads.make_walker(cfg)
+    prob, _, _ = w.make_step(cfg["theta0"])
+    ow = oracle_walker(orc, cfg)
+    ref = np.array([ow.logp(t)[0] for t in cfg["theta0"]])
+    if N == 0:
+        assert np.all(prob == 0.0) and np.all(ref == 0.0)   # (reduce #'+ nil) = 0
+    else:
+        assert rel_err(prob, ref) < TOL
+    w.close()
+
+
+def test_cutoff_clamps_like_reference(orc):
+    cfg = _family_cfg("lorentz", 700, 9, "log-liklihood-normal-cutoff")
+    cfg["theta0"][:, 0] *= 50.0   # far off: most terms hit the -5000 floor (:426)
+    w = workloads.make_walker(cfg)
+    prob, _, _ = w.make_step(cfg["theta0"])
+    ow = oracle_walker(orc, cfg)
+    ref = np.array([ow.logp(t)[0] for t in cfg["theta0"]])
+    assert np.any(ref <= -5000.0 * 300)
+    assert rel_err(prob, ref) < TOL
+    w.close()
+
+
+def test_nan_and_inf_are_returned_not_raised(orc):
+    cfg = _family_cfg("expo", 600, 4)
+    cfg["theta0"][1, 1] = 400.0       # exp overflow -> inf -> ll = -inf or nan
+    cfg["theta0"][2, 0] = np.nan
+    w = workloads.make_walker(cfg)
+    prob, _, _ = w.make_step(cfg["theta0"])
+    ow = oracle_walker(orc, cfg)
+    ref = np.array([ow.logp(t)[0] for t in cfg["theta0"]])
+    assert np.isfinite(prob[0]) and rel_err(prob[0], ref[0]) < TOL
+    assert not np.isfinite(prob[1]) and not np.isfinite(ref[1])
+    assert np.isnan(prob[2]) and np.isnan(ref[2])
+    w.close()
+
+
+def test_user_sexpr_model_matches_builtin_and_oracle(orc):
+    cfg = _family_cfg("gauss_lin", 2000, 40)
+    w1 = workloads.make_walker(cfg)
+    p1, _, _ = w1.make_step(cfg["theta0"])
+    cfg2 = dict(cfg)
+    cfg2["function"] = [cfg["function"][0].lisp_text()]      # same family through lower.cpp + NVRTC
+    w2 = workloads.make_walker(cfg2)
+    p2, _, _ = w2.make_step(cfg["theta0"])
+    ow = oracle_walker(orc, cfg2)
+    ref = np.array([ow.logp(t)[0] for t in cfg["theta0"]])
+    assert rel_err(p2, ref) < TOL and rel_err(p1, ref) < TOL
+    w1.close(); w2.close()
+
+
+def test_c5_user_model_poly5_times_exp(orc):
+    cfg = workloads.c5(W=50, N=3000)
+    w = workloads.make_walker(cfg)
+    prob, _, _ = w.make_step(cfg["theta0"])
+    ow = oracle_walker(orc, cfg)
+    ref = np.array([ow.logp(t)[0] for t in cfg["theta0"]])
+    assert rel_err(prob, ref) < TOL
+    w.close()
+
+
+def test_prior_bounds_let_constant_bounds(orc):
+    cfg = workloads.c1(W=6)
+    th = cfg["theta0"].copy()
+    th[1, 0] = -3e-6          # a below its lower bound
+    th[2, 1] = 3000.5         # x0 above
+    th[3, 2] = 1.0            # gamma exactly on the bound: strict < fails (:358)
+    th[4, :] = [2e-4, 1999.0, 600.0, 2e-5]
+    cfg["theta0"] = th
+    w = workloads.make_walker(cfg)
+    prob, ll, lp = w.make_step(th)
+    ow = oracle_walker(orc, cfg)
+    for c in range(6):
+        rp, rll, rlp = ow.logp(th[c])
+        assert rel_err(ll[c], rll) < TOL
+        # ill-conditioned when active: -1e10 (exp(d 1e-5) - 1) turns one ulp of exp into 2e-6
+        assert abs(lp[c, 0] - rlp[0]) <= 1e10 * 2.0 ** -50
+        assert (lp[c, 0] == 0.0) == (rlp[0] == 0.0)
+    w.close()
+
+
+def test_nv_prior_sexpr_and_global_fit(orc):
+    cfg = workloads.c4(W=20, D=3, N=1200)
+    th = cfg["theta0"].copy()
+    th[3, cfg["keys"].index("mu1-1")] = 2889.0     # violates mu1 < mu2 - 6 and the mu1 bound
+    th[4, cfg["keys"].index("scale1-2")] *= 1.3     # ratio constraint
+    th[5, 0] = 25.0                                 # shared sigma out of (9, 20): penalised by every dataset's prior
+    cfg["theta0"] = th
+    w = workloads.make_walker(cfg)
+    prob, ll, lp = w.make_step(th)
+    ow = oracle_walker(orc, cfg)
+    for c in range(th.shape[0]):
+        rp, rll, rlp = ow.logp(th[c])
+        assert rel_err(ll[c], rll) < TOL
+        assert np.all(np.abs(lp[c] - rlp) <= 1e10 * 2.0 ** -50 + 1e-12 * np.abs(rlp))
+        assert abs(prob[c] - rp) <= 1e-12 * abs(rp) + 3e10 * 2.0 ** -50
+    assert lp[3, 1] < -1e9 and lp[5, 0] < 0 and lp[5, 2] < 0 and lp[0].max() == 0.0
+    w.close()
+
+
+def _compare_chain(orc, cfg, w, z, u, run_oracle, chains, bit_exact=True):
+    th, pr, nv = w.trace(int(w.stats()["length"].max()))
+    Ls = w.l_matrix()
+    ow = oracle_walker(orc, cfg)
+    for c in chains:
+        ow.init(cfg["theta0"][c])
+        run_oracle(ow, z[c], u[c] if u is not None else None)
+        oth, opr = ow.trace(0)
+        n = len(opr)
+        assert nv[c] == n, "chain %d took %d steps, oracle %d" % (c, nv[c], n)
+        # identical accept/reject sequence <=> identical runs of repeated rows
+        acc_g = (pr[c, :n - 1] != pr[c, 1:n])
+        acc_o = (opr[:-1] != opr[1:])
+        assert np.array_equal(acc_g, acc_o), "chain %d accept/reject sequence differs" % c
+        if bit_exact:
+            assert np.array_equal(th[c, :n], oth), "chain %d parameter trace differs" % c
+            assert np.array_equal(Ls[c], ow.last_l_matrix()), "chain %d final l-matrix differs" % c
+        assert rel_err(pr[c, :n], opr) < TOL
+
+
+def test_many_steps_injected_stream_identical_to_oracle(orc):
+    cfg = workloads.c2(W=40, N=1500)
+    w = workloads.make_walker(cfg)
+    n = 400
+    rng = np.random.default_rng(11)
+    z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    Lm = np.diag(0.004 * np.abs(cfg["theta_star"])) + 1e-4 * np.tril(np.ones((w.P, w.P)), -1)
+    w.many_steps(n, Lm, z=z, u=u)
+    _compare_chain(orc, cfg, w, z, u, lambda ow, zz, uu: ow.many_steps(n, Lm, z=zz, u=uu), range(0, 40, 3))
+    w.close()
+
+
+@pytest.mark.parametrize("auto", [None, "prob-settle"])
+def test_adaptive_steps_full_injected_stream_identical_to_oracle(orc, auto):
+    """walker-adaptive-steps-full end to end: temperature schedule, 200-step acceptance windows, x0.1 / x1.9 rescales,
+    forward-step covariance + Cholesky re-estimates, shutdown tail and (auto) the :prob-settle stop."""
+    cfg = workloads.c2(W=12, N=400)
+    w = workloads.make_walker(cfg)
+    n = 9000
+    rng = np.random.default_rng(12)
+    z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    w.adaptive_steps_full(n=n, temperature=10, auto=auto, z=z, u=u)
+    st = w.stats()
+    assert st["l_updates"].min() > 3
+    a = orc.AUTO_PROB_SETTLE if auto else orc.AUTO_NONE
+    _compare_chain(orc, cfg, w, z, u,
+                   lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=a, z=zz, u=uu), range(12))
+    w.close()
+
+
+def test_adaptive_with_bounds_prior_lorentzian_c1(orc):
+    cfg = workloads.c1(W=3)
+    cfg["theta0"] = cfg["theta0"] * np.array([[1.0], [1.02], [0.97]])
+    w = workloads.make_walker(cfg)
+    n = 5000
+    rng = np.random.default_rng(13)
+    z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    w.adaptive_steps_full(n=n, temperature=10, auto=None, z=z, u=u)
+    _compare_chain(orc, cfg, w, z, u,
+                   lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu), range(3))
+    w.close()
+
+
+def test_sample_region_and_force_take_step(orc):
+    cfg = workloads.c2(W=5, N=300)
+    w = workloads.make_walker(cfg)
+    rng = np.random.default_rng(14)
+    z = rng.standard_normal((w.W, 2999, w.P))
+    w.sample_region(1e-3, z=z)
+    w.force_take_step()
+
+    def run(ow, zz, uu):
+        ow.sample_region(1e-3, z=zz)
+        ow.force_take_step()
+    _compare_chain(orc, cfg, w, z, None, run, range(5))
+    st = w.stats()
+    assert np.all(st["length"] == 1 + 2999 + 1) and np.all(st["age"] == st["length"])
+    w.close()
+
+
+def test_resume_reestimates_l_matrix_from_existing_walk(orc):
+    """calling walker-adaptive-steps again on a long walk derives the l-matrix from it (:896-901)"""
+    cfg = workloads.c2(W=4, N=300)
+    w = workloads.make_walker(cfg)
+    n = 3000
+    rng = np.random.default_rng(15)
+    z1, u1 = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    z2, u2 = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    w.adaptive_steps_full(n=n, temperature=10, z=z1, u=u1)
+    w.adaptive_steps_full(n=n, temperature=10, z=z2, u=u2)
+    th, pr, nv = w.trace(2 * n)
+    ow = oracle_walker(orc, cfg)
+    for c in range(4):
+        ow.init(cfg["theta0"][c])
+        ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=z1[c], u=u1[c])
+        ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=z2[c], u=u2[c])
+        oth, opr = ow.trace(0)
+        assert nv[c] == len(opr)
+        assert np.array_equal(th[c, :nv[c]], oth)
+    w.close()
+
+
+def test_philox_run_replays_through_oracle(orc):
+    """on-device Philox4x32-10 proposals: export the stream the device drew and replay it through the oracle"""
+    cfg = workloads.c2(W=6, N=500)
+    w = workloads.make_walker(cfg, seed=1234, chain_id_base=77)
+    n = 1500
+    w.adaptive_steps_full(n=n, temperature=10)
+    z, u = w.philox_stream(1, n)   # the first take-step happens at walker age 1
+    assert abs(z.mean()) < 0.05 and abs(z.std() - 1) < 0.05 and 0.45 < u.mean() < 0.55 and u.min() > 0 and u.max() < 1
+    _compare_chain(orc, cfg, w, z, u,
+                   lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu), range(6))
+    w.close()
+
+
+def test_chain_sharding_is_bit_identical(orc):
+    """W chains in one context == the same chains split over two contexts keyed by global chain id"""
+    cfg = workloads.c2(W=10, N=700)
+    n = 800
+    w = workloads.make_walker(cfg, seed=99)
+    w.adaptive_steps_full(n=n, temperature=10)
+    th, pr, nv = w.trace(n)
+    parts = []
+    from lisp_mcmc_b200 import shard_chains
+    for r in range(2):
+        lo, cnt = shard_chains(10, r, 2)
+        wr = workloads.make_walker(cfg, theta0=cfg["theta0"][lo:lo + cnt], seed=99, chain_id_base=lo)
+        wr.adaptive_steps_full(n=n, temperature=10)
+        parts.append(wr.trace(n))
+        wr.close()
+    th2 = np.concatenate([p[0] for p in parts]); pr2 = np.concatenate([p[1] for p in parts])
+    assert np.array_equal(th, th2) and np.array_equal(pr, pr2)
+    w.close()
+
+
+def test_full_size_c2_properties():
+    """BASELINE configs[1] at full size (100k points x 4096 chains): properties that need no oracle pass --
+    chain independence (a permutation of chains permutes results bit for bit), run-to-run determinism, and
+    additivity over a split of the data into two datasets of a global fit."""
+    cfg = workloads.c2()
+    w = workloads.make_walker(cfg)
+    th = cfg["theta0"]
+    p1, _, _ = w.make_step(th)
+    p1b, _, _ = w.make_step(th)
+    assert np.array_equal(p1, p1b)
+    perm = np.random.default_rng(3).permutation(len(th))
+    p2, _, _ = w.make_step(th[perm])
+    assert np.array_equal(p2, p1[perm])
+    w.close()
+    x, y = cfg["data"][0]
+    s = cfg["data_error"][0]
+    h = 51200   # a whole number of 512-point tiles, so the halves cover the same segments
+    cfg2 = dict(cfg)
+    cfg2["function"] = [cfg["function"][0], cfg["function"][0]]
+    cfg2["data"] = [[x[:h], y[:h]], [x[h:], y[h:]]]
+    cfg2["data_error"] = [s[:h], s[h:]]
+    w2 = workloads.make_walker(cfg2)
+    q, ll, _ = w2.make_step(th[:512])
+    assert rel_err(q, p1[:512]) < TOL
+    w2.close()
+
+
+def test_errors_are_codes_not_crashes():
+    cfg = workloads.c2(W=4, N=100)
+    with pytest.raises(_lib.MfitError):
+        bad = dict(cfg); bad["function"] = ["(lambda (x &key a) (frobnicate a x))"]
+        workloads.make_walker(bad)
+    with pytest.raises(ValueError):
+        walker_create(function=cfg["function"], data=[[1.0, 2.0], [1.0]], params=[("a", 1.0)])
+    w = workloads.make_walker(cfg)
+    with pytest.raises(_lib.MfitError) as e:
+        w.adaptive_steps_full(n=500, z=np.zeros((4, 10, 5)), u=np.zeros((4, 10)))
+    assert e.value.code == _lib.ERR_STREAM
+    w.close()
