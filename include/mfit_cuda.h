@@ -142,6 +142,12 @@ int mfit_chains_init(mfit_ctx* ctx, const double* theta0, int64_t W, uint64_t se
  * receives the number of MH steps enqueued (the longest chain). */
 int mfit_run_adaptive(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, const double* l_matrix,
                       const double* z, const double* u, int64_t nstream, int64_t* steps_launched);
+/* The same run in two halves, so that the host can poll mfit-walker-estop (:860, tested every iteration at :904),
+ * report progress or time it: begin = the set-up of :866-901, advance = up to max_steps more iterations of the
+ * `do` loop :902-942 (-1 = to the end).  *finished is set when every chain has left the loop. */
+int mfit_run_begin(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, const double* l_matrix, const double* z, const double* u,
+                   int64_t nstream);
+int mfit_run_advance(mfit_ctx* ctx, int64_t max_steps, int64_t* steps_done, int* finished);
 /* walker-many-steps :849-853: n steps, constant l-matrix (required), temperature 1 */
 int mfit_run_many_steps(mfit_ctx* ctx, int64_t n, const double* l_matrix, const double* z, const double* u,
                         int64_t nstream);

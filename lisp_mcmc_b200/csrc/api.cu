@@ -101,6 +101,11 @@ struct mfit_ctx {
 
   std::atomic<int> stop{0};
 
+  // an open run (mfit_run_begin ... mfit_run_advance)
+  bool run_open = false;
+  MfitRunCfg run_cfg;
+  long long run_t = 0, run_max = 0;
+
   // measurement
   bool timing = false;
   std::vector<EventPair> ev;
@@ -383,15 +388,13 @@ int upload_opt(mfit_ctx* ctx, const double* host, size_t count, double** dev, si
   return 0;
 }
 
-// the step loop shared by the three run modes
-int run_loop(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long long max_steps, long long* steps_launched) {
+// set-up of a run (:866-901): driver state per chain, first proposals
+int run_begin(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long long max_steps) {
   MfitChains& c = ctx->ch;
   int rc = check_problem_ready(ctx);
   if (rc) return rc;
+  ctx->run_open = false;
   ctx->stop.store(0);
-  ctx->eval_seconds = 0.0;
-  ctx->eval_launches = 0;
-  ctx->ev_used = 0;
   if (max_steps < 0) max_steps = 0;
   rc = grow_trace(ctx, ctx->rows_upper + max_steps + 1);
   if (rc) return rc;
@@ -414,12 +417,28 @@ int run_loop(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long long
     CU(cudaMalloc(&ctx->active_dev, sizeof(int) * 4));
     ctx->poll_ev_made = true;
   }
+  ctx->run_cfg = r;
+  ctx->run_t = 0;
+  ctx->run_max = max_steps;
+  ctx->run_open = true;
+  return 0;
+}
+
+// up to `budget` more MH steps of the open run; returns when they have completed on the device
+int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* finished) {
+  MfitChains& c = ctx->ch;
+  if (!ctx->run_open) return fail(ctx, MFIT_ERR_STATE, "no open run");
+  MfitRunCfg r = ctx->run_cfg;
+  ctx->eval_seconds = 0.0;
+  ctx->eval_launches = 0;
+  ctx->ev_used = 0;
   const long long poll_every = 64;
   bool poll_pending[4] = {false, false, false, false};
-  int poll_slot = 0;
-  long long t = 0;
+  int poll_slot = 0, rc = 0;
+  long long t = ctx->run_t;
+  const long long t_end = (budget < 0 || t + budget > ctx->run_max) ? ctx->run_max : t + budget;
   bool all_done = false;
-  for (; t < max_steps && !all_done; t++) {
+  for (; t < t_end && !all_done; t++) {
     if (ctx->stop.load()) break;  // mfit-walker-estop, :904
     r.t = t;
     rc = eval_all(ctx, ctx->ws, c, c.prop_theta, c.done);
@@ -456,9 +475,23 @@ int run_loop(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long long
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
   collect_timing(ctx);
-  ctx->rows_upper += t;
-  if (steps_launched) *steps_launched = t;
+  ctx->rows_upper += t - ctx->run_t;
+  if (steps_done) *steps_done = t - ctx->run_t;
+  ctx->run_t = t;
+  const bool fin = all_done || t >= ctx->run_max || ctx->stop.load();
+  if (fin) ctx->run_open = false;
+  if (finished) *finished = fin ? 1 : 0;
   return 0;
+}
+
+int run_loop(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long long max_steps, long long* steps_launched) {
+  int rc = run_begin(ctx, r, l_shared_host, max_steps);
+  if (rc) return rc;
+  long long done = 0;
+  rc = run_advance(ctx, -1, &done, nullptr);
+  ctx->run_open = false;
+  if (steps_launched) *steps_launched = done;
+  return rc;
 }
 
 }  // namespace
@@ -874,12 +907,47 @@ int mfit_run_adaptive(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, const double* l_
   MfitRunCfg r;
   int rc = make_cfg(ctx, cfg, r);
   if (rc) return rc;
-  const long long max_steps = r.n > 1 ? r.n - 1 : 0;
+  // i runs 1..n-1, but the shutdown test (:905-917) jumps back to i = n - tail once: n steps when n > tail,
+  // tail steps for 2 <= n <= tail (the jump lands on a non-positive i), none for n < 2
+  const long long max_steps = r.n > 1 ? (r.n > r.tail ? r.n : r.tail) : 0;
   rc = attach_streams(ctx, r, z, u, nstream, max_steps, !cfg->greedy);
   if (rc) return rc;
   long long launched = 0;
   rc = run_loop(ctx, r, l_matrix, max_steps, &launched);
   if (steps_launched) *steps_launched = launched;
+  return rc;
+}
+
+int mfit_run_begin(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, const double* l_matrix, const double* z, const double* u,
+                   int64_t nstream) {
+  if (!ctx || !cfg) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (cfg->n < 0) return fail(ctx, MFIT_ERR_ARG, "n < 0");
+  CU(cudaSetDevice(ctx->device));
+  MfitRunCfg r;
+  int rc = make_cfg(ctx, cfg, r);
+  if (rc) return rc;
+  const long long max_steps = r.n > 1 ? (r.n > r.tail ? r.n : r.tail) : 0;  // see mfit_run_adaptive
+  rc = attach_streams(ctx, r, z, u, nstream, z ? (nstream < max_steps ? nstream : max_steps) : 0, !cfg->greedy);
+  if (rc) return rc;
+  return run_begin(ctx, r, l_matrix, max_steps);
+}
+
+int mfit_run_advance(mfit_ctx* ctx, int64_t max_steps, int64_t* steps_done, int* finished) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->run_cfg.z && ctx->run_t + (max_steps < 0 ? ctx->run_max - ctx->run_t : max_steps) > ctx->run_cfg.nstream &&
+      ctx->run_t + 1 > ctx->run_cfg.nstream)
+    return fail(ctx, MFIT_ERR_STREAM, "injected stream exhausted");
+  long long budget = max_steps;
+  if (ctx->run_cfg.z) {  // never step past the injected stream
+    const long long left = ctx->run_cfg.nstream - ctx->run_t;
+    if (budget < 0 || budget > left) budget = left;
+  }
+  long long done = 0;
+  int rc = run_advance(ctx, budget, &done, finished);
+  if (steps_done) *steps_done = done;
   return rc;
 }
 

@@ -89,6 +89,10 @@ typedef struct {
  * take-step calls inside this call.  NULL => internal PRNG (seeded). */
 int orc_walker_adaptive_steps_full(orc_walker* w, const orc_adapt_cfg* cfg, const double* l_matrix_or_null,
                                    const double* z, const double* u, long nstream, long* steps_taken);
+/* the same loop interrupted after max_steps take-step calls (mfit-walker-estop, :860/:904); -1 = no limit */
+int orc_walker_adaptive_steps_limited(orc_walker* w, const orc_adapt_cfg* cfg, const double* l_matrix_or_null,
+                                      const double* z, const double* u, long nstream, long max_steps,
+                                      long* steps_taken);
 int orc_walker_many_steps(orc_walker* w, long n, const double* l_matrix_or_null,
                           const double* z, const double* u, long nstream);
 int orc_walker_sample_region(orc_walker* w, double initial_scale, const double* z, long nstream);
@@ -108,7 +112,7 @@ int orc_walker_keep_walks(orc_walker* w, long keep);
 /* multi-threaded CPU baseline: W independent walkers sharing one configuration
  * (a template walker is cloned), internal PRNG, returns wall seconds */
 double orc_bench_many(orc_walker* templ, const double* theta0 /* W x P */, long W, const orc_adapt_cfg* cfg,
-                      int n_threads, unsigned long long seed, double* last_prob /* W */);
+                      int n_threads, unsigned long long seed, double* last_prob /* W */, long max_steps);
 
 #ifdef __cplusplus
 }

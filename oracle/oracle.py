@@ -90,6 +90,7 @@ def lib():
         L.orc_walker_logp.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp]
         L.orc_walker_init.argtypes = [C.c_void_p, _dp]
         L.orc_walker_adaptive_steps_full.argtypes = [C.c_void_p, C.POINTER(AdaptCfg), _dp, _dp, _dp, C.c_long, _lp]
+        L.orc_walker_adaptive_steps_limited.argtypes = [C.c_void_p, C.POINTER(AdaptCfg), _dp, _dp, _dp, C.c_long, C.c_long, _lp]
         L.orc_walker_many_steps.argtypes = [C.c_void_p, C.c_long, _dp, _dp, _dp, C.c_long]
         L.orc_walker_sample_region.argtypes = [C.c_void_p, C.c_double, _dp, C.c_long]
         L.orc_walker_force_take_step.argtypes = [C.c_void_p]
@@ -105,7 +106,7 @@ def lib():
         L.orc_walker_acceptance.argtypes = [C.c_void_p, C.c_long, _lp, _lp]
         L.orc_walker_keep_walks.argtypes = [C.c_void_p, C.c_long]
         L.orc_bench_many.restype = C.c_double
-        L.orc_bench_many.argtypes = [C.c_void_p, _dp, C.c_long, C.POINTER(AdaptCfg), C.c_int, C.c_ulonglong, _dp]
+        L.orc_bench_many.argtypes = [C.c_void_p, _dp, C.c_long, C.POINTER(AdaptCfg), C.c_int, C.c_ulonglong, _dp, C.c_long]
         _LIB = L
     return _LIB
 
@@ -265,7 +266,7 @@ class Walker:
         lib().orc_walker_seed(self.h, s)
 
     def adaptive_steps_full(self, n=100000, temperature=1e3, auto=AUTO_NONE, sampling_optimization=OPT_COVARIANCE,
-                            max_walker_length=0, l_matrix=None, z=None, u=None, greedy=False):
+                            max_walker_length=0, l_matrix=None, z=None, u=None, greedy=False, max_steps=-1):
         cfg = AdaptCfg(int(n), float(temperature), auto, sampling_optimization, int(max_walker_length or 0),
                        int(bool(greedy)))
         pl = pz = pu = None
@@ -278,7 +279,8 @@ class Walker:
         if u is not None:
             u, pu = _d(u)
         taken = C.c_long()
-        self._chk(lib().orc_walker_adaptive_steps_full(self.h, C.byref(cfg), pl, pz, pu, nstream, C.byref(taken)))
+        self._chk(lib().orc_walker_adaptive_steps_limited(self.h, C.byref(cfg), pl, pz, pu, nstream, int(max_steps),
+                                                          C.byref(taken)))
         return taken.value
 
     def adaptive_steps(self, n=30000, **kw):
@@ -342,13 +344,14 @@ class Walker:
     def keep_walks(self, keep):
         lib().orc_walker_keep_walks(self.h, keep)
 
-    def bench_many(self, theta0, n_steps, n_threads, seed=1, temperature=10.0):
-        """CPU baseline: W independent copies of this walker, chains split across threads; returns seconds."""
+    def bench_many(self, theta0, n, n_threads, seed=1, temperature=10.0, max_steps=-1):
+        """CPU baseline: W independent copies of this walker run walker-adaptive-steps-full :n n (interrupted after
+        max_steps take-step calls when >= 0), chains split across threads; returns (seconds, last probs)."""
         theta0, p = _d(theta0)
         W = theta0.shape[0]
-        cfg = AdaptCfg(int(n_steps), float(temperature), AUTO_NONE, OPT_COVARIANCE, 0, 0)
+        cfg = AdaptCfg(int(n), float(temperature), AUTO_NONE, OPT_COVARIANCE, 0, 0)
         last = np.zeros(W)
-        secs = lib().orc_bench_many(self.h, p, W, C.byref(cfg), n_threads, seed, last.ctypes.data_as(_dp))
+        secs = lib().orc_bench_many(self.h, p, W, C.byref(cfg), n_threads, seed, last.ctypes.data_as(_dp), int(max_steps))
         return secs, last
 
     def __del__(self):

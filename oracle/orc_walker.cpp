@@ -530,9 +530,10 @@ int orc_walker_init(orc_walker* w, const double* theta0) {
   } catch (std::exception& e) { w->err = e.what(); return -3; }
 }
 
-// walker-adaptive-steps-full :862-942
-int orc_walker_adaptive_steps_full(orc_walker* w, const orc_adapt_cfg* cfg, const double* l_matrix_or_null,
-                                   const double* z, const double* u, long nstream, long* steps_taken) {
+// walker-adaptive-steps-full :862-942.  max_steps >= 0 interrupts the loop after that many take-step calls,
+// like setting mfit-walker-estop (:860, :904) from another thread; -1 = run to the end.
+static int adaptive_impl(orc_walker* w, const orc_adapt_cfg* cfg, const double* l_matrix_or_null, const double* z,
+                         const double* u, long nstream, long max_steps, long* steps_taken) {
   try {
     int P = w->P;
     long n = cfg->n;
@@ -558,6 +559,7 @@ int orc_walker_adaptive_steps_full(orc_walker* w, const orc_adapt_cfg* cfg, cons
       }
     }
     for (long i = 1; i < n; i++) {
+      if (max_steps >= 0 && st.t >= max_steps) break;  // estop
       bool trig = (!shutting && (n - i) < tail);
       if (!trig && cfg->auto_mode != ORC_AUTO_NONE && !shutting && (i % 1000 == 0) && i > 2 * S) {
         long c, len;
@@ -602,6 +604,16 @@ int orc_walker_adaptive_steps_full(orc_walker* w, const orc_adapt_cfg* cfg, cons
     if (steps_taken) *steps_taken = st.t;
     return 0;
   } catch (std::exception& e) { w->err = e.what(); return -3; }
+}
+
+int orc_walker_adaptive_steps_full(orc_walker* w, const orc_adapt_cfg* cfg, const double* l_matrix_or_null,
+                                   const double* z, const double* u, long nstream, long* steps_taken) {
+  return adaptive_impl(w, cfg, l_matrix_or_null, z, u, nstream, -1, steps_taken);
+}
+int orc_walker_adaptive_steps_limited(orc_walker* w, const orc_adapt_cfg* cfg, const double* l_matrix_or_null,
+                                      const double* z, const double* u, long nstream, long max_steps,
+                                      long* steps_taken) {
+  return adaptive_impl(w, cfg, l_matrix_or_null, z, u, nstream, max_steps, steps_taken);
 }
 
 // walker-many-steps :849-853 (constant l-matrix, temperature 1)
@@ -686,7 +698,7 @@ int orc_walker_keep_walks(orc_walker* w, long keep) {
 
 // CPU baseline: W independent walkers, chains split across threads
 double orc_bench_many(orc_walker* templ, const double* theta0, long W, const orc_adapt_cfg* cfg, int n_threads,
-                      unsigned long long seed, double* last_prob) {
+                      unsigned long long seed, double* last_prob, long max_steps) {
   if (n_threads < 1) n_threads = 1;
   auto t0 = std::chrono::steady_clock::now();
   std::vector<std::thread> pool;
@@ -701,7 +713,7 @@ double orc_bench_many(orc_walker* templ, const double* theta0, long W, const orc
         w.rng.seed(seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(c + 1));
         orc_walker_init(&w, theta0 + (size_t)c * w.P);
         long taken = 0;
-        orc_walker_adaptive_steps_full(&w, cfg, nullptr, nullptr, nullptr, 0, &taken);
+        adaptive_impl(&w, cfg, nullptr, nullptr, nullptr, 0, max_steps, &taken);
         if (last_prob) last_prob[c] = w.last.prob;
         for (auto& d : w.ds) { d.fn = nullptr; d.prior_fn = nullptr; }  // owned by the template
       }

@@ -99,7 +99,7 @@ def test_cutoff_clamps_like_reference(orc):
     prob, _, _ = w.make_step(cfg["theta0"])
     ow = oracle_walker(orc, cfg)
     ref = np.array([ow.logp(t)[0] for t in cfg["theta0"]])
-    assert np.any(ref <= -5000.0 * 300)
+    assert np.all(ref <= -5000.0 * 100)   # > 100 points sit on the -5000 floor
     assert rel_err(prob, ref) < TOL
     w.close()
 
