@@ -221,8 +221,8 @@ struct Lower {
   std::map<std::string, std::vector<Ex>> scope;  // name -> stack of bindings
   std::vector<std::string>* block = nullptr;     // statements of the block being emitted
   int tmp = 0;
-  std::set<std::string> helpers;
-  std::string helper_code;
+  bool fast_math = false;  // model lambdas: exp/log/sin/cos -> mfit_math.cuh (prior kernels keep libdevice)
+  int uses = 0;            // MFIT_USES_* tables the lowered code needs
 
   std::string fresh(const char* stem) { return std::string(stem) + std::to_string(tmp++); }
 
@@ -298,11 +298,19 @@ struct Lower {
     }
   }
 
-  Ex irrational(const char* fn, const Ex& a) {
-    if (a.ty == T_BOOL) throw Err(std::string(fn) + " of a boolean");
-    if (a.ty == T_DBL) return mk(T_DBL, std::string(fn) + "(" + a.code + ")");
+  Ex irrational(const char* fn0, const Ex& a) {
+    std::string fn = fn0;
+    if (a.ty == T_BOOL) throw Err(fn + " of a boolean");
+    std::string tail = ")";
+    if (fast_math) {
+      if (fn == "exp") { fn = "mfit_exp_t<SLOW>"; uses |= 1; tail = ", gd)"; }
+      else if (fn == "log") { fn = "mfit_log_t<SLOW>"; uses |= 2; tail = ", gd)"; }
+      else if (fn == "sin") { fn = "mfit_sin_t<SLOW>"; tail = ", gd)"; }
+      else if (fn == "cos") { fn = "mfit_cos_t<SLOW>"; tail = ", gd)"; }
+    }
+    if (a.ty == T_DBL) return mk(T_DBL, fn + "(" + a.code + tail);
     // rational or single argument: computed in double, result is a single-float
-    return mk(T_SGL, "((float)" + std::string(fn) + "(" + as_code(a, T_DBL) + "))");
+    return mk(T_SGL, "((float)" + fn + "(" + as_code(a, T_DBL) + tail + ")");
   }
 
   // exact three-way knowledge about a rational constant c and its double rounding r: sign(r - c)
@@ -741,6 +749,7 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
   }
   std::vector<std::string> pre;  // statements
   L.block = &pre;
+  L.fast_math = kind == 0;
 
   std::vector<std::string> positional;
   bool in_key = false;
@@ -787,10 +796,10 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
   std::string stmts;
   for (auto& sline : pre) stmts += "    " + sline + "\n";
   if (kind == 0) {
-    out += "struct MfitUser {\n" + decls;
+    out += "struct MfitUser {\n  static constexpr int USES = " + std::to_string(L.uses) + ";\n" + decls;
     out += "  __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {\n";
     out += "    const double* theta = a.theta; const long long stride = a.stride;\n    (void)theta; (void)stride; (void)chain;\n" + loads + "  }\n";
-    out += "  __device__ __forceinline__ double eval(double x) const {\n    (void)x;\n" + stmts + "    return " + ret + ";\n  }\n};\n";
+    out += "  template <bool SLOW>\n  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {\n    (void)x; (void)gd;\n" + stmts + "    return " + ret + ";\n  }\n};\n";
   } else {
     out += "__device__ __forceinline__ double mfit_user_prior(const double* theta, long long stride, long long chain) {\n";
     out += "  (void)theta; (void)stride; (void)chain;\n";

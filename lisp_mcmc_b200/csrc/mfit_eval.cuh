@@ -16,11 +16,12 @@
 // added in segment order by the chain kernel, so results do not depend on grid size, SM
 // count or GPU count.
 //
-// The file is freestanding (no #include) because the very same text is embedded in
-// libmfit_cuda.so and handed to NVRTC together with a model struct generated from a user
-// s-expression (csrc/lower.cpp).
+// The file is freestanding (its only #include is mfit_math.cuh, which embed_source.py inlines) because the very
+// same text is embedded in libmfit_cuda.so and handed to NVRTC together with a model struct generated from a
+// user s-expression (csrc/lower.cpp).
 #ifndef MFIT_EVAL_CUH
 #define MFIT_EVAL_CUH
+#include "mfit_math.cuh"
 
 #define MFIT_TILE 512    /* points per shared-memory stage */
 #define MFIT_STAGES 3    /* TMA ring depth */
@@ -96,7 +97,9 @@ struct MfitTerm;
 template <>
 struct MfitTerm<MFITK_NORMAL> {
   static constexpr int NARR = 3;
-  __device__ __forceinline__ static double add(double acc, double f, double y, double w, double) {
+  static constexpr int USES = 0;
+  template <bool SLOW>
+  __device__ __forceinline__ static double add(double acc, double f, double y, double w, double, MfitGuard&) {
     double r = (y - f) * w;
     return fma(r, r, acc);
   }
@@ -105,7 +108,9 @@ struct MfitTerm<MFITK_NORMAL> {
 template <>
 struct MfitTerm<MFITK_CUTOFF> {
   static constexpr int NARR = 4;
-  __device__ __forceinline__ static double add(double acc, double f, double y, double w, double c) {
+  static constexpr int USES = 0;
+  template <bool SLOW>
+  __device__ __forceinline__ static double add(double acc, double f, double y, double w, double c, MfitGuard&) {
     double r = (y - f) * w;
     double t = fma(-0.5 * r, r, c);
     t = (t > -5000.0) ? t : ((t != t) ? t : -5000.0);
@@ -116,10 +121,37 @@ struct MfitTerm<MFITK_CUTOFF> {
 template <>
 struct MfitTerm<MFITK_POISSON> {
   static constexpr int NARR = 2;
-  __device__ __forceinline__ static double add(double acc, double f, double y, double, double) {
-    return acc + fma(y, log(f), -f);
+  static constexpr int USES = MFIT_USES_LOG;
+  template <bool SLOW>
+  __device__ __forceinline__ static double add(double acc, double f, double y, double, double, MfitGuard& gd) {
+    return acc + fma(y, mfit_log_t<SLOW>(f, gd), -f);
   }
 };
+
+// ---------------------------------------------------------------- one data tile, one chain per thread
+// Two points in flight per thread (independent accumulators, fixed order).  SLOW = libdevice math, used only to redo a
+// tile in which a fast routine met an argument outside its domain (see mfit_math.cuh).
+template <class Model, int LL, bool SLOW>
+__device__ __forceinline__ void mfit_tile_pass(const Model& m, const double* xs, const double* ys, const double* ws,
+                                               const double* cs, int cnt, double& acc0, double& acc1, MfitGuard& gd) {
+  const int pairs = cnt >> 1;
+  const double2* x2 = reinterpret_cast<const double2*>(xs);
+  const double2* y2 = reinterpret_cast<const double2*>(ys);
+  const double2* w2 = reinterpret_cast<const double2*>(ws);
+  const double2* c2 = reinterpret_cast<const double2*>(cs);
+#pragma unroll 2
+  for (int i = 0; i < pairs; i++) {
+    const double2 xv = x2[i], yv = y2[i], wv = w2[i], cv = c2[i];
+    const double f0 = m.template eval<SLOW>(xv.x, gd);
+    const double f1 = m.template eval<SLOW>(xv.y, gd);
+    acc0 = MfitTerm<LL>::template add<SLOW>(acc0, f0, yv.x, wv.x, cv.x, gd);
+    acc1 = MfitTerm<LL>::template add<SLOW>(acc1, f1, yv.y, wv.y, cv.y, gd);
+  }
+  if (cnt & 1) {
+    const int i = cnt - 1;
+    acc0 = MfitTerm<LL>::template add<SLOW>(acc0, m.template eval<SLOW>(xs[i], gd), ys[i], ws[i], cs[i], gd);
+  }
+}
 
 // ---------------------------------------------------------------- the kernel body
 template <class Model, int LL>
@@ -138,6 +170,7 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   const bool valid = chain < a.W;
   const long long cl = valid ? chain : (long long)a.W - 1;
   const bool live = valid && !(a.skip != nullptr && a.skip[cl] != 0);
+  mfit_math_stage(Model::USES | MfitTerm<LL>::USES, tid, MFIT_CB);  // exp/log tables -> shared memory
   if (__syncthreads_or(live ? 1 : 0) == 0) return;  // every chain of this block has finished
 
   const long long n_tiles = (a.n + MFIT_TILE - 1) / MFIT_TILE;
@@ -175,6 +208,7 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   m.load(a, cl);
 
   double acc0 = 0.0, acc1 = 0.0;
+  MfitGuard gd;
   for (int k = 0; k < nt; k++) {
     const int s = k % MFIT_STAGES;
     const unsigned ph = (unsigned)(k / MFIT_STAGES) & 1u;
@@ -192,22 +226,13 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
     const double* cs = xs + (NARR > 3 ? 3 : 0) * MFIT_TILE;
     long long rem = a.n - (t0 + k) * (long long)MFIT_TILE;
     const int cnt = rem < MFIT_TILE ? (int)rem : MFIT_TILE;
-    const int pairs = cnt >> 1;
-    const double2* x2 = reinterpret_cast<const double2*>(xs);
-    const double2* y2 = reinterpret_cast<const double2*>(ys);
-    const double2* w2 = reinterpret_cast<const double2*>(ws);
-    const double2* c2 = reinterpret_cast<const double2*>(cs);
-#pragma unroll 2
-    for (int i = 0; i < pairs; i++) {
-      const double2 xv = x2[i], yv = y2[i], wv = w2[i], cv = c2[i];
-      const double f0 = m.eval(xv.x);
-      const double f1 = m.eval(xv.y);
-      acc0 = MfitTerm<LL>::add(acc0, f0, yv.x, wv.x, cv.x);
-      acc1 = MfitTerm<LL>::add(acc1, f1, yv.y, wv.y, cv.y);
-    }
-    if (cnt & 1) {
-      const int i = cnt - 1;
-      acc0 = MfitTerm<LL>::add(acc0, m.eval(xs[i]), ys[i], ws[i], cs[i]);
+    const double save0 = acc0, save1 = acc1;
+    gd.reset();
+    mfit_tile_pass<Model, LL, false>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
+    if (gd.tripped()) {  // rare: overflow / NaN / log of a non-positive number ... -> redo the tile with libdevice math
+      acc0 = save0;
+      acc1 = save1;
+      mfit_tile_pass<Model, LL, true>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
     }
     __syncwarp();
     if ((tid & 31) == 0) mfit_mbar_arrive(&empty[s]);

@@ -1,0 +1,185 @@
+// mfit_math.cuh -- FP64 exp / log / sin / cos built for DFMA-pipe-bound kernels (freestanding, NVRTC-safe).
+//
+// B200 issues one warp-wide DFMA every 2 cycles per SM sub-partition; the likelihood kernels are bound by that
+// pipe (ncu: profiles/), so what matters is the number of FP64 instructions per call, and that the other
+// instructions (integer, LDS, select) stay below one per FP64 instruction so that they hide in the pipe's shadow.
+// CUDA's libdevice spends 22 / 46 / 32 DFMA issue slots on exp / log / sin (measured, mfit_measure_fp64); these
+// spend 10 / 13 / 14 FP64 instructions: table-driven range reduction (Tang) with the tables staged in shared
+// memory, short polynomials with coefficients taken straight from constant memory, exponent arithmetic on the
+// integer pipe.  Accuracy is <= 2.4 ulp (tools/check_math.cpp measures it against long double), far inside the
+// 1e-12 relative tolerance on log-likelihoods.
+//
+// Special values cost nothing on the hot path: every routine has a FAST form that is only valid on its regular
+// domain and records, in a sticky per-thread guard (one integer max per call), whether an argument left that
+// domain; the kernel checks the guard once per data tile and, if it tripped (overflow, NaN, log of a non-positive
+// number, |x| >= 1e5 for sin/cos ...), recomputes that tile with the SLOW forms, which are the libdevice routines.
+// Fast forms are memory-safe for any input (table indices are masked).
+#ifndef MFIT_MATH_CUH
+#define MFIT_MATH_CUH
+
+#ifdef MFIT_HOST_TEST  // tools/check_math.cpp compiles this header for the CPU
+#include <cmath>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+#define __constant__ const
+static inline int mfit_hi(double x) { long long b; memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int mfit_lo(double x) { long long b; memcpy(&b, &x, 8); return (int)b; }
+static inline double mfit_mk(int hi, int lo) {
+  long long b = ((long long)hi << 32) | (unsigned)lo;
+  double x; memcpy(&x, &b, 8); return x;
+}
+static inline unsigned mfit_umax(unsigned a, unsigned b) { return a > b ? a : b; }
+#define MFIT_TAB_EXP mfit_c_exp2
+#define MFIT_TAB_LOG mfit_c_log
+#else
+__device__ __forceinline__ int mfit_hi(double x) { return __double2hiint(x); }
+__device__ __forceinline__ int mfit_lo(double x) { return __double2loint(x); }
+__device__ __forceinline__ double mfit_mk(int hi, int lo) { return __hiloint2double(hi, lo); }
+__device__ __forceinline__ unsigned mfit_umax(unsigned a, unsigned b) { return max(a, b); }
+// shared-memory copies, filled by mfit_math_stage() at kernel start
+__shared__ unsigned long long mfit_s_exp2[64];
+__shared__ double mfit_s_log[256];
+#define MFIT_TAB_EXP mfit_s_exp2
+#define MFIT_TAB_LOG mfit_s_log
+#endif
+
+#include "mfit_math_tables.inc"
+
+#define MFIT_USES_EXP 1
+#define MFIT_USES_LOG 2
+
+#ifndef MFIT_HOST_TEST
+// every thread of the CTA calls this before the first __syncthreads of the kernel
+__device__ __forceinline__ void mfit_math_stage(int uses, int tid, int nthreads) {
+  if (uses & MFIT_USES_EXP)
+    for (int i = tid; i < 64; i += nthreads) mfit_s_exp2[i] = mfit_c_exp2[i];
+  if (uses & MFIT_USES_LOG)
+    for (int i = tid; i < 256; i += nthreads) mfit_s_log[i] = mfit_c_log[i];
+}
+#endif
+
+// sticky record of the most extreme argument each fast routine has seen since reset()
+struct MfitGuard {
+  unsigned e, g, l, s;
+  __device__ __forceinline__ void reset() { e = 0u; g = 0u; l = 0u; s = 0u; }
+  __device__ __forceinline__ bool tripped() const {
+    return e >= 0x40862000u      // exp: |x| >= 708 (overflow / underflow), inf, nan
+        || g >= 0x406ff800u      // gauss: |zs| >= 255.75 (result below 2^-1022), inf, nan
+        || l >= 0x7fe00000u      // log: x <= 0, subnormal, inf, nan   (l tracks hi(x) - 0x00100000 as unsigned)
+        || s >= 0x40f86a00u;     // sin/cos: |x| >= 1e5, inf, nan
+  }
+};
+
+/* 1.5 * 2^52 + 2^31: adding it rounds to an integer k held in the low mantissa word.  The 2^31 bias keeps the low
+ * word free of borrows for |k| < 2^31 and vanishes from every use of k below (k & 63, k << 14, n & 3 are all taken
+ * modulo a power of two that divides 2^31). */
+#define MFIT_MAGIC 6755401588539392.0
+
+// 2^(k/64) for the integer k held (biased) in the low word of tmp = q + MAGIC: table entry (k & 63), exponent
+// k >> 6 added on the integer pipe (the table entries are pre-biased so that a plain k << 14 does both jobs).
+// Three integer instructions and one LDS.64.
+__device__ __forceinline__ double mfit_exp2_64th(double tmp) {
+  const int k = mfit_lo(tmp);
+  const unsigned long long t = MFIT_TAB_EXP[k & 63];
+  return mfit_mk((int)(t >> 32) + (k << 14), (int)t);
+}
+
+// exp(x): 10 FP64 instructions
+template <bool SLOW>
+__device__ __forceinline__ double mfit_exp_t(double x, MfitGuard& gd) {
+  if (SLOW) return exp(x);
+  gd.e = mfit_umax(gd.e, (unsigned)mfit_hi(x) & 0x7fffffffu);
+  const double tmp = fma(x, MFIT_K_L2E64, MFIT_MAGIC);  // x 64/ln2
+  const double kd = tmp - MFIT_MAGIC;
+  double r = fma(kd, -0x1.62e42fef00000p-7, x);         // ln2/64 in two pieces (Cody-Waite); the first is a 32-bit constant
+  r = fma(kd, -0x1.473de6af278edp-40, r);
+  double p = fma(r, MFIT_K_EXN5, MFIT_K_EXN4);
+  p = fma(r, p, MFIT_K_EXN3);
+  p = fma(r, p, 0.5);
+  p = fma(r, p, 1.0);
+  p = fma(r, p, 1.0);
+  return mfit_exp2_64th(tmp) * p;
+}
+
+// exp(-zs^2 ln2/64) = s * p  (zs = z sqrt(32/ln2) turns exp(-z^2/2) into this form): the square is both the argument
+// and, through one FMA each, its rounding to 1/64 octaves and the exact remainder.  8 FP64 instructions; the caller
+// folds the amplitude:  f = fma(a * s, p, rest).
+__device__ __forceinline__ void mfit_gauss_parts(double zs, double* s, double* p, MfitGuard& gd) {
+  gd.g = mfit_umax(gd.g, (unsigned)mfit_hi(zs) & 0x7fffffffu);
+  const double tmp = fma(-zs, zs, MFIT_MAGIC);
+  const double kd = tmp - MFIT_MAGIC;
+  const double r = fma(-zs, zs, -kd);
+  double q = fma(r, MFIT_K_EXS5, MFIT_K_EXS4);
+  q = fma(r, q, MFIT_K_EXS3);
+  q = fma(r, q, MFIT_K_EXS2);
+  q = fma(r, q, MFIT_K_EXS1);
+  *p = fma(r, q, 1.0);
+  *s = mfit_exp2_64th(tmp);
+}
+#define MFIT_GAUSS_ZSCALE 0x1.b2da4e9808a53p+2 /* sqrt(32/ln2) */
+
+// log(x): 13 FP64 instructions.  x = 2^e m with m in [0.707, 1.414); r = m c_i - 1 (one FMA, exact before rounding),
+// log x = e ln2 + L_i + log1p(r); the table intervals next to 1 have c = 1 (1/2) and L = 0 exactly, which keeps full
+// relative accuracy around x = 1.
+template <bool SLOW>
+__device__ __forceinline__ double mfit_log_t(double x, MfitGuard& gd) {
+  if (SLOW) return log(x);
+  const int hx = mfit_hi(x);
+  gd.l = mfit_umax(gd.l, (unsigned)(hx - 0x00100000));
+  const int i = (hx >> 13) & 127;
+  const int e = ((hx + 0x00096000) >> 20) - 1023;  // +1 exactly when i >= 53 (m >= 1.4140625 is halved)
+  const double m = mfit_mk((hx & 0x000fffff) | 0x3ff00000, mfit_lo(x));
+  const double c = MFIT_TAB_LOG[2 * i], L = MFIT_TAB_LOG[2 * i + 1];
+  const double r = fma(m, c, -1.0);
+  const double ed = mfit_mk(0x43300000, e ^ 0x80000000) - 0x1.0000080000000p+52;  // int -> double via the exponent trick
+  const double r2 = r * r;
+  double q = fma(r, MFIT_K_LG8, MFIT_K_LG7);
+  q = fma(r, q, MFIT_K_LG6);
+  q = fma(r, q, MFIT_K_LG5);
+  q = fma(r, q, -0.25);
+  q = fma(r, q, MFIT_K_LG3);
+  q = fma(r, q, -0.5);
+  const double base = fma(ed, 0x1.62e42fef00000p-1, L);  // e ln2_hi is exact (32-bit constant)
+  const double lp = fma(r2, q, r);                        // log1p(r)
+  return fma(ed, 0x1.473de6af278edp-34, lp) + base;       // ln2_lo rides on the small term
+}
+
+// sin and cos share the reduction x = n pi/2 + r (Cody-Waite, three pieces: exact for |n| < 2^20) and the
+// polynomial body; the quadrant picks the coefficient set with selects (integer pipe), not with a branch.
+// 14 FP64 instructions.
+__device__ __forceinline__ double mfit_sincos_core(double x, int quad_shift) {
+  const double tmp = fma(x, MFIT_K_2OPI, MFIT_MAGIC);
+  const double nd = tmp - MFIT_MAGIC;
+  double r = fma(nd, -0x1.921fb54400000p+0, x);
+  r = fma(nd, -0x1.0b4611a600000p-34, r);
+  r = fma(nd, -0x1.3198a2e037073p-69, r);
+  const int n = mfit_lo(tmp) + quad_shift;
+  const bool c = (n & 1) != 0;  // odd quadrant: cosine polynomial
+  const double r2 = r * r;
+  // cos r = 1 + r2 (c2 + r2 (c4 + ... + r2 c16))          sin r = r (1 + r2 (s3 + r2 (s5 + ... + r2 s15)))
+  double q = c ? MFIT_K_CS16 : MFIT_K_SN15;
+  q = fma(r2, q, c ? MFIT_K_CS14 : MFIT_K_SN13);
+  q = fma(r2, q, c ? MFIT_K_CS12 : MFIT_K_SN11);
+  q = fma(r2, q, c ? MFIT_K_CS10 : MFIT_K_SN9);
+  q = fma(r2, q, c ? MFIT_K_CS8 : MFIT_K_SN7);
+  q = fma(r2, q, c ? MFIT_K_CS6 : MFIT_K_SN5);
+  q = fma(r2, q, c ? MFIT_K_CS4 : MFIT_K_SN3);
+  q = fma(r2, q, c ? -0.5 : 1.0);
+  const double res = fma(c ? r2 : r, q, c ? 1.0 : 0.0);
+  return mfit_mk(mfit_hi(res) ^ ((n & 2) << 30), mfit_lo(res));  // quadrants 2, 3: negate
+}
+template <bool SLOW>
+__device__ __forceinline__ double mfit_sin_t(double x, MfitGuard& gd) {
+  if (SLOW) return sin(x);
+  gd.s = mfit_umax(gd.s, (unsigned)mfit_hi(x) & 0x7fffffffu);
+  return mfit_sincos_core(x, 0);
+}
+template <bool SLOW>
+__device__ __forceinline__ double mfit_cos_t(double x, MfitGuard& gd) {
+  if (SLOW) return cos(x);
+  gd.s = mfit_umax(gd.s, (unsigned)mfit_hi(x) & 0x7fffffffu);
+  return mfit_sincos_core(x, 1);
+}
+
+#endif  // MFIT_MATH_CUH

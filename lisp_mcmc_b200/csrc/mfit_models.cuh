@@ -13,12 +13,14 @@
 // f = c0 + x (c1 + x (c2 + ... ))   -- Horner, D FMAs
 template <int D>
 struct MfitPoly {
+  static constexpr int USES = 0;
   double c[D + 1];
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
 #pragma unroll
     for (int k = 0; k <= D; k++) c[k] = MFIT_TH(k);
   }
-  __device__ __forceinline__ double eval(double x) const {
+  template <bool SLOW>
+  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {
     double r = c[D];
 #pragma unroll
     for (int k = D - 1; k >= 0; k--) r = fma(x, r, c[k]);
@@ -28,24 +30,29 @@ struct MfitPoly {
 
 // f = a exp(b x) + c
 struct MfitExpo {
+  static constexpr int USES = MFIT_USES_EXP;
   double a_, b_, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     a_ = MFIT_TH(0); b_ = MFIT_TH(1); c_ = MFIT_TH(2);
   }
-  __device__ __forceinline__ double eval(double x) const { return fma(a_, exp(b_ * x), c_); }
+  template <bool SLOW>
+  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const { return fma(a_, mfit_exp_t<SLOW>(b_ * x, gd), c_); }
 };
 
 // f = a sin(omega x + phi) + c
 struct MfitSinus {
+  static constexpr int USES = 0;
   double a_, om, ph, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     a_ = MFIT_TH(0); om = MFIT_TH(1); ph = MFIT_TH(2); c_ = MFIT_TH(3);
   }
-  __device__ __forceinline__ double eval(double x) const { return fma(a_, sin(fma(om, x, ph)), c_); }
+  template <bool SLOW>
+  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const { return fma(a_, mfit_sin_t<SLOW>(fma(om, x, ph), gd), c_); }
 };
 
 // f = a gamma^2 / ((x - x0)^2 + gamma^2) + c
 struct MfitLorentz {
+  static constexpr int USES = 0;
   double ag2, x0, g2, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     const double g = MFIT_TH(2);
@@ -54,28 +61,39 @@ struct MfitLorentz {
     x0 = MFIT_TH(1);
     c_ = MFIT_TH(3);
   }
-  __device__ __forceinline__ double eval(double x) const {
+  template <bool SLOW>
+  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {
     const double d = x - x0;
     return ag2 / fma(d, d, g2) + c_;
   }
 };
 
-// f = a exp(-((x - mu)/s)^2 / 2) + b0 + b1 x
+// f = a exp(-((x - mu)/s)^2 / 2) + b0 + b1 x.  The Gaussian argument is formed directly in 1/64 octaves
+// (zs = z sqrt(32/ln2), exp(-z^2/2) = 2^(-zs^2/64)), see mfit_gauss_parts: 15 FP64 instructions per point in all.
 struct MfitGaussLin {
-  double a_, mu, is, b0, b1;
+  static constexpr int USES = MFIT_USES_EXP;
+  double a_, mu, is_, isq, b0, b1;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
-    a_ = MFIT_TH(0); mu = MFIT_TH(1); is = 1.0 / MFIT_TH(2); b0 = MFIT_TH(3); b1 = MFIT_TH(4);
+    a_ = MFIT_TH(0); mu = MFIT_TH(1); is_ = 1.0 / MFIT_TH(2); isq = is_ * MFIT_GAUSS_ZSCALE; b0 = MFIT_TH(3); b1 = MFIT_TH(4);
   }
-  __device__ __forceinline__ double eval(double x) const {
-    const double z = (x - mu) * is;
-    const double e = exp(-0.5 * (z * z));
-    return fma(a_, e, fma(b1, x, b0));
+  template <bool SLOW>
+  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {
+    const double d = x - mu;
+    const double lin = fma(b1, x, b0);
+    if (SLOW) {
+      const double z = d * is_;
+      return fma(a_, exp(-0.5 * (z * z)), lin);
+    }
+    double s, p;
+    mfit_gauss_parts(d * isq, &s, &p, gd);
+    return fma(a_ * s, p, lin);
   }
 };
 
 // f = bg0 - sum_k scale_k sigma^2 / ((x - mu_k)^2 + sigma^2);  theta = scale_1..K mu_1..K sigma bg0
 template <int K>
 struct MfitNvMulti {
+  static constexpr int USES = 0;
   double sg[K], mu[K], g2, bg0;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     const double g = MFIT_TH(2 * K);
@@ -84,7 +102,8 @@ struct MfitNvMulti {
 #pragma unroll
     for (int k = 0; k < K; k++) { sg[k] = MFIT_TH(k) * g2; mu[k] = MFIT_TH(K + k); }
   }
-  __device__ __forceinline__ double eval(double x) const {
+  template <bool SLOW>
+  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {
     double r = bg0;
 #pragma unroll
     for (int k = 0; k < K; k++) {

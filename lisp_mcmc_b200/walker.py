@@ -102,26 +102,34 @@ def clean_data(data, n_functions):
 
 
 def clean_data_error(err, data):
-    """clean-data-error :774-805: a scalar, or a short list, is broadcast to the shape of each y using the FIRST
-    value found; a full per-point list is kept.  nil means 1 (:1144)."""
+    """clean-data-error :774-805.  The stddev tree is kept when its structure equals the structure of the y data
+    (one full list per data set); otherwise each data set takes the stddev list if it is flat and as long as that
+    data set's y, and in every other case all its points get the FIRST number found in stddev.  nil means 1 (:1144)."""
     if err is None:
         err = 1.0
+
+    def first_element(t):
+        while isinstance(t, (list, tuple, np.ndarray)):
+            if len(t) == 0:
+                return None
+            t = t[0]
+        return float(t)
+
+    def flat_numbers(t):
+        return isinstance(t, np.ndarray) and t.ndim == 1 or \
+            (isinstance(t, (list, tuple)) and all(np.ndim(v) == 0 for v in t))
+
+    default = first_element(err)
+    ys = [y for _, y in data]
+    if isinstance(err, (list, tuple)) and len(err) == len(ys) and \
+            all(not np.ndim(e) == 0 and flat_numbers(e) and len(e) == len(y) for e, y in zip(err, ys)):
+        return [_f64(e) for e in err]                      # eq-structure with the whole y tree (:800)
     out = []
-    per_set = None
-    if isinstance(err, (list, tuple, np.ndarray)) and get_depth(err) >= 2 and len(err) == len(data):
-        per_set = list(err)
-    for d, (x, y) in enumerate(data):
-        e = per_set[d] if per_set is not None else err
-        if np.ndim(e) == 0:
-            out.append(np.full(y.shape, float(e)))
+    for y in ys:
+        if not np.ndim(err) == 0 and flat_numbers(err) and len(err) == len(y):
+            out.append(_f64(err))                          # eq-structure with this data set's y
         else:
-            e = _f64(e).ravel()
-            if e.shape == y.shape:
-                out.append(e)
-            elif per_set is None and len(data) > 1 and len(e) == len(data):
-                out.append(np.full(y.shape, float(e[d])))
-            else:
-                out.append(np.full(y.shape, float(e[0])))
+            out.append(np.full(y.shape, default))          # every number replaced by the first stddev
     return out
 
 
@@ -168,6 +176,7 @@ class Walker:
         D = len(self.function)
         self.param_keys, p0 = plist(params)                         # :1145
         P = len(self.param_keys)
+        self.P, self.D = P, D
         self.data = clean_data(data, D)                             # :1143
         self.data_error = clean_data_error(data_error, self.data)   # :1144
         ll = log_liklihood if isinstance(log_liklihood, (list, tuple)) else [log_liklihood] * D

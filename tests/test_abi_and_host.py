@@ -1,0 +1,117 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/mfit_cuda.h declares, fails loudly
+without a GPU (no CPU fallback), and the host-side mirror normalises inputs like walker-create does."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from lisp_mcmc_b200 import _lib, families, shard_chains, shard_datasets
+from lisp_mcmc_b200.walker import clean_data, clean_data_error, force_list, get_depth, plist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    txt = open(os.path.join(ROOT, "include", "mfit_cuda.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mfit_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = _header_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), "libmfit_cuda.so does not export %s" % n
+    assert set(names) == set(_lib.SIGNATURES), "ctypes table and header disagree: %s" % (set(names) ^ set(_lib.SIGNATURES))
+    assert L.mfit_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.AdaptCfg) == 40 and C.sizeof(_lib.ChainStats) == 64
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = _lib.lib().mfit_ctx_create(0, None, C.byref(h))
+    assert rc == _lib.ERR_CUDA and not h.value
+    assert b"no CPU fallback" in _lib.lib().mfit_last_error(None)
+    from lisp_mcmc_b200 import walker_create, builtin
+    with pytest.raises(_lib.MfitError):
+        walker_create(function=builtin("poly", degree=1), data=[[0.0, 1.0], [0.0, 1.0]], params=[("c0", 0.0), ("c1", 1.0)])
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "lisp_mcmc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".lisp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "liborc" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_get_depth_and_force_list_docstring_examples():
+    # get-depth :763-764, force-list :755-759
+    assert get_depth([1, 2, 3]) == 1 and get_depth([[1, 2], [3, 4]]) == 2 and get_depth([[[1]]]) == 3
+    assert force_list(3) == [3] and force_list([3, 4]) == [3, 4]
+
+
+def test_clean_data_shapes_and_errors():
+    d = clean_data([[1, 2, 3], [4, 5, 6]], 1)
+    assert len(d) == 1 and d[0][0].dtype == np.float64 and list(d[0][1]) == [4.0, 5.0, 6.0]
+    d2 = clean_data([[[1, 2], [3, 4]], [[5, 6, 7], [8, 9, 10]]], 2)
+    assert len(d2) == 2 and len(d2[1][0]) == 3
+    with pytest.raises(ValueError):
+        clean_data([[1, 2, 3], [4, 5, 6]], 2)        # one data set for two functions (:819)
+    with pytest.raises(ValueError):
+        clean_data([[1, 2, 3], [4, 5]], 1)
+    with pytest.raises(ValueError):
+        clean_data([1, 2, 3], 1)
+
+
+def test_clean_data_error_broadcasts_first_value():
+    data = clean_data([[[1, 2, 3], [4, 5, 6]], [[1, 2], [3, 4]]], 2)
+    e = clean_data_error(0.2, data)                    # scalar -> every point (:776-777)
+    assert [len(v) for v in e] == [3, 2] and np.all(e[0] == 0.2) and np.all(e[1] == 0.2)
+    e = clean_data_error(None, data)                   # nil -> 1 (:1144)
+    assert np.all(e[0] == 1.0)
+    e = clean_data_error([0.1, 0.3], data)             # flat list: fits the 2-point set, first value elsewhere
+    assert np.all(e[0] == 0.1) and list(e[1]) == [0.1, 0.3]
+    e = clean_data_error([[0.1], [0.4]], data)         # docstring example :776-777: structure differs -> first value
+    assert np.all(e[0] == 0.1) and np.all(e[1] == 0.1)
+    e = clean_data_error([[0.1, 0.2, 0.3], [0.5, 0.6]], data)   # full per-point lists are kept
+    assert list(e[0]) == [0.1, 0.2, 0.3] and list(e[1]) == [0.5, 0.6]
+    one = clean_data([[1, 2, 3], [4, 5, 6]], 1)
+    assert np.all(clean_data_error([0.7, 0.9], one)[0] == 0.7)   # short list: the FIRST value is used (:794-805)
+
+
+def test_plist_forms():
+    assert plist([":b", -1, ":m", 2])[0] == ["b", "m"]
+    k, v = plist({"B": -1, "m": 2})
+    assert k == ["b", "m"] and v.dtype == np.float64 and list(v) == [-1.0, 2.0]
+    with pytest.raises(ValueError):
+        plist([":a", 1, ":a", 2])
+    with pytest.raises(ValueError):
+        plist([":a", 1, ":b"])
+
+
+def test_shard_plans():
+    parts = [shard_chains(4099, r, 8) for r in range(8)]
+    assert parts[0][0] == 0 and sum(c for _, c in parts) == 4099
+    assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(7))
+    assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+    assert shard_datasets(8, 8) == list(range(8)) and shard_datasets(5, 2) == [0, 1, 0, 1, 0]
+
+
+def test_family_texts_parse_and_lower():
+    for name, deg in [("poly", 0), ("poly", 7), ("expo", 0), ("sinus", 0), ("lorentz", 0), ("gauss_lin", 0), ("nv_multi", 3)]:
+        keys = families.slots(name, deg)
+        code = _lib.lower_sexpr(families.lisp_text(name, deg), keys)
+        assert "struct MfitUser" in code and "eval(double x, MfitGuard& gd)" in code
