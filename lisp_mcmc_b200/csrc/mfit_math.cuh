@@ -30,6 +30,7 @@ static inline double mfit_mk(int hi, int lo) {
   double x; memcpy(&x, &b, 8); return x;
 }
 static inline unsigned mfit_umax(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 #define MFIT_TAB_EXP mfit_c_exp2
 #define MFIT_TAB_LOG mfit_c_log
 #else
@@ -65,7 +66,7 @@ struct MfitGuard {
   __device__ __forceinline__ void reset() { e = 0u; g = 0u; l = 0u; s = 0u; }
   __device__ __forceinline__ bool tripped() const {
     return e >= 0x40862000u      // exp: |x| >= 708 (overflow / underflow), inf, nan
-        || g >= 0x406ff800u      // gauss: |zs| >= 255.75 (result below 2^-1022), inf, nan
+        || g > 0x7ff00000u       // gauss: nan (underflow and +-inf are clamped in place, see mfit_gauss_parts)
         || l >= 0x7fe00000u      // log: x <= 0, subnormal, inf, nan   (l tracks hi(x) - 0x00100000 as unsigned)
         || s >= 0x40f86a00u;     // sin/cos: |x| >= 1e5, inf, nan
   }
@@ -106,7 +107,12 @@ __device__ __forceinline__ double mfit_exp_t(double x, MfitGuard& gd) {
 // and, through one FMA each, its rounding to 1/64 octaves and the exact remainder.  8 FP64 instructions; the caller
 // folds the amplitude:  f = fma(a * s, p, rest).
 __device__ __forceinline__ void mfit_gauss_parts(double zs, double* s, double* p, MfitGuard& gd) {
-  gd.g = mfit_umax(gd.g, (unsigned)mfit_hi(zs) & 0x7fffffffu);
+  // |zs| is clamped on the integer pipe at 255.875 (exp(-z^2/2) ~ 2^-1023, which the arithmetic below turns into a
+  // subnormal-sized number, i.e. zero next to any amplitude): wild proposals underflow all the time during the
+  // reference's start-up phase (its first l-matrix is diag(theta)), so that case must not leave the fast path.
+  const unsigned ah = (unsigned)mfit_hi(zs) & 0x7fffffffu;
+  gd.g = mfit_umax(gd.g, ah);
+  zs = mfit_mk((int)min(ah, 0x406ffc00u), mfit_lo(zs));
   const double tmp = fma(-zs, zs, MFIT_MAGIC);
   const double kd = tmp - MFIT_MAGIC;
   const double r = fma(-zs, zs, -kd);

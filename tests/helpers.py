@@ -42,6 +42,18 @@ def oracle_walker(orc, cfg, use_builtin_formula=False):
     return ow
 
 
-def rel_err(a, b):
+def rel_err(a, b, scale=0.0):
+    """max |a - b| / max(|b|, scale).  `scale` is the size of the terms that were summed (see ll_scale): a sum that
+    cancels to nearly zero is only defined to 1e-12 of what went into it -- the reference's own sequential sum
+    carries ~sqrt(N) eps of that."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+    return np.max(np.abs(a - b) / np.maximum(np.maximum(np.abs(b), scale), 1e-300))
+
+
+def ll_scale(cfg):
+    """sum_i |-ln(2 pi)/2 - ln sigma_i| over all data sets: the theta-independent half of log-liklihood-normal
+    (mcmc-fitting.lisp:377), against which -sum r^2/2 cancels near the best fit."""
+    D = len(cfg["function"])
+    data = clean_data(cfg["data"] if D > 1 else cfg["data"][0], D)
+    err = clean_data_error(cfg["data_error"], data)
+    return float(sum(np.sum(np.abs(-0.5 * np.log(2 * np.pi) - np.log(e))) for e in err))

@@ -6,7 +6,7 @@ import pytest
 
 from lisp_mcmc_b200 import builtin, families, walker_create, workloads
 from lisp_mcmc_b200 import _lib
-from helpers import oracle_walker, rel_err
+from helpers import ll_scale, oracle_walker, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -198,7 +198,7 @@ def _compare_chain(orc, cfg, w, z, u, run_oracle, chains, bit_exact=True):
         if bit_exact:
             assert np.array_equal(th[c, :n], oth), "chain %d parameter trace differs" % c
             assert np.array_equal(Ls[c], ow.last_l_matrix()), "chain %d final l-matrix differs" % c
-        assert rel_err(pr[c, :n], opr) < TOL
+        assert rel_err(pr[c, :n], opr, ll_scale(cfg)) < TOL
 
 
 def test_many_steps_injected_stream_identical_to_oracle(orc):
