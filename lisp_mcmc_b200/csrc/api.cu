@@ -73,6 +73,7 @@ struct mfit_ctx {
   int D = 0, P = 0;
   std::vector<Dataset> ds;
   int seg_tiles_override = 0;
+  std::map<const void*, int> resident;  // eval kernel -> CTAs resident on the whole device
 
   // chains
   bool have_chains = false;
@@ -265,9 +266,18 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
                                               : mfit_builtin_eval_kernel(s.family, s.degree, s.ll_kind);
   if (!fn) return fail(ctx, MFIT_ERR_STATE, "no kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
   const size_t smem = mfit_eval_smem_bytes(s.ll_kind);
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto it = ctx->resident.find(fn);
+  if (it == ctx->resident.end()) {  // persistent grid = CTAs resident at once (occupancy x SMs), queried once per kernel
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, sms = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MFIT_CB, smem));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (per_sm < 1) per_sm = 1;
+    it = ctx->resident.emplace(fn, per_sm * sms).first;
+  }
   void* args[] = {&a};
-  const unsigned grid = (unsigned)((long long)a.n_cb * a.n_seg);
+  const long long items = (long long)a.n_cb * a.n_seg;
+  const unsigned grid = (unsigned)(items < it->second ? items : it->second);
   CU(cudaLaunchKernel(fn, dim3(grid), dim3(MFIT_CB), args, smem, ctx->stream));
   ctx->launches++;
   return 0;

@@ -6,8 +6,8 @@
 //     ll_d(theta) = sum_i  density(y_i, f(x_i; theta), sigma_i)
 // evaluated for W parameter vectors (chains) at once against shared (x, y, sigma).
 //
-// Work decomposition: one CTA = one chain-block (MFIT_CB chains, one chain per thread) x one
-// segment of the data (tiles_per_seg tiles of MFIT_TILE points).  The data tile is moved
+// Work decomposition: one work item = one chain-block (MFIT_CB chains, one chain per thread) x one
+// segment of the data (tiles_per_seg tiles of MFIT_TILE points); persistent CTAs walk contiguous ranges of items.  The data tile is moved
 // global -> shared by the TMA engine (cp.async.bulk, 1-D) through an MFIT_STAGES-deep
 // mbarrier ring and is read back as warp-uniform (broadcast) 128-bit LDS; theta lives in
 // registers, one chain per lane, so the FP64 pipe sees no cross-lane traffic at all and
@@ -154,6 +154,11 @@ __device__ __forceinline__ void mfit_tile_pass(const Model& m, const double* xs,
 }
 
 // ---------------------------------------------------------------- the kernel body
+// Persistent CTAs: the work items (segment, chain-block) -- chain-block fastest -- are split into gridDim.x
+// contiguous ranges, one per CTA, and the grid is sized to what is resident at once (occupancy x SM count), so there
+// is no wave quantisation and the prologue (mbarriers, math tables) is paid once per CTA.  The TMA ring runs across
+// item boundaries: while the chains of one item are being evaluated the tiles of the next are already in flight, and
+// the next item's parameters are loaded into registers one item ahead.
 template <class Model, int LL>
 __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   constexpr int NARR = MfitTerm<LL>::NARR;
@@ -164,21 +169,18 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   unsigned long long* empty = full + MFIT_STAGES;
 
   const int tid = threadIdx.x;
-  const int cb = blockIdx.x % a.n_cb;   // chain-block fastest: CTAs launched together share a data segment in L2
-  const int seg = blockIdx.x / a.n_cb;
-  const long long chain = (long long)cb * MFIT_CB + tid;
-  const bool valid = chain < a.W;
-  const long long cl = valid ? chain : (long long)a.W - 1;
-  const bool live = valid && !(a.skip != nullptr && a.skip[cl] != 0);
-  mfit_math_stage(Model::USES | MfitTerm<LL>::USES, tid, MFIT_CB);  // exp/log tables -> shared memory
-  if (__syncthreads_or(live ? 1 : 0) == 0) return;  // every chain of this block has finished
-
+  const long long total = (long long)a.n_cb * a.n_seg;
+  const long long item_lo = total * blockIdx.x / gridDim.x;
+  const long long item_hi = total * (blockIdx.x + 1) / gridDim.x;
+  if (item_lo >= item_hi) return;
   const long long n_tiles = (a.n + MFIT_TILE - 1) / MFIT_TILE;
-  const long long t0 = (long long)seg * a.tiles_per_seg;
-  long long t1 = t0 + a.tiles_per_seg;
-  if (t1 > n_tiles) t1 = n_tiles;
-  const int nt = (int)(t1 - t0);
+  auto tiles_of = [&](long long seg) -> int {
+    long long t0 = seg * a.tiles_per_seg, t1 = t0 + a.tiles_per_seg;
+    if (t1 > n_tiles) t1 = n_tiles;
+    return (int)(t1 - t0);
+  };
 
+  mfit_math_stage(Model::USES | MfitTerm<LL>::USES, tid, MFIT_CB);  // exp/log tables -> shared memory
   if (tid == 0) {
     for (int s = 0; s < MFIT_STAGES; s++) {
       mfit_mbar_init(&full[s], 1);
@@ -188,56 +190,75 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   }
   __syncthreads();
 
-  auto issue = [&](int k) {  // tile t0+k -> stage k % STAGES   (thread 0 only)
-    const int s = k % MFIT_STAGES;
-    const long long off = (t0 + k) * (long long)MFIT_TILE;
+  // producer cursor (thread 0 only): next tile to request = tile p_k of item p_item; `issued` counts requests
+  long long p_item = item_lo;
+  int p_k = 0;
+  unsigned issued = 0;
+  auto issue_next = [&]() {
+    const long long seg = p_item / a.n_cb;
+    const int s = (int)(issued % MFIT_STAGES);
+    const long long off = (seg * a.tiles_per_seg + p_k) * (long long)MFIT_TILE;
     double* dst = buf + (size_t)s * NARR * MFIT_TILE;
     mfit_mbar_expect_tx(&full[s], STAGE_BYTES);
     mfit_tma_load_1d(dst, a.x + off, MFIT_TILE * 8u, &full[s]);
     mfit_tma_load_1d(dst + MFIT_TILE, a.y + off, MFIT_TILE * 8u, &full[s]);
     if (NARR > 2) mfit_tma_load_1d(dst + 2 * MFIT_TILE, a.w + off, MFIT_TILE * 8u, &full[s]);
     if (NARR > 3) mfit_tma_load_1d(dst + 3 * MFIT_TILE, a.c + off, MFIT_TILE * 8u, &full[s]);
+    issued++;
+    if (++p_k == tiles_of(seg)) { p_k = 0; p_item++; }
   };
-  if (tid == 0) {
-    const int pre = nt < MFIT_STAGES ? nt : MFIT_STAGES;
-    for (int k = 0; k < pre; k++) issue(k);
-  }
+  if (tid == 0)
+    for (int s = 0; s < MFIT_STAGES && p_item < item_hi; s++) issue_next();
 
-  // theta -> registers while the first tiles are in flight
-  Model m;
-  m.load(a, cl);
+  auto chain_of = [&](long long item) -> long long { return (item % a.n_cb) * MFIT_CB + tid; };
+  auto clamp_chain = [&](long long ch) -> long long { return ch < a.W ? ch : (long long)a.W - 1; };
 
-  double acc0 = 0.0, acc1 = 0.0;
+  Model m_next;
+  m_next.load(a, clamp_chain(chain_of(item_lo)));  // parameters of the first item, while its tiles are in flight
+  unsigned consumed = 0;
   MfitGuard gd;
-  for (int k = 0; k < nt; k++) {
-    const int s = k % MFIT_STAGES;
-    const unsigned ph = (unsigned)(k / MFIT_STAGES) & 1u;
-    // refill the stage freed one tile ago (gives the other warps a tile of slack)
-    if (tid == 0 && k >= 1 && k - 1 + MFIT_STAGES < nt) {
-      const int sp = (k - 1) % MFIT_STAGES;
-      mfit_mbar_wait(&empty[sp], (unsigned)((k - 1) / MFIT_STAGES) & 1u);
-      issue(k - 1 + MFIT_STAGES);
+  for (long long item = item_lo; item < item_hi; item++) {
+    const long long seg = item / a.n_cb;
+    const long long chain = chain_of(item);
+    const bool valid = chain < a.W;
+    const long long cl = clamp_chain(chain);
+    const bool live = valid && !(a.skip != nullptr && a.skip[cl] != 0);
+    const bool any_live = __syncthreads_or(live ? 1 : 0) != 0;  // a finished chain-block only drains its tiles
+    const Model m = m_next;
+    if (item + 1 < item_hi) m_next.load(a, clamp_chain(chain_of(item + 1)));
+    const int nt = tiles_of(seg);
+    const long long t0 = seg * a.tiles_per_seg;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int k = 0; k < nt; k++, consumed++) {
+      const int s = (int)(consumed % MFIT_STAGES);
+      // refill the stage freed one tile ago (gives the other warps a tile of slack)
+      if (tid == 0 && consumed >= 1 && p_item < item_hi) {
+        const unsigned c1 = consumed - 1;
+        mfit_mbar_wait(&empty[c1 % MFIT_STAGES], (c1 / MFIT_STAGES) & 1u);
+        issue_next();
+      }
+      mfit_mbar_wait(&full[s], (consumed / MFIT_STAGES) & 1u);
+      if (any_live) {
+        const double* xs = buf + (size_t)s * NARR * MFIT_TILE;
+        const double* ys = xs + MFIT_TILE;
+        const double* ws = xs + (NARR > 2 ? 2 : 0) * MFIT_TILE;
+        const double* cs = xs + (NARR > 3 ? 3 : 0) * MFIT_TILE;
+        long long rem = a.n - (t0 + k) * (long long)MFIT_TILE;
+        const int cnt = rem < MFIT_TILE ? (int)rem : MFIT_TILE;
+        const double save0 = acc0, save1 = acc1;
+        gd.reset();
+        mfit_tile_pass<Model, LL, false>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
+        if (gd.tripped()) {  // rare: overflow / NaN / log of a non-positive number ... -> redo the tile with libdevice math
+          acc0 = save0;
+          acc1 = save1;
+          mfit_tile_pass<Model, LL, true>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) mfit_mbar_arrive(&empty[s]);
     }
-    mfit_mbar_wait(&full[s], ph);
-
-    const double* xs = buf + (size_t)s * NARR * MFIT_TILE;
-    const double* ys = xs + MFIT_TILE;
-    const double* ws = xs + (NARR > 2 ? 2 : 0) * MFIT_TILE;
-    const double* cs = xs + (NARR > 3 ? 3 : 0) * MFIT_TILE;
-    long long rem = a.n - (t0 + k) * (long long)MFIT_TILE;
-    const int cnt = rem < MFIT_TILE ? (int)rem : MFIT_TILE;
-    const double save0 = acc0, save1 = acc1;
-    gd.reset();
-    mfit_tile_pass<Model, LL, false>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
-    if (gd.tripped()) {  // rare: overflow / NaN / log of a non-positive number ... -> redo the tile with libdevice math
-      acc0 = save0;
-      acc1 = save1;
-      mfit_tile_pass<Model, LL, true>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
-    }
-    __syncwarp();
-    if ((tid & 31) == 0) mfit_mbar_arrive(&empty[s]);
+    if (live) a.partial[(size_t)seg * a.stride + chain] = acc0 + acc1;
   }
-  if (live) a.partial[(size_t)seg * a.stride + chain] = acc0 + acc1;
 }
 
 #endif  // MFIT_EVAL_CUH

@@ -182,23 +182,43 @@ def test_nv_prior_sexpr_and_global_fit(orc):
 
 
 def _compare_chain(orc, cfg, w, z, u, run_oracle, chains, bit_exact=True):
+    """Same injected streams through the GPU and through the oracle: the parameter traces must be bit-identical and the
+    log-probabilities within TOL -- until, at most, a decision whose |delta log p| is itself below the tolerance
+    (north_star: "identical accept/reject sequences ... except where |delta log p| falls below that tolerance"), after
+    which the two chains legitimately part ways (the greedy sampler of walker-sample-region shrinks its steps until
+    every proposal is such a coin toss)."""
     th, pr, nv = w.trace(int(w.stats()["length"].max()))
     Ls = w.l_matrix()
     ow = oracle_walker(orc, cfg)
+    scale = ll_scale(cfg)
+    compared = 0
     for c in chains:
         ow.init(cfg["theta0"][c])
         run_oracle(ow, z[c], u[c] if u is not None else None)
         oth, opr = ow.trace(0)
         n = len(opr)
         assert nv[c] == n, "chain %d took %d steps, oracle %d" % (c, nv[c], n)
-        # identical accept/reject sequence <=> identical runs of repeated rows
-        acc_g = (pr[c, :n - 1] != pr[c, 1:n])
-        acc_o = (opr[:-1] != opr[1:])
-        assert np.array_equal(acc_g, acc_o), "chain %d accept/reject sequence differs" % c
-        if bit_exact:
-            assert np.array_equal(th[c, :n], oth), "chain %d parameter trace differs" % c
-            assert np.array_equal(Ls[c], ow.last_l_matrix()), "chain %d final l-matrix differs" % c
-        assert rel_err(pr[c, :n], opr, ll_scale(cfg)) < TOL
+        g_th, g_pr = th[c, :n][::-1], pr[c, :n][::-1]      # oldest first
+        o_th, o_pr = oth[::-1], opr[::-1]
+        same = np.all(g_th == o_th, axis=1)
+        first = n if same.all() else int(np.argmin(same))
+        assert rel_err(g_pr[:first], o_pr[:first], scale) < TOL
+        compared += first
+        if first == n:
+            if bit_exact:
+                assert np.array_equal(Ls[c], ow.last_l_matrix()), "chain %d final l-matrix differs" % c
+            continue
+        # the step at which they part: one side accepted the (bit-identical) proposal, the other kept the old state
+        assert first >= 1
+        prev_same_g = np.array_equal(g_th[first], g_th[first - 1])
+        prev_same_o = np.array_equal(o_th[first], o_th[first - 1])
+        assert prev_same_g != prev_same_o, "chain %d step %d: traces differ by more than one decision" % (c, first)
+        proposal = o_th[first] if prev_same_g else g_th[first]
+        p1 = ow.logp(proposal)[0]
+        p0 = o_pr[first - 1]
+        assert abs(p1 - p0) <= 4 * TOL * max(abs(p0), scale), \
+            "chain %d step %d: decisions differ although |delta log p| = %g is above the tolerance" % (c, first, abs(p1 - p0))
+    return compared
 
 
 def test_many_steps_injected_stream_identical_to_oracle(orc):
@@ -209,7 +229,8 @@ def test_many_steps_injected_stream_identical_to_oracle(orc):
     z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
     Lm = np.diag(0.004 * np.abs(cfg["theta_star"])) + 1e-4 * np.tril(np.ones((w.P, w.P)), -1)
     w.many_steps(n, Lm, z=z, u=u)
-    _compare_chain(orc, cfg, w, z, u, lambda ow, zz, uu: ow.many_steps(n, Lm, z=zz, u=uu), range(0, 40, 3))
+    done = _compare_chain(orc, cfg, w, z, u, lambda ow, zz, uu: ow.many_steps(n, Lm, z=zz, u=uu), range(0, 40, 3))
+    assert done == 14 * (n + 1)      # nothing borderline here: every step of every compared chain matched
     w.close()
 
 
@@ -255,7 +276,8 @@ def test_sample_region_and_force_take_step(orc):
     def run(ow, zz, uu):
         ow.sample_region(1e-3, z=zz)
         ow.force_take_step()
-    _compare_chain(orc, cfg, w, z, None, run, range(5))
+    done = _compare_chain(orc, cfg, w, z, None, run, range(5))
+    assert done > 5 * 200   # the chains agree bit for bit until the sampler has shrunk its steps into the noise
     st = w.stats()
     assert np.all(st["length"] == 1 + 2999 + 1) and np.all(st["age"] == st["length"])
     w.close()
