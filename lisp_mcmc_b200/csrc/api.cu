@@ -32,7 +32,8 @@ std::string g_create_error;
 
 struct Dataset {
   long long n = -1, n_pad = 0;
-  double *x = nullptr, *y = nullptr, *w = nullptr, *c = nullptr;
+  double *x = nullptr, *y = nullptr, *yw = nullptr, *w = nullptr, *c = nullptr;
+  double xmin = 0.0, xmax = 0.0;  // -inf / +inf when some x is not finite
   double cst_normal = 0.0, cst_poisson = 0.0;
   bool poisson_ok = false;
   int family = -1, degree = 0;
@@ -143,8 +144,8 @@ long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 void free_dev(void* p) { if (p) cudaFree(p); }
 
 void dataset_free_data(Dataset& d) {
-  free_dev(d.x); free_dev(d.y); free_dev(d.w); free_dev(d.c);
-  d.x = d.y = d.w = d.c = nullptr;
+  free_dev(d.x); free_dev(d.y); free_dev(d.yw); free_dev(d.w); free_dev(d.c);
+  d.x = d.y = d.yw = d.w = d.c = nullptr;
   d.n = -1;
 }
 void dataset_free_prior(Dataset& d) {
@@ -250,8 +251,10 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
   if (s.n == 0 || s.n_seg == 0) return 0;
   MfitEvalArgs a;
   memset(&a, 0, sizeof a);
-  a.x = s.x; a.y = s.y; a.w = s.w; a.c = s.c;
+  a.x = s.x; a.y = s.y; a.yw = s.yw; a.w = s.w; a.c = s.c;
   a.n = s.n;
+  a.xmin = s.xmin;
+  a.xmax = s.xmax;
   a.tiles_per_seg = s.tiles_per_seg;
   a.n_seg = s.n_seg;
   a.n_cb = (int)(w.stride / MFIT_CB);
@@ -268,7 +271,8 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
   const size_t smem = mfit_eval_smem_bytes(s.ll_kind);
   auto it = ctx->resident.find(fn);
   if (it == ctx->resident.end()) {  // persistent grid = CTAs resident at once (occupancy x SMs), queried once per kernel
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // static (math tables) + dynamic (TMA ring) shared memory may exceed the 48 KB default together
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MFIT_CB, smem));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -597,7 +601,10 @@ int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, 
   dataset_free_data(s);
   s.n = n;
   s.n_pad = round_up(n > 0 ? n : 1, MFIT_TILE);
-  std::vector<double> w((size_t)s.n_pad, 0.0), cc((size_t)s.n_pad, 0.0), xx((size_t)s.n_pad, 0.0), yy((size_t)s.n_pad, 0.0);
+  std::vector<double> w((size_t)s.n_pad, 0.0), cc((size_t)s.n_pad, 0.0), xx((size_t)s.n_pad, 0.0), yy((size_t)s.n_pad, 0.0),
+      yw((size_t)s.n_pad, 0.0);
+  double xmin = INFINITY, xmax = -INFINITY;
+  bool x_finite = true;
   const double a = -0.5 * std::log(2.0 * 3.141592653589793);  // (* -1/2 (log (* 2 pi))) :377
   double cst = 0.0;
   bool pois_ok = true;
@@ -608,6 +615,10 @@ int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, 
     xx[i] = x[i];
     yy[i] = y[i];
     w[i] = 1.0 / sg;
+    yw[i] = y[i] * w[i];
+    if (!std::isfinite(x[i])) x_finite = false;
+    if (x[i] < xmin) xmin = x[i];
+    if (x[i] > xmax) xmax = x[i];
     const double ci = a + (-1.0 * std::log(sg));
     cc[i] = ci;
     cst = i == 0 ? ci : cst + ci;
@@ -620,13 +631,17 @@ int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, 
       }
     }
   }
+  s.xmin = x_finite && n > 0 ? xmin : -INFINITY;
+  s.xmax = x_finite && n > 0 ? xmax : INFINITY;
   s.cst_normal = cst;
   s.cst_poisson = pcst;
   s.poisson_ok = pois_ok;
   const size_t bytes = sizeof(double) * (size_t)s.n_pad;
-  CU(cudaMalloc(&s.x, bytes)); CU(cudaMalloc(&s.y, bytes)); CU(cudaMalloc(&s.w, bytes)); CU(cudaMalloc(&s.c, bytes));
+  CU(cudaMalloc(&s.x, bytes)); CU(cudaMalloc(&s.y, bytes)); CU(cudaMalloc(&s.yw, bytes)); CU(cudaMalloc(&s.w, bytes));
+  CU(cudaMalloc(&s.c, bytes));
   CU(cudaMemcpyAsync(s.x, xx.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(s.y, yy.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.yw, yw.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(s.w, w.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(s.c, cc.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));

@@ -223,6 +223,7 @@ struct Lower {
   int tmp = 0;
   bool fast_math = false;  // model lambdas: exp/log/sin/cos -> mfit_math.cuh (prior kernels keep libdevice)
   int uses = 0;            // MFIT_USES_* tables the lowered code needs
+  bool guarded = false;    // some fast routine with a restricted domain is called
 
   std::string fresh(const char* stem) { return std::string(stem) + std::to_string(tmp++); }
 
@@ -303,10 +304,10 @@ struct Lower {
     if (a.ty == T_BOOL) throw Err(fn + " of a boolean");
     std::string tail = ")";
     if (fast_math) {
-      if (fn == "exp") { fn = "mfit_exp_t<SLOW>"; uses |= 1; tail = ", gd)"; }
-      else if (fn == "log") { fn = "mfit_log_t<SLOW>"; uses |= 2; tail = ", gd)"; }
-      else if (fn == "sin") { fn = "mfit_sin_t<SLOW>"; tail = ", gd)"; }
-      else if (fn == "cos") { fn = "mfit_cos_t<SLOW>"; tail = ", gd)"; }
+      if (fn == "exp") { fn = "mfit_exp_t<SLOW>"; uses |= 1; guarded = true; tail = ", gd)"; }
+      else if (fn == "log") { fn = "mfit_log_t<SLOW>"; uses |= 2; guarded = true; tail = ", gd)"; }
+      else if (fn == "sin") { fn = "mfit_sin_t<SLOW>"; guarded = true; tail = ", gd)"; }
+      else if (fn == "cos") { fn = "mfit_cos_t<SLOW>"; guarded = true; tail = ", gd)"; }
     }
     if (a.ty == T_DBL) return mk(T_DBL, fn + "(" + a.code + tail);
     // rational or single argument: computed in double, result is a single-float
@@ -796,10 +797,14 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
   std::string stmts;
   for (auto& sline : pre) stmts += "    " + sline + "\n";
   if (kind == 0) {
-    out += "struct MfitUser {\n  static constexpr int USES = " + std::to_string(L.uses) + ";\n" + decls;
+    // a user model carries no proof about its arguments (safe() is false): its fast routines always run guarded
+    out += "struct MfitUser {\n  static constexpr int USES = " + std::to_string(L.uses) + ";\n";
+    out += std::string("  static constexpr bool GUARDED = ") + (L.guarded ? "true" : "false") + ";\n" + decls;
     out += "  __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {\n";
     out += "    const double* theta = a.theta; const long long stride = a.stride;\n    (void)theta; (void)stride; (void)chain;\n" + loads + "  }\n";
-    out += "  template <bool SLOW>\n  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {\n    (void)x; (void)gd;\n" + stmts + "    return " + ret + ";\n  }\n};\n";
+    out += "  __device__ __forceinline__ void setup() {}\n";
+    out += "  __device__ __forceinline__ bool safe(const MfitEvalArgs&) const { return false; }\n";
+    out += "  template <bool SLOW, class G>\n  __device__ __forceinline__ double eval(double x, G& gd) const {\n    (void)x; (void)gd;\n" + stmts + "    return " + ret + ";\n  }\n};\n";
   } else {
     out += "__device__ __forceinline__ double mfit_user_prior(const double* theta, long long stride, long long chain) {\n";
     out += "  (void)theta; (void)stride; (void)chain;\n";

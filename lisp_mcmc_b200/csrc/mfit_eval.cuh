@@ -34,10 +34,12 @@
 
 struct MfitEvalArgs {
   const double* x;      /* [n_pad] */
-  const double* y;      /* [n_pad] */
+  const double* y;      /* [n_pad]                      (cutoff, poisson) */
+  const double* yw;     /* [n_pad] y_i/sigma_i          (normal) */
   const double* w;      /* [n_pad] 1/sigma_i            (normal, cutoff) */
   const double* c;      /* [n_pad] -ln(2pi)/2 - ln sigma_i  (cutoff only) */
   long long n;          /* valid points */
+  double xmin, xmax;    /* range of x over the data set (-inf, +inf when some x is not finite): Model::safe */
   int tiles_per_seg;
   int n_seg;
   int n_cb;             /* chain blocks */
@@ -93,14 +95,15 @@ template <int LL>
 struct MfitTerm;
 
 // log-normal :372-377 with the theta-independent part hoisted: the kernel accumulates
-// sum r^2, r = (y - f)/sigma; the chain kernel forms  C_d - sum/2.
+// sum r^2, r = (y - f)/sigma = y/sigma - f/sigma with y/sigma precomputed at upload (two FP64 instructions per
+// point); the chain kernel forms  C_d - sum/2.
 template <>
 struct MfitTerm<MFITK_NORMAL> {
   static constexpr int NARR = 3;
   static constexpr int USES = 0;
-  template <bool SLOW>
-  __device__ __forceinline__ static double add(double acc, double f, double y, double w, double, MfitGuard&) {
-    double r = (y - f) * w;
+  template <bool SLOW, class G>
+  __device__ __forceinline__ static double add(double acc, double f, double yw, double w, double, G&) {
+    double r = fma(-f, w, yw);
     return fma(r, r, acc);
   }
 };
@@ -109,8 +112,8 @@ template <>
 struct MfitTerm<MFITK_CUTOFF> {
   static constexpr int NARR = 4;
   static constexpr int USES = 0;
-  template <bool SLOW>
-  __device__ __forceinline__ static double add(double acc, double f, double y, double w, double c, MfitGuard&) {
+  template <bool SLOW, class G>
+  __device__ __forceinline__ static double add(double acc, double f, double y, double w, double c, G&) {
     double r = (y - f) * w;
     double t = fma(-0.5 * r, r, c);
     t = (t > -5000.0) ? t : ((t != t) ? t : -5000.0);
@@ -122,24 +125,29 @@ template <>
 struct MfitTerm<MFITK_POISSON> {
   static constexpr int NARR = 2;
   static constexpr int USES = MFIT_USES_LOG;
-  template <bool SLOW>
-  __device__ __forceinline__ static double add(double acc, double f, double y, double, double, MfitGuard& gd) {
+  template <bool SLOW, class G>
+  __device__ __forceinline__ static double add(double acc, double f, double y, double, double, G& gd) {
     return acc + fma(y, mfit_log_t<SLOW>(f, gd), -f);
   }
 };
 
 // ---------------------------------------------------------------- one data tile, one chain per thread
-// Two points in flight per thread (independent accumulators, fixed order).  SLOW = libdevice math, used only to redo a
-// tile in which a fast routine met an argument outside its domain (see mfit_math.cuh).
-template <class Model, int LL, bool SLOW>
+// MFIT_UNROLL_PAIRS pairs of points in flight per thread (two independent accumulators, fixed order).  SLOW = libdevice
+// math, used only to redo a tile in which a fast routine met an argument outside its domain (see mfit_math.cuh);
+// G = MfitGuard records such arguments, MfitNoGuard is for chains whose Model::safe() has ruled them out.
+#ifndef MFIT_UNROLL_PAIRS
+#define MFIT_UNROLL_PAIRS 4
+#endif
+template <class Model, int LL, bool SLOW, class G>
 __device__ __forceinline__ void mfit_tile_pass(const Model& m, const double* xs, const double* ys, const double* ws,
-                                               const double* cs, int cnt, double& acc0, double& acc1, MfitGuard& gd) {
+                                               const double* cs, int cnt, double& acc0, double& acc1, G& gd) {
   const int pairs = cnt >> 1;
   const double2* x2 = reinterpret_cast<const double2*>(xs);
   const double2* y2 = reinterpret_cast<const double2*>(ys);
   const double2* w2 = reinterpret_cast<const double2*>(ws);
   const double2* c2 = reinterpret_cast<const double2*>(cs);
-#pragma unroll 2
+  constexpr int UNROLL = MFIT_UNROLL_PAIRS;
+#pragma unroll UNROLL
   for (int i = 0; i < pairs; i++) {
     const double2 xv = x2[i], yv = y2[i], wv = w2[i], cv = c2[i];
     const double f0 = m.template eval<SLOW>(xv.x, gd);
@@ -201,7 +209,7 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
     double* dst = buf + (size_t)s * NARR * MFIT_TILE;
     mfit_mbar_expect_tx(&full[s], STAGE_BYTES);
     mfit_tma_load_1d(dst, a.x + off, MFIT_TILE * 8u, &full[s]);
-    mfit_tma_load_1d(dst + MFIT_TILE, a.y + off, MFIT_TILE * 8u, &full[s]);
+    mfit_tma_load_1d(dst + MFIT_TILE, (LL == MFITK_NORMAL ? a.yw : a.y) + off, MFIT_TILE * 8u, &full[s]);
     if (NARR > 2) mfit_tma_load_1d(dst + 2 * MFIT_TILE, a.w + off, MFIT_TILE * 8u, &full[s]);
     if (NARR > 3) mfit_tma_load_1d(dst + 3 * MFIT_TILE, a.c + off, MFIT_TILE * 8u, &full[s]);
     issued++;
@@ -213,10 +221,11 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   auto chain_of = [&](long long item) -> long long { return (item % a.n_cb) * MFIT_CB + tid; };
   auto clamp_chain = [&](long long ch) -> long long { return ch < a.W ? ch : (long long)a.W - 1; };
 
+  // GUARDED: some fast routine on the path has a restricted domain (transcendentals of the model, log of log-poisson)
+  constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
   Model m_next;
   m_next.load(a, clamp_chain(chain_of(item_lo)));  // parameters of the first item, while its tiles are in flight
   unsigned consumed = 0;
-  MfitGuard gd;
   for (long long item = item_lo; item < item_hi; item++) {
     const long long seg = item / a.n_cb;
     const long long chain = chain_of(item);
@@ -224,8 +233,11 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
     const long long cl = clamp_chain(chain);
     const bool live = valid && !(a.skip != nullptr && a.skip[cl] != 0);
     const bool any_live = __syncthreads_or(live ? 1 : 0) != 0;  // a finished chain-block only drains its tiles
-    const Model m = m_next;
+    Model m = m_next;
     if (item + 1 < item_hi) m_next.load(a, clamp_chain(chain_of(item + 1)));
+    m.setup();  // theta-only subexpressions
+    // warp-uniform: every chain of this warp stays inside the fast domain over the whole x range of the data set
+    const bool unguarded = !GUARDED || (MfitTerm<LL>::USES == 0 && __all_sync(0xffffffffu, m.safe(a) ? 1 : 0) != 0);
     const int nt = tiles_of(seg);
     const long long t0 = seg * a.tiles_per_seg;
     double acc0 = 0.0, acc1 = 0.0;
@@ -245,13 +257,19 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
         const double* cs = xs + (NARR > 3 ? 3 : 0) * MFIT_TILE;
         long long rem = a.n - (t0 + k) * (long long)MFIT_TILE;
         const int cnt = rem < MFIT_TILE ? (int)rem : MFIT_TILE;
-        const double save0 = acc0, save1 = acc1;
-        gd.reset();
-        mfit_tile_pass<Model, LL, false>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
-        if (gd.tripped()) {  // rare: overflow / NaN / log of a non-positive number ... -> redo the tile with libdevice math
-          acc0 = save0;
-          acc1 = save1;
-          mfit_tile_pass<Model, LL, true>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
+        if (unguarded) {
+          MfitNoGuard ng;
+          mfit_tile_pass<Model, LL, false>(m, xs, ys, ws, cs, cnt, acc0, acc1, ng);
+        } else {
+          const double save0 = acc0, save1 = acc1;
+          MfitGuard gd;
+          gd.reset();
+          mfit_tile_pass<Model, LL, false>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
+          if (gd.tripped()) {  // rare: overflow / NaN / log of a non-positive number ... -> redo the tile with libdevice math
+            acc0 = save0;
+            acc1 = save1;
+            mfit_tile_pass<Model, LL, true>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
+          }
         }
       }
       __syncwarp();

@@ -31,18 +31,18 @@ static inline double mfit_mk(int hi, int lo) {
 }
 static inline unsigned mfit_umax(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
-#define MFIT_TAB_EXP mfit_c_exp2
-#define MFIT_TAB_LOG mfit_c_log
 #else
 __device__ __forceinline__ int mfit_hi(double x) { return __double2hiint(x); }
 __device__ __forceinline__ int mfit_lo(double x) { return __double2loint(x); }
 __device__ __forceinline__ double mfit_mk(int hi, int lo) { return __hiloint2double(hi, lo); }
 __device__ __forceinline__ unsigned mfit_umax(unsigned a, unsigned b) { return max(a, b); }
-// shared-memory copies, filled by mfit_math_stage() at kernel start
-__shared__ unsigned long long mfit_s_exp2[64];
-__shared__ double mfit_s_log[256];
-#define MFIT_TAB_EXP mfit_s_exp2
-#define MFIT_TAB_LOG mfit_s_log
+// Shared-memory copies, filled by mfit_math_stage() at kernel start.  Table indices differ from lane to lane, so a
+// plain copy would serialise on bank conflicts (ncu, profiles/: 2.8 extra wavefronts per exp, the shared-memory
+// crossbar ran at 62 % next to a 68 % FP64 pipe).  Each table is therefore replicated so that every lane of a
+// crossbar phase reads its own banks: 16 copies of the 8-byte exp entries (a 64-bit load is served in two phases of
+// 16 lanes), 8 copies of the 16-byte log entries (four phases of 8 lanes).  Entry j of copy c sits at [j][c].
+__shared__ __align__(16) unsigned long long mfit_s_exp2[64 * 16];
+__shared__ __align__(16) double mfit_s_log[128 * 8 * 2];
 #endif
 
 #include "mfit_math_tables.inc"
@@ -54,22 +54,42 @@ __shared__ double mfit_s_log[256];
 // every thread of the CTA calls this before the first __syncthreads of the kernel
 __device__ __forceinline__ void mfit_math_stage(int uses, int tid, int nthreads) {
   if (uses & MFIT_USES_EXP)
-    for (int i = tid; i < 64; i += nthreads) mfit_s_exp2[i] = mfit_c_exp2[i];
+    for (int i = tid; i < 64 * 16; i += nthreads) mfit_s_exp2[i] = mfit_c_exp2[i >> 4];
   if (uses & MFIT_USES_LOG)
-    for (int i = tid; i < 256; i += nthreads) mfit_s_log[i] = mfit_c_log[i];
+    for (int i = tid; i < 128 * 8; i += nthreads) {
+      mfit_s_log[2 * i] = mfit_c_log[2 * (i >> 3)];
+      mfit_s_log[2 * i + 1] = mfit_c_log[2 * (i >> 3) + 1];
+    }
 }
 #endif
 
 // sticky record of the most extreme argument each fast routine has seen since reset()
 struct MfitGuard {
+  static constexpr bool ON = true;
   unsigned e, g, l, s;
   __device__ __forceinline__ void reset() { e = 0u; g = 0u; l = 0u; s = 0u; }
+  __device__ __forceinline__ void see_exp(unsigned v) { e = mfit_umax(e, v); }
+  __device__ __forceinline__ void see_gauss(unsigned v) { g = mfit_umax(g, v); }
+  __device__ __forceinline__ void see_log(unsigned v) { l = mfit_umax(l, v); }
+  __device__ __forceinline__ void see_sin(unsigned v) { s = mfit_umax(s, v); }
   __device__ __forceinline__ bool tripped() const {
     return e >= 0x40862000u      // exp: |x| >= 708 (overflow / underflow), inf, nan
         || g > 0x7ff00000u       // gauss: nan (underflow and +-inf are clamped in place, see mfit_gauss_parts)
         || l >= 0x7fe00000u      // log: x <= 0, subnormal, inf, nan   (l tracks hi(x) - 0x00100000 as unsigned)
         || s >= 0x40f86a00u;     // sin/cos: |x| >= 1e5, inf, nan
   }
+};
+// The same interface with nothing behind it: used when a model has proved, from its parameters and the x range of
+// the data set (Model::safe), that no argument can leave the fast domain -- the guard and clamp instructions
+// (two to three integer-pipe slots per call) then disappear from the loop.
+struct MfitNoGuard {
+  static constexpr bool ON = false;
+  __device__ __forceinline__ void reset() {}
+  __device__ __forceinline__ void see_exp(unsigned) {}
+  __device__ __forceinline__ void see_gauss(unsigned) {}
+  __device__ __forceinline__ void see_log(unsigned) {}
+  __device__ __forceinline__ void see_sin(unsigned) {}
+  __device__ __forceinline__ bool tripped() const { return false; }
 };
 
 /* 1.5 * 2^52 + 2^31: adding it rounds to an integer k held in the low mantissa word.  The 2^31 bias keeps the low
@@ -79,18 +99,23 @@ struct MfitGuard {
 
 // 2^(k/64) for the integer k held (biased) in the low word of tmp = q + MAGIC: table entry (k & 63), exponent
 // k >> 6 added on the integer pipe (the table entries are pre-biased so that a plain k << 14 does both jobs).
-// Three integer instructions and one LDS.64.
+// Three integer instructions and one conflict-free LDS.64.
 __device__ __forceinline__ double mfit_exp2_64th(double tmp) {
   const int k = mfit_lo(tmp);
-  const unsigned long long t = MFIT_TAB_EXP[k & 63];
+#ifdef MFIT_HOST_TEST
+  const unsigned long long t = mfit_c_exp2[k & 63];
+#else
+  const char* base = reinterpret_cast<const char*>(mfit_s_exp2) + ((threadIdx.x & 15u) << 3);
+  const unsigned long long t = *reinterpret_cast<const unsigned long long*>(base + ((k & 63) << 7));
+#endif
   return mfit_mk((int)(t >> 32) + (k << 14), (int)t);
 }
 
 // exp(x): 10 FP64 instructions
-template <bool SLOW>
-__device__ __forceinline__ double mfit_exp_t(double x, MfitGuard& gd) {
+template <bool SLOW, class G>
+__device__ __forceinline__ double mfit_exp_t(double x, G& gd) {
   if (SLOW) return exp(x);
-  gd.e = mfit_umax(gd.e, (unsigned)mfit_hi(x) & 0x7fffffffu);
+  if (G::ON) gd.see_exp((unsigned)mfit_hi(x) & 0x7fffffffu);
   const double tmp = fma(x, MFIT_K_L2E64, MFIT_MAGIC);  // x 64/ln2
   const double kd = tmp - MFIT_MAGIC;
   double r = fma(kd, -0x1.62e42fef00000p-7, x);         // ln2/64 in two pieces (Cody-Waite); the first is a 32-bit constant
@@ -103,40 +128,57 @@ __device__ __forceinline__ double mfit_exp_t(double x, MfitGuard& gd) {
   return mfit_exp2_64th(tmp) * p;
 }
 
-// exp(-zs^2 ln2/64) = s * p  (zs = z sqrt(32/ln2) turns exp(-z^2/2) into this form): the square is both the argument
-// and, through one FMA each, its rounding to 1/64 octaves and the exact remainder.  8 FP64 instructions; the caller
-// folds the amplitude:  f = fma(a * s, p, rest).
-__device__ __forceinline__ void mfit_gauss_parts(double zs, double* s, double* p, MfitGuard& gd) {
-  // |zs| is clamped on the integer pipe at 255.875 (exp(-z^2/2) ~ 2^-1023, which the arithmetic below turns into a
-  // subnormal-sized number, i.e. zero next to any amplitude): wild proposals underflow all the time during the
-  // reference's start-up phase (its first l-matrix is diag(theta)), so that case must not leave the fast path.
-  const unsigned ah = (unsigned)mfit_hi(zs) & 0x7fffffffu;
-  gd.g = mfit_umax(gd.g, ah);
-  zs = mfit_mk((int)min(ah, 0x406ffc00u), mfit_lo(zs));
+// exp(-zs^2 ln2/64) = s * (1 + r q)  (zs = z sqrt(32/ln2) turns exp(-z^2/2) into this form): the square is both the
+// argument and, through one FMA each, its rounding to 1/64 octaves and the exact remainder r.  Three FP64
+// instructions here; the caller runs the polynomial (coefficients MFIT_K_EXS1..5, which it may pre-multiply by its
+// amplitude) and folds s:  f = fma(s, a (1 + r q), rest).
+template <class G>
+__device__ __forceinline__ void mfit_gauss_reduce(double zs, double* s, double* r, G& gd) {
+  if (G::ON) {
+    // |zs| is clamped on the integer pipe at 255.875 (exp(-z^2/2) ~ 2^-1023, which the arithmetic below turns into
+    // a subnormal-sized number, i.e. zero next to any amplitude): wild proposals underflow all the time during the
+    // reference's start-up phase (its first l-matrix is diag(theta)), so that case must not leave the fast path.
+    const unsigned ah = (unsigned)mfit_hi(zs) & 0x7fffffffu;
+    gd.see_gauss(ah);
+    zs = mfit_mk((int)min(ah, 0x406ffc00u), mfit_lo(zs));
+  }
   const double tmp = fma(-zs, zs, MFIT_MAGIC);
   const double kd = tmp - MFIT_MAGIC;
-  const double r = fma(-zs, zs, -kd);
+  *r = fma(-zs, zs, -kd);
+  *s = mfit_exp2_64th(tmp);
+}
+// the plain form (amplitude 1): exp(-zs^2 ln2/64) = s * p
+template <class G>
+__device__ __forceinline__ void mfit_gauss_parts(double zs, double* s, double* p, G& gd) {
+  double r;
+  mfit_gauss_reduce(zs, s, &r, gd);
   double q = fma(r, MFIT_K_EXS5, MFIT_K_EXS4);
   q = fma(r, q, MFIT_K_EXS3);
   q = fma(r, q, MFIT_K_EXS2);
   q = fma(r, q, MFIT_K_EXS1);
   *p = fma(r, q, 1.0);
-  *s = mfit_exp2_64th(tmp);
 }
+#define MFIT_GAUSS_ZLIMIT 255.875 /* |zs| beyond this needs the clamp of the guarded form */
 #define MFIT_GAUSS_ZSCALE 0x1.b2da4e9808a53p+2 /* sqrt(32/ln2) */
 
 // log(x): 13 FP64 instructions.  x = 2^e m with m in [0.707, 1.414); r = m c_i - 1 (one FMA, exact before rounding),
 // log x = e ln2 + L_i + log1p(r); the table intervals next to 1 have c = 1 (1/2) and L = 0 exactly, which keeps full
 // relative accuracy around x = 1.
-template <bool SLOW>
-__device__ __forceinline__ double mfit_log_t(double x, MfitGuard& gd) {
+template <bool SLOW, class G>
+__device__ __forceinline__ double mfit_log_t(double x, G& gd) {
   if (SLOW) return log(x);
   const int hx = mfit_hi(x);
-  gd.l = mfit_umax(gd.l, (unsigned)(hx - 0x00100000));
+  if (G::ON) gd.see_log((unsigned)(hx - 0x00100000));
   const int i = (hx >> 13) & 127;
   const int e = ((hx + 0x00096000) >> 20) - 1023;  // +1 exactly when i >= 53 (m >= 1.4140625 is halved)
   const double m = mfit_mk((hx & 0x000fffff) | 0x3ff00000, mfit_lo(x));
-  const double c = MFIT_TAB_LOG[2 * i], L = MFIT_TAB_LOG[2 * i + 1];
+#ifdef MFIT_HOST_TEST
+  const double c = mfit_c_log[2 * i], L = mfit_c_log[2 * i + 1];
+#else
+  const char* tab = reinterpret_cast<const char*>(mfit_s_log) + ((threadIdx.x & 7u) << 4);
+  const double2 cl = *reinterpret_cast<const double2*>(tab + (i << 7));
+  const double c = cl.x, L = cl.y;
+#endif
   const double r = fma(m, c, -1.0);
   const double ed = mfit_mk(0x43300000, e ^ 0x80000000) - 0x1.0000080000000p+52;  // int -> double via the exponent trick
   const double r2 = r * r;
@@ -175,16 +217,16 @@ __device__ __forceinline__ double mfit_sincos_core(double x, int quad_shift) {
   const double res = fma(c ? r2 : r, q, c ? 1.0 : 0.0);
   return mfit_mk(mfit_hi(res) ^ ((n & 2) << 30), mfit_lo(res));  // quadrants 2, 3: negate
 }
-template <bool SLOW>
-__device__ __forceinline__ double mfit_sin_t(double x, MfitGuard& gd) {
+template <bool SLOW, class G>
+__device__ __forceinline__ double mfit_sin_t(double x, G& gd) {
   if (SLOW) return sin(x);
-  gd.s = mfit_umax(gd.s, (unsigned)mfit_hi(x) & 0x7fffffffu);
+  if (G::ON) gd.see_sin((unsigned)mfit_hi(x) & 0x7fffffffu);
   return mfit_sincos_core(x, 0);
 }
-template <bool SLOW>
-__device__ __forceinline__ double mfit_cos_t(double x, MfitGuard& gd) {
+template <bool SLOW, class G>
+__device__ __forceinline__ double mfit_cos_t(double x, G& gd) {
   if (SLOW) return cos(x);
-  gd.s = mfit_umax(gd.s, (unsigned)mfit_hi(x) & 0x7fffffffu);
+  if (G::ON) gd.see_sin((unsigned)mfit_hi(x) & 0x7fffffffu);
   return mfit_sincos_core(x, 1);
 }
 

@@ -10,17 +10,30 @@
 
 #define MFIT_TH(k) a.theta[(size_t)a.idx[k] * a.stride + chain]
 
+// Every model struct provides:
+//   load(a, chain)   read the chain's parameters (issued one work item ahead, so only raw values are kept live)
+//   setup()          theta-only subexpressions, once per work item
+//   safe(a)          true when no argument of a fast math routine can leave its domain for any x in [a.xmin, a.xmax]
+//                    (NaN parameters make every comparison false -> not safe -> guarded path -> libdevice redo)
+//   eval<SLOW>(x,gd) the model function
+//   GUARDED          whether eval uses a fast routine with a restricted domain at all
+
+__device__ __forceinline__ double mfit_absmax(double u, double v) { return fmax(fabs(u), fabs(v)); }
+
 // f = c0 + x (c1 + x (c2 + ... ))   -- Horner, D FMAs
 template <int D>
 struct MfitPoly {
   static constexpr int USES = 0;
+  static constexpr bool GUARDED = false;
   double c[D + 1];
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
 #pragma unroll
     for (int k = 0; k <= D; k++) c[k] = MFIT_TH(k);
   }
-  template <bool SLOW>
-  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {
+  __device__ __forceinline__ void setup() {}
+  __device__ __forceinline__ bool safe(const MfitEvalArgs&) const { return true; }
+  template <bool SLOW, class G>
+  __device__ __forceinline__ double eval(double x, G& gd) const {
     double r = c[D];
 #pragma unroll
     for (int k = D - 1; k >= 0; k--) r = fma(x, r, c[k]);
@@ -31,62 +44,86 @@ struct MfitPoly {
 // f = a exp(b x) + c
 struct MfitExpo {
   static constexpr int USES = MFIT_USES_EXP;
+  static constexpr bool GUARDED = true;
   double a_, b_, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     a_ = MFIT_TH(0); b_ = MFIT_TH(1); c_ = MFIT_TH(2);
   }
-  template <bool SLOW>
-  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const { return fma(a_, mfit_exp_t<SLOW>(b_ * x, gd), c_); }
+  __device__ __forceinline__ void setup() {}
+  __device__ __forceinline__ bool safe(const MfitEvalArgs& a) const { return fabs(b_) * mfit_absmax(a.xmin, a.xmax) < 700.0; }
+  template <bool SLOW, class G>
+  __device__ __forceinline__ double eval(double x, G& gd) const { return fma(a_, mfit_exp_t<SLOW>(b_ * x, gd), c_); }
 };
 
 // f = a sin(omega x + phi) + c
 struct MfitSinus {
   static constexpr int USES = 0;
+  static constexpr bool GUARDED = true;
   double a_, om, ph, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     a_ = MFIT_TH(0); om = MFIT_TH(1); ph = MFIT_TH(2); c_ = MFIT_TH(3);
   }
-  template <bool SLOW>
-  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const { return fma(a_, mfit_sin_t<SLOW>(fma(om, x, ph), gd), c_); }
+  __device__ __forceinline__ void setup() {}
+  __device__ __forceinline__ bool safe(const MfitEvalArgs& a) const {
+    return fabs(om) * mfit_absmax(a.xmin, a.xmax) + fabs(ph) < 9.0e4;
+  }
+  template <bool SLOW, class G>
+  __device__ __forceinline__ double eval(double x, G& gd) const { return fma(a_, mfit_sin_t<SLOW>(fma(om, x, ph), gd), c_); }
 };
 
 // f = a gamma^2 / ((x - x0)^2 + gamma^2) + c
 struct MfitLorentz {
   static constexpr int USES = 0;
+  static constexpr bool GUARDED = false;
   double ag2, x0, g2, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
-    const double g = MFIT_TH(2);
-    g2 = g * g;
-    ag2 = MFIT_TH(0) * g2;
-    x0 = MFIT_TH(1);
-    c_ = MFIT_TH(3);
+    ag2 = MFIT_TH(0); x0 = MFIT_TH(1); g2 = MFIT_TH(2); c_ = MFIT_TH(3);
   }
-  template <bool SLOW>
-  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {
+  __device__ __forceinline__ void setup() {
+    g2 = g2 * g2;
+    ag2 = ag2 * g2;
+  }
+  __device__ __forceinline__ bool safe(const MfitEvalArgs&) const { return true; }
+  template <bool SLOW, class G>
+  __device__ __forceinline__ double eval(double x, G& gd) const {
     const double d = x - x0;
     return ag2 / fma(d, d, g2) + c_;
   }
 };
 
 // f = a exp(-((x - mu)/s)^2 / 2) + b0 + b1 x.  The Gaussian argument is formed directly in 1/64 octaves
-// (zs = z sqrt(32/ln2), exp(-z^2/2) = 2^(-zs^2/64)), see mfit_gauss_parts: 15 FP64 instructions per point in all.
+// (zs = z sqrt(32/ln2), exp(-z^2/2) = 2^(-zs^2/64)), see mfit_gauss_reduce, and the amplitude is folded into the
+// polynomial coefficients once per work item:  a exp(..) = s (a + r (a k1 + r (a k2 + ...))).  12 FP64 instructions
+// per point (d, zs, lin, tmp, kd, r, five FMAs, the final FMA with s), 14 with the log-normal term.
 struct MfitGaussLin {
   static constexpr int USES = MFIT_USES_EXP;
-  double a_, mu, is_, isq, b0, b1;
+  static constexpr bool GUARDED = true;
+  double a_, mu, isq, b0, b1, k1, k2, k3, k4, k5;  // load() leaves s in isq
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
-    a_ = MFIT_TH(0); mu = MFIT_TH(1); is_ = 1.0 / MFIT_TH(2); isq = is_ * MFIT_GAUSS_ZSCALE; b0 = MFIT_TH(3); b1 = MFIT_TH(4);
+    a_ = MFIT_TH(0); mu = MFIT_TH(1); isq = MFIT_TH(2); b0 = MFIT_TH(3); b1 = MFIT_TH(4);
   }
-  template <bool SLOW>
-  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {
+  __device__ __forceinline__ void setup() {
+    isq = (1.0 / isq) * MFIT_GAUSS_ZSCALE;
+    k1 = a_ * MFIT_K_EXS1; k2 = a_ * MFIT_K_EXS2; k3 = a_ * MFIT_K_EXS3; k4 = a_ * MFIT_K_EXS4; k5 = a_ * MFIT_K_EXS5;
+  }
+  __device__ __forceinline__ bool safe(const MfitEvalArgs& a) const {
+    return mfit_absmax(a.xmin - mu, a.xmax - mu) * fabs(isq) < MFIT_GAUSS_ZLIMIT && fabs(a_) < 1.0e300;
+  }
+  template <bool SLOW, class G>
+  __device__ __forceinline__ double eval(double x, G& gd) const {
     const double d = x - mu;
     const double lin = fma(b1, x, b0);
     if (SLOW) {
-      const double z = d * is_;
+      const double z = d * (isq * (1.0 / MFIT_GAUSS_ZSCALE));
       return fma(a_, exp(-0.5 * (z * z)), lin);
     }
-    double s, p;
-    mfit_gauss_parts(d * isq, &s, &p, gd);
-    return fma(a_ * s, p, lin);
+    double s, r;
+    mfit_gauss_reduce(d * isq, &s, &r, gd);
+    double q = fma(r, k5, k4);
+    q = fma(r, q, k3);
+    q = fma(r, q, k2);
+    q = fma(r, q, k1);
+    return fma(s, fma(r, q, a_), lin);
   }
 };
 
@@ -94,16 +131,22 @@ struct MfitGaussLin {
 template <int K>
 struct MfitNvMulti {
   static constexpr int USES = 0;
+  static constexpr bool GUARDED = false;
   double sg[K], mu[K], g2, bg0;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
-    const double g = MFIT_TH(2 * K);
-    g2 = g * g;
+    g2 = MFIT_TH(2 * K);
     bg0 = MFIT_TH(2 * K + 1);
 #pragma unroll
-    for (int k = 0; k < K; k++) { sg[k] = MFIT_TH(k) * g2; mu[k] = MFIT_TH(K + k); }
+    for (int k = 0; k < K; k++) { sg[k] = MFIT_TH(k); mu[k] = MFIT_TH(K + k); }
   }
-  template <bool SLOW>
-  __device__ __forceinline__ double eval(double x, MfitGuard& gd) const {
+  __device__ __forceinline__ void setup() {
+    g2 = g2 * g2;
+#pragma unroll
+    for (int k = 0; k < K; k++) sg[k] = sg[k] * g2;
+  }
+  __device__ __forceinline__ bool safe(const MfitEvalArgs&) const { return true; }
+  template <bool SLOW, class G>
+  __device__ __forceinline__ double eval(double x, G& gd) const {
     double r = bg0;
 #pragma unroll
     for (int k = 0; k < K; k++) {

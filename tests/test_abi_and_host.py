@@ -57,6 +57,31 @@ def test_product_never_touches_the_oracle():
                 assert "liborc" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
 
 
+def test_lisp_cffi_bindings_match_the_header():
+    """lisp/mfit-cuda.lisp cannot be executed in this image (no Common Lisp): at least every defcfun must name a
+    symbol the header declares, with the declared number of arguments and 64-bit integers where the ABI has them."""
+    txt = open(os.path.join(ROOT, "lisp_mcmc_b200", "lisp", "mfit-cuda.lisp")).read()
+    txt = re.sub(r";[^\n]*", "", txt)
+    forms = re.findall(r'\(cffi:defcfun \("(mfit_[a-z0-9_]+)" [^)]*\) (:[a-z0-9]+)((?:\s*\([a-z0-9-]+ :[a-z0-9]+\))*)\)', txt)
+    assert len(forms) >= 25
+    lisp_t = {C.c_int: ":int", C.c_int64: ":int64", C.c_uint64: ":uint64", C.c_double: ":double", C.c_char_p: ":string"}
+    for name, ret, args in forms:
+        assert name in _lib.SIGNATURES, name
+        res, argtypes = _lib.SIGNATURES[name]
+        got = re.findall(r"\([a-z0-9-]+ (:[a-z0-9]+)\)", args)
+        assert len(got) == len(argtypes), "%s: %d lisp args, header has %d" % (name, len(got), len(argtypes))
+        for g, a in zip(got, argtypes):
+            ok = (":string", ":pointer") if a is C.c_char_p else (lisp_t.get(a, ":pointer"),)   # char* out-buffers
+            assert g in ok, "%s: %s vs %s" % (name, g, a)
+        assert ret == {None: ":void", C.c_char_p: ":string", C.c_int64: ":int64"}.get(res, ":int"), name
+    # the two structs passed by pointer
+    for struct, cls in (("adapt-cfg", _lib.AdaptCfg), ("chain-stats", _lib.ChainStats)):
+        body = re.search(r"\(cffi:defcstruct %s(.*?)\)\)" % struct, txt, flags=re.S).group(1)
+        types = re.findall(r"\([a-z0-9-]+ (:[a-z0-9]+)\)", body + ")")
+        want = [{C.c_int64: ":int64", C.c_int32: ":int32", C.c_double: ":double"}[t] for _, t in cls._fields_]
+        assert types == want, struct
+
+
 def test_get_depth_and_force_list_docstring_examples():
     # get-depth :763-764, force-list :755-759
     assert get_depth([1, 2, 3]) == 1 and get_depth([[1, 2], [3, 4]]) == 2 and get_depth([[[1]]]) == 3
@@ -114,4 +139,4 @@ def test_family_texts_parse_and_lower():
     for name, deg in [("poly", 0), ("poly", 7), ("expo", 0), ("sinus", 0), ("lorentz", 0), ("gauss_lin", 0), ("nv_multi", 3)]:
         keys = families.slots(name, deg)
         code = _lib.lower_sexpr(families.lisp_text(name, deg), keys)
-        assert "struct MfitUser" in code and "eval(double x, MfitGuard& gd)" in code
+        assert "struct MfitUser" in code and "eval(double x, G& gd)" in code

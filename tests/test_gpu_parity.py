@@ -293,7 +293,7 @@ def test_resume_reestimates_l_matrix_from_existing_walk(orc):
     z2, u2 = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
     w.adaptive_steps_full(n=n, temperature=10, z=z1, u=u1)
     w.adaptive_steps_full(n=n, temperature=10, z=z2, u=u2)
-    th, pr, nv = w.trace(2 * n)
+    th, pr, nv = w.trace(2 * n + 1)   # walker-create's first step + n take-steps per run
     ow = oracle_walker(orc, cfg)
     for c in range(4):
         ow.init(cfg["theta0"][c])
@@ -311,7 +311,7 @@ def test_philox_run_replays_through_oracle(orc):
     w = workloads.make_walker(cfg, seed=1234, chain_id_base=77)
     n = 1500
     w.adaptive_steps_full(n=n, temperature=10)
-    z, u = w.philox_stream(1, n)   # the first take-step happens at walker age 1
+    z, u = w.philox_stream(1, 2000)   # the first take-step happens at walker age 1; n <= 2000 runs the full 2000-step tail (:906)
     assert abs(z.mean()) < 0.05 and abs(z.std() - 1) < 0.05 and 0.45 < u.mean() < 0.55 and u.min() > 0 and u.max() < 1
     _compare_chain(orc, cfg, w, z, u,
                    lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu), range(6))
@@ -361,7 +361,7 @@ def test_full_size_c2_properties():
     cfg2["data_error"] = [s[:h], s[h:]]
     w2 = workloads.make_walker(cfg2)
     q, ll, _ = w2.make_step(th[:512])
-    assert rel_err(q, p1[:512]) < TOL
+    assert rel_err(q, p1[:512], ll_scale(cfg)) < TOL   # C_d - sum/2 cancels for chains near the best fit (helpers.rel_err)
     w2.close()
 
 
