@@ -120,7 +120,7 @@ int mfit_lower_sexpr(const char* lambda_text, const char* const* key_names, int 
 /* lower + NVRTC-compile (sm_100a cubin) without touching a GPU; returns the cubin size or a negative status */
 int mfit_compile_sexpr(const char* lambda_text, const char* const* key_names, int n_keys, int kind,
                        char* err, int err_len);
-/* points per reduction segment = 512 * tiles (0 = default: a function of the point count only, so that
+/* points per reduction segment = 128 * tiles (0 = default: a function of the point count only, so that
  * log-likelihood bits do not depend on chain count or GPU count) */
 int mfit_set_segment_tiles(mfit_ctx* ctx, int tiles_per_segment);
 

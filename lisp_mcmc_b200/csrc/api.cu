@@ -75,6 +75,7 @@ struct mfit_ctx {
   std::vector<Dataset> ds;
   int seg_tiles_override = 0;
   std::map<const void*, int> resident;  // eval kernel -> CTAs resident on the whole device
+  int* sched_dev = nullptr;             // [2] work-item counter / finished-CTA counter of the eval kernels (zero between launches)
 
   // chains
   bool have_chains = false;
@@ -184,7 +185,7 @@ double log_factorial_ref(long long n, std::vector<float>& memo) {
 // every log-likelihood bit -- do not depend on chain count, SM count or the number of GPUs
 void plan_segments(mfit_ctx* ctx, Dataset& d) {
   const long long n_tiles = (d.n + MFIT_TILE - 1) / MFIT_TILE;
-  long long tps = ctx->seg_tiles_override > 0 ? ctx->seg_tiles_override : (n_tiles + 255) / 256;
+  long long tps = ctx->seg_tiles_override > 0 ? ctx->seg_tiles_override : (n_tiles + MFIT_MAX_SEG - 1) / MFIT_MAX_SEG;
   if (tps < 1) tps = 1;
   d.tiles_per_seg = (int)tps;
   d.n_seg = (int)((n_tiles + tps - 1) / tps);
@@ -249,6 +250,10 @@ int check_problem_ready(mfit_ctx* ctx) {
 
 int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const double* theta, const unsigned char* skip) {
   if (s.n == 0 || s.n_seg == 0) return 0;
+  if (!ctx->sched_dev) {
+    CU(cudaMalloc(&ctx->sched_dev, 2 * sizeof(int)));
+    CU(cudaMemsetAsync(ctx->sched_dev, 0, 2 * sizeof(int), ctx->stream));
+  }
   MfitEvalArgs a;
   memset(&a, 0, sizeof a);
   a.x = s.x; a.y = s.y; a.yw = s.yw; a.w = s.w; a.c = s.c;
@@ -263,6 +268,7 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
   a.theta = theta;
   a.skip = skip;
   a.partial = w.partial[d];
+  a.sched = ctx->sched_dev;
   for (int k = 0; k < MFIT_MAXK; k++) a.idx[k] = s.idx[k];
   a.degree = s.degree;
   const void* fn = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user[s.ll_kind]
@@ -273,16 +279,20 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
   if (it == ctx->resident.end()) {  // persistent grid = CTAs resident at once (occupancy x SMs), queried once per kernel
     // static (math tables) + dynamic (TMA ring) shared memory may exceed the 48 KB default together
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // without this the driver's carve-out heuristic leaves room for 3 CTAs per SM only (ncu: 11.8 resident warps
+    // instead of 16), and the persistent grid sized for 4 runs its last quarter as a second wave
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0, sms = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MFIT_CB, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MFIT_THREADS, smem));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     if (per_sm < 1) per_sm = 1;
     it = ctx->resident.emplace(fn, per_sm * sms).first;
   }
   void* args[] = {&a};
   const long long items = (long long)a.n_cb * a.n_seg;
+  if (items > 2000000000LL) return fail(ctx, MFIT_ERR_ARG, "dataset %d: too many work items (%lld chain-blocks x %d segments)", d, (long long)a.n_cb, a.n_seg);
   const unsigned grid = (unsigned)(items < it->second ? items : it->second);
-  CU(cudaLaunchKernel(fn, dim3(grid), dim3(MFIT_CB), args, smem, ctx->stream));
+  CU(cudaLaunchKernel(fn, dim3(grid), dim3(MFIT_THREADS), args, smem, ctx->stream));
   ctx->launches++;
   return 0;
 }
@@ -550,7 +560,7 @@ void mfit_ctx_destroy(mfit_ctx* ctx) {
   chains_free(ctx);
   for (auto& d : ctx->ds) { dataset_free_data(d); dataset_free_prior(d); dataset_free_model(d); }
   free_dev(ctx->temps_dev); free_dev(ctx->z_dev); free_dev(ctx->u_dev); free_dev(ctx->lshared_dev);
-  free_dev(ctx->active_dev); free_dev(ctx->flush_buf);
+  free_dev(ctx->active_dev); free_dev(ctx->flush_buf); free_dev(ctx->sched_dev);
   if (ctx->active_host) cudaFreeHost(ctx->active_host);
   if (ctx->poll_ev_made) for (auto& e : ctx->poll_ev) cudaEventDestroy(e);
   for (auto& p : ctx->ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }

@@ -134,13 +134,33 @@ __device__ __forceinline__ double* lp_ptr(const MfitChains& c, int d) {
   return c.lpd + (size_t)d * c.stride;
 }
 
-// per-segment partial sums -> dataset log-likelihood (segments added in order)
-__device__ double finalize_ll(const MfitChains& c, int d, long long w) {
+// per-segment partial sums -> dataset log-likelihood.  The likelihood kernel cuts a data set into up to 1024
+// segments (fine-grained work items, see mfit_eval.cuh), so the sum over segments is itself parallel: a block of
+// MFIT_RED_T threads handles 32 chains x MFIT_RED_S slices; slice k adds the segments [k B, (k+1) B), B =
+// ceil(n_seg / MFIT_RED_S), in order, and the slice sums are then added in slice order.  The shape depends on n_seg
+// only (i.e. on the point count), so every bit of the result is independent of chain count, grid and GPU count.
+#define MFIT_RED_S 8
+#define MFIT_RED_T (32 * MFIT_RED_S)
+// called by all MFIT_RED_T threads of the block (w may be >= c.W: such threads only take part in the barriers);
+// the result is valid in the threads of slice 0
+__device__ double reduce_ll(const MfitChains& c, int d, long long w, int slice, double (*red)[32]) {
   const MfitDsDev& s = c.ds[d];
+  const int lane = threadIdx.x & 31;
+  const int B = (s.n_seg + MFIT_RED_S - 1) / MFIT_RED_S;
   double sum = 0.0;
-  if (s.n_seg > 0) {
-    sum = s.partial[w];
-    for (int k = 1; k < s.n_seg; k++) sum = sum + s.partial[(size_t)k * c.stride + w];
+  if (w < c.W) {
+    const int lo = slice * B, hi = min(s.n_seg, lo + B);
+    if (lo < hi) {
+      sum = s.partial[(size_t)lo * c.stride + w];
+      for (int k = lo + 1; k < hi; k++) sum = sum + s.partial[(size_t)k * c.stride + w];
+    }
+  }
+  __syncthreads();  // red is free again
+  red[slice][lane] = sum;
+  __syncthreads();
+  if (slice == 0 && B > 0) {
+    const int used = (s.n_seg + B - 1) / B;
+    for (int k = 1; k < used; k++) sum = sum + red[k][lane];
   }
   switch (s.ll_kind) {
     case MFIT_LL_NORMAL: return s.cst + (-0.5 * sum);
@@ -217,14 +237,13 @@ __device__ void pre_body(const MfitChains& c, const MfitRunCfg& r, long long w) 
 }
 
 // ------------------------------------------------------------------ after the likelihood: accept, push, adapt
-template <bool FIN>
 __device__ void post_body(const MfitChains& c, const MfitRunCfg& r, long long w) {
   if (c.done[w]) return;
   const int P = c.P;
   // walker-make-step :1067-1070
   double ll = 0.0, lp = 0.0;
   for (int d = 0; d < c.D; d++) {
-    double v = FIN ? finalize_ll(c, d, w) : ll_ptr(c, d)[w];
+    double v = ll_ptr(c, d)[w];
     ll = d == 0 ? v : ll + v;
   }
   for (int d = 0; d < c.D; d++) {
@@ -314,21 +333,40 @@ __global__ void k_pre(const MfitChains c, const MfitRunCfg r) {
   long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w < c.W) pre_body(c, r, w);
 }
+// FIN: the per-segment sums of this rank's data sets are reduced here (blocks of 32 chains x MFIT_RED_S slices); the
+// per-chain work that follows runs in the threads of slice 0.  Without FIN (data sets sharded over ranks: k_finalize
+// and the all-gather have run) one thread per chain.
 template <bool FIN, bool FUSE>
 __global__ void k_post(const MfitChains c, MfitRunCfg r) {
-  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long w;
+  if (FIN) {
+    __shared__ double red[MFIT_RED_S][32];
+    const int slice = threadIdx.x >> 5;
+    w = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+    for (int d = 0; d < c.D; d++) {
+      if (!c.ds[d].owned) continue;
+      const double v = reduce_ll(c, d, w, slice, red);
+      if (slice == 0 && w < c.W) ll_ptr(c, d)[w] = v;
+    }
+    if (slice != 0) return;
+  } else
+    w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= c.W) return;
-  post_body<FIN>(c, r, w);
+  post_body(c, r, w);
   if (FUSE) {
     r.t += 1;
     pre_body(c, r, w);
   }
 }
 __global__ void k_finalize(const MfitChains c) {
-  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= c.W) return;
-  for (int d = 0; d < c.D; d++)
-    if (c.ds[d].owned) ll_ptr(c, d)[w] = finalize_ll(c, d, w);
+  __shared__ double red[MFIT_RED_S][32];
+  const int slice = threadIdx.x >> 5;
+  const long long w = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+  for (int d = 0; d < c.D; d++) {
+    if (!c.ds[d].owned) continue;
+    const double v = reduce_ll(c, d, w, slice, red);
+    if (slice == 0 && w < c.W) ll_ptr(c, d)[w] = v;
+  }
 }
 
 // ------------------------------------------------------------------ run set-up (:866-901)
@@ -675,15 +713,16 @@ void mfit_launch_post(const MfitChains& c, const MfitRunCfg& r, bool fuse_pre, c
   const bool fin = c.xch == nullptr;
   const unsigned g = blocks_for(c.W, 128);
   if (fin) {
-    if (fuse_pre) k_post<true, true><<<g, 128, 0, st>>>(c, r);
-    else k_post<true, false><<<g, 128, 0, st>>>(c, r);
+    const unsigned gr = blocks_for(c.W, 32);
+    if (fuse_pre) k_post<true, true><<<gr, MFIT_RED_T, 0, st>>>(c, r);
+    else k_post<true, false><<<gr, MFIT_RED_T, 0, st>>>(c, r);
   } else {
     if (fuse_pre) k_post<false, true><<<g, 128, 0, st>>>(c, r);
     else k_post<false, false><<<g, 128, 0, st>>>(c, r);
   }
 }
 void mfit_launch_finalize(const MfitChains& c, cudaStream_t st) {
-  k_finalize<<<blocks_for(c.W, 128), 128, 0, st>>>(c);
+  k_finalize<<<blocks_for(c.W, 32), MFIT_RED_T, 0, st>>>(c);
 }
 void mfit_launch_first_step(const MfitChains& c, cudaStream_t st) {
   k_first_step<<<blocks_for(c.W, 128), 128, 0, st>>>(c);

@@ -5,7 +5,7 @@
 #include "mfit_internal.h"
 
 template <class Model, int LL>
-__global__ void __launch_bounds__(MFIT_CB, 4) mfit_eval_kernel(const __grid_constant__ MfitEvalArgs a) {
+__global__ void __launch_bounds__(MFIT_THREADS, MFIT_MIN_CTAS) mfit_eval_kernel(const __grid_constant__ MfitEvalArgs a) {
   mfit_eval_body<Model, LL>(a);
 }
 
@@ -51,5 +51,5 @@ int mfit_family_nparams(int family, int degree) {
 
 size_t mfit_eval_smem_bytes(int ll) {
   int narr = ll == MFIT_LL_NORMAL ? 3 : ll == MFIT_LL_NORMAL_CUTOFF ? 4 : 2;
-  return (size_t)MFIT_STAGES * narr * MFIT_TILE * 8 + 2 * MFIT_STAGES * 8;
+  return (size_t)MFIT_STAGES * narr * MFIT_TILE * 8 + 2 * MFIT_STAGES * 8 + MFIT_QN * 4;
 }

@@ -6,15 +6,21 @@
 //     ll_d(theta) = sum_i  density(y_i, f(x_i; theta), sigma_i)
 // evaluated for W parameter vectors (chains) at once against shared (x, y, sigma).
 //
-// Work decomposition: one work item = one chain-block (MFIT_CB chains, one chain per thread) x one
-// segment of the data (tiles_per_seg tiles of MFIT_TILE points); persistent CTAs walk contiguous ranges of items.  The data tile is moved
-// global -> shared by the TMA engine (cp.async.bulk, 1-D) through an MFIT_STAGES-deep
-// mbarrier ring and is read back as warp-uniform (broadcast) 128-bit LDS; theta lives in
-// registers, one chain per lane, so the FP64 pipe sees no cross-lane traffic at all and
-// each fetched point is reused by 128 chains.  Per-chain sums are sequential inside a
-// segment (two interleaved accumulators, fixed order) and the per-segment partials are
-// added in segment order by the chain kernel, so results do not depend on grid size, SM
-// count or GPU count.
+// Work decomposition: one work item = one chain-block (MFIT_CB = 256 chains, two chains per thread) x one segment of
+// the data (tiles_per_seg tiles of MFIT_TILE points).  Persistent CTAs (one grid = what is resident at once) take
+// items from a global counter, chain-block fastest.  The data tile is moved global -> shared by the TMA engine
+// (cp.async.bulk, 1-D) through an MFIT_STAGES-deep mbarrier ring that runs across item boundaries, and is read back
+// as warp-uniform (broadcast) 128-bit LDS; theta lives in registers, so the FP64 pipe sees no cross-lane traffic.
+//
+// Why two chains per thread: a broadcast LDS.128 still returns 512 bytes to the register file and the shared-memory
+// return path moves 128 B/clk/SM, i.e. 4 cycles per load, shared by the four schedulers.  With one chain per thread
+// the 24 bytes of (x, y/sigma, 1/sigma) cost 6 of those cycles per warp-point and the kernel ran at the speed of
+// that path, not of the FP64 pipe (tools/probe/loop_probe.cu: 5th-order polynomial at 62 % of the DFMA rate, ncu:
+// profiles/); every fetched point now feeds two evaluations.
+//
+// Per-chain sums are sequential inside a segment (two interleaved accumulators, fixed order) and the per-segment
+// partials are added in segment order by the chain kernel, so results do not depend on grid size, on which CTA took
+// which item, on SM count or on GPU count.
 //
 // The file is freestanding (its only #include is mfit_math.cuh, which embed_source.py inlines) because the very
 // same text is embedded in libmfit_cuda.so and handed to NVRTC together with a model struct generated from a
@@ -23,9 +29,15 @@
 #define MFIT_EVAL_CUH
 #include "mfit_math.cuh"
 
-#define MFIT_TILE 512    /* points per shared-memory stage */
-#define MFIT_STAGES 3    /* TMA ring depth */
-#define MFIT_CB 128      /* chains per CTA = threads per CTA */
+#define MFIT_TILE 128    /* points per shared-memory stage */
+#define MFIT_STAGES 4    /* TMA ring depth */
+#define MFIT_MAX_SEG 1024 /* segments (= work items per chain-block, = partial sums per chain) a data set is cut into at most */
+#define MFIT_THREADS 128 /* threads per CTA */
+#define MFIT_CB 256      /* chains per CTA: two per thread (thread t: chains t and t + MFIT_THREADS of the block) */
+#ifndef MFIT_MIN_CTAS
+#define MFIT_MIN_CTAS 4   /* CTAs per SM the register allocation is bounded for */
+#endif
+#define MFIT_QN 8        /* ring of item ids handed from the producer thread to the CTA */
 #define MFIT_MAXK 16     /* parameters a built-in family may gather */
 
 #define MFITK_NORMAL 0
@@ -48,6 +60,7 @@ struct MfitEvalArgs {
   const double* theta;  /* [P][stride] parameter vectors to evaluate */
   const unsigned char* skip; /* [stride] 1 = chain finished, nothing to do (may be null) */
   double* partial;      /* [n_seg][stride] per-segment sums */
+  int* sched;           /* [2] zero between launches: next item to hand out, CTAs that have finished */
   int idx[MFIT_MAXK];   /* built-in families: family slot -> shared parameter index */
   int degree;
 };
@@ -131,42 +144,72 @@ struct MfitTerm<MFITK_POISSON> {
   }
 };
 
-// ---------------------------------------------------------------- one data tile, one chain per thread
-// MFIT_UNROLL_PAIRS pairs of points in flight per thread (two independent accumulators, fixed order).  SLOW = libdevice
-// math, used only to redo a tile in which a fast routine met an argument outside its domain (see mfit_math.cuh);
-// G = MfitGuard records such arguments, MfitNoGuard is for chains whose Model::safe() has ruled them out.
+// ---------------------------------------------------------------- one data tile
+// NC chains per thread (2, or 1 for a chain-block whose second half is empty), UNROLL pairs of points per iteration:
+// 2 NC UNROLL evaluations in flight per thread, two accumulators per chain, fixed order.  SLOW = libdevice math, used
+// only to redo a tile in which a fast routine met an argument outside its domain (see mfit_math.cuh); G = MfitGuard
+// records such arguments, MfitNoGuard is for chains whose Model::safe() has ruled them out.
 #ifndef MFIT_UNROLL_PAIRS
-#define MFIT_UNROLL_PAIRS 4
+#define MFIT_UNROLL_PAIRS 2
 #endif
-template <class Model, int LL, bool SLOW, class G>
-__device__ __forceinline__ void mfit_tile_pass(const Model& m, const double* xs, const double* ys, const double* ws,
-                                               const double* cs, int cnt, double& acc0, double& acc1, G& gd) {
+template <class Model, int LL, bool SLOW, int NC, class G>
+__device__ __forceinline__ void mfit_tile_pass(const Model* m, const double* xs, const double* ys, const double* ws,
+                                               const double* cs, int cnt, double* acc, G& gd) {
   const int pairs = cnt >> 1;
   const double2* x2 = reinterpret_cast<const double2*>(xs);
   const double2* y2 = reinterpret_cast<const double2*>(ys);
   const double2* w2 = reinterpret_cast<const double2*>(ws);
   const double2* c2 = reinterpret_cast<const double2*>(cs);
-  constexpr int UNROLL = MFIT_UNROLL_PAIRS;
+  constexpr int UNROLL = MFIT_UNROLL_PAIRS * (NC == 1 ? 2 : 1);
 #pragma unroll UNROLL
   for (int i = 0; i < pairs; i++) {
     const double2 xv = x2[i], yv = y2[i], wv = w2[i], cv = c2[i];
-    const double f0 = m.template eval<SLOW>(xv.x, gd);
-    const double f1 = m.template eval<SLOW>(xv.y, gd);
-    acc0 = MfitTerm<LL>::template add<SLOW>(acc0, f0, yv.x, wv.x, cv.x, gd);
-    acc1 = MfitTerm<LL>::template add<SLOW>(acc1, f1, yv.y, wv.y, cv.y, gd);
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const double f0 = m[c].template eval<SLOW>(xv.x, gd);
+      const double f1 = m[c].template eval<SLOW>(xv.y, gd);
+      acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], f0, yv.x, wv.x, cv.x, gd);
+      acc[2 * c + 1] = MfitTerm<LL>::template add<SLOW>(acc[2 * c + 1], f1, yv.y, wv.y, cv.y, gd);
+    }
   }
   if (cnt & 1) {
     const int i = cnt - 1;
-    acc0 = MfitTerm<LL>::template add<SLOW>(acc0, m.template eval<SLOW>(xs[i], gd), ys[i], ws[i], cs[i], gd);
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+      acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], m[c].template eval<SLOW>(xs[i], gd), ys[i], ws[i], cs[i], gd);
+  }
+}
+
+// fast pass with whatever protection the chains of this warp need; a tripped guard redoes the tile with libdevice
+template <class Model, int LL, int NC>
+__device__ __forceinline__ void mfit_tile(const Model* m, bool unguarded, const double* xs, const double* ys,
+                                          const double* ws, const double* cs, int cnt, double* acc) {
+  constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
+  if (!GUARDED || unguarded) {
+    MfitNoGuard ng;
+    mfit_tile_pass<Model, LL, false, NC>(m, xs, ys, ws, cs, cnt, acc, ng);
+  } else {
+    double save[2 * NC];
+#pragma unroll
+    for (int k = 0; k < 2 * NC; k++) save[k] = acc[k];
+    MfitGuard gd;
+    gd.reset();
+    mfit_tile_pass<Model, LL, false, NC>(m, xs, ys, ws, cs, cnt, acc, gd);
+    if (gd.tripped()) {  // rare: overflow / NaN / log of a non-positive number ...
+#pragma unroll
+      for (int k = 0; k < 2 * NC; k++) acc[k] = save[k];
+      mfit_tile_pass<Model, LL, true, NC>(m, xs, ys, ws, cs, cnt, acc, gd);
+    }
   }
 }
 
 // ---------------------------------------------------------------- the kernel body
-// Persistent CTAs: the work items (segment, chain-block) -- chain-block fastest -- are split into gridDim.x
-// contiguous ranges, one per CTA, and the grid is sized to what is resident at once (occupancy x SM count), so there
-// is no wave quantisation and the prologue (mbarriers, math tables) is paid once per CTA.  The TMA ring runs across
-// item boundaries: while the chains of one item are being evaluated the tiles of the next are already in flight, and
-// the next item's parameters are loaded into registers one item ahead.
+// Persistent CTAs: the grid is sized to what is resident at once (occupancy x SM count) and every CTA takes work
+// items (segment, chain-block) -- chain-block fastest -- from a.sched[0] until they run out, so there is no wave
+// quantisation, no tail longer than one item, and the prologue (mbarriers, math tables) is paid once per CTA.
+// Thread 0 is the producer: it draws the next item while the tiles of the current one are still being consumed, keeps
+// MFIT_STAGES tiles in flight across item boundaries and publishes item ids through a small ring in shared memory;
+// the parameters of the next item are loaded into registers one item ahead.
 template <class Model, int LL>
 __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   constexpr int NARR = MfitTerm<LL>::NARR;
@@ -175,37 +218,48 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   double* buf = reinterpret_cast<double*>(mfit_smem);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(mfit_smem + MFIT_STAGES * STAGE_BYTES);
   unsigned long long* empty = full + MFIT_STAGES;
+  volatile int* q_items = reinterpret_cast<volatile int*>(empty + MFIT_STAGES);
 
   const int tid = threadIdx.x;
-  const long long total = (long long)a.n_cb * a.n_seg;
-  const long long item_lo = total * blockIdx.x / gridDim.x;
-  const long long item_hi = total * (blockIdx.x + 1) / gridDim.x;
-  if (item_lo >= item_hi) return;
+  const int total = a.n_cb * a.n_seg;
   const long long n_tiles = (a.n + MFIT_TILE - 1) / MFIT_TILE;
-  auto tiles_of = [&](long long seg) -> int {
-    long long t0 = seg * a.tiles_per_seg, t1 = t0 + a.tiles_per_seg;
+  auto tiles_of = [&](int seg) -> int {
+    long long t0 = (long long)seg * a.tiles_per_seg, t1 = t0 + a.tiles_per_seg;
     if (t1 > n_tiles) t1 = n_tiles;
     return (int)(t1 - t0);
   };
 
-  mfit_math_stage(Model::USES | MfitTerm<LL>::USES, tid, MFIT_CB);  // exp/log tables -> shared memory
+  mfit_math_stage(Model::USES | MfitTerm<LL>::USES, tid, MFIT_THREADS);  // exp/log tables -> shared memory
   if (tid == 0) {
     for (int s = 0; s < MFIT_STAGES; s++) {
       mfit_mbar_init(&full[s], 1);
-      mfit_mbar_init(&empty[s], MFIT_CB / 32);
+      mfit_mbar_init(&empty[s], MFIT_THREADS / 32);
     }
     mfit_fence_mbar_init();
   }
-  __syncthreads();
 
   // producer cursor (thread 0 only): next tile to request = tile p_k of item p_item; `issued` counts requests
-  long long p_item = item_lo;
-  int p_k = 0;
+  int p_item = 0, p_k = 0, p_nt = 0, p_seq = 0;
+  bool p_done = false;
   unsigned issued = 0;
+  auto fetch_item = [&]() {
+    p_item = atomicAdd(a.sched, 1);
+    if (p_item >= total) {
+      p_item = -1;
+      p_done = true;
+    } else {
+      p_k = 0;
+      p_nt = tiles_of(p_item / a.n_cb);
+    }
+    q_items[(p_seq + 1) % MFIT_QN] = -2;  // "not drawn yet": a reader running ahead must never see a stale id
+    __threadfence_block();
+    q_items[p_seq % MFIT_QN] = p_item;
+    p_seq++;
+  };
   auto issue_next = [&]() {
-    const long long seg = p_item / a.n_cb;
+    const int seg = p_item / a.n_cb;
     const int s = (int)(issued % MFIT_STAGES);
-    const long long off = (seg * a.tiles_per_seg + p_k) * (long long)MFIT_TILE;
+    const long long off = ((long long)seg * a.tiles_per_seg + p_k) * (long long)MFIT_TILE;
     double* dst = buf + (size_t)s * NARR * MFIT_TILE;
     mfit_mbar_expect_tx(&full[s], STAGE_BYTES);
     mfit_tma_load_1d(dst, a.x + off, MFIT_TILE * 8u, &full[s]);
@@ -213,38 +267,60 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
     if (NARR > 2) mfit_tma_load_1d(dst + 2 * MFIT_TILE, a.w + off, MFIT_TILE * 8u, &full[s]);
     if (NARR > 3) mfit_tma_load_1d(dst + 3 * MFIT_TILE, a.c + off, MFIT_TILE * 8u, &full[s]);
     issued++;
-    if (++p_k == tiles_of(seg)) { p_k = 0; p_item++; }
+    if (++p_k == p_nt) fetch_item();
   };
-  if (tid == 0)
-    for (int s = 0; s < MFIT_STAGES && p_item < item_hi; s++) issue_next();
+  __syncthreads();  // mbarriers initialised, tables staged
+  if (tid == 0) {
+    fetch_item();
+    for (int s = 0; s < MFIT_STAGES && !p_done; s++) issue_next();
+  }
+  __syncthreads();  // q_items[0] published
 
-  auto chain_of = [&](long long item) -> long long { return (item % a.n_cb) * MFIT_CB + tid; };
   auto clamp_chain = [&](long long ch) -> long long { return ch < a.W ? ch : (long long)a.W - 1; };
 
-  // GUARDED: some fast routine on the path has a restricted domain (transcendentals of the model, log of log-poisson)
-  constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
-  Model m_next;
-  m_next.load(a, clamp_chain(chain_of(item_lo)));  // parameters of the first item, while its tiles are in flight
+  Model m_next[2];
+  auto load_params = [&](int it) {
+    const long long c0 = (long long)(it % a.n_cb) * MFIT_CB + tid;
+    m_next[0].load(a, clamp_chain(c0));
+    m_next[1].load(a, clamp_chain(c0 + MFIT_THREADS));
+  };
+  bool have_params = false;
   unsigned consumed = 0;
-  for (long long item = item_lo; item < item_hi; item++) {
-    const long long seg = item / a.n_cb;
-    const long long chain = chain_of(item);
-    const bool valid = chain < a.W;
-    const long long cl = clamp_chain(chain);
-    const bool live = valid && !(a.skip != nullptr && a.skip[cl] != 0);
-    const bool any_live = __syncthreads_or(live ? 1 : 0) != 0;  // a finished chain-block only drains its tiles
-    Model m = m_next;
-    if (item + 1 < item_hi) m_next.load(a, clamp_chain(chain_of(item + 1)));
-    m.setup();  // theta-only subexpressions
+  for (int seq = 0;; seq++) {
+    // the id of item seq was published before thread 0 passed the barrier that ended item seq - 1
+    const int item = q_items[seq % MFIT_QN];
+    if (item < 0) break;
+    const int seg = item / a.n_cb;
+    const long long cb0 = (long long)(item % a.n_cb) * MFIT_CB;
+    const long long chain[2] = {cb0 + tid, cb0 + MFIT_THREADS + tid};
+    bool live[2];
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const long long cl = clamp_chain(chain[c]);
+      live[c] = chain[c] < a.W && !(a.skip != nullptr && a.skip[cl] != 0);
+    }
+    const bool any_live = __syncthreads_or((live[0] || live[1]) ? 1 : 0) != 0;  // a finished chain-block only drains its tiles
+    const bool two = cb0 + MFIT_THREADS < a.W;                                  // CTA-uniform: second half of the block holds chains
+    if (!have_params) load_params(item);
+    Model m[2] = {m_next[0], m_next[1]};
+    {
+      // parameters of the next item one item ahead, if the producer has drawn it already (-2: not yet, -1: none)
+      const int nxt = q_items[(seq + 1) % MFIT_QN];
+      have_params = nxt >= 0;
+      if (have_params) load_params(nxt);
+    }
+    m[0].setup();  // theta-only subexpressions
+    m[1].setup();
     // warp-uniform: every chain of this warp stays inside the fast domain over the whole x range of the data set
-    const bool unguarded = !GUARDED || (MfitTerm<LL>::USES == 0 && __all_sync(0xffffffffu, m.safe(a) ? 1 : 0) != 0);
+    const bool unguarded =
+        MfitTerm<LL>::USES == 0 && __all_sync(0xffffffffu, (m[0].safe(a) && (!two || m[1].safe(a))) ? 1 : 0) != 0;
     const int nt = tiles_of(seg);
-    const long long t0 = seg * a.tiles_per_seg;
-    double acc0 = 0.0, acc1 = 0.0;
+    const long long t0 = (long long)seg * a.tiles_per_seg;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int k = 0; k < nt; k++, consumed++) {
       const int s = (int)(consumed % MFIT_STAGES);
       // refill the stage freed one tile ago (gives the other warps a tile of slack)
-      if (tid == 0 && consumed >= 1 && p_item < item_hi) {
+      if (tid == 0 && consumed >= 1 && !p_done) {
         const unsigned c1 = consumed - 1;
         mfit_mbar_wait(&empty[c1 % MFIT_STAGES], (c1 / MFIT_STAGES) & 1u);
         issue_next();
@@ -257,25 +333,24 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
         const double* cs = xs + (NARR > 3 ? 3 : 0) * MFIT_TILE;
         long long rem = a.n - (t0 + k) * (long long)MFIT_TILE;
         const int cnt = rem < MFIT_TILE ? (int)rem : MFIT_TILE;
-        if (unguarded) {
-          MfitNoGuard ng;
-          mfit_tile_pass<Model, LL, false>(m, xs, ys, ws, cs, cnt, acc0, acc1, ng);
-        } else {
-          const double save0 = acc0, save1 = acc1;
-          MfitGuard gd;
-          gd.reset();
-          mfit_tile_pass<Model, LL, false>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
-          if (gd.tripped()) {  // rare: overflow / NaN / log of a non-positive number ... -> redo the tile with libdevice math
-            acc0 = save0;
-            acc1 = save1;
-            mfit_tile_pass<Model, LL, true>(m, xs, ys, ws, cs, cnt, acc0, acc1, gd);
-          }
-        }
+        if (two) mfit_tile<Model, LL, 2>(m, unguarded, xs, ys, ws, cs, cnt, acc);
+        else mfit_tile<Model, LL, 1>(m, unguarded, xs, ys, ws, cs, cnt, acc);
       }
       __syncwarp();
       if ((tid & 31) == 0) mfit_mbar_arrive(&empty[s]);
     }
-    if (live) a.partial[(size_t)seg * a.stride + chain] = acc0 + acc1;
+    if (live[0]) a.partial[(size_t)seg * a.stride + chain[0]] = acc[0] + acc[1];
+    if (live[1]) a.partial[(size_t)seg * a.stride + chain[1]] = acc[2] + acc[3];
+    __syncthreads();  // thread 0 has requested every tile of this item, hence published the id of the next one
+  }
+  // the last CTA out re-arms the scheduler for the next launch on this stream
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(a.sched + 1, 1) == (int)gridDim.x - 1) {
+      a.sched[0] = 0;
+      a.sched[1] = 0;
+      __threadfence();
+    }
   }
 }
 

@@ -77,7 +77,7 @@ def test_log_poisson_matches_oracle(orc, name):
     w.close()
 
 
-@pytest.mark.parametrize("N", [0, 1, 2, 511, 512, 513, 1024, 4097])
+@pytest.mark.parametrize("N", [0, 1, 2, 127, 128, 129, 511, 512, 513, 1024, 4097])
 @pytest.mark.parametrize("W", [1, 128, 129])
 def test_ragged_sizes(orc, N, W):
     cfg = _family_cfg("gauss_lin", N, W, seed=N + W)
@@ -354,7 +354,7 @@ def test_full_size_c2_properties():
     w.close()
     x, y = cfg["data"][0]
     s = cfg["data_error"][0]
-    h = 51200   # a whole number of 512-point tiles, so the halves cover the same segments
+    h = 51200   # a whole number of 128-point tiles, so the halves cover the same segments
     cfg2 = dict(cfg)
     cfg2["function"] = [cfg["function"][0], cfg["function"][0]]
     cfg2["data"] = [[x[:h], y[:h]], [x[h:], y[h:]]]
