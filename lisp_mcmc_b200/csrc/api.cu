@@ -117,6 +117,9 @@ struct mfit_ctx {
   long long eval_launches = 0;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  // pinned bounce buffers for large device -> host reads (traces): pageable destinations are filled from here
+  char* stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2];
 };
 
 namespace {
@@ -359,6 +362,36 @@ void collect_timing(mfit_ctx* ctx) {
   ctx->ev_used = 0;
 }
 
+// device -> host copy of a large block into caller memory that is probably pageable: the DMA goes into two pinned
+// bounce buffers (full PCIe rate instead of the driver's pageable path) and the CPU copies chunk i out while chunk
+// i + 1 is in flight.  Returns after everything has landed in dst.
+constexpr size_t kStageBytes = (size_t)16 << 20;
+int d2h_staged(mfit_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes < ((size_t)1 << 20)) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  for (int i = 0; i < 2; i++)
+    if (!ctx->stage[i]) {
+      CU(cudaMallocHost(&ctx->stage[i], kStageBytes));
+      CU(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    }
+  const size_t n_chunks = (bytes + kStageBytes - 1) / kStageBytes;
+  auto chunk_len = [&](size_t i) { return i + 1 < n_chunks ? kStageBytes : bytes - i * kStageBytes; };
+  for (size_t i = 0; i <= n_chunks; i++) {
+    if (i < n_chunks) {
+      CU(cudaMemcpyAsync(ctx->stage[i & 1], (const char*)src + i * kStageBytes, chunk_len(i), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaEventRecord(ctx->stage_ev[i & 1], ctx->stream));
+    }
+    if (i >= 1) {
+      CU(cudaEventSynchronize(ctx->stage_ev[(i - 1) & 1]));
+      memcpy((char*)dst + (i - 1) * kStageBytes, ctx->stage[(i - 1) & 1], chunk_len(i - 1));
+    }
+  }
+  return 0;
+}
+
 template <class T>
 int chain_alloc(mfit_ctx* ctx, T** out, size_t count, bool zero = true) {
   void* p = nullptr;
@@ -562,6 +595,8 @@ void mfit_ctx_destroy(mfit_ctx* ctx) {
   free_dev(ctx->temps_dev); free_dev(ctx->z_dev); free_dev(ctx->u_dev); free_dev(ctx->lshared_dev);
   free_dev(ctx->active_dev); free_dev(ctx->flush_buf); free_dev(ctx->sched_dev);
   if (ctx->active_host) cudaFreeHost(ctx->active_host);
+  for (int i = 0; i < 2; i++)
+    if (ctx->stage[i]) { cudaFreeHost(ctx->stage[i]); cudaEventDestroy(ctx->stage_ev[i]); }
   if (ctx->poll_ev_made) for (auto& e : ctx->poll_ev) cudaEventDestroy(e);
   for (auto& p : ctx->ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (ctx->comm) mfit_nccl_comm_destroy(ctx->comm);
@@ -1068,10 +1103,10 @@ int mfit_trace_read(mfit_ctx* ctx, int64_t take, double* theta, double* prob, in
   if (e == cudaSuccess) {
     mfit_launch_trace_gather(c, take, dt, dp, dn, ctx->stream);
     ctx->launches++;
-    if (theta) e = cudaMemcpyAsync(theta, dt, sizeof(double) * W * take * c.P, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && prob) e = cudaMemcpyAsync(prob, dp, sizeof(double) * W * take, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && n_valid) e = cudaMemcpyAsync(n_valid, dn, sizeof(long long) * W, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (n_valid) e = cudaMemcpyAsync(n_valid, dn, sizeof(long long) * W, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && theta) rc = d2h_staged(ctx, theta, dt, sizeof(double) * W * take * c.P);
+    if (e == cudaSuccess && rc == 0 && prob) rc = d2h_staged(ctx, prob, dp, sizeof(double) * W * take);
+    if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(ctx->stream);
   }
   if (e != cudaSuccess) rc = fail(ctx, e == cudaErrorMemoryAllocation ? MFIT_ERR_NOMEM : MFIT_ERR_CUDA, "trace_read: %s", cudaGetErrorString(e));
   free_dev(dt); free_dev(dp); free_dev(dn);

@@ -377,3 +377,21 @@ def test_errors_are_codes_not_crashes():
         w.adaptive_steps_full(n=500, z=np.zeros((4, 10, 5)), u=np.zeros((4, 10)))
     assert e.value.code == _lib.ERR_STREAM
     w.close()
+
+
+def test_multi_gpu_sharding_is_bit_identical():
+    """chains and data sets sharded over every GPU of the box (tests/mgpu/mgpu_check.py under torchrun) reproduce the
+    single-GPU traces bit for bit; skipped on a one-GPU box"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = min(n, 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", "29731",
+                        os.path.join(root, "tests", "mgpu", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
