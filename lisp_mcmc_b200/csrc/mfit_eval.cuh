@@ -35,7 +35,7 @@
 #define MFIT_THREADS 128 /* threads per CTA */
 #define MFIT_CB 256      /* chains per CTA: two per thread (thread t: chains t and t + MFIT_THREADS of the block) */
 #ifndef MFIT_MIN_CTAS
-#define MFIT_MIN_CTAS 4   /* CTAs per SM the register allocation is bounded for */
+#define MFIT_MIN_CTAS 3   /* CTAs per SM the register allocation is bounded for */
 #endif
 #define MFIT_QN 8        /* ring of item ids handed from the producer thread to the CTA */
 #define MFIT_MAXK 16     /* parameters a built-in family may gather */

@@ -4,7 +4,7 @@
 // pipe (ncu: profiles/), so what matters is the number of FP64 instructions per call, and that the other
 // instructions (integer, LDS, select) stay below one per FP64 instruction so that they hide in the pipe's shadow.
 // CUDA's libdevice spends 22 / 46 / 32 DFMA issue slots on exp / log / sin (measured, mfit_measure_fp64); these
-// spend 10 / 13 / 14 FP64 instructions: table-driven range reduction (Tang) with the tables staged in shared
+// spend 9 / 13 / 15 FP64 instructions: table-driven range reduction (Tang) with the tables staged in shared
 // memory, short polynomials with coefficients taken straight from constant memory, exponent arithmetic on the
 // integer pipe.  Accuracy is <= 2.4 ulp (tools/check_math.cpp measures it against long double), far inside the
 // 1e-12 relative tolerance on log-likelihoods.
@@ -41,7 +41,7 @@ __device__ __forceinline__ unsigned mfit_umax(unsigned a, unsigned b) { return m
 // crossbar ran at 62 % next to a 68 % FP64 pipe).  Each table is therefore replicated so that every lane of a
 // crossbar phase reads its own banks: 16 copies of the 8-byte exp entries (a 64-bit load is served in two phases of
 // 16 lanes), 8 copies of the 16-byte log entries (four phases of 8 lanes).  Entry j of copy c sits at [j][c].
-__shared__ __align__(16) unsigned long long mfit_s_exp2[64 * 16];
+__shared__ __align__(16) unsigned long long mfit_s_exp2[256 * 16];
 __shared__ __align__(16) double mfit_s_log[128 * 8 * 2];
 #endif
 
@@ -54,7 +54,7 @@ __shared__ __align__(16) double mfit_s_log[128 * 8 * 2];
 // every thread of the CTA calls this before the first __syncthreads of the kernel
 __device__ __forceinline__ void mfit_math_stage(int uses, int tid, int nthreads) {
   if (uses & MFIT_USES_EXP)
-    for (int i = tid; i < 64 * 16; i += nthreads) mfit_s_exp2[i] = mfit_c_exp2[i >> 4];
+    for (int i = tid; i < 256 * 16; i += nthreads) mfit_s_exp2[i] = mfit_c_exp2[i >> 4];
   if (uses & MFIT_USES_LOG)
     for (int i = tid; i < 128 * 8; i += nthreads) {
       mfit_s_log[2 * i] = mfit_c_log[2 * (i >> 3)];
@@ -66,17 +66,19 @@ __device__ __forceinline__ void mfit_math_stage(int uses, int tid, int nthreads)
 // sticky record of the most extreme argument each fast routine has seen since reset()
 struct MfitGuard {
   static constexpr bool ON = true;
-  unsigned e, g, l, s;
-  __device__ __forceinline__ void reset() { e = 0u; g = 0u; l = 0u; s = 0u; }
+  unsigned e, g, l, s, d;
+  __device__ __forceinline__ void reset() { e = 0u; g = 0u; l = 0u; s = 0u; d = 0u; }
   __device__ __forceinline__ void see_exp(unsigned v) { e = mfit_umax(e, v); }
   __device__ __forceinline__ void see_gauss(unsigned v) { g = mfit_umax(g, v); }
   __device__ __forceinline__ void see_log(unsigned v) { l = mfit_umax(l, v); }
   __device__ __forceinline__ void see_sin(unsigned v) { s = mfit_umax(s, v); }
+  __device__ __forceinline__ void see_div(unsigned v) { d = mfit_umax(d, v); }
   __device__ __forceinline__ bool tripped() const {
     return e >= 0x40862000u      // exp: |x| >= 708 (overflow / underflow), inf, nan
         || g > 0x7ff00000u       // gauss: nan (underflow and +-inf are clamped in place, see mfit_gauss_parts)
         || l >= 0x7fe00000u      // log: x <= 0, subnormal, inf, nan   (l tracks hi(x) - 0x00100000 as unsigned)
-        || s >= 0x40f86a00u;     // sin/cos: |x| >= 1e5, inf, nan
+        || s >= 0x40f86a00u      // sin/cos: |x| >= 1e5, inf, nan
+        || d >= 0x7fb00000u;     // rcp: |x| outside [2^-1021, 2^1022), zero, inf, nan   (d tracks |hi(x)| - 0x00200000)
   }
 };
 // The same interface with nothing behind it: used when a model has proved, from its parameters and the x range of
@@ -89,6 +91,7 @@ struct MfitNoGuard {
   __device__ __forceinline__ void see_gauss(unsigned) {}
   __device__ __forceinline__ void see_log(unsigned) {}
   __device__ __forceinline__ void see_sin(unsigned) {}
+  __device__ __forceinline__ void see_div(unsigned) {}
   __device__ __forceinline__ bool tripped() const { return false; }
 };
 
@@ -97,69 +100,68 @@ struct MfitNoGuard {
  * modulo a power of two that divides 2^31). */
 #define MFIT_MAGIC 6755401588539392.0
 
-// 2^(k/64) for the integer k held (biased) in the low word of tmp = q + MAGIC: table entry (k & 63), exponent
-// k >> 6 added on the integer pipe (the table entries are pre-biased so that a plain k << 14 does both jobs).
-// Three integer instructions and one conflict-free LDS.64.
-__device__ __forceinline__ double mfit_exp2_64th(double tmp) {
+// 2^(k/256) for the integer k held (biased) in the low word of tmp = q + MAGIC: table entry (k & 255), exponent
+// k >> 8 added on the integer pipe (the table entries are pre-biased so that a plain k << 12 does both jobs).
+// Three integer instructions and one conflict-free LDS.64.  256 entries (32 KB replicated) instead of 64 buy one
+// polynomial degree, i.e. one FP64 instruction per call -- the pipe this code is bound by.
+__device__ __forceinline__ double mfit_exp2_256th(double tmp) {
   const int k = mfit_lo(tmp);
 #ifdef MFIT_HOST_TEST
-  const unsigned long long t = mfit_c_exp2[k & 63];
+  const unsigned long long t = mfit_c_exp2[k & 255];
 #else
   const char* base = reinterpret_cast<const char*>(mfit_s_exp2) + ((threadIdx.x & 15u) << 3);
-  const unsigned long long t = *reinterpret_cast<const unsigned long long*>(base + ((k & 63) << 7));
+  const unsigned long long t = *reinterpret_cast<const unsigned long long*>(base + ((k & 255) << 7));
 #endif
-  return mfit_mk((int)(t >> 32) + (k << 14), (int)t);
+  return mfit_mk((int)(t >> 32) + (k << 12), (int)t);
 }
 
-// exp(x): 10 FP64 instructions
+// exp(x): 9 FP64 instructions
 template <bool SLOW, class G>
 __device__ __forceinline__ double mfit_exp_t(double x, G& gd) {
   if (SLOW) return exp(x);
   if (G::ON) gd.see_exp((unsigned)mfit_hi(x) & 0x7fffffffu);
-  const double tmp = fma(x, MFIT_K_L2E64, MFIT_MAGIC);  // x 64/ln2
+  const double tmp = fma(x, MFIT_K_L2E256, MFIT_MAGIC);  // x 256/ln2
   const double kd = tmp - MFIT_MAGIC;
-  double r = fma(kd, -0x1.62e42fef00000p-7, x);         // ln2/64 in two pieces (Cody-Waite); the first is a 32-bit constant
-  r = fma(kd, -0x1.473de6af278edp-40, r);
-  double p = fma(r, MFIT_K_EXN5, MFIT_K_EXN4);
-  p = fma(r, p, MFIT_K_EXN3);
+  double r = fma(kd, -0x1.62e42fef00000p-9, x);          // ln2/256 in two pieces (Cody-Waite); the first is a 32-bit constant
+  r = fma(kd, -0x1.473de6af278edp-42, r);
+  double p = fma(r, MFIT_K_EXN4, MFIT_K_EXN3);           // |r| <= ln2/512: degree 4 is good to 4e-17
   p = fma(r, p, 0.5);
   p = fma(r, p, 1.0);
   p = fma(r, p, 1.0);
-  return mfit_exp2_64th(tmp) * p;
+  return mfit_exp2_256th(tmp) * p;
 }
 
-// exp(-zs^2 ln2/64) = s * (1 + r q)  (zs = z sqrt(32/ln2) turns exp(-z^2/2) into this form): the square is both the
-// argument and, through one FMA each, its rounding to 1/64 octaves and the exact remainder r.  Three FP64
-// instructions here; the caller runs the polynomial (coefficients MFIT_K_EXS1..5, which it may pre-multiply by its
+// exp(-zs^2 ln2/256) = s * (1 + r q)  (zs = z sqrt(128/ln2) turns exp(-z^2/2) into this form): the square is both the
+// argument and, through one FMA each, its rounding to 1/256 octaves and the exact remainder r.  Three FP64
+// instructions here; the caller runs the polynomial (coefficients MFIT_K_EXS1..4, which it may pre-multiply by its
 // amplitude) and folds s:  f = fma(s, a (1 + r q), rest).
 template <class G>
 __device__ __forceinline__ void mfit_gauss_reduce(double zs, double* s, double* r, G& gd) {
   if (G::ON) {
-    // |zs| is clamped on the integer pipe at 255.875 (exp(-z^2/2) ~ 2^-1023, which the arithmetic below turns into
+    // |zs| is clamped on the integer pipe at 511.75 (exp(-z^2/2) ~ 2^-1023, which the arithmetic below turns into
     // a subnormal-sized number, i.e. zero next to any amplitude): wild proposals underflow all the time during the
     // reference's start-up phase (its first l-matrix is diag(theta)), so that case must not leave the fast path.
     const unsigned ah = (unsigned)mfit_hi(zs) & 0x7fffffffu;
     gd.see_gauss(ah);
-    zs = mfit_mk((int)min(ah, 0x406ffc00u), mfit_lo(zs));
+    zs = mfit_mk((int)min(ah, 0x407ffc00u), mfit_lo(zs));
   }
   const double tmp = fma(-zs, zs, MFIT_MAGIC);
   const double kd = tmp - MFIT_MAGIC;
   *r = fma(-zs, zs, -kd);
-  *s = mfit_exp2_64th(tmp);
+  *s = mfit_exp2_256th(tmp);
 }
-// the plain form (amplitude 1): exp(-zs^2 ln2/64) = s * p
+// the plain form (amplitude 1): exp(-zs^2 ln2/256) = s * p
 template <class G>
 __device__ __forceinline__ void mfit_gauss_parts(double zs, double* s, double* p, G& gd) {
   double r;
   mfit_gauss_reduce(zs, s, &r, gd);
-  double q = fma(r, MFIT_K_EXS5, MFIT_K_EXS4);
-  q = fma(r, q, MFIT_K_EXS3);
+  double q = fma(r, MFIT_K_EXS4, MFIT_K_EXS3);
   q = fma(r, q, MFIT_K_EXS2);
   q = fma(r, q, MFIT_K_EXS1);
   *p = fma(r, q, 1.0);
 }
-#define MFIT_GAUSS_ZLIMIT 255.875 /* |zs| beyond this needs the clamp of the guarded form */
-#define MFIT_GAUSS_ZSCALE 0x1.b2da4e9808a53p+2 /* sqrt(32/ln2) */
+#define MFIT_GAUSS_ZLIMIT 511.75 /* |zs| beyond this needs the clamp of the guarded form */
+#define MFIT_GAUSS_ZSCALE 0x1.b2da4e9808a53p+3 /* sqrt(128/ln2) */
 
 // log(x): 13 FP64 instructions.  x = 2^e m with m in [0.707, 1.414); r = m c_i - 1 (one FMA, exact before rounding),
 // log x = e ln2 + L_i + log1p(r); the table intervals next to 1 have c = 1 (1/2) and L = 0 exactly, which keeps full
@@ -193,41 +195,75 @@ __device__ __forceinline__ double mfit_log_t(double x, G& gd) {
   return fma(ed, 0x1.473de6af278edp-34, lp) + base;       // ln2_lo rides on the small term
 }
 
-// sin and cos share the reduction x = n pi/2 + r (Cody-Waite, three pieces: exact for |n| < 2^20) and the
-// polynomial body; the quadrant picks the coefficient set with selects (integer pipe), not with a branch.
-// 14 FP64 instructions.
-__device__ __forceinline__ double mfit_sincos_core(double x, int quad_shift) {
-  const double tmp = fma(x, MFIT_K_2OPI, MFIT_MAGIC);
+// 1/x: the MUFU.RCP64H seed (about 22 bits) and two Newton steps -- 4 FP64 instructions and no branch, against the
+// 8 FP64 instructions, the range test and the out-of-line slow path of the compiler's IEEE division (ncu: the
+// Lorentzian loop spent more issue slots on that scaffolding than on FP64).  About 1 ulp, not correctly rounded.
+template <bool SLOW, class G>
+__device__ __forceinline__ double mfit_rcp_t(double x, G& gd) {
+  if (SLOW) return 1.0 / x;
+  if (G::ON) gd.see_div(((unsigned)mfit_hi(x) & 0x7fffffffu) - 0x00200000u);
+  double y;
+#ifdef MFIT_HOST_TEST
+  y = (double)(float)(1.0 / x);
+#else
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#endif
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// sin(x): x = n pi + r (Cody-Waite, three pieces: exact for |n| < 2^20), |r| <= pi/2, sin x = (-1)^n sin r with ONE odd
+// polynomial of degree 17 for sin r -- 15 FP64 instructions and two integer ones for the sign.  (A quadrant scheme
+// with separate sine and cosine polynomials saves one FP64 instruction but has to pick its coefficients per lane:
+// 18 selects per call, which made the sinusoid kernels issue-bound instead of FP64-bound.)
+__device__ __forceinline__ double mfit_sin_core(double x) {
+  const double tmp = fma(x, MFIT_K_1OPI, MFIT_MAGIC);
   const double nd = tmp - MFIT_MAGIC;
-  double r = fma(nd, -0x1.921fb54400000p+0, x);
-  r = fma(nd, -0x1.0b4611a600000p-34, r);
-  r = fma(nd, -0x1.3198a2e037073p-69, r);
-  const int n = mfit_lo(tmp) + quad_shift;
-  const bool c = (n & 1) != 0;  // odd quadrant: cosine polynomial
+  double r = fma(nd, -0x1.921fb54400000p+1, x);
+  r = fma(nd, -0x1.0b4611a600000p-33, r);
+  r = fma(nd, -0x1.3198a2e037073p-68, r);
   const double r2 = r * r;
-  // cos r = 1 + r2 (c2 + r2 (c4 + ... + r2 c16))          sin r = r (1 + r2 (s3 + r2 (s5 + ... + r2 s15)))
-  double q = c ? MFIT_K_CS16 : MFIT_K_SN15;
-  q = fma(r2, q, c ? MFIT_K_CS14 : MFIT_K_SN13);
-  q = fma(r2, q, c ? MFIT_K_CS12 : MFIT_K_SN11);
-  q = fma(r2, q, c ? MFIT_K_CS10 : MFIT_K_SN9);
-  q = fma(r2, q, c ? MFIT_K_CS8 : MFIT_K_SN7);
-  q = fma(r2, q, c ? MFIT_K_CS6 : MFIT_K_SN5);
-  q = fma(r2, q, c ? MFIT_K_CS4 : MFIT_K_SN3);
-  q = fma(r2, q, c ? -0.5 : 1.0);
-  const double res = fma(c ? r2 : r, q, c ? 1.0 : 0.0);
-  return mfit_mk(mfit_hi(res) ^ ((n & 2) << 30), mfit_lo(res));  // quadrants 2, 3: negate
+  double q = fma(r2, MFIT_K_SP17, MFIT_K_SP15);
+  q = fma(r2, q, MFIT_K_SP13);
+  q = fma(r2, q, MFIT_K_SP11);
+  q = fma(r2, q, MFIT_K_SP9);
+  q = fma(r2, q, MFIT_K_SP7);
+  q = fma(r2, q, MFIT_K_SP5);
+  q = fma(r2, q, MFIT_K_SP3);
+  const double res = fma(r2 * r, q, r);
+  return mfit_mk(mfit_hi(res) ^ (mfit_lo(tmp) << 31), mfit_lo(res));  // odd n: negate
 }
 template <bool SLOW, class G>
 __device__ __forceinline__ double mfit_sin_t(double x, G& gd) {
   if (SLOW) return sin(x);
   if (G::ON) gd.see_sin((unsigned)mfit_hi(x) & 0x7fffffffu);
-  return mfit_sincos_core(x, 0);
+  return mfit_sin_core(x);
 }
+// cos x = sin(x + pi/2); the shift is added in two pieces so that its rounding error stays below that of the reduction
 template <bool SLOW, class G>
 __device__ __forceinline__ double mfit_cos_t(double x, G& gd) {
   if (SLOW) return cos(x);
   if (G::ON) gd.see_sin((unsigned)mfit_hi(x) & 0x7fffffffu);
-  return mfit_sincos_core(x, 1);
+  // n = round(x/pi + 1/2) would need a half-integer magic constant; instead reduce |x| first and shift the remainder
+  const double t2 = fma(fabs(x), MFIT_K_1OPI, MFIT_MAGIC);
+  const double nd = t2 - MFIT_MAGIC;
+  double r = fma(nd, -0x1.921fb54400000p+1, fabs(x));
+  r = fma(nd, -0x1.0b4611a600000p-33, r);
+  r = fma(nd, -0x1.3198a2e037073p-68, r);       // |x| = n pi + r, |r| <= pi/2;  cos x = (-1)^n cos r = (-1)^n sin(pi/2 - |r|)
+  double rr = 0x1.921fb54442d18p+0 - fabs(r);
+  rr = rr + 0x1.1a62633145c07p-54;
+  const double r2 = rr * rr;
+  double q = fma(r2, MFIT_K_SP17, MFIT_K_SP15);
+  q = fma(r2, q, MFIT_K_SP13);
+  q = fma(r2, q, MFIT_K_SP11);
+  q = fma(r2, q, MFIT_K_SP9);
+  q = fma(r2, q, MFIT_K_SP7);
+  q = fma(r2, q, MFIT_K_SP5);
+  q = fma(r2, q, MFIT_K_SP3);
+  const double res = fma(r2 * rr, q, rr);
+  return mfit_mk(mfit_hi(res) ^ (mfit_lo(t2) << 31), mfit_lo(res));
 }
 
 #endif  // MFIT_MATH_CUH

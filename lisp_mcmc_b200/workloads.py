@@ -29,7 +29,7 @@ def c1(W=1):
     return dict(name="C1", function=[builtin("lorentz", keys)], data=[[x, y]], data_error=1e-7, keys=keys,
                 theta_star=th, theta0=theta0, log_liklihood="log-liklihood-normal",
                 log_prior=[[("a", 0.0, 1e-4), ("x0", 2000.0, 3000.0), ("gamma", 1.0, 500.0), ("c", -1e-5, 1e-5)]],
-                steps=100000, flop_per_point=9, transc_per_point={}, fp64_instr_per_point=13)
+                steps=100000, flop_per_point=9, transc_per_point={}, fp64_instr_per_point=9)
 
 
 def c2(W=4096, N=100000):
@@ -43,7 +43,7 @@ def c2(W=4096, N=100000):
     keys = ["a", "mu", "s", "b0", "b1"]
     return dict(name="C2", function=[builtin("gauss_lin", keys)], data=[[x, y]], data_error=[sig], keys=keys,
                 theta_star=th, theta0=_jitter(th, W, 0.05, 2002), log_liklihood="log-liklihood-normal",
-                log_prior="log-prior-flat", steps=2000, flop_per_point=12, transc_per_point={"exp": 1}, fp64_instr_per_point=14)
+                log_prior="log-prior-flat", steps=2000, flop_per_point=12, transc_per_point={"exp": 1}, fp64_instr_per_point=13)
 
 
 def c3(W=16384, N=1000000):
@@ -56,7 +56,7 @@ def c3(W=16384, N=1000000):
     keys = ["a", "omega", "phi", "c"]
     return dict(name="C3", function=[builtin("sinus", keys)], data=[[x, y]], data_error=1.0, keys=keys,
                 theta_star=th, theta0=_jitter(th, W, 0.02, 2003), log_liklihood="log-poisson",
-                log_prior="log-prior-flat", steps=200, flop_per_point=7, transc_per_point={"sin": 1, "log": 1}, fp64_instr_per_point=31)
+                log_prior="log-prior-flat", steps=200, flop_per_point=7, transc_per_point={"sin": 1, "log": 1}, fp64_instr_per_point=32)
 
 
 def c4(W=1024, D=8, N=1000000):
@@ -84,7 +84,7 @@ def c4(W=1024, D=8, N=1000000):
         priors.append(families.log_prior_nv_text(sfx))
     return dict(name="C4", function=fns, data=data, data_error=1e-7, keys=keys, theta_star=th,
                 theta0=_jitter(th, W, 1e-4, 2004), log_liklihood="log-liklihood-normal", log_prior=priors,
-                steps=200, flop_per_point=14, transc_per_point={"div": 2}, fp64_instr_per_point=24)
+                steps=200, flop_per_point=14, transc_per_point={"div": 2}, fp64_instr_per_point=16)
 
 
 def c5(W=65536, N=10000000):
@@ -97,7 +97,7 @@ def c5(W=65536, N=10000000):
     keys = ["c0", "c1", "c2", "c3", "c4", "c5", "k"]
     return dict(name="C5", function=[USER_POLY5_EXP], data=[[x, y]], data_error=0.01, keys=keys, theta_star=th,
                 theta0=_jitter(th, W, 0.01, 2005), log_liklihood="log-liklihood-normal", log_prior="log-prior-flat",
-                steps=20, flop_per_point=16, transc_per_point={"exp": 1}, fp64_instr_per_point=20)
+                steps=20, flop_per_point=16, transc_per_point={"exp": 1}, fp64_instr_per_point=19)
 
 
 CONFIGS = {"C1": c1, "C2": c2, "C3": c3, "C4": c4, "C5": c5}
