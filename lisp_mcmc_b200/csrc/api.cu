@@ -14,9 +14,12 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -366,6 +369,21 @@ void collect_timing(mfit_ctx* ctx) {
 // bounce buffers (full PCIe rate instead of the driver's pageable path) and the CPU copies chunk i out while chunk
 // i + 1 is in flight.  Returns after everything has landed in dst.
 constexpr size_t kStageBytes = (size_t)16 << 20;
+// pageable destinations are usually untouched pages: the copy out of the bounce buffer is page-fault bound on one
+// core, so it is split over a few threads
+void copy_out(char* dst, const char* src, size_t bytes) {
+  const int nt = bytes >= ((size_t)4 << 20) ? 4 : 1;
+  if (nt == 1) { memcpy(dst, src, bytes); return; }
+  std::thread th[3];
+  const size_t per = (bytes / nt + 4095) & ~(size_t)4095;
+  for (int t = 1; t < nt; t++) {
+    const size_t lo = per * t, hi = lo + per < bytes ? lo + per : bytes;
+    if (lo < hi) th[t - 1] = std::thread([=] { memcpy(dst + lo, src + lo, hi - lo); });
+  }
+  memcpy(dst, src, per < bytes ? per : bytes);
+  for (auto& t : th) if (t.joinable()) t.join();
+}
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 int d2h_staged(mfit_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes < ((size_t)1 << 20)) {
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -386,7 +404,7 @@ int d2h_staged(mfit_ctx* ctx, void* dst, const void* src, size_t bytes) {
     }
     if (i >= 1) {
       CU(cudaEventSynchronize(ctx->stage_ev[(i - 1) & 1]));
-      memcpy((char*)dst + (i - 1) * kStageBytes, ctx->stage[(i - 1) & 1], chunk_len(i - 1));
+      copy_out((char*)dst + (i - 1) * kStageBytes, ctx->stage[(i - 1) & 1], chunk_len(i - 1));
     }
   }
   return 0;
@@ -1100,16 +1118,21 @@ int mfit_trace_read(mfit_ctx* ctx, int64_t take, double* theta, double* prob, in
   if (theta) e = cudaMalloc(&dt, sizeof(double) * W * take * c.P);
   if (e == cudaSuccess && prob) e = cudaMalloc(&dp, sizeof(double) * W * take);
   if (e == cudaSuccess && n_valid) e = cudaMalloc(&dn, sizeof(long long) * W);
+  const bool dbg = getenv("MFIT_DEBUG_TIMING") != nullptr;
+  const double t_a = now_ms();
   if (e == cudaSuccess) {
     mfit_launch_trace_gather(c, take, dt, dp, dn, ctx->stream);
     ctx->launches++;
+    if (dbg) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "trace_read: malloc+gather %.1f ms\n", now_ms() - t_a); }
     if (n_valid) e = cudaMemcpyAsync(n_valid, dn, sizeof(long long) * W, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && theta) rc = d2h_staged(ctx, theta, dt, sizeof(double) * W * take * c.P);
     if (e == cudaSuccess && rc == 0 && prob) rc = d2h_staged(ctx, prob, dp, sizeof(double) * W * take);
     if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(ctx->stream);
   }
   if (e != cudaSuccess) rc = fail(ctx, e == cudaErrorMemoryAllocation ? MFIT_ERR_NOMEM : MFIT_ERR_CUDA, "trace_read: %s", cudaGetErrorString(e));
+  if (dbg) fprintf(stderr, "trace_read: +copies %.1f ms\n", now_ms() - t_a);
   free_dev(dt); free_dev(dp); free_dev(dn);
+  if (dbg) fprintf(stderr, "trace_read: +free %.1f ms\n", now_ms() - t_a);
   return rc;
 }
 

@@ -139,7 +139,7 @@ __device__ __forceinline__ double* lp_ptr(const MfitChains& c, int d) {
 // MFIT_RED_T threads handles 32 chains x MFIT_RED_S slices; slice k adds the segments [k B, (k+1) B), B =
 // ceil(n_seg / MFIT_RED_S), in order, and the slice sums are then added in slice order.  The shape depends on n_seg
 // only (i.e. on the point count), so every bit of the result is independent of chain count, grid and GPU count.
-#define MFIT_RED_S 8
+#define MFIT_RED_S 16
 #define MFIT_RED_T (32 * MFIT_RED_S)
 // called by all MFIT_RED_T threads of the block (w may be >= c.W: such threads only take part in the barriers);
 // the result is valid in the threads of slice 0
@@ -151,8 +151,17 @@ __device__ double reduce_ll(const MfitChains& c, int d, long long w, int slice, 
   if (w < c.W) {
     const int lo = slice * B, hi = min(s.n_seg, lo + B);
     if (lo < hi) {
-      sum = s.partial[(size_t)lo * c.stride + w];
-      for (int k = lo + 1; k < hi; k++) sum = sum + s.partial[(size_t)k * c.stride + w];
+      const double* p = s.partial + (size_t)lo * c.stride + w;
+      sum = *p;
+      int k = lo + 1;
+      for (; k + 8 <= hi; k += 8) {  // eight loads in flight, added in order
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = p[(size_t)(k - lo + j) * c.stride];
+#pragma unroll
+        for (int j = 0; j < 8; j++) sum = sum + v[j];
+      }
+      for (; k < hi; k++) sum = sum + p[(size_t)(k - lo) * c.stride];
     }
   }
   __syncthreads();  // red is free again

@@ -208,7 +208,8 @@ __device__ __forceinline__ void mfit_tile(const Model* m, bool unguarded, const 
 // items (segment, chain-block) -- chain-block fastest -- from a.sched[0] until they run out, so there is no wave
 // quantisation, no tail longer than one item, and the prologue (mbarriers, math tables) is paid once per CTA.
 // Thread 0 is the producer: it draws the next item while the tiles of the current one are still being consumed, keeps
-// MFIT_STAGES tiles in flight across item boundaries and publishes item ids through a small ring in shared memory;
+// MFIT_STAGES tiles in flight across item boundaries and publishes item ids through a small ring in shared memory
+// (the warps of a CTA are coupled by the mbarriers of the tile ring only, never by a CTA-wide barrier);
 // the parameters of the next item are loaded into registers one item ahead.
 template <class Model, int LL>
 __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
@@ -287,8 +288,10 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   bool have_params = false;
   unsigned consumed = 0;
   for (int seq = 0;; seq++) {
-    // the id of item seq was published before thread 0 passed the barrier that ended item seq - 1
-    const int item = q_items[seq % MFIT_QN];
+    // No CTA-wide barrier per item: the id of item seq is published by thread 0 right after it has requested the last
+    // tile of item seq - 1 (which every warp had to wait for), and the slot reads -2 until then.
+    int item;
+    do { item = q_items[seq % MFIT_QN]; } while (item == -2);
     if (item < 0) break;
     const int seg = item / a.n_cb;
     const long long cb0 = (long long)(item % a.n_cb) * MFIT_CB;
@@ -299,7 +302,7 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
       const long long cl = clamp_chain(chain[c]);
       live[c] = chain[c] < a.W && !(a.skip != nullptr && a.skip[cl] != 0);
     }
-    const bool any_live = __syncthreads_or((live[0] || live[1]) ? 1 : 0) != 0;  // a finished chain-block only drains its tiles
+    const bool any_live = __any_sync(0xffffffffu, (live[0] || live[1]) ? 1 : 0) != 0;  // a finished warp only drains its tiles
     const bool two = cb0 + MFIT_THREADS < a.W;                                  // CTA-uniform: second half of the block holds chains
     if (!have_params) load_params(item);
     Model m[2] = {m_next[0], m_next[1]};
@@ -341,8 +344,8 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
     }
     if (live[0]) a.partial[(size_t)seg * a.stride + chain[0]] = acc[0] + acc[1];
     if (live[1]) a.partial[(size_t)seg * a.stride + chain[1]] = acc[2] + acc[3];
-    __syncthreads();  // thread 0 has requested every tile of this item, hence published the id of the next one
   }
+  __syncthreads();
   // the last CTA out re-arms the scheduler for the next launch on this stream
   if (tid == 0) {
     __threadfence();
