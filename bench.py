@@ -257,7 +257,7 @@ def main():
         e2e_value = W_total * K * N / (e2e_ms_max * 1e-3)
         fpp = flops_per_point(base, costs)
         per_launch_s = ksec.value / max(klaunch.value, 1)
-        evals = W_per_gpu * N
+        evals = W_per_gpu * N * K / max(klaunch.value, 1)   # point-evals per likelihood-kernel launch (one launch per data set)
         instr = float(base["fp64_instr_per_point"])
         achieved_tf = evals * instr * 2.0 / per_launch_s / 1e12
         survey_tf = evals * fpp / per_launch_s / 1e12
@@ -271,7 +271,9 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                         "what": "walker_create (host x,y,sigma,theta0 -> HBM) + %d adaptive steps + trace read-back" % K},
                 "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma.value / 1e12, "unit": "TFLOP/s",
-                             "frac": achieved_tf / (dfma.value / 1e12), "traffic": None,
+                             "frac": achieved_tf / (dfma.value / 1e12),
+                             # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r01_eval_kernel_ncu.md)
+                             "traffic": 2638336 if args.config == "C2" else None,
                              "what": "FP64-pipe instructions executed (%.1f per point-eval, SASS count, x2 flop) / "
                                      "kernel time, against the DFMA issue peak" % instr,
                              "peak_source": "DFMA issue peak measured live by mfit_measure_fp64 (MEASURED_PEAKS.json has no FP64 figure)",

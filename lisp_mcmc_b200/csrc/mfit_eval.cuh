@@ -154,7 +154,7 @@ struct MfitTerm<MFITK_POISSON> {
 #endif
 template <class Model, int LL, bool SLOW, int NC, class G>
 __device__ __forceinline__ void mfit_tile_pass(const Model* m, const double* xs, const double* ys, const double* ws,
-                                               const double* cs, int cnt, double* acc, G& gd) {
+                                               const double* cs, int cnt, double* acc, G* gd) {
   const int pairs = cnt >> 1;
   const double2* x2 = reinterpret_cast<const double2*>(xs);
   const double2* y2 = reinterpret_cast<const double2*>(ys);
@@ -166,17 +166,17 @@ __device__ __forceinline__ void mfit_tile_pass(const Model* m, const double* xs,
     const double2 xv = x2[i], yv = y2[i], wv = w2[i], cv = c2[i];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      const double f0 = m[c].template eval<SLOW>(xv.x, gd);
-      const double f1 = m[c].template eval<SLOW>(xv.y, gd);
-      acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], f0, yv.x, wv.x, cv.x, gd);
-      acc[2 * c + 1] = MfitTerm<LL>::template add<SLOW>(acc[2 * c + 1], f1, yv.y, wv.y, cv.y, gd);
+      const double f0 = m[c].template eval<SLOW>(xv.x, gd[c]);
+      const double f1 = m[c].template eval<SLOW>(xv.y, gd[c]);
+      acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], f0, yv.x, wv.x, cv.x, gd[c]);
+      acc[2 * c + 1] = MfitTerm<LL>::template add<SLOW>(acc[2 * c + 1], f1, yv.y, wv.y, cv.y, gd[c]);
     }
   }
   if (cnt & 1) {
     const int i = cnt - 1;
 #pragma unroll
     for (int c = 0; c < NC; c++)
-      acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], m[c].template eval<SLOW>(xs[i], gd), ys[i], ws[i], cs[i], gd);
+      acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], m[c].template eval<SLOW>(xs[i], gd[c]), ys[i], ws[i], cs[i], gd[c]);
   }
 }
 
@@ -186,19 +186,27 @@ __device__ __forceinline__ void mfit_tile(const Model* m, bool unguarded, const 
                                           const double* ws, const double* cs, int cnt, double* acc) {
   constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
   if (!GUARDED || unguarded) {
-    MfitNoGuard ng;
+    MfitNoGuard ng[NC];
     mfit_tile_pass<Model, LL, false, NC>(m, xs, ys, ws, cs, cnt, acc, ng);
   } else {
     double save[2 * NC];
 #pragma unroll
     for (int k = 0; k < 2 * NC; k++) save[k] = acc[k];
-    MfitGuard gd;
-    gd.reset();
-    mfit_tile_pass<Model, LL, false, NC>(m, xs, ys, ws, cs, cnt, acc, gd);
-    if (gd.tripped()) {  // rare: overflow / NaN / log of a non-positive number ...
+    MfitGuard gd[NC];
 #pragma unroll
-      for (int k = 0; k < 2 * NC; k++) acc[k] = save[k];
-      mfit_tile_pass<Model, LL, true, NC>(m, xs, ys, ws, cs, cnt, acc, gd);
+    for (int c = 0; c < NC; c++) gd[c].reset();
+    mfit_tile_pass<Model, LL, false, NC>(m, xs, ys, ws, cs, cnt, acc, gd);
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      if (!gd[c].tripped()) continue;
+      if ((MfitTerm<LL>::USES & MFIT_USES_LOG) != 0 && (Model::USES & MFIT_USES_LOG) == 0 && gd[c].log_of_negative()) {
+        // the only log on the path is log-poisson's own, (log lambda) :383, and its NaN reaches the sum whatever else happened
+        acc[2 * c] = __longlong_as_double(0x7ff8000000000000LL);
+      } else {  // rare: overflow / NaN / zero rate ... -> this chain's tile again with libdevice
+        acc[2 * c] = save[2 * c];
+        acc[2 * c + 1] = save[2 * c + 1];
+        mfit_tile_pass<Model, LL, true, 1>(m + c, xs, ys, ws, cs, cnt, acc + 2 * c, gd + c);
+      }
     }
   }
 }

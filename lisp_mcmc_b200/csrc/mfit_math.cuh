@@ -80,6 +80,10 @@ struct MfitGuard {
         || s >= 0x40f86a00u      // sin/cos: |x| >= 1e5, inf, nan
         || d >= 0x7fb00000u;     // rcp: |x| outside [2^-1021, 2^1022), zero, inf, nan   (d tracks |hi(x)| - 0x00200000)
   }
+  // some log argument was a negative normal number (hi(x) in [0x80100000, 0xffefffff]): that term is NaN, hence so
+  // is every sum it enters -- no need to redo anything (wild proposals of the reference's start-up phase drive
+  // a log-poisson rate below zero all the time)
+  __device__ __forceinline__ bool log_of_negative() const { return l >= 0x80000000u && l < 0xfff00000u; }
 };
 // The same interface with nothing behind it: used when a model has proved, from its parameters and the x range of
 // the data set (Model::safe), that no argument can leave the fast domain -- the guard and clamp instructions
@@ -93,6 +97,7 @@ struct MfitNoGuard {
   __device__ __forceinline__ void see_sin(unsigned) {}
   __device__ __forceinline__ void see_div(unsigned) {}
   __device__ __forceinline__ bool tripped() const { return false; }
+  __device__ __forceinline__ bool log_of_negative() const { return false; }
 };
 
 /* 1.5 * 2^52 + 2^31: adding it rounds to an integer k held in the low mantissa word.  The 2^31 bias keeps the low

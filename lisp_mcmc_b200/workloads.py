@@ -97,7 +97,7 @@ def c5(W=65536, N=10000000):
     keys = ["c0", "c1", "c2", "c3", "c4", "c5", "k"]
     return dict(name="C5", function=[USER_POLY5_EXP], data=[[x, y]], data_error=0.01, keys=keys, theta_star=th,
                 theta0=_jitter(th, W, 0.01, 2005), log_liklihood="log-liklihood-normal", log_prior="log-prior-flat",
-                steps=20, flop_per_point=16, transc_per_point={"exp": 1}, fp64_instr_per_point=19)
+                steps=20, flop_per_point=16, transc_per_point={"exp": 1}, fp64_instr_per_point=18)
 
 
 CONFIGS = {"C1": c1, "C2": c2, "C3": c3, "C4": c4, "C5": c5}

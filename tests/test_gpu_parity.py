@@ -77,6 +77,25 @@ def test_log_poisson_matches_oracle(orc, name):
     w.close()
 
 
+def test_log_poisson_negative_rate_is_nan_without_disturbing_neighbours(orc):
+    """a rate that dips below zero makes (log lambda) complex in the reference / NaN here (:383): that chain's sum is
+    NaN -- decided from the guard, without a libdevice redo -- while the chains sharing its thread, warp and CTA
+    (chains w and w + 128 share a thread) keep their exact values; lambda = 0 with k > 0 still takes the redo (-inf)"""
+    cfg = _family_cfg("sinus", 1300, 300, "log-poisson")
+    th = cfg["theta0"]
+    bad = [3, 131, 200, 299]
+    for b in bad:
+        th[b, 3] = 0.5 * th[b, 0]          # c < a: lambda < 0 around the troughs
+    w = workloads.make_walker(cfg)
+    prob, _, _ = w.make_step(th)
+    ow = oracle_walker(orc, cfg)
+    ref = np.array([ow.logp(t)[0] for t in th])
+    assert np.all(np.isnan(ref[bad])) and np.all(np.isnan(prob[bad]))
+    good = np.setdiff1d(np.arange(300), bad)
+    assert np.all(np.isfinite(prob[good])) and rel_err(prob[good], ref[good]) < TOL
+    w.close()
+
+
 @pytest.mark.parametrize("N", [0, 1, 2, 127, 128, 129, 511, 512, 513, 1024, 4097])
 @pytest.mark.parametrize("W", [1, 128, 129])
 def test_ragged_sizes(orc, N, W):

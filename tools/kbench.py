@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--W", type=int, default=0)
     ap.add_argument("--N", type=int, default=0)
     ap.add_argument("--e2e", type=int, default=0)
+    ap.add_argument("--seg-tiles", type=int, default=0)
     args = ap.parse_args()
     from lisp_mcmc_b200 import _lib, workloads
     if args.lib:
@@ -37,6 +38,8 @@ def main():
     N = sum(len(d[0]) for d in cfg["data"])
     W = cfg["theta0"].shape[0]
     w = workloads.make_walker(cfg)
+    if args.seg_tiles:
+        w._chk(L.mfit_set_segment_tiles(w._h, args.seg_tiles))
     w._chk(L.mfit_set_timing(w._h, 1))
     ksec, kl = C.c_double(), C.c_int64()
     best, tot = 1e30, 0.0
@@ -47,8 +50,8 @@ def main():
             best = min(best, ksec.value)
             tot += ksec.value
     mean = tot / args.reps
-    print("%s lib=%s W=%d N=%d: eval kernels %.4f ms mean, %.4f ms best -> %.4g point-evals/s (mean), %.4g (best)"
-          % (args.config, os.path.basename(_lib.LIB_PATH), W, N, mean * 1e3, best * 1e3, W * N / mean, W * N / best))
+    print("%s lib=%s seg_tiles=%d W=%d N=%d: eval kernels %.4f ms mean, %.4f ms best -> %.4g point-evals/s (mean), %.4g (best)"
+          % (args.config, os.path.basename(_lib.LIB_PATH), args.seg_tiles, W, N, mean * 1e3, best * 1e3, W * N / mean, W * N / best))
     w.close()
     if args.e2e:
         K = args.e2e

@@ -9,7 +9,7 @@
 
 // the same pass with (x, y, w) synthesised on the integer pipe instead of read from shared memory
 template <class Model, int LL, int NCH, class G>
-__device__ __forceinline__ void tile_pass_noload(const Model* m, int cnt, double* acc, G& gd, int seed) {
+__device__ __forceinline__ void tile_pass_noload(const Model* m, int cnt, double* acc, G* gd, int seed) {
   constexpr int UNR = MFIT_UNROLL_PAIRS;
 #pragma unroll UNR
   for (int i = 0; i < (cnt >> 1); i++) {
@@ -21,10 +21,10 @@ __device__ __forceinline__ void tile_pass_noload(const Model* m, int cnt, double
     cv.x = cv.y = -1.0;
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
-      const double f0 = m[c].template eval<false>(xv.x, gd);
-      const double f1 = m[c].template eval<false>(xv.y, gd);
-      acc[2 * c] = MfitTerm<LL>::template add<false>(acc[2 * c], f0, yv.x, wv.x, cv.x, gd);
-      acc[2 * c + 1] = MfitTerm<LL>::template add<false>(acc[2 * c + 1], f1, yv.y, wv.y, cv.y, gd);
+      const double f0 = m[c].template eval<false>(xv.x, gd[c]);
+      const double f1 = m[c].template eval<false>(xv.y, gd[c]);
+      acc[2 * c] = MfitTerm<LL>::template add<false>(acc[2 * c], f0, yv.x, wv.x, cv.x, gd[c]);
+      acc[2 * c + 1] = MfitTerm<LL>::template add<false>(acc[2 * c + 1], f1, yv.y, wv.y, cv.y, gd[c]);
     }
   }
 }
@@ -54,8 +54,9 @@ __global__ void __launch_bounds__(THREADS, CTAS) k(MfitEvalArgs a, int iters, do
   m[0].setup();
   m[1].setup();
   double acc[4] = {0, 0, 0, 0};
-  G gd;
-  gd.reset();
+  G gd[2];
+  gd[0].reset();
+  gd[1].reset();
   for (int it = 0; it < iters; it++) {
 #ifdef NOLOAD
     tile_pass_noload<Model, LL, PNC>(m, MFIT_TILE, acc, gd, it);
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k(MfitEvalArgs a, int iters, do
     mfit_tile_pass<Model, LL, false, PNC>(m, buf, buf + MFIT_TILE, buf + 2 * MFIT_TILE, buf + 3 * MFIT_TILE, MFIT_TILE, acc, gd);
 #endif
   }
-  out[(size_t)blockIdx.x * THREADS + threadIdx.x] = acc[0] + acc[1] + acc[2] + acc[3] + (gd.tripped() ? 1.0 : 0.0);
+  out[(size_t)blockIdx.x * THREADS + threadIdx.x] = acc[0] + acc[1] + acc[2] + acc[3] + ((gd[0].tripped() || gd[1].tripped()) ? 1.0 : 0.0);
 }
 
 template <class Model, int LL, class G>
