@@ -191,7 +191,11 @@ double log_factorial_ref(long long n, std::vector<float>& memo) {
 // every log-likelihood bit -- do not depend on chain count, SM count or the number of GPUs
 void plan_segments(mfit_ctx* ctx, Dataset& d) {
   const long long n_tiles = (d.n + MFIT_TILE - 1) / MFIT_TILE;
-  long long tps = ctx->seg_tiles_override > 0 ? ctx->seg_tiles_override : (n_tiles + MFIT_MAX_SEG - 1) / MFIT_MAX_SEG;
+  // at most MFIT_MAX_SEG segments; two tiles per work item as soon as that still leaves >= 256 items per chain-block
+  // (one-tile items pay ~4 % for their per-item set-up: measured on C2, tools/kbench.py --seg-tiles)
+  long long tps = (n_tiles + MFIT_MAX_SEG - 1) / MFIT_MAX_SEG;
+  if (tps < 2 && n_tiles >= 512) tps = 2;
+  if (ctx->seg_tiles_override > 0) tps = ctx->seg_tiles_override;
   if (tps < 1) tps = 1;
   d.tiles_per_seg = (int)tps;
   d.n_seg = (int)((n_tiles + tps - 1) / tps);

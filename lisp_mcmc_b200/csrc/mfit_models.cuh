@@ -97,20 +97,19 @@ struct MfitLorentz {
 };
 
 // f = a exp(-((x - mu)/s)^2 / 2) + b0 + b1 x.  The Gaussian argument is formed directly in 1/256 octaves
-// (zs = z sqrt(128/ln2), exp(-z^2/2) = 2^(-zs^2/256)), see mfit_gauss_reduce, and the amplitude is folded into the
-// polynomial coefficients once per work item:  a exp(..) = s (a + r (a k1 + r (a k2 + ...))).  11 FP64 instructions
-// per point (d, zs, lin, tmp, kd, r, four FMAs, the final FMA with s), 13 with the log-normal term.
+// (zs = z sqrt(128/ln2), exp(-z^2/2) = 2^(-zs^2/256)), see mfit_gauss_reduce.  12 FP64 instructions per point (d, zs,
+// lin, tmp, kd, r, four polynomial FMAs, a s, the final FMA), 14 with the log-normal term.  The polynomial takes its
+// coefficients from the constant bank: folding the amplitude into per-chain coefficient registers saves the a s
+// multiply but turns four FMAs into three-register-operand ones, which the FP64 pipe issues more slowly
+// (tools/probe/horner_probe.cu: 56 against 63 DFMA/clk/SM; loop_probe: 9.98e11 against 1.03e12 point-evals/s).
 struct MfitGaussLin {
   static constexpr int USES = MFIT_USES_EXP;
   static constexpr bool GUARDED = true;
-  double a_, mu, isq, b0, b1, k1, k2, k3, k4;  // load() leaves s in isq
+  double a_, mu, isq, b0, b1;  // load() leaves s in isq
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     a_ = MFIT_TH(0); mu = MFIT_TH(1); isq = MFIT_TH(2); b0 = MFIT_TH(3); b1 = MFIT_TH(4);
   }
-  __device__ __forceinline__ void setup() {
-    isq = (1.0 / isq) * MFIT_GAUSS_ZSCALE;
-    k1 = a_ * MFIT_K_EXS1; k2 = a_ * MFIT_K_EXS2; k3 = a_ * MFIT_K_EXS3; k4 = a_ * MFIT_K_EXS4;
-  }
+  __device__ __forceinline__ void setup() { isq = (1.0 / isq) * MFIT_GAUSS_ZSCALE; }
   __device__ __forceinline__ bool safe(const MfitEvalArgs& a) const {
     return mfit_absmax(a.xmin - mu, a.xmax - mu) * fabs(isq) < MFIT_GAUSS_ZLIMIT && fabs(a_) < 1.0e300;
   }
@@ -122,12 +121,9 @@ struct MfitGaussLin {
       const double z = d * (isq * (1.0 / MFIT_GAUSS_ZSCALE));
       return fma(a_, exp(-0.5 * (z * z)), lin);
     }
-    double s, r;
-    mfit_gauss_reduce(d * isq, &s, &r, gd);
-    double q = fma(r, k4, k3);
-    q = fma(r, q, k2);
-    q = fma(r, q, k1);
-    return fma(s, fma(r, q, a_), lin);
+    double s, p;
+    mfit_gauss_parts(d * isq, &s, &p, gd);
+    return fma(a_ * s, p, lin);
   }
 };
 
