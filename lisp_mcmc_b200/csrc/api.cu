@@ -29,6 +29,16 @@
 #include "mfit_eval.cuh"
 #include "mfit_internal.h"
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync on the context's stream, release
+// threshold raised so that freed blocks stay cached): walker-create / trace reads allocate and free hundreds of MB per
+// call, which costs tens of milliseconds with cudaMalloc / cudaFree and next to nothing from a warm pool.  Everything
+// a context does is enqueued on its one stream, so stream-ordered frees are safe.
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+static inline cudaError_t mfit_pool_malloc(void** p, size_t bytes) { return cudaMallocAsync(p, bytes, g_alloc_stream); }
+static inline cudaError_t mfit_pool_free(void* p) { return cudaFreeAsync(p, g_alloc_stream); }
+#define cudaMalloc(p, bytes) mfit_pool_malloc((void**)(p), (bytes))
+#define cudaFree(p) mfit_pool_free(p)
+
 namespace {
 
 std::string g_create_error;
@@ -604,6 +614,11 @@ int mfit_ctx_create(int device, void* stream, mfit_ctx** out) {
     if (e != cudaSuccess) { delete c; return fail(nullptr, MFIT_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     c->own_stream = true;
   }
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   *out = c;
   return 0;
 }
@@ -611,6 +626,7 @@ int mfit_ctx_create(int device, void* stream, mfit_ctx** out) {
 void mfit_ctx_destroy(mfit_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  g_alloc_stream = ctx->stream;
   cudaStreamSynchronize(ctx->stream);
   chains_free(ctx);
   for (auto& d : ctx->ds) { dataset_free_data(d); dataset_free_prior(d); dataset_free_model(d); }
@@ -622,6 +638,7 @@ void mfit_ctx_destroy(mfit_ctx* ctx) {
   if (ctx->poll_ev_made) for (auto& e : ctx->poll_ev) cudaEventDestroy(e);
   for (auto& p : ctx->ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (ctx->comm) mfit_nccl_comm_destroy(ctx->comm);
+  cudaStreamSynchronize(ctx->stream);  // the stream-ordered frees above
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -644,7 +661,7 @@ int mfit_problem_define(mfit_ctx* ctx, int n_datasets, int n_params) {
   if (!ctx) return MFIT_ERR_ARG;
   if (n_datasets < 1 || n_params < 1 || n_params > MFIT_MAX_P)
     return fail(ctx, MFIT_ERR_ARG, "need 1 <= datasets and 1 <= params <= %d", MFIT_MAX_P);
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   chains_free(ctx);
   for (auto& d : ctx->ds) { dataset_free_data(d); dataset_free_prior(d); dataset_free_model(d); }
   ctx->ds.assign(n_datasets, Dataset());
@@ -657,13 +674,14 @@ int mfit_problem_define(mfit_ctx* ctx, int n_datasets, int n_params) {
 
 #define NEED_DS(d)                                                                       \
   if (!ctx) return MFIT_ERR_ARG;                                                          \
+  g_alloc_stream = ctx->stream;                                                           \
   if (ctx->D <= 0) return fail(ctx, MFIT_ERR_STATE, "mfit_problem_define has not been called"); \
   if ((d) < 0 || (d) >= ctx->D) return fail(ctx, MFIT_ERR_ARG, "dataset index %d out of range", (d))
 
 int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, const double* sigma, int64_t n) {
   NEED_DS(d);
   if (n < 0 || (n > 0 && (!x || !y))) return fail(ctx, MFIT_ERR_ARG, "dataset %d: bad x/y/n", d);
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   Dataset& s = ctx->ds[d];
   dataset_free_data(s);
   s.n = n;
@@ -741,7 +759,7 @@ static int load_cubin(mfit_ctx* ctx, const std::vector<char>& cubin, cudaLibrary
 int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* const* key_names, int n_keys) {
   NEED_DS(d);
   if (!lambda_text || n_keys != ctx->P) return fail(ctx, MFIT_ERR_ARG, "need the lambda text and exactly P=%d key names", ctx->P);
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   std::string code, e;
   int rc = mfit_lower_to_string(lambda_text, key_names, n_keys, 0, code, e);
   if (rc) return fail(ctx, rc, "%s", e.c_str());
@@ -781,7 +799,7 @@ int mfit_prior_bounds(mfit_ctx* ctx, int d, int n, const int32_t* idx, const dou
   if (n < 0 || (n > 0 && (!idx || !lo || !hi))) return fail(ctx, MFIT_ERR_ARG, "bad bounds arrays");
   for (int k = 0; k < n; k++)
     if (idx[k] >= ctx->P) return fail(ctx, MFIT_ERR_ARG, "bounds idx[%d]=%d out of range", k, idx[k]);
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   if (ctx->have_chains) chains_free(ctx);
   Dataset& s = ctx->ds[d];
   dataset_free_prior(s);
@@ -791,9 +809,10 @@ int mfit_prior_bounds(mfit_ctx* ctx, int d, int n, const int32_t* idx, const dou
     CU(cudaMalloc(&s.b_idx, sizeof(int) * n));
     CU(cudaMalloc(&s.b_lo, sizeof(double) * n));
     CU(cudaMalloc(&s.b_hi, sizeof(double) * n));
-    CU(cudaMemcpy(s.b_idx, idx, sizeof(int) * n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s.b_lo, lo, sizeof(double) * n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(s.b_hi, hi, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(s.b_idx, idx, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(s.b_lo, lo, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(s.b_hi, hi, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // the caller's arrays are free to go
   }
   return 0;
 }
@@ -801,7 +820,7 @@ int mfit_prior_bounds(mfit_ctx* ctx, int d, int n, const int32_t* idx, const dou
 int mfit_prior_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* const* key_names, int n_keys) {
   NEED_DS(d);
   if (!lambda_text || n_keys != ctx->P) return fail(ctx, MFIT_ERR_ARG, "need the lambda text and exactly P=%d key names", ctx->P);
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   std::string code, e;
   int rc = mfit_lower_to_string(lambda_text, key_names, n_keys, 1, code, e);
   if (rc) return fail(ctx, rc, "%s", e.c_str());
@@ -820,6 +839,7 @@ int mfit_prior_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* 
 
 int mfit_set_segment_tiles(mfit_ctx* ctx, int tiles_per_segment) {
   if (!ctx || tiles_per_segment < 0) return MFIT_ERR_ARG;
+  g_alloc_stream = ctx->stream;
   if (ctx->have_chains) chains_free(ctx);
   ctx->seg_tiles_override = tiles_per_segment;
   return 0;
@@ -832,7 +852,7 @@ int mfit_eval_logp(mfit_ctx* ctx, const double* theta, int64_t W, double* prob, 
   int rc = check_problem_ready(ctx);
   if (rc) return rc;
   if (W == 0) return 0;
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   Workspace w;
   rc = workspace_make(ctx, w, W);
   if (rc) { workspace_free(w); return rc; }
@@ -885,7 +905,7 @@ int mfit_chains_init(mfit_ctx* ctx, const double* theta0, int64_t W, uint64_t se
   if (W > 2000000000LL) return fail(ctx, MFIT_ERR_ARG, "W too large");
   int rc = check_problem_ready(ctx);
   if (rc) return rc;
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   chains_free(ctx);
   rc = workspace_make(ctx, ctx->ws, W);
   if (rc) return rc;
@@ -995,7 +1015,7 @@ int mfit_run_adaptive(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, const double* l_
   if (!ctx || !cfg) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
   if (cfg->n < 0) return fail(ctx, MFIT_ERR_ARG, "n < 0");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   MfitRunCfg r;
   int rc = make_cfg(ctx, cfg, r);
   if (rc) return rc;
@@ -1015,7 +1035,7 @@ int mfit_run_begin(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, const double* l_mat
   if (!ctx || !cfg) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
   if (cfg->n < 0) return fail(ctx, MFIT_ERR_ARG, "n < 0");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   MfitRunCfg r;
   int rc = make_cfg(ctx, cfg, r);
   if (rc) return rc;
@@ -1028,7 +1048,7 @@ int mfit_run_begin(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, const double* l_mat
 int mfit_run_advance(mfit_ctx* ctx, int64_t max_steps, int64_t* steps_done, int* finished) {
   if (!ctx) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   if (ctx->run_cfg.z && ctx->run_t + (max_steps < 0 ? ctx->run_max - ctx->run_t : max_steps) > ctx->run_cfg.nstream &&
       ctx->run_t + 1 > ctx->run_cfg.nstream)
     return fail(ctx, MFIT_ERR_STREAM, "injected stream exhausted");
@@ -1049,7 +1069,7 @@ int mfit_run_many_steps(mfit_ctx* ctx, int64_t n, const double* l_matrix, const 
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
   if (!l_matrix) return fail(ctx, MFIT_ERR_ARG, "walker-many-steps needs an l-matrix here (the :median-params default is post-processing)");
   if (n < 0) return fail(ctx, MFIT_ERR_ARG, "n < 0");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   MfitRunCfg r;
   memset(&r, 0, sizeof r);
   r.mode = MFIT_MODE_MANY;
@@ -1064,7 +1084,7 @@ int mfit_run_many_steps(mfit_ctx* ctx, int64_t n, const double* l_matrix, const 
 int mfit_run_sample_region(mfit_ctx* ctx, double initial_scale, const double* z, int64_t nstream) {
   if (!ctx) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   MfitRunCfg r;
   memset(&r, 0, sizeof r);
   r.mode = MFIT_MODE_SAMPLE_REGION;
@@ -1081,7 +1101,7 @@ int mfit_run_sample_region(mfit_ctx* ctx, double initial_scale, const double* z,
 int mfit_force_take_step(mfit_ctx* ctx) {
   if (!ctx) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   MfitChains& c = ctx->ch;
   int rc = grow_trace(ctx, ctx->rows_upper + 2);
   if (rc) return rc;
@@ -1112,7 +1132,7 @@ int mfit_trace_read(mfit_ctx* ctx, int64_t take, double* theta, double* prob, in
   if (!ctx) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
   if (take < 1) return fail(ctx, MFIT_ERR_ARG, "take < 1");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   MfitChains& c = ctx->ch;
   const size_t W = (size_t)c.W;
   double *dt = nullptr, *dp = nullptr;
@@ -1143,7 +1163,7 @@ int mfit_trace_read(mfit_ctx* ctx, int64_t take, double* theta, double* prob, in
 int mfit_stats_read(mfit_ctx* ctx, mfit_chain_stats* stats) {
   if (!ctx || !stats) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   MfitChains& c = ctx->ch;
   mfit_chain_stats* d = nullptr;
   CU(cudaMalloc(&d, sizeof(mfit_chain_stats) * c.W));
@@ -1178,20 +1198,20 @@ static int read_soa(mfit_ctx* ctx, const double* src_theta, const double* src_pr
 int mfit_best_read(mfit_ctx* ctx, double* theta, double* prob) {
   if (!ctx) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   return read_soa(ctx, ctx->ch.best_theta, ctx->ch.best_prob, theta, prob);
 }
 int mfit_last_read(mfit_ctx* ctx, double* theta, double* prob) {
   if (!ctx) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   return read_soa(ctx, ctx->ch.cur_theta, ctx->ch.cur_prob, theta, prob);
 }
 
 int mfit_l_matrix_read(mfit_ctx* ctx, double* l) {
   if (!ctx || !l) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   MfitChains& c = ctx->ch;
   const size_t cnt = (size_t)c.W * c.P * c.P;
   double* tmp = nullptr;
@@ -1209,7 +1229,7 @@ int mfit_keep_walks(mfit_ctx* ctx, int64_t keep) {
   if (!ctx) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
   if (keep < 1) return fail(ctx, MFIT_ERR_ARG, "keep < 1");
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   mfit_launch_keep_walks(ctx->ch, keep, ctx->stream);
   ctx->launches++;
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1219,7 +1239,7 @@ int mfit_keep_walks(mfit_ctx* ctx, int64_t keep) {
 int mfit_philox_stream(mfit_ctx* ctx, uint64_t seed, int64_t chain_id_base, int64_t W, int64_t first_step,
                        int64_t nsteps, int P, double* z, double* u) {
   if (!ctx || !z || !u || W < 1 || nsteps < 1 || P < 1 || P > MFIT_MAX_P) return MFIT_ERR_ARG;
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   double *dz = nullptr, *du = nullptr;
   CU(cudaMalloc(&dz, sizeof(double) * W * nsteps * P));
   cudaError_t e = cudaMalloc(&du, sizeof(double) * W * nsteps);
@@ -1246,7 +1266,7 @@ int mfit_nccl_unique_id(void* id_out) {
 
 int mfit_nccl_attach(mfit_ctx* ctx, const void* unique_id, int rank, int n_ranks) {
   if (!ctx || !unique_id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return MFIT_ERR_ARG;
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   if (ctx->comm) { mfit_nccl_comm_destroy(ctx->comm); ctx->comm = nullptr; }
   std::string e;
   int rc = mfit_nccl_comm_init(&ctx->comm, n_ranks, unique_id, rank, e);
@@ -1260,6 +1280,7 @@ int mfit_dataset_owners(mfit_ctx* ctx, const int32_t* owner) {
   if (!ctx || !owner) return MFIT_ERR_ARG;
   if (ctx->D <= 0) return fail(ctx, MFIT_ERR_STATE, "mfit_problem_define has not been called");
   if (!ctx->comm) return fail(ctx, MFIT_ERR_STATE, "mfit_nccl_attach has not been called");
+  g_alloc_stream = ctx->stream;
   std::vector<int> per_rank(ctx->n_ranks, 0);
   for (int d = 0; d < ctx->D; d++) {
     if (owner[d] < 0 || owner[d] >= ctx->n_ranks) return fail(ctx, MFIT_ERR_ARG, "owner[%d]=%d out of range", d, owner[d]);
@@ -1279,7 +1300,7 @@ int mfit_nccl_allgather_f64(mfit_ctx* ctx, const double* local_host, int64_t cou
   if (!ctx || !local_host || !out_host || count < 0) return MFIT_ERR_ARG;
   if (!ctx->comm) return fail(ctx, MFIT_ERR_STATE, "mfit_nccl_attach has not been called");
   if (count == 0) return 0;
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   double* buf = nullptr;
   const size_t per = sizeof(double) * (size_t)count;
   CU(cudaMalloc(&buf, per * ctx->n_ranks));
@@ -1302,7 +1323,7 @@ int mfit_nccl_allgather_f64(mfit_ctx* ctx, const double* local_host, int64_t cou
 int mfit_measure_fp64(mfit_ctx* ctx, double* dfma_flops, double* cost_exp, double* cost_log, double* cost_sin,
                       double* cost_div) {
   if (!ctx) return MFIT_ERR_ARG;
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   if (mfit_measure_fp64_dev(ctx->stream, dfma_flops, cost_exp, cost_log, cost_sin, cost_div) != 0)
     return fail(ctx, MFIT_ERR_CUDA, "fp64 micro-benchmark failed: %s", cudaGetErrorString(cudaGetLastError()));
   ctx->launches += 5 * 4;
@@ -1311,7 +1332,7 @@ int mfit_measure_fp64(mfit_ctx* ctx, double* dfma_flops, double* cost_exp, doubl
 
 int mfit_set_timing(mfit_ctx* ctx, int on) {
   if (!ctx) return MFIT_ERR_ARG;
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   ctx->timing = on != 0;
   if (ctx->timing && ctx->ev.empty()) {
     ctx->ev.resize(4096);
@@ -1329,7 +1350,7 @@ int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches) {
 
 int mfit_flush_l2(mfit_ctx* ctx) {
   if (!ctx) return MFIT_ERR_ARG;
-  CU(cudaSetDevice(ctx->device));
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   if (!ctx->flush_buf) {
     ctx->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
     CU(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));

@@ -57,6 +57,14 @@ def main():
         K = args.e2e
         cfgc = _lib.AdaptCfg(30000, 10.0, _lib.AUTO_NONE, _lib.OPT_COVARIANCE, 0, 0, 0)
         for rep in range(2):
+            if rep == 1:   # where does walker_create spend its time?
+                import cProfile, pstats
+                pr_ = cProfile.Profile()
+                pr_.enable()
+                wp = workloads.make_walker(cfg, seed=1, trace_capacity=K + 1100)
+                pr_.disable()
+                wp.close()
+                pstats.Stats(pr_).sort_stats("cumulative").print_stats(12)
             t = [time.perf_counter()]
             w2 = workloads.make_walker(cfg, seed=2025 + rep, trace_capacity=K + 1100)
             t.append(time.perf_counter())
