@@ -167,6 +167,19 @@ int mfit_best_read(mfit_ctx* ctx, double* theta, double* prob);
 int mfit_last_read(mfit_ctx* ctx, double* theta, double* prob);
 /* l-matrix in use at the end of the last run, W x P x P */
 int mfit_l_matrix_read(mfit_ctx* ctx, double* l);
+/* walker-get analytics over the newest `take` rows of every chain, computed on the device.  Any output
+ * may be NULL.
+ *   most_likely_theta W x P, most_likely_prob W : :most-likely-step :503-505 (largest prob; of equal ones the oldest,
+ *                                                 as the reference's `reduce` leaves it)
+ *   median W x P        : :median-params :516-523 = nth-percentile 50 :1493-1504 (mean of the two middle order
+ *                         statistics when the count is even)
+ *   acceptance W        : :acceptance :506-508
+ *   covariance W x P x P: :covariance-matrix = lplist-covariance :614-643 of the :unique-steps :491-495
+ *   l_matrix W x P x P  : :l-matrix :543 = cholesky-decomp of the covariance of the differences of the :forward-steps;
+ *                         its diagonal is :stddev-params :526-539.  NaN where the reference would signal an error
+ *                         (fewer than two forward steps). */
+int mfit_trace_analytics(mfit_ctx* ctx, int64_t take, double* most_likely_theta, double* most_likely_prob,
+                         double* median, double* acceptance, double* covariance, double* l_matrix);
 /* walker-modify :keep-walks :568-569 applied to every chain */
 int mfit_keep_walks(mfit_ctx* ctx, int64_t keep);
 

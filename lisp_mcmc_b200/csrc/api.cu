@@ -1225,6 +1225,45 @@ int mfit_l_matrix_read(mfit_ctx* ctx, double* l) {
   return 0;
 }
 
+int mfit_trace_analytics(mfit_ctx* ctx, int64_t take, double* most_likely_theta, double* most_likely_prob,
+                         double* median, double* acceptance, double* covariance, double* l_matrix) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (take < 1) return fail(ctx, MFIT_ERR_ARG, "take < 1");
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  MfitChains& c = ctx->ch;
+  if (take > c.cap) take = c.cap;  // no chain holds more rows than the ring
+  const size_t W = (size_t)c.W, P = (size_t)c.P;
+  struct Out { double* host; size_t count; double* dev; };
+  Out outs[6] = {{most_likely_theta, W * P, nullptr}, {most_likely_prob, W, nullptr}, {median, W * P, nullptr},
+                 {acceptance, W, nullptr}, {covariance, W * P * P, nullptr}, {l_matrix, W * P * P, nullptr}};
+  int* sel = nullptr;
+  cudaError_t e = cudaSuccess;
+  for (auto& o : outs)
+    if (o.host && e == cudaSuccess) e = cudaMalloc(&o.dev, sizeof(double) * o.count);
+  const bool window = most_likely_theta || most_likely_prob || acceptance || covariance || l_matrix;
+  if (e == cudaSuccess && window) e = cudaMalloc(&sel, sizeof(int) * W * (size_t)(take + 1));
+  if (e == cudaSuccess) {
+    if (window) {
+      mfit_launch_analytics(c, take, sel, outs[0].dev, outs[1].dev, outs[3].dev, outs[4].dev, outs[5].dev, ctx->stream);
+      ctx->launches++;
+    }
+    if (median) {
+      mfit_launch_median(c, take, outs[2].dev, ctx->stream);
+      ctx->launches++;
+    }
+    for (auto& o : outs)
+      if (o.host && e == cudaSuccess) e = cudaMemcpyAsync(o.host, o.dev, sizeof(double) * o.count, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  for (auto& o : outs) free_dev(o.dev);
+  free_dev(sel);
+  if (e != cudaSuccess)
+    return fail(ctx, e == cudaErrorMemoryAllocation ? MFIT_ERR_NOMEM : MFIT_ERR_CUDA, "trace_analytics: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int mfit_keep_walks(mfit_ctx* ctx, int64_t keep) {
   if (!ctx) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");

@@ -697,6 +697,199 @@ __global__ void k_flush(double* buf, size_t n) {
   for (; i < n; i += step) buf[i] = (double)i;
 }
 
+// ------------------------------------------------------------------ walker-get analytics over the trace (:487-543)
+// One CTA per chain over the newest `take` rows of its trace ring.  The two covariance-type results keep the
+// reference's operation order (sequential sums in list order = newest first, divide inside the sum, :614-643;
+// Cholesky :583-598), so they are bit-identical to the CPU oracle; selection and counting are order-free.
+//   sel: [W][take + 1] int scratch (row offsets of the selected steps, newest first)
+__device__ unsigned long long dbits(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+// compact the offsets k in [0, m) (k = 0 is the newest row) for which pred(k) holds, in order; returns the count
+template <class Pred>
+__device__ int block_select(int m, int* out, Pred pred, int* sh /* [blockDim.x + 1] */) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  int base = 0;
+  for (int k0 = 0; k0 < m; k0 += nth) {
+    const int k = k0 + tid;
+    const int flag = (k < m && pred(k)) ? 1 : 0;
+    sh[tid] = flag;
+    __syncthreads();
+    // inclusive scan (blockDim.x <= 128: a simple log-step scan)
+    for (int off = 1; off < nth; off <<= 1) {
+      int v = tid >= off ? sh[tid - off] : 0;
+      __syncthreads();
+      sh[tid] += v;
+      __syncthreads();
+    }
+    if (flag) out[base + sh[tid] - 1] = k;
+    const int total = sh[nth - 1];
+    __syncthreads();
+    base += total;
+  }
+  return base;
+}
+
+// lplist-covariance :614-643 of n rows (accessor val(k, i), k in list order) -> cov[P*P]; avg is scratch [P]
+template <class Val>
+__device__ void block_covariance(int n, int P, Val val, double* avg, double* cov) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int i = tid; i < P; i += nth) {
+    double s = val(0, i);
+    for (int k = 1; k < n; k++) s = s + val(k, i);
+    avg[i] = s / (double)n;
+  }
+  __syncthreads();
+  for (int e = tid; e < P * P; e += nth) {
+    const int i = e / P, j = e % P;
+    const double ai = avg[i], aj = avg[j];
+    double s = 0.0;
+    for (int k = 0; k < n; k++) s = s + ((val(k, i) - ai) * (val(k, j) - aj)) / (double)n;
+    cov[e] = s;
+  }
+  __syncthreads();
+}
+
+__global__ void k_analytics(const MfitChains c, long long take, int* sel_all, double* ml_theta, double* ml_prob,
+                            double* acceptance, double* cov_out, double* l_out) {
+  const long long w = blockIdx.x;
+  if (w >= c.W) return;
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int P = c.P, PP = P * P, tid = threadIdx.x, nth = blockDim.x;
+  double* avg = reinterpret_cast<double*>(sm);
+  double* cov = avg + P;
+  double* Ln = cov + PP;
+  int* sh = reinterpret_cast<int*>(Ln + PP);        // [nth + 1]
+  double* redp = reinterpret_cast<double*>(sh + nth + 2);  // [nth]
+  int* redk = reinterpret_cast<int*>(redp + nth);          // [nth]
+  int* sel = sel_all + (size_t)w * (take + 1);
+  const int m = (int)wlen(c, w, take);
+  const long long newest = c.rows[w] - 1;
+  auto prob_at = [&](int k) { return tprob(c, newest - k, w); };
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+
+  // :most-likely-step -- (reduce (lambda (x y) (if (> x y) x y)) steps): the largest prob, of equal ones the oldest
+  if (ml_prob || ml_theta) {
+    double bp = -INFINITY;
+    int bk = -1;
+    for (int k = tid; k < m; k += nth) {
+      const double p = prob_at(k);
+      if (p >= bp) { bp = p; bk = k; }   // k ascending = towards older rows
+    }
+    redp[tid] = bp;
+    redk[tid] = bk;
+    __syncthreads();
+    if (tid == 0) {
+      for (int t = 1; t < nth; t++)
+        if (redk[t] >= 0 && (redk[0] < 0 || redp[t] > redp[0] || (redp[t] == redp[0] && redk[t] > redk[0]))) {
+          redp[0] = redp[t];
+          redk[0] = redk[t];
+        }
+      if (redk[0] < 0) redk[0] = m - 1;  // every prob is NaN: reduce ends on the oldest step
+    }
+    __syncthreads();
+    const int bk0 = redk[0];
+    if (ml_prob && tid == 0) ml_prob[w] = m > 0 ? prob_at(bk0) : nanv;
+    if (ml_theta)
+      for (int i = tid; i < P; i += nth) ml_theta[(size_t)w * P + i] = m > 0 ? ttheta(c, newest - bk0, i, w) : nanv;
+    __syncthreads();
+  }
+  // :unique-steps :491-495 (a step whose prob differs from the next older one's; the oldest always) and :acceptance :506-508
+  const int n_uni = block_select(m, sel, [&](int k) { return k == m - 1 || dbits(prob_at(k)) != dbits(prob_at(k + 1)); }, sh);
+  if (acceptance && tid == 0) acceptance[w] = m > 0 ? (double)n_uni / (double)m : nanv;
+  if (cov_out) {
+    __syncthreads();  // sel visible
+    if (n_uni > 0) {
+      block_covariance(n_uni, P, [&](int k, int i) { return ttheta(c, newest - sel[k], i, w); }, avg, cov);
+      for (int e = tid; e < PP; e += nth) cov_out[(size_t)w * PP + e] = cov[e];
+    } else
+      for (int e = tid; e < PP; e += nth) cov_out[(size_t)w * PP + e] = nanv;
+    __syncthreads();
+  }
+  // :l-matrix :543 = cholesky(covariance(differences (older - newer) of the :forward-steps :497-502))
+  if (l_out) {
+    const int n_fwd = block_select(m, sel, [&](int k) { return k + 1 < m && prob_at(k) > prob_at(k + 1); }, sh);
+    __syncthreads();
+    const int n = n_fwd - 1;
+    if (n >= 1) {
+      block_covariance(n, P, [&](int k, int i) { return ttheta(c, newest - sel[k + 1], i, w) - ttheta(c, newest - sel[k], i, w); },
+                       avg, cov);
+      for (int e = tid; e < PP; e += nth) Ln[e] = 0.0;
+      __syncthreads();
+      if (tid == 0) {  // cholesky-decomp :583-598
+        for (int i = 0; i < P; i++)
+          for (int k = 0; k <= i; k++) {
+            double tmp = 0.0;
+            for (int j = 0; j < k; j++) tmp = tmp + Ln[i * P + j] * Ln[k * P + j];
+            if (i == k) {
+              const double d = cov[i * P + k] - tmp;
+              Ln[i * P + k] = sqrt(d > 0.0 ? d : (d != d ? d : 0.0));
+            } else
+              Ln[i * P + k] = (cov[i * P + k] - tmp) / Ln[k * P + k];
+          }
+      }
+      __syncthreads();
+      for (int e = tid; e < PP; e += nth) l_out[(size_t)w * PP + e] = Ln[e];
+    } else
+      for (int e = tid; e < PP; e += nth) l_out[(size_t)w * PP + e] = nanv;  // the reference signals an error here
+  }
+}
+
+// :median-params :516-523 = nth-percentile 50 (:1493-1504) of every parameter over the newest `take` rows: a 4-bit
+// radix select per (chain, parameter), adjacent lanes = adjacent chains so that every pass over the ring is coalesced
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  const unsigned long long b = dbits(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+__global__ void k_median(const MfitChains c, long long take, double* out) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long w = id % c.stride;
+  const int i = (int)(id / c.stride);
+  if (i >= c.P || w >= c.W) return;
+  const int m = (int)wlen(c, w, take);
+  if (m == 0) { out[(size_t)w * c.P + i] = __longlong_as_double(0x7ff8000000000000LL); return; }
+  const long long newest = c.rows[w] - 1;
+  long long rank = (m - 1) / 2;          // (floor (* 50 (- len 1) 1/100))
+  const bool two = ((m - 1) & 1) != 0;   // non-zero remainder: mean of the elements at pos and pos + 1
+  unsigned long long prefix = 0;
+  for (int shift = 60; shift >= 0; shift -= 4) {
+    unsigned cnt[16];
+#pragma unroll
+    for (int b = 0; b < 16; b++) cnt[b] = 0;
+    for (int k = 0; k < m; k++) {
+      const unsigned long long key = order_key(ttheta(c, newest - k, i, w));
+      const bool match = shift == 60 || (key >> (shift + 4)) == prefix;
+      const unsigned d = (unsigned)(key >> shift) & 15u;
+#pragma unroll
+      for (int b = 0; b < 16; b++) cnt[b] += (match && d == (unsigned)b) ? 1u : 0u;
+    }
+    unsigned d = 0;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      if (d == (unsigned)b && rank >= cnt[b] && b < 15) { rank -= cnt[b]; d = b + 1; }
+    }
+    prefix = (prefix << 4) | d;
+  }
+  const double e1 = key_value(prefix);
+  double res = e1;
+  if (two) {  // the next order statistic: e1 again if it is repeated beyond `rank`, else the smallest larger value
+    long long le = 0;
+    unsigned long long next = ~0ull;
+    for (int k = 0; k < m; k++) {
+      const unsigned long long key = order_key(ttheta(c, newest - k, i, w));
+      if (key <= prefix) le++;
+      else if (key < next) next = key;
+    }
+    const long long pos = (m - 1) / 2;
+    const double e2 = le >= pos + 2 ? e1 : key_value(next);
+    res = (e1 + e2) / 2.0;
+  }
+  out[(size_t)w * c.P + i] = res;
+}
+
 inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -777,4 +970,19 @@ void mfit_launch_trace_regrow(const MfitChains& c, double* new_theta, double* ne
 }
 void mfit_launch_flush(void* buf, size_t bytes, cudaStream_t st) {
   k_flush<<<148 * 8, 256, 0, st>>>((double*)buf, bytes / 8);
+}
+void mfit_launch_analytics(const MfitChains& c, long long take, int* sel, double* ml_theta, double* ml_prob,
+                           double* acceptance, double* cov, double* l_out, cudaStream_t st) {
+  const int nth = 128;
+  const size_t smem = sizeof(double) * (c.P + 2 * (size_t)c.P * c.P) + sizeof(int) * (nth + 2) + sizeof(double) * nth +
+                      sizeof(int) * nth + 16;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(k_analytics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  k_analytics<<<(unsigned)c.W, nth, smem, st>>>(c, take, sel, ml_theta, ml_prob, acceptance, cov, l_out);
+}
+void mfit_launch_median(const MfitChains& c, long long take, double* out, cudaStream_t st) {
+  k_median<<<blocks_for(c.stride * c.P, 128), 128, 0, st>>>(c, take, out);
 }

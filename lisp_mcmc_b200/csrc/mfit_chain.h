@@ -94,6 +94,9 @@ void mfit_launch_l_read(const MfitChains& c, double* out, cudaStream_t st);
 int mfit_measure_fp64_dev(cudaStream_t st, double* dfma_flops, double* cost_exp, double* cost_log, double* cost_sin,
                           double* cost_div);
 void mfit_launch_flush(void* buf, size_t bytes, cudaStream_t st);
+void mfit_launch_analytics(const MfitChains& c, long long take, int* sel, double* ml_theta, double* ml_prob,
+                           double* acceptance, double* cov, double* l_out, cudaStream_t st);
+void mfit_launch_median(const MfitChains& c, long long take, double* out, cudaStream_t st);
 void mfit_launch_trace_regrow(const MfitChains& c, double* new_theta, double* new_prob, long long new_cap,
                               cudaStream_t st);
 #endif

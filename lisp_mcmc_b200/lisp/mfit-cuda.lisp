@@ -84,6 +84,9 @@
 (cffi:defcfun ("mfit_last_read" %last-read) :int (ctx :pointer) (theta :pointer) (prob :pointer))
 (cffi:defcfun ("mfit_l_matrix_read" %l-matrix-read) :int (ctx :pointer) (l :pointer))
 (cffi:defcfun ("mfit_keep_walks" %keep-walks) :int (ctx :pointer) (keep :int64))
+(cffi:defcfun ("mfit_trace_analytics" %trace-analytics) :int
+  (ctx :pointer) (take :int64) (most-likely-theta :pointer) (most-likely-prob :pointer) (median :pointer)
+  (acceptance :pointer) (covariance :pointer) (l-matrix :pointer))
 
 (defmacro with-traps-masked (&body body)
   #+sbcl `(sb-int:with-float-traps-masked (:invalid :divide-by-zero :overflow :inexact :underflow) ,@body)
@@ -314,6 +317,21 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
       (:most-likely-params (values (read-step walker #'%best-read chain)))
       (:most-likely-step (read-step walker #'%best-read chain))
       (:last-step (read-step walker #'%last-read chain))
+      ((:median-params :stddev-params :covariance-matrix :l-matrix)      ; :516-543, computed on the device for all chains
+       (let ((take (or take 1000000000)) (null (cffi:null-pointer)))
+         (cffi:with-foreign-objects ((med :double (* w p)) (mat :double (* w p p)))
+           (ecase get
+             (:median-params (chk ctx (%trace-analytics ctx take null null med null null null)))
+             (:covariance-matrix (chk ctx (%trace-analytics ctx take null null null null mat null)))
+             ((:l-matrix :stddev-params) (chk ctx (%trace-analytics ctx take null null null null null mat))))
+           (flet ((mat-at (i j) (cffi:mem-aref mat :double (+ (* chain p p) (* i p) j))))
+             (ecase get
+               (:median-params (loop for k in keys for i from 0
+                                     append (list k (cffi:mem-aref med :double (+ (* chain p) i)))))
+               (:stddev-params (loop for k in keys for i from 0 append (list k (mat-at i i))))
+               ((:covariance-matrix :l-matrix)
+                (let ((a (make-array (list p p) :element-type 'double-float)))
+                  (dotimes (i p a) (dotimes (j p) (setf (aref a i j) (mat-at i j)))))))))))
       ((:steps :params :param :log-liklihoods :acceptance)
        (let ((take (or take (cffi:with-foreign-object (st '(:struct chain-stats) w)
                               (chk ctx (%stats-read ctx st))

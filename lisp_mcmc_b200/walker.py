@@ -387,6 +387,28 @@ class Walker:
         self._chk(self._L.mfit_l_matrix_read(self._h, _ptr(out)))
         return out
 
+    def analytics(self, take=None, which=("most-likely-step", "median-params", "acceptance", "covariance-matrix", "l-matrix")):
+        """walker-get's trace analytics for every chain at once, computed on the device (mfit_trace_analytics):
+        dict with any of most_likely_theta[W,P], most_likely_prob[W], median[W,P], acceptance[W], covariance[W,P,P],
+        l_matrix[W,P,P], stddev[W,P] (= diagonal of l_matrix, :stddev-params)."""
+        if take is None:
+            take = int(self.stats()["length"].max())
+        W, P = self.W, self.P
+        want = set(str(k).lstrip(":").lower() for k in which)
+        bufs = {"most_likely_theta": np.empty((W, P)) if "most-likely-step" in want else None,
+                "most_likely_prob": np.empty(W) if "most-likely-step" in want else None,
+                "median": np.empty((W, P)) if "median-params" in want else None,
+                "acceptance": np.empty(W) if "acceptance" in want else None,
+                "covariance": np.empty((W, P, P)) if "covariance-matrix" in want else None,
+                "l_matrix": np.empty((W, P, P)) if want & {"l-matrix", "stddev-params"} else None}
+        self._chk(self._L.mfit_trace_analytics(self._h, int(take), _ptr(bufs["most_likely_theta"]), _ptr(bufs["most_likely_prob"]),
+                                               _ptr(bufs["median"]), _ptr(bufs["acceptance"]), _ptr(bufs["covariance"]),
+                                               _ptr(bufs["l_matrix"])))
+        out = {k: v for k, v in bufs.items() if v is not None}
+        if "l_matrix" in out:
+            out["stddev"] = np.einsum("wii->wi", out["l_matrix"]).copy()
+        return out
+
     def philox_stream(self, first_step, nsteps):
         """The normals z[W,nsteps,P] and uniforms u[W,nsteps] the device draws for take-step calls made at walker
         age first_step, first_step+1, ... (for replaying a Philox run through an injected-stream implementation)."""
@@ -402,12 +424,27 @@ class Walker:
         st = self.stats()
         n = int(st["length"].max()) if take is None else int(take)
         sel = (lambda a: a if chain is None else a[chain])
-        if g in ("most-likely-params", "most-likely-step"):
+        if g == "most-likely-params":   # :511-515 reads the walker's most-likely-step slot
             th, pr = self.most_likely()
-            return sel(th) if g == "most-likely-params" else (sel(th), sel(pr))
+            return sel(th)
+        if g == "most-likely-step":     # :503-505 searches the newest `take` steps
+            a = self.analytics(n, ["most-likely-step"])
+            return sel(a["most_likely_theta"]), sel(a["most_likely_prob"])
         if g == "last-step":
             th, pr = self.last_step()
             return sel(th), sel(pr)
+        if g == "median-params":      # :516-523, on the device
+            return sel(self.analytics(n, ["median-params"])["median"])
+        if g == "acceptance":         # :506-508
+            return sel(self.analytics(n, ["acceptance"])["acceptance"])
+        if g == "covariance-matrix":  # :541
+            return sel(self.analytics(n, ["covariance-matrix"])["covariance"])
+        if g == "l-matrix":           # :543
+            return sel(self.analytics(n, ["l-matrix"])["l_matrix"])
+        if g == "stddev-params":      # :526-539 (zeros for walks shorter than 10 steps)
+            sd = self.analytics(n, ["stddev-params"])["stddev"]
+            sd[st["length"] < 10] = 0.0
+            return sel(sd)
         th, pr, nv = self.trace(max(n, 1))
         if g == "steps":
             return sel(th), sel(pr), sel(nv)
@@ -417,17 +454,6 @@ class Walker:
             return sel(pr)
         if g == "param":
             return sel(th[:, :, self.param_keys.index(str(param).lstrip(":").lower())])
-        if g == "acceptance":      # :506-508: runs of distinct consecutive probs / window
-            acc = np.empty(self.W)
-            for w in range(self.W):
-                p = pr[w, :nv[w]]
-                acc[w] = (1 + np.count_nonzero(p[1:].view(np.int64) != p[:-1].view(np.int64))) / float(len(p))
-            return sel(acc)
-        if g == "median-params":   # :516-523 with `median` = nth-percentile 50 (:1499-1513, midpoint form)
-            med = np.empty((self.W, self.P))
-            for w in range(self.W):
-                med[w] = np.median(th[w, :nv[w]], axis=0)
-            return sel(med)
         raise NotImplementedError("walker-get :%s" % g)
 
     # -------------------------------------------------------------- walker-save / walker-load (:971-1001)

@@ -414,3 +414,48 @@ def test_multi_gpu_sharding_is_bit_identical():
                         "--master-addr", "127.0.0.1", "--master-port", "29731",
                         os.path.join(root, "tests", "mgpu", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _nth_percentile(n, seq):
+    """nth-percentile :1493-1504 restated: position n (len-1)/100; a fractional position gives the MEAN of its two
+    neighbours (not an interpolation)"""
+    s = np.sort(np.asarray(seq, dtype=np.float64))
+    num = n * (len(s) - 1)
+    pos, rem = divmod(num, 100)
+    return s[pos] if rem == 0 else (s[pos] + s[pos + 1]) / 2
+
+
+@pytest.mark.parametrize("take", [37, 400, 1201])
+def test_trace_analytics_match_reference_definitions(orc, take):
+    """walker-get :most-likely-step / :median-params / :acceptance / :covariance-matrix / :l-matrix / :stddev-params
+    computed on the device over W chains at once == the reference's list definitions (:487-543) applied to the trace
+    (covariance and Cholesky through the oracle's restatement of :614-643 / :583-598: bit-identical)"""
+    cfg = workloads.c2(W=9, N=400)
+    w = workloads.make_walker(cfg, seed=3)
+    w.adaptive_steps_full(n=1200, temperature=10)
+    a = w.analytics(take)
+    th, pr, nv = w.trace(take)
+    for c in range(w.W):
+        m = int(nv[c])
+        p, t = pr[c, :m], th[c, :m]              # newest first
+        # :most-likely-step: reduce keeps x only when strictly greater, so of equal maxima the oldest wins
+        k = m - 1 - int(np.argmax(p[::-1]))
+        assert a["most_likely_prob"][c] == p[k] and np.array_equal(a["most_likely_theta"][c], t[k])
+        for i in range(w.P):
+            assert a["median"][c, i] == _nth_percentile(50, t[:, i])
+        changes = p[:-1].view(np.int64) != p[1:].view(np.int64)
+        assert a["acceptance"][c] == (1 + np.count_nonzero(changes)) / m
+        uniq = t[np.append(changes, True)]
+        assert np.array_equal(a["covariance"][c], orc.lplist_covariance(uniq))
+        fwd = t[:-1][p[:-1] > p[1:]]
+        if len(fwd) >= 2:
+            L = orc.lplist_to_l_matrix(fwd)
+            assert np.array_equal(a["l_matrix"][c], L, equal_nan=True)
+            assert np.array_equal(a["stddev"][c], np.diag(L), equal_nan=True)
+        else:
+            assert np.all(np.isnan(a["l_matrix"][c]))
+    # the same through walker-get
+    assert np.array_equal(w.get("median-params", take=take), a["median"])
+    assert np.array_equal(w.get("acceptance", take=take), a["acceptance"])
+    assert np.array_equal(w.get("most-likely-step", take=take)[1], a["most_likely_prob"])
+    w.close()
