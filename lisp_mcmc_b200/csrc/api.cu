@@ -88,7 +88,14 @@ struct mfit_ctx {
   std::vector<Dataset> ds;
   int seg_tiles_override = 0;
   std::map<const void*, int> resident;  // eval kernel -> CTAs resident on the whole device
-  int* sched_dev = nullptr;             // [2] work-item counter / finished-CTA counter of the eval kernels (zero between launches)
+  int* sched_dev = nullptr;             // [2 per group] work-item counter / finished-CTA counter of the eval kernels (zero between launches)
+  // A run splits the chains into two groups that advance on separate streams: the per-chain kernels of one group
+  // (segment reduction, accept/adapt, next proposal -- latency-bound, one warp per SM) and the tail of its likelihood
+  // kernel then overlap the likelihood kernel of the other group.  Chains never interact, so results are unchanged.
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  int n_groups = 1;
+  int groups_override = 0;              // mfit_set_groups: 0 = automatic
 
   // chains
   bool have_chains = false;
@@ -268,11 +275,14 @@ int check_problem_ready(mfit_ctx* ctx) {
   return 0;
 }
 
-int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const double* theta, const unsigned char* skip) {
+int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const double* theta, const unsigned char* skip,
+                int group = 0, int cb0 = 0, int n_cb = -1, cudaStream_t st = nullptr) {
+  if (!st) st = ctx->stream;
   if (s.n == 0 || s.n_seg == 0) return 0;
   if (!ctx->sched_dev) {
-    CU(cudaMalloc(&ctx->sched_dev, 2 * sizeof(int)));
-    CU(cudaMemsetAsync(ctx->sched_dev, 0, 2 * sizeof(int), ctx->stream));
+    CU(cudaMalloc(&ctx->sched_dev, 4 * sizeof(int)));
+    CU(cudaMemsetAsync(ctx->sched_dev, 0, 4 * sizeof(int), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
   }
   MfitEvalArgs a;
   memset(&a, 0, sizeof a);
@@ -282,13 +292,14 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
   a.xmax = s.xmax;
   a.tiles_per_seg = s.tiles_per_seg;
   a.n_seg = s.n_seg;
-  a.n_cb = (int)(w.stride / MFIT_CB);
+  a.n_cb = n_cb >= 0 ? n_cb : (int)(w.stride / MFIT_CB);
+  a.cb0 = cb0;
   a.W = (int)w.W;
   a.stride = w.stride;
   a.theta = theta;
   a.skip = skip;
   a.partial = w.partial[d];
-  a.sched = ctx->sched_dev;
+  a.sched = ctx->sched_dev + 2 * group;
   for (int k = 0; k < MFIT_MAXK; k++) a.idx[k] = s.idx[k];
   a.degree = s.degree;
   const void* fn = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user[s.ll_kind]
@@ -312,25 +323,27 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
   const long long items = (long long)a.n_cb * a.n_seg;
   if (items > 2000000000LL) return fail(ctx, MFIT_ERR_ARG, "dataset %d: too many work items (%lld chain-blocks x %d segments)", d, (long long)a.n_cb, a.n_seg);
   const unsigned grid = (unsigned)(items < it->second ? items : it->second);
-  CU(cudaLaunchKernel(fn, dim3(grid), dim3(MFIT_THREADS), args, smem, ctx->stream));
+  CU(cudaLaunchKernel(fn, dim3(grid), dim3(MFIT_THREADS), args, smem, st));
   ctx->launches++;
   return 0;
 }
 
 // all owned datasets: per-segment partial sums (+ user priors).  Built-in priors are written by the chain kernels.
-int eval_all(mfit_ctx* ctx, Workspace& w, const MfitChains& view, const double* theta, const unsigned char* skip) {
+int eval_all(mfit_ctx* ctx, Workspace& w, const MfitChains& view, const double* theta, const unsigned char* skip,
+             int group = 0, int cb0 = 0, int n_cb = -1, cudaStream_t st = nullptr) {
+  if (!st) st = ctx->stream;
   const bool timed = ctx->timing && ctx->ev_used < ctx->ev.size();
-  if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_used].a, ctx->stream));
+  if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_used].a, st));
   int n_eval = 0;
   for (int d = 0; d < ctx->D; d++) {
     Dataset& s = ctx->ds[d];
     if (!s.owned) continue;
-    int rc = launch_eval(ctx, s, w, d, theta, skip);
+    int rc = launch_eval(ctx, s, w, d, theta, skip, group, cb0, n_cb, st);
     if (rc) return rc;
     if (s.n > 0) n_eval++;
   }
   if (timed) {
-    CU(cudaEventRecord(ctx->ev[ctx->ev_used].b, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[ctx->ev_used].b, st));
     ctx->ev_used++;
     ctx->eval_launches += n_eval;
   }
@@ -339,9 +352,17 @@ int eval_all(mfit_ctx* ctx, Workspace& w, const MfitChains& view, const double* 
     if (!s.owned || s.prior_kind != 2) continue;
     double* out = view.xch ? const_cast<double*>(view.xch) + ((size_t)(s.owner * view.xslots + s.xslot) * 2 + 1) * view.stride
                            : view.lpd + (size_t)d * view.stride;
-    long long stride = w.stride, W = w.W;
-    void* args[] = {(void*)&theta, &stride, &W, (void*)&skip, &out};
-    CU(cudaLaunchKernel((const void*)s.k_prior, dim3((unsigned)((W + 127) / 128)), dim3(128), args, 0, ctx->stream));
+    // the user prior kernel indexes chains from 0: a group passes pointers advanced to its first chain
+    const long long w_lo = (long long)cb0 * MFIT_CB;
+    long long w_hi = n_cb >= 0 ? w_lo + (long long)n_cb * MFIT_CB : w.W;
+    if (w_hi > w.W) w_hi = w.W;
+    long long stride = w.stride, Wg = w_hi - w_lo;
+    if (Wg <= 0) continue;
+    const double* th_g = theta + w_lo;
+    const unsigned char* skip_g = skip ? skip + w_lo : nullptr;
+    double* out_g = out + w_lo;
+    void* args[] = {(void*)&th_g, &stride, &Wg, (void*)&skip_g, &out_g};
+    CU(cudaLaunchKernel((const void*)s.k_prior, dim3((unsigned)((Wg + 127) / 128)), dim3(128), args, 0, st));
     ctx->launches++;
   }
   return 0;
@@ -363,6 +384,8 @@ MfitChains view_of(mfit_ctx* ctx, Workspace& w) {
   v.P = ctx->P;
   v.D = ctx->D;
   v.stride = w.stride;
+  v.w0 = 0;
+  v.w1 = w.W;
   v.lld = w.lld;
   v.lpd = w.lpd;
   v.xch = w.xch;
@@ -527,22 +550,58 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
   long long t = ctx->run_t;
   const long long t_end = (budget < 0 || t + budget > ctx->run_max) ? ctx->run_max : t + budget;
   bool all_done = false;
+  // chain groups (see mfit_ctx::stream2): two when there are enough chains to fill the machine twice over, the data sets
+  // are not sharded over ranks (the exchange is a whole-set collective) and kernel times are not being recorded
+  // (an overlapped kernel's event interval includes its wait for SM slots)
+  const long long n_cb_all = c.stride / MFIT_CB;
+  int n_groups = (!ctx->sharded && !ctx->timing && n_cb_all >= 8) ? 2 : 1;
+  if (ctx->groups_override > 0) n_groups = ctx->groups_override > 2 ? 2 : ctx->groups_override;
+  if (ctx->sharded || n_cb_all < 2) n_groups = 1;
+  ctx->n_groups = n_groups;
+  if (n_groups == 2) {
+    if (!ctx->stream2) {
+      CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(ctx->fork_ev, ctx->stream));  // everything enqueued so far (run set-up, earlier steps) comes first
+    CU(cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0));
+  }
+  struct Group { int cb0, n_cb; long long w0, w1; cudaStream_t st; } grp[2];
+  {
+    const int half = (int)((n_cb_all + 1) / 2);
+    grp[0] = {0, n_groups == 2 ? half : (int)n_cb_all, 0, 0, ctx->stream};
+    grp[1] = {half, (int)n_cb_all - half, 0, 0, ctx->stream2};
+    for (int g = 0; g < 2; g++) {
+      grp[g].w0 = (long long)grp[g].cb0 * MFIT_CB;
+      grp[g].w1 = grp[g].w0 + (long long)grp[g].n_cb * MFIT_CB;
+      if (grp[g].w1 > c.W) grp[g].w1 = c.W;
+      if (grp[g].w0 > c.W) grp[g].w0 = c.W;
+    }
+  }
   for (; t < t_end && !all_done; t++) {
     if (ctx->stop.load()) break;  // mfit-walker-estop, :904
     r.t = t;
-    rc = eval_all(ctx, ctx->ws, c, c.prop_theta, c.done);
-    if (rc) return rc;
-    if (ctx->sharded) {
-      mfit_launch_finalize(c, ctx->stream);
-      ctx->launches++;
-      rc = exchange(ctx, ctx->ws);
+    for (int g = 0; g < n_groups; g++) {
+      const Group& G = grp[g];
+      if (G.w1 <= G.w0) continue;
+      MfitChains cg = c;
+      cg.w0 = G.w0;
+      cg.w1 = G.w1;
+      rc = eval_all(ctx, ctx->ws, c, c.prop_theta, c.done, g, G.cb0, G.n_cb, G.st);
       if (rc) return rc;
+      if (ctx->sharded) {
+        mfit_launch_finalize(c, ctx->stream);
+        ctx->launches++;
+        rc = exchange(ctx, ctx->ws);
+        if (rc) return rc;
+      }
+      mfit_launch_post(cg, r, true, G.st);  // accept/push/adapt of step t, proposal of step t+1
+      MfitRunCfg rn = r;
+      rn.t = t + 1;
+      mfit_launch_reest(cg, rn, G.st);
+      ctx->launches += 2;
     }
-    mfit_launch_post(c, r, true, ctx->stream);  // accept/push/adapt of step t, proposal of step t+1
-    MfitRunCfg rn = r;
-    rn.t = t + 1;
-    mfit_launch_reest(c, rn, ctx->stream);
-    ctx->launches += 2;
     if ((t + 1) % poll_every == 0) {
       // lagging poll: look at the answer of an earlier query if it has arrived; never block
       for (int s = 0; s < 4; s++)
@@ -551,6 +610,10 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
           if (ctx->active_host[s] == 0) all_done = true;
         }
       if (!poll_pending[poll_slot]) {
+        if (n_groups == 2) {  // the count must see both groups' step t
+          CU(cudaEventRecord(ctx->join_ev, ctx->stream2));
+          CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
+        }
         mfit_launch_count_active(c, ctx->active_dev + poll_slot, ctx->stream);
         ctx->launches++;
         CU(cudaMemcpyAsync(ctx->active_host + poll_slot, ctx->active_dev + poll_slot, sizeof(int),
@@ -560,6 +623,10 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
         poll_slot = (poll_slot + 1) & 3;
       }
     }
+  }
+  if (n_groups == 2) {
+    CU(cudaEventRecord(ctx->join_ev, ctx->stream2));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
   }
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
@@ -639,6 +706,7 @@ void mfit_ctx_destroy(mfit_ctx* ctx) {
   for (auto& p : ctx->ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (ctx->comm) mfit_nccl_comm_destroy(ctx->comm);
   cudaStreamSynchronize(ctx->stream);  // the stream-ordered frees above
+  if (ctx->stream2) { cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->fork_ev); cudaEventDestroy(ctx->join_ev); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1384,6 +1452,12 @@ int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches) {
   if (!ctx) return MFIT_ERR_ARG;
   if (seconds) *seconds = ctx->eval_seconds;
   if (launches) *launches = ctx->eval_launches;
+  return 0;
+}
+
+int mfit_set_groups(mfit_ctx* ctx, int n_groups) {
+  if (!ctx || n_groups < 0 || n_groups > 2) return MFIT_ERR_ARG;
+  ctx->groups_override = n_groups;
   return 0;
 }
 

@@ -148,7 +148,7 @@ __device__ double reduce_ll(const MfitChains& c, int d, long long w, int slice, 
   const int lane = threadIdx.x & 31;
   const int B = (s.n_seg + MFIT_RED_S - 1) / MFIT_RED_S;
   double sum = 0.0;
-  if (w < c.W) {
+  if (w < c.w1) {
     const int lo = slice * B, hi = min(s.n_seg, lo + B);
     if (lo < hi) {
       const double* p = s.partial + (size_t)lo * c.stride + w;
@@ -351,16 +351,16 @@ __global__ void k_post(const MfitChains c, MfitRunCfg r) {
   if (FIN) {
     __shared__ double red[MFIT_RED_S][32];
     const int slice = threadIdx.x >> 5;
-    w = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+    w = c.w0 + (long long)blockIdx.x * 32 + (threadIdx.x & 31);
     for (int d = 0; d < c.D; d++) {
       if (!c.ds[d].owned) continue;
       const double v = reduce_ll(c, d, w, slice, red);
-      if (slice == 0 && w < c.W) ll_ptr(c, d)[w] = v;
+      if (slice == 0 && w < c.w1) ll_ptr(c, d)[w] = v;
     }
     if (slice != 0) return;
   } else
-    w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= c.W) return;
+    w = c.w0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.w1) return;
   post_body(c, r, w);
   if (FUSE) {
     r.t += 1;
@@ -507,8 +507,8 @@ __device__ int reest_body(const MfitChains& c, const MfitRunCfg& r, long long w,
 
 // r.t is the take-step index of the step that FOLLOWS the re-estimate; the chain's proposal for it is made here
 __global__ void k_reest(const MfitChains c, const MfitRunCfg r) {
-  const long long w = blockIdx.x;
-  if (w >= c.W || !c.need_reest[w]) return;
+  const long long w = c.w0 + blockIdx.x;
+  if (w >= c.w1 || !c.need_reest[w]) return;
   extern __shared__ __align__(16) unsigned char sm[];
   const int upd = reest_body(c, r, w, sm);
   __syncthreads();  // l-matrix writes of every thread are visible to thread 0
@@ -906,16 +906,16 @@ void mfit_launch_reest(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st
     cudaFuncSetAttribute(k_reest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  k_reest<<<(unsigned)c.W, 128, smem, st>>>(c, r);
+  k_reest<<<(unsigned)(c.w1 - c.w0), 128, smem, st>>>(c, r);
 }
 void mfit_launch_pre(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st) {
   k_pre<<<blocks_for(c.W, 128), 128, 0, st>>>(c, r);
 }
 void mfit_launch_post(const MfitChains& c, const MfitRunCfg& r, bool fuse_pre, cudaStream_t st) {
   const bool fin = c.xch == nullptr;
-  const unsigned g = blocks_for(c.W, 128);
+  const unsigned g = blocks_for(c.w1 - c.w0, 128);
   if (fin) {
-    const unsigned gr = blocks_for(c.W, 32);
+    const unsigned gr = blocks_for(c.w1 - c.w0, 32);
     if (fuse_pre) k_post<true, true><<<gr, MFIT_RED_T, 0, st>>>(c, r);
     else k_post<true, false><<<gr, MFIT_RED_T, 0, st>>>(c, r);
   } else {

@@ -27,6 +27,7 @@ struct MfitDsDev {
 struct MfitChains {
   int W, P, D;
   long long stride;
+  long long w0, w1;     // chain range a per-step launch (k_post, k_reest) covers: [w0, w1), the whole set by default
   double* cur_theta;    // [P][stride]   (walker-last-step params)
   double* cur_prob;     // [stride]
   double* prop_theta;   // [P][stride]   proposal under evaluation

@@ -29,8 +29,12 @@
 #define MFIT_EVAL_CUH
 #include "mfit_math.cuh"
 
+#ifndef MFIT_TILE
 #define MFIT_TILE 128    /* points per shared-memory stage */
+#endif
+#ifndef MFIT_STAGES
 #define MFIT_STAGES 4    /* TMA ring depth */
+#endif
 #define MFIT_MAX_SEG 1024 /* segments (= work items per chain-block, = partial sums per chain) a data set is cut into at most */
 #define MFIT_THREADS 128 /* threads per CTA */
 #define MFIT_CB 256      /* chains per CTA: two per thread (thread t: chains t and t + MFIT_THREADS of the block) */
@@ -54,7 +58,8 @@ struct MfitEvalArgs {
   double xmin, xmax;    /* range of x over the data set (-inf, +inf when some x is not finite): Model::safe */
   int tiles_per_seg;
   int n_seg;
-  int n_cb;             /* chain blocks */
+  int n_cb;             /* chain blocks this launch covers */
+  int cb0;              /* first of them (a run may split the chains into groups that advance on separate streams) */
   int W;                /* chains */
   long long stride;     /* chain stride of theta / partial (W rounded up to MFIT_CB) */
   const double* theta;  /* [P][stride] parameter vectors to evaluate */
@@ -289,7 +294,7 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
 
   Model m_next[2];
   auto load_params = [&](int it) {
-    const long long c0 = (long long)(it % a.n_cb) * MFIT_CB + tid;
+    const long long c0 = (long long)(a.cb0 + it % a.n_cb) * MFIT_CB + tid;
     m_next[0].load(a, clamp_chain(c0));
     m_next[1].load(a, clamp_chain(c0 + MFIT_THREADS));
   };
@@ -302,7 +307,7 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
     do { item = q_items[seq % MFIT_QN]; } while (item == -2);
     if (item < 0) break;
     const int seg = item / a.n_cb;
-    const long long cb0 = (long long)(item % a.n_cb) * MFIT_CB;
+    const long long cb0 = (long long)(a.cb0 + item % a.n_cb) * MFIT_CB;
     const long long chain[2] = {cb0 + tid, cb0 + MFIT_THREADS + tid};
     bool live[2];
 #pragma unroll

@@ -351,6 +351,10 @@ class Walker:
         """(setf mfit-walker-estop t) :860"""
         self._L.mfit_request_stop(self._h)
 
+    def set_groups(self, n_groups):
+        """0 = automatic, 1 / 2 = advance the chains as one / two groups on separate streams (mfit_set_groups)"""
+        self._chk(self._L.mfit_set_groups(self._h, int(n_groups)))
+
     def keep_walks(self, keep):
         """walker-modify :keep-walks :568-569"""
         self._chk(self._L.mfit_keep_walks(self._h, int(keep)))

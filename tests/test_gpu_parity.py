@@ -459,3 +459,32 @@ def test_trace_analytics_match_reference_definitions(orc, take):
     assert np.array_equal(w.get("acceptance", take=take), a["acceptance"])
     assert np.array_equal(w.get("most-likely-step", take=take)[1], a["most_likely_prob"])
     w.close()
+
+
+def test_two_stream_chain_groups_do_not_change_results(orc):
+    """a run advances the chains as two groups on two streams (the per-chain kernels of one overlap the likelihood
+    kernel of the other): bit-identical to the one-group run, with built-in and NVRTC priors, Philox and injected
+    streams, and still identical to the oracle"""
+    cfg = workloads.c1(W=600)                      # 3 chain-blocks -> groups of 2 and 1; constant-bounds prior
+    cfg["theta0"] = cfg["theta0"] * (1 + 0.01 * np.random.default_rng(1).standard_normal(cfg["theta0"].shape))
+    n = 450
+    out = []
+    for g in (1, 2):
+        w = workloads.make_walker(cfg, seed=17)
+        w.set_groups(g)
+        w.adaptive_steps_full(n=n, temperature=10)
+        out.append(w.trace(2001) + (w.l_matrix(),))
+        w.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b, equal_nan=True)
+    # a global fit with lowered (NVRTC) priors and injected streams, against the oracle
+    g4 = workloads.c4(W=520, D=2, N=700)
+    rng = np.random.default_rng(2)
+    z, u = rng.standard_normal((520, 2000, len(g4["keys"]))), rng.uniform(size=(520, 2000))
+    w = workloads.make_walker(g4)
+    w.set_groups(2)
+    w.adaptive_steps_full(n=300, temperature=10, z=z, u=u)
+    _compare_chain(orc, g4, w, z, u,
+                   lambda ow, zz, uu: ow.adaptive_steps_full(n=300, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu),
+                   [0, 255, 256, 519])
+    w.close()
