@@ -488,3 +488,61 @@ def test_two_stream_chain_groups_do_not_change_results(orc):
                    lambda ow, zz, uu: ow.adaptive_steps_full(n=300, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu),
                    [0, 255, 256, 519])
     w.close()
+
+
+@pytest.mark.parametrize("opt", ["max-walker-length", "best-value", "l-matrix"])
+def test_adaptive_driver_options_identical_to_oracle(orc, opt):
+    """the remaining keyword arguments of walker-adaptive-steps-full (:862): :max-walker-length (the walk is cut to
+    half of it at the reset index, :868 / :923-927), :sampling-optimization :best-value (:895) and a caller-supplied
+    :l-matrix (:896)"""
+    cfg = workloads.c2(W=6, N=300)
+    w = workloads.make_walker(cfg)
+    n = 12500 if opt == "max-walker-length" else 2600
+    rng = np.random.default_rng(21)
+    z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    kw, okw = {}, {}
+    if opt == "max-walker-length":
+        kw = okw = dict(max_walker_length=3000)
+    elif opt == "best-value":
+        kw, okw = dict(sampling_optimization="best-value"), dict(sampling_optimization=orc.OPT_BEST_VALUE)
+    else:
+        Lm = np.diag(1e-3 * np.abs(cfg["theta_star"])) + 1e-4 * np.tril(np.ones((w.P, w.P)), -1)
+        kw = okw = dict(l_matrix=Lm)
+    w.adaptive_steps_full(n=n, temperature=10, z=z, u=u, **kw)
+    _compare_chain(orc, cfg, w, z, u,
+                   lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu, **okw),
+                   range(6))
+    if opt == "max-walker-length":
+        assert np.all(w.stats()["length"] < 3000 + 1600)   # the walk really was cut
+    w.close()
+
+
+def test_estop_slices_and_keep_walks(orc):
+    """mfit-walker-estop (:860, :904): a run issued in slices and stopped after 700 steps == the oracle's loop interrupted
+    after 700 take-steps; walker-modify :keep-walks (:568-569) then limits what walker-get :steps returns"""
+    cfg = workloads.c2(W=4, N=300)
+    w = workloads.make_walker(cfg)
+    n = 3000
+    rng = np.random.default_rng(22)
+    z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    import ctypes as C
+    L, h = w._L, w._h
+    cfgc = _lib.AdaptCfg(n, 10.0, _lib.AUTO_NONE, _lib.OPT_COVARIANCE, 0, 0, 0)
+    zp, up = np.ascontiguousarray(z), np.ascontiguousarray(u)
+    dp = C.POINTER(C.c_double)
+    w._chk(L.mfit_run_begin(h, C.byref(cfgc), None, zp.ctypes.data_as(dp), up.ctypes.data_as(dp), n))
+    done, fin, total = C.c_int64(), C.c_int(), 0
+    for k in (100, 250, 350):
+        w._chk(L.mfit_run_advance(h, k, C.byref(done), C.byref(fin)))
+        total += done.value
+        assert not fin.value
+    w.request_stop()
+    w._chk(L.mfit_run_advance(h, 500, C.byref(done), C.byref(fin)))
+    assert done.value == 0 and fin.value == 1 and total == 700
+    _compare_chain(orc, cfg, w, z, u,
+                   lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu, max_steps=700),
+                   range(4))
+    w.keep_walks(50)
+    th, pr, nv = w.trace(200)
+    assert np.all(nv == 50) and np.all(w.stats()["length"] == 50)
+    w.close()
