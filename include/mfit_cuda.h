@@ -98,6 +98,12 @@ int mfit_problem_define(mfit_ctx* ctx, int n_datasets, int n_params);
 /* :data (list x y) and :data-error of dataset d.  sigma==NULL means data-error 1 (:1144).
  * Stands in for clean-data / clean-data-error / to-double-floats :774-835 (the host flattens). */
 int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, const double* sigma, int64_t n);
+/* Walker set with per-walker data -- the reference's own many-walker workload (nv-specific.lisp:50-66: one walker per
+ * measured spectrum, same :function / priors, `(mapc #'walker-adaptive-steps walkers)`): chain w of W is fitted to its
+ * own row of y (W x n row-major) and of x / sigma unless x_shared / sigma_shared say that one n-vector serves all.
+ * mfit_chains_init / mfit_eval_logp must then be called with exactly W chains.  One warp per chain on the device. */
+int mfit_dataset_upload_per_walker(mfit_ctx* ctx, int d, const double* x, const double* y, const double* sigma,
+                                   int64_t n, int64_t W, int x_shared, int sigma_shared);
 /* :function slot of dataset d = built-in family; param_index maps family theta slots to the
  * shared parameter vector (global fits share keys across datasets, README.md "Global Parameter Fitting"). */
 int mfit_model_builtin(mfit_ctx* ctx, int d, int family, int degree, const int32_t* param_index, int n_idx);

@@ -49,6 +49,11 @@ struct Dataset {
   double xmin = 0.0, xmax = 0.0;  // -inf / +inf when some x is not finite
   double cst_normal = 0.0, cst_poisson = 0.0;
   bool poisson_ok = false;
+  // walker set with per-walker data: W_pc chains, chain w owns row w of y / yw / w / c (and of x unless x_shared)
+  long long W_pc = 0;
+  bool x_shared = false, sigma_shared = false;
+  double *cst_normal_pc = nullptr, *cst_poisson_pc = nullptr;  // [W_pc] device
+  cudaKernel_t k_user_pc[3] = {nullptr, nullptr, nullptr};
   int family = -1, degree = 0;
   int idx[MFIT_MAXK];
   int ll_kind = MFIT_LL_NORMAL;
@@ -169,7 +174,11 @@ void free_dev(void* p) { if (p) cudaFree(p); }
 
 void dataset_free_data(Dataset& d) {
   free_dev(d.x); free_dev(d.y); free_dev(d.yw); free_dev(d.w); free_dev(d.c);
+  free_dev(d.cst_normal_pc); free_dev(d.cst_poisson_pc);
   d.x = d.y = d.yw = d.w = d.c = nullptr;
+  d.cst_normal_pc = d.cst_poisson_pc = nullptr;
+  d.W_pc = 0;
+  d.x_shared = d.sigma_shared = false;
   d.n = -1;
 }
 void dataset_free_prior(Dataset& d) {
@@ -181,6 +190,7 @@ void dataset_free_prior(Dataset& d) {
 void dataset_free_model(Dataset& d) {
   if (d.lib_model) { cudaLibraryUnload(d.lib_model); d.lib_model = nullptr; }
   d.k_user[0] = d.k_user[1] = d.k_user[2] = nullptr;
+  d.k_user_pc[0] = d.k_user_pc[1] = d.k_user_pc[2] = nullptr;
 }
 
 void workspace_free(Workspace& w) {
@@ -207,6 +217,11 @@ double log_factorial_ref(long long n, std::vector<float>& memo) {
 // segment geometry is a function of the point count alone, so that partial sums -- and therefore
 // every log-likelihood bit -- do not depend on chain count, SM count or the number of GPUs
 void plan_segments(mfit_ctx* ctx, Dataset& d) {
+  if (d.W_pc > 0) {  // one warp sums a whole (short) data set
+    d.tiles_per_seg = 1;
+    d.n_seg = d.n > 0 ? 1 : 0;
+    return;
+  }
   const long long n_tiles = (d.n + MFIT_TILE - 1) / MFIT_TILE;
   // at most MFIT_MAX_SEG segments; two tiles per work item as soon as that still leaves >= 256 items per chain-block
   // (one-tile items pay ~4 % for their per-item set-up: measured on C2, tools/kbench.py --seg-tiles)
@@ -252,6 +267,9 @@ int workspace_make(mfit_ctx* ctx, Workspace& w, long long W) {
       plan_segments(ctx, s);
       h.n_seg = s.n_seg;
       h.cst = s.ll_kind == MFIT_LL_NORMAL ? s.cst_normal : s.ll_kind == MFIT_LL_POISSON ? s.cst_poisson : 0.0;
+      h.cst_pc = s.W_pc > 0 ? (s.ll_kind == MFIT_LL_NORMAL ? s.cst_normal_pc : s.ll_kind == MFIT_LL_POISSON ? s.cst_poisson_pc : nullptr) : nullptr;
+      if (s.W_pc > 0 && s.W_pc != W)
+        return fail(ctx, MFIT_ERR_ARG, "dataset %d holds data for %lld walkers, %lld chains requested", d, s.W_pc, (long long)W);
       if (s.n_seg > 0) CU(cudaMalloc(&w.partial[d], sizeof(double) * (size_t)s.n_seg * w.stride));
       h.partial = w.partial[d];
     }
@@ -302,6 +320,29 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
   a.sched = ctx->sched_dev + 2 * group;
   for (int k = 0; k < MFIT_MAXK; k++) a.idx[k] = s.idx[k];
   a.degree = s.degree;
+  if (s.W_pc > 0) {  // walker set with per-walker data: one warp per chain, no staging, no work-item queue
+    a.x_stride = s.x_shared ? 0 : s.n_pad;
+    a.pc_stride = s.n_pad;
+    a.w_stride = s.sigma_shared ? 0 : s.n_pad;
+    const void* fpc = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_pc[s.ll_kind]
+                                                : mfit_builtin_perchain_kernel(s.family, s.degree, s.ll_kind);
+    if (!fpc) return fail(ctx, MFIT_ERR_STATE, "no per-walker kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
+    auto itp = ctx->resident.find(fpc);
+    if (itp == ctx->resident.end()) {
+      int per_sm = 0, sms = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc, MFIT_PC_THREADS, 0));
+      CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      if (per_sm < 1) per_sm = 1;
+      itp = ctx->resident.emplace(fpc, per_sm * sms).first;
+    }
+    const long long chains = (long long)a.n_cb * MFIT_CB;
+    const long long need = (chains + MFIT_PC_THREADS / 32 - 1) / (MFIT_PC_THREADS / 32);
+    const unsigned gridp = (unsigned)(need < itp->second ? need : itp->second);
+    void* argsp[] = {&a};
+    CU(cudaLaunchKernel(fpc, dim3(gridp > 0 ? gridp : 1), dim3(MFIT_PC_THREADS), argsp, 0, st));
+    ctx->launches++;
+    return 0;
+  }
   const void* fn = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user[s.ll_kind]
                                               : mfit_builtin_eval_kernel(s.family, s.degree, s.ll_kind);
   if (!fn) return fail(ctx, MFIT_ERR_STATE, "no kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
@@ -386,6 +427,9 @@ MfitChains view_of(mfit_ctx* ctx, Workspace& w) {
   v.stride = w.stride;
   v.w0 = 0;
   v.w1 = w.W;
+  v.max_seg = 0;
+  for (const Dataset& s : ctx->ds)
+    if (s.owned && s.n_seg > v.max_seg) v.max_seg = s.n_seg;
   v.lld = w.lld;
   v.lpd = w.lpd;
   v.xch = w.xch;
@@ -802,6 +846,77 @@ int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, 
   return 0;
 }
 
+// walker set with per-walker data
+int mfit_dataset_upload_per_walker(mfit_ctx* ctx, int d, const double* x, const double* y, const double* sigma,
+                                   int64_t n, int64_t W, int x_shared, int sigma_shared) {
+  NEED_DS(d);
+  if (n < 0 || W < 1 || (n > 0 && (!x || !y))) return fail(ctx, MFIT_ERR_ARG, "dataset %d: bad x/y/n/W", d);
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  Dataset& s = ctx->ds[d];
+  dataset_free_data(s);
+  s.n = n;
+  s.n_pad = round_up(n > 0 ? n : 1, 32);
+  s.W_pc = W;
+  s.x_shared = x_shared != 0;
+  s.sigma_shared = sigma_shared != 0 || sigma == nullptr;
+  const size_t np = (size_t)s.n_pad, rows = (size_t)W, xrows = x_shared ? 1 : rows, wrows = s.sigma_shared ? 1 : rows;
+  std::vector<double> xx(np * xrows, 0.0), yy(np * rows, 0.0), yw(np * rows, 0.0), w(np * wrows, 0.0), cc(np * wrows, 0.0);
+  std::vector<double> cst(rows, 0.0), pcst(rows, 0.0);
+  const double a = -0.5 * std::log(2.0 * 3.141592653589793);  // (* -1/2 (log (* 2 pi))) :377
+  double xmin = INFINITY, xmax = -INFINITY;
+  bool x_finite = true, pois_ok = true;
+  std::vector<float> memo;
+  for (size_t r = 0; r < xrows; r++)
+    for (long long i = 0; i < n; i++) {
+      const double v = x[r * (size_t)n + i];
+      xx[r * np + i] = v;
+      if (!std::isfinite(v)) x_finite = false;
+      if (v < xmin) xmin = v;
+      if (v > xmax) xmax = v;
+    }
+  for (size_t r = 0; r < rows; r++) {
+    double c0 = 0.0, p0 = 0.0;
+    for (long long i = 0; i < n; i++) {
+      const double sg = sigma ? sigma[(sigma_shared ? 0 : r * (size_t)n) + i] : 1.0;  // (if data-error data-error 1) :1144
+      const double yv = y[r * (size_t)n + i];
+      const size_t o = r * np + i, ow = (s.sigma_shared ? 0 : r * np) + i;
+      yy[o] = yv;
+      w[ow] = 1.0 / sg;
+      yw[o] = yv * w[ow];
+      const double ci = a + (-1.0 * std::log(sg));
+      cc[ow] = ci;
+      c0 = i == 0 ? ci : c0 + ci;
+      if (pois_ok) {
+        if (!(yv >= 0.0) || yv != std::floor(yv) || yv > 5e6) pois_ok = false;
+        else {
+          const double lf = log_factorial_ref((long long)yv, memo);
+          p0 = i == 0 ? -lf : p0 - lf;
+        }
+      }
+    }
+    cst[r] = c0;
+    pcst[r] = p0;
+  }
+  s.xmin = x_finite && n > 0 ? xmin : -INFINITY;
+  s.xmax = x_finite && n > 0 ? xmax : INFINITY;
+  s.cst_normal = s.cst_poisson = 0.0;
+  s.poisson_ok = pois_ok;
+  const size_t bytes = sizeof(double) * np * rows, xbytes = sizeof(double) * np * xrows, cb = sizeof(double) * rows;
+  const size_t wbytes = sizeof(double) * np * wrows;
+  CU(cudaMalloc(&s.x, xbytes)); CU(cudaMalloc(&s.y, bytes)); CU(cudaMalloc(&s.yw, bytes)); CU(cudaMalloc(&s.w, wbytes));
+  CU(cudaMalloc(&s.c, wbytes)); CU(cudaMalloc(&s.cst_normal_pc, cb)); CU(cudaMalloc(&s.cst_poisson_pc, cb));
+  CU(cudaMemcpyAsync(s.x, xx.data(), xbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.y, yy.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.yw, yw.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.w, w.data(), wbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.c, cc.data(), wbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.cst_normal_pc, cst.data(), cb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(s.cst_poisson_pc, pcst.data(), cb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->have_chains) chains_free(ctx);
+  return 0;
+}
+
 int mfit_model_builtin(mfit_ctx* ctx, int d, int family, int degree, const int32_t* param_index, int n_idx) {
   NEED_DS(d);
   const int need = mfit_family_nparams(family, degree);
@@ -841,6 +956,9 @@ int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* 
   CU(cudaLibraryGetKernel(&s.k_user[0], s.lib_model, "mfit_user_eval_normal"));
   CU(cudaLibraryGetKernel(&s.k_user[1], s.lib_model, "mfit_user_eval_cutoff"));
   CU(cudaLibraryGetKernel(&s.k_user[2], s.lib_model, "mfit_user_eval_poisson"));
+  CU(cudaLibraryGetKernel(&s.k_user_pc[0], s.lib_model, "mfit_user_perchain_normal"));
+  CU(cudaLibraryGetKernel(&s.k_user_pc[1], s.lib_model, "mfit_user_perchain_cutoff"));
+  CU(cudaLibraryGetKernel(&s.k_user_pc[2], s.lib_model, "mfit_user_perchain_poisson"));
   s.family = MFIT_FAM_SEXPR;
   s.degree = 0;
   return 0;

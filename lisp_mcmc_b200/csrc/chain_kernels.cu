@@ -143,10 +143,11 @@ __device__ __forceinline__ double* lp_ptr(const MfitChains& c, int d) {
 #define MFIT_RED_T (32 * MFIT_RED_S)
 // called by all MFIT_RED_T threads of the block (w may be >= c.W: such threads only take part in the barriers);
 // the result is valid in the threads of slice 0
+template <int S>
 __device__ double reduce_ll(const MfitChains& c, int d, long long w, int slice, double (*red)[32]) {
   const MfitDsDev& s = c.ds[d];
   const int lane = threadIdx.x & 31;
-  const int B = (s.n_seg + MFIT_RED_S - 1) / MFIT_RED_S;
+  const int B = (s.n_seg + S - 1) / S;
   double sum = 0.0;
   if (w < c.w1) {
     const int lo = slice * B, hi = min(s.n_seg, lo + B);
@@ -164,17 +165,20 @@ __device__ double reduce_ll(const MfitChains& c, int d, long long w, int slice, 
       for (; k < hi; k++) sum = sum + p[(size_t)(k - lo) * c.stride];
     }
   }
-  __syncthreads();  // red is free again
-  red[slice][lane] = sum;
-  __syncthreads();
-  if (slice == 0 && B > 0) {
-    const int used = (s.n_seg + B - 1) / B;
-    for (int k = 1; k < used; k++) sum = sum + red[k][lane];
+  if (S > 1) {
+    __syncthreads();  // red is free again
+    red[slice][lane] = sum;
+    __syncthreads();
+    if (slice == 0 && B > 0) {
+      const int used = (s.n_seg + B - 1) / B;
+      for (int k = 1; k < used; k++) sum = sum + red[k][lane];
+    }
   }
+  const double cst = (s.cst_pc != nullptr && w < c.W) ? s.cst_pc[w] : s.cst;
   switch (s.ll_kind) {
-    case MFIT_LL_NORMAL: return s.cst + (-0.5 * sum);
+    case MFIT_LL_NORMAL: return cst + (-0.5 * sum);
     case MFIT_LL_NORMAL_CUTOFF: return sum;
-    default: return s.cst + sum;
+    default: return cst + sum;
   }
 }
 
@@ -342,19 +346,20 @@ __global__ void k_pre(const MfitChains c, const MfitRunCfg r) {
   long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w < c.W) pre_body(c, r, w);
 }
-// FIN: the per-segment sums of this rank's data sets are reduced here (blocks of 32 chains x MFIT_RED_S slices); the
-// per-chain work that follows runs in the threads of slice 0.  Without FIN (data sets sharded over ranks: k_finalize
-// and the all-gather have run) one thread per chain.
-template <bool FIN, bool FUSE>
+// FIN: the per-segment sums of this rank's data sets are reduced here (blocks of 32 chains x S slices; S = 1, one thread
+// per chain, when every data set has only a few segments -- walker sets with per-walker data have one); the per-chain
+// work that follows runs in the threads of slice 0.  Without FIN (data sets sharded over ranks: k_finalize and the
+// all-gather have run) one thread per chain.
+template <bool FIN, bool FUSE, int S>
 __global__ void k_post(const MfitChains c, MfitRunCfg r) {
   long long w;
   if (FIN) {
-    __shared__ double red[MFIT_RED_S][32];
-    const int slice = threadIdx.x >> 5;
-    w = c.w0 + (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+    __shared__ double red[S][32];
+    const int slice = S > 1 ? threadIdx.x >> 5 : 0;
+    w = S > 1 ? c.w0 + (long long)blockIdx.x * 32 + (threadIdx.x & 31) : c.w0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (int d = 0; d < c.D; d++) {
       if (!c.ds[d].owned) continue;
-      const double v = reduce_ll(c, d, w, slice, red);
+      const double v = reduce_ll<S>(c, d, w, slice, red);
       if (slice == 0 && w < c.w1) ll_ptr(c, d)[w] = v;
     }
     if (slice != 0) return;
@@ -373,7 +378,7 @@ __global__ void k_finalize(const MfitChains c) {
   const long long w = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
   for (int d = 0; d < c.D; d++) {
     if (!c.ds[d].owned) continue;
-    const double v = reduce_ll(c, d, w, slice, red);
+    const double v = reduce_ll<MFIT_RED_S>(c, d, w, slice, red);
     if (slice == 0 && w < c.W) ll_ptr(c, d)[w] = v;
   }
 }
@@ -915,12 +920,17 @@ void mfit_launch_post(const MfitChains& c, const MfitRunCfg& r, bool fuse_pre, c
   const bool fin = c.xch == nullptr;
   const unsigned g = blocks_for(c.w1 - c.w0, 128);
   if (fin) {
-    const unsigned gr = blocks_for(c.w1 - c.w0, 32);
-    if (fuse_pre) k_post<true, true><<<gr, MFIT_RED_T, 0, st>>>(c, r);
-    else k_post<true, false><<<gr, MFIT_RED_T, 0, st>>>(c, r);
+    if (c.max_seg <= 8) {  // few segments: one thread per chain
+      if (fuse_pre) k_post<true, true, 1><<<g, 128, 0, st>>>(c, r);
+      else k_post<true, false, 1><<<g, 128, 0, st>>>(c, r);
+    } else {
+      const unsigned gr = blocks_for(c.w1 - c.w0, 32);
+      if (fuse_pre) k_post<true, true, MFIT_RED_S><<<gr, MFIT_RED_T, 0, st>>>(c, r);
+      else k_post<true, false, MFIT_RED_S><<<gr, MFIT_RED_T, 0, st>>>(c, r);
+    }
   } else {
-    if (fuse_pre) k_post<false, true><<<g, 128, 0, st>>>(c, r);
-    else k_post<false, false><<<g, 128, 0, st>>>(c, r);
+    if (fuse_pre) k_post<false, true, 1><<<g, 128, 0, st>>>(c, r);
+    else k_post<false, false, 1><<<g, 128, 0, st>>>(c, r);
   }
 }
 void mfit_launch_finalize(const MfitChains& c, cudaStream_t st) {

@@ -14,6 +14,7 @@ struct MfitDsDev {
   int n_seg;
   int ll_kind;
   double cst;             // theta-independent part of the log-likelihood
+  const double* cst_pc;   // per-chain constants instead (walker sets with per-walker data), or null
   int owned;              // this rank evaluates the dataset
   int prior_kind;         // 0 flat, 1 bounds, 2 user kernel (lp written by an NVRTC kernel)
   int nb;
@@ -27,6 +28,7 @@ struct MfitDsDev {
 struct MfitChains {
   int W, P, D;
   long long stride;
+  int max_seg;          // largest n_seg over this rank's data sets (picks the shape of the segment reduction)
   long long w0, w1;     // chain range a per-step launch (k_post, k_reest) covers: [w0, w1), the whole set by default
   double* cur_theta;    // [P][stride]   (walker-last-step params)
   double* cur_prob;     // [stride]

@@ -41,6 +41,7 @@
 #ifndef MFIT_MIN_CTAS
 #define MFIT_MIN_CTAS 3   /* CTAs per SM the register allocation is bounded for */
 #endif
+#define MFIT_PC_THREADS 256 /* threads per CTA of the per-walker-data kernel (one warp per chain) */
 #define MFIT_QN 8        /* ring of item ids handed from the producer thread to the CTA */
 #define MFIT_MAXK 16     /* parameters a built-in family may gather */
 
@@ -66,6 +67,9 @@ struct MfitEvalArgs {
   const unsigned char* skip; /* [stride] 1 = chain finished, nothing to do (may be null) */
   double* partial;      /* [n_seg][stride] per-segment sums */
   int* sched;           /* [2] zero between launches: next item to hand out, CTAs that have finished */
+  /* walker sets with per-walker data (mfit_eval_perchain_body): chain w reads x + w * x_stride (0: one x for all),
+   * y / yw + w * pc_stride, w / c + w * w_stride; chains [cb0 * MFIT_CB, (cb0 + n_cb) * MFIT_CB) of this launch */
+  long long x_stride, pc_stride, w_stride;  /* w_stride: rows of w / c (0: one sigma vector for all chains) */
   int idx[MFIT_MAXK];   /* built-in families: family slot -> shared parameter index */
   int degree;
 };
@@ -367,6 +371,83 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
       a.sched[1] = 0;
       __threadfence();
     }
+  }
+}
+
+// ---------------------------------------------------------------- walker sets with per-walker data
+// The reference's own many-walker workload (nv-specific.lisp:50-66): one walker per measured spectrum, a few hundred
+// points each, same :function / priors, `(mapc #'walker-adaptive-steps walkers)`.  Nothing is shared between chains
+// here, so the mapping flips: one WARP per chain, the lanes stride over that chain's points (coalesced 256-byte
+// reads straight from global memory -- every byte is used once per step, there is nothing to stage), theta is
+// warp-uniform, four independent accumulators per lane, and the 128 partial sums are combined in a fixed order
+// (accumulators, then a shuffle tree).  This kernel is bound by L2 / HBM bandwidth (24 bytes per point-eval), not
+// by the FP64 pipe.  Persistent warps stride over the chains of the launch.
+#define MFIT_PC_U 8 /* strides of 32 points whose loads are issued together (memory-level parallelism per warp) */
+template <class Model, int LL, bool SLOW, class G>
+__device__ __forceinline__ double mfit_perchain_pass(const Model& m, const double* xs, const double* ys, const double* ws,
+                                                     const double* cs, long long n, int lane, G& gd) {
+  constexpr int NARR = MfitTerm<LL>::NARR;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long i0 = 0; i0 < n; i0 += 32 * MFIT_PC_U) {
+    // all loads of this block first: a warp issues in order, so loads left inside the arithmetic would each expose a
+    // full memory latency (the kernel ran at 1.9 TB/s that way)
+    double xv[MFIT_PC_U], yv[MFIT_PC_U], wv[MFIT_PC_U], cv[MFIT_PC_U];
+#pragma unroll
+    for (int u = 0; u < MFIT_PC_U; u++) {
+      const long long j = i0 + 32 * u + lane;
+      const bool in = j < n;
+      xv[u] = in ? xs[j] : 0.0;
+      yv[u] = in ? ys[j] : 0.0;
+      wv[u] = (NARR > 2 && in) ? ws[j] : 0.0;
+      cv[u] = (NARR > 3 && in) ? cs[j] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < MFIT_PC_U; u++) {
+      if (i0 + 32 * u + lane < n) {
+        const double f = m.template eval<SLOW>(xv[u], gd);
+        acc[u & 3] = MfitTerm<LL>::template add<SLOW>(acc[u & 3], f, yv[u], wv[u], cv[u], gd);
+      }
+    }
+  }
+  double sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum = sum + __shfl_down_sync(0xffffffffu, sum, off);
+  return sum;  // valid in lane 0
+}
+
+template <class Model, int LL>
+__device__ __forceinline__ void mfit_eval_perchain_body(const MfitEvalArgs& a) {
+  constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
+  mfit_math_stage(Model::USES | MfitTerm<LL>::USES, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long w_lo = (long long)a.cb0 * MFIT_CB;
+  long long w_hi = w_lo + (long long)a.n_cb * MFIT_CB;
+  if (w_hi > a.W) w_hi = a.W;
+  long long chain = w_lo + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  Model m_next;
+  if (chain < w_hi) m_next.load(a, chain);
+  for (; chain < w_hi; chain += warps) {
+    Model m = m_next;
+    if (chain + warps < w_hi) m_next.load(a, chain + warps);  // the next chain's parameters, one chain ahead
+    if (a.skip != nullptr && a.skip[chain] != 0) continue;
+    m.setup();
+    const double* xs = a.x + chain * a.x_stride;
+    const double* ys = (LL == MFITK_NORMAL ? a.yw : a.y) + chain * a.pc_stride;
+    const double* ws = a.w + chain * a.w_stride;
+    const double* cs = a.c + chain * a.w_stride;
+    double sum;
+    if (!GUARDED) {
+      MfitNoGuard ng;
+      sum = mfit_perchain_pass<Model, LL, false>(m, xs, ys, ws, cs, a.n, lane, ng);
+    } else {
+      MfitGuard gd;
+      gd.reset();
+      sum = mfit_perchain_pass<Model, LL, false>(m, xs, ys, ws, cs, a.n, lane, gd);
+      if (__any_sync(0xffffffffu, gd.tripped() ? 1 : 0)) sum = mfit_perchain_pass<Model, LL, true>(m, xs, ys, ws, cs, a.n, lane, gd);
+    }
+    if (lane == 0) a.partial[chain] = sum;  // one segment
   }
 }
 

@@ -169,7 +169,7 @@ class Walker:
 
     def __init__(self, function, data, params, data_error=None, log_liklihood=None, log_prior=None,
                  n_walkers=None, theta0=None, seed=0, device=0, chain_id_base=0, trace_capacity=0,
-                 nccl=None, dataset_owners=None, stream=None):
+                 nccl=None, dataset_owners=None, stream=None, per_walker=None):
         L = _lib.lib()
         self._L = L
         self.function = force_list(function)                        # :1142
@@ -177,8 +177,14 @@ class Walker:
         self.param_keys, p0 = plist(params)                         # :1145
         P = len(self.param_keys)
         self.P, self.D = P, D
-        self.data = clean_data(data, D)                             # :1143
-        self.data_error = clean_data_error(data_error, self.data)   # :1144
+        self.per_walker = per_walker
+        if per_walker is not None:    # walker set with per-walker data (walker_set_create): one :function, W data sets
+            if D != 1:
+                raise ValueError("a walker set with per-walker data takes one :function")
+            self.data, self.data_error = [(per_walker["x"], per_walker["y"])], [per_walker["sigma"]]
+        else:
+            self.data = clean_data(data, D)                             # :1143
+            self.data_error = clean_data_error(data_error, self.data)   # :1144
         ll = log_liklihood if isinstance(log_liklihood, (list, tuple)) else [log_liklihood] * D
         self.log_liklihood = [x if x is not None else "log-liklihood-normal" for x in ll]
         if isinstance(log_prior, (list, tuple)) and log_prior and not isinstance(log_prior[0], (tuple, list)):
@@ -213,7 +219,12 @@ class Walker:
             self._chk(L.mfit_dataset_owners(h, own.ctypes.data_as(C.POINTER(C.c_int32))))
             self.dataset_owners = list(own)
         for d in range(D):
-            if self.dataset_owners is None or self.dataset_owners[d] == self.rank:
+            if per_walker is not None:
+                pw = per_walker
+                self._chk(L.mfit_dataset_upload_per_walker(h, d, _ptr(pw["x"]), _ptr(pw["y"]), _ptr(pw["sigma"]),
+                                                           pw["y"].shape[1], pw["y"].shape[0], int(pw["x"].ndim == 1),
+                                                           int(pw["sigma"].ndim == 1)))
+            elif self.dataset_owners is None or self.dataset_owners[d] == self.rank:
                 x, y = self.data[d]
                 e = self.data_error[d]
                 self._chk(L.mfit_dataset_upload(h, d, _ptr(x), _ptr(y), _ptr(e), len(x)))
@@ -225,7 +236,7 @@ class Walker:
             self._set_prior(d, self.log_prior[d])
 
         if theta0 is None:
-            W = int(n_walkers or 1)
+            W = int(per_walker["y"].shape[0] if per_walker is not None else (n_walkers or 1))
             theta0 = np.tile(p0, (W, 1))
         else:
             theta0 = _f64(theta0)
@@ -505,6 +516,35 @@ def walker_create(function=None, data=None, params=None, data_error=None, log_li
     """walker-create :1132-1163 (param-bounds is ignorable in the reference too, :1141).  Extra keywords select the
     GPU-side batch: n_walkers / theta0, seed, device, chain_id_base, trace_capacity, nccl, dataset_owners."""
     return Walker(function, data, params, data_error, log_liklihood, log_prior, **gpu)
+
+
+def walker_set_create(function=None, data=None, params=None, data_error=None, log_liklihood=None, log_prior=None, **gpu):
+    """A walker set with per-walker data, the reference's own many-walker workload: file->nv-walkers makes one walker per
+    spectrum -- (x y_k) pairs with a common x -- and advances them one after another with mapc (nv-specific.lisp:50-66).
+    `data` is a list of W (x y) sets of equal length, or (x, Y) with Y of shape W x n sharing one x; `data_error` a
+    number, one n-vector for all walkers, or W x n.  :function / :log-liklihood / :log-prior are shared; `params` is the
+    common starting point unless theta0 (W x P) is given.  All W walkers advance together, one warp per walker."""
+    if isinstance(data, (list, tuple)) and len(data) == 2 and np.ndim(data[1]) == 2 and np.ndim(data[0]) == 1:
+        x, Y = _f64(data[0]), _f64(data[1])
+    else:
+        sets = [(_f64(s_[0]), _f64(s_[1])) for s_ in data]
+        n = len(sets[0][0])
+        if any(len(a) != n or len(b) != n for a, b in sets):
+            raise ValueError("every walker's data set must have the same number of points")
+        Y = np.stack([b for _, b in sets])
+        x = sets[0][0] if all(np.array_equal(a, sets[0][0]) for a, _ in sets) else np.stack([a for a, _ in sets])
+    W, n = Y.shape
+    if x.shape not in ((n,), (W, n)):
+        raise ValueError("x must have n points, or W x n")
+    if data_error is None:
+        data_error = 1.0                                            # (if data-error data-error 1) :1144
+    e = _f64(data_error)
+    if e.ndim == 0 or (e.ndim == 1 and len(e) != n):                # clean-data-error :794-805: the first number, broadcast
+        e = np.full(n, float(e.ravel()[0]))
+    if e.shape not in ((n,), (W, n)):
+        raise ValueError("data_error must be a number, n values, or W x n")
+    pw = {"x": np.ascontiguousarray(x), "y": np.ascontiguousarray(Y), "sigma": np.ascontiguousarray(e)}
+    return Walker(function, None, params, None, log_liklihood, log_prior, per_walker=pw, **gpu)
 
 
 def walker_adaptive_steps_full(walker, **kw):

@@ -100,6 +100,29 @@ def c5(W=65536, N=10000000):
                 steps=20, flop_per_point=16, transc_per_point={"exp": 1}, fp64_instr_per_point=18)
 
 
+def nvset(W=131072, N=500):
+    """walker set with per-walker data: one double-Lorentzian (NV) spectrum of N points per walker, common x and sigma
+    (the reference's own many-walker workload, nv-specific.lisp:50-66); returns a dict for make_walker_set"""
+    rng = np.random.default_rng(1006)
+    x = np.linspace(2800.0, 2940.0, N)
+    keys = ["scale1", "scale2", "mu1", "mu2", "sigma", "bg0"]
+    th = np.array([1e-2, 1e-2, 2860.0, 2880.0, 12.0, 5e-6])
+    thk = th[None, :] * (1.0 + np.array([0.05, 0.05, 1e-3, 1e-3, 0.05, 0.05])[None, :] * rng.standard_normal((W, 6)))
+    g2 = thk[:, 4:5] ** 2
+    f = thk[:, 5:6] - thk[:, 0:1] * g2 / ((x[None, :] - thk[:, 2:3]) ** 2 + g2) - thk[:, 1:2] * g2 / ((x[None, :] - thk[:, 3:4]) ** 2 + g2)
+    Y = f + 1e-7 * rng.standard_normal((W, N))
+    return dict(name="NVSET", function=[builtin("nv_multi", keys, degree=2)], data=(x, Y), data_error=1e-7, keys=keys,
+                theta_star=th, theta0=thk * (1.0 + 1e-4 * rng.standard_normal((W, 6))), log_liklihood="log-liklihood-normal",
+                log_prior=families.log_prior_nv_text(), steps=200, fp64_instr_per_point=16, bytes_per_point=8)
+
+
+def make_walker_set(cfg, **gpu):
+    from .walker import walker_set_create
+    params = [(k, v) for k, v in zip(cfg["keys"], cfg["theta_star"])]
+    return walker_set_create(function=cfg["function"][0], data=cfg["data"], params=params, data_error=cfg["data_error"],
+                             log_liklihood=cfg["log_liklihood"], log_prior=cfg["log_prior"], theta0=cfg["theta0"], **gpu)
+
+
 CONFIGS = {"C1": c1, "C2": c2, "C3": c3, "C4": c4, "C5": c5}
 
 

@@ -34,10 +34,16 @@ def main():
         kw["W"] = args.W
     if args.N:
         kw["N"] = args.N
-    cfg = workloads.CONFIGS[args.config](**kw)
-    N = sum(len(d[0]) for d in cfg["data"])
-    W = cfg["theta0"].shape[0]
-    w = workloads.make_walker(cfg)
+    if args.config == "NVSET":
+        cfg = workloads.nvset(**kw)
+        N = cfg["data"][1].shape[1]
+        W = cfg["theta0"].shape[0]
+        w = workloads.make_walker_set(cfg)
+    else:
+        cfg = workloads.CONFIGS[args.config](**kw)
+        N = sum(len(d[0]) for d in cfg["data"])
+        W = cfg["theta0"].shape[0]
+        w = workloads.make_walker(cfg)
     if args.seg_tiles:
         w._chk(L.mfit_set_segment_tiles(w._h, args.seg_tiles))
     w._chk(L.mfit_set_timing(w._h, 1))
@@ -52,6 +58,20 @@ def main():
     mean = tot / args.reps
     print("%s lib=%s seg_tiles=%d W=%d N=%d: eval kernels %.4f ms mean, %.4f ms best -> %.4g point-evals/s (mean), %.4g (best)"
           % (args.config, os.path.basename(_lib.LIB_PATH), args.seg_tiles, W, N, mean * 1e3, best * 1e3, W * N / mean, W * N / best))
+    if args.config == "NVSET":
+        by = cfg["bytes_per_point"] * W * N
+        print("  per-walker data: %.1f MB of y/sigma per pass -> %.0f GB/s of algorithmic traffic (measured copy peak 6540 GB/s)"
+              % (by / 1e6, by / mean / 1e9))
+        cfgc = _lib.AdaptCfg(30000, 10.0, _lib.AUTO_NONE, _lib.OPT_COVARIANCE, 0, 0, 0)
+        done, fin = C.c_int64(), C.c_int()
+        w._chk(L.mfit_set_timing(w._h, 0))
+        w._chk(L.mfit_run_begin(w._h, C.byref(cfgc), None, None, None, 0))
+        w._chk(L.mfit_run_advance(w._h, 5, C.byref(done), C.byref(fin)))
+        t0 = time.perf_counter()
+        w._chk(L.mfit_run_advance(w._h, 50, C.byref(done), C.byref(fin)))
+        dt = time.perf_counter() - t0
+        print("  50 adaptive MH steps of %d walkers: %.2f ms/step -> %.3g MH steps/s, %.3g point-evals/s"
+              % (W, dt / 50 * 1e3, W * 50 / dt, W * N * 50 / dt))
     w.close()
     if args.e2e:
         K = args.e2e
