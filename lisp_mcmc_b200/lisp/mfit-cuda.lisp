@@ -28,7 +28,7 @@
   (:use :cl)
   (:export #:gpu-lambda #:gpu-builtin #:gpu-walker #:walker-create #:walker-adaptive-steps
            #:walker-adaptive-steps-full #:walker-many-steps #:walker-sample-region #:walker-force-take-step
-           #:walker-get #:walker-save #:walker-free #:mcmc-fit #:mfit-walker-estop #:lower-to-cuda))
+           #:walker-get #:walker-save #:walker-free #:mcmc-fit #:mfit-walker-estop #:lower-to-cuda #:walker-set-create))
 (in-package :mfit-cuda)
 
 (cffi:define-foreign-library libmfit-cuda (t (:default "libmfit_cuda")))
@@ -50,6 +50,8 @@
 (cffi:defcfun ("mfit_problem_define" %problem-define) :int (ctx :pointer) (n-datasets :int) (n-params :int))
 (cffi:defcfun ("mfit_dataset_upload" %dataset-upload) :int
   (ctx :pointer) (d :int) (x :pointer) (y :pointer) (sigma :pointer) (n :int64))
+(cffi:defcfun ("mfit_dataset_upload_per_walker" %dataset-upload-per-walker) :int
+  (ctx :pointer) (d :int) (x :pointer) (y :pointer) (sigma :pointer) (n :int64) (w :int64) (x-shared :int) (sigma-shared :int))
 (cffi:defcfun ("mfit_model_builtin" %model-builtin) :int
   (ctx :pointer) (d :int) (family :int) (degree :int) (param-index :pointer) (n-idx :int))
 (cffi:defcfun ("mfit_model_sexpr" %model-sexpr) :int
@@ -257,6 +259,30 @@ lists in :params order) gives each chain its own start; SEED keys the Philox str
       (chk ctx (%chains-init ctx t0 w seed 0 trace-capacity)))
     (make-gpu-walker :ctx ctx :function function :param-keys keys :n-walkers w :n-params p :data data
                      :data-error data-error :log-liklihood ll :log-prior lp)))
+
+(defun walker-set-create (&key function x ys params data-error log-liklihood log-prior (seed 0) (device 0) (trace-capacity 0))
+  "A walker set with per-walker data -- what file->nv-walkers builds (nv-specific.lisp:50-66): one walker per y list in
+YS, all over the common X, same :function / :log-liklihood / :log-prior, every walker starting at PARAMS.  DATA-ERROR is
+a number or one list as long as X.  The walkers advance together on the GPU, one warp each."
+  (let* ((keys (plist-keys params)) (p (length keys)) (w (length ys)) (n (length x))
+         (sigma (if (listp data-error) data-error (make-list n :initial-element (or data-error 1))))
+         ctx)
+    (cffi:with-foreign-object (out :pointer)
+      (let ((rc (with-traps-masked (%ctx-create device (cffi:null-pointer) out))))
+        (unless (zerop rc) (error 'mfit-error :code rc :message (%last-error (cffi:null-pointer)))))
+      (setf ctx (cffi:mem-ref out :pointer)))
+    (chk ctx (%problem-define ctx 1 p))
+    (with-doubles (xp x)
+      (with-doubles (yp (apply #'append ys))                 ; W x n row-major
+        (with-doubles (sp sigma)
+          (chk ctx (%dataset-upload-per-walker ctx 0 xp yp sp n w 1 1)))))
+    (set-function ctx 0 function keys)
+    (chk ctx (%likelihood-set ctx 0 (likelihood-kind log-liklihood)))
+    (set-prior ctx 0 log-prior keys)
+    (with-doubles (t0 (loop repeat w append (plist-values params)))
+      (chk ctx (%chains-init ctx t0 w seed 0 trace-capacity)))
+    (make-gpu-walker :ctx ctx :function (list function) :param-keys keys :n-walkers w :n-params p
+                     :data (list x ys) :data-error sigma :log-liklihood (list log-liklihood) :log-prior (list log-prior))))
 
 (defun walker-free (walker)
   (when (gpu-walker-ctx walker) (%ctx-destroy (gpu-walker-ctx walker)) (setf (gpu-walker-ctx walker) nil)))
