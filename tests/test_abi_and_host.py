@@ -140,3 +140,38 @@ def test_family_texts_parse_and_lower():
         keys = families.slots(name, deg)
         code = _lib.lower_sexpr(families.lisp_text(name, deg), keys)
         assert "struct MfitUser" in code and "eval(double x, G& gd)" in code
+
+
+def test_cl_reader_numbers_and_file_reader():
+    """the Common Lisp reader quirk the input side must reproduce: `2.003E+3` is a single-float, `2.003d3` a double,
+    integers and ratios are exact; read-file->data / file->file-specs / create-walker-data on a TSV with a header line
+    and CRLF line ends (an excerpt of the reference's example-data.xls)"""
+    from lisp_mcmc_b200 import io as mio
+    assert mio.cl_read_number("2.003E+3") == 2003.0
+    assert mio.cl_read_number("-4.172E-7") == float(np.float32(-4.172e-7)) != -4.172e-7
+    assert mio.cl_read_number("-4.172d-7") == -4.172e-7
+    assert mio.cl_read_number("1e0") == 1.0 and mio.cl_read_number("7") == 7.0 and mio.cl_read_number("3/4") == 0.75
+    assert mio.cl_read_number("0.1") == float(np.float32(0.1)) and mio.cl_read_number("0.1d0") == 0.1
+    assert mio.cl_read_number("Probe") is None and mio.cl_read_number("") is None
+    path = os.path.join(ROOT, "tests", "golden", "example_data_excerpt.tsv")
+    specs = mio.file_specs(path)
+    assert specs["header-lines"] == 1 and specs["data-length"] == 9 and specs["data-rows"] == 6 and specs["num-pages"] == 1
+    data = mio.read_file_to_data(path)
+    assert len(data) == 9 and all(len(c) == 6 for c in data)
+    assert data[0][0] == 2000.0 and data[0][1] == 2003.0
+    assert data[2][0] == float(np.float32(-4.172e-7))
+    x, y = mio.create_walker_data(data, 0, 3)
+    assert np.array_equal(x, data[0]) and np.array_equal(y, data[3])
+    rows = mio.read_file_to_data(path, transpose=False)
+    assert len(rows) == 6 and len(rows[0]) == 9 and rows[1][0] == 2003.0
+
+
+def test_file_reader_pages(tmp_path):
+    """pages = blocks of data rows separated by an empty line (read-file->data :pages, :1443-1450)"""
+    from lisp_mcmc_b200 import io as mio
+    p = tmp_path / "pages.csv"
+    p.write_text("x;y\n1;1.5\n2;2.5\n3;3.5\n\n4;4.5\n5;5.5\n6;6.5\n")
+    specs = mio.file_specs(str(p), delim=";")
+    assert specs["header-lines"] == 1 and specs["data-rows"] == 3 and specs["num-pages"] == 2
+    pages = mio.read_file_to_data(str(p), delim=";", pages=True)
+    assert len(pages) == 2 and np.array_equal(pages[1][0], [4.0, 5.0, 6.0]) and np.array_equal(pages[0][1], [1.5, 2.5, 3.5])
