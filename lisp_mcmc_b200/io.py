@@ -18,7 +18,10 @@ _FLOAT = re.compile(r"^[+-]?(\d+\.?\d*|\.\d+)(([eEsSfFdDlL])([+-]?\d+))?$")
 def cl_read_number(token):
     """What (read-from-string token) yields, already passed through to-double-floats: float64, or None for a token that
     does not read as a number (a symbol, a string, NIL)."""
-    t = token.strip()
+    # read-from-string returns the FIRST object: the token ends at whitespace or a terminating macro character
+    # (`;` starts a comment, so "1;1.5" reads as 1 -- which is how file->file-specs recognises data lines of files
+    # that are not tab-separated)
+    t = re.split(r"[\s;()\"'`,]", token.strip(), maxsplit=1)[0]
     if not t:
         return None
     if _INT.match(t):
