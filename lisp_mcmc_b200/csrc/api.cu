@@ -293,16 +293,9 @@ int check_problem_ready(mfit_ctx* ctx) {
   return 0;
 }
 
-int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const double* theta, const unsigned char* skip,
-                int group = 0, int cb0 = 0, int n_cb = -1, cudaStream_t st = nullptr) {
-  if (!st) st = ctx->stream;
-  if (s.n == 0 || s.n_seg == 0) return 0;
-  if (!ctx->sched_dev) {
-    CU(cudaMalloc(&ctx->sched_dev, 4 * sizeof(int)));
-    CU(cudaMemsetAsync(ctx->sched_dev, 0, 4 * sizeof(int), ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-  }
-  MfitEvalArgs a;
+// the arguments one data set contributes to a likelihood launch
+void fill_eval_args(MfitEvalArgs& a, const Dataset& s, const Workspace& w, int d, const double* theta, const unsigned char* skip,
+                    int cb0, int n_cb) {
   memset(&a, 0, sizeof a);
   a.x = s.x; a.y = s.y; a.yw = s.yw; a.w = s.w; a.c = s.c;
   a.n = s.n;
@@ -317,42 +310,78 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
   a.theta = theta;
   a.skip = skip;
   a.partial = w.partial[d];
-  a.sched = ctx->sched_dev + 2 * group;
   for (int k = 0; k < MFIT_MAXK; k++) a.idx[k] = s.idx[k];
   a.degree = s.degree;
-  if (s.W_pc > 0) {  // walker set with per-walker data: one warp per chain, no staging, no work-item queue
-    a.x_stride = s.x_shared ? 0 : s.n_pad;
-    a.pc_stride = s.n_pad;
-    a.w_stride = s.sigma_shared ? 0 : s.n_pad;
-    const void* fpc = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_pc[s.ll_kind]
-                                                : mfit_builtin_perchain_kernel(s.family, s.degree, s.ll_kind);
-    if (!fpc) return fail(ctx, MFIT_ERR_STATE, "no per-walker kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
-    auto itp = ctx->resident.find(fpc);
-    if (itp == ctx->resident.end()) {
-      int per_sm = 0, sms = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc, MFIT_PC_THREADS, 0));
-      CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-      if (per_sm < 1) per_sm = 1;
-      itp = ctx->resident.emplace(fpc, per_sm * sms).first;
-    }
-    const long long chains = (long long)a.n_cb * MFIT_CB;
-    const long long need = (chains + MFIT_PC_THREADS / 32 - 1) / (MFIT_PC_THREADS / 32);
-    const unsigned gridp = (unsigned)(need < itp->second ? need : itp->second);
-    void* argsp[] = {&a};
-    CU(cudaLaunchKernel(fpc, dim3(gridp > 0 ? gridp : 1), dim3(MFIT_PC_THREADS), argsp, 0, st));
-    ctx->launches++;
-    return 0;
+}
+
+int ensure_sched(mfit_ctx* ctx) {
+  if (!ctx->sched_dev) {
+    CU(cudaMalloc(&ctx->sched_dev, 4 * sizeof(int)));
+    CU(cudaMemsetAsync(ctx->sched_dev, 0, 4 * sizeof(int), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
   }
-  const void* fn = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user[s.ll_kind]
-                                              : mfit_builtin_eval_kernel(s.family, s.degree, s.ll_kind);
-  if (!fn) return fail(ctx, MFIT_ERR_STATE, "no kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
+  return 0;
+}
+
+// walker set with per-walker data: one warp per chain, no staging, no work-item queue
+int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const double* theta, const unsigned char* skip,
+                           int cb0, int n_cb, cudaStream_t st) {
+  MfitEvalArgs a;
+  fill_eval_args(a, s, w, d, theta, skip, cb0, n_cb);
+  a.x_stride = s.x_shared ? 0 : s.n_pad;
+  a.pc_stride = s.n_pad;
+  a.w_stride = s.sigma_shared ? 0 : s.n_pad;
+  const void* fpc = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_pc[s.ll_kind]
+                                              : mfit_builtin_perchain_kernel(s.family, s.degree, s.ll_kind);
+  if (!fpc) return fail(ctx, MFIT_ERR_STATE, "no per-walker kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
+  auto itp = ctx->resident.find(fpc);
+  if (itp == ctx->resident.end()) {
+    int per_sm = 0, sms = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc, MFIT_PC_THREADS, 0));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (per_sm < 1) per_sm = 1;
+    itp = ctx->resident.emplace(fpc, per_sm * sms).first;
+  }
+  const long long chains = (long long)a.n_cb * MFIT_CB;
+  const long long need = (chains + MFIT_PC_THREADS / 32 - 1) / (MFIT_PC_THREADS / 32);
+  const unsigned gridp = (unsigned)(need < itp->second ? need : itp->second);
+  void* argsp[] = {&a};
+  CU(cudaLaunchKernel(fpc, dim3(gridp > 0 ? gridp : 1), dim3(MFIT_PC_THREADS), argsp, 0, st));
+  ctx->launches++;
+  return 0;
+}
+
+const void* shared_data_kernel(const Dataset& s) {
+  return s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user[s.ll_kind] : mfit_builtin_eval_kernel(s.family, s.degree, s.ll_kind);
+}
+
+// One launch for the data sets ds[0..n) (same kernel = same model family / lowered lambda and likelihood kind): their
+// work items share one queue.
+int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, const double* theta, const unsigned char* skip,
+                      int group, int cb0, int n_cb, cudaStream_t st) {
+  int rc = ensure_sched(ctx);
+  if (rc) return rc;
+  MfitMultiArgs ma;
+  memset(&ma, 0, sizeof ma);
+  ma.n_ds = n;
+  ma.sched = ctx->sched_dev + 2 * group;
+  long long items = 0;
+  for (int k = 0; k < n; k++) {
+    fill_eval_args(ma.d[k], ctx->ds[ds[k]], w, ds[k], theta, skip, cb0, n_cb);
+    ma.item_start[k] = (int)items;
+    items += (long long)ma.d[k].n_cb * ma.d[k].n_seg;
+    if (items > 2000000000LL) return fail(ctx, MFIT_ERR_ARG, "too many work items in one launch (%lld)", items);
+  }
+  ma.item_start[n] = (int)items;
+  if (items == 0) return 0;
+  Dataset& s = ctx->ds[ds[0]];
+  const void* fn = shared_data_kernel(s);
+  if (!fn) return fail(ctx, MFIT_ERR_STATE, "no kernel for dataset %d (family %d degree %d)", ds[0], s.family, s.degree);
   const size_t smem = mfit_eval_smem_bytes(s.ll_kind);
   auto it = ctx->resident.find(fn);
   if (it == ctx->resident.end()) {  // persistent grid = CTAs resident at once (occupancy x SMs), queried once per kernel
     // static (math tables) + dynamic (TMA ring) shared memory may exceed the 48 KB default together
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // without this the driver's carve-out heuristic leaves room for 3 CTAs per SM only (ncu: 11.8 resident warps
-    // instead of 16), and the persistent grid sized for 4 runs its last quarter as a second wave
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MFIT_THREADS, smem));
@@ -360,9 +389,7 @@ int launch_eval(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d, const doub
     if (per_sm < 1) per_sm = 1;
     it = ctx->resident.emplace(fn, per_sm * sms).first;
   }
-  void* args[] = {&a};
-  const long long items = (long long)a.n_cb * a.n_seg;
-  if (items > 2000000000LL) return fail(ctx, MFIT_ERR_ARG, "dataset %d: too many work items (%lld chain-blocks x %d segments)", d, (long long)a.n_cb, a.n_seg);
+  void* args[] = {&ma};
   const unsigned grid = (unsigned)(items < it->second ? items : it->second);
   CU(cudaLaunchKernel(fn, dim3(grid), dim3(MFIT_THREADS), args, smem, st));
   ctx->launches++;
@@ -376,12 +403,30 @@ int eval_all(mfit_ctx* ctx, Workspace& w, const MfitChains& view, const double* 
   const bool timed = ctx->timing && ctx->ev_used < ctx->ev.size();
   if (timed) CU(cudaEventRecord(ctx->ev[ctx->ev_used].a, st));
   int n_eval = 0;
-  for (int d = 0; d < ctx->D; d++) {
+  for (int d = 0; d < ctx->D;) {
     Dataset& s = ctx->ds[d];
-    if (!s.owned) continue;
-    int rc = launch_eval(ctx, s, w, d, theta, skip, group, cb0, n_cb, st);
+    if (!s.owned || s.n == 0 || s.n_seg == 0) { d++; continue; }
+    if (s.W_pc > 0) {
+      int rc = launch_eval_per_walker(ctx, s, w, d, theta, skip, cb0, n_cb, st);
+      if (rc) return rc;
+      n_eval++;
+      d++;
+      continue;
+    }
+    // batch the following data sets that run the same kernel (global fits: the same family on every data set)
+    int batch[MFIT_MAX_FUSED], nb = 0;
+    const void* fn = shared_data_kernel(s);
+    int e = d;
+    for (; e < ctx->D && nb < MFIT_MAX_FUSED; e++) {
+      Dataset& t = ctx->ds[e];
+      if (!t.owned || t.n == 0 || t.n_seg == 0) continue;
+      if (t.W_pc > 0 || shared_data_kernel(t) != fn) break;
+      batch[nb++] = e;
+    }
+    int rc = launch_eval_fused(ctx, batch, nb, w, theta, skip, group, cb0, n_cb, st);
     if (rc) return rc;
-    if (s.n > 0) n_eval++;
+    n_eval++;
+    d = e;
   }
   if (timed) {
     CU(cudaEventRecord(ctx->ev[ctx->ev_used].b, st));

@@ -5,7 +5,7 @@
 #include "mfit_internal.h"
 
 template <class Model, int LL>
-__global__ void __launch_bounds__(MFIT_THREADS, MFIT_MIN_CTAS) mfit_eval_kernel(const __grid_constant__ MfitEvalArgs a) {
+__global__ void __launch_bounds__(MFIT_THREADS, MFIT_MIN_CTAS) mfit_eval_kernel(const __grid_constant__ MfitMultiArgs a) {
   mfit_eval_body<Model, LL>(a);
 }
 

@@ -66,12 +66,22 @@ struct MfitEvalArgs {
   const double* theta;  /* [P][stride] parameter vectors to evaluate */
   const unsigned char* skip; /* [stride] 1 = chain finished, nothing to do (may be null) */
   double* partial;      /* [n_seg][stride] per-segment sums */
-  int* sched;           /* [2] zero between launches: next item to hand out, CTAs that have finished */
   /* walker sets with per-walker data (mfit_eval_perchain_body): chain w reads x + w * x_stride (0: one x for all),
    * y / yw + w * pc_stride, w / c + w * w_stride; chains [cb0 * MFIT_CB, (cb0 + n_cb) * MFIT_CB) of this launch */
   long long x_stride, pc_stride, w_stride;  /* w_stride: rows of w / c (0: one sigma vector for all chains) */
   int idx[MFIT_MAXK];   /* built-in families: family slot -> shared parameter index */
   int degree;
+};
+
+// One launch of the shared-data kernel evaluates up to MFIT_MAX_FUSED data sets that use the same model family and
+// likelihood kind (the data sets of a global fit usually do): their work items share one queue, so a global fit costs
+// one launch per step instead of one per data set and its last CTAs wait for the tail of one queue, not of eight.
+#define MFIT_MAX_FUSED 8
+struct MfitMultiArgs {
+  int n_ds;
+  int item_start[MFIT_MAX_FUSED + 1]; /* items [item_start[k], item_start[k+1]) belong to d[k]; chain-block fastest inside */
+  int* sched;                         /* [2] zero between launches: next item to hand out, CTAs that have finished */
+  MfitEvalArgs d[MFIT_MAX_FUSED];
 };
 
 // ---------------------------------------------------------------- PTX helpers (mbarrier + TMA bulk copy)
@@ -228,8 +238,10 @@ __device__ __forceinline__ void mfit_tile(const Model* m, bool unguarded, const 
 // MFIT_STAGES tiles in flight across item boundaries and publishes item ids through a small ring in shared memory
 // (the warps of a CTA are coupled by the mbarriers of the tile ring only, never by a CTA-wide barrier);
 // the parameters of the next item are loaded into registers one item ahead.
-template <class Model, int LL>
-__device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
+// MULTI = false: one data set, whose arguments are then compile-time-addressed kernel parameters (constant-bank
+// operands); with MULTI the per-item data set index makes them indexed loads, which costs the one-data-set case 5 %.
+template <class Model, int LL, bool MULTI>
+__device__ __forceinline__ void mfit_eval_body_t(const MfitMultiArgs& ma) {
   constexpr int NARR = MfitTerm<LL>::NARR;
   constexpr unsigned STAGE_BYTES = NARR * MFIT_TILE * 8u;
   extern __shared__ __align__(128) unsigned char mfit_smem[];
@@ -239,9 +251,17 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   volatile int* q_items = reinterpret_cast<volatile int*>(empty + MFIT_STAGES);
 
   const int tid = threadIdx.x;
-  const int total = a.n_cb * a.n_seg;
-  const long long n_tiles = (a.n + MFIT_TILE - 1) / MFIT_TILE;
-  auto tiles_of = [&](int seg) -> int {
+  const int total = ma.item_start[ma.n_ds];
+  // item id -> data set and its (segment, chain-block) item
+  auto ds_of = [&](int item) -> int {
+    if (!MULTI) return 0;
+    int k = 0;
+    while (k + 1 < ma.n_ds && item >= ma.item_start[k + 1]) k++;
+    return k;
+  };
+  auto start_of = [&](int k) -> int { return MULTI ? ma.item_start[k] : 0; };
+  auto tiles_of = [&](const MfitEvalArgs& a, int seg) -> int {
+    const long long n_tiles = (a.n + MFIT_TILE - 1) / MFIT_TILE;
     long long t0 = (long long)seg * a.tiles_per_seg, t1 = t0 + a.tiles_per_seg;
     if (t1 > n_tiles) t1 = n_tiles;
     return (int)(t1 - t0);
@@ -257,17 +277,20 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   }
 
   // producer cursor (thread 0 only): next tile to request = tile p_k of item p_item; `issued` counts requests
-  int p_item = 0, p_k = 0, p_nt = 0, p_seq = 0;
+  int p_item = 0, p_k = 0, p_nt = 0, p_seq = 0, p_ds = 0, p_seg = 0;
   bool p_done = false;
   unsigned issued = 0;
   auto fetch_item = [&]() {
-    p_item = atomicAdd(a.sched, 1);
+    p_item = atomicAdd(ma.sched, 1);
     if (p_item >= total) {
       p_item = -1;
       p_done = true;
     } else {
+      p_ds = ds_of(p_item);
+      const MfitEvalArgs& a = ma.d[MULTI ? p_ds : 0];
+      p_seg = (p_item - start_of(p_ds)) / a.n_cb;
       p_k = 0;
-      p_nt = tiles_of(p_item / a.n_cb);
+      p_nt = tiles_of(a, p_seg);
     }
     q_items[(p_seq + 1) % MFIT_QN] = -2;  // "not drawn yet": a reader running ahead must never see a stale id
     __threadfence_block();
@@ -275,9 +298,9 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
     p_seq++;
   };
   auto issue_next = [&]() {
-    const int seg = p_item / a.n_cb;
+    const MfitEvalArgs& a = ma.d[MULTI ? p_ds : 0];
     const int s = (int)(issued % MFIT_STAGES);
-    const long long off = ((long long)seg * a.tiles_per_seg + p_k) * (long long)MFIT_TILE;
+    const long long off = ((long long)p_seg * a.tiles_per_seg + p_k) * (long long)MFIT_TILE;
     double* dst = buf + (size_t)s * NARR * MFIT_TILE;
     mfit_mbar_expect_tx(&full[s], STAGE_BYTES);
     mfit_tma_load_1d(dst, a.x + off, MFIT_TILE * 8u, &full[s]);
@@ -294,13 +317,14 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   }
   __syncthreads();  // q_items[0] published
 
-  auto clamp_chain = [&](long long ch) -> long long { return ch < a.W ? ch : (long long)a.W - 1; };
-
   Model m_next[2];
   auto load_params = [&](int it) {
-    const long long c0 = (long long)(a.cb0 + it % a.n_cb) * MFIT_CB + tid;
-    m_next[0].load(a, clamp_chain(c0));
-    m_next[1].load(a, clamp_chain(c0 + MFIT_THREADS));
+    const int k = ds_of(it);
+    const MfitEvalArgs& a = ma.d[MULTI ? k : 0];
+    const long long c0 = (long long)(a.cb0 + (it - start_of(k)) % a.n_cb) * MFIT_CB + tid;
+    const long long last = (long long)a.W - 1;
+    m_next[0].load(a, c0 < a.W ? c0 : last);
+    m_next[1].load(a, c0 + MFIT_THREADS < a.W ? c0 + MFIT_THREADS : last);
   };
   bool have_params = false;
   unsigned consumed = 0;
@@ -310,13 +334,16 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
     int item;
     do { item = q_items[seq % MFIT_QN]; } while (item == -2);
     if (item < 0) break;
-    const int seg = item / a.n_cb;
-    const long long cb0 = (long long)(a.cb0 + item % a.n_cb) * MFIT_CB;
+    const int ds = ds_of(item);
+    const MfitEvalArgs& a = ma.d[MULTI ? ds : 0];
+    const int local = item - start_of(ds);
+    const int seg = local / a.n_cb;
+    const long long cb0 = (long long)(a.cb0 + local % a.n_cb) * MFIT_CB;
     const long long chain[2] = {cb0 + tid, cb0 + MFIT_THREADS + tid};
     bool live[2];
 #pragma unroll
     for (int c = 0; c < 2; c++) {
-      const long long cl = clamp_chain(chain[c]);
+      const long long cl = chain[c] < a.W ? chain[c] : (long long)a.W - 1;
       live[c] = chain[c] < a.W && !(a.skip != nullptr && a.skip[cl] != 0);
     }
     const bool any_live = __any_sync(0xffffffffu, (live[0] || live[1]) ? 1 : 0) != 0;  // a finished warp only drains its tiles
@@ -334,7 +361,7 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
     // warp-uniform: every chain of this warp stays inside the fast domain over the whole x range of the data set
     const bool unguarded =
         MfitTerm<LL>::USES == 0 && __all_sync(0xffffffffu, (m[0].safe(a) && (!two || m[1].safe(a))) ? 1 : 0) != 0;
-    const int nt = tiles_of(seg);
+    const int nt = tiles_of(a, seg);
     const long long t0 = (long long)seg * a.tiles_per_seg;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int k = 0; k < nt; k++, consumed++) {
@@ -366,12 +393,18 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
   // the last CTA out re-arms the scheduler for the next launch on this stream
   if (tid == 0) {
     __threadfence();
-    if (atomicAdd(a.sched + 1, 1) == (int)gridDim.x - 1) {
-      a.sched[0] = 0;
-      a.sched[1] = 0;
+    if (atomicAdd(ma.sched + 1, 1) == (int)gridDim.x - 1) {
+      ma.sched[0] = 0;
+      ma.sched[1] = 0;
       __threadfence();
     }
   }
+}
+
+template <class Model, int LL>
+__device__ __forceinline__ void mfit_eval_body(const MfitMultiArgs& ma) {
+  if (ma.n_ds == 1) mfit_eval_body_t<Model, LL, false>(ma);
+  else mfit_eval_body_t<Model, LL, true>(ma);
 }
 
 // ---------------------------------------------------------------- walker sets with per-walker data
@@ -382,7 +415,10 @@ __device__ __forceinline__ void mfit_eval_body(const MfitEvalArgs& a) {
 // warp-uniform, four independent accumulators per lane, and the 128 partial sums are combined in a fixed order
 // (accumulators, then a shuffle tree).  This kernel is bound by L2 / HBM bandwidth (24 bytes per point-eval), not
 // by the FP64 pipe.  Persistent warps stride over the chains of the launch.
-#define MFIT_PC_U 8 /* strides of 32 points whose loads are issued together (memory-level parallelism per warp) */
+#ifndef MFIT_PC_U
+#define MFIT_PC_U 8
+#endif
+// /* strides of 32 points whose loads are issued together (memory-level parallelism per warp) */
 template <class Model, int LL, bool SLOW, class G>
 __device__ __forceinline__ double mfit_perchain_pass(const Model& m, const double* xs, const double* ys, const double* ws,
                                                      const double* cs, long long n, int lane, G& gd) {

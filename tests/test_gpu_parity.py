@@ -597,3 +597,20 @@ def test_walker_set_with_per_walker_data_matches_oracle(orc, name, ll, shared_x)
         same = np.all(th_g[k, :nv[k]] == oth, axis=1)
         assert same[::-1].cumprod().sum() > 0.9 * len(opr)   # bit-identical until, at most, a borderline decision
     w.close()
+
+
+def test_walker_save_and_load_round_trip(tmp_path):
+    """walker-save / walker-load (:971-1001, dead code in the reference, revived): an s-expression header in the layout
+    of the reference's dump followed by the FP64 trace, newest step first"""
+    from lisp_mcmc_b200 import walker_load, walker_save
+    cfg = workloads.c2(W=5, N=200)
+    w = workloads.make_walker(cfg, seed=8)
+    w.adaptive_steps_full(n=300, temperature=10)
+    path = walker_save(w, str(tmp_path / "walk.mfit"))
+    th, pr, nv = w.trace(int(w.stats()["length"].max()))
+    got = walker_load(path)
+    assert got["param_keys"] == cfg["keys"] and got["header"].startswith("(:mfit-walker 1 :fn (")
+    assert np.array_equal(got["n_valid"], nv)
+    assert np.array_equal(got["theta"], th, equal_nan=True) and np.array_equal(got["prob"], pr, equal_nan=True)
+    assert ":log-liklihood (\"log-liklihood-normal\")" in got["header"] and ":n-walkers 5" in got["header"]
+    w.close()
