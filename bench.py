@@ -142,10 +142,14 @@ def main():
         raise SystemExit("--gpus %d but WORLD_SIZE %d" % (args.gpus, world))
 
     from lisp_mcmc_b200 import workloads
-    cfg_fn = workloads.CONFIGS[args.config]
+    walker_set = args.config == "NVSET"     # walker set with per-walker data: an HBM-bound kernel
+    cfg_fn = workloads.nvset if walker_set else workloads.CONFIGS[args.config]
     base = cfg_fn()
     W_per_gpu = base["theta0"].shape[0]
-    N = sum(len(d[0]) for d in base["data"])
+    N = base["data"][1].shape[1] if walker_set else sum(len(d[0]) for d in base["data"])
+    make = workloads.make_walker_set if walker_set else workloads.make_walker
+    if walker_set and (args.impl == "reference" or args.gpus > 1):
+        raise SystemExit("--config NVSET is a one-GPU kernel bench (no CPU arm)")
     config = {"workload": "%s: %s" % (args.config, cfg_fn.__doc__.strip().split("\n")[0]), "points": N,
               "chains_per_gpu": W_per_gpu, "params": len(base["keys"]), "driver": "walker-adaptive-steps-full n=30000 "
               "temperature=10 auto=nil", "l2": "likelihood inputs (2.4 MB) are L2/SMEM-resident by design; chain state "
@@ -193,8 +197,9 @@ def main():
     tstream = torch.cuda.Stream()          # a real (non-default) stream shared by torch's events and the library
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-    w = workloads.make_walker(base, theta0=theta0, seed=2024, device=local_rank, chain_id_base=lo,
-                              trace_capacity=Wm + K + 1200, stream=C.c_void_p(stream))
+    kw0 = {} if walker_set else {"theta0": theta0}
+    w = make(base, seed=2024, device=local_rank, chain_id_base=lo, trace_capacity=Wm + K + 1200,
+             stream=C.c_void_p(stream), **kw0)
     h = w._h
     dfma, c_exp, c_log, c_sin, c_div = (C.c_double() for _ in range(5))
     w._chk(L.mfit_measure_fp64(h, C.byref(dfma), C.byref(c_exp), C.byref(c_log), C.byref(c_sin), C.byref(c_div)))
@@ -233,8 +238,8 @@ def main():
 
     # ---------------------------------------------------------------- e2e through the public API, host buffers
     def e2e_pass(steps, seed):
-        w2 = workloads.make_walker(base, theta0=theta0, seed=seed, device=local_rank, chain_id_base=lo,
-                                   trace_capacity=steps + 1100, stream=C.c_void_p(stream))
+        w2 = make(base, seed=seed, device=local_rank, chain_id_base=lo, trace_capacity=steps + 1100,
+                  stream=C.c_void_p(stream), **kw0)
         w2._chk(L.mfit_run_begin(w2._h, C.byref(cfgc), None, None, None, 0))
         w2._chk(L.mfit_run_advance(w2._h, steps, C.byref(done), C.byref(fin)))
         out = w2.trace(steps + 1)
@@ -250,7 +255,7 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0)
     w2.close()
-    h2d = sum(3 * 8 * len(d[0]) for d in base["data"]) + theta0.nbytes
+    h2d = (base["data"][1].nbytes + 2 * 8 * N if walker_set else sum(3 * 8 * len(d[0]) for d in base["data"])) + theta0.nbytes
     d2h = th.nbytes + pr.nbytes + nv.nbytes
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -291,7 +296,20 @@ def main():
                              "hbm": {"achieved": alg_bytes / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": alg_bytes / per_launch_s / 1e9 / hbm_peak, "peak_source": hbm_src}},
                 "mean_accept_200": acc}
-        if not args.no_cpu and world == 1:
+        if walker_set:   # bound by HBM, not by the FP64 pipe: report that roofline as the primary one
+            r = line["roofline"]
+            by = float(base["bytes_per_point"]) * evals
+            r["fp64"] = {k: r[k] for k in ("achieved", "peak", "frac", "unit")}
+            r.update({"bound": "hbm", "achieved": by / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": by / per_launch_s / 1e9 / hbm_peak, "traffic": 549064960,
+                      "what": "algorithmic bytes (%g per point-eval: y/sigma; x and 1/sigma are shared vectors) / kernel time, "
+                              "against the measured copy bandwidth (%s)" % (base["bytes_per_point"], hbm_src)})
+            r["kernel"] = "mfit_eval_perchain_kernel"
+            r["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (%s)" % hbm_src
+            r.pop("hbm", None)
+            r.pop("survey_8d", None)
+            line["config"]["l2"] = "524 MB of per-walker data per pass (> 126 MB L2): streamed from HBM every step"
+        if not args.no_cpu and world == 1 and not walker_set:
             threads = os.cpu_count() or 1
             r = cpu_reference_run(base, min(K, 50), 2, threads, budget_s=args.cpu_budget)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"]}

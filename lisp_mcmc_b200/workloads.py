@@ -113,7 +113,7 @@ def nvset(W=131072, N=500):
     Y = f + 1e-7 * rng.standard_normal((W, N))
     return dict(name="NVSET", function=[builtin("nv_multi", keys, degree=2)], data=(x, Y), data_error=1e-7, keys=keys,
                 theta_star=th, theta0=thk * (1.0 + 1e-4 * rng.standard_normal((W, 6))), log_liklihood="log-liklihood-normal",
-                log_prior=families.log_prior_nv_text(), steps=200, fp64_instr_per_point=16, bytes_per_point=8)
+                log_prior=families.log_prior_nv_text(), steps=200, fp64_instr_per_point=16, bytes_per_point=8, flop_per_point=14, transc_per_point={"div": 2})
 
 
 def make_walker_set(cfg, **gpu):
