@@ -53,7 +53,7 @@ struct Dataset {
   long long W_pc = 0;
   bool x_shared = false, sigma_shared = false;
   double *cst_normal_pc = nullptr, *cst_poisson_pc = nullptr;  // [W_pc] device
-  cudaKernel_t k_user_pc[3] = {nullptr, nullptr, nullptr};
+  cudaKernel_t k_user_pc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [kind + 3 * staged]
   int family = -1, degree = 0;
   int idx[MFIT_MAXK];
   int ll_kind = MFIT_LL_NORMAL;
@@ -190,7 +190,7 @@ void dataset_free_prior(Dataset& d) {
 void dataset_free_model(Dataset& d) {
   if (d.lib_model) { cudaLibraryUnload(d.lib_model); d.lib_model = nullptr; }
   d.k_user[0] = d.k_user[1] = d.k_user[2] = nullptr;
-  d.k_user_pc[0] = d.k_user_pc[1] = d.k_user_pc[2] = nullptr;
+  for (auto& k : d.k_user_pc) k = nullptr;
 }
 
 void workspace_free(Workspace& w) {
@@ -331,13 +331,19 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
   a.x_stride = s.x_shared ? 0 : s.n_pad;
   a.pc_stride = s.n_pad;
   a.w_stride = s.sigma_shared ? 0 : s.n_pad;
-  const void* fpc = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_pc[s.ll_kind]
-                                              : mfit_builtin_perchain_kernel(s.family, s.degree, s.ll_kind);
+  // shared x / sigma vectors are staged in shared memory (mfit_eval_perchain_body)
+  const bool staged = a.x_stride == 0 && a.w_stride == 0 && a.n <= MFIT_PC_STAGE_MAX;
+  const size_t smem_pc = staged ? sizeof(double) * 3 * (size_t)((a.n + 31) & ~31LL) : 0;
+  const void* fpc = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_pc[s.ll_kind + (staged ? 3 : 0)]
+                                              : mfit_builtin_perchain_kernel(s.family, s.degree, s.ll_kind, staged);
   if (!fpc) return fail(ctx, MFIT_ERR_STATE, "no per-walker kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
   auto itp = ctx->resident.find(fpc);
   if (itp == ctx->resident.end()) {
+    const size_t smem_max = sizeof(double) * 3 * MFIT_PC_STAGE_MAX;
+    CU(cudaFuncSetAttribute(fpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU(cudaFuncSetAttribute(fpc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0, sms = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc, MFIT_PC_THREADS, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc, MFIT_PC_THREADS, smem_pc));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     if (per_sm < 1) per_sm = 1;
     itp = ctx->resident.emplace(fpc, per_sm * sms).first;
@@ -346,7 +352,7 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
   const long long need = (chains + MFIT_PC_THREADS / 32 - 1) / (MFIT_PC_THREADS / 32);
   const unsigned gridp = (unsigned)(need < itp->second ? need : itp->second);
   void* argsp[] = {&a};
-  CU(cudaLaunchKernel(fpc, dim3(gridp > 0 ? gridp : 1), dim3(MFIT_PC_THREADS), argsp, 0, st));
+  CU(cudaLaunchKernel(fpc, dim3(gridp > 0 ? gridp : 1), dim3(MFIT_PC_THREADS), argsp, smem_pc, st));
   ctx->launches++;
   return 0;
 }
@@ -1004,6 +1010,9 @@ int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* 
   CU(cudaLibraryGetKernel(&s.k_user_pc[0], s.lib_model, "mfit_user_perchain_normal"));
   CU(cudaLibraryGetKernel(&s.k_user_pc[1], s.lib_model, "mfit_user_perchain_cutoff"));
   CU(cudaLibraryGetKernel(&s.k_user_pc[2], s.lib_model, "mfit_user_perchain_poisson"));
+  CU(cudaLibraryGetKernel(&s.k_user_pc[3], s.lib_model, "mfit_user_perchain_staged_normal"));
+  CU(cudaLibraryGetKernel(&s.k_user_pc[4], s.lib_model, "mfit_user_perchain_staged_cutoff"));
+  CU(cudaLibraryGetKernel(&s.k_user_pc[5], s.lib_model, "mfit_user_perchain_staged_poisson"));
   s.family = MFIT_FAM_SEXPR;
   s.degree = 0;
   return 0;

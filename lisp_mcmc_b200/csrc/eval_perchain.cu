@@ -4,28 +4,33 @@
 #include "mfit_models.cuh"
 #include "mfit_internal.h"
 
-template <class Model, int LL>
-__global__ void __launch_bounds__(MFIT_PC_THREADS) mfit_eval_perchain_kernel(const __grid_constant__ MfitEvalArgs a) {
-  mfit_eval_perchain_body<Model, LL>(a);
+template <class Model, int LL, bool STAGED>
+__global__ void __launch_bounds__(MFIT_PC_THREADS, STAGED ? MFIT_PC_STAGED_CTAS : 1) mfit_eval_perchain_kernel(const __grid_constant__ MfitEvalArgs a) {
+  mfit_eval_perchain_body_t<Model, LL, STAGED>(a);
 }
 
-#define MFIT_ROW(M)                                                        \
-  {(const void*)mfit_eval_perchain_kernel<M, MFITK_NORMAL>,               \
-   (const void*)mfit_eval_perchain_kernel<M, MFITK_CUTOFF>,               \
-   (const void*)mfit_eval_perchain_kernel<M, MFITK_POISSON>}
+// [likelihood kind + 3 * staged]
+#define MFIT_ROW(M)                                                               \
+  {(const void*)mfit_eval_perchain_kernel<M, MFITK_NORMAL, false>,               \
+   (const void*)mfit_eval_perchain_kernel<M, MFITK_CUTOFF, false>,               \
+   (const void*)mfit_eval_perchain_kernel<M, MFITK_POISSON, false>,              \
+   (const void*)mfit_eval_perchain_kernel<M, MFITK_NORMAL, true>,                \
+   (const void*)mfit_eval_perchain_kernel<M, MFITK_CUTOFF, true>,                \
+   (const void*)mfit_eval_perchain_kernel<M, MFITK_POISSON, true>}
 
-static const void* const k_poly[][3] = {MFIT_ROW(MfitPoly<0>), MFIT_ROW(MfitPoly<1>), MFIT_ROW(MfitPoly<2>),
+static const void* const k_poly[][6] = {MFIT_ROW(MfitPoly<0>), MFIT_ROW(MfitPoly<1>), MFIT_ROW(MfitPoly<2>),
                                         MFIT_ROW(MfitPoly<3>), MFIT_ROW(MfitPoly<4>), MFIT_ROW(MfitPoly<5>),
                                         MFIT_ROW(MfitPoly<6>), MFIT_ROW(MfitPoly<7>)};
-static const void* const k_expo[3] = MFIT_ROW(MfitExpo);
-static const void* const k_sinus[3] = MFIT_ROW(MfitSinus);
-static const void* const k_lorentz[3] = MFIT_ROW(MfitLorentz);
-static const void* const k_gauss[3] = MFIT_ROW(MfitGaussLin);
-static const void* const k_nv[][3] = {MFIT_ROW(MfitNvMulti<1>), MFIT_ROW(MfitNvMulti<2>), MFIT_ROW(MfitNvMulti<3>),
+static const void* const k_expo[6] = MFIT_ROW(MfitExpo);
+static const void* const k_sinus[6] = MFIT_ROW(MfitSinus);
+static const void* const k_lorentz[6] = MFIT_ROW(MfitLorentz);
+static const void* const k_gauss[6] = MFIT_ROW(MfitGaussLin);
+static const void* const k_nv[][6] = {MFIT_ROW(MfitNvMulti<1>), MFIT_ROW(MfitNvMulti<2>), MFIT_ROW(MfitNvMulti<3>),
                                       MFIT_ROW(MfitNvMulti<4>)};
 
-const void* mfit_builtin_perchain_kernel(int family, int degree, int ll) {
+const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int staged) {
   if (ll < 0 || ll > 2) return nullptr;
+  ll += staged ? 3 : 0;
   switch (family) {
     case MFIT_FAM_POLY: return (degree >= 0 && degree <= 7) ? k_poly[degree][ll] : nullptr;
     case MFIT_FAM_EXPO: return k_expo[ll];

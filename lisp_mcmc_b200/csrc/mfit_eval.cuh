@@ -416,32 +416,44 @@ __device__ __forceinline__ void mfit_eval_body(const MfitMultiArgs& ma) {
 // (accumulators, then a shuffle tree).  This kernel is bound by L2 / HBM bandwidth (24 bytes per point-eval), not
 // by the FP64 pipe.  Persistent warps stride over the chains of the launch.
 #ifndef MFIT_PC_U
-#define MFIT_PC_U 8
+#define MFIT_PC_U 8 /* strides of 32 points whose loads are issued together (memory-level parallelism per warp) */
 #endif
-// /* strides of 32 points whose loads are issued together (memory-level parallelism per warp) */
-template <class Model, int LL, bool SLOW, class G>
+#ifndef MFIT_PC_STAGED_CTAS
+#define MFIT_PC_STAGED_CTAS 1 /* min CTAs per SM asked of the staged per-walker kernel: bounding it to 3 or 4 (80 / 64 registers, spills) was 20-35 % slower */
+#endif
+#define MFIT_PC_STAGE_MAX 2048 /* points up to which shared x / sigma vectors are staged in shared memory */
+// STAGED: x and 1/sigma (and the cutoff constants) are one vector for all chains and sit in shared memory (xs, ws, cs
+// point there), so only the chain's own y values are streamed.
+template <class Model, int LL, bool SLOW, bool STAGED, class G>
 __device__ __forceinline__ double mfit_perchain_pass(const Model& m, const double* xs, const double* ys, const double* ws,
                                                      const double* cs, long long n, int lane, G& gd) {
   constexpr int NARR = MfitTerm<LL>::NARR;
+  constexpr int U = MFIT_PC_U;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (long long i0 = 0; i0 < n; i0 += 32 * MFIT_PC_U) {
-    // all loads of this block first: a warp issues in order, so loads left inside the arithmetic would each expose a
-    // full memory latency (the kernel ran at 1.9 TB/s that way)
-    double xv[MFIT_PC_U], yv[MFIT_PC_U], wv[MFIT_PC_U], cv[MFIT_PC_U];
+  for (long long i0 = 0; i0 < n; i0 += 32 * U) {
+    // all global loads of this block first: a warp issues in order, so loads left inside the arithmetic would each
+    // expose a full memory latency (the kernel ran at 1.9 TB/s that way)
+    double xv[STAGED ? 1 : U], yv[U], wv[STAGED ? 1 : U], cv[STAGED ? 1 : U];
 #pragma unroll
-    for (int u = 0; u < MFIT_PC_U; u++) {
+    for (int u = 0; u < U; u++) {
       const long long j = i0 + 32 * u + lane;
       const bool in = j < n;
-      xv[u] = in ? xs[j] : 0.0;
       yv[u] = in ? ys[j] : 0.0;
-      wv[u] = (NARR > 2 && in) ? ws[j] : 0.0;
-      cv[u] = (NARR > 3 && in) ? cs[j] : 0.0;
+      if (!STAGED) {
+        xv[u] = in ? xs[j] : 0.0;
+        wv[u] = (NARR > 2 && in) ? ws[j] : 0.0;
+        cv[u] = (NARR > 3 && in) ? cs[j] : 0.0;
+      }
     }
 #pragma unroll
-    for (int u = 0; u < MFIT_PC_U; u++) {
-      if (i0 + 32 * u + lane < n) {
-        const double f = m.template eval<SLOW>(xv[u], gd);
-        acc[u & 3] = MfitTerm<LL>::template add<SLOW>(acc[u & 3], f, yv[u], wv[u], cv[u], gd);
+    for (int u = 0; u < U; u++) {
+      const long long j = i0 + 32 * u + lane;
+      if (j < n) {
+        const double x = STAGED ? xs[j] : xv[u];
+        const double w = STAGED ? (NARR > 2 ? ws[j] : 0.0) : wv[u];
+        const double c = STAGED ? (NARR > 3 ? cs[j] : 0.0) : cv[u];
+        const double f = m.template eval<SLOW>(x, gd);
+        acc[u & 3] = MfitTerm<LL>::template add<SLOW>(acc[u & 3], f, yv[u], w, c, gd);
       }
     }
   }
@@ -451,10 +463,19 @@ __device__ __forceinline__ double mfit_perchain_pass(const Model& m, const doubl
   return sum;  // valid in lane 0
 }
 
-template <class Model, int LL>
-__device__ __forceinline__ void mfit_eval_perchain_body(const MfitEvalArgs& a) {
+template <class Model, int LL, bool STAGED>
+__device__ __forceinline__ void mfit_eval_perchain_body_t(const MfitEvalArgs& a) {
   constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
+  constexpr int NARR = MfitTerm<LL>::NARR;
+  extern __shared__ __align__(16) double mfit_pc_smem[];
   mfit_math_stage(Model::USES | MfitTerm<LL>::USES, threadIdx.x, blockDim.x);
+  const long long n_pad = (a.n + 31) & ~31LL;
+  if (STAGED)
+    for (long long i = threadIdx.x; i < a.n; i += blockDim.x) {
+      mfit_pc_smem[i] = a.x[i];
+      if (NARR > 2) mfit_pc_smem[n_pad + i] = a.w[i];
+      if (NARR > 3) mfit_pc_smem[2 * n_pad + i] = a.c[i];
+    }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -464,27 +485,84 @@ __device__ __forceinline__ void mfit_eval_perchain_body(const MfitEvalArgs& a) {
   long long chain = w_lo + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   Model m_next;
   if (chain < w_hi) m_next.load(a, chain);
+  const double* ybase = LL == MFITK_NORMAL ? a.yw : a.y;
+  double ycur[MFIT_PC_U];  // STAGED: the block of y values about to be evaluated
+  auto prime = [&](long long ch) {
+    const double* yn = ybase + ch * a.pc_stride;
+#pragma unroll
+    for (int u = 0; u < MFIT_PC_U; u++) {
+      const long long j = 32 * u + lane;
+      ycur[u] = (STAGED && ch < w_hi && j < a.n) ? yn[j] : 0.0;
+    }
+  };
+  if (STAGED) prime(chain);
   for (; chain < w_hi; chain += warps) {
     Model m = m_next;
     if (chain + warps < w_hi) m_next.load(a, chain + warps);  // the next chain's parameters, one chain ahead
-    if (a.skip != nullptr && a.skip[chain] != 0) continue;
+    if (a.skip != nullptr && a.skip[chain] != 0) {
+      if (STAGED) prime(chain + warps);
+      continue;
+    }
     m.setup();
-    const double* xs = a.x + chain * a.x_stride;
+    const double* xs = STAGED ? mfit_pc_smem : a.x + chain * a.x_stride;
     const double* ys = (LL == MFITK_NORMAL ? a.yw : a.y) + chain * a.pc_stride;
-    const double* ws = a.w + chain * a.w_stride;
-    const double* cs = a.c + chain * a.w_stride;
+    const double* ws = STAGED ? mfit_pc_smem + n_pad : a.w + chain * a.w_stride;
+    const double* cs = STAGED ? mfit_pc_smem + 2 * n_pad : a.c + chain * a.w_stride;
     double sum;
-    if (!GUARDED) {
+    // theta is warp-uniform here, so is the model's verdict on its arguments
+    const bool unguarded = !GUARDED || (MfitTerm<LL>::USES == 0 && m.safe(a));
+    if (STAGED) {
+      // Software pipeline over 256-point blocks, across chain boundaries: the y values of the NEXT block (of this chain,
+      // or the first block of this warp's next chain) are requested before the current block is evaluated, so a warp
+      // always has a block in flight instead of alternating between waiting for memory and computing.
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      MfitGuard gd;
+      gd.reset();
       MfitNoGuard ng;
-      sum = mfit_perchain_pass<Model, LL, false>(m, xs, ys, ws, cs, a.n, lane, ng);
+      for (long long i0 = 0; i0 < a.n; i0 += 32 * MFIT_PC_U) {
+        double ynext[MFIT_PC_U];
+        {
+          long long nch = chain, ni0 = i0 + 32 * MFIT_PC_U;
+          if (ni0 >= a.n) { nch = chain + warps; ni0 = 0; }
+          const double* yn = ybase + nch * a.pc_stride;
+#pragma unroll
+          for (int u = 0; u < MFIT_PC_U; u++) {
+            const long long j = ni0 + 32 * u + lane;
+            ynext[u] = (nch < w_hi && j < a.n) ? yn[j] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < MFIT_PC_U; u++) {
+          const long long j = i0 + 32 * u + lane;
+          if (j < a.n) {
+            const double w = NARR > 2 ? ws[j] : 0.0, c = NARR > 3 ? cs[j] : 0.0;
+            if (unguarded) acc[u & 3] = MfitTerm<LL>::template add<false>(acc[u & 3], m.template eval<false>(xs[j], ng), ycur[u], w, c, ng);
+            else acc[u & 3] = MfitTerm<LL>::template add<false>(acc[u & 3], m.template eval<false>(xs[j], gd), ycur[u], w, c, gd);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < MFIT_PC_U; u++) ycur[u] = ynext[u];
+      }
+      sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sum = sum + __shfl_down_sync(0xffffffffu, sum, off);
+      if (!unguarded && __any_sync(0xffffffffu, gd.tripped() ? 1 : 0))  // rare: this chain again with libdevice
+        sum = mfit_perchain_pass<Model, LL, true, true>(m, xs, ys, ws, cs, a.n, lane, gd);
+    } else if (unguarded) {
+      MfitNoGuard ng;
+      sum = mfit_perchain_pass<Model, LL, false, false>(m, xs, ys, ws, cs, a.n, lane, ng);
     } else {
       MfitGuard gd;
       gd.reset();
-      sum = mfit_perchain_pass<Model, LL, false>(m, xs, ys, ws, cs, a.n, lane, gd);
-      if (__any_sync(0xffffffffu, gd.tripped() ? 1 : 0)) sum = mfit_perchain_pass<Model, LL, true>(m, xs, ys, ws, cs, a.n, lane, gd);
+      sum = mfit_perchain_pass<Model, LL, false, false>(m, xs, ys, ws, cs, a.n, lane, gd);
+      if (__any_sync(0xffffffffu, gd.tripped() ? 1 : 0))
+        sum = mfit_perchain_pass<Model, LL, true, false>(m, xs, ys, ws, cs, a.n, lane, gd);
     }
     if (lane == 0) a.partial[chain] = sum;  // one segment
   }
 }
+
+// the host picks STAGED (separate kernels, so that the staged one keeps its lower register count):
+// a.x_stride == 0 && a.w_stride == 0 && a.n <= MFIT_PC_STAGE_MAX
 
 #endif  // MFIT_EVAL_CUH

@@ -14,7 +14,7 @@ const void* mfit_builtin_eval_kernel(int family, int degree, int ll);
 int mfit_family_nparams(int family, int degree);
 size_t mfit_eval_smem_bytes(int ll);
 // eval_perchain.cu
-const void* mfit_builtin_perchain_kernel(int family, int degree, int ll);
+const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int staged);
 
 // lower.cpp
 int mfit_lower_to_string(const char* text, const char* const* keys, int n_keys, int kind, std::string& out,
