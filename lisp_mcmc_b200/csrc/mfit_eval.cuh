@@ -419,7 +419,7 @@ __device__ __forceinline__ void mfit_eval_body(const MfitMultiArgs& ma) {
 #define MFIT_PC_U 8 /* strides of 32 points whose loads are issued together (memory-level parallelism per warp) */
 #endif
 #ifndef MFIT_PC_STAGED_CTAS
-#define MFIT_PC_STAGED_CTAS 1 /* min CTAs per SM asked of the staged per-walker kernel: bounding it to 3 or 4 (80 / 64 registers, spills) was 20-35 % slower */
+#define MFIT_PC_STAGED_CTAS 2 /* min CTAs per SM the staged per-walker kernel is register-bounded for (3 or 4: 80 / 64 registers with spills, 20-35 % slower; 1: the compiler takes 200+ registers, one CTA per SM, 60 % slower) */
 #endif
 #define MFIT_PC_STAGE_MAX 2048 /* points up to which shared x / sigma vectors are staged in shared memory */
 // STAGED: x and 1/sigma (and the cutoff constants) are one vector for all chains and sit in shared memory (xs, ws, cs

@@ -72,6 +72,15 @@ def main():
         dt = time.perf_counter() - t0
         print("  50 adaptive MH steps of %d walkers: %.2f ms/step -> %.3g MH steps/s, %.3g point-evals/s"
               % (W, dt / 50 * 1e3, W * 50 / dt, W * N * 50 / dt))
+        for groups in (1, 2):
+            w._chk(L.mfit_set_groups(w._h, groups))
+            w._chk(L.mfit_set_timing(w._h, 1 if groups == 1 else 0))
+            t0 = time.perf_counter()
+            w._chk(L.mfit_run_advance(w._h, 50, C.byref(done), C.byref(fin)))
+            dt = time.perf_counter() - t0
+            L.mfit_eval_kernel_time(w._h, C.byref(ksec), C.byref(kl))
+            print("  groups=%d: %.3f ms/step%s" % (groups, dt / 50 * 1e3,
+                  ", eval kernel %.4f ms per launch inside the run" % (ksec.value / max(kl.value, 1) * 1e3) if groups == 1 else ""))
     w.close()
     if args.e2e:
         K = args.e2e
