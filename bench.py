@@ -133,6 +133,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shard", default="chains", choices=["chains", "datasets"],
+                    help="N > 1: 'chains' = W more chains per GPU, no collective (weak scaling, the default); 'datasets' = a "
+                         "global fit's data sets spread over the ranks, every rank holds all chains, per-step NCCL "
+                         "all-gather of the per-data-set terms (strong scaling; e.g. --config C4 --gpus 8)")
     args = ap.parse_args()
     K, Wm = args.steps, max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -150,7 +154,7 @@ def main():
     make = workloads.make_walker_set if walker_set else workloads.make_walker
     if walker_set and (args.impl == "reference" or args.gpus > 1):
         raise SystemExit("--config NVSET is a one-GPU kernel bench (no CPU arm)")
-    config = {"workload": "%s: %s" % (args.config, cfg_fn.__doc__.strip().split("\n")[0]), "points": N,
+    config = {"workload": "%s: %s" % (args.config, cfg_fn.__doc__.strip().split("\n")[0]), "points": N, "shard": args.shard,
               "chains_per_gpu": W_per_gpu, "params": len(base["keys"]), "driver": "walker-adaptive-steps-full n=30000 "
               "temperature=10 auto=nil", "l2": "likelihood inputs (2.4 MB) are L2/SMEM-resident by design; chain state "
               "+ trace are streamed; an L2 flush (256 MB write) runs between warm-up and the timed steps"}
@@ -190,10 +194,18 @@ def main():
     import ctypes as C
     from lisp_mcmc_b200 import _lib
     L = _lib.lib()
-    W_total = W_per_gpu * world
-    full = cfg_fn(W=W_total) if world > 1 else base
-    lo = rank * W_per_gpu
+    by_dataset = args.shard == "datasets" and world > 1
+    W_total = W_per_gpu if by_dataset else W_per_gpu * world
+    full = cfg_fn(W=W_total) if (world > 1 and not by_dataset) else base
+    lo = 0 if by_dataset else rank * W_per_gpu
     theta0 = np.ascontiguousarray(full["theta0"][lo:lo + W_per_gpu])
+    if by_dataset:
+        from lisp_mcmc_b200 import distributed as Dist
+        owners = Dist.shard_datasets(len(base["function"]), world)
+        # every walker set brings up its own communicator: an ncclUniqueId serves one ncclCommInitRank round only
+        make = lambda cfg_, **kw_: workloads.make_walker(cfg_, nccl=(Dist.broadcast_nccl_unique_id(), rank, world),
+                                                         dataset_owners=owners, **kw_)
+        n_owned = sum(len(d[0]) for d, o in zip(base["data"], owners) if o == rank)
     tstream = torch.cuda.Stream()          # a real (non-default) stream shared by torch's events and the library
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
@@ -267,15 +279,15 @@ def main():
         e2e_value = W_total * K * N / (e2e_ms_max * 1e-3)
         fpp = flops_per_point(base, costs)
         per_launch_s = ksec.value / max(klaunch.value, 1)
-        evals = W_per_gpu * N * Kk / max(klaunch.value, 1)   # point-evals per likelihood-kernel launch (one launch per data set)
+        evals = W_per_gpu * (n_owned if by_dataset else N) * Kk / max(klaunch.value, 1)   # point-evals per likelihood-kernel launch
         instr = float(base["fp64_instr_per_point"])
         achieved_tf = evals * instr * 2.0 / per_launch_s / 1e12
         survey_tf = evals * fpp / per_launch_s / 1e12
         hbm_peak, hbm_src = load_peaks()
         alg_bytes = 24.0 * N + 8.0 * (len(base["keys"]) + 1) * W_per_gpu   # one data pass + one theta/partial row per chain
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": config,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong" if by_dataset else "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "mh_steps_per_sec": W_total * K / (ms_max * 1e-3),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
