@@ -31,7 +31,8 @@
 
 // Device memory comes from the device's stream-ordered pool (cudaMallocAsync on the context's stream, release
 // threshold raised so that freed blocks stay cached): walker-create / trace reads allocate and free hundreds of MB per
-// call, which costs tens of milliseconds with cudaMalloc / cudaFree and next to nothing from a warm pool.  Everything
+// call, which costs tens of milliseconds with cudaMalloc / cudaFree and next to nothing from a warm pool (the pool's
+// release threshold is raised to 16 GB in mfit_ctx_create).  Everything
 // a context does is enqueued on its one stream, so stream-ordered frees are safe.
 static thread_local cudaStream_t g_alloc_stream = nullptr;
 static inline cudaError_t mfit_pool_malloc(void** p, size_t bytes) { return cudaMallocAsync(p, bytes, g_alloc_stream); }
@@ -778,7 +779,7 @@ int mfit_ctx_create(int device, void* stream, mfit_ctx** out) {
   }
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    unsigned long long keep = ~0ull;
+    unsigned long long keep = 16ull << 30;  // freed blocks stay cached up to 16 GB; beyond that they go back to the driver
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   *out = c;
