@@ -215,9 +215,10 @@ int mfit_set_timing(mfit_ctx* ctx, int on);
 /* device time of the eval kernels of the last run / eval call, seconds (CUDA events on the ctx stream),
  * and how many eval launches it covered */
 int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches);
-/* A run advances the chains as two groups on two streams when there are enough of them, so that one group's per-chain
- * kernels overlap the other's likelihood kernel (results do not depend on it).  0 = automatic, 1 = one group (also what
- * mfit_set_timing(1) implies: an overlapped kernel cannot be timed with events), 2 = two whenever possible. */
+/* A run advances the chains as up to four groups on separate streams when there are enough of them, so that one group's
+ * per-chain kernels overlap the others' likelihood kernels (results do not depend on it).  0 = automatic (3, 2 or 1 by
+ * chain count), 1 = one group (also what mfit_set_timing(1) implies: an overlapped kernel cannot be timed with events),
+ * 2..4 = that many whenever possible. */
 int mfit_set_groups(mfit_ctx* ctx, int n_groups);
 /* write > L2 bytes on the ctx stream (bench hygiene between timed steps) */
 int mfit_flush_l2(mfit_ctx* ctx);

@@ -95,11 +95,12 @@ struct mfit_ctx {
   int seg_tiles_override = 0;
   std::map<const void*, int> resident;  // eval kernel -> CTAs resident on the whole device
   int* sched_dev = nullptr;             // [2 per group] work-item counter / finished-CTA counter of the eval kernels (zero between launches)
-  // A run splits the chains into two groups that advance on separate streams: the per-chain kernels of one group
-  // (segment reduction, accept/adapt, next proposal -- latency-bound, one warp per SM) and the tail of its likelihood
-  // kernel then overlap the likelihood kernel of the other group.  Chains never interact, so results are unchanged.
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  // A run splits the chains into two or three groups that advance on separate streams: the per-chain kernels of one
+  // group (segment reduction, accept/adapt, next proposal -- latency-bound, one warp per SM) and the tail of its
+  // likelihood kernel then overlap the likelihood kernels of the others.  Chains never interact: results are unchanged.
+  static constexpr int kMaxGroups = 4;
+  cudaStream_t gstream[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};  // [0] is `stream`
+  cudaEvent_t fork_ev = nullptr, join_ev[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
   int n_groups = 1;
   int groups_override = 0;              // mfit_set_groups: 0 = automatic
 
@@ -224,11 +225,15 @@ void plan_segments(mfit_ctx* ctx, Dataset& d) {
     return;
   }
   const long long n_tiles = (d.n + MFIT_TILE - 1) / MFIT_TILE;
-  // at most MFIT_MAX_SEG segments; two tiles per work item as soon as that still leaves >= 256 items per chain-block
-  // (one-tile items pay ~4 % for their per-item set-up: measured on C2, tools/kbench.py --seg-tiles)
+  // at most MFIT_MAX_SEG segments, and up to eight tiles per work item as long as that leaves >= 64 items per
+  // chain-block: per-item set-up costs ~4 % with one-tile items, and since a run overlaps the tail of one chain group's
+  // kernel with the next group's, fine granularity buys nothing (C2, bench.py with MFIT_SEG_TILES = 1 / 2 / 8 / 12:
+  // 0.471 / 0.460 / 0.445 / 0.442 ms per step; 12 slows the kernel on its own by 10 %, 8 does not)
   long long tps = (n_tiles + MFIT_MAX_SEG - 1) / MFIT_MAX_SEG;
-  if (tps < 2 && n_tiles >= 512) tps = 2;
+  const long long want = n_tiles / 64 < 8 ? n_tiles / 64 : 8;
+  if (tps < want) tps = want;
   if (ctx->seg_tiles_override > 0) tps = ctx->seg_tiles_override;
+  else if (const char* e = getenv("MFIT_SEG_TILES")) { if (atoi(e) > 0) tps = atoi(e); }  // tuning aid
   if (tps < 1) tps = 1;
   d.tiles_per_seg = (int)tps;
   d.n_seg = (int)((n_tiles + tps - 1) / tps);
@@ -317,8 +322,8 @@ void fill_eval_args(MfitEvalArgs& a, const Dataset& s, const Workspace& w, int d
 
 int ensure_sched(mfit_ctx* ctx) {
   if (!ctx->sched_dev) {
-    CU(cudaMalloc(&ctx->sched_dev, 4 * sizeof(int)));
-    CU(cudaMemsetAsync(ctx->sched_dev, 0, 4 * sizeof(int), ctx->stream));
+    CU(cudaMalloc(&ctx->sched_dev, 2 * mfit_ctx::kMaxGroups * sizeof(int)));
+    CU(cudaMemsetAsync(ctx->sched_dev, 0, 2 * mfit_ctx::kMaxGroups * sizeof(int), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
   return 0;
@@ -646,34 +651,44 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
   long long t = ctx->run_t;
   const long long t_end = (budget < 0 || t + budget > ctx->run_max) ? ctx->run_max : t + budget;
   bool all_done = false;
-  // chain groups (see mfit_ctx::stream2): two when there are enough chains to fill the machine twice over, the data sets
+  // chain groups (see mfit_ctx::gstream): two when there are enough chains to fill the machine twice over, the data sets
   // are not sharded over ranks (the exchange is a whole-set collective) and kernel times are not being recorded
   // (an overlapped kernel's event interval includes its wait for SM slots)
   const long long n_cb_all = c.stride / MFIT_CB;
-  int n_groups = (!ctx->sharded && !ctx->timing && n_cb_all >= 8) ? 2 : 1;
-  if (ctx->groups_override > 0) n_groups = ctx->groups_override > 2 ? 2 : ctx->groups_override;
-  if (ctx->sharded || n_cb_all < 2) n_groups = 1;
+  int n_groups = (ctx->sharded || ctx->timing) ? 1 : n_cb_all >= 12 ? 3 : n_cb_all >= 8 ? 2 : 1;
+  if (const char* e = getenv("MFIT_GROUPS")) { if (atoi(e) > 0 && !ctx->timing) n_groups = atoi(e); }  // tuning aid
+  if (ctx->groups_override > 0) n_groups = ctx->groups_override;
+  if (n_groups > mfit_ctx::kMaxGroups) n_groups = mfit_ctx::kMaxGroups;
+  if (n_groups > n_cb_all) n_groups = (int)n_cb_all;
+  if (ctx->sharded || n_groups < 1) n_groups = 1;
   ctx->n_groups = n_groups;
-  if (n_groups == 2) {
-    if (!ctx->stream2) {
-      CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
-    }
+  ctx->gstream[0] = ctx->stream;
+  if (n_groups > 1) {
+    if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
     CU(cudaEventRecord(ctx->fork_ev, ctx->stream));  // everything enqueued so far (run set-up, earlier steps) comes first
-    CU(cudaStreamWaitEvent(ctx->stream2, ctx->fork_ev, 0));
-  }
-  struct Group { int cb0, n_cb; long long w0, w1; cudaStream_t st; } grp[2];
-  {
-    const int half = (int)((n_cb_all + 1) / 2);
-    grp[0] = {0, n_groups == 2 ? half : (int)n_cb_all, 0, 0, ctx->stream};
-    grp[1] = {half, (int)n_cb_all - half, 0, 0, ctx->stream2};
-    for (int g = 0; g < 2; g++) {
-      grp[g].w0 = (long long)grp[g].cb0 * MFIT_CB;
-      grp[g].w1 = grp[g].w0 + (long long)grp[g].n_cb * MFIT_CB;
-      if (grp[g].w1 > c.W) grp[g].w1 = c.W;
-      if (grp[g].w0 > c.W) grp[g].w0 = c.W;
+    for (int g = 1; g < n_groups; g++) {
+      if (!ctx->gstream[g]) {
+        CU(cudaStreamCreateWithFlags(&ctx->gstream[g], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->join_ev[g], cudaEventDisableTiming));
+      }
+      CU(cudaStreamWaitEvent(ctx->gstream[g], ctx->fork_ev, 0));
     }
+  }
+  auto join_groups = [&]() -> int {  // the context's stream waits for what the other groups have enqueued
+    for (int g = 1; g < n_groups; g++) {
+      CU(cudaEventRecord(ctx->join_ev[g], ctx->gstream[g]));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[g], 0));
+    }
+    return 0;
+  };
+  struct Group { int cb0, n_cb; long long w0, w1; cudaStream_t st; } grp[mfit_ctx::kMaxGroups];
+  for (int g = 0; g < n_groups; g++) {
+    const int lo = (int)(n_cb_all * g / n_groups), hi = (int)(n_cb_all * (g + 1) / n_groups);
+    grp[g] = {lo, hi - lo, 0, 0, ctx->gstream[g]};
+    grp[g].w0 = (long long)lo * MFIT_CB;
+    grp[g].w1 = (long long)hi * MFIT_CB;
+    if (grp[g].w1 > c.W) grp[g].w1 = c.W;
+    if (grp[g].w0 > c.W) grp[g].w0 = c.W;
   }
   for (; t < t_end && !all_done; t++) {
     if (ctx->stop.load()) break;  // mfit-walker-estop, :904
@@ -706,10 +721,7 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
           if (ctx->active_host[s] == 0) all_done = true;
         }
       if (!poll_pending[poll_slot]) {
-        if (n_groups == 2) {  // the count must see both groups' step t
-          CU(cudaEventRecord(ctx->join_ev, ctx->stream2));
-          CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
-        }
+        if ((rc = join_groups()) != 0) return rc;  // the count must see every group's step t
         mfit_launch_count_active(c, ctx->active_dev + poll_slot, ctx->stream);
         ctx->launches++;
         CU(cudaMemcpyAsync(ctx->active_host + poll_slot, ctx->active_dev + poll_slot, sizeof(int),
@@ -720,10 +732,7 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
       }
     }
   }
-  if (n_groups == 2) {
-    CU(cudaEventRecord(ctx->join_ev, ctx->stream2));
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
-  }
+  if ((rc = join_groups()) != 0) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
   collect_timing(ctx);
@@ -802,7 +811,9 @@ void mfit_ctx_destroy(mfit_ctx* ctx) {
   for (auto& p : ctx->ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   if (ctx->comm) mfit_nccl_comm_destroy(ctx->comm);
   cudaStreamSynchronize(ctx->stream);  // the stream-ordered frees above
-  if (ctx->stream2) { cudaStreamDestroy(ctx->stream2); cudaEventDestroy(ctx->fork_ev); cudaEventDestroy(ctx->join_ev); }
+  for (int g = 1; g < mfit_ctx::kMaxGroups; g++)
+    if (ctx->gstream[g]) { cudaStreamDestroy(ctx->gstream[g]); cudaEventDestroy(ctx->join_ev[g]); }
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1629,7 +1640,7 @@ int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches) {
 }
 
 int mfit_set_groups(mfit_ctx* ctx, int n_groups) {
-  if (!ctx || n_groups < 0 || n_groups > 2) return MFIT_ERR_ARG;
+  if (!ctx || n_groups < 0 || n_groups > mfit_ctx::kMaxGroups) return MFIT_ERR_ARG;
   ctx->groups_override = n_groups;
   return 0;
 }
