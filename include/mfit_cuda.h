@@ -186,6 +186,22 @@ int mfit_l_matrix_read(mfit_ctx* ctx, double* l);
  *                         (fewer than two forward steps). */
 int mfit_trace_analytics(mfit_ctx* ctx, int64_t take, double* most_likely_theta, double* most_likely_prob,
                          double* median, double* acceptance, double* covariance, double* l_matrix);
+/* walker-get-data-and-fit :1231-1255 for every chain at once, on data set d (:fn-number): the fit curve and the
+ * max / min envelope the reference plots (walker-plot-data-and-fit :1257).
+ *   take            :take, clamped per chain to its walker length (:1233-1235)
+ *   which_solution  MFIT_FIT_MOST_LIKELY: (walker-get :most-likely-step :take take); MFIT_FIT_MEDIAN: :median-params
+ *   x_fit[n_fit]    abscissae, made by the caller: (linspace (reduce #'min x-data) (reduce #'max x-data) :len 1000)
+ *   y_fit   W x n_fit : (apply fn x params) :1246
+ *   y_max, y_min W x n_fit : over the ceil(0.66 take) most probable entries of the chain's whole walk (:1248-1252;
+ *                   0.66 is a single-float and so is the product), the largest / smallest model value at every x;
+ *                   NaN for a chain without steps
+ *   params  W x P   : the parameters of the fit curve
+ *   n_distinct W    : distinct steps among the selected entries (a rejected proposal repeats its step in the walk)
+ * x-shift / y-shift of the reference are plain additions left to the caller.  Any output may be NULL. */
+#define MFIT_FIT_MOST_LIKELY 0
+#define MFIT_FIT_MEDIAN 1
+int mfit_fit_envelope(mfit_ctx* ctx, int d, int64_t take, int which_solution, const double* x_fit, int n_fit,
+                      double* y_fit, double* y_max, double* y_min, double* params, int64_t* n_distinct);
 /* walker-modify :keep-walks :568-569 applied to every chain */
 int mfit_keep_walks(mfit_ctx* ctx, int64_t keep);
 

@@ -12,6 +12,7 @@ FAM_POLY, FAM_EXPO, FAM_SINUS, FAM_LORENTZ, FAM_GAUSS_LIN, FAM_NV_MULTI, FAM_SEX
 LL_NORMAL, LL_NORMAL_CUTOFF, LL_POISSON = 0, 1, 2
 AUTO_NONE, AUTO_PROB_SETTLE = 0, 1
 OPT_COVARIANCE, OPT_BEST_VALUE = 0, 1
+FIT_MOST_LIKELY, FIT_MEDIAN = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -68,6 +69,7 @@ SIGNATURES = {
     "mfit_last_read": (C.c_int, [C.c_void_p, _dp, _dp]),
     "mfit_l_matrix_read": (C.c_int, [C.c_void_p, _dp]),
     "mfit_trace_analytics": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "mfit_fit_envelope": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, _lp]),
     "mfit_keep_walks": (C.c_int, [C.c_void_p, C.c_int64]),
     "mfit_philox_stream": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _dp, _dp]),
     "mfit_nccl_unique_id": (C.c_int, [C.c_void_p]),

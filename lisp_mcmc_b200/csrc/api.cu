@@ -64,6 +64,7 @@ struct Dataset {
   double *b_lo = nullptr, *b_hi = nullptr;
   cudaLibrary_t lib_model = nullptr, lib_prior = nullptr;
   cudaKernel_t k_user[3] = {nullptr, nullptr, nullptr};
+  cudaKernel_t k_user_fit = nullptr;
   cudaKernel_t k_prior = nullptr;
   int owner = 0, xslot = 0;
   bool owned = true;
@@ -1025,6 +1026,7 @@ int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* 
   CU(cudaLibraryGetKernel(&s.k_user_pc[3], s.lib_model, "mfit_user_perchain_staged_normal"));
   CU(cudaLibraryGetKernel(&s.k_user_pc[4], s.lib_model, "mfit_user_perchain_staged_cutoff"));
   CU(cudaLibraryGetKernel(&s.k_user_pc[5], s.lib_model, "mfit_user_perchain_staged_poisson"));
+  CU(cudaLibraryGetKernel(&s.k_user_fit, s.lib_model, "mfit_user_fit_envelope"));
   s.family = MFIT_FAM_SEXPR;
   s.degree = 0;
   return 0;
@@ -1513,6 +1515,89 @@ int mfit_trace_analytics(mfit_ctx* ctx, int64_t take, double* most_likely_theta,
   free_dev(sel);
   if (e != cudaSuccess)
     return fail(ctx, e == cudaErrorMemoryAllocation ? MFIT_ERR_NOMEM : MFIT_ERR_CUDA, "trace_analytics: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int mfit_fit_envelope(mfit_ctx* ctx, int d, int64_t take, int which_solution, const double* x_fit, int n_fit,
+                      double* y_fit, double* y_max, double* y_min, double* params, int64_t* n_distinct) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (d < 0 || d >= ctx->D) return fail(ctx, MFIT_ERR_ARG, "dataset index %d out of range", d);
+  if (take < 1) return fail(ctx, MFIT_ERR_ARG, "take < 1");
+  if (!x_fit || n_fit < 1) return fail(ctx, MFIT_ERR_ARG, "x_fit: need at least one point");
+  if (which_solution != MFIT_FIT_MOST_LIKELY && which_solution != MFIT_FIT_MEDIAN)
+    return fail(ctx, MFIT_ERR_ARG, "which_solution must be MFIT_FIT_MOST_LIKELY or MFIT_FIT_MEDIAN");
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  Dataset& s = ctx->ds[d];
+  const void* fn = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_fit : mfit_builtin_fit_kernel(s.family, s.degree);
+  if (!fn) return fail(ctx, MFIT_ERR_STATE, "dataset %d has no model", d);
+  MfitChains& c = ctx->ch;
+  if (take > c.cap) take = c.cap;  // no chain holds more rows than the ring
+  const size_t W = (size_t)c.W, P = (size_t)c.P;
+  // columns per chain: the distinct steps among the ceil(0.66 take) best entries, plus the fit's own parameters
+  const long long cols = (long long)std::ceil(0.66f * (float)take) + 1;
+  // chains per pass: gathered parameter columns bounded by 512 MB
+  long long nb = (long long)((512ull << 20) / (sizeof(double) * P * (size_t)cols));
+  if (nb < 1) nb = 1;
+  if (nb > (long long)W) nb = (long long)W;
+  double *fit = nullptr, *cols_dev = nullptr, *xf = nullptr, *out = nullptr;
+  int *sel = nullptr, *nsel = nullptr;
+  std::vector<int> nsel_host((size_t)nb);
+  cudaError_t e = cudaMalloc(&fit, sizeof(double) * W * P);
+  if (e == cudaSuccess) e = cudaMalloc(&cols_dev, sizeof(double) * (size_t)nb * P * (size_t)cols);
+  if (e == cudaSuccess) e = cudaMalloc(&xf, sizeof(double) * (size_t)n_fit);
+  if (e == cudaSuccess) e = cudaMalloc(&out, sizeof(double) * 3 * (size_t)nb * (size_t)n_fit);
+  if (e == cudaSuccess) e = cudaMalloc(&nsel, sizeof(int) * (size_t)nb);
+  // scratch of the selection: the window pass of the most likely step wants take + 1 offsets per chain
+  const size_t sel_window = which_solution == MFIT_FIT_MOST_LIKELY ? W * (size_t)(take + 1) : 0;
+  const size_t sel_cols = (size_t)nb * (size_t)cols;
+  if (e == cudaSuccess) e = cudaMalloc(&sel, sizeof(int) * (sel_window > sel_cols ? sel_window : sel_cols));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(xf, x_fit, sizeof(double) * (size_t)n_fit, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    // params :1240-1243
+    if (which_solution == MFIT_FIT_MOST_LIKELY)
+      mfit_launch_analytics(c, take, sel, fit, nullptr, nullptr, nullptr, nullptr, ctx->stream);
+    else
+      mfit_launch_median(c, take, fit, ctx->stream);
+    ctx->launches++;
+    if (params) e = cudaMemcpyAsync(params, fit, sizeof(double) * W * P, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  for (long long w0 = 0; w0 < (long long)W && e == cudaSuccess; w0 += nb) {
+    const long long nw = w0 + nb <= (long long)W ? nb : (long long)W - w0;
+    mfit_launch_envelope_select(c, take, w0, nw, cols, fit, cols_dev, nsel, sel, ctx->stream);
+    MfitFitArgs f;
+    memset(&f, 0, sizeof f);
+    f.a.xmin = s.xmin; f.a.xmax = s.xmax; f.a.n = s.n;
+    for (int k = 0; k < MFIT_MAXK; k++) f.a.idx[k] = s.idx[k];
+    f.a.degree = s.degree;
+    f.a.theta = cols_dev;
+    f.chain_pitch = (long long)P * cols;
+    f.cols = cols;
+    f.n_sel = nsel;
+    f.xfit = xf;
+    f.n_fit = n_fit;
+    f.ymax = out;
+    f.ymin = out + (size_t)nb * (size_t)n_fit;
+    f.yfit = out + 2 * (size_t)nb * (size_t)n_fit;
+    void* args[] = {&f};
+    const unsigned gy = (unsigned)((n_fit + MFIT_FIT_THREADS * MFIT_FIT_PTS - 1) / (MFIT_FIT_THREADS * MFIT_FIT_PTS));
+    e = cudaLaunchKernel(fn, dim3((unsigned)nw, gy), dim3(MFIT_FIT_THREADS), args, 0, ctx->stream);
+    ctx->launches += 2;
+    const size_t cnt = sizeof(double) * (size_t)nw * (size_t)n_fit, off = (size_t)w0 * (size_t)n_fit;
+    if (e == cudaSuccess && y_max) e = cudaMemcpyAsync(y_max + off, f.ymax, cnt, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && y_min) e = cudaMemcpyAsync(y_min + off, f.ymin, cnt, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && y_fit) e = cudaMemcpyAsync(y_fit + off, f.yfit, cnt, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && n_distinct)
+      e = cudaMemcpyAsync(nsel_host.data(), nsel, sizeof(int) * (size_t)nw, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the pass buffers are reused
+    if (e == cudaSuccess && n_distinct)
+      for (long long k = 0; k < nw; k++) n_distinct[w0 + k] = nsel_host[(size_t)k];
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  free_dev(fit); free_dev(cols_dev); free_dev(xf); free_dev(out); free_dev(nsel); free_dev(sel);
+  if (e != cudaSuccess)
+    return fail(ctx, e == cudaErrorMemoryAllocation ? MFIT_ERR_NOMEM : MFIT_ERR_CUDA, "fit_envelope: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -711,7 +711,7 @@ __device__ unsigned long long dbits(double v) { return (unsigned long long)__dou
 
 // compact the offsets k in [0, m) (k = 0 is the newest row) for which pred(k) holds, in order; returns the count
 template <class Pred>
-__device__ int block_select(int m, int* out, Pred pred, int* sh /* [blockDim.x + 1] */) {
+__device__ int block_select(int m, int* out, Pred pred, int* sh /* [blockDim.x + 1] */, int limit = 0x7fffffff) {
   const int tid = threadIdx.x, nth = blockDim.x;
   int base = 0;
   for (int k0 = 0; k0 < m; k0 += nth) {
@@ -726,12 +726,12 @@ __device__ int block_select(int m, int* out, Pred pred, int* sh /* [blockDim.x +
       sh[tid] += v;
       __syncthreads();
     }
-    if (flag) out[base + sh[tid] - 1] = k;
+    if (flag && base + sh[tid] - 1 < limit) out[base + sh[tid] - 1] = k;
     const int total = sh[nth - 1];
     __syncthreads();
     base += total;
   }
-  return base;
+  return base < limit ? base : limit;
 }
 
 // lplist-covariance :614-643 of n rows (accessor val(k, i), k in list order) -> cov[P*P]; avg is scratch [P]
@@ -895,6 +895,70 @@ __global__ void k_median(const MfitChains c, long long take, double* out) {
   out[(size_t)w * c.P + i] = res;
 }
 
+// walker-get-data-and-fit :1248-1249: sorted-walks = the ceil(0.66 take) most probable entries of the WHOLE walk (repeated
+// entries of a rejected proposal counted), reduced here to its distinct steps -- only the set matters to the max / min
+// envelope -- and gathered as parameter columns for the model kernel (mfit_fit_envelope_body):
+//   out_theta [chains of this launch][P][cols]: column j = j-th selected distinct step, newest first; column cols - 1 =
+//   the parameters of the fit curve itself (fit[w][P], most likely / median of the newest `take` steps)
+// One CTA per chain: an 8 x 8-bit radix select over the prob column of the ring finds the prob of the M-th best entry,
+// a block-wide compaction keeps one row per run of equal probs at or above it.  (Entries tied with the M-th are all
+// taken: they are repeats of one step, which the reference's sort keeps at least once.)
+__device__ __forceinline__ unsigned long long prob_key(double p) { return p != p ? 0ull : order_key(p); }  // NaN sorts last
+__global__ void k_envelope_select(const MfitChains c, long long take, long long w_first, long long cols, const double* fit,
+                                  double* out_theta, int* n_sel, int* sel_all) {
+  const long long wl = blockIdx.x, w = w_first + wl;
+  if (w >= c.W) return;
+  __shared__ unsigned hist[256];
+  __shared__ int scan[128 + 1];
+  __shared__ unsigned long long s_prefix;
+  __shared__ long long s_rank;
+  const int tid = threadIdx.x, nth = blockDim.x, P = c.P;
+  int* sel = sel_all + (size_t)wl * cols;
+  const int m_all = (int)wlen(c, w, 0x7fffffffffffffffLL);     // (walker-get walker :get :steps): every step held
+  const long long tk = wlen(c, w, take);                       // take clamped to the walker length :1233-1235
+  const long long newest = c.rows[w] - 1;
+  double* outw = out_theta + (size_t)wl * P * cols;
+  for (int i = tid; i < P; i += nth) outw[(size_t)i * cols + cols - 1] = fit[(size_t)w * P + i];
+  const float prod = __fmul_rn(0.66f, (float)tk);              // (* 0.66 take): single-float
+  long long M = (long long)ceilf(prod);
+  if (m_all == 0 || M < 1) {
+    if (tid == 0) n_sel[wl] = 0;
+    return;
+  }
+  if (M > m_all) M = m_all;
+  if (tid == 0) { s_prefix = 0ull; s_rank = M; }
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int b = tid; b < 256; b += nth) hist[b] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    for (int k = tid; k < m_all; k += nth) {
+      const unsigned long long key = prob_key(tprob(c, newest - k, w));
+      if (shift == 56 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      long long rank = s_rank;
+      int b = 255;
+      for (; b > 0; b--) {
+        if (rank <= (long long)hist[b]) break;
+        rank -= hist[b];
+      }
+      s_rank = rank;
+      s_prefix = (prefix << 8) | (unsigned long long)b;
+    }
+    __syncthreads();
+  }
+  const unsigned long long thr = s_prefix;
+  const int n = block_select(m_all, sel, [&](int k) {
+    const double p = tprob(c, newest - k, w);
+    return prob_key(p) >= thr && (k == m_all - 1 || dbits(p) != dbits(tprob(c, newest - k - 1, w)));
+  }, scan, (int)cols - 1);
+  __syncthreads();
+  for (int i = 0; i < P; i++)
+    for (int j = tid; j < n; j += nth) outw[(size_t)i * cols + j] = ttheta(c, newest - sel[j], i, w);
+  if (tid == 0) n_sel[wl] = n;
+}
+
 inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
@@ -992,6 +1056,10 @@ void mfit_launch_analytics(const MfitChains& c, long long take, int* sel, double
     configured = smem;
   }
   k_analytics<<<(unsigned)c.W, nth, smem, st>>>(c, take, sel, ml_theta, ml_prob, acceptance, cov, l_out);
+}
+void mfit_launch_envelope_select(const MfitChains& c, long long take, long long w_first, long long n_chains, long long cols,
+                                 const double* fit, double* out_theta, int* n_sel, int* sel, cudaStream_t st) {
+  k_envelope_select<<<(unsigned)n_chains, 128, 0, st>>>(c, take, w_first, cols, fit, out_theta, n_sel, sel);
 }
 void mfit_launch_median(const MfitChains& c, long long take, double* out, cudaStream_t st) {
   k_median<<<blocks_for(c.stride * c.P, 128), 128, 0, st>>>(c, take, out);

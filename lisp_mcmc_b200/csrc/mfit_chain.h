@@ -100,6 +100,8 @@ void mfit_launch_flush(void* buf, size_t bytes, cudaStream_t st);
 void mfit_launch_analytics(const MfitChains& c, long long take, int* sel, double* ml_theta, double* ml_prob,
                            double* acceptance, double* cov, double* l_out, cudaStream_t st);
 void mfit_launch_median(const MfitChains& c, long long take, double* out, cudaStream_t st);
+void mfit_launch_envelope_select(const MfitChains& c, long long take, long long w_first, long long n_chains, long long cols,
+                                 const double* fit, double* out_theta, int* n_sel, int* sel, cudaStream_t st);
 void mfit_launch_trace_regrow(const MfitChains& c, double* new_theta, double* new_prob, long long new_cap,
                               cudaStream_t st);
 #endif

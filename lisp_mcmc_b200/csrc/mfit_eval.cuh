@@ -565,4 +565,69 @@ __device__ __forceinline__ void mfit_eval_perchain_body_t(const MfitEvalArgs& a)
 // the host picks STAGED (separate kernels, so that the staged one keeps its lower register count):
 // a.x_stride == 0 && a.w_stride == 0 && a.n <= MFIT_PC_STAGE_MAX
 
+// ---------------------------------------------------------------- fit curve and max / min envelope over the trace
+// walker-get-data-and-fit (mcmc-fitting.lisp:1231-1255): y-fit = (apply fn x params) over x-fit, and for every x the
+// largest and smallest model value over the selected steps of the walk (all-ys / max-ys / min-ys :1250-1252).  The
+// chain kernels have gathered each chain's distinct selected steps as parameter columns (k_envelope_select), so a
+// "chain" of Model::load is a column here.  One CTA row per chain, MFIT_FIT_PTS x-fit points per thread held in
+// registers, the columns are CTA-uniform (broadcast loads, the next one requested before the current one is
+// evaluated).  libdevice math throughout (SLOW forms): this runs once per plot, not once per step.
+#define MFIT_FIT_THREADS 128
+#define MFIT_FIT_PTS 4
+struct MfitFitArgs {
+  MfitEvalArgs a;        /* the data set's model slots (idx, degree, xmin, xmax); theta = gathered columns
+                            [chains of this launch][P][cols], stride = cols */
+  long long chain_pitch; /* P * cols */
+  long long cols;        /* columns per chain; the last one holds the parameters of the fit curve */
+  const int* n_sel;      /* [chains of this launch] selected distinct steps */
+  const double* xfit;    /* [n_fit] */
+  int n_fit;
+  double* ymax;          /* [chains of this launch][n_fit] */
+  double* ymin;
+  double* yfit;
+};
+
+template <class Model>
+__device__ __forceinline__ void mfit_fit_envelope_body(const MfitFitArgs& f) {
+  const long long wl = blockIdx.x;
+  MfitEvalArgs a = f.a;
+  a.theta = f.a.theta + (size_t)wl * f.chain_pitch;
+  a.stride = f.cols;
+  a.W = (int)f.cols;
+  const int n = f.n_sel[wl];
+  const int i0 = (int)blockIdx.y * (MFIT_FIT_THREADS * MFIT_FIT_PTS) + (int)threadIdx.x;
+  double x[MFIT_FIT_PTS], mx[MFIT_FIT_PTS], mn[MFIT_FIT_PTS];
+#pragma unroll
+  for (int u = 0; u < MFIT_FIT_PTS; u++) {
+    const int i = i0 + u * MFIT_FIT_THREADS;
+    x[u] = i < f.n_fit ? f.xfit[i] : 0.0;
+    mx[u] = mn[u] = __longlong_as_double(0x7ff8000000000000LL);  // no step selected: NaN
+  }
+  MfitNoGuard ng;
+  Model m_next;
+  m_next.load(a, n > 0 ? 0 : f.cols - 1);
+  for (int j = 0; j < n; j++) {
+    Model m = m_next;
+    m_next.load(a, j + 1 < n ? j + 1 : f.cols - 1);
+    m.setup();
+#pragma unroll
+    for (int u = 0; u < MFIT_FIT_PTS; u++) {
+      const double v = m.template eval<true>(x[u], ng);
+      if (j == 0) { mx[u] = v; mn[u] = v; }       // (reduce #'max y) starts from the first element
+      else { mx[u] = v > mx[u] ? v : mx[u]; mn[u] = v < mn[u] ? v : mn[u]; }
+    }
+  }
+  m_next.setup();  // the fit's own parameters
+#pragma unroll
+  for (int u = 0; u < MFIT_FIT_PTS; u++) {
+    const int i = i0 + u * MFIT_FIT_THREADS;
+    if (i < f.n_fit) {
+      const size_t o = (size_t)wl * f.n_fit + i;
+      f.yfit[o] = m_next.template eval<true>(x[u], ng);
+      f.ymax[o] = mx[u];
+      f.ymin[o] = mn[u];
+    }
+  }
+}
+
 #endif  // MFIT_EVAL_CUH

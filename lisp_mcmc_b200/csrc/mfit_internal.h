@@ -16,6 +16,9 @@ size_t mfit_eval_smem_bytes(int ll);
 // eval_perchain.cu
 const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int staged);
 
+// eval_fit.cu
+const void* mfit_builtin_fit_kernel(int family, int degree);
+
 // lower.cpp
 int mfit_lower_to_string(const char* text, const char* const* keys, int n_keys, int kind, std::string& out,
                          std::string& err);

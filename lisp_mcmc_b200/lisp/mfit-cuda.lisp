@@ -28,7 +28,7 @@
   (:use :cl)
   (:export #:gpu-lambda #:gpu-builtin #:gpu-walker #:walker-create #:walker-adaptive-steps
            #:walker-adaptive-steps-full #:walker-many-steps #:walker-sample-region #:walker-force-take-step
-           #:walker-get #:walker-save #:walker-free #:mcmc-fit #:mfit-walker-estop #:lower-to-cuda #:walker-set-create))
+           #:walker-get #:walker-get-data-and-fit #:walker-save #:walker-free #:mcmc-fit #:mfit-walker-estop #:lower-to-cuda #:walker-set-create))
 (in-package :mfit-cuda)
 
 (cffi:define-foreign-library libmfit-cuda (t (:default "libmfit_cuda")))
@@ -89,6 +89,10 @@
 (cffi:defcfun ("mfit_trace_analytics" %trace-analytics) :int
   (ctx :pointer) (take :int64) (most-likely-theta :pointer) (most-likely-prob :pointer) (median :pointer)
   (acceptance :pointer) (covariance :pointer) (l-matrix :pointer))
+
+(cffi:defcfun ("mfit_fit_envelope" %fit-envelope) :int
+  (ctx :pointer) (d :int) (take :int64) (which-solution :int) (x-fit :pointer) (n-fit :int) (y-fit :pointer)
+  (y-max :pointer) (y-min :pointer) (params :pointer) (n-distinct :pointer))
 
 (defmacro with-traps-masked (&body body)
   #+sbcl `(sb-int:with-float-traps-masked (:invalid :divide-by-zero :overflow :inexact :underflow) ,@body)
@@ -376,6 +380,34 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
                (:param (mapcar (lambda (row) (getf row param)) rows))
                (:log-liklihoods probs)
                (:acceptance (/ (1+ (loop for (a b) on probs while b count (/= a b))) m))))))))))   ; :506-508
+
+(defun walker-get-data-and-fit (walker &key (take 1000) (x-column 0) (y-column 1) (fn-number 0)
+                                          (which-solution :most-likely) x-shift y-shift (chain 0))
+  "walker-get-data-and-fit :1231-1255 for one CHAIN -> (x-fit max-ys min-ys y-fit x-data y-data params).  The fit
+curve and the envelope over the best 66 % of the walk are evaluated on the device for every chain at once."
+  (let* ((ctx (gpu-walker-ctx walker)) (w (gpu-walker-n-walkers walker)) (p (gpu-walker-n-params walker))
+         (data (elt (gpu-walker-data walker) fn-number))
+         (x-data (elt data x-column)) (y-data (elt data y-column))
+         (x-fit (let* ((lo (reduce #'min x-data)) (hi (reduce #'max x-data))           ; linspace :235-247, :len 1000
+                       (step (/ (rational (- hi lo)) 999)))
+                  (loop for n below 1000 collect (coerce (+ (rational lo) (* n step)) 'double-float))))
+         (n-fit (length x-fit))
+         (shift (lambda (s seq) (if s (map 'list (lambda (v) (+ s v)) seq) (coerce seq 'list)))))
+    (cffi:with-foreign-objects ((xf :double n-fit) (yf :double (* w n-fit)) (ymax :double (* w n-fit))
+                                (ymin :double (* w n-fit)) (par :double (* w p)))
+      (loop for x in x-fit for i from 0 do (setf (cffi:mem-aref xf :double i) (coerce x 'double-float)))
+      (with-traps-masked
+        (chk ctx (%fit-envelope ctx fn-number take (if (eq which-solution :most-likely) 0 1) xf n-fit yf ymax ymin par
+                                (cffi:null-pointer))))
+      (flet ((row (ptr) (loop for i below n-fit collect (cffi:mem-aref ptr :double (+ (* chain n-fit) i)))))
+        (list (funcall shift x-shift x-fit)
+              (funcall shift y-shift (row ymax))
+              (funcall shift y-shift (row ymin))
+              (funcall shift y-shift (row yf))
+              (funcall shift x-shift x-data)
+              (funcall shift y-shift y-data)
+              (loop for k in (gpu-walker-param-keys walker) for i from 0
+                    append (list k (cffi:mem-aref par :double (+ (* chain p) i)))))))))
 
 (defun walker-save (walker filename &key take (chain 0))
   "walker-save :971-1001 revived: one readable s-expression per file."

@@ -62,6 +62,15 @@ _OPT = {None: _lib.OPT_COVARIANCE, "covariance": _lib.OPT_COVARIANCE, ":covarian
         "best-value": _lib.OPT_BEST_VALUE, ":best-value": _lib.OPT_BEST_VALUE}
 
 
+def linspace(start, end, length=50):
+    """linspace :235-247 with :len -- exact rationals start + n (end - start)/(len - 1), the difference taken in double
+    arithmetic first, every element rounded to a double once (numpy.linspace rounds differently)."""
+    from fractions import Fraction
+    step = Fraction(float(end) - float(start)) / (length - 1)
+    first = Fraction(float(start))
+    return np.array([float(first + n * step) for n in range(length)], dtype=np.float64)
+
+
 # ------------------------------------------------------------------ input normalisation (walker-create :1142-1147)
 def force_list(item):
     """force-list :755-759"""
@@ -470,6 +479,28 @@ class Walker:
         if g == "param":
             return sel(th[:, :, self.param_keys.index(str(param).lstrip(":").lower())])
         raise NotImplementedError("walker-get :%s" % g)
+
+    def data_and_fit(self, take=1000, x_column=0, y_column=1, fn_number=0, which_solution="most-likely", x_shift=None,
+                     y_shift=None, n_fit=1000):
+        """walker-get-data-and-fit :1231-1255 for every chain at once (mfit_fit_envelope) ->
+        (x_fit[n_fit], max_ys[W,n_fit], min_ys[W,n_fit], y_fit[W,n_fit], x_data, y_data, params[W,P]): the model at the
+        most likely / median parameters of the newest `take` steps and, at every abscissa, the largest and smallest
+        model value over the ceil(0.66 take) most probable entries of each chain's whole walk."""
+        if self.per_walker:
+            raise NotImplementedError("walker sets with per-walker data: one x range per walker")
+        st = self.stats()
+        take = int(st["length"].max()) if take is None else int(take)
+        cols = self.data[fn_number]
+        x_data, y_data = np.asarray(cols[x_column]), np.asarray(cols[y_column])
+        x_fit = linspace(float(np.min(x_data)), float(np.max(x_data)), n_fit)   # :1243
+        W, P = self.W, self.P
+        y_fit, y_max, y_min, par = np.empty((W, n_fit)), np.empty((W, n_fit)), np.empty((W, n_fit)), np.empty((W, P))
+        which = _lib.FIT_MOST_LIKELY if str(which_solution).lstrip(":").lower() == "most-likely" else _lib.FIT_MEDIAN
+        self._chk(self._L.mfit_fit_envelope(self._h, int(fn_number), take, which, _ptr(x_fit), n_fit, _ptr(y_fit),
+                                            _ptr(y_max), _ptr(y_min), _ptr(par), None))
+        xs = 0.0 if x_shift is None else x_shift
+        ys = 0.0 if y_shift is None else y_shift
+        return x_fit + xs, y_max + ys, y_min + ys, y_fit + ys, x_data + xs, y_data + ys, par
 
     # -------------------------------------------------------------- walker-save / walker-load (:971-1001)
     def save(self, path, take=None):

@@ -108,6 +108,12 @@ void orc_walker_last_l_matrix(orc_walker* w, double* L);
 /* walker-get :acceptance :take -> count, len (exact rational count/len) */
 void orc_walker_acceptance(orc_walker* w, long take, long* count, long* len);
 int orc_walker_keep_walks(orc_walker* w, long keep);
+/* test support: replace the walk (theta n x P, prob n; newest first) */
+int orc_walker_load_walk(orc_walker* w, const double* theta, const double* prob, long n);
+/* walker-get-data-and-fit :1231-1255 on dataset d: fit curve at the most likely (0) / median (1) parameters of the
+ * newest `take` steps and the max / min envelope over the ceil(0.66 take) most probable steps of the whole walk */
+int orc_walker_data_and_fit(orc_walker* w, long take, int d, int which_solution, const double* x_fit, long n_fit,
+                            double* y_fit, double* max_ys, double* min_ys, double* params);
 
 /* multi-threaded CPU baseline: W independent walkers sharing one configuration
  * (a template walker is cloned), internal PRNG, returns wall seconds */

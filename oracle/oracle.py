@@ -105,6 +105,8 @@ def lib():
         L.orc_walker_last_l_matrix.argtypes = [C.c_void_p, _dp]
         L.orc_walker_acceptance.argtypes = [C.c_void_p, C.c_long, _lp, _lp]
         L.orc_walker_keep_walks.argtypes = [C.c_void_p, C.c_long]
+        L.orc_walker_load_walk.argtypes = [C.c_void_p, _dp, _dp, C.c_long]
+        L.orc_walker_data_and_fit.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, _dp, C.c_long, _dp, _dp, _dp, _dp]
         L.orc_bench_many.restype = C.c_double
         L.orc_bench_many.argtypes = [C.c_void_p, _dp, C.c_long, C.POINTER(AdaptCfg), C.c_int, C.c_ulonglong, _dp, C.c_long]
         _LIB = L
@@ -171,6 +173,15 @@ def model_builtin(family, degree, theta, x):
     return lib().orc_model_builtin(family, degree, p, float(x))
 
 
+def linspace(start, end, length=50):
+    """linspace :235-247 with :len: exact rationals start + n (end - start)/(len - 1) -- the difference formed in double
+    arithmetic first -- each coerced to double-float (one rounding per element)."""
+    from fractions import Fraction
+    step = Fraction(float(end) - float(start)) / (length - 1)
+    s0 = Fraction(float(start))
+    return np.array([float(s0 + n * step) for n in range(length)], dtype=np.float64)
+
+
 def temperature_schedule(n, P, temperature):
     Tn = lib().orc_temp_steps(n, P)
     out = np.zeros(Tn)
@@ -226,6 +237,9 @@ class Walker:
             sigma = np.broadcast_to(np.asarray(sigma, dtype=np.float64), x.shape)
             sigma, ps = _d(sigma)
         self._chk(lib().orc_walker_dataset(self.h, d, px, py, ps, len(x)))
+        if not hasattr(self, "_x"):
+            self._x = {}
+        self._x[d] = x
 
     def model_builtin(self, d, family, idx, degree=0):
         idx = np.ascontiguousarray(idx, dtype=np.int32)
@@ -343,6 +357,26 @@ class Walker:
 
     def keep_walks(self, keep):
         lib().orc_walker_keep_walks(self.h, keep)
+
+    def load_walk(self, theta, prob):
+        """replace the walk by (theta[n,P], prob[n]), newest first"""
+        theta, pt = _d(theta)
+        prob, pp = _d(prob)
+        self._chk(lib().orc_walker_load_walk(self.h, pt, pp, len(prob)))
+
+    def data_and_fit(self, take=1000, fn_number=0, which_solution="most-likely", n_fit=1000, x_shift=None, y_shift=None):
+        """walker-get-data-and-fit :1231-1255 -> (x_fit, max_ys, min_ys, y_fit, params); x-data / y-data are the
+        caller's own arrays and are not repeated here."""
+        x = self._x[fn_number]
+        xf = linspace(float(np.min(x)), float(np.max(x)), n_fit)
+        yf, mx, mn, par = np.zeros(n_fit), np.zeros(n_fit), np.zeros(n_fit), np.zeros(self.P)
+        which = 0 if str(which_solution).lstrip(":") == "most-likely" else 1
+        self._chk(lib().orc_walker_data_and_fit(self.h, int(take or 0), fn_number, which, xf.ctypes.data_as(_dp), n_fit,
+                                                yf.ctypes.data_as(_dp), mx.ctypes.data_as(_dp), mn.ctypes.data_as(_dp),
+                                                par.ctypes.data_as(_dp)))
+        xs = xf if x_shift is None else xf + x_shift
+        ys = 0.0 if y_shift is None else y_shift
+        return xs, mx + ys, mn + ys, yf + ys, par
 
     def bench_many(self, theta0, n, n_threads, seed=1, temperature=10.0, max_steps=-1):
         """CPU baseline: W independent copies of this walker run walker-adaptive-steps-full :n n (interrupted after

@@ -24,6 +24,7 @@ struct Val {
 struct Fn;
 Fn* fn_parse(const char* text, const std::vector<std::string>& keys);
 double fn_call_model(Fn* f, double x, const double* theta);
+double fn_call_model_v(Fn* f, const double* x, int xdim, const double* theta);
 double fn_call_prior(Fn* f, const double* theta);
 void fn_free(Fn* f);
 

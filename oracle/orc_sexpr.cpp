@@ -12,6 +12,7 @@
 #include "orc_internal.h"
 #include <cctype>
 #include <cmath>
+#include <limits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -242,7 +243,7 @@ static Val irrational(fn1 f, const Val& a) {
 enum Op {
   O_CONST, O_VAR, O_ADD, O_SUB, O_MUL, O_DIV, O_INC, O_DEC, O_EXP, O_LOG, O_SIN, O_COS, O_TAN, O_ASIN,
   O_ACOS, O_ATAN, O_SINH, O_COSH, O_TANH, O_SQRT, O_EXPT, O_ABS, O_MIN, O_MAX, O_SIGNUM, O_IF, O_AND,
-  O_OR, O_NOT, O_LT, O_GT, O_LE, O_GE, O_EQ, O_NE, O_LET, O_PROGN, O_FLOAT
+  O_OR, O_NOT, O_LT, O_GT, O_LE, O_GE, O_EQ, O_NE, O_LET, O_PROGN, O_FLOAT, O_XELT
 };
 
 struct Node {
@@ -306,6 +307,32 @@ struct Compiler {
       return v;
     };
     if (f == "THE") return compile(s.kids.at(2));
+    {
+      // multi-dimensional inputs (walker-create docstring :1137): x is itself a sequence (x1 x2 ...) and the model
+      // picks its components with elt / aref / svref / nth / first ... fourth / car / cadr / caddr
+      static const struct { const char* name; int fixed; } acc[] = {
+          {"ELT", -1}, {"AREF", -1}, {"SVREF", -1}, {"NTH", -2}, {"FIRST", 0}, {"SECOND", 1}, {"THIRD", 2},
+          {"FOURTH", 3}, {"CAR", 0}, {"CADR", 1}, {"CADDR", 2}};
+      for (auto& a : acc)
+        if (f == a.name) {
+          const bool fixed = a.fixed >= 0;
+          if (s.kids.size() != (fixed ? 2u : 3u)) throw std::runtime_error("wrong number of arguments to " + f);
+          const Sx& seq = s.kids[a.fixed == -2 ? 2 : 1];
+          if (seq.t != Sx::SYM || fn->x_slot < 0 || sc.find(seq.sym) != fn->x_slot)
+            throw std::runtime_error(f + ": only the model's positional argument can be indexed");
+          long long idx = a.fixed;
+          if (!fixed) {
+            const Sx& ix = s.kids[a.fixed == -2 ? 1 : 2];
+            if (ix.t != Sx::NUM || ix.num.k != Val::RAT || ix.num.den != 1 || ix.num.num < 0)
+              throw std::runtime_error(f + ": the index must be a literal non-negative integer");
+            idx = ix.num.num;
+          }
+          Node n;
+          n.op = O_XELT;
+          n.slot = (int)idx;
+          return n;
+        }
+    }
     if (f == "DECLARE") return konst(Val::boolean(false));
     if (f == "PROGN") return call(O_PROGN, args());
     if (f == "LET" || f == "LET*") {
@@ -443,9 +470,17 @@ struct Compiler {
 
 static bool truthy(const Val& v) { return !(v.k == Val::BOOL && !v.b); }
 
+// the components of a multi-dimensional x for the call in progress (null: x is a number)
+static thread_local const double* t_xvec = nullptr;
+static thread_local int t_xdim = 0;
+
 static Val eval(const Node& n, Val* env) {
   switch (n.op) {
     case O_CONST: return n.c;
+    case O_XELT:
+      if (!t_xvec) throw std::runtime_error("x is a number, not a sequence");
+      if (n.slot >= t_xdim) throw std::runtime_error("index beyond the end of x");
+      return Val::dbl(t_xvec[n.slot]);
     case O_VAR: return env[n.slot];
     case O_ADD: case O_MUL: {
       char op = n.op == O_ADD ? '+' : '*';
@@ -633,7 +668,7 @@ Fn* fn_parse(const char* text, const std::vector<std::string>& keys_in) {
   return fn.release();
 }
 
-static double run(Fn* f, double x, const double* theta) {
+static double run(Fn* f, double x, const double* theta, bool x_is_sequence = false) {
   Val envbuf[256];
   std::vector<Val> big;
   Val* env = envbuf;
@@ -641,13 +676,21 @@ static double run(Fn* f, double x, const double* theta) {
   for (int i = 0; i < f->P; i++)
     if (f->theta_slot[i] >= 0) env[f->theta_slot[i]] = Val::dbl(theta[i]);
   for (auto& d : f->defaults) env[d.first] = d.second;
-  if (f->x_slot >= 0) env[f->x_slot] = Val::dbl(x);
+  if (f->x_slot >= 0) env[f->x_slot] = x_is_sequence ? Val::boolean(true) : Val::dbl(x);  // a sequence is no number
   Val v = eval(f->body, env);
   if (v.k == Val::BOOL) throw std::runtime_error("function returned a non-number");
   return v.as_double();
 }
 
 double fn_call_model(Fn* f, double x, const double* theta) { return run(f, x, theta); }
+// (apply fn x params) with x a sequence of xdim numbers: using x itself as a number is a type error
+double fn_call_model_v(Fn* f, const double* x, int xdim, const double* theta) {
+  struct Bind {
+    Bind(const double* x, int d) { t_xvec = x; t_xdim = d; }
+    ~Bind() { t_xvec = nullptr; t_xdim = 0; }
+  } bind(x, xdim);
+  return run(f, std::numeric_limits<double>::quiet_NaN(), theta, true);
+}
 double fn_call_prior(Fn* f, const double* theta) { return run(f, 0.0, theta); }
 void fn_free(Fn* f) { delete f; }
 
@@ -671,6 +714,10 @@ extern "C" orc_fn* orc_fn_parse(const char* text, const char* const* keys, int P
 extern "C" void orc_fn_free(orc_fn* f) { if (f) { orc::fn_free(f->f); delete f; } }
 extern "C" double orc_fn_call_model(orc_fn* f, double x, const double* theta) {
   try { return orc::fn_call_model(f->f, x, theta); }
+  catch (std::exception& e) { if (getenv("ORC_DEBUG")) fprintf(stderr, "orc: %s\n", e.what()); return NAN; }
+}
+extern "C" double orc_fn_call_model_v(orc_fn* f, const double* x, int xdim, const double* theta) {
+  try { return orc::fn_call_model_v(f->f, x, xdim, theta); }
   catch (std::exception& e) { if (getenv("ORC_DEBUG")) fprintf(stderr, "orc: %s\n", e.what()); return NAN; }
 }
 extern "C" double orc_fn_call_prior(orc_fn* f, const double* theta) {

@@ -8,6 +8,7 @@
 // schedule and the :prob-settle auto stop.  Compile with -ffp-contract=off: SBCL
 // on x86-64 never fuses a multiply with an add.
 #include "orc_internal.h"
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -688,6 +689,77 @@ void orc_walker_last_l_matrix(orc_walker* w, double* L) {
   if (w->lastL.size() == (size_t)w->P * w->P) memcpy(L, w->lastL.data(), sizeof(double) * w->P * w->P);
 }
 void orc_walker_acceptance(orc_walker* w, long take, long* count, long* len) { acceptance(w, take, count, len); }
+
+// test support: replace the walk by a given one (newest first, like walker-get :steps), so that the trace analytics
+// can be checked on exactly the walk another implementation produced
+extern "C" int orc_walker_load_walk(orc_walker* w, const double* theta, const double* prob, long n) {
+  w->walk.clear();
+  for (long r = n; r-- > 0;) {
+    Step s;
+    s.prob = prob[r];
+    s.params.assign(theta + (size_t)r * w->P, theta + (size_t)(r + 1) * w->P);
+    w->walk.push_back(s);
+  }
+  w->length = n;
+  if (n > 0) w->last = w->walk.back();
+  return 0;
+}
+
+// walker-get-data-and-fit :1231-1255.  x_fit is (linspace (reduce #'min x-data) (reduce #'max x-data) :len 1000),
+// made by the caller (exact rationals, :235-247: oracle.py linspace).
+//   take          clamped to the walker length (:1233-1235); <= 0 means nil
+//   params        which_solution 0: (walker-get :most-likely-step :take take) = reduce keeping x only when strictly
+//                 greater, i.e. of equal maxima the OLDEST (:503-505); 1: :median-params = nth-percentile 50 (:516-523,
+//                 :1493-1504: position 50 (len-1)/100, the MEAN of the two neighbours when fractional)
+//   y_fit         (apply fn x params) over x-fit (:1246)
+//   sorted-walks  (subseq (sort (walker-get :steps) #'> :key prob) 0 (ceiling (* 0.66 take))) (:1248-1249): the WHOLE
+//                 walk sorted, 0.66 a single-float, the product formed in single precision
+//   max_ys/min_ys (reduce #'max y) / (reduce #'min y) over those steps at every x (:1250-1252)
+// x-shift / y-shift are plain additions done by the caller.
+extern "C" int orc_walker_data_and_fit(orc_walker* w, long take, int d, int which_solution, const double* x_fit,
+                                       long n_fit, double* y_fit, double* max_ys, double* min_ys, double* params) {
+  if (d < 0 || d >= w->D) return -1;
+  const size_t n = w->walk.size();
+  if (n == 0) return -2;
+  long tk = (take <= 0 || take > w->length) ? w->length : take;
+  if ((size_t)tk > n) tk = (long)n;
+  const size_t lo = n - (size_t)tk;
+  std::vector<double> par(w->P);
+  if (which_solution == 0) {
+    size_t best = n - 1;                       // x = newest; y walks towards older steps
+    for (size_t j = n - 1; j-- > lo;)
+      if (!(w->walk[best].prob > w->walk[j].prob)) best = j;
+    par = w->walk[best].params;
+  } else {
+    std::vector<double> col((size_t)tk);
+    for (int i = 0; i < w->P; i++) {
+      for (size_t j = lo; j < n; j++) col[j - lo] = w->walk[j].params[i];
+      std::sort(col.begin(), col.end());
+      const long num = 50 * (tk - 1), pos = num / 100, rem = num % 100;
+      par[i] = rem == 0 ? col[pos] : (col[pos] + col[pos + 1]) / 2.0;
+    }
+  }
+  if (params) memcpy(params, par.data(), sizeof(double) * w->P);
+  const Dataset& ds = w->ds[d];
+  for (long i = 0; i < n_fit; i++) y_fit[i] = model_eval(ds, par.data(), x_fit[i]);
+  const float prod = 0.66f * (float)tk;        // (* 0.66 take): single-float contagion
+  const long M = (long)std::ceil(prod);
+  if (M < 1 || (size_t)M > n) return -3;       // subseq would signal an error
+  std::vector<size_t> order(n);
+  for (size_t j = 0; j < n; j++) order[j] = n - 1 - j;  // list order: newest first
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return w->walk[a].prob > w->walk[b].prob; });
+  for (long i = 0; i < n_fit; i++) {
+    double mx = 0.0, mn = 0.0;
+    for (long k = 0; k < M; k++) {
+      const double v = model_eval(ds, w->walk[order[k]].params.data(), x_fit[i]);
+      if (k == 0) { mx = v; mn = v; }
+      else { if (v > mx) mx = v; if (v < mn) mn = v; }
+    }
+    max_ys[i] = mx;
+    min_ys[i] = mn;
+  }
+  return 0;
+}
 
 // walker-modify :keep-walks :568-569 -- keeps the NEWEST keep steps
 int orc_walker_keep_walks(orc_walker* w, long keep) {

@@ -111,6 +111,34 @@ def test_ragged_sizes(orc, N, W):
     w.close()
 
 
+def test_gauss_far_from_origin(orc):
+    """Data far from x = 0 with peaks that are narrow next to that offset (|mu / s| from 570 to 9500): the Gaussian
+    argument must be formed as (x - mu) first -- hoisting -(mu / s) into one FMA, fma(x, 1/s, -mu/s), saves an FP64
+    instruction but loses these cases (1.4e-11 on this very input, measured)"""
+    rng = np.random.default_rng(77)
+    N, W = 3001, 260
+    keys = families.slots("gauss_lin")
+    th = np.array([10.0, 2869.3, 5.0, 2.0, 0.01])
+    x = np.linspace(2800.0, 2940.0, N)
+    from oracle import oracle as orc_mod
+    f = np.array([orc_mod.model_builtin(families.family_id("gauss_lin"), 0, th, xi) for xi in x])
+    sig = rng.uniform(0.05, 0.15, N)
+    y = f + sig * rng.standard_normal(N)
+    theta0 = th[None, :] * (1 + 0.002 * rng.standard_normal((W, 5)))
+    theta0[::7, 1] += 6.0            # peaks a good sigma off the data: large residuals, full sensitivity to the argument
+    narrow = [5, 128 + 5, 200, 259]
+    theta0[narrow, 2] = [2.0, 1.0, 0.3, 2.2]
+    cfg = dict(function=[builtin("gauss_lin", keys, 0)], data=[[x, y]], data_error=[sig], keys=keys, theta_star=th,
+               theta0=theta0, log_liklihood="log-liklihood-normal", log_prior="log-prior-flat")
+    w = workloads.make_walker(cfg)
+    prob, _, _ = w.make_step(theta0)
+    ow = oracle_walker(orc, cfg)
+    ref = np.array([ow.logp(t)[0] for t in theta0])
+    assert np.all(np.isfinite(prob))
+    assert rel_err(prob, ref) < TOL
+    w.close()
+
+
 def test_cutoff_clamps_like_reference(orc):
     cfg = _family_cfg("lorentz", 700, 9, "log-liklihood-normal-cutoff")
     cfg["theta0"][:, 0] *= 50.0   # far off: most terms hit the -5000 floor (:426)
@@ -458,6 +486,65 @@ def test_trace_analytics_match_reference_definitions(orc, take):
     assert np.array_equal(w.get("median-params", take=take), a["median"])
     assert np.array_equal(w.get("acceptance", take=take), a["acceptance"])
     assert np.array_equal(w.get("most-likely-step", take=take)[1], a["most_likely_prob"])
+    w.close()
+
+
+def _check_data_and_fit(orc, cfg, w, chains, take, which, fn_number=0, n_fit=1000):
+    """walker-get-data-and-fit :1231-1255 on the device for all chains == the oracle's restatement applied to the very
+    walk the GPU holds (loaded into an oracle walker): abscissae and parameters bit-identical, model values within TOL
+    of the size of the curve"""
+    xf, mx, mn, yf, xd, yd, par = w.data_and_fit(take=take, fn_number=fn_number, which_solution=which, n_fit=n_fit)
+    th, pr, nv = w.trace(int(w.stats()["length"].max()))
+    ow = oracle_walker(orc, cfg)
+    for c in chains:
+        m = int(nv[c])
+        ow.load_walk(th[c, :m], pr[c, :m])
+        oxf, omx, omn, oyf, opar = ow.data_and_fit(take=take, fn_number=fn_number, which_solution=which, n_fit=n_fit)
+        assert np.array_equal(xf, oxf)
+        assert np.array_equal(par[c], opar)
+        scale = float(np.max(np.abs(oyf)))
+        assert rel_err(yf[c], oyf, scale) < TOL
+        assert rel_err(mx[c], omx, scale) < TOL and rel_err(mn[c], omn, scale) < TOL
+        assert np.all(mn[c] <= mx[c])
+        # the envelope may miss the curve itself (:most-likely searches the newest `take` steps, the envelope the best
+        # of the whole walk), but it always brackets the walk's most likely step
+        best = th[c, int(np.argmax(pr[c, :m]))]
+        ybest = np.array([orc.Fn(_fn_text(cfg, fn_number), cfg["keys"]).model(x, best) for x in xf[::97]])
+        assert np.all(ybest <= mx[c][::97] + TOL * scale) and np.all(ybest >= mn[c][::97] - TOL * scale)
+    return xf, mx, mn, yf, xd, yd, par
+
+
+def _fn_text(cfg, d):
+    f = cfg["function"][d]
+    return f if isinstance(f, str) else f.lisp_text()
+
+
+@pytest.mark.parametrize("take,which", [(37, "most-likely"), (400, "median"), (1000, "most-likely"), (5000, "median")])
+def test_data_and_fit_envelope_matches_reference_definition(orc, take, which):
+    cfg = workloads.c2(W=131, N=300)
+    w = workloads.make_walker(cfg, seed=5)
+    w.adaptive_steps_full(n=900, temperature=10)
+    xf, mx, mn, yf, xd, yd, par = _check_data_and_fit(orc, cfg, w, [0, 64, 130], take, which, n_fit=1000 if take == 400 else 120)
+    # :x-shift / :y-shift are plain additions (:1236-1247, :1251-1252)
+    xs, mxs, mns, yfs, xds, yds, _ = w.data_and_fit(take=take, which_solution=which, n_fit=len(xf), x_shift=2.5, y_shift=-1.0)
+    assert np.array_equal(xs, xf + 2.5) and np.array_equal(mxs, mx - 1.0) and np.array_equal(mns, mn - 1.0)
+    assert np.array_equal(yfs, yf - 1.0) and np.array_equal(xds, xd + 2.5) and np.array_equal(yds, yd - 1.0)
+    w.close()
+
+
+def test_data_and_fit_global_fit_and_user_model(orc):
+    """:fn-number picks the data set of a global fit (its own x range and parameter slots); an NVRTC-lowered model goes
+    through the same kernel body; a walk cut by walker-modify :keep-walks is searched as it stands"""
+    g4 = workloads.c4(W=40, D=2, N=500)
+    w = workloads.make_walker(g4, seed=9)
+    w.adaptive_steps_full(n=500, temperature=10)
+    _check_data_and_fit(orc, g4, w, [0, 39], 300, "most-likely", fn_number=1, n_fit=90)
+    w.close()
+    c5 = workloads.c5(W=33, N=400)
+    w = workloads.make_walker(c5, seed=11)
+    w.adaptive_steps_full(n=450, temperature=10)
+    w.keep_walks(200)
+    _check_data_and_fit(orc, c5, w, [0, 32], 150, "median", n_fit=64)
     w.close()
 
 

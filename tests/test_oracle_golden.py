@@ -135,3 +135,53 @@ def test_oracle_families_match_their_lisp_text(orc):
             th = rng.uniform(0.5, 2.0, len(keys))
             x = rng.uniform(-2, 2)
             assert fn.model(x, th) == orc.model_builtin(families.family_id(name), deg, th, x)
+
+
+def test_linspace_is_the_exact_rational_one(orc):
+    """linspace :235-247: start + n (end - start)/(len - 1) in exact rationals, rounded once per element -- not the
+    floating-point recurrence numpy uses; the docstring case (linspace 0 50 :len 100) of :78 ends exactly on 50"""
+    from fractions import Fraction
+    xs = orc.linspace(0.0, 50.0, 100)
+    assert xs[0] == 0.0 and xs[-1] == 50.0 and len(xs) == 100
+    assert xs[1] == float(Fraction(50, 99)) and xs[37] == float(Fraction(50 * 37, 99))
+    a, b = 0.1, 0.7                                   # (- end start) is rounded in double arithmetic first
+    ys = orc.linspace(a, b, 7)
+    assert ys[3] == float(Fraction(a) + 3 * Fraction(b - a) / 6)
+    from lisp_mcmc_b200.walker import linspace as host_linspace
+    assert np.array_equal(host_linspace(-3.7, 11.9, 1000), orc.linspace(-3.7, 11.9, 1000))
+
+
+def test_data_and_fit_follows_the_list_definition(orc):
+    """walker-get-data-and-fit :1231-1255 restated in C++ == the same definition spelled out on the step list in Python:
+    sort the whole walk by prob (descending), keep ceil(0.66f take) entries, max / min of the model over them"""
+    rng = np.random.default_rng(3)
+    x = np.linspace(-4.0, 10.0, 25)
+    y = 1.0 + 2.0 * x + 0.2 * rng.standard_normal(25)
+    keys = ["b", "m"]
+    text = "(lambda (x &key m b &allow-other-keys) (+ b (* m x)))"
+    ow = orc.Walker(keys, 1)
+    ow.dataset(0, x, y, 0.2)
+    ow.model_sexpr(0, text)
+    ow.init([-1.0, 2.0])
+    ow.adaptive_steps_full(n=700, temperature=10)
+    th, pr = ow.trace(0)                               # newest first
+    fn = orc.Fn(text, keys)
+    for take, which in [(100, "most-likely"), (150, "median"), (333, "median"), (10**6, "most-likely")]:
+        xf, mx, mn, yf, par = ow.data_and_fit(take=take, which_solution=which, n_fit=40)
+        tk = min(take, len(pr))
+        if which == "most-likely":
+            k = tk - 1 - int(np.argmax(pr[:tk][::-1]))   # of equal maxima the oldest
+            ref_par = th[k]
+        else:
+            s = np.sort(th[:tk], axis=0)
+            pos, rem = divmod(50 * (tk - 1), 100)
+            ref_par = s[pos] if rem == 0 else (s[pos] + s[pos + 1]) / 2
+        assert np.array_equal(par, ref_par)
+        M = int(np.ceil(np.float32(0.66) * np.float32(tk)))
+        order = np.argsort(-pr, kind="stable")[:M]
+        ys = np.array([[fn.model(xx, th[j]) for j in order] for xx in xf])
+        assert np.array_equal(mx, ys.max(axis=1)) and np.array_equal(mn, ys.min(axis=1))
+        assert np.array_equal(yf, [fn.model(xx, ref_par) for xx in xf])
+        assert np.array_equal(xf, orc.linspace(-4.0, 10.0, 40))
+    # (* 0.66 take) is a single-float product: take = 150 gives 99.00001 -> 100 steps, where 0.66d0 would give 99
+    assert int(np.ceil(np.float32(0.66) * np.float32(150))) == 100
