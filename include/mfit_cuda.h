@@ -98,6 +98,14 @@ int mfit_problem_define(mfit_ctx* ctx, int n_datasets, int n_params);
 /* :data (list x y) and :data-error of dataset d.  sigma==NULL means data-error 1 (:1144).
  * Stands in for clean-data / clean-data-error / to-double-floats :774-835 (the host flattens). */
 int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, const double* sigma, int64_t n);
+/* Multi-dimensional inputs (walker-create docstring :1137: "x may itself be a sequence"): every x of the :data is a
+ * sequence of x_dims numbers, flattened by the host component-major -- component k of point i at x[k * n + i] -- and
+ * the :function (a lowered lambda, mfit_model_sexpr) reads them with elt / aref / svref / nth / first ... fourth.
+ * x_dims = 0 is mfit_dataset_upload.  A model that uses x as a number on such data, or indexes beyond x_dims, is the
+ * reference's type error: MFIT_ERR_ARG when the chains are initialised. */
+#define MFIT_MAX_XDIMS 8
+int mfit_dataset_upload_xd(mfit_ctx* ctx, int d, const double* x, int x_dims, const double* y, const double* sigma,
+                           int64_t n);
 /* Walker set with per-walker data -- the reference's own many-walker workload (nv-specific.lisp:50-66: one walker per
  * measured spectrum, same :function / priors, `(mapc #'walker-adaptive-steps walkers)`): chain w of W is fitted to its
  * own row of y (W x n row-major) and of x / sigma unless x_shared / sigma_shared say that one n-vector serves all.

@@ -44,6 +44,7 @@ SIGNATURES = {
     "mfit_launch_count": (C.c_int64, [C.c_void_p]),
     "mfit_problem_define": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mfit_dataset_upload": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int64]),
+    "mfit_dataset_upload_xd": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int64]),
     "mfit_dataset_upload_per_walker": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "mfit_model_builtin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_int]),
     "mfit_model_sexpr": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, _cpp, C.c_int]),

@@ -46,6 +46,9 @@ std::string g_create_error;
 
 struct Dataset {
   long long n = -1, n_pad = 0;
+  bool x_is_sequence = false;  // uploaded through mfit_dataset_upload_xd (a one-component sequence is still a sequence)
+  int x_dims = 1;        // components of every x (multi-dimensional inputs :1137); x holds x_dims arrays of n_pad
+  int model_xdims = 0;   // 0: the model takes x as a number; k > 0: it reads components 0 .. k-1 of a sequence
   double *x = nullptr, *y = nullptr, *yw = nullptr, *w = nullptr, *c = nullptr;
   double xmin = 0.0, xmax = 0.0;  // -inf / +inf when some x is not finite
   double cst_normal = 0.0, cst_poisson = 0.0;
@@ -194,6 +197,8 @@ void dataset_free_model(Dataset& d) {
   if (d.lib_model) { cudaLibraryUnload(d.lib_model); d.lib_model = nullptr; }
   d.k_user[0] = d.k_user[1] = d.k_user[2] = nullptr;
   for (auto& k : d.k_user_pc) k = nullptr;
+  d.k_user_fit = nullptr;
+  d.model_xdims = 0;
 }
 
 void workspace_free(Workspace& w) {
@@ -296,6 +301,14 @@ int check_problem_ready(mfit_ctx* ctx) {
     if (s.family < 0) return fail(ctx, MFIT_ERR_STATE, "dataset %d has no model (:function)", d);
     if (s.ll_kind == MFIT_LL_POISSON && !s.poisson_ok)
       return fail(ctx, MFIT_ERR_ARG, "dataset %d: log-poisson needs non-negative integer-valued y (log-factorial :379-380)", d);
+    // the reference would signal a type error inside the model (a sequence used as a number, or the reverse)
+    if (s.x_dims > 1 && s.model_xdims == 0)
+      return fail(ctx, MFIT_ERR_ARG, "dataset %d: x has %d components but the model takes x as a number", d, s.x_dims);
+    if (s.model_xdims > 0 && s.W_pc > 0)
+      return fail(ctx, MFIT_ERR_ARG, "dataset %d: walker sets with per-walker data take a one-dimensional x", d);
+    if (s.model_xdims > s.x_dims || (s.model_xdims > 0 && !s.x_is_sequence))
+      return fail(ctx, MFIT_ERR_ARG, "dataset %d: the model reads %d components of x, the data have %s%d", d, s.model_xdims,
+                  s.x_is_sequence ? "" : "a plain number, not a sequence of ", s.x_dims);
   }
   return 0;
 }
@@ -306,6 +319,7 @@ void fill_eval_args(MfitEvalArgs& a, const Dataset& s, const Workspace& w, int d
   memset(&a, 0, sizeof a);
   a.x = s.x; a.y = s.y; a.yw = s.yw; a.w = s.w; a.c = s.c;
   a.n = s.n;
+  a.xd_stride = s.n_pad;
   a.xmin = s.xmin;
   a.xmax = s.xmax;
   a.tiles_per_seg = s.tiles_per_seg;
@@ -390,7 +404,7 @@ int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, c
   Dataset& s = ctx->ds[ds[0]];
   const void* fn = shared_data_kernel(s);
   if (!fn) return fail(ctx, MFIT_ERR_STATE, "no kernel for dataset %d (family %d degree %d)", ds[0], s.family, s.degree);
-  const size_t smem = mfit_eval_smem_bytes(s.ll_kind);
+  const size_t smem = mfit_eval_smem_bytes(s.ll_kind, s.model_xdims > 0 ? s.model_xdims : 1);
   auto it = ctx->resident.find(fn);
   if (it == ctx->resident.end()) {  // persistent grid = CTAs resident at once (occupancy x SMs), queried once per kernel
     // static (math tables) + dynamic (TMA ring) shared memory may exceed the 48 KB default together
@@ -855,15 +869,26 @@ int mfit_problem_define(mfit_ctx* ctx, int n_datasets, int n_params) {
   if ((d) < 0 || (d) >= ctx->D) return fail(ctx, MFIT_ERR_ARG, "dataset index %d out of range", (d))
 
 int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, const double* sigma, int64_t n) {
+  return mfit_dataset_upload_xd(ctx, d, x, 0, y, sigma, n);
+}
+
+// x_dims = 0: every x is a number; x_dims >= 1: every x is a sequence of x_dims numbers, component k of point i at
+// x[k * n + i]
+int mfit_dataset_upload_xd(mfit_ctx* ctx, int d, const double* x, int x_dims, const double* y, const double* sigma, int64_t n) {
   NEED_DS(d);
   if (n < 0 || (n > 0 && (!x || !y))) return fail(ctx, MFIT_ERR_ARG, "dataset %d: bad x/y/n", d);
+  if (x_dims < 0 || x_dims > MFIT_MAX_XDIMS) return fail(ctx, MFIT_ERR_ARG, "dataset %d: x_dims must be 0 .. %d", d, MFIT_MAX_XDIMS);
   CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   Dataset& s = ctx->ds[d];
   dataset_free_data(s);
   s.n = n;
   s.n_pad = round_up(n > 0 ? n : 1, MFIT_TILE);
-  std::vector<double> w((size_t)s.n_pad, 0.0), cc((size_t)s.n_pad, 0.0), xx((size_t)s.n_pad, 0.0), yy((size_t)s.n_pad, 0.0),
+  s.x_is_sequence = x_dims > 0;
+  s.x_dims = x_dims > 0 ? x_dims : 1;
+  std::vector<double> w((size_t)s.n_pad, 0.0), cc((size_t)s.n_pad, 0.0), xx((size_t)s.n_pad * s.x_dims, 0.0), yy((size_t)s.n_pad, 0.0),
       yw((size_t)s.n_pad, 0.0);
+  for (int k = 1; k < s.x_dims; k++)
+    for (long long i = 0; i < n; i++) xx[(size_t)k * s.n_pad + i] = x[(size_t)k * n + i];
   double xmin = INFINITY, xmax = -INFINITY;
   bool x_finite = true;
   const double a = -0.5 * std::log(2.0 * 3.141592653589793);  // (* -1/2 (log (* 2 pi))) :377
@@ -892,13 +917,16 @@ int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, 
       }
     }
   }
-  s.xmin = x_finite && n > 0 ? xmin : -INFINITY;
-  s.xmax = x_finite && n > 0 ? xmax : INFINITY;
+  s.xmin = x_finite && n > 0 && !s.x_is_sequence ? xmin : -INFINITY;
+  s.xmax = x_finite && n > 0 && !s.x_is_sequence ? xmax : INFINITY;
   s.cst_normal = cst;
   s.cst_poisson = pcst;
   s.poisson_ok = pois_ok;
   const size_t bytes = sizeof(double) * (size_t)s.n_pad;
-  CU(cudaMalloc(&s.x, bytes)); CU(cudaMalloc(&s.y, bytes)); CU(cudaMalloc(&s.yw, bytes)); CU(cudaMalloc(&s.w, bytes));
+  CU(cudaMalloc(&s.x, bytes * s.x_dims));
+  if (s.x_dims > 1)
+    CU(cudaMemcpyAsync(s.x + s.n_pad, xx.data() + s.n_pad, bytes * (s.x_dims - 1), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMalloc(&s.y, bytes)); CU(cudaMalloc(&s.yw, bytes)); CU(cudaMalloc(&s.w, bytes));
   CU(cudaMalloc(&s.c, bytes));
   CU(cudaMemcpyAsync(s.x, xx.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(s.y, yy.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -920,6 +948,8 @@ int mfit_dataset_upload_per_walker(mfit_ctx* ctx, int d, const double* x, const 
   dataset_free_data(s);
   s.n = n;
   s.n_pad = round_up(n > 0 ? n : 1, 32);
+  s.x_dims = 1;
+  s.x_is_sequence = false;
   s.W_pc = W;
   s.x_shared = x_shared != 0;
   s.sigma_shared = sigma_shared != 0 || sigma == nullptr;
@@ -995,6 +1025,7 @@ int mfit_model_builtin(mfit_ctx* ctx, int d, int family, int degree, const int32
   dataset_free_model(s);
   s.family = family;
   s.degree = degree;
+  s.model_xdims = 0;
   return 0;
 }
 
@@ -1008,7 +1039,8 @@ int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* 
   if (!lambda_text || n_keys != ctx->P) return fail(ctx, MFIT_ERR_ARG, "need the lambda text and exactly P=%d key names", ctx->P);
   CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   std::string code, e;
-  int rc = mfit_lower_to_string(lambda_text, key_names, n_keys, 0, code, e);
+  int model_xdims = 0;
+  int rc = mfit_lower_to_string(lambda_text, key_names, n_keys, 0, code, e, &model_xdims);
   if (rc) return fail(ctx, rc, "%s", e.c_str());
   std::vector<char> cubin;
   rc = mfit_nvrtc_compile(mfit_user_model_source(code), cubin, e);
@@ -1029,6 +1061,7 @@ int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* 
   CU(cudaLibraryGetKernel(&s.k_user_fit, s.lib_model, "mfit_user_fit_envelope"));
   s.family = MFIT_FAM_SEXPR;
   s.degree = 0;
+  s.model_xdims = model_xdims;
   return 0;
 }
 
@@ -1531,6 +1564,7 @@ int mfit_fit_envelope(mfit_ctx* ctx, int d, int64_t take, int which_solution, co
   Dataset& s = ctx->ds[d];
   const void* fn = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_fit : mfit_builtin_fit_kernel(s.family, s.degree);
   if (!fn) return fail(ctx, MFIT_ERR_STATE, "dataset %d has no model", d);
+  if (s.model_xdims > 0) return fail(ctx, MFIT_ERR_ARG, "dataset %d: the fit curve needs a model of a one-dimensional x", d);
   MfitChains& c = ctx->ch;
   if (take > c.cap) take = c.cap;  // no chain holds more rows than the ring
   const size_t W = (size_t)c.W, P = (size_t)c.P;

@@ -49,7 +49,7 @@ int mfit_family_nparams(int family, int degree) {
   return -1;
 }
 
-size_t mfit_eval_smem_bytes(int ll) {
-  int narr = ll == MFIT_LL_NORMAL ? 3 : ll == MFIT_LL_NORMAL_CUTOFF ? 4 : 2;
+size_t mfit_eval_smem_bytes(int ll, int x_dims) {
+  int narr = (ll == MFIT_LL_NORMAL ? 3 : ll == MFIT_LL_NORMAL_CUTOFF ? 4 : 2) + x_dims - 1;
   return (size_t)MFIT_STAGES * narr * MFIT_TILE * 8 + 2 * MFIT_STAGES * 8 + MFIT_QN * 4;
 }

@@ -224,6 +224,9 @@ struct Lower {
   bool fast_math = false;  // model lambdas: exp/log/sin/cos -> mfit_math.cuh (prior kernels keep libdevice)
   int uses = 0;            // MFIT_USES_* tables the lowered code needs
   bool guarded = false;    // some fast routine with a restricted domain is called
+  std::string x_name;      // the model's positional argument
+  int x_dims = 0;          // > 0: x is a sequence and components 0 .. x_dims - 1 are read (elt / aref / nth / first ...)
+  bool x_scalar = false;   // x is used as a number
 
   std::string fresh(const char* stem) { return std::string(stem) + std::to_string(tmp++); }
 
@@ -519,6 +522,13 @@ struct Lower {
     return acc;
   }
 
+  // the symbol names the model's positional argument and is not shadowed by a let binding
+  bool is_x(const Sx& s) const {
+    if (s.t != Sx::SYM || x_name.empty() || s.sym != x_name) return false;
+    auto it = scope.find(s.sym);
+    return it != scope.end() && it->second.size() == 1 && it->second.back().code == "x";
+  }
+
   Ex lower(const Sx& s) {
     if (s.t == Sx::NUM) {
       if (s.nk == 0) return mk_rat(s.num, s.den);
@@ -531,6 +541,10 @@ struct Lower {
       if (s.sym == "NIL") return mk_bool(false);
       auto it = scope.find(s.sym);
       if (it == scope.end() || it->second.empty()) throw Err("unbound variable " + s.sym);
+      if (is_x(s)) {
+        if (x_dims > 0) throw Err("x is used both as a number and as a sequence");
+        x_scalar = true;
+      }
       return it->second.back();
     }
     if (s.kids.empty()) return mk_bool(false);
@@ -541,6 +555,29 @@ struct Lower {
       if (na < lo || na > hi) throw Err("wrong number of arguments to " + f);
     };
     if (f == "THE") { need(2, 2); return lower(s.kids[2]); }
+    {
+      // multi-dimensional inputs (walker-create docstring, mcmc-fitting.lisp:1137): x is itself a sequence and the model
+      // reads its components -- each becomes one more shared-memory-staged data array (xv[k] in the lowered code)
+      static const struct { const char* name; int fixed; } acc[] = {
+          {"ELT", -1}, {"AREF", -1}, {"SVREF", -1}, {"NTH", -2}, {"FIRST", 0}, {"SECOND", 1}, {"THIRD", 2},
+          {"FOURTH", 3}, {"CAR", 0}, {"CADR", 1}, {"CADDR", 2}};
+      for (auto& a : acc)
+        if (f == a.name) {
+          const bool fixed = a.fixed >= 0;
+          need(fixed ? 1 : 2, fixed ? 1 : 2);
+          if (!is_x(s.kids[a.fixed == -2 ? 2 : 1])) throw Err(f + ": only the model's positional argument can be indexed");
+          i64 idx = a.fixed;
+          if (!fixed) {
+            const Sx& ix = s.kids[a.fixed == -2 ? 1 : 2];
+            if (ix.t != Sx::NUM || ix.nk != 0 || ix.den != 1 || ix.num < 0) throw Err(f + ": the index must be a literal non-negative integer");
+            idx = ix.num;
+          }
+          if (idx >= MFIT_MAX_XDIMS) throw Err(f + ": at most " + std::to_string(MFIT_MAX_XDIMS) + " components of x are supported");
+          if (x_scalar) throw Err("x is used both as a number and as a sequence");
+          if ((int)idx + 1 > x_dims) x_dims = (int)idx + 1;
+          return mk(T_DBL, "xv[" + std::to_string(idx) + "]");
+        }
+    }
     if (f == "DECLARE") return mk_bool(false);
     if (f == "PROGN") return body(s, 1);
     if (f == "LET") return lower_let(s, false);
@@ -730,7 +767,7 @@ struct Parsed {
   size_t body_from = 0;
 };
 
-std::string lower_text(const char* text, const char* const* key_names, int n_keys, int kind) {
+std::string lower_text(const char* text, const char* const* key_names, int n_keys, int kind, int* x_dims_out = nullptr) {
   Reader rd{text};
   Sx top = rd.read();
   if (top.t != Sx::LIST || top.kids.size() < 3 || top.kids[0].t != Sx::SYM) throw Err("expected (lambda (args) body)");
@@ -773,6 +810,7 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
   std::string out;
   if (kind == 0) {
     if (positional.size() != 1) throw Err("a model lambda takes exactly one positional argument (x)");
+    L.x_name = positional[0];
     L.bind(positional[0], mk(T_DBL, "x"));
   } else {
     if (positional.size() != 2) throw Err("a prior lambda takes (params data)");
@@ -796,15 +834,21 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
   }
   std::string stmts;
   for (auto& sline : pre) stmts += "    " + sline + "\n";
+  if (x_dims_out) *x_dims_out = kind == 0 ? L.x_dims : 0;
   if (kind == 0) {
     // a user model carries no proof about its arguments (safe() is false): its fast routines always run guarded
     out += "struct MfitUser {\n  static constexpr int USES = " + std::to_string(L.uses) + ";\n";
-    out += std::string("  static constexpr bool GUARDED = ") + (L.guarded ? "true" : "false") + ";\n" + decls;
+    out += std::string("  static constexpr bool GUARDED = ") + (L.guarded ? "true" : "false") + ";\n";
+    out += "  static constexpr int XDIMS = " + std::to_string(L.x_dims > 0 ? L.x_dims : 1) + ";\n";
+    out += std::string("  static constexpr bool XVEC = ") + (L.x_dims > 0 ? "true" : "false") + ";\n" + decls;
     out += "  __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {\n";
     out += "    const double* theta = a.theta; const long long stride = a.stride;\n    (void)theta; (void)stride; (void)chain;\n" + loads + "  }\n";
     out += "  __device__ __forceinline__ void setup() {}\n";
     out += "  __device__ __forceinline__ bool safe(const MfitEvalArgs&) const { return false; }\n";
-    out += "  template <bool SLOW, class G>\n  __device__ __forceinline__ double eval(double x, G& gd) const {\n    (void)x; (void)gd;\n" + stmts + "    return " + ret + ";\n  }\n};\n";
+    if (L.x_dims > 0)
+      out += "  template <bool SLOW, class G>\n  __device__ __forceinline__ double evalv(const double (&xv)[XDIMS], G& gd) const {\n    (void)xv; (void)gd;\n" + stmts + "    return " + ret + ";\n  }\n};\n";
+    else
+      out += "  template <bool SLOW, class G>\n  __device__ __forceinline__ double eval(double x, G& gd) const {\n    (void)x; (void)gd;\n" + stmts + "    return " + ret + ";\n  }\n};\n";
   } else {
     out += "__device__ __forceinline__ double mfit_user_prior(const double* theta, long long stride, long long chain) {\n";
     out += "  (void)theta; (void)stride; (void)chain;\n";
@@ -840,9 +884,9 @@ extern "C" int mfit_lower_sexpr(const char* lambda_text, const char* const* key_
 
 // C++ face used by api.cu
 int mfit_lower_to_string(const char* text, const char* const* keys, int n_keys, int kind, std::string& out,
-                         std::string& err) {
+                         std::string& err, int* x_dims) {
   try {
-    out = lower_text(text, keys, n_keys, kind);
+    out = lower_text(text, keys, n_keys, kind, x_dims);
     return 0;
   } catch (std::exception& e) {
     err = e.what();

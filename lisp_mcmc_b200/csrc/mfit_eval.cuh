@@ -50,7 +50,7 @@
 #define MFITK_POISSON 2
 
 struct MfitEvalArgs {
-  const double* x;      /* [n_pad] */
+  const double* x;      /* [n_pad]; multi-dimensional inputs: component k at x + k * xd_stride */
   const double* y;      /* [n_pad]                      (cutoff, poisson) */
   const double* yw;     /* [n_pad] y_i/sigma_i          (normal) */
   const double* w;      /* [n_pad] 1/sigma_i            (normal, cutoff) */
@@ -69,6 +69,7 @@ struct MfitEvalArgs {
   /* walker sets with per-walker data (mfit_eval_perchain_body): chain w reads x + w * x_stride (0: one x for all),
    * y / yw + w * pc_stride, w / c + w * w_stride; chains [cb0 * MFIT_CB, (cb0 + n_cb) * MFIT_CB) of this launch */
   long long x_stride, pc_stride, w_stride;  /* w_stride: rows of w / c (0: one sigma vector for all chains) */
+  long long xd_stride;  /* distance between the component arrays of a multi-dimensional x (n_pad) */
   int idx[MFIT_MAXK];   /* built-in families: family slot -> shared parameter index */
   int degree;
 };
@@ -171,6 +172,28 @@ struct MfitTerm<MFITK_POISSON> {
 #ifndef MFIT_UNROLL_PAIRS
 #define MFIT_UNROLL_PAIRS 2
 #endif
+// f(x_i) for a model whose x is a number (eval) or a sequence of Model::XDIMS components (evalv; the component arrays
+// of a stage lie MFIT_TILE apart)
+template <class Model, bool SLOW, class G>
+__device__ __forceinline__ double mfit_model_at(const Model& m, const double* xs, int i, G& gd) {
+  if constexpr (Model::XVEC) {
+    double xv[Model::XDIMS];
+#pragma unroll
+    for (int d = 0; d < Model::XDIMS; d++) xv[d] = xs[d * MFIT_TILE + i];
+    return m.template evalv<SLOW>(xv, gd);
+  } else {
+    return m.template eval<SLOW>(xs[i], gd);
+  }
+}
+
+// f(x) for the kernels that only take a number for x (walker sets with per-walker data, the fit envelope); the host
+// refuses to launch them for a model that reads x as a sequence
+template <class Model, bool SLOW, class G>
+__device__ __forceinline__ double mfit_model_scalar(const Model& m, double x, G& gd) {
+  if constexpr (Model::XVEC) return __longlong_as_double(0x7ff8000000000000LL);
+  else return m.template eval<SLOW>(x, gd);
+}
+
 template <class Model, int LL, bool SLOW, int NC, class G>
 __device__ __forceinline__ void mfit_tile_pass(const Model* m, const double* xs, const double* ys, const double* ws,
                                                const double* cs, int cnt, double* acc, G* gd) {
@@ -182,20 +205,38 @@ __device__ __forceinline__ void mfit_tile_pass(const Model* m, const double* xs,
   constexpr int UNROLL = MFIT_UNROLL_PAIRS * (NC == 1 ? 2 : 1);
 #pragma unroll UNROLL
   for (int i = 0; i < pairs; i++) {
-    const double2 xv = x2[i], yv = y2[i], wv = w2[i], cv = c2[i];
+    const double2 yv = y2[i], wv = w2[i], cv = c2[i];
+    if constexpr (Model::XVEC) {
+      double xa[Model::XDIMS], xb[Model::XDIMS];
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const double f0 = m[c].template eval<SLOW>(xv.x, gd[c]);
-      const double f1 = m[c].template eval<SLOW>(xv.y, gd[c]);
-      acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], f0, yv.x, wv.x, cv.x, gd[c]);
-      acc[2 * c + 1] = MfitTerm<LL>::template add<SLOW>(acc[2 * c + 1], f1, yv.y, wv.y, cv.y, gd[c]);
+      for (int d = 0; d < Model::XDIMS; d++) {
+        const double2 xv = x2[d * (MFIT_TILE / 2) + i];
+        xa[d] = xv.x;
+        xb[d] = xv.y;
+      }
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        const double f0 = m[c].template evalv<SLOW>(xa, gd[c]);
+        const double f1 = m[c].template evalv<SLOW>(xb, gd[c]);
+        acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], f0, yv.x, wv.x, cv.x, gd[c]);
+        acc[2 * c + 1] = MfitTerm<LL>::template add<SLOW>(acc[2 * c + 1], f1, yv.y, wv.y, cv.y, gd[c]);
+      }
+    } else {
+      const double2 xv = x2[i];
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        const double f0 = m[c].template eval<SLOW>(xv.x, gd[c]);
+        const double f1 = m[c].template eval<SLOW>(xv.y, gd[c]);
+        acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], f0, yv.x, wv.x, cv.x, gd[c]);
+        acc[2 * c + 1] = MfitTerm<LL>::template add<SLOW>(acc[2 * c + 1], f1, yv.y, wv.y, cv.y, gd[c]);
+      }
     }
   }
   if (cnt & 1) {
     const int i = cnt - 1;
 #pragma unroll
     for (int c = 0; c < NC; c++)
-      acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], m[c].template eval<SLOW>(xs[i], gd[c]), ys[i], ws[i], cs[i], gd[c]);
+      acc[2 * c] = MfitTerm<LL>::template add<SLOW>(acc[2 * c], mfit_model_at<Model, SLOW>(m[c], xs, i, gd[c]), ys[i], ws[i], cs[i], gd[c]);
   }
 }
 
@@ -242,7 +283,9 @@ __device__ __forceinline__ void mfit_tile(const Model* m, bool unguarded, const 
 // operands); with MULTI the per-item data set index makes them indexed loads, which costs the one-data-set case 5 %.
 template <class Model, int LL, bool MULTI>
 __device__ __forceinline__ void mfit_eval_body_t(const MfitMultiArgs& ma) {
-  constexpr int NARR = MfitTerm<LL>::NARR;
+  constexpr int XD = Model::XDIMS;                  // component arrays of x (1 unless x is a sequence)
+  constexpr int LNARR = MfitTerm<LL>::NARR;          // x, y, [w, [c]] as the likelihood term counts them
+  constexpr int NARR = LNARR + XD - 1;               // arrays per stage: XD of x, then y, w, c
   constexpr unsigned STAGE_BYTES = NARR * MFIT_TILE * 8u;
   extern __shared__ __align__(128) unsigned char mfit_smem[];
   double* buf = reinterpret_cast<double*>(mfit_smem);
@@ -303,10 +346,11 @@ __device__ __forceinline__ void mfit_eval_body_t(const MfitMultiArgs& ma) {
     const long long off = ((long long)p_seg * a.tiles_per_seg + p_k) * (long long)MFIT_TILE;
     double* dst = buf + (size_t)s * NARR * MFIT_TILE;
     mfit_mbar_expect_tx(&full[s], STAGE_BYTES);
-    mfit_tma_load_1d(dst, a.x + off, MFIT_TILE * 8u, &full[s]);
-    mfit_tma_load_1d(dst + MFIT_TILE, (LL == MFITK_NORMAL ? a.yw : a.y) + off, MFIT_TILE * 8u, &full[s]);
-    if (NARR > 2) mfit_tma_load_1d(dst + 2 * MFIT_TILE, a.w + off, MFIT_TILE * 8u, &full[s]);
-    if (NARR > 3) mfit_tma_load_1d(dst + 3 * MFIT_TILE, a.c + off, MFIT_TILE * 8u, &full[s]);
+#pragma unroll
+    for (int d = 0; d < XD; d++) mfit_tma_load_1d(dst + d * MFIT_TILE, a.x + d * a.xd_stride + off, MFIT_TILE * 8u, &full[s]);
+    mfit_tma_load_1d(dst + XD * MFIT_TILE, (LL == MFITK_NORMAL ? a.yw : a.y) + off, MFIT_TILE * 8u, &full[s]);
+    if (LNARR > 2) mfit_tma_load_1d(dst + (XD + 1) * MFIT_TILE, a.w + off, MFIT_TILE * 8u, &full[s]);
+    if (LNARR > 3) mfit_tma_load_1d(dst + (XD + 2) * MFIT_TILE, a.c + off, MFIT_TILE * 8u, &full[s]);
     issued++;
     if (++p_k == p_nt) fetch_item();
   };
@@ -375,9 +419,9 @@ __device__ __forceinline__ void mfit_eval_body_t(const MfitMultiArgs& ma) {
       mfit_mbar_wait(&full[s], (consumed / MFIT_STAGES) & 1u);
       if (any_live) {
         const double* xs = buf + (size_t)s * NARR * MFIT_TILE;
-        const double* ys = xs + MFIT_TILE;
-        const double* ws = xs + (NARR > 2 ? 2 : 0) * MFIT_TILE;
-        const double* cs = xs + (NARR > 3 ? 3 : 0) * MFIT_TILE;
+        const double* ys = xs + XD * MFIT_TILE;
+        const double* ws = xs + (LNARR > 2 ? XD + 1 : 0) * MFIT_TILE;
+        const double* cs = xs + (LNARR > 3 ? XD + 2 : 0) * MFIT_TILE;
         long long rem = a.n - (t0 + k) * (long long)MFIT_TILE;
         const int cnt = rem < MFIT_TILE ? (int)rem : MFIT_TILE;
         if (two) mfit_tile<Model, LL, 2>(m, unguarded, xs, ys, ws, cs, cnt, acc);
@@ -452,7 +496,7 @@ __device__ __forceinline__ double mfit_perchain_pass(const Model& m, const doubl
         const double x = STAGED ? xs[j] : xv[u];
         const double w = STAGED ? (NARR > 2 ? ws[j] : 0.0) : wv[u];
         const double c = STAGED ? (NARR > 3 ? cs[j] : 0.0) : cv[u];
-        const double f = m.template eval<SLOW>(x, gd);
+        const double f = mfit_model_scalar<Model, SLOW>(m, x, gd);
         acc[u & 3] = MfitTerm<LL>::template add<SLOW>(acc[u & 3], f, yv[u], w, c, gd);
       }
     }
@@ -536,8 +580,8 @@ __device__ __forceinline__ void mfit_eval_perchain_body_t(const MfitEvalArgs& a)
           const long long j = i0 + 32 * u + lane;
           if (j < a.n) {
             const double w = NARR > 2 ? ws[j] : 0.0, c = NARR > 3 ? cs[j] : 0.0;
-            if (unguarded) acc[u & 3] = MfitTerm<LL>::template add<false>(acc[u & 3], m.template eval<false>(xs[j], ng), ycur[u], w, c, ng);
-            else acc[u & 3] = MfitTerm<LL>::template add<false>(acc[u & 3], m.template eval<false>(xs[j], gd), ycur[u], w, c, gd);
+            if (unguarded) acc[u & 3] = MfitTerm<LL>::template add<false>(acc[u & 3], mfit_model_scalar<Model, false>(m, xs[j], ng), ycur[u], w, c, ng);
+            else acc[u & 3] = MfitTerm<LL>::template add<false>(acc[u & 3], mfit_model_scalar<Model, false>(m, xs[j], gd), ycur[u], w, c, gd);
           }
         }
 #pragma unroll
@@ -612,7 +656,7 @@ __device__ __forceinline__ void mfit_fit_envelope_body(const MfitFitArgs& f) {
     m.setup();
 #pragma unroll
     for (int u = 0; u < MFIT_FIT_PTS; u++) {
-      const double v = m.template eval<true>(x[u], ng);
+      const double v = mfit_model_scalar<Model, true>(m, x[u], ng);
       if (j == 0) { mx[u] = v; mn[u] = v; }       // (reduce #'max y) starts from the first element
       else { mx[u] = v > mx[u] ? v : mx[u]; mn[u] = v < mn[u] ? v : mn[u]; }
     }
@@ -623,7 +667,7 @@ __device__ __forceinline__ void mfit_fit_envelope_body(const MfitFitArgs& f) {
     const int i = i0 + u * MFIT_FIT_THREADS;
     if (i < f.n_fit) {
       const size_t o = (size_t)wl * f.n_fit + i;
-      f.yfit[o] = m_next.template eval<true>(x[u], ng);
+      f.yfit[o] = mfit_model_scalar<Model, true>(m_next, x[u], ng);
       f.ymax[o] = mx[u];
       f.ymin[o] = mn[u];
     }

@@ -12,7 +12,7 @@
 // eval_builtin.cu
 const void* mfit_builtin_eval_kernel(int family, int degree, int ll);
 int mfit_family_nparams(int family, int degree);
-size_t mfit_eval_smem_bytes(int ll);
+size_t mfit_eval_smem_bytes(int ll, int x_dims);
 // eval_perchain.cu
 const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int staged);
 
@@ -20,8 +20,9 @@ const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int sta
 const void* mfit_builtin_fit_kernel(int family, int degree);
 
 // lower.cpp
+// x_dims (may be null): 0 when the model uses x as a number, else the number of components of x it reads
 int mfit_lower_to_string(const char* text, const char* const* keys, int n_keys, int kind, std::string& out,
-                         std::string& err);
+                         std::string& err, int* x_dims = nullptr);
 // nvrtc_glue.cpp
 std::string mfit_user_model_source(const std::string& model_struct);
 std::string mfit_user_prior_source(const std::string& prior_fn);

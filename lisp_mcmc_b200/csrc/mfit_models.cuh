@@ -17,6 +17,8 @@
 //                    (NaN parameters make every comparison false -> not safe -> guarded path -> libdevice redo)
 //   eval<SLOW>(x,gd) the model function
 //   GUARDED          whether eval uses a fast routine with a restricted domain at all
+//   XDIMS, XVEC      components of x the model reads; XVEC: x is a sequence and the model provides evalv(xv[XDIMS], gd)
+//                    instead of eval (lowered user models only, csrc/lower.cpp)
 
 __device__ __forceinline__ double mfit_absmax(double u, double v) { return fmax(fabs(u), fabs(v)); }
 
@@ -24,6 +26,8 @@ __device__ __forceinline__ double mfit_absmax(double u, double v) { return fmax(
 template <int D>
 struct MfitPoly {
   static constexpr int USES = 0;
+  static constexpr int XDIMS = 1;
+  static constexpr bool XVEC = false;
   static constexpr bool GUARDED = false;
   double c[D + 1];
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
@@ -44,6 +48,8 @@ struct MfitPoly {
 // f = a exp(b x) + c
 struct MfitExpo {
   static constexpr int USES = MFIT_USES_EXP;
+  static constexpr int XDIMS = 1;
+  static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
   double a_, b_, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
@@ -58,6 +64,8 @@ struct MfitExpo {
 // f = a sin(omega x + phi) + c
 struct MfitSinus {
   static constexpr int USES = 0;
+  static constexpr int XDIMS = 1;
+  static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
   double a_, om, ph, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
@@ -75,6 +83,8 @@ struct MfitSinus {
 // 7 FP64 instructions per point, 9 with the log-normal term.
 struct MfitLorentz {
   static constexpr int USES = 0;
+  static constexpr int XDIMS = 1;
+  static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
   double ag2, x0, g2, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
@@ -104,6 +114,8 @@ struct MfitLorentz {
 // (tools/probe/horner_probe.cu: 56 against 63 DFMA/clk/SM; loop_probe: 9.98e11 against 1.03e12 point-evals/s).
 struct MfitGaussLin {
   static constexpr int USES = MFIT_USES_EXP;
+  static constexpr int XDIMS = 1;
+  static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
   double a_, mu, isq, b0, b1;  // load() leaves s in isq
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
@@ -132,6 +144,8 @@ struct MfitGaussLin {
 template <int K>
 struct MfitNvMulti {
   static constexpr int USES = 0;
+  static constexpr int XDIMS = 1;
+  static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
   double sg[K], mu[K], g2, bg0;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {

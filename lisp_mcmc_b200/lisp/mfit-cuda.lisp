@@ -50,6 +50,8 @@
 (cffi:defcfun ("mfit_problem_define" %problem-define) :int (ctx :pointer) (n-datasets :int) (n-params :int))
 (cffi:defcfun ("mfit_dataset_upload" %dataset-upload) :int
   (ctx :pointer) (d :int) (x :pointer) (y :pointer) (sigma :pointer) (n :int64))
+(cffi:defcfun ("mfit_dataset_upload_xd" %dataset-upload-xd) :int
+  (ctx :pointer) (d :int) (x :pointer) (x-dims :int) (y :pointer) (sigma :pointer) (n :int64))
 (cffi:defcfun ("mfit_dataset_upload_per_walker" %dataset-upload-per-walker) :int
   (ctx :pointer) (d :int) (x :pointer) (y :pointer) (sigma :pointer) (n :int64) (w :int64) (x-shared :int) (sigma-shared :int))
 (cffi:defcfun ("mfit_model_builtin" %model-builtin) :int
@@ -252,10 +254,18 @@ lists in :params order) gives each chain its own start; SEED keys the Philox str
       (setf ctx (cffi:mem-ref out :pointer)))
     (chk ctx (%problem-define ctx d-count p))
     (loop for d from 0 for f in function for set in data for e in data-error do
-      (with-doubles (x (first set))
-        (with-doubles (y (second set))
-          (with-doubles (s e)
-            (chk ctx (%dataset-upload ctx d x y s (length (second set)))))))
+      (let* ((xs (first set))
+             ;; multi-dimensional inputs (:1137): every x is itself a sequence -> component-major for the device
+             (x-dims (if (and (plusp (length xs)) (typep (elt xs 0) 'sequence)) (length (elt xs 0)) 0))
+             (flat (if (plusp x-dims)
+                       (loop for k below x-dims append (map 'list (lambda (xi) (elt xi k)) xs))
+                       xs)))
+        (with-doubles (x flat)
+          (with-doubles (y (second set))
+            (with-doubles (s e)
+              (chk ctx (if (plusp x-dims)
+                           (%dataset-upload-xd ctx d x x-dims y s (length (second set)))
+                           (%dataset-upload ctx d x y s (length (second set)))))))))
       (set-function ctx d f keys)
       (chk ctx (%likelihood-set ctx d (likelihood-kind (nth d ll))))
       (set-prior ctx d (nth d lp) keys))

@@ -92,9 +92,9 @@ def clean_data(data, n_functions):
     `error` when the shape does not match the number of functions."""
     depth = get_depth(data)
     if depth == 2:
-        sets = [data]
-    elif depth == 3:
-        sets = list(data)
+        sets = [data]                                  # :818
+    elif depth >= 3:
+        sets = list(data)                              # :820 (depth 4: sets whose x are sequences, :1137)
     else:
         raise ValueError("data must be (x y) or a list of (x y) sets, got depth %d" % depth)
     if len(sets) != n_functions:
@@ -104,8 +104,9 @@ def clean_data(data, n_functions):
         if len(s) < 2:
             raise ValueError("each data set needs x and y")
         x, y = _f64(s[0]), _f64(s[1])
-        if x.ndim != 1 or x.shape != y.shape:
-            raise ValueError("x and y must be flat and of equal length")
+        # multi-dimensional inputs (:1137): every x may itself be a sequence (x1 x2 ...) -> x is n x K
+        if x.ndim not in (1, 2) or y.ndim != 1 or x.shape[0] != y.shape[0]:
+            raise ValueError("x and y must be of equal length (x: numbers, or sequences of equal length)")
         out.append((x, y))
     return out
 
@@ -236,7 +237,11 @@ class Walker:
             elif self.dataset_owners is None or self.dataset_owners[d] == self.rank:
                 x, y = self.data[d]
                 e = self.data_error[d]
-                self._chk(L.mfit_dataset_upload(h, d, _ptr(x), _ptr(y), _ptr(e), len(x)))
+                if x.ndim == 2:      # component-major for the device: one array per component of x
+                    xt = np.ascontiguousarray(x.T)
+                    self._chk(L.mfit_dataset_upload_xd(h, d, _ptr(xt), x.shape[1], _ptr(y), _ptr(e), len(y)))
+                else:
+                    self._chk(L.mfit_dataset_upload(h, d, _ptr(x), _ptr(y), _ptr(e), len(x)))
             self._set_function(d, self.function[d])
             kind = _LL.get(self.log_liklihood[d])
             if kind is None:

@@ -53,6 +53,7 @@ typedef struct orc_fn orc_fn;
 orc_fn* orc_fn_parse(const char* text, const char* const* keys, int P, char* err, int errlen);
 void orc_fn_free(orc_fn* f);
 double orc_fn_call_model(orc_fn* f, double x, const double* theta);
+double orc_fn_call_model_v(orc_fn* f, const double* x, int xdim, const double* theta);
 double orc_fn_call_prior(orc_fn* f, const double* theta);
 
 /* temperature schedule, :875-878 */
@@ -64,6 +65,8 @@ typedef struct orc_walker orc_walker;
 orc_walker* orc_walker_new(int D, int P);
 void orc_walker_free(orc_walker* w);
 int orc_walker_dataset(orc_walker* w, int d, const double* x, const double* y, const double* sigma, long n);
+/* multi-dimensional inputs (:1137): every x is a sequence of xd numbers, x[i*xd + k]; s-expression models only */
+int orc_walker_dataset_xd(orc_walker* w, int d, const double* x, int xd, const double* y, const double* sigma, long n);
 int orc_walker_model_builtin(orc_walker* w, int d, int family, int degree, const int* idx, int n_idx);
 int orc_walker_model_sexpr(orc_walker* w, int d, const char* text, const char* const* keys);
 int orc_walker_likelihood(orc_walker* w, int d, int kind);

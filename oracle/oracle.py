@@ -70,6 +70,9 @@ def lib():
         L.orc_fn_free.argtypes = [C.c_void_p]
         L.orc_fn_call_model.restype = C.c_double
         L.orc_fn_call_model.argtypes = [C.c_void_p, C.c_double, _dp]
+        L.orc_fn_call_model_v.restype = C.c_double
+        L.orc_fn_call_model_v.argtypes = [C.c_void_p, _dp, C.c_int, _dp]
+        L.orc_walker_dataset_xd.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _dp, _dp, C.c_long]
         L.orc_fn_call_prior.restype = C.c_double
         L.orc_fn_call_prior.argtypes = [C.c_void_p, _dp]
         L.orc_temp_steps.restype = C.c_long
@@ -204,6 +207,12 @@ class Fn:
         theta, p = _d(theta)
         return lib().orc_fn_call_model(self.h, float(x), p)
 
+    def model_v(self, x, theta):
+        """(apply fn x params) with x a sequence of numbers"""
+        theta, p = _d(theta)
+        x, px = _d(x)
+        return lib().orc_fn_call_model_v(self.h, px, len(x), p)
+
     def prior(self, theta):
         theta, p = _d(theta)
         return lib().orc_fn_call_prior(self.h, p)
@@ -229,6 +238,8 @@ class Walker:
             raise RuntimeError("oracle: rc=%d %s" % (rc, lib().orc_walker_error(self.h).decode()))
 
     def dataset(self, d, x, y, sigma=None):
+        if np.ndim(x) == 2:               # every x is a sequence: x[i] = (x1 x2 ...)
+            return self._dataset_xd(d, x, y, sigma)
         x, px = _d(x)
         y, py = _d(y)
         if sigma is None:
@@ -240,6 +251,14 @@ class Walker:
         if not hasattr(self, "_x"):
             self._x = {}
         self._x[d] = x
+
+    def _dataset_xd(self, d, x, y, sigma):
+        x, px = _d(x)
+        y, py = _d(y)
+        ps = None
+        if sigma is not None:
+            sigma, ps = _d(np.broadcast_to(np.asarray(sigma, dtype=np.float64), y.shape))
+        self._chk(lib().orc_walker_dataset_xd(self.h, d, px, x.shape[1], py, ps, len(y)))
 
     def model_builtin(self, d, family, idx, degree=0):
         idx = np.ascontiguousarray(idx, dtype=np.int32)

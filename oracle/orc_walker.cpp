@@ -162,6 +162,8 @@ namespace {
 
 struct Dataset {
   std::vector<double> x, y, sigma;
+  int xd = 1;                    // components of every x (multi-dimensional inputs, walker-create docstring :1137)
+  std::vector<double> xv;        // xd > 1: [n][xd], the components of point i; `x` then holds the first component
   int family = ORC_FAM_POLY, degree = 1;
   std::vector<int> idx;
   orc::Fn* fn = nullptr;        // model s-expression
@@ -225,7 +227,8 @@ double dataset_ll(const Dataset& d, const double* theta, int mode) {
   size_t n = d.x.size();
   if (n == 0) return 0.0;  // (reduce #'+ nil) = 0
   for (size_t i = 0; i < n; i++) {
-    double f = model_eval(d, theta, d.x[i]);
+    double f = d.xd > 1 ? (d.family == ORC_FAM_SEXPR ? orc::fn_call_model_v(d.fn, &d.xv[i * d.xd], d.xd, theta) : NAN)
+                        : model_eval(d, theta, d.x[i]);
     double t;
     switch (d.ll_kind) {
       case ORC_LL_NORMAL: t = orc_log_normal(d.y[i], f, d.sigma[i]); break;
@@ -457,10 +460,25 @@ void orc_walker_seed(orc_walker* w, unsigned long long seed) { w->rng.seed(seed)
 int orc_walker_dataset(orc_walker* w, int d, const double* x, const double* y, const double* sigma, long n) {
   if (d < 0 || d >= w->D) return -1;
   Dataset& s = w->ds[d];
+  s.xd = 1;
+  s.xv.clear();
   s.x.assign(x, x + n);
   s.y.assign(y, y + n);
   if (sigma) s.sigma.assign(sigma, sigma + n);
   else s.sigma.assign(n, 1.0);  // (if data-error data-error 1) :1144
+  return 0;
+}
+// :data whose x elements are themselves sequences of xd numbers: x[i*xd + k] = component k of point i
+int orc_walker_dataset_xd(orc_walker* w, int d, const double* x, int xd, const double* y, const double* sigma, long n) {
+  if (d < 0 || d >= w->D || xd < 1) return -1;
+  Dataset& s = w->ds[d];
+  s.xd = xd;
+  s.xv.assign(x, x + (size_t)n * xd);
+  s.x.resize(n);
+  for (long i = 0; i < n; i++) s.x[i] = x[(size_t)i * xd];
+  s.y.assign(y, y + n);
+  if (sigma) s.sigma.assign(sigma, sigma + n);
+  else s.sigma.assign(n, 1.0);
   return 0;
 }
 int orc_walker_model_builtin(orc_walker* w, int d, int family, int degree, const int* idx, int n_idx) {

@@ -12,7 +12,8 @@ def oracle_walker(orc, cfg, use_builtin_formula=False):
     fns = cfg["function"]
     D = len(fns)
     ow = orc.Walker(cfg["keys"], D)
-    data = clean_data(cfg["data"] if D > 1 else cfg["data"][0], D)
+    seq_x = np.ndim(cfg["data"][0][0]) == 2   # x made of sequences (:1137): only the list-of-sets form is accepted
+    data = clean_data(cfg["data"] if D > 1 or seq_x else cfg["data"][0], D)
     err = clean_data_error(cfg["data_error"], data)
     lls = cfg["log_liklihood"] if isinstance(cfg["log_liklihood"], (list, tuple)) else [cfg["log_liklihood"]] * D
     lps = cfg["log_prior"]
@@ -54,6 +55,7 @@ def ll_scale(cfg):
     """sum_i |-ln(2 pi)/2 - ln sigma_i| over all data sets: the theta-independent half of log-liklihood-normal
     (mcmc-fitting.lisp:377), against which -sum r^2/2 cancels near the best fit."""
     D = len(cfg["function"])
-    data = clean_data(cfg["data"] if D > 1 else cfg["data"][0], D)
+    seq_x = np.ndim(cfg["data"][0][0]) == 2   # x made of sequences (:1137): only the list-of-sets form is accepted
+    data = clean_data(cfg["data"] if D > 1 or seq_x else cfg["data"][0], D)
     err = clean_data_error(cfg["data_error"], data)
     return float(sum(np.sum(np.abs(-0.5 * np.log(2 * np.pi) - np.log(e))) for e in err))

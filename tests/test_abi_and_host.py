@@ -101,6 +101,19 @@ def test_clean_data_shapes_and_errors():
         clean_data([1, 2, 3], 1)
 
 
+def test_clean_data_keeps_sequences_as_x():
+    """multi-dimensional inputs (:1137): each x is itself a sequence; clean-data :807-825 takes such a tree as it is when
+    its length equals the number of functions (a single (x y) set of depth 3 is therefore an error for one function --
+    the reference asks for (list (list xs ys)))"""
+    xs = [[0.0, 1.0], [0.5, 2.0], [1.0, 4.0]]
+    d = clean_data([[xs, [1, 2, 3]]], 1)
+    assert d[0][0].shape == (3, 2) and d[0][1].shape == (3,)
+    with pytest.raises(ValueError):
+        clean_data([xs, [1, 2, 3]], 1)
+    with pytest.raises(ValueError):
+        clean_data([[xs, [1, 2]]], 1)
+
+
 def test_clean_data_error_broadcasts_first_value():
     data = clean_data([[[1, 2, 3], [4, 5, 6]], [[1, 2], [3, 4]]], 2)
     e = clean_data_error(0.2, data)                    # scalar -> every point (:776-777)

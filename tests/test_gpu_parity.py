@@ -548,6 +548,91 @@ def test_data_and_fit_global_fit_and_user_model(orc):
     w.close()
 
 
+def _xvec_cfg(N, W, ll="log-liklihood-normal", seed=0):
+    """a model of a two-component x, the walker-create docstring's own shape (:1137): x = (t, v)"""
+    rng = np.random.default_rng(500 + seed)
+    keys = ["a", "b", "k"]
+    text = "(lambda (x &key a b k &allow-other-keys) (+ (* a (elt x 0)) (* b (exp (* -1 k (elt x 1))))))"
+    th = np.array([1.5, 4.0, 0.8])
+    x = np.stack([np.linspace(0.0, 3.0, N), rng.uniform(0.0, 2.0, N)], axis=1)     # N x 2
+    f = th[0] * x[:, 0] + th[1] * np.exp(-th[2] * x[:, 1])
+    if ll == "log-poisson":
+        y, sig = rng.poisson(10 * f).astype(np.float64), 1.0
+        th = th * np.array([10.0, 10.0, 1.0])
+    else:
+        sig = rng.uniform(0.02, 0.06, N)
+        y = f + sig * rng.standard_normal(N)
+    theta0 = th[None, :] * (1 + 0.01 * rng.standard_normal((W, 3)))
+    return dict(function=[text], data=[[x, y]], data_error=[sig] if np.ndim(sig) else sig, keys=keys, theta_star=th,
+                theta0=theta0, log_liklihood=ll, log_prior="log-prior-flat")
+
+
+def _make_xvec_walker(cfg, **kw):
+    params = [(k, v) for k, v in zip(cfg["keys"], cfg["theta_star"])]
+    # one function, x made of sequences: the reference wants the data as a list of sets, (list (list xs ys)) :818-820
+    return walker_create(function=cfg["function"], data=cfg["data"], params=params, data_error=cfg["data_error"],
+                         log_liklihood=cfg["log_liklihood"], log_prior=cfg["log_prior"], theta0=cfg["theta0"], **kw)
+
+
+@pytest.mark.parametrize("ll,N,W", [("log-liklihood-normal", 1537, 70), ("log-liklihood-normal-cutoff", 300, 257),
+                                    ("log-poisson", 1000, 33), ("log-liklihood-normal", 1, 1)])
+def test_multi_dimensional_x_loglik_matches_oracle(orc, ll, N, W):
+    """x is itself a sequence (walker-create docstring :1137); every component is one more TMA-staged data
+    array of the likelihood kernel, read by the lowered model as xv[k]"""
+    cfg = _xvec_cfg(N, W, ll, seed=N)
+    w = _make_xvec_walker(cfg)
+    prob, llv, _ = w.make_step(cfg["theta0"])
+    ow = oracle_walker(orc, cfg)
+    ref = np.array([ow.logp(t)[0] for t in cfg["theta0"]])
+    assert np.all(np.isfinite(ref)) and rel_err(prob, ref, ll_scale(cfg)) < TOL
+    w.close()
+
+
+def test_multi_dimensional_x_run_identical_to_oracle_and_next_to_a_scalar_set(orc):
+    """a global fit of one data set with a two-component x and one with a plain x, sharing parameters; injected streams"""
+    cx = _xvec_cfg(700, 20, seed=3)
+    rng = np.random.default_rng(8)
+    x1 = np.linspace(0.0, 2.0, 450)
+    s1 = 0.05
+    y1 = cx["theta_star"][1] * np.exp(-cx["theta_star"][2] * x1) + s1 * rng.standard_normal(450)
+    f1 = "(lambda (x &key b k &allow-other-keys) (* b (exp (* -1 k x))))"
+    cfg = dict(function=[cx["function"][0], f1], data=[cx["data"][0], [x1, y1]], data_error=[cx["data_error"][0], np.full(450, s1)],
+               keys=cx["keys"], theta_star=cx["theta_star"], theta0=cx["theta0"], log_liklihood="log-liklihood-normal",
+               log_prior="log-prior-flat")
+    w = workloads.make_walker(cfg)
+    n = 2200                                  # (the loop never takes fewer than 2000 steps, :906 / :917)
+    z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    w.adaptive_steps_full(n=n, temperature=10, z=z, u=u)
+    _compare_chain(orc, cfg, w, z, u,
+                   lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu), [0, 7, 19])
+    w.close()
+
+
+def test_multi_dimensional_x_type_errors():
+    """what the reference would signal inside the model: a sequence used as a number, a number indexed, an index beyond
+    the end of x, a built-in family (all take a number) on sequence data"""
+    cfg = _xvec_cfg(64, 4)
+    bad = dict(cfg)
+    bad["function"] = ["(lambda (x &key a b k &allow-other-keys) (+ a (* b x) k))"]          # x as a number
+    with pytest.raises(_lib.MfitError) as e:
+        _make_xvec_walker(bad)
+    assert e.value.code == _lib.ERR_ARG
+    bad["function"] = ["(lambda (x &key a b k &allow-other-keys) (+ a (* b (elt x 2)) k))"]  # third of two components
+    with pytest.raises(_lib.MfitError) as e:
+        _make_xvec_walker(bad)
+    assert e.value.code == _lib.ERR_ARG
+    flat = dict(cfg)
+    flat["data"] = [[cfg["data"][0][0][:, 0], cfg["data"][0][1]]]                              # plain x, indexing model
+    with pytest.raises(_lib.MfitError) as e:
+        _make_xvec_walker(flat)
+    assert e.value.code == _lib.ERR_ARG
+    fam = dict(cfg)
+    fam["function"] = [builtin("poly", ["a", "b", "k"], 2)]
+    with pytest.raises(_lib.MfitError) as e:
+        _make_xvec_walker(fam)
+    assert e.value.code == _lib.ERR_ARG
+
+
 def test_two_stream_chain_groups_do_not_change_results(orc):
     """a run advances the chains as two groups on two streams (the per-chain kernels of one overlap the likelihood
     kernel of the other): bit-identical to the one-group run, with built-in and NVRTC priors, Philox and injected

@@ -113,3 +113,51 @@ def test_nvrtc_compiles_user_model_and_prior_for_sm100a():
     assert n > 10000
     n = _lib.compile_sexpr(families.LOG_PRIOR_NV, ["scale1", "scale2", "mu1", "mu2", "sigma", "bg0"], 1)
     assert n > 1000
+
+
+XVEC_MODEL = ("(lambda (x &key a b c &allow-other-keys) (+ (* a (elt x 0)) (* b (exp (* -1 c (second x)))) "
+              "(* 1/2 (nth 2 x)) (aref x 1)))")
+
+
+def test_multi_dimensional_x_lowers_to_component_reads():
+    """walker-create docstring :1137 -- "(elt x 0) ... (elt x 1)": x is a sequence; the lowered model declares how many
+    components it reads (one staged data array each) and evaluates them like the oracle's (apply fn x params)"""
+    from oracle import oracle as orc
+    keys = ["a", "b", "c"]
+    code = _lib.lower_sexpr(XVEC_MODEL, keys, 0)
+    assert "XDIMS = 3" in code and "XVEC = true" in code and "evalv(" in code and "xv[2]" in code
+    d = tempfile.mkdtemp()
+    src = os.path.join(d, "m.cpp")
+    tail = ('extern "C" double call(const double* th, const double* x) { MfitEvalArgs a{th, 1}; MfitUser m; m.load(a, 0); '
+            "MfitGuard gd; double xv[MfitUser::XDIMS]; for (int k = 0; k < MfitUser::XDIMS; k++) xv[k] = x[k]; "
+            "return m.evalv<false>(xv, gd); }")
+    open(src, "w").write(HOST_PRELUDE + code + tail)
+    so = os.path.join(d, "m.so")
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.call.restype = C.c_double
+    dp = C.POINTER(C.c_double)
+    lib.call.argtypes = [dp, dp]
+    ref = orc.Fn(XVEC_MODEL, keys)
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        th, x = rng.uniform(-2, 2, 3), rng.uniform(-3, 3, 3)
+        got = lib.call(th.ctypes.data_as(dp), x.ctypes.data_as(dp))
+        want = ref.model_v(x, th)
+        assert got == want or abs(got - want) <= 4e-16 * abs(want)
+    assert np.isnan(ref.model(1.0, [1.0, 1.0, 1.0]))          # a number where a sequence is indexed: type error
+    assert np.isnan(ref.model_v([1.0, 2.0], [1.0, 1.0, 1.0]))  # (nth 2 x) beyond the end
+    # a scalar model keeps the scalar form
+    code1 = _lib.lower_sexpr("(lambda (x &key a b c &allow-other-keys) (+ a (* b x) c))", keys, 0)
+    assert "XDIMS = 1" in code1 and "XVEC = false" in code1 and "eval(double x" in code1
+    assert _lib.compile_sexpr(XVEC_MODEL, keys, 0) > 10000      # the whole NVRTC pipeline, sm_100a
+
+
+@pytest.mark.parametrize("text", ["(lambda (x &key a) (+ x (elt x 0) a))",            # number and sequence at once
+                                  "(lambda (x &key a) (+ a (elt x a)))",              # index must be a literal
+                                  "(lambda (x &key a) (+ a (elt x 8)))",              # more than MFIT_MAX_XDIMS components
+                                  "(lambda (x &key a) (let ((x a)) (elt x 0)))"])     # a shadowing binding is not x
+def test_multi_dimensional_x_errors(text):
+    with pytest.raises(_lib.MfitError) as e:
+        _lib.lower_sexpr(text, ["a"], 0)
+    assert e.value.code == _lib.ERR_SEXPR
