@@ -176,6 +176,14 @@ int mfit_request_stop(mfit_ctx* ctx);
  * n_valid: W (rows filled per chain; the rest is NaN).  Any output may be NULL. */
 int mfit_trace_read(mfit_ctx* ctx, int64_t take, double* theta, double* prob, int64_t* n_valid);
 int mfit_stats_read(mfit_ctx* ctx, mfit_chain_stats* stats /* W */);
+/* walker-load :989-1001 revived (checkpoint / resume): after mfit_chains_init with W chains, replace every chain's walk
+ * by a saved one -- the inverse of mfit_trace_read.  theta W x rows x P and prob W x rows, newest first; chain w holds
+ * n_valid[w] <= rows steps.  The last step becomes the newest row; walker-length = steps held; walker-age = age[w]
+ * (NULL: the steps held), which also keys the Philox stream, so a restored chain continues exactly as the saved one
+ * would have; the most likely step is the saved one (best_theta W x P, best_prob W) unless the walk holds a better
+ * one, or, with NULL, the first strictly largest prob from the oldest row up (walker-modify :add-walks :558-563). */
+int mfit_chains_restore(mfit_ctx* ctx, int64_t rows, const double* theta, const double* prob, const int64_t* n_valid,
+                        const int64_t* age, const double* best_theta, const double* best_prob);
 /* most-likely-step :474 and last-step :475.  theta outputs W x P. */
 int mfit_best_read(mfit_ctx* ctx, double* theta, double* prob);
 int mfit_last_read(mfit_ctx* ctx, double* theta, double* prob);

@@ -1447,6 +1447,54 @@ int mfit_trace_read(mfit_ctx* ctx, int64_t take, double* theta, double* prob, in
   return rc;
 }
 
+int mfit_chains_restore(mfit_ctx* ctx, int64_t rows, const double* theta, const double* prob, const int64_t* n_valid,
+                        const int64_t* age, const double* best_theta, const double* best_prob) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (ctx->run_open) return fail(ctx, MFIT_ERR_STATE, "a run is open");
+  if (rows < 1 || !theta || !prob || !n_valid) return fail(ctx, MFIT_ERR_ARG, "need rows >= 1, theta, prob and n_valid");
+  if ((best_theta == nullptr) != (best_prob == nullptr)) return fail(ctx, MFIT_ERR_ARG, "best_theta and best_prob go together");
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  MfitChains& c = ctx->ch;
+  const size_t W = (size_t)c.W, P = (size_t)c.P;
+  long long most = 0;
+  for (size_t w = 0; w < W; w++) {
+    if (n_valid[w] < 1 || n_valid[w] > rows) return fail(ctx, MFIT_ERR_ARG, "n_valid[%zu] = %lld outside 1 .. rows", w, (long long)n_valid[w]);
+    if (age && age[w] < n_valid[w]) return fail(ctx, MFIT_ERR_ARG, "age[%zu] below the number of steps held", w);
+    if (n_valid[w] > most) most = n_valid[w];
+  }
+  int rc = grow_trace(ctx, most + 1);
+  if (rc) return rc;
+  double *dt = nullptr, *dp = nullptr, *dbt = nullptr, *dbp = nullptr;
+  long long *dn = nullptr, *da = nullptr;
+  cudaError_t e = cudaMalloc(&dt, sizeof(double) * W * (size_t)rows * P);
+  if (e == cudaSuccess) e = cudaMalloc(&dp, sizeof(double) * W * (size_t)rows);
+  if (e == cudaSuccess) e = cudaMalloc(&dn, sizeof(long long) * W);
+  if (e == cudaSuccess && age) e = cudaMalloc(&da, sizeof(long long) * W);
+  if (e == cudaSuccess && best_theta) e = cudaMalloc(&dbt, sizeof(double) * W * P);
+  if (e == cudaSuccess && best_prob) e = cudaMalloc(&dbp, sizeof(double) * W);
+  auto up = [&](void* dst, const void* src, size_t bytes) {
+    if (e == cudaSuccess && dst) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  };
+  up(dt, theta, sizeof(double) * W * (size_t)rows * P);
+  up(dp, prob, sizeof(double) * W * (size_t)rows);
+  up(dn, n_valid, sizeof(long long) * W);
+  up(da, age, sizeof(long long) * W);
+  up(dbt, best_theta, sizeof(double) * W * P);
+  up(dbp, best_prob, sizeof(double) * W);
+  if (e == cudaSuccess) {
+    mfit_launch_trace_restore(c, rows, dt, dp, dn, da, dbt, dbp, ctx->stream);
+    ctx->launches += 2;
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  free_dev(dt); free_dev(dp); free_dev(dn); free_dev(da); free_dev(dbt); free_dev(dbp);
+  if (e != cudaSuccess)
+    return fail(ctx, e == cudaErrorMemoryAllocation ? MFIT_ERR_NOMEM : MFIT_ERR_CUDA, "chains_restore: %s", cudaGetErrorString(e));
+  ctx->rows_upper = most;
+  return 0;
+}
+
 int mfit_stats_read(mfit_ctx* ctx, mfit_chain_stats* stats) {
   if (!ctx || !stats) return MFIT_ERR_ARG;
   if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");

@@ -664,6 +664,53 @@ __global__ void k_trace_gather(const MfitChains c, long long take, double* theta
     if (prob) prob[(size_t)w * take + r] = nanv;
   }
 }
+// walker-load :989-1001 revived (checkpoint / resume): the inverse of k_trace_gather.  Row r (newest first) of chain w
+// goes to absolute row n_valid[w] - 1 - r of its ring; rows the ring cannot hold (r >= cap) are the oldest and drop out.
+__global__ void k_trace_scatter(const MfitChains c, long long rows, const double* theta, const double* prob,
+                                const long long* n_valid) {
+  long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (long long)c.W * rows) return;
+  const long long r = id / c.W, w = id % c.W;  // adjacent threads = adjacent chains (coalesced ring writes)
+  const long long m = n_valid[w];
+  if (r >= m || r >= c.cap) return;
+  const long long slot = (m - 1 - r) % c.cap;
+  for (int i = 0; i < c.P; i++) c.trace_theta[((size_t)slot * c.P + i) * c.stride + w] = theta[((size_t)w * rows + r) * c.P + i];
+  c.trace_prob[(size_t)slot * c.stride + w] = prob[(size_t)w * rows + r];
+}
+// the per-chain slots that go with a restored walk: last step = newest row, length, age, and the most likely step --
+// the saved one, or (walker-modify :add-walks :558-563) the first strictly largest prob going from the oldest row up
+__global__ void k_restore_state(const MfitChains c, const long long* n_valid, const long long* age, const double* best_theta,
+                                const double* best_prob) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  const int P = c.P;
+  const long long m = n_valid[w];
+  const long long held = m < c.cap ? m : c.cap;
+  c.rows[w] = m;
+  c.length[w] = held;
+  c.age[w] = age ? age[w] : m;
+  const long long newest = m - 1;
+  for (int i = 0; i < P; i++) c.cur_theta[(size_t)i * c.stride + w] = ttheta(c, newest, i, w);
+  c.cur_prob[w] = tprob(c, newest, w);
+  long long brow = m - held;
+  double bp = tprob(c, brow, w);
+  for (long long row = m - held + 1; row <= newest; row++) {
+    const double p = tprob(c, row, w);
+    if (p > bp) { bp = p; brow = row; }
+  }
+  const bool given = best_theta != nullptr && best_prob != nullptr && !(bp > best_prob[w]);
+  for (int i = 0; i < P; i++)
+    c.best_theta[(size_t)i * c.stride + w] = given ? best_theta[(size_t)w * P + i] : ttheta(c, brow, i, w);
+  c.best_prob[w] = given ? best_prob[w] : bp;
+  c.done[w] = 0;
+  c.shutting[w] = 0;
+  c.need_reest[w] = 0;
+  c.steps_run[w] = 0;
+  c.l_updates[w] = 0;
+  c.loop_i[w] = 0;
+  c.temperature[w] = 1.0;
+  c.reset_index[w] = 10000;
+}
 __global__ void k_philox_stream(unsigned long long seed, long long chain_base, long long W, long long first,
                                 long long nsteps, int P, double* z, double* u) {
   long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1021,6 +1068,12 @@ void mfit_launch_stats(const MfitChains& c, void* stats_dev, cudaStream_t st) {
 void mfit_launch_trace_gather(const MfitChains& c, long long take, double* theta, double* prob, long long* nvalid,
                               cudaStream_t st) {
   k_trace_gather<<<blocks_for((long long)c.W * take, 256), 256, 0, st>>>(c, take, theta, prob, nvalid);
+}
+void mfit_launch_trace_restore(const MfitChains& c, long long rows, const double* theta, const double* prob,
+                               const long long* n_valid, const long long* age, const double* best_theta,
+                               const double* best_prob, cudaStream_t st) {
+  k_trace_scatter<<<blocks_for((long long)c.W * rows, 256), 256, 0, st>>>(c, rows, theta, prob, n_valid);
+  k_restore_state<<<blocks_for(c.W, 128), 128, 0, st>>>(c, n_valid, age, best_theta, best_prob);
 }
 void mfit_launch_philox_stream(unsigned long long seed, long long chain_base, long long W, long long first,
                                long long nsteps, int P, double* z, double* u, cudaStream_t st) {

@@ -86,6 +86,9 @@ void mfit_launch_keep_walks(const MfitChains& c, long long keep, cudaStream_t st
 void mfit_launch_stats(const MfitChains& c, void* stats_dev, cudaStream_t st);
 void mfit_launch_trace_gather(const MfitChains& c, long long take, double* theta, double* prob, long long* nvalid,
                               cudaStream_t st);
+void mfit_launch_trace_restore(const MfitChains& c, long long rows, const double* theta, const double* prob,
+                               const long long* n_valid, const long long* age, const double* best_theta,
+                               const double* best_prob, cudaStream_t st);
 void mfit_launch_philox_stream(unsigned long long seed, long long chain_base, long long W, long long first,
                                long long nsteps, int P, double* z, double* u, cudaStream_t st);
 void mfit_launch_transpose_in(const double* src_rowmajor, double* dst, long long W, int P, long long stride,

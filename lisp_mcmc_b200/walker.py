@@ -509,41 +509,87 @@ class Walker:
 
     # -------------------------------------------------------------- walker-save / walker-load (:971-1001)
     def save(self, path, take=None):
-        """s-expression header in the layout of the reference's (commented-out) walker-save, followed by a binary
-        FP64 blob: W x rows x (P+1) doubles (prob first), newest step first."""
+        """s-expression header in the layout of the reference's (commented-out) walker-save -- :fn :param-keys
+        :log-liklihood :log-prior as *recommendations* for walker-load, like the reference prints them -- followed by
+        binary FP64 blobs: the walk, W x rows x (P+1) doubles (prob first, newest step first), then every chain's most
+        likely step, W x (P+1).  With the ages and the Philox key in the header this is a checkpoint: walker_load
+        continues the chains exactly where they stood."""
         st = self.stats()
         rows = int(st["length"].max()) if take is None else int(take)
         th, pr, nv = self.trace(rows)
+        bth, bpr = self.most_likely()
         fn_names = " ".join('"%s"' % (repr(f) if isinstance(f, Builtin) else f).replace('"', '\\"') for f in self.function)
-        hdr = ("(:mfit-walker 1 :fn (%s) :param-keys (%s) :log-liklihood (%s) :log-prior (%s) :n-walkers %d :rows %d "
-               ":n-params %d :seed %d :lengths (%s))\n") % (
+        hdr = ("(:mfit-walker 2 :fn (%s) :param-keys (%s) :log-liklihood (%s) :log-prior (%s) :n-walkers %d :rows %d "
+               ":n-params %d :seed %d :chain-id-base %d :lengths (%s) :ages (%s))\n") % (
             fn_names, " ".join(":" + k for k in self.param_keys),
             " ".join('"%s"' % x for x in self.log_liklihood),
             " ".join('"%s"' % (x if isinstance(x, str) else repr(list(x))).replace('"', '\\"') for x in self.log_prior),
-            self.W, rows, self.P, self.seed, " ".join(str(int(v)) for v in nv))
+            self.W, rows, self.P, self.seed, self.chain_id_base, " ".join(str(int(v)) for v in nv),
+            " ".join(str(int(v)) for v in st["age"]))
         blob = np.concatenate([pr[:, :, None], th], axis=2).astype("<f8")
+        best = np.concatenate([bpr[:, None], bth], axis=1).astype("<f8")
         with open(path, "wb") as f:
             f.write(hdr.encode())
             f.write(struct.pack("<q", blob.size))
             f.write(blob.tobytes())
+            f.write(struct.pack("<q", best.size))
+            f.write(best.tobytes())
         return path
 
+    def restore(self, theta, prob, n_valid, age=None, best_theta=None, best_prob=None):
+        """walker-modify :add-walks as walker-load uses it (:989-1001), for all chains: replace every chain's walk by
+        theta[W,rows,P] / prob[W,rows] (newest first, n_valid[w] rows each) -- mfit_chains_restore."""
+        theta, prob = _f64(theta), _f64(prob)
+        nv = np.ascontiguousarray(n_valid, dtype=np.int64)
+        ag = None if age is None else np.ascontiguousarray(age, dtype=np.int64)
+        if theta.shape != (self.W, prob.shape[1], self.P) or prob.shape[0] != self.W or nv.shape != (self.W,):
+            raise ValueError("theta must be W x rows x P, prob W x rows, n_valid W")
+        lp = C.POINTER(C.c_int64)
+        self._chk(self._L.mfit_chains_restore(
+            self._h, prob.shape[1], _ptr(theta), _ptr(prob), nv.ctypes.data_as(lp), None if ag is None else ag.ctypes.data_as(lp),
+            _ptr(None if best_theta is None else _f64(best_theta)), _ptr(None if best_prob is None else _f64(best_prob))))
+        return self
 
-def walker_load(path):
-    """Read a file written by Walker.save -> dict(header text, param_keys, prob[W,rows], theta[W,rows,P], n_valid[W])."""
+
+def walker_load(path, function=None, data=None, data_error=None, log_liklihood=None, log_prior=None, **gpu):
+    """walker-load :989-1001.  Without :function / :data the file is only read -> dict(header, param_keys, prob[W,rows],
+    theta[W,rows,P], n_valid[W], age[W], best_theta, best_prob, seed, chain_id_base); the header names the functions the
+    walker was saved with (the reference prints them as *Recommendations*).  With them, the walker set is rebuilt
+    (walker-create with the newest step of every chain as its parameters, :999) and its walks restored (:add-walks),
+    Philox key and ages included, so that it goes on exactly like the saved one."""
+    import re
     with open(path, "rb") as f:
         hdr = f.readline().decode()
         (cnt,) = struct.unpack("<q", f.read(8))
         blob = np.frombuffer(f.read(cnt * 8), dtype="<f8")
-    import re
+        tail = f.read(8)
+        best = None
+        if len(tail) == 8:
+            (bcnt,) = struct.unpack("<q", tail)
+            best = np.frombuffer(f.read(bcnt * 8), dtype="<f8")
     W = int(re.search(r":n-walkers (\d+)", hdr).group(1))
     rows = int(re.search(r":rows (\d+)", hdr).group(1))
     P = int(re.search(r":n-params (\d+)", hdr).group(1))
-    keys = re.search(r":param-keys \(([^)]*)\)", hdr).group(1).split()
-    lens = [int(v) for v in re.search(r":lengths \(([^)]*)\)", hdr).group(1).split()]
+    keys = [k.lstrip(":") for k in re.search(r":param-keys \(([^)]*)\)", hdr).group(1).split()]
+    lens = np.array([int(v) for v in re.search(r":lengths \(([^)]*)\)", hdr).group(1).split()], dtype=np.int64)
+    m = re.search(r":ages \(([^)]*)\)", hdr)
+    ages = np.array([int(v) for v in m.group(1).split()], dtype=np.int64) if m else lens.copy()
+    m = re.search(r":chain-id-base (\d+)", hdr)
     blob = blob.reshape(W, rows, P + 1)
-    return {"header": hdr, "param_keys": [k.lstrip(":") for k in keys], "prob": blob[:, :, 0].copy(),
-            "theta": blob[:, :, 1:].copy(), "n_valid": np.array(lens, dtype=np.int64)}
+    out = {"header": hdr, "param_keys": keys, "prob": blob[:, :, 0].copy(), "theta": blob[:, :, 1:].copy(), "n_valid": lens,
+           "age": ages, "seed": int(re.search(r":seed (\d+)", hdr).group(1)), "chain_id_base": int(m.group(1)) if m else 0,
+           "best_theta": None, "best_prob": None}
+    if best is not None:
+        best = best.reshape(W, P + 1)
+        out["best_prob"], out["best_theta"] = best[:, 0].copy(), best[:, 1:].copy()
+    if function is None or data is None:
+        return out
+    gpu.setdefault("seed", out["seed"])
+    gpu.setdefault("chain_id_base", out["chain_id_base"])
+    theta0 = out["theta"][:, 0, :]
+    w = Walker(function, data, [(k, v) for k, v in zip(keys, theta0[0])], data_error, log_liklihood, log_prior,
+               theta0=theta0, **gpu)
+    return w.restore(out["theta"], out["prob"], out["n_valid"], out["age"], out["best_theta"], out["best_prob"])
 
 
 # ------------------------------------------------------------------ the reference's function names

@@ -781,8 +781,42 @@ def test_walker_save_and_load_round_trip(tmp_path):
     path = walker_save(w, str(tmp_path / "walk.mfit"))
     th, pr, nv = w.trace(int(w.stats()["length"].max()))
     got = walker_load(path)
-    assert got["param_keys"] == cfg["keys"] and got["header"].startswith("(:mfit-walker 1 :fn (")
+    assert got["param_keys"] == cfg["keys"] and got["header"].startswith("(:mfit-walker 2 :fn (")
     assert np.array_equal(got["n_valid"], nv)
     assert np.array_equal(got["theta"], th, equal_nan=True) and np.array_equal(got["prob"], pr, equal_nan=True)
     assert ":log-liklihood (\"log-liklihood-normal\")" in got["header"] and ":n-walkers 5" in got["header"]
+    assert np.array_equal(got["age"], w.stats()["age"]) and got["seed"] == 8
+    bth, bpr = w.most_likely()
+    assert np.array_equal(got["best_theta"], bth) and np.array_equal(got["best_prob"], bpr)
     w.close()
+
+
+@pytest.mark.parametrize("keep", [None, 700])
+def test_walker_load_resumes_exactly(tmp_path, keep):
+    """a walker set rebuilt by walker-load (:989-1001: walker-create on the newest step, then :add-walks) continues bit
+    for bit like the one that was saved -- same walk, ages (the Philox key), most likely steps -- through a fixed-L run
+    and through another adaptive run (whose first l-matrix comes from the restored walk); also after :keep-walks, when
+    the most likely step may have left the walk"""
+    from lisp_mcmc_b200 import walker_load, walker_save
+    cfg = workloads.c2(W=140, N=300)
+    a = workloads.make_walker(cfg, seed=21, chain_id_base=1000)
+    a.adaptive_steps_full(n=2100, temperature=10)
+    if keep:
+        a.keep_walks(keep)
+    path = walker_save(a, str(tmp_path / "ckpt.mfit"))
+    b = walker_load(path, function=cfg["function"], data=cfg["data"][0], data_error=cfg["data_error"],
+                    log_liklihood=cfg["log_liklihood"], log_prior=cfg["log_prior"])
+    sa, sb = a.stats(), b.stats()
+    for k in ("length", "age", "last_prob", "best_prob"):
+        assert np.array_equal(sa[k], sb[k]), k
+    assert np.array_equal(a.most_likely()[0], b.most_likely()[0])
+    Lm = np.diag(0.002 * np.abs(cfg["theta_star"]))
+    for w in (a, b):
+        w.many_steps(150, Lm)
+        w.adaptive_steps_full(n=2100, temperature=10)
+    ta, tb = a.trace(5000), b.trace(5000)
+    for x, y in zip(ta, tb):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert np.array_equal(a.l_matrix(), b.l_matrix())
+    assert ta[2].min() >= 2100 + 150                   # every chain really ran on
+    a.close(); b.close()
