@@ -220,6 +220,16 @@ int mfit_fit_envelope(mfit_ctx* ctx, int d, int64_t take, int which_solution, co
                       double* y_fit, double* y_max, double* y_min, double* params, int64_t* n_distinct);
 /* walker-modify :keep-walks :568-569 applied to every chain */
 int mfit_keep_walks(mfit_ctx* ctx, int64_t keep);
+/* the other list surgery of walker-modify :546-580, applied to every chain: :burn-walks (the walk loses its OLDEST
+ * `number` steps, :566-567), :keep-walks (= mfit_keep_walks), :reset (the walk shrinks to its OLDEST step, which becomes
+ * the last step -- (last walk) on a newest-first list, :570-573), :reset-to-most-likely (:574-578).  walker-age and the
+ * most likely step are left alone, as in the reference.  (:add-step is the MH step itself, :add-walks is
+ * mfit_chains_restore, :delete is mfit_ctx_destroy.) */
+#define MFIT_MODIFY_BURN_WALKS 1
+#define MFIT_MODIFY_KEEP_WALKS 2
+#define MFIT_MODIFY_RESET 3
+#define MFIT_MODIFY_RESET_TO_MOST_LIKELY 4
+int mfit_walker_modify(mfit_ctx* ctx, int mode, int64_t number);
 
 /* normals / uniforms the on-device Philox stream yields for (seed, global chain id, step index):
  * lets a test replay a Philox run through the injected-stream path of another implementation. */

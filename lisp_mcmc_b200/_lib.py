@@ -73,6 +73,7 @@ SIGNATURES = {
     "mfit_fit_envelope": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, _lp]),
     "mfit_chains_restore": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _lp, _lp, _dp, _dp]),
     "mfit_keep_walks": (C.c_int, [C.c_void_p, C.c_int64]),
+    "mfit_walker_modify": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "mfit_philox_stream": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _dp, _dp]),
     "mfit_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mfit_nccl_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),

@@ -1694,6 +1694,22 @@ int mfit_keep_walks(mfit_ctx* ctx, int64_t keep) {
   return 0;
 }
 
+int mfit_walker_modify(mfit_ctx* ctx, int mode, int64_t number) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (ctx->run_open) return fail(ctx, MFIT_ERR_STATE, "a run is open");
+  if (mode == MFIT_MODIFY_KEEP_WALKS) return mfit_keep_walks(ctx, number);
+  if (mode != MFIT_MODIFY_BURN_WALKS && mode != MFIT_MODIFY_RESET && mode != MFIT_MODIFY_RESET_TO_MOST_LIKELY)
+    return fail(ctx, MFIT_ERR_ARG, "unknown walker-modify mode %d", mode);
+  if (mode == MFIT_MODIFY_BURN_WALKS && number < 0) return fail(ctx, MFIT_ERR_ARG, "burn-number < 0");
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  mfit_launch_modify(ctx->ch, mode, number, ctx->stream);
+  ctx->launches++;
+  if (mode != MFIT_MODIFY_BURN_WALKS) ctx->rows_upper += 1;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int mfit_philox_stream(mfit_ctx* ctx, uint64_t seed, int64_t chain_id_base, int64_t W, int64_t first_step,
                        int64_t nsteps, int P, double* z, double* u) {
   if (!ctx || !z || !u || W < 1 || nsteps < 1 || P < 1 || P > MFIT_MAX_P) return MFIT_ERR_ARG;

@@ -628,6 +628,39 @@ __global__ void k_keep_walks(const MfitChains c, long long keep) {  // :568-569
   long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w < c.W) c.length[w] = keep;
 }
+// walker-modify :burn-walks :566-567 (the walk loses its OLDEST burn-number steps), :reset :570-573 ((last walk): the walk
+// shrinks to its OLDEST step, which also becomes the last step) and :reset-to-most-likely :574-578.  The ring keeps the
+// newest `length` rows as the walk, so the surviving step of the two resets is pushed as a new row of a walk of length 1.
+__global__ void k_modify(const MfitChains c, int mode, long long number) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= c.W) return;
+  const int P = c.P;
+  if (mode == MFIT_MODIFY_BURN_WALKS) {
+    const long long held = wlen(c, w, 0x7fffffffffffffffLL);
+    c.length[w] = held > number ? held - number : 0;
+    return;
+  }
+  const long long held = wlen(c, w, 0x7fffffffffffffffLL);
+  double th[MFIT_MAX_P], p;
+  if (mode == MFIT_MODIFY_RESET) {
+    if (held < 1) return;
+    const long long oldest = c.rows[w] - held;
+    for (int i = 0; i < P; i++) th[i] = ttheta(c, oldest, i, w);
+    p = tprob(c, oldest, w);
+  } else {
+    for (int i = 0; i < P; i++) th[i] = c.best_theta[(size_t)i * c.stride + w];
+    p = c.best_prob[w];
+  }
+  const long long slot = c.rows[w] % c.cap;
+  for (int i = 0; i < P; i++) {
+    c.trace_theta[((size_t)slot * P + i) * c.stride + w] = th[i];
+    c.cur_theta[(size_t)i * c.stride + w] = th[i];
+  }
+  c.trace_prob[(size_t)slot * c.stride + w] = p;
+  c.cur_prob[w] = p;
+  c.rows[w] += 1;
+  c.length[w] = 1;
+}
 __global__ void k_stats(const MfitChains c, mfit_chain_stats* out) {
   long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= c.W) return;
@@ -1061,6 +1094,9 @@ void mfit_launch_count_active(const MfitChains& c, int* out, cudaStream_t st) {
 }
 void mfit_launch_keep_walks(const MfitChains& c, long long keep, cudaStream_t st) {
   k_keep_walks<<<blocks_for(c.W, 128), 128, 0, st>>>(c, keep);
+}
+void mfit_launch_modify(const MfitChains& c, int mode, long long number, cudaStream_t st) {
+  k_modify<<<blocks_for(c.W, 128), 128, 0, st>>>(c, mode, number);
 }
 void mfit_launch_stats(const MfitChains& c, void* stats_dev, cudaStream_t st) {
   k_stats<<<blocks_for(c.W, 128), 128, 0, st>>>(c, (mfit_chain_stats*)stats_dev);

@@ -83,6 +83,7 @@ void mfit_launch_force_step(const MfitChains& c, cudaStream_t st);
 void mfit_launch_priors(const MfitChains& c, const double* theta, cudaStream_t st);
 void mfit_launch_count_active(const MfitChains& c, int* out, cudaStream_t st);
 void mfit_launch_keep_walks(const MfitChains& c, long long keep, cudaStream_t st);
+void mfit_launch_modify(const MfitChains& c, int mode, long long number, cudaStream_t st);
 void mfit_launch_stats(const MfitChains& c, void* stats_dev, cudaStream_t st);
 void mfit_launch_trace_gather(const MfitChains& c, long long take, double* theta, double* prob, long long* nvalid,
                               cudaStream_t st);

@@ -28,7 +28,7 @@
   (:use :cl)
   (:export #:gpu-lambda #:gpu-builtin #:gpu-walker #:walker-create #:walker-adaptive-steps
            #:walker-adaptive-steps-full #:walker-many-steps #:walker-sample-region #:walker-force-take-step
-           #:walker-get #:walker-get-data-and-fit #:walker-save #:walker-free #:mcmc-fit #:mfit-walker-estop #:lower-to-cuda #:walker-set-create))
+           #:walker-get #:walker-get-data-and-fit #:walker-save #:walker-load #:walker-modify #:walker-free #:mcmc-fit #:mfit-walker-estop #:lower-to-cuda #:walker-set-create))
 (in-package :mfit-cuda)
 
 (cffi:define-foreign-library libmfit-cuda (t (:default "libmfit_cuda")))
@@ -88,6 +88,10 @@
 (cffi:defcfun ("mfit_last_read" %last-read) :int (ctx :pointer) (theta :pointer) (prob :pointer))
 (cffi:defcfun ("mfit_l_matrix_read" %l-matrix-read) :int (ctx :pointer) (l :pointer))
 (cffi:defcfun ("mfit_keep_walks" %keep-walks) :int (ctx :pointer) (keep :int64))
+(cffi:defcfun ("mfit_walker_modify" %walker-modify) :int (ctx :pointer) (mode :int) (number :int64))
+(cffi:defcfun ("mfit_chains_restore" %chains-restore) :int
+  (ctx :pointer) (rows :int64) (theta :pointer) (prob :pointer) (n-valid :pointer) (age :pointer)
+  (best-theta :pointer) (best-prob :pointer))
 (cffi:defcfun ("mfit_trace_analytics" %trace-analytics) :int
   (ctx :pointer) (take :int64) (most-likely-theta :pointer) (most-likely-prob :pointer) (median :pointer)
   (acceptance :pointer) (covariance :pointer) (l-matrix :pointer))
@@ -430,6 +434,44 @@ curve and the envelope over the best 66 % of the walk are evaluated on the devic
                    :walker (walker-get walker :get :steps :take take :chain chain))
              out)))
   filename)
+
+(defun walker-load (filename &key function log-liklihood log-prior quiet (seed 0) (device 0))
+  "walker-load :989-1001 revived for a file written by walker-save: prints the saved names as *Recommendations*; with
+:function given, rebuilds the walker (walker-create on the newest step, :999) and restores its walk on the device
+(:add-walks :556-563 as the loader means it: the walk, the last step and the most likely step)."
+  (with-open-file (in filename :direction :input)
+    (with-standard-io-syntax
+      (let* ((full (read in))
+             (data (getf full :data))
+             (data-error (getf full :stddev))
+             (walks (getf full :walker))                      ; ((prob . plist) ...), newest first
+             (keys (getf full :param-keys))
+             (dummy-params (cdr (first walks))))
+        (unless quiet
+          (format t "*Recommendations*~%function: ~s~%log-liklihood: ~s~%" (getf full :fn) (getf full :log-liklihood)))
+        (when function
+          (let* ((walker (walker-create :function function :data data :params dummy-params :data-error data-error
+                                        :log-liklihood log-liklihood :log-prior log-prior :seed seed :device device))
+                 (ctx (gpu-walker-ctx walker)) (rows (length walks)) (p (length keys)))
+            (cffi:with-foreign-objects ((th :double (* rows p)) (pr :double rows) (nv :int64 1))
+              (loop for (prob . plist) in walks for r from 0 do
+                (setf (cffi:mem-aref pr :double r) (coerce prob 'double-float))
+                (loop for k in keys for i from 0 do
+                  (setf (cffi:mem-aref th :double (+ (* r p) i)) (coerce (getf plist k) 'double-float))))
+              (setf (cffi:mem-aref nv :int64 0) rows)
+              (with-traps-masked
+                (chk ctx (%chains-restore ctx rows th pr nv (cffi:null-pointer) (cffi:null-pointer) (cffi:null-pointer)))))
+            walker))))))
+
+(defun walker-modify (walker &key (modify :keep-walks) burn-number keep-number)
+  "walker-modify :546-580 on the device, every chain: :burn-walks :keep-walks :reset :reset-to-most-likely."
+  (let ((ctx (gpu-walker-ctx walker)))
+    (chk ctx (ecase modify
+               (:burn-walks (%walker-modify ctx 1 burn-number))
+               (:keep-walks (%walker-modify ctx 2 keep-number))
+               (:reset (%walker-modify ctx 3 0))
+               (:reset-to-most-likely (%walker-modify ctx 4 0))))
+    walker))
 
 (defun mcmc-fit (&rest args &key function data params data-error log-liklihood log-prior param-bounds &allow-other-keys)
   "mcmc-fit :1165-1175"

@@ -380,6 +380,14 @@ class Walker:
         """0 = automatic, 1 / 2 = advance the chains as one / two groups on separate streams (mfit_set_groups)"""
         self._chk(self._L.mfit_set_groups(self._h, int(n_groups)))
 
+    def modify(self, modify, burn_number=None, keep_number=None):
+        """walker-modify :546-580 for every chain: :burn-walks, :keep-walks, :reset, :reset-to-most-likely"""
+        m = str(modify).lstrip(":").lower()
+        mode = {"burn-walks": 1, "keep-walks": 2, "reset": 3, "reset-to-most-likely": 4}[m]
+        number = burn_number if mode == 1 else keep_number if mode == 2 else 0
+        self._chk(self._L.mfit_walker_modify(self._h, mode, int(number)))
+        return self
+
     def keep_walks(self, keep):
         """walker-modify :keep-walks :568-569"""
         self._chk(self._L.mfit_keep_walks(self._h, int(keep)))

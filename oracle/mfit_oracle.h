@@ -111,6 +111,8 @@ void orc_walker_last_l_matrix(orc_walker* w, double* L);
 /* walker-get :acceptance :take -> count, len (exact rational count/len) */
 void orc_walker_acceptance(orc_walker* w, long take, long* count, long* len);
 int orc_walker_keep_walks(orc_walker* w, long keep);
+/* walker-modify :566-578: mode 1 :burn-walks, 2 :keep-walks, 3 :reset, 4 :reset-to-most-likely */
+int orc_walker_modify(orc_walker* w, int mode, long number);
 /* test support: replace the walk (theta n x P, prob n; newest first) */
 int orc_walker_load_walk(orc_walker* w, const double* theta, const double* prob, long n);
 /* walker-get-data-and-fit :1231-1255 on dataset d: fit curve at the most likely (0) / median (1) parameters of the

@@ -108,6 +108,7 @@ def lib():
         L.orc_walker_last_l_matrix.argtypes = [C.c_void_p, _dp]
         L.orc_walker_acceptance.argtypes = [C.c_void_p, C.c_long, _lp, _lp]
         L.orc_walker_keep_walks.argtypes = [C.c_void_p, C.c_long]
+        L.orc_walker_modify.argtypes = [C.c_void_p, C.c_int, C.c_long]
         L.orc_walker_load_walk.argtypes = [C.c_void_p, _dp, _dp, C.c_long]
         L.orc_walker_data_and_fit.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int, _dp, C.c_long, _dp, _dp, _dp, _dp]
         L.orc_bench_many.restype = C.c_double
@@ -376,6 +377,11 @@ class Walker:
 
     def keep_walks(self, keep):
         lib().orc_walker_keep_walks(self.h, keep)
+
+    def modify(self, modify, number=0):
+        """walker-modify :burn-walks / :keep-walks / :reset / :reset-to-most-likely"""
+        mode = {"burn-walks": 1, "keep-walks": 2, "reset": 3, "reset-to-most-likely": 4}[str(modify).lstrip(":")]
+        self._chk(lib().orc_walker_modify(self.h, mode, int(number)))
 
     def load_walk(self, theta, prob):
         """replace the walk by (theta[n,P], prob[n]), newest first"""

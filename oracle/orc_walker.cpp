@@ -786,6 +786,34 @@ int orc_walker_keep_walks(orc_walker* w, long keep) {
   return 0;
 }
 
+// walker-modify :burn-walks :566-567 (drops the OLDEST burn-number steps), :reset :570-573 ((last walk): the walk shrinks
+// to its OLDEST step, which also becomes the last step), :reset-to-most-likely :574-578
+int orc_walker_modify(orc_walker* w, int mode, long number) {
+  switch (mode) {
+    case 1: {  // :burn-walks
+      const long keep = w->length - number;
+      if (keep < 0) return -1;  // subseq would signal an error
+      return orc_walker_keep_walks(w, keep);
+    }
+    case 2: return orc_walker_keep_walks(w, number);
+    case 3: {
+      if (w->walk.empty()) return -1;
+      Step s = w->walk.front();
+      w->walk.assign(1, s);
+      w->last = s;
+      w->length = 1;
+      return 0;
+    }
+    case 4: {
+      w->walk.assign(1, w->most_likely);
+      w->last = w->most_likely;
+      w->length = 1;
+      return 0;
+    }
+  }
+  return -1;
+}
+
 // CPU baseline: W independent walkers, chains split across threads
 double orc_bench_many(orc_walker* templ, const double* theta0, long W, const orc_adapt_cfg* cfg, int n_threads,
                       unsigned long long seed, double* last_prob, long max_steps) {

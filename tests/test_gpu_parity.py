@@ -771,6 +771,42 @@ def test_walker_set_with_per_walker_data_matches_oracle(orc, name, ll, shared_x)
     w.close()
 
 
+@pytest.mark.parametrize("modify,number", [("burn-walks", 120), ("reset", 0), ("reset-to-most-likely", 0)])
+def test_walker_modify_list_surgery(orc, modify, number):
+    """walker-modify :566-578 on every chain == the oracle's list surgery: :burn-walks drops the OLDEST steps, :reset keeps
+    the OLDEST step ((last walk) of a newest-first list) and makes it the last step, :reset-to-most-likely restarts from
+    the best step; a run taken up afterwards stays identical"""
+    cfg = workloads.c2(W=130, N=300)
+    w = workloads.make_walker(cfg)
+    rng = np.random.default_rng(31)
+    n = 300
+    z, u = rng.standard_normal((w.W, 2 * n, w.P)), rng.uniform(size=(w.W, 2 * n))
+    Lm = np.diag(0.003 * np.abs(cfg["theta_star"]))
+    w.many_steps(n, Lm, z=z[:, :n], u=u[:, :n])
+    w.modify(modify, burn_number=number)
+    st = w.stats()
+    th, pr, nv = w.trace(1000)
+    lth, lpr = w.last_step()
+    ows = {}
+    for c in (0, 64, 129):
+        ow = oracle_walker(orc, cfg)
+        ow.init(cfg["theta0"][c])
+        ow.many_steps(n, Lm, z=z[c, :n], u=u[c, :n])
+        ow.modify(modify, number)
+        oth, opr = ow.trace(0)
+        assert st["length"][c] == ow.length == len(opr) == nv[c] and st["age"][c] == ow.age
+        assert np.array_equal(th[c, :nv[c]], oth) and rel_err(pr[c, :nv[c]], opr, ll_scale(cfg)) < TOL
+        assert np.array_equal(lth[c], oth[0])
+        ows[c] = ow
+    w.many_steps(n, Lm, z=z[:, n:], u=u[:, n:])
+    th, pr, nv = w.trace(1000)
+    for c, ow in ows.items():
+        ow.many_steps(n, Lm, z=z[c, n:], u=u[c, n:])
+        oth, opr = ow.trace(0)
+        assert nv[c] == len(opr) and np.array_equal(th[c, :nv[c]], oth)
+    w.close()
+
+
 def test_walker_save_and_load_round_trip(tmp_path):
     """walker-save / walker-load (:971-1001, dead code in the reference, revived): an s-expression header in the layout
     of the reference's dump followed by the FP64 trace, newest step first"""
