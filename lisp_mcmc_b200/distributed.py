@@ -118,6 +118,18 @@ def gather_trace(walker, take, W):
     return gather_chains(th, W), gather_chains(pr, W), gather_chains(nv, W)
 
 
+def gather_stats(stats, W):
+    """The per-chain statistics of a chain-sharded walker set (Walker.stats(): length, age, acceptance over the last 200
+    steps, best / last prob, temperature ...) on every rank, in global chain order: one gather per field."""
+    stats = np.asarray(stats)
+    out = np.empty(W, dtype=stats.dtype)
+    for name in stats.dtype.names:
+        col = np.ascontiguousarray(stats[name])
+        wide = col.astype(np.int64) if col.dtype.kind in "iu" else col.astype(np.float64)
+        out[name] = gather_chains(wide, W).astype(col.dtype)
+    return out
+
+
 def max_over_ranks(value):
     """device-timed durations are reported as the maximum over ranks"""
     import torch

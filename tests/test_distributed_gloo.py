@@ -85,6 +85,18 @@ def _worker(rank, world, port, q):
         ref = np.array([ow.logp(g["theta0"][c])[0] for c in range(5)])
         out["datasets_bitwise"] = bool(np.array_equal(prob, ref))
 
+        # 3b. per-chain statistics (what Walker.stats() returns) gathered field by field in global chain order
+        sdt = [("length", "i8"), ("age", "i8"), ("accept_200", "f8"), ("shutting_down", "i4")]
+        mine = np.zeros(cnt, dtype=sdt)
+        mine["length"] = np.arange(lo, lo + cnt) + 100
+        mine["age"] = mine["length"] + 1
+        mine["accept_200"] = 0.25 + 0.01 * np.arange(lo, lo + cnt)
+        mine["shutting_down"] = np.arange(lo, lo + cnt) % 2
+        allst = D.gather_stats(mine, W)
+        out["stats_ok"] = bool(np.array_equal(allst["length"], np.arange(W) + 100) and allst.dtype == np.dtype(sdt) and
+                               np.array_equal(allst["accept_200"], 0.25 + 0.01 * np.arange(W)) and
+                               np.array_equal(allst["shutting_down"], np.arange(W) % 2))
+
         # 4. max over ranks
         out["max"] = D.max_over_ranks(10.0 + rank)
         dist.barrier()
@@ -114,6 +126,7 @@ def test_two_rank_gloo_host_logic():
         assert res[r]["uid_same"]
         assert res[r]["owners"] == [0, 1, 0]
         assert res[r]["datasets_bitwise"]
+        assert res[r]["stats_ok"]
         assert res[r]["max"] == 11.0
     assert res[0]["shard"] == (0, 4) and res[1]["shard"] == (4, 3)
     assert res[0]["chains_bitwise"]
