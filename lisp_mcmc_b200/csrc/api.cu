@@ -354,13 +354,28 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
   a.w_stride = s.sigma_shared ? 0 : s.n_pad;
   // shared x / sigma vectors are staged in shared memory (mfit_eval_perchain_body)
   const bool staged = a.x_stride == 0 && a.w_stride == 0 && a.n <= MFIT_PC_STAGE_MAX;
-  const size_t smem_pc = staged ? sizeof(double) * 3 * (size_t)((a.n + 31) & ~31LL) : 0;
+  const size_t n_pad32 = (size_t)((a.n + 31) & ~31LL);
+  size_t smem_pc = staged ? sizeof(double) * 3 * n_pad32 : 0;
+  // ... and the chains' own y rows go through a per-warp TMA ring when two CTAs per SM still fit with at least two
+  // stages (mfit_perchain_ring): rows of up to ~800 points; longer ones are read straight into registers
+  a.ring_stages = 0;
+  if (staged && a.n > 0 && getenv("MFIT_NO_PC_RING") == nullptr) {
+    const char* bk = getenv("MFIT_PC_RING_BUDGET_KB");  // experiments: shared memory one CTA may take (default: two CTAs per SM)
+    const size_t warps = MFIT_PC_THREADS / 32, budget = (bk ? (size_t)atoi(bk) : 110) * 1024;
+    for (int S = 3; S >= 2 && a.ring_stages == 0; S--) {
+      const size_t need = smem_pc + warps * S * n_pad32 * sizeof(double) + warps * S * sizeof(unsigned long long);
+      if (need <= budget) {
+        a.ring_stages = S;
+        smem_pc = need;
+      }
+    }
+  }
   const void* fpc = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_pc[s.ll_kind + (staged ? 3 : 0)]
                                               : mfit_builtin_perchain_kernel(s.family, s.degree, s.ll_kind, staged);
   if (!fpc) return fail(ctx, MFIT_ERR_STATE, "no per-walker kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
   auto itp = ctx->resident.find(fpc);
   if (itp == ctx->resident.end()) {
-    const size_t smem_max = sizeof(double) * 3 * MFIT_PC_STAGE_MAX;
+    const size_t smem_max = 112 * 1024;
     CU(cudaFuncSetAttribute(fpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CU(cudaFuncSetAttribute(fpc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0, sms = 0;

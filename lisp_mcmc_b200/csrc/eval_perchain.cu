@@ -5,7 +5,7 @@
 #include "mfit_internal.h"
 
 template <class Model, int LL, bool STAGED>
-__global__ void __launch_bounds__(MFIT_PC_THREADS, 2) mfit_eval_perchain_kernel(const __grid_constant__ MfitEvalArgs a) {
+__global__ void __launch_bounds__(MFIT_PC_THREADS, STAGED ? MFIT_PC_STAGED_CTAS : 2) mfit_eval_perchain_kernel(const __grid_constant__ MfitEvalArgs a) {
   mfit_eval_perchain_body_t<Model, LL, STAGED>(a);
 }
 

@@ -69,6 +69,8 @@ struct MfitEvalArgs {
   /* walker sets with per-walker data (mfit_eval_perchain_body): chain w reads x + w * x_stride (0: one x for all),
    * y / yw + w * pc_stride, w / c + w * w_stride; chains [cb0 * MFIT_CB, (cb0 + n_cb) * MFIT_CB) of this launch */
   long long x_stride, pc_stride, w_stride;  /* w_stride: rows of w / c (0: one sigma vector for all chains) */
+  int ring_stages;      /* walker sets, staged kernel: > 0 = every warp keeps this many y rows in flight through its own
+                           TMA ring in shared memory (mfit_perchain_ring); 0 = rows are read straight into registers */
   long long xd_stride;  /* distance between the component arrays of a multi-dimensional x (n_pad) */
   int idx[MFIT_MAXK];   /* built-in families: family slot -> shared parameter index */
   int degree;
@@ -507,6 +509,109 @@ __device__ __forceinline__ double mfit_perchain_pass(const Model& m, const doubl
   return sum;  // valid in lane 0
 }
 
+// STAGED with a ring (a.ring_stages = S >= 2): the chain's own y row -- the only per-chain data here -- is fetched by the
+// TMA engine (cp.async.bulk, one request per row) into a per-warp ring of S rows in shared memory, S - 1 rows ahead of the
+// one being evaluated.  A warp that reads its rows straight into registers alternates between waiting for memory and
+// computing, and 16 warps x 2 KB in flight per SM is about half of what HBM3e needs to stay busy (6.5 TB/s x ~0.8 us
+// = 35 KB per SM *on average*): the kernel ran at 0.43 of the copy peak.  With the ring the bytes in flight no longer
+// depend on what the warps are doing: 16 warps x (S - 1) rows of n_pad doubles per SM.
+// Shared memory: [x][1/sigma][c] (3 n_pad doubles, as for the register path), then [warp][stage][n_pad] doubles, then
+// [warp][stage] mbarriers.  Sums are formed exactly as in the register path (same four accumulators per lane, same
+// shuffle tree), so the two are bit-identical.
+template <class Model, int LL>
+__device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double* smem, long long n_pad) {
+  constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
+  constexpr int NARR = MfitTerm<LL>::NARR;
+  constexpr int U = MFIT_PC_U;
+  const int S = a.ring_stages;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  double* ring = smem + 3 * n_pad + (size_t)wib * S * n_pad;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 3 * n_pad + (size_t)nwarp * S * n_pad) + wib * S;
+  const double* xs = smem;
+  const double* ws = smem + n_pad;
+  const double* cs = smem + 2 * n_pad;
+  const long long warps = (long long)gridDim.x * nwarp;
+  const long long w_lo = (long long)a.cb0 * MFIT_CB;
+  long long w_hi = w_lo + (long long)a.n_cb * MFIT_CB;
+  if (w_hi > a.W) w_hi = a.W;
+  const long long first = w_lo + (long long)blockIdx.x * nwarp + wib;
+  const double* ybase = LL == MFITK_NORMAL ? a.yw : a.y;
+  const unsigned row_bytes = (unsigned)(n_pad * 8);
+  if (lane == 0)
+    for (int s = 0; s < S; s++) {
+      const long long ch = first + (long long)s * warps;
+      if (ch < w_hi) {
+        mfit_mbar_expect_tx(&bars[s], row_bytes);
+        mfit_tma_load_1d(ring + (size_t)s * n_pad, ybase + ch * a.pc_stride, row_bytes, &bars[s]);
+      }
+    }
+  Model m_next;
+  bool skip_next = false;
+  if (first < w_hi) {
+    m_next.load(a, first);
+    skip_next = a.skip != nullptr && a.skip[first] != 0;
+  }
+  const int n = (int)a.n;
+  long long k = 0;
+  for (long long chain = first; chain < w_hi; chain += warps, k++) {
+    const int slot = (int)(k % S);
+    Model m = m_next;
+    const bool skip = skip_next;
+    if (chain + warps < w_hi) {  // the next chain's parameters and its finished flag, one chain ahead
+      m_next.load(a, chain + warps);
+      skip_next = a.skip != nullptr && a.skip[chain + warps] != 0;
+    }
+    m.setup();
+    const bool unguarded = !GUARDED || (MfitTerm<LL>::USES == 0 && m.safe(a));  // theta is warp-uniform
+    mfit_mbar_wait(&bars[slot], (unsigned)((k / S) & 1));
+    const double* row = ring + (size_t)slot * n_pad;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double sum = 0.0;
+    bool redo = false;
+    if (!skip) {
+      MfitGuard gd;
+      gd.reset();
+      MfitNoGuard ng;
+      // blocks of 32 U points, the whole ones without a bounds test and with 32-bit indices (the register path spends
+      // 51 warp-instructions per point on 16 FP64 ones, ncu); the order of the additions is that of the register path
+      auto pass = [&](auto& g) {   // one instance per guard type: no per-point branch on `unguarded`
+        auto term = [&](int u, int j) {
+          const double w = NARR > 2 ? ws[j] : 0.0, c = NARR > 3 ? cs[j] : 0.0;
+          acc[u & 3] = MfitTerm<LL>::template add<false>(acc[u & 3], mfit_model_scalar<Model, false>(m, xs[j], g), row[j], w, c, g);
+        };
+        int j0 = lane;
+        for (; j0 + 32 * (U - 1) + (31 - lane) < n; j0 += 32 * U) {  // warp-uniform: the block's last point exists
+#pragma unroll
+          for (int u = 0; u < U; u++) term(u, j0 + 32 * u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (j0 + 32 * u < n) term(u, j0 + 32 * u);
+      };
+      if (unguarded) pass(ng);
+      else pass(gd);
+      redo = !unguarded && __any_sync(0xffffffffu, gd.tripped() ? 1 : 0) != 0;
+      if (redo) sum = mfit_perchain_pass<Model, LL, true, true>(m, xs, row, ws, cs, a.n, lane, gd);  // rare: libdevice
+    }
+    __syncwarp();  // every lane is done with the row: its slot goes back to the TMA engine before the sums are combined
+    if (lane == 0) {
+      const long long nxt = chain + (long long)S * warps;
+      if (nxt < w_hi) {
+        mfit_mbar_expect_tx(&bars[slot], row_bytes);
+        mfit_tma_load_1d(ring + (size_t)slot * n_pad, ybase + nxt * a.pc_stride, row_bytes, &bars[slot]);
+      }
+    }
+    if (!skip) {
+      if (!redo) {
+        sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum = sum + __shfl_down_sync(0xffffffffu, sum, off);
+      }
+      if (lane == 0) a.partial[chain] = sum;  // one segment
+    }
+  }
+}
+
 template <class Model, int LL, bool STAGED>
 __device__ __forceinline__ void mfit_eval_perchain_body_t(const MfitEvalArgs& a) {
   constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
@@ -520,6 +625,18 @@ __device__ __forceinline__ void mfit_eval_perchain_body_t(const MfitEvalArgs& a)
       if (NARR > 2) mfit_pc_smem[n_pad + i] = a.w[i];
       if (NARR > 3) mfit_pc_smem[2 * n_pad + i] = a.c[i];
     }
+  if (STAGED && a.ring_stages > 0) {
+    if ((threadIdx.x & 31) == 0) {  // every warp owns the mbarriers of its own ring
+      unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+                                     mfit_pc_smem + 3 * n_pad + (size_t)(blockDim.x >> 5) * a.ring_stages * n_pad) +
+                                 (threadIdx.x >> 5) * a.ring_stages;
+      for (int s_ = 0; s_ < a.ring_stages; s_++) mfit_mbar_init(&bars[s_], 1);
+      mfit_fence_mbar_init();
+    }
+    __syncthreads();
+    mfit_perchain_ring<Model, LL>(a, mfit_pc_smem, n_pad);
+    return;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);

@@ -771,6 +771,45 @@ def test_walker_set_with_per_walker_data_matches_oracle(orc, name, ll, shared_x)
     w.close()
 
 
+@pytest.mark.parametrize("W,n", [(300, 500), (20011, 96), (5, 1)])
+def test_walker_set_tma_ring_matches_register_path_and_oracle(orc, W, n):
+    """walker sets with a common x and sigma (the NV workload's shape): every warp streams its chains' y rows through
+    its own TMA ring in shared memory (mfit_perchain_ring).  Bit-identical to the path that reads the rows straight into
+    registers (MFIT_NO_PC_RING), also when a warp works through many chains (more chains than resident warps x ring
+    stages) and when some chains have finished; within 1e-12 of the oracle"""
+    import os
+    ns = workloads.nvset(W=W, N=n)
+    w = workloads.make_walker_set(ns, seed=3)
+    th0 = ns["theta0"]
+    p_ring = w.make_step(th0)[0]
+    os.environ["MFIT_NO_PC_RING"] = "1"
+    try:
+        p_reg = w.make_step(th0)[0]
+    finally:
+        del os.environ["MFIT_NO_PC_RING"]
+    assert np.array_equal(p_ring, p_reg)
+    x, Y = ns["data"]
+    for k in sorted({0, W // 2, W - 1}):
+        cfgk = dict(function=ns["function"], data=[[x, Y[k]]], data_error=ns["data_error"], keys=ns["keys"],
+                    log_liklihood=ns["log_liklihood"], log_prior=ns["log_prior"])
+        ref = oracle_walker(orc, cfgk).logp(th0[k])[0]
+        assert abs(p_ring[k] - ref) <= TOL * max(abs(ref), ll_scale(cfgk))
+    if W == 300:   # a run: chains that stop early (:prob-settle) are skipped by the kernel while the others go on
+        w.adaptive_steps(n=2500)
+        a = w.trace(4000)
+        w2 = workloads.make_walker_set(ns, seed=3)
+        os.environ["MFIT_NO_PC_RING"] = "1"
+        try:
+            w2.adaptive_steps(n=2500)
+        finally:
+            del os.environ["MFIT_NO_PC_RING"]
+        b = w2.trace(4000)
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v, equal_nan=True)
+        w2.close()
+    w.close()
+
+
 @pytest.mark.parametrize("modify,number", [("burn-walks", 120), ("reset", 0), ("reset-to-most-likely", 0)])
 def test_walker_modify_list_surgery(orc, modify, number):
     """walker-modify :566-578 on every chain == the oracle's list surgery: :burn-walks drops the OLDEST steps, :reset keeps
