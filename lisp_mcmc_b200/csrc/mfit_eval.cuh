@@ -522,7 +522,6 @@ template <class Model, int LL>
 __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double* smem, long long n_pad) {
   constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
   constexpr int NARR = MfitTerm<LL>::NARR;
-  constexpr int U = MFIT_PC_U;
   const int S = a.ring_stages;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   double* ring = smem + 3 * n_pad + (size_t)wib * S * n_pad;
@@ -572,20 +571,25 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       MfitGuard gd;
       gd.reset();
       MfitNoGuard ng;
-      // blocks of 32 U points, the whole ones without a bounds test and with 32-bit indices (the register path spends
-      // 51 warp-instructions per point on 16 FP64 ones, ncu); the order of the additions is that of the register path
+      // whole groups run without a bounds test and with 32-bit indices (the register path spends 51 warp-instructions
+      // per point on 16 FP64 ones, ncu); the order of the additions is that of the register path
       auto pass = [&](auto& g) {   // one instance per guard type: no per-point branch on `unguarded`
         auto term = [&](int u, int j) {
           const double w = NARR > 2 ? ws[j] : 0.0, c = NARR > 3 ? cs[j] : 0.0;
           acc[u & 3] = MfitTerm<LL>::template add<false>(acc[u & 3], mfit_model_scalar<Model, false>(m, xs[j], g), row[j], w, c, g);
         };
+        // groups of four rows of 32 points (row r adds into accumulator r mod 4, as in the register path's blocks of
+        // eight); only the last, incomplete group carries bounds tests
         int j0 = lane;
-        for (; j0 + 32 * (U - 1) + (31 - lane) < n; j0 += 32 * U) {  // warp-uniform: the block's last point exists
-#pragma unroll
-          for (int u = 0; u < U; u++) term(u, j0 + 32 * u);
+#pragma unroll 2
+        for (; j0 + 96 + (31 - lane) < n; j0 += 128) {  // warp-uniform: the group's last point exists
+          term(0, j0);
+          term(1, j0 + 32);
+          term(2, j0 + 64);
+          term(3, j0 + 96);
         }
 #pragma unroll
-        for (int u = 0; u < U; u++)
+        for (int u = 0; u < 4; u++)
           if (j0 + 32 * u < n) term(u, j0 + 32 * u);
       };
       if (unguarded) pass(ng);
