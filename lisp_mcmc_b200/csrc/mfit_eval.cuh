@@ -509,6 +509,33 @@ __device__ __forceinline__ double mfit_perchain_pass(const Model& m, const doubl
   return sum;  // valid in lane 0
 }
 
+// one chain's row out of shared memory: lane sums acc[0..3].  Whole groups of four rows of 32 points run without a
+// bounds test and with 32-bit indices (the register path spends 51 warp-instructions per point on 16 FP64 ones, ncu);
+// row r adds into accumulator r mod 4, the order of the register path's blocks of eight.  One instance per guard type,
+// so there is no per-point branch on it.  (A function template, not a generic lambda: NVRTC takes the latter's call
+// operator for a host function.)
+template <class Model, int LL, class G>
+__device__ __forceinline__ void mfit_ring_row(const Model& m, const double* xs, const double* ws, const double* cs,
+                                              const double* row, int n, int lane, double* acc, G& g) {
+  constexpr int NARR = MfitTerm<LL>::NARR;
+#define MFIT_RING_TERM(u, j)                                                                                      \
+  acc[u] = MfitTerm<LL>::template add<false>(acc[u], mfit_model_scalar<Model, false>(m, xs[j], g), row[j],          \
+                                             NARR > 2 ? ws[j] : 0.0, NARR > 3 ? cs[j] : 0.0, g)
+  int j0 = lane;
+#pragma unroll 2
+  for (; j0 + 96 + (31 - lane) < n; j0 += 128) {  // warp-uniform: the group's last point exists
+    MFIT_RING_TERM(0, j0);
+    MFIT_RING_TERM(1, j0 + 32);
+    MFIT_RING_TERM(2, j0 + 64);
+    MFIT_RING_TERM(3, j0 + 96);
+  }
+  if (j0 < n) MFIT_RING_TERM(0, j0);
+  if (j0 + 32 < n) MFIT_RING_TERM(1, j0 + 32);
+  if (j0 + 64 < n) MFIT_RING_TERM(2, j0 + 64);
+  if (j0 + 96 < n) MFIT_RING_TERM(3, j0 + 96);
+#undef MFIT_RING_TERM
+}
+
 // STAGED with a ring (a.ring_stages = S >= 2): the chain's own y row -- the only per-chain data here -- is fetched by the
 // TMA engine (cp.async.bulk, one request per row) into a per-warp ring of S rows in shared memory, S - 1 rows ahead of the
 // one being evaluated.  A warp that reads its rows straight into registers alternates between waiting for memory and
@@ -571,29 +598,8 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       MfitGuard gd;
       gd.reset();
       MfitNoGuard ng;
-      // whole groups run without a bounds test and with 32-bit indices (the register path spends 51 warp-instructions
-      // per point on 16 FP64 ones, ncu); the order of the additions is that of the register path
-      auto pass = [&](auto& g) {   // one instance per guard type: no per-point branch on `unguarded`
-        auto term = [&](int u, int j) {
-          const double w = NARR > 2 ? ws[j] : 0.0, c = NARR > 3 ? cs[j] : 0.0;
-          acc[u & 3] = MfitTerm<LL>::template add<false>(acc[u & 3], mfit_model_scalar<Model, false>(m, xs[j], g), row[j], w, c, g);
-        };
-        // groups of four rows of 32 points (row r adds into accumulator r mod 4, as in the register path's blocks of
-        // eight); only the last, incomplete group carries bounds tests
-        int j0 = lane;
-#pragma unroll 2
-        for (; j0 + 96 + (31 - lane) < n; j0 += 128) {  // warp-uniform: the group's last point exists
-          term(0, j0);
-          term(1, j0 + 32);
-          term(2, j0 + 64);
-          term(3, j0 + 96);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (j0 + 32 * u < n) term(u, j0 + 32 * u);
-      };
-      if (unguarded) pass(ng);
-      else pass(gd);
+      if (unguarded) mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, ng);
+      else mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, gd);
       redo = !unguarded && __any_sync(0xffffffffu, gd.tripped() ? 1 : 0) != 0;
       if (redo) sum = mfit_perchain_pass<Model, LL, true, true>(m, xs, row, ws, cs, a.n, lane, gd);  // rare: libdevice
     }

@@ -633,6 +633,38 @@ def test_multi_dimensional_x_type_errors():
     assert e.value.code == _lib.ERR_ARG
 
 
+def test_data_and_fit_with_walks_of_different_lengths(orc):
+    """after walker-adaptive-steps (:auto :prob-settle) the chains hold walks of different lengths: take is clamped per
+    chain (:1233-1235) and the 66 % count follows it"""
+    cfg = workloads.c2(W=70, N=250)
+    w = workloads.make_walker(cfg, seed=13)
+    w.adaptive_steps(n=6000)
+    lens = w.stats()["length"]
+    assert lens.min() < lens.max()
+    order = np.argsort(lens)
+    _check_data_and_fit(orc, cfg, w, [int(order[0]), int(order[len(order) // 2]), int(order[-1])], int(lens.min()) + 50,
+                        "most-likely", n_fit=60)
+    w.close()
+
+
+def test_restore_into_a_smaller_fixed_ring_keeps_the_newest_steps():
+    """mfit_chains_restore with a trace ring that cannot hold the whole saved walk (trace_capacity fixed by the caller):
+    the oldest steps drop out, like :max-walker-length; last step, age and most likely step are still the saved ones"""
+    cfg = workloads.c2(W=33, N=200)
+    a = workloads.make_walker(cfg, seed=2)
+    a.many_steps(1500, np.diag(0.002 * np.abs(cfg["theta_star"])))
+    th, pr, nv = a.trace(2000)
+    assert np.all(nv == 1501)
+    b = workloads.make_walker(cfg, seed=2, trace_capacity=1100)
+    b.restore(th[:, :1501], pr[:, :1501], nv, a.stats()["age"], *a.most_likely())
+    th2, pr2, nv2 = b.trace(2000)
+    assert np.all(nv2 == 1100)
+    assert np.array_equal(th2[:, :1100], th[:, :1100]) and np.array_equal(pr2[:, :1100], pr[:, :1100])
+    assert np.array_equal(b.last_step()[0], th[:, 0]) and np.array_equal(b.stats()["age"], a.stats()["age"])
+    assert np.array_equal(b.most_likely()[1], a.most_likely()[1])
+    a.close(); b.close()
+
+
 def test_two_stream_chain_groups_do_not_change_results(orc):
     """a run advances the chains as two groups on two streams (the per-chain kernels of one overlap the likelihood
     kernel of the other): bit-identical to the one-group run, with built-in and NVRTC priors, Philox and injected
