@@ -231,12 +231,15 @@ void plan_segments(mfit_ctx* ctx, Dataset& d) {
     return;
   }
   const long long n_tiles = (d.n + MFIT_TILE - 1) / MFIT_TILE;
-  // at most MFIT_MAX_SEG segments, and up to eight tiles per work item as long as that leaves >= 64 items per
-  // chain-block: per-item set-up costs ~4 % with one-tile items, and since a run overlaps the tail of one chain group's
-  // kernel with the next group's, fine granularity buys nothing (C2, bench.py with MFIT_SEG_TILES = 1 / 2 / 8 / 12:
-  // 0.471 / 0.460 / 0.445 / 0.442 ms per step; 12 slows the kernel on its own by 10 %, 8 does not)
+  // at most MFIT_MAX_SEG segments, and up to five tiles per work item as long as that leaves >= 64 items per
+  // chain-block: per-item set-up costs ~4 % with one-tile items.  Inside a run the granularity hardly matters, because
+  // the tail of one chain group's kernel overlaps the next group's (C2, bench.py with MFIT_SEG_TILES = 1 / 2 / 3 / 5 / 6 /
+  // 7 / 8 / 10 / 12: 0.471 / 0.460 / 0.445 / 0.443 / 0.442 / 0.442 / 0.442 / 0.444 / 0.442 ms per step), but a launch on
+  // its own (walker-make-step batches, the kernel-timing phase of bench.py) ends with a partly empty last wave: all
+  // 4096 C2 chains are 1568 items of eight tiles on 444 resident CTAs = four waves of eight tile-times where 28.2
+  // would do (0.497 ms), 2512 items of five tiles = six waves of five (0.439 ms; tools/seg_sweep.sh).
   long long tps = (n_tiles + MFIT_MAX_SEG - 1) / MFIT_MAX_SEG;
-  const long long want = n_tiles / 64 < 8 ? n_tiles / 64 : 8;
+  const long long want = n_tiles / 64 < 5 ? n_tiles / 64 : 5;
   if (tps < want) tps = want;
   if (ctx->seg_tiles_override > 0) tps = ctx->seg_tiles_override;
   else if (const char* e = getenv("MFIT_SEG_TILES")) { if (atoi(e) > 0) tps = atoi(e); }  // tuning aid
