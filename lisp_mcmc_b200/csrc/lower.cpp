@@ -171,6 +171,11 @@ struct Ex {
   std::string code;     // C expression (parenthesised where needed)
   i64 num = 0, den = 1; // T_RAT
   bool bconst = false, bval = false;  // T_BOOL known at translation time
+  // what is known about the dependence on the model's x, for the proof Model::safe() makes about the arguments of the
+  // fast math routines: 0 = does not depend on x (value = B), 1 = affine in x (value = A x + B), 2 = unknown.
+  // A and B are double-valued C expressions over parameters and constants only ("" = zero).
+  int xk = 2;
+  std::string A, B;
 };
 
 std::string fmt_double(double v) {
@@ -215,6 +220,42 @@ std::string as_code(const Ex& e, Ty to) {
 }
 Ty wider(Ty a, Ty b) { return a > b ? a : b; }
 
+// (A, B) of e if it is known to be affine in x
+bool affine_parts(const Ex& e, std::string& A, std::string& B) {
+  if (e.ty == T_BOOL) return false;
+  if (e.ty == T_RAT) { A.clear(); B = fmt_double(rat_value(e)); return true; }
+  if (e.xk == 0) { A.clear(); B = e.B; return true; }
+  if (e.xk == 1) { A = e.A; B = e.B; return true; }
+  return false;
+}
+std::string aff_join(const std::string& a, char op, const std::string& b) {
+  if (a.empty() && b.empty()) return "";
+  if (op == '+') return a.empty() ? b : b.empty() ? a : "(" + a + " + " + b + ")";
+  if (op == '-') return b.empty() ? a : a.empty() ? "(-" + b + ")" : "(" + a + " - " + b + ")";
+  if (a.empty() || b.empty()) return "";            // '*' with a zero factor
+  return "(" + a + " * " + b + ")";
+}
+// r = a op b: carry the affine form along when it survives the operation
+void affine_combine(Ex& r, char op, const Ex& a, const Ex& b) {
+  r.xk = 2;
+  if (r.ty == T_RAT || r.ty == T_BOOL) return;
+  std::string Aa, Ba, Ab, Bb;
+  if (!affine_parts(a, Aa, Ba) || !affine_parts(b, Ab, Bb)) return;
+  if (op == '+' || op == '-') {
+    r.A = aff_join(Aa, op, Ab);
+    r.B = aff_join(Ba, op, Bb);
+  } else if (op == '*') {
+    if (!Aa.empty() && !Ab.empty()) return;         // quadratic in x
+    r.A = Aa.empty() ? aff_join(Ba, '*', Ab) : aff_join(Aa, '*', Bb);
+    r.B = aff_join(Ba, '*', Bb);
+  } else {
+    if (!Ab.empty() || Bb.empty()) return;          // x in the divisor (or a zero divisor)
+    r.A = Aa.empty() ? "" : "(" + Aa + " / " + Bb + ")";
+    r.B = Ba.empty() ? "" : "(" + Ba + " / " + Bb + ")";
+  }
+  r.xk = r.A.empty() ? 0 : 1;
+}
+
 struct Lower {
   std::vector<std::string> keys;         // upper-case, no ':'
   std::vector<int> used;                 // theta indices referenced, in first-use order
@@ -224,6 +265,9 @@ struct Lower {
   bool fast_math = false;  // model lambdas: exp/log/sin/cos -> mfit_math.cuh (prior kernels keep libdevice)
   int uses = 0;            // MFIT_USES_* tables the lowered code needs
   bool guarded = false;    // some fast routine with a restricted domain is called
+  struct Check { std::string fn, A, B; };
+  std::vector<Check> checks;   // arguments of fast routines that are affine in x: what safe() has to bound
+  bool provable = true;        // every such argument is
   std::string x_name;      // the model's positional argument
   int x_dims = 0;          // > 0: x is a sequence and components 0 .. x_dims - 1 are read (elt / aref / nth / first ...)
   bool x_scalar = false;   // x is used as a number
@@ -234,7 +278,10 @@ struct Lower {
     bool seen = false;
     for (int u : used) seen = seen || u == i;
     if (!seen) used.push_back(i);
-    return mk(T_DBL, "th" + std::to_string(i));
+    Ex e = mk(T_DBL, "th" + std::to_string(i));
+    e.xk = 0;
+    e.B = e.code;
+    return e;
   }
   int key_index(std::string k) const {
     if (!k.empty() && k[0] == ':') k = k.substr(1);
@@ -283,7 +330,9 @@ struct Lower {
     if (op == '*' && b.ty == T_RAT && b.num == 1 && b.den == 1) return a;
     Ty t = wider(a.ty, b.ty);
     if (t == T_RAT) t = T_SGL;
-    return mk(t, "(" + as_code(a, t) + " " + op + " " + as_code(b, t) + ")");
+    Ex r = mk(t, "(" + as_code(a, t) + " " + op + " " + as_code(b, t) + ")");
+    affine_combine(r, op, a, b);
+    return r;
   }
 
   // SBCL intexp: binary powering, base squared each round (code/numbers.lisp)
@@ -302,15 +351,49 @@ struct Lower {
     }
   }
 
+  // the expression mentions nothing but parameters (th<i>), literals and casts: it can be evaluated in safe()
+  static bool only_parameters(const std::string& c) {
+    for (size_t i = 0; i < c.size();) {
+      const unsigned char ch = (unsigned char)c[i];
+      if (isdigit(ch) || (ch == '.' && i + 1 < c.size() && isdigit((unsigned char)c[i + 1]))) {  // a numeric literal
+        while (i < c.size() && (isalnum((unsigned char)c[i]) || c[i] == '.' ||
+                                ((c[i] == '+' || c[i] == '-') && (c[i - 1] == 'e' || c[i - 1] == 'E')))) i++;
+        continue;
+      }
+      if (isalpha(ch) || ch == '_') {
+        size_t j = i;
+        while (j < c.size() && (isalnum((unsigned char)c[j]) || c[j] == '_')) j++;
+        const std::string id = c.substr(i, j - i);
+        bool ok = id == "double" || id == "float";
+        if (!ok && id.size() > 2 && id[0] == 't' && id[1] == 'h') {
+          ok = true;
+          for (size_t k = 2; k < id.size(); k++) ok = ok && isdigit((unsigned char)id[k]);
+        }
+        if (!ok) return false;
+        i = j;
+        continue;
+      }
+      i++;
+    }
+    return true;
+  }
+
   Ex irrational(const char* fn0, const Ex& a) {
     std::string fn = fn0;
     if (a.ty == T_BOOL) throw Err(fn + " of a boolean");
     std::string tail = ")";
     if (fast_math) {
+      const std::string plain = fn;
       if (fn == "exp") { fn = "mfit_exp_t<SLOW>"; uses |= 1; guarded = true; tail = ", gd)"; }
       else if (fn == "log") { fn = "mfit_log_t<SLOW>"; uses |= 2; guarded = true; tail = ", gd)"; }
       else if (fn == "sin") { fn = "mfit_sin_t<SLOW>"; guarded = true; tail = ", gd)"; }
       else if (fn == "cos") { fn = "mfit_cos_t<SLOW>"; guarded = true; tail = ", gd)"; }
+      if (fn != plain) {   // a routine with a restricted fast domain: can safe() bound its argument over the x range?
+        Check c;
+        c.fn = plain;
+        if (affine_parts(a, c.A, c.B) && only_parameters(c.A) && only_parameters(c.B)) checks.push_back(c);
+        else provable = false;
+      }
     }
     if (a.ty == T_DBL) return mk(T_DBL, fn + "(" + a.code + tail);
     // rational or single argument: computed in double, result is a single-float
@@ -532,8 +615,10 @@ struct Lower {
   Ex lower(const Sx& s) {
     if (s.t == Sx::NUM) {
       if (s.nk == 0) return mk_rat(s.num, s.den);
-      if (s.nk == 1) return mk(T_SGL, fmt_float((float)s.fv));
-      return mk(T_DBL, fmt_double(s.fv));
+      Ex lit = s.nk == 1 ? mk(T_SGL, fmt_float((float)s.fv)) : mk(T_DBL, fmt_double(s.fv));
+      lit.xk = 0;
+      lit.B = as_code(lit, T_DBL);
+      return lit;
     }
     if (s.t == Sx::SYM) {
       if (s.sym == "PI") return mk(T_DBL, "3.141592653589793");
@@ -651,7 +736,9 @@ struct Lower {
         if (f == "-") {
           if (a[0].ty == T_RAT) return mk_rat(-a[0].num, a[0].den);
           if (a[0].ty == T_BOOL) throw Err("negation of a boolean");
-          return mk(a[0].ty, "(-" + a[0].code + ")");
+          Ex neg = mk(a[0].ty, "(-" + a[0].code + ")");
+          affine_combine(neg, '-', mk_rat(0, 1), a[0]);
+          return neg;
         }
         return arith('/', mk_rat(1, 1), a[0]);
       }
@@ -811,7 +898,10 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
   if (kind == 0) {
     if (positional.size() != 1) throw Err("a model lambda takes exactly one positional argument (x)");
     L.x_name = positional[0];
-    L.bind(positional[0], mk(T_DBL, "x"));
+    Ex xe = mk(T_DBL, "x");
+    xe.xk = 1;
+    xe.A = "1.0";
+    L.bind(positional[0], xe);
   } else {
     if (positional.size() != 2) throw Err("a prior lambda takes (params data)");
   }
@@ -844,7 +934,33 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
     out += "  __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {\n";
     out += "    const double* theta = a.theta; const long long stride = a.stride;\n    (void)theta; (void)stride; (void)chain;\n" + loads + "  }\n";
     out += "  __device__ __forceinline__ void setup() {}\n";
-    out += "  __device__ __forceinline__ bool safe(const MfitEvalArgs&) const { return false; }\n";
+    // safe(): every argument of a fast routine is affine in x with parameter-only coefficients, hence monotone over the
+    // data set's x range: bounding it at both ends bounds it everywhere (NaN anywhere makes a comparison false)
+    if (L.provable && !L.checks.empty() && L.x_dims == 0) {
+      std::string cond;
+      int ci = 0;
+      std::string pre2;
+      for (auto& c : L.checks) {
+        const std::string A = c.A.empty() ? "0.0" : c.A, B = c.B.empty() ? "0.0" : c.B;
+        const std::string v0 = "s" + std::to_string(ci) + "a", v1 = "s" + std::to_string(ci) + "b";
+        // with no dependence on x the range of x must not enter (0 * inf)
+        pre2 += "    const double " + v0 + " = " + (c.A.empty() ? B : "fma(" + A + ", a.xmin, " + B + ")") + ", " + v1 + " = " +
+                (c.A.empty() ? B : "fma(" + A + ", a.xmax, " + B + ")") + ";\n";
+        std::string t;
+        // plain comparisons, not fmax / fmin: those drop a NaN operand
+        auto both = [&](const std::string& pre_, const std::string& post_) {
+          return pre_ + v0 + post_ + " && " + pre_ + v1 + post_;
+        };
+        if (c.fn == "exp") t = both("fabs(", ") < 700.0");
+        else if (c.fn == "log") t = both("", " > 1e-290") + " && " + both("", " < 1e290");
+        else t = both("fabs(", ") < 9.0e4");
+        cond += (ci ? " && " : "") + t;
+        ci++;
+      }
+      out += "  __device__ __forceinline__ bool safe(const MfitEvalArgs& a) const {\n" + pre2 + "    return " + cond + ";\n  }\n";
+    } else {
+      out += "  __device__ __forceinline__ bool safe(const MfitEvalArgs&) const { return false; }\n";
+    }
     if (L.x_dims > 0)
       out += "  template <bool SLOW, class G>\n  __device__ __forceinline__ double evalv(const double (&xv)[XDIMS], G& gd) const {\n    (void)xv; (void)gd;\n" + stmts + "    return " + ret + ";\n  }\n};\n";
     else

@@ -16,7 +16,7 @@ HOST_PRELUDE = """
 #include <cstddef>
 #define __device__
 #define __forceinline__ inline
-struct MfitEvalArgs { const double* theta; long long stride; };
+struct MfitEvalArgs { const double* theta; long long stride; double xmin, xmax; };
 struct MfitGuard {};
 using std::fabs; using std::exp; using std::log; using std::sin; using std::cos; using std::sqrt; using std::pow;
 // the device build routes these through mfit_math.cuh (<= 2.4 ulp); here only the lowering itself is under test
@@ -161,3 +161,45 @@ def test_multi_dimensional_x_errors(text):
     with pytest.raises(_lib.MfitError) as e:
         _lib.lower_sexpr(text, ["a"], 0)
     assert e.value.code == _lib.ERR_SEXPR
+
+
+def test_lowered_model_proves_its_fast_math_arguments_safe():
+    """Model::safe() of a lowered lambda: when every argument of a fast routine (exp / log / sin / cos) is affine in x
+    with parameter-only coefficients it is monotone over the data set's x range, so bounding it at both ends lets the
+    chain take the guard-free loop; anything else keeps safe() = false (always guarded, as before)"""
+    keys = ["a", "b", "k"]
+    text = "(lambda (x &key a b k &allow-other-keys) (let ((u (* -1 k x))) (+ (* a (exp u)) (log (+ b (* 1/2 x))) (sin (- (* 3 x) a)))))"
+    code = _lib.lower_sexpr(text, keys, 0)
+    assert "bool safe(const MfitEvalArgs& a) const {" in code and ") < 700.0" in code and " > 1e-290" in code and ") < 9.0e4" in code
+    d = tempfile.mkdtemp()
+    src = os.path.join(d, "m.cpp")
+    tail = ('extern "C" int call(const double* th, double xmin, double xmax) { MfitEvalArgs a{th, 1, xmin, xmax}; MfitUser m; '
+            "m.load(a, 0); return m.safe(a) ? 1 : 0; }")
+    open(src, "w").write(HOST_PRELUDE + code + tail)
+    so = os.path.join(d, "m.so")
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src])
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.call.argtypes = [dp, C.c_double, C.c_double]
+    rng = np.random.default_rng(9)
+    seen = set()
+    for _ in range(400):
+        th = np.array([rng.uniform(-5, 5), rng.uniform(-3, 8), rng.choice([0.5, 40.0, 400.0]) * rng.uniform(-1, 1)])
+        xmin = rng.uniform(-6, 0)
+        xmax = xmin + rng.uniform(0.1, 12)
+        got = lib.call(th.ctypes.data_as(dp), xmin, xmax)
+        xs = np.linspace(xmin, xmax, 201)
+        e_arg, l_arg, s_arg = -th[2] * xs, th[1] + 0.5 * xs, 3 * xs - th[0]
+        inside = np.all(np.abs(e_arg) < 700) and np.all(l_arg > 1e-290) and np.all(np.abs(s_arg) < 9e4)
+        assert bool(got) == bool(inside), (th, xmin, xmax)
+        seen.add(bool(got))
+    assert seen == {True, False}
+    a = np.array([1.0, 1.0, 1.0])
+    assert lib.call(a.ctypes.data_as(dp), -np.inf, np.inf) == 0 and lib.call(a.ctypes.data_as(dp), 0.0, np.nan) == 0
+    nan_th = np.array([1.0, 1.0, np.nan])
+    assert lib.call(nan_th.ctypes.data_as(dp), 0.0, 1.0) == 0
+    # not affine in x, or built from a local that is not a parameter expression: no proof
+    for t in ["(lambda (x &key a b k &allow-other-keys) (+ a b k (exp (* x x))))",
+              "(lambda (x &key a b k &allow-other-keys) (+ a b (exp (* k (sin x)))))"]:
+        assert "safe(const MfitEvalArgs&) const { return false; }" in _lib.lower_sexpr(t, keys, 0)
+    assert "fabs(s0b) < 700.0" in _lib.lower_sexpr(workloads.USER_POLY5_EXP, ["c0", "c1", "c2", "c3", "c4", "c5", "k"], 0)
