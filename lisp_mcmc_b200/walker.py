@@ -670,6 +670,29 @@ def walker_save(walker, path, take=None):
     return walker.save(path, take)
 
 
+# "Functionality for a set of similar walker instances" :1003-1036.  A Walker here IS a set -- W chains advanced
+# together -- so the set forms are the plain ones with the leading chain axis kept.
+def walker_set_get(the_walker_set, get, take=None, param=None):
+    """walker-set-get :1029-1030: (mapcar (lambda (x) (walker-get x ...)) the-walker-set) -> results with a chain axis"""
+    return the_walker_set.get(get, take=take, param=param)
+
+
+def walker_set_save(the_walker_set, path, take=None):
+    """walker-set-save :1004-1010 (dead code in the reference): every chain's walk in one file"""
+    return the_walker_set.save(path, take)
+
+
+def walker_set_load(path, function, data, data_error=None, log_liklihood=None, log_prior=None, **gpu):
+    """walker-set-load :1012-1027 (dead code in the reference): rebuild the set and restore its walks"""
+    return walker_load(path, function=function, data=data, data_error=data_error, log_liklihood=log_liklihood,
+                       log_prior=log_prior, **gpu)
+
+
+def walker_set_delete(the_walker_set):
+    """walker-set-delete :1032-1033 / walker-modify :delete :579-580: frees the device memory of the set"""
+    the_walker_set.close()
+
+
 def mcmc_fit(**kw):
     """mcmc-fit :1165-1175"""
     w = walker_create(**kw)

@@ -188,3 +188,15 @@ def test_file_reader_pages(tmp_path):
     assert specs["header-lines"] == 1 and specs["data-rows"] == 3 and specs["num-pages"] == 2
     pages = mio.read_file_to_data(str(p), delim=";", pages=True)
     assert len(pages) == 2 and np.array_equal(pages[1][0], [4.0, 5.0, 6.0]) and np.array_equal(pages[0][1], [1.5, 2.5, 3.5])
+
+
+def test_reference_function_names_are_exported():
+    """the host mirror keeps the reference's exported names for the path (mcmc-fitting.lisp `export` forms) -- including
+    the walker-set forms :1003-1036, which a walker SET (W chains in one object) serves directly"""
+    import lisp_mcmc_b200 as m
+    for name in ["walker_create", "walker_adaptive_steps", "walker_adaptive_steps_full", "walker_many_steps",
+                 "walker_sample_region", "walker_force_take_step", "walker_get", "walker_save", "walker_load", "mcmc_fit",
+                 "walker_set_create", "walker_set_get", "walker_set_save", "walker_set_load", "walker_set_delete", "linspace"]:
+        assert callable(getattr(m, name)), name
+    for meth in ["data_and_fit", "modify", "keep_walks", "restore", "analytics", "make_step", "trace", "stats"]:
+        assert callable(getattr(m.Walker, meth)), meth
