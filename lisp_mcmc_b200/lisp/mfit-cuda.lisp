@@ -28,7 +28,7 @@
   (:use :cl)
   (:export #:gpu-lambda #:gpu-builtin #:gpu-walker #:walker-create #:walker-adaptive-steps
            #:walker-adaptive-steps-full #:walker-many-steps #:walker-sample-region #:walker-force-take-step
-           #:walker-get #:walker-get-data-and-fit #:walker-save #:walker-load #:walker-modify #:walker-free #:mcmc-fit #:mfit-walker-estop #:lower-to-cuda #:walker-set-create))
+           #:walker-get #:walker-get-data-and-fit #:walker-save #:walker-load #:walker-modify #:walker-set-get #:walker-free #:mcmc-fit #:mfit-walker-estop #:lower-to-cuda #:walker-set-create))
 (in-package :mfit-cuda)
 
 (cffi:define-foreign-library libmfit-cuda (t (:default "libmfit_cuda")))
@@ -462,6 +462,11 @@ curve and the envelope over the best 66 % of the walk are evaluated on the devic
               (with-traps-masked
                 (chk ctx (%chains-restore ctx rows th pr nv (cffi:null-pointer) (cffi:null-pointer) (cffi:null-pointer)))))
             walker))))))
+
+(defun walker-set-get (walker &key (get :steps) take param)
+  "walker-set-get :1029-1030: a gpu-walker is a set of chains; one walker-get result per chain."
+  (loop for c below (gpu-walker-n-walkers walker)
+        collect (walker-get walker :get get :take take :param param :chain c)))
 
 (defun walker-modify (walker &key (modify :keep-walks) burn-number keep-number)
   "walker-modify :546-580 on the device, every chain: :burn-walks :keep-walks :reset :reset-to-most-likely."
