@@ -200,3 +200,38 @@ def test_reference_function_names_are_exported():
         assert callable(getattr(m, name)), name
     for meth in ["data_and_fit", "modify", "keep_walks", "restore", "analytics", "make_step", "trace", "stats"]:
         assert callable(getattr(m.Walker, meth)), meth
+
+
+def test_lisp_host_file_is_balanced():
+    """no Common Lisp in the image: at least the reader must be able to get through lisp/mfit-cuda.lisp -- parentheses
+    balance outside strings, comments and character literals, and every top-level form starts at depth 0"""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lisp_mcmc_b200", "lisp", "mfit-cuda.lisp")
+    s = open(path).read()
+    depth, i, n, forms = 0, 0, len(s), 0
+    while i < n:
+        c = s[i]
+        if c == ";":
+            while i < n and s[i] != "\n":
+                i += 1
+            continue
+        if c == "#" and s[i + 1:i + 2] == "|":
+            i = s.index("|#", i + 2) + 2
+            continue
+        if c == '"':
+            i += 1
+            while s[i] != '"':
+                i += 2 if s[i] == "\\" else 1
+            i += 1
+            continue
+        if c == "#" and s[i + 1:i + 2] == "\\":
+            i += 3
+            continue
+        if c == "(":
+            forms += depth == 0
+            depth += 1
+        elif c == ")":
+            depth -= 1
+            assert depth >= 0, "unbalanced ) near offset %d" % i
+        i += 1
+    assert depth == 0 and forms > 50
