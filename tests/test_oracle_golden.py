@@ -185,3 +185,36 @@ def test_data_and_fit_follows_the_list_definition(orc):
         assert np.array_equal(xf, orc.linspace(-4.0, 10.0, 40))
     # (* 0.66 take) is a single-float product: take = 150 gives 99.00001 -> 100 steps, where 0.66d0 would give 99
     assert int(np.ceil(np.float32(0.66) * np.float32(150))) == 100
+
+
+def test_walker_modify_list_surgery_on_the_oracle(orc):
+    """walker-modify :546-580 restated: the walk is newest-first, so :burn-walks (subseq walk 0 (- length n)) drops the
+    OLDEST n steps, :keep-walks keeps the newest, :reset keeps (last walk) = the OLDEST step and makes it the last
+    step, :reset-to-most-likely restarts from the best step; none of them touches walker-age"""
+    ow = orc.Walker(["b", "m"], 1)
+    ow.dataset(0, [-4.0, -1, 2, 5, 10], [0.0, 2, 5, 9, 13], 0.2)
+    ow.model_sexpr(0, "(lambda (x &key m b &allow-other-keys) (+ b (* m x)))")
+
+    def fresh():
+        ow.init([-1.0, 2.0])
+        rng = np.random.default_rng(1)
+        ow.many_steps(40, 0.05 * np.eye(2), z=rng.standard_normal((40, 2)), u=rng.uniform(size=40))
+        return ow.trace(0)
+
+    th, pr = fresh()
+    assert len(pr) == 41 and ow.age == 41
+    ow.modify("burn-walks", 10)
+    t2, p2 = ow.trace(0)
+    assert ow.length == 31 and ow.age == 41 and np.array_equal(t2, th[:31]) and np.array_equal(p2, pr[:31])
+    th, pr = fresh()
+    ow.modify("keep-walks", 7)
+    assert ow.length == 7 and np.array_equal(ow.trace(0)[0], th[:7])
+    th, pr = fresh()
+    ow.modify("reset")
+    t2, p2 = ow.trace(0)
+    assert ow.length == 1 and ow.age == 41 and np.array_equal(t2[0], th[-1]) and p2[0] == pr[-1]   # the FIRST step ever taken
+    th, pr = fresh()
+    best = ow.most_likely()
+    ow.modify("reset-to-most-likely")
+    t2, p2 = ow.trace(0)
+    assert ow.length == 1 and np.array_equal(t2[0], best[0]) and p2[0] == best[1] == pr.max()
