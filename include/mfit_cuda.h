@@ -137,6 +137,9 @@ int mfit_compile_sexpr(const char* lambda_text, const char* const* key_names, in
 /* points per reduction segment = 128 * tiles (0 = default: a function of the point count only, so that
  * log-likelihood bits do not depend on chain count or GPU count) */
 int mfit_set_segment_tiles(mfit_ctx* ctx, int tiles_per_segment);
+/* the geometry in use for data set d once chains exist or a batch has been evaluated: 128-point tiles per segment and
+ * segments (= partial sums per chain, added in segment order); tests pin parity at the benchmarked geometry with it */
+int mfit_segment_geometry(mfit_ctx* ctx, int d, int32_t* tiles_per_segment, int32_t* n_segments);
 
 /* ---- walker-make-step :1067-1070 over a batch of parameter vectors ------------------------------
  * theta: W x P row-major.  ll, lp: W x D row-major per-dataset terms (either may be NULL);

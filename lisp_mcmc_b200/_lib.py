@@ -55,6 +55,7 @@ SIGNATURES = {
     "mfit_lower_sexpr": (C.c_int, [C.c_char_p, _cpp, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]),
     "mfit_compile_sexpr": (C.c_int, [C.c_char_p, _cpp, C.c_int, C.c_int, C.c_char_p, C.c_int]),
     "mfit_set_segment_tiles": (C.c_int, [C.c_void_p, C.c_int]),
+    "mfit_segment_geometry": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip]),
     "mfit_eval_logp": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp, _dp]),
     "mfit_chains_init": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_uint64, C.c_int64, C.c_int64]),
     "mfit_run_adaptive": (C.c_int, [C.c_void_p, C.POINTER(AdaptCfg), _dp, _dp, _dp, C.c_int64, _lp]),

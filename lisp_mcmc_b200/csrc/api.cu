@@ -124,6 +124,8 @@ struct mfit_ctx {
   double* lshared_dev = nullptr;
   int* active_dev = nullptr;
   int* active_host = nullptr;  // pinned [4]
+  int* xflag_dev = nullptr;    // [n_ranks][2] (chains still active, stop requested) of every rank: the collective stop test
+  int* xflag_host = nullptr;   // pinned copy
   cudaEvent_t poll_ev[4];
   bool poll_ev_made = false;
 
@@ -723,8 +725,11 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
     if (grp[g].w1 > c.W) grp[g].w1 = c.W;
     if (grp[g].w0 > c.W) grp[g].w0 = c.W;
   }
+  bool stop_seen = false;
   for (; t < t_end && !all_done; t++) {
-    if (ctx->stop.load()) break;  // mfit-walker-estop, :904
+    // mfit-walker-estop, :904.  With the data sets sharded over ranks every step holds a collective, so all ranks must
+    // leave the loop at the same t: the flag is then only looked at -- all-gathered -- at the poll boundaries below.
+    if (!ctx->sharded && ctx->stop.load()) break;
     r.t = t;
     for (int g = 0; g < n_groups; g++) {
       const Group& G = grp[g];
@@ -746,7 +751,31 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
       mfit_launch_reest(cg, rn, G.st);
       ctx->launches += 2;
     }
-    if ((t + 1) % poll_every == 0) {
+    if (ctx->sharded && (t + 1) % poll_every == 0) {
+      // Collective, deterministic stop test: every rank holds the same chains (so the same active count) but its own
+      // stop flag and its own host timing.  (active, stop) of all ranks are all-gathered and read back with a blocking
+      // copy at the same step on every rank; any stop request, or no chain left, ends the loop everywhere at t + 1.
+      const int R = ctx->n_ranks;
+      if (!ctx->xflag_dev) {
+        CU(cudaMalloc(&ctx->xflag_dev, sizeof(int) * 2 * R));
+        CU(cudaMallocHost(&ctx->xflag_host, sizeof(int) * 2 * R));
+      }
+      mfit_launch_count_active(c, ctx->xflag_dev + 2 * ctx->rank, ctx->stream);
+      ctx->launches++;
+      ctx->xflag_host[2 * ctx->rank + 1] = ctx->stop.load();
+      CU(cudaMemcpyAsync(ctx->xflag_dev + 2 * ctx->rank + 1, ctx->xflag_host + 2 * ctx->rank + 1, sizeof(int),
+                         cudaMemcpyHostToDevice, ctx->stream));
+      std::string er;
+      rc = mfit_nccl_allgather_bytes(ctx->comm, ctx->xflag_dev + 2 * ctx->rank, ctx->xflag_dev, 2 * sizeof(int), ctx->stream, er);
+      if (rc) return fail(ctx, rc, "%s", er.c_str());
+      CU(cudaMemcpyAsync(ctx->xflag_host, ctx->xflag_dev, sizeof(int) * 2 * R, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      for (int k = 0; k < R; k++) {
+        if (ctx->xflag_host[2 * k] == 0) all_done = true;
+        if (ctx->xflag_host[2 * k + 1] != 0) stop_seen = true;
+      }
+      if (stop_seen) { t++; break; }
+    } else if ((t + 1) % poll_every == 0) {
       // lagging poll: look at the answer of an earlier query if it has arrived; never block
       for (int s = 0; s < 4; s++)
         if (poll_pending[s] && cudaEventQuery(ctx->poll_ev[s]) == cudaSuccess) {
@@ -772,7 +801,7 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
   ctx->rows_upper += t - ctx->run_t;
   if (steps_done) *steps_done = t - ctx->run_t;
   ctx->run_t = t;
-  const bool fin = all_done || t >= ctx->run_max || ctx->stop.load();
+  const bool fin = all_done || t >= ctx->run_max || (ctx->sharded ? stop_seen : ctx->stop.load() != 0);
   if (fin) ctx->run_open = false;
   if (finished) *finished = fin ? 1 : 0;
   return 0;
@@ -838,6 +867,8 @@ void mfit_ctx_destroy(mfit_ctx* ctx) {
   free_dev(ctx->temps_dev); free_dev(ctx->z_dev); free_dev(ctx->u_dev); free_dev(ctx->lshared_dev);
   free_dev(ctx->active_dev); free_dev(ctx->flush_buf); free_dev(ctx->sched_dev);
   if (ctx->active_host) cudaFreeHost(ctx->active_host);
+  free_dev(ctx->xflag_dev);
+  if (ctx->xflag_host) cudaFreeHost(ctx->xflag_host);
   for (int i = 0; i < 2; i++)
     if (ctx->stage[i]) { cudaFreeHost(ctx->stage[i]); cudaEventDestroy(ctx->stage_ev[i]); }
   if (ctx->poll_ev_made) for (auto& e : ctx->poll_ev) cudaEventDestroy(e);
@@ -1147,6 +1178,16 @@ int mfit_set_segment_tiles(mfit_ctx* ctx, int tiles_per_segment) {
   g_alloc_stream = ctx->stream;
   if (ctx->have_chains) chains_free(ctx);
   ctx->seg_tiles_override = tiles_per_segment;
+  return 0;
+}
+
+int mfit_segment_geometry(mfit_ctx* ctx, int d, int32_t* tiles_per_segment, int32_t* n_segments) {
+  NEED_DS(d);
+  Dataset& s = ctx->ds[d];
+  if (s.n < 0) return fail(ctx, MFIT_ERR_STATE, "dataset %d has no data", d);
+  plan_segments(ctx, s);
+  if (tiles_per_segment) *tiles_per_segment = s.tiles_per_seg;
+  if (n_segments) *n_segments = s.n_seg;
   return 0;
 }
 

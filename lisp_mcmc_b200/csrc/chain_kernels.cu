@@ -626,7 +626,7 @@ __global__ void k_count_active(const MfitChains c, int* out) {
 }
 __global__ void k_keep_walks(const MfitChains c, long long keep) {  // :568-569
   long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w < c.W) c.length[w] = keep;
+  if (w < c.W && c.length[w] > keep) c.length[w] = keep;  // (subseq walk 0 keep) of a shorter walk is an error in the reference: never grow
 }
 // walker-modify :burn-walks :566-567 (the walk loses its OLDEST burn-number steps), :reset :570-573 ((last walk): the walk
 // shrinks to its OLDEST step, which also becomes the last step) and :reset-to-most-likely :574-578.  The ring keeps the

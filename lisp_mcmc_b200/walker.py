@@ -334,9 +334,12 @@ class Walker:
                 raise ValueError("u must be W x nstream and come with z")
         return z, u, nstream
 
-    def adaptive_steps_full(self, n=100000, temperature=1e3, auto=None, sampling_optimization=None,
-                            max_walker_length=None, l_matrix=None, z=None, u=None, greedy=False):
-        """walker-adaptive-steps-full :862-942.  `auto` = "prob-settle" or None (:slope-settle is not supported)."""
+    def adaptive_steps_full(self, n=100000, temperature=1e3, auto="prob-settle", sampling_optimization=None,
+                            max_walker_length=None, l_matrix=None, z=None, u=None, greedy=False, max_steps=None):
+        """walker-adaptive-steps-full :862-942.  `auto` = "prob-settle" (the reference's default: `(or :prob-settle
+        :slope-settle nil)` evaluates to :prob-settle) or None / False for nil; :slope-settle is not supported.
+        max_steps (not in the reference): leave the loop after that many take-step calls, as a stop request would
+        (mfit-walker-estop :904) -- used by tests and benchmarks to time or compare the first iterations of a long run."""
         if auto in ("slope-settle", ":slope-settle"):
             raise NotImplementedError(":slope-settle runs a nested mcmc-fit on the host (:886-887); use :prob-settle")
         cfg = _lib.AdaptCfg(int(np.floor(n)), float(temperature), _AUTO[auto], _OPT[sampling_optimization],
@@ -346,7 +349,12 @@ class Walker:
         if lm is not None and lm.shape != (self.P, self.P):
             raise ValueError(":l-matrix must be P x P")
         launched = C.c_int64()
-        self._chk(self._L.mfit_run_adaptive(self._h, C.byref(cfg), _ptr(lm), _ptr(z), _ptr(u), nstream, C.byref(launched)))
+        if max_steps is None:
+            self._chk(self._L.mfit_run_adaptive(self._h, C.byref(cfg), _ptr(lm), _ptr(z), _ptr(u), nstream, C.byref(launched)))
+        else:
+            fin = C.c_int()
+            self._chk(self._L.mfit_run_begin(self._h, C.byref(cfg), _ptr(lm), _ptr(z), _ptr(u), nstream))
+            self._chk(self._L.mfit_run_advance(self._h, int(max_steps), C.byref(launched), C.byref(fin)))
         self.last_steps_launched = launched.value
         return self
 
@@ -375,6 +383,12 @@ class Walker:
     def request_stop(self):
         """(setf mfit-walker-estop t) :860"""
         self._L.mfit_request_stop(self._h)
+
+    def segment_geometry(self, d=0):
+        """(tiles per segment, segments) the likelihood kernel uses for data set d (mfit_segment_geometry)"""
+        t, n = C.c_int32(), C.c_int32()
+        self._chk(self._L.mfit_segment_geometry(self._h, int(d), C.byref(t), C.byref(n)))
+        return t.value, n.value
 
     def set_groups(self, n_groups):
         """0 = automatic, 1 / 2 = advance the chains as one / two groups on separate streams (mfit_set_groups)"""
@@ -536,8 +550,11 @@ class Walker:
             " ".join(str(int(v)) for v in st["age"]))
         blob = np.concatenate([pr[:, :, None], th], axis=2).astype("<f8")
         best = np.concatenate([bpr[:, None], bth], axis=1).astype("<f8")
+        hb = hdr.encode()
         with open(path, "wb") as f:
-            f.write(hdr.encode())
+            # lambda texts are usually multi-line Lisp source: the header is length-prefixed by a Lisp comment line
+            f.write((";; mfit-walker header-bytes=%d\n" % len(hb)).encode())
+            f.write(hb)
             f.write(struct.pack("<q", blob.size))
             f.write(blob.tobytes())
             f.write(struct.pack("<q", best.size))
@@ -567,7 +584,9 @@ def walker_load(path, function=None, data=None, data_error=None, log_liklihood=N
     Philox key and ages included, so that it goes on exactly like the saved one."""
     import re
     with open(path, "rb") as f:
-        hdr = f.readline().decode()
+        first = f.readline().decode()
+        m = re.match(r";; mfit-walker header-bytes=(\d+)", first)
+        hdr = f.read(int(m.group(1))).decode() if m else first   # files written before the length prefix: one line
         (cnt,) = struct.unpack("<q", f.read(8))
         blob = np.frombuffer(f.read(cnt * 8), dtype="<f8")
         tail = f.read(8)

@@ -25,13 +25,13 @@ def main():
     W, n = 37, 400
     cfg = workloads.c2(W=W, N=3000)
     w = D.walker_create_sharded(cfg, "chains", seed=11)
-    w.adaptive_steps_full(n=n, temperature=10)
+    w.adaptive_steps_full(n=n, temperature=10, auto=None)
     th, pr, nv = D.gather_trace(w, 2001, W)
     w.close()
     ok1 = True
     if rank == 0:
         w0 = workloads.make_walker(cfg, seed=11, device=local_rank)
-        w0.adaptive_steps_full(n=n, temperature=10)
+        w0.adaptive_steps_full(n=n, temperature=10, auto=None)
         th0, pr0, nv0 = w0.trace(2001)
         w0.close()
         m = int(nv0.max())
@@ -42,13 +42,13 @@ def main():
     Dn = max(world, 3)
     g = workloads.c4(W=24, D=Dn, N=2000)
     wg = D.walker_create_sharded(g, "datasets", seed=5)
-    wg.adaptive_steps_full(n=300, temperature=10)
+    wg.adaptive_steps_full(n=300, temperature=10, auto=None)
     thg, prg, nvg = wg.trace(2001)
     wg.close()
     ok2 = True
     if rank == 0:
         w1 = workloads.make_walker(g, seed=5, device=local_rank)
-        w1.adaptive_steps_full(n=300, temperature=10)
+        w1.adaptive_steps_full(n=300, temperature=10, auto=None)
         th1, pr1, nv1 = w1.trace(2001)
         w1.close()
         m = int(nv1.max())

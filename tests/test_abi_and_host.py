@@ -235,3 +235,17 @@ def test_lisp_host_file_is_balanced():
             assert depth >= 0, "unbalanced ) near offset %d" % i
         i += 1
     assert depth == 0 and forms > 50
+
+
+def test_adaptive_defaults_match_the_reference_lambda_list():
+    """walker-adaptive-steps-full (mcmc-fitting.lisp:862): (n 100000) (temperature 1d3) (auto (or :prob-settle
+    :slope-settle nil)) -> :prob-settle.  The Python mirror and the Lisp host must agree with it and with each other."""
+    import inspect
+    from lisp_mcmc_b200.walker import Walker
+    sig = inspect.signature(Walker.adaptive_steps_full).parameters
+    assert sig["n"].default == 100000 and sig["temperature"].default == 1e3 and sig["auto"].default == "prob-settle"
+    txt = open(os.path.join(ROOT, "lisp_mcmc_b200", "lisp", "mfit-cuda.lisp")).read()
+    m = re.search(r"\(defun walker-adaptive-steps-full \(walker &key \(n (\d+)\) \(temperature ([0-9d.]+)\) \(auto (:[a-z-]+)\)", txt)
+    assert m and m.group(1) == "100000" and m.group(2) == "1d3" and m.group(3) == ":prob-settle"
+    sig = inspect.signature(Walker.adaptive_steps).parameters
+    assert sig["n"].default == 30000          # walker-adaptive-steps :946

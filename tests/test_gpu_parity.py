@@ -338,8 +338,8 @@ def test_resume_reestimates_l_matrix_from_existing_walk(orc):
     rng = np.random.default_rng(15)
     z1, u1 = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
     z2, u2 = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
-    w.adaptive_steps_full(n=n, temperature=10, z=z1, u=u1)
-    w.adaptive_steps_full(n=n, temperature=10, z=z2, u=u2)
+    w.adaptive_steps_full(n=n, temperature=10, auto=None, z=z1, u=u1)
+    w.adaptive_steps_full(n=n, temperature=10, auto=None, z=z2, u=u2)
     th, pr, nv = w.trace(2 * n + 1)   # walker-create's first step + n take-steps per run
     ow = oracle_walker(orc, cfg)
     for c in range(4):
@@ -357,7 +357,7 @@ def test_philox_run_replays_through_oracle(orc):
     cfg = workloads.c2(W=6, N=500)
     w = workloads.make_walker(cfg, seed=1234, chain_id_base=77)
     n = 1500
-    w.adaptive_steps_full(n=n, temperature=10)
+    w.adaptive_steps_full(n=n, temperature=10, auto=None)
     z, u = w.philox_stream(1, 2000)   # the first take-step happens at walker age 1; n <= 2000 runs the full 2000-step tail (:906)
     assert abs(z.mean()) < 0.05 and abs(z.std() - 1) < 0.05 and 0.45 < u.mean() < 0.55 and u.min() > 0 and u.max() < 1
     _compare_chain(orc, cfg, w, z, u,
@@ -370,14 +370,14 @@ def test_chain_sharding_is_bit_identical(orc):
     cfg = workloads.c2(W=10, N=700)
     n = 800
     w = workloads.make_walker(cfg, seed=99)
-    w.adaptive_steps_full(n=n, temperature=10)
+    w.adaptive_steps_full(n=n, temperature=10, auto=None)
     th, pr, nv = w.trace(n)
     parts = []
     from lisp_mcmc_b200 import shard_chains
     for r in range(2):
         lo, cnt = shard_chains(10, r, 2)
         wr = workloads.make_walker(cfg, theta0=cfg["theta0"][lo:lo + cnt], seed=99, chain_id_base=lo)
-        wr.adaptive_steps_full(n=n, temperature=10)
+        wr.adaptive_steps_full(n=n, temperature=10, auto=None)
         parts.append(wr.trace(n))
         wr.close()
     th2 = np.concatenate([p[0] for p in parts]); pr2 = np.concatenate([p[1] for p in parts])
@@ -421,7 +421,7 @@ def test_errors_are_codes_not_crashes():
         walker_create(function=cfg["function"], data=[[1.0, 2.0], [1.0]], params=[("a", 1.0)])
     w = workloads.make_walker(cfg)
     with pytest.raises(_lib.MfitError) as e:
-        w.adaptive_steps_full(n=500, z=np.zeros((4, 10, 5)), u=np.zeros((4, 10)))
+        w.adaptive_steps_full(n=500, auto=None, z=np.zeros((4, 10, 5)), u=np.zeros((4, 10)))
     assert e.value.code == _lib.ERR_STREAM
     w.close()
 
@@ -460,7 +460,7 @@ def test_trace_analytics_match_reference_definitions(orc, take):
     (covariance and Cholesky through the oracle's restatement of :614-643 / :583-598: bit-identical)"""
     cfg = workloads.c2(W=9, N=400)
     w = workloads.make_walker(cfg, seed=3)
-    w.adaptive_steps_full(n=1200, temperature=10)
+    w.adaptive_steps_full(n=1200, temperature=10, auto=None)
     a = w.analytics(take)
     th, pr, nv = w.trace(take)
     for c in range(w.W):
@@ -523,7 +523,7 @@ def _fn_text(cfg, d):
 def test_data_and_fit_envelope_matches_reference_definition(orc, take, which):
     cfg = workloads.c2(W=131, N=300)
     w = workloads.make_walker(cfg, seed=5)
-    w.adaptive_steps_full(n=900, temperature=10)
+    w.adaptive_steps_full(n=900, temperature=10, auto=None)
     xf, mx, mn, yf, xd, yd, par = _check_data_and_fit(orc, cfg, w, [0, 64, 130], take, which, n_fit=1000 if take == 400 else 120)
     # :x-shift / :y-shift are plain additions (:1236-1247, :1251-1252)
     xs, mxs, mns, yfs, xds, yds, _ = w.data_and_fit(take=take, which_solution=which, n_fit=len(xf), x_shift=2.5, y_shift=-1.0)
@@ -537,12 +537,12 @@ def test_data_and_fit_global_fit_and_user_model(orc):
     through the same kernel body; a walk cut by walker-modify :keep-walks is searched as it stands"""
     g4 = workloads.c4(W=40, D=2, N=500)
     w = workloads.make_walker(g4, seed=9)
-    w.adaptive_steps_full(n=500, temperature=10)
+    w.adaptive_steps_full(n=500, temperature=10, auto=None)
     _check_data_and_fit(orc, g4, w, [0, 39], 300, "most-likely", fn_number=1, n_fit=90)
     w.close()
     c5 = workloads.c5(W=33, N=400)
     w = workloads.make_walker(c5, seed=11)
-    w.adaptive_steps_full(n=450, temperature=10)
+    w.adaptive_steps_full(n=450, temperature=10, auto=None)
     w.keep_walks(200)
     _check_data_and_fit(orc, c5, w, [0, 32], 150, "median", n_fit=64)
     w.close()
@@ -602,7 +602,7 @@ def test_multi_dimensional_x_run_identical_to_oracle_and_next_to_a_scalar_set(or
     w = workloads.make_walker(cfg)
     n = 2200                                  # (the loop never takes fewer than 2000 steps, :906 / :917)
     z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
-    w.adaptive_steps_full(n=n, temperature=10, z=z, u=u)
+    w.adaptive_steps_full(n=n, temperature=10, auto=None, z=z, u=u)
     _compare_chain(orc, cfg, w, z, u,
                    lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu), [0, 7, 19])
     w.close()
@@ -676,7 +676,7 @@ def test_two_stream_chain_groups_do_not_change_results(orc):
     for g in (1, 2):
         w = workloads.make_walker(cfg, seed=17)
         w.set_groups(g)
-        w.adaptive_steps_full(n=n, temperature=10)
+        w.adaptive_steps_full(n=n, temperature=10, auto=None)
         out.append(w.trace(2001) + (w.l_matrix(),))
         w.close()
     for a, b in zip(out[0], out[1]):
@@ -687,7 +687,7 @@ def test_two_stream_chain_groups_do_not_change_results(orc):
     z, u = rng.standard_normal((520, 2000, len(g4["keys"]))), rng.uniform(size=(520, 2000))
     w = workloads.make_walker(g4)
     w.set_groups(2)
-    w.adaptive_steps_full(n=300, temperature=10, z=z, u=u)
+    w.adaptive_steps_full(n=300, temperature=10, auto=None, z=z, u=u)
     _compare_chain(orc, g4, w, z, u,
                    lambda ow, zz, uu: ow.adaptive_steps_full(n=300, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu),
                    [0, 255, 256, 519])
@@ -712,7 +712,7 @@ def test_adaptive_driver_options_identical_to_oracle(orc, opt):
     else:
         Lm = np.diag(1e-3 * np.abs(cfg["theta_star"])) + 1e-4 * np.tril(np.ones((w.P, w.P)), -1)
         kw = okw = dict(l_matrix=Lm)
-    w.adaptive_steps_full(n=n, temperature=10, z=z, u=u, **kw)
+    w.adaptive_steps_full(n=n, temperature=10, auto=None, z=z, u=u, **kw)
     _compare_chain(orc, cfg, w, z, u,
                    lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu, **okw),
                    range(6))
@@ -790,7 +790,7 @@ def test_walker_set_with_per_walker_data_matches_oracle(orc, name, ll, shared_x)
     assert rel_err(prob, ref, scale) < TOL
     nsteps = 250
     z, u = rng.standard_normal((W, 2000, len(th))), rng.uniform(size=(W, 2000))
-    w.adaptive_steps_full(n=nsteps, temperature=10, z=z, u=u)
+    w.adaptive_steps_full(n=nsteps, temperature=10, auto=None, z=z, u=u)
     th_g, pr_g, nv = w.trace(2001)
     for k in (0, 17, 36):
         ow, _ = oracle_for(k)
@@ -884,7 +884,7 @@ def test_walker_save_and_load_round_trip(tmp_path):
     from lisp_mcmc_b200 import walker_load, walker_save
     cfg = workloads.c2(W=5, N=200)
     w = workloads.make_walker(cfg, seed=8)
-    w.adaptive_steps_full(n=300, temperature=10)
+    w.adaptive_steps_full(n=300, temperature=10, auto=None)
     path = walker_save(w, str(tmp_path / "walk.mfit"))
     th, pr, nv = w.trace(int(w.stats()["length"].max()))
     got = walker_load(path)
@@ -898,6 +898,43 @@ def test_walker_save_and_load_round_trip(tmp_path):
     w.close()
 
 
+def test_walker_save_load_multiline_lambda(tmp_path):
+    """:function and :log-prior given as multi-line Lisp source (the usual form) survive the header round trip"""
+    from lisp_mcmc_b200 import walker_load, walker_save
+    cfg = workloads.c2(W=5, N=200)
+    fn = """(lambda (x &key a mu s b0 b1 &allow-other-keys)
+  ;; gaussian on a line, "quoted" text in a comment
+  (+ (* a (exp (* -1/2 (expt (/ (- x mu) s) 2))))
+     b0
+     (* b1 x)))"""
+    prior = """(lambda (params data)
+  (prior-bounds-let ((:a 0 100)
+                     (:s 0 10))
+    bounds-total))"""
+    a = walker_create(function=fn, data=cfg["data"][0], params=list(zip(cfg["keys"], cfg["theta_star"])),
+                      data_error=cfg["data_error"], log_prior=prior, theta0=cfg["theta0"], seed=3)
+    a.adaptive_steps_full(n=300, temperature=10, auto=None)
+    path = walker_save(a, str(tmp_path / "ml.mfit"))
+    got = walker_load(path)
+    assert "gaussian on a line" in got["header"] and "bounds-total" in got["header"]
+    assert got["theta"].shape == (5, int(a.stats()["length"].max()), 5)
+    b = walker_load(path, function=fn, data=cfg["data"][0], data_error=cfg["data_error"], log_prior=prior)
+    assert np.array_equal(a.trace(301)[0], b.trace(301)[0]) and np.array_equal(a.stats()["age"], b.stats()["age"])
+    a.close(); b.close()
+
+
+def test_keep_walks_never_grows_a_walk():
+    """(subseq walk 0 keep) on a shorter walk is an error in the reference; here the walk is left alone"""
+    cfg = workloads.c2(W=3, N=100)
+    w = workloads.make_walker(cfg)
+    w.adaptive_steps_full(n=300, temperature=10, auto=None)
+    w.modify("reset")
+    assert np.all(w.stats()["length"] == 1)
+    w.keep_walks(50)
+    assert np.all(w.stats()["length"] == 1)
+    w.close()
+
+
 @pytest.mark.parametrize("keep", [None, 700])
 def test_walker_load_resumes_exactly(tmp_path, keep):
     """a walker set rebuilt by walker-load (:989-1001: walker-create on the newest step, then :add-walks) continues bit
@@ -907,7 +944,7 @@ def test_walker_load_resumes_exactly(tmp_path, keep):
     from lisp_mcmc_b200 import walker_load, walker_save
     cfg = workloads.c2(W=140, N=300)
     a = workloads.make_walker(cfg, seed=21, chain_id_base=1000)
-    a.adaptive_steps_full(n=2100, temperature=10)
+    a.adaptive_steps_full(n=2100, temperature=10, auto=None)
     if keep:
         a.keep_walks(keep)
     path = walker_save(a, str(tmp_path / "ckpt.mfit"))
@@ -920,7 +957,7 @@ def test_walker_load_resumes_exactly(tmp_path, keep):
     Lm = np.diag(0.002 * np.abs(cfg["theta_star"]))
     for w in (a, b):
         w.many_steps(150, Lm)
-        w.adaptive_steps_full(n=2100, temperature=10)
+        w.adaptive_steps_full(n=2100, temperature=10, auto=None)
     ta, tb = a.trace(5000), b.trace(5000)
     for x, y in zip(ta, tb):
         assert np.array_equal(x, y, equal_nan=True)

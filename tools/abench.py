@@ -25,7 +25,7 @@ def main():
     from lisp_mcmc_b200 import workloads
     cfg = workloads.c2(W=args.W, N=args.N)
     w = workloads.make_walker(cfg, seed=1)
-    w.adaptive_steps_full(n=args.steps, temperature=10)
+    w.adaptive_steps_full(n=args.steps, temperature=10, auto=None)
     rows = int(w.stats()["length"].max())
 
     def timed(label, fn, reps=3):
