@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfit_cuda.so")
+LIB_PATH = os.environ.get("MFIT_LIB") or os.path.join(_HERE, "libmfit_cuda.so")   # MFIT_LIB: an alternative build (tools/build_variant.sh)
 
 OK, ERR_ARG, ERR_CUDA, ERR_SEXPR, ERR_NVRTC, ERR_STATE, ERR_STREAM, ERR_NCCL, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6, -7, -8
 FAM_POLY, FAM_EXPO, FAM_SINUS, FAM_LORENTZ, FAM_GAUSS_LIN, FAM_NV_MULTI, FAM_SEXPR = 0, 1, 2, 3, 4, 5, 100

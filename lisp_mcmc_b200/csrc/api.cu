@@ -86,6 +86,9 @@ struct Workspace {
 
 struct EventPair { cudaEvent_t a, b; };
 
+// launch shape of a shared-data likelihood kernel (mfit_eval.cuh): persistent CTAs of `warps` independent warps
+struct EvalShape { int warps = 0, stages = 0, ctas = 0; size_t smem = 0; };
+
 }  // namespace
 
 struct mfit_ctx {
@@ -97,7 +100,8 @@ struct mfit_ctx {
   int D = 0, P = 0;
   std::vector<Dataset> ds;
   int seg_tiles_override = 0;
-  std::map<const void*, int> resident;  // eval kernel -> CTAs resident on the whole device
+  std::map<const void*, int> resident;  // per-walker eval kernel -> CTAs resident on the whole device
+  std::map<const void*, EvalShape> shape;  // shared-data eval kernel -> launch shape
   int* sched_dev = nullptr;             // [2 per group] work-item counter / finished-CTA counter of the eval kernels (zero between launches)
   // A run splits the chains into two or three groups that advance on separate streams: the per-chain kernels of one
   // group (segment reduction, accept/adapt, next proposal -- latency-bound, one warp per SM) and the tail of its
@@ -223,6 +227,21 @@ double log_factorial_ref(long long n, std::vector<float>& memo) {
   for (long long j = (long long)memo.size(); j <= n; j++) memo.push_back(memo[(size_t)j - 1] + (float)std::log((double)j));
   return (double)memo[(size_t)n];
 }
+
+// Sum of the theta-independent terms hoisted out of the likelihood (-ln(2 pi)/2 - ln sigma_i, -log k_i!).  With a
+// scalar :data-error every term is the SAME number, and a plain running sum then rounds the same way at every step:
+// the drift grows like N eps, not sqrt(N) eps (measured: 1.3e-10 relative on C5's 1e7 points, test_gpu_fullsize.py).
+// The reference adds these terms together with the random -z^2/2 (:400), which keeps its own sum within ~3e-14 of
+// exact; the hoisted constant is therefore formed exactly-rounded-ish (Neumaier).
+struct CompSum {
+  double s = 0.0, c = 0.0;
+  void add(double v) {
+    const double t = s + v;
+    c += std::fabs(s) >= std::fabs(v) ? (s - t) + v : (v - t) + s;
+    s = t;
+  }
+  double value() const { return s + c; }
+};
 
 // segment geometry is a function of the point count alone, so that partial sums -- and therefore
 // every log-likelihood bit -- do not depend on chain count, SM count or the number of GPUs
@@ -416,7 +435,7 @@ int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, c
   for (int k = 0; k < n; k++) {
     fill_eval_args(ma.d[k], ctx->ds[ds[k]], w, ds[k], theta, skip, cb0, n_cb);
     ma.item_start[k] = (int)items;
-    items += (long long)ma.d[k].n_cb * ma.d[k].n_seg;
+    items += (long long)ma.d[k].n_cb * (MFIT_CB / MFIT_WB) * ma.d[k].n_seg;
     if (items > 2000000000LL) return fail(ctx, MFIT_ERR_ARG, "too many work items in one launch (%lld)", items);
   }
   ma.item_start[n] = (int)items;
@@ -424,21 +443,54 @@ int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, c
   Dataset& s = ctx->ds[ds[0]];
   const void* fn = shared_data_kernel(s);
   if (!fn) return fail(ctx, MFIT_ERR_STATE, "no kernel for dataset %d (family %d degree %d)", ds[0], s.family, s.degree);
-  const size_t smem = mfit_eval_smem_bytes(s.ll_kind, s.model_xdims > 0 ? s.model_xdims : 1);
-  auto it = ctx->resident.find(fn);
-  if (it == ctx->resident.end()) {  // persistent grid = CTAs resident at once (occupancy x SMs), queried once per kernel
-    // static (math tables) + dynamic (TMA ring) shared memory may exceed the 48 KB default together
-    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int per_sm = 0, sms = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MFIT_THREADS, smem));
+  auto it = ctx->shape.find(fn);
+  if (it == ctx->shape.end()) {
+    // Persistent CTAs of MFIT_WARPS independent warps, MFIT_MIN_CTAS per SM, a three-stage TMA ring per warp.  The
+    // shape is fixed once per kernel; when the stages of a wide data set (many x components, the cutoff constants) do
+    // not fit next to the math tables, first a shallower ring, then fewer warps.
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, fn));
+    int sms = 0, max_optin = 0;
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    if (per_sm < 1) per_sm = 1;
-    it = ctx->resident.emplace(fn, per_sm * sms).first;
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    const long long room = (long long)max_optin - (long long)fa.sharedSizeBytes;
+    const int xd = s.model_xdims > 0 ? s.model_xdims : 1;
+    EvalShape sh;
+    sh.warps = 0;
+    int max_warps = MFIT_WARPS;
+    if (fa.maxThreadsPerBlock / 32 < max_warps) max_warps = fa.maxThreadsPerBlock / 32;
+    if (const char* e = getenv("MFIT_EVAL_WARPS")) { if (atoi(e) > 0 && atoi(e) < max_warps) max_warps = atoi(e); }  // tuning aid
+    int want_stages = MFIT_STAGES;
+    if (const char* e = getenv("MFIT_EVAL_STAGES")) { if (atoi(e) > 0 && atoi(e) <= 4) want_stages = atoi(e); }   // tuning aid
+    // all MFIT_MIN_CTAS CTAs of an SM must fit: each takes its static tables + the rings (+ 1 KB the system reserves per CTA)
+    int smem_sm = 0;
+    CU(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    const long long per_cta = (long long)smem_sm / MFIT_MIN_CTAS - (long long)fa.sharedSizeBytes - 1024;
+    const long long fit = per_cta < room ? per_cta : room;
+    for (int w = max_warps; w >= 1 && sh.warps == 0; w = w > 4 ? w - 4 : w - 1)
+      for (int st = want_stages; st >= 2 && sh.warps == 0; st--)
+        if ((long long)mfit_eval_smem_bytes(s.ll_kind, xd, w, st) <= fit) { sh.warps = w; sh.stages = st; }
+    if (sh.warps == 0)  // fewer CTAs per SM rather than none
+      for (int w = max_warps; w >= 1 && sh.warps == 0; w--)
+        if ((long long)mfit_eval_smem_bytes(s.ll_kind, xd, w, 2) <= room) { sh.warps = w; sh.stages = 2; }
+    if (sh.warps == 0) return fail(ctx, MFIT_ERR_ARG, "dataset %d: a tile of its %d arrays does not fit in shared memory", ds[0], xd + 3);
+    sh.smem = mfit_eval_smem_bytes(s.ll_kind, xd, sh.warps, sh.stages);
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sh.warps * 32, sh.smem));
+    if (per_sm < 1) return fail(ctx, MFIT_ERR_CUDA, "likelihood kernel of dataset %d cannot be resident (%d warps, %zu bytes)", ds[0], sh.warps, sh.smem);
+    // the kernel's __launch_bounds__ say how many CTAs per SM its registers are allotted for (MFIT_MIN_CTAS)
+    if (per_sm > MFIT_MIN_CTAS) per_sm = MFIT_MIN_CTAS;
+    sh.ctas = per_sm * sms;
+    it = ctx->shape.emplace(fn, sh).first;
   }
+  const EvalShape& sh = it->second;
+  ma.stages = sh.stages;
   void* args[] = {&ma};
-  const unsigned grid = (unsigned)(items < it->second ? items : it->second);
-  CU(cudaLaunchKernel(fn, dim3(grid), dim3(MFIT_THREADS), args, smem, st));
+  const long long need = (items + sh.warps - 1) / sh.warps;
+  const unsigned grid = (unsigned)(need < sh.ctas ? need : sh.ctas);
+  CU(cudaLaunchKernel(fn, dim3(grid), dim3(sh.warps * 32), args, sh.smem, st));
   ctx->launches++;
   return 0;
 }
@@ -941,10 +993,9 @@ int mfit_dataset_upload_xd(mfit_ctx* ctx, int d, const double* x, int x_dims, co
   double xmin = INFINITY, xmax = -INFINITY;
   bool x_finite = true;
   const double a = -0.5 * std::log(2.0 * 3.141592653589793);  // (* -1/2 (log (* 2 pi))) :377
-  double cst = 0.0;
+  CompSum cst, pcst;
   bool pois_ok = true;
   std::vector<float> memo;
-  double pcst = 0.0;
   for (long long i = 0; i < n; i++) {
     const double sg = sigma ? sigma[i] : 1.0;  // (if data-error data-error 1) :1144
     xx[i] = x[i];
@@ -956,20 +1007,17 @@ int mfit_dataset_upload_xd(mfit_ctx* ctx, int d, const double* x, int x_dims, co
     if (x[i] > xmax) xmax = x[i];
     const double ci = a + (-1.0 * std::log(sg));
     cc[i] = ci;
-    cst = i == 0 ? ci : cst + ci;
+    cst.add(ci);
     const double k = y[i];
     if (pois_ok) {
       if (!(k >= 0.0) || k != std::floor(k) || k > 5e6) pois_ok = false;
-      else {
-        const double lf = log_factorial_ref((long long)k, memo);
-        pcst = i == 0 ? -lf : pcst - lf;
-      }
+      else pcst.add(-log_factorial_ref((long long)k, memo));
     }
   }
   s.xmin = x_finite && n > 0 && !s.x_is_sequence ? xmin : -INFINITY;
   s.xmax = x_finite && n > 0 && !s.x_is_sequence ? xmax : INFINITY;
-  s.cst_normal = cst;
-  s.cst_poisson = pcst;
+  s.cst_normal = cst.value();
+  s.cst_poisson = pcst.value();
   s.poisson_ok = pois_ok;
   const size_t bytes = sizeof(double) * (size_t)s.n_pad;
   CU(cudaMalloc(&s.x, bytes * s.x_dims));
@@ -1018,7 +1066,7 @@ int mfit_dataset_upload_per_walker(mfit_ctx* ctx, int d, const double* x, const 
       if (v > xmax) xmax = v;
     }
   for (size_t r = 0; r < rows; r++) {
-    double c0 = 0.0, p0 = 0.0;
+    CompSum c0, p0;
     for (long long i = 0; i < n; i++) {
       const double sg = sigma ? sigma[(sigma_shared ? 0 : r * (size_t)n) + i] : 1.0;  // (if data-error data-error 1) :1144
       const double yv = y[r * (size_t)n + i];
@@ -1028,17 +1076,14 @@ int mfit_dataset_upload_per_walker(mfit_ctx* ctx, int d, const double* x, const 
       yw[o] = yv * w[ow];
       const double ci = a + (-1.0 * std::log(sg));
       cc[ow] = ci;
-      c0 = i == 0 ? ci : c0 + ci;
+      c0.add(ci);
       if (pois_ok) {
         if (!(yv >= 0.0) || yv != std::floor(yv) || yv > 5e6) pois_ok = false;
-        else {
-          const double lf = log_factorial_ref((long long)yv, memo);
-          p0 = i == 0 ? -lf : p0 - lf;
-        }
+        else p0.add(-log_factorial_ref((long long)yv, memo));
       }
     }
-    cst[r] = c0;
-    pcst[r] = p0;
+    cst[r] = c0.value();
+    pcst[r] = p0.value();
   }
   s.xmin = x_finite && n > 0 ? xmin : -INFINITY;
   s.xmax = x_finite && n > 0 ? xmax : INFINITY;

@@ -49,7 +49,8 @@ int mfit_family_nparams(int family, int degree) {
   return -1;
 }
 
-size_t mfit_eval_smem_bytes(int ll, int x_dims) {
+// dynamic shared memory of the shared-data kernel: per warp `stages` stages of narr arrays, one mbarrier per stage, the item ring
+size_t mfit_eval_smem_bytes(int ll, int x_dims, int warps, int stages) {
   int narr = (ll == MFIT_LL_NORMAL ? 3 : ll == MFIT_LL_NORMAL_CUTOFF ? 4 : 2) + x_dims - 1;
-  return (size_t)MFIT_STAGES * narr * MFIT_TILE * 8 + 2 * MFIT_STAGES * 8 + MFIT_QN * 4;
+  return (size_t)warps * ((size_t)stages * (narr * MFIT_TILE * 8 + 8) + MFIT_QN * 4);
 }

@@ -6,10 +6,10 @@
 //     ll_d(theta) = sum_i  density(y_i, f(x_i; theta), sigma_i)
 // evaluated for W parameter vectors (chains) at once against shared (x, y, sigma).
 //
-// Work decomposition: one work item = one chain-block (MFIT_CB = 256 chains, two chains per thread) x one segment of
-// the data (tiles_per_seg tiles of MFIT_TILE points).  Persistent CTAs (one grid = what is resident at once) take
-// items from a global counter, chain-block fastest.  The data tile is moved global -> shared by the TMA engine
-// (cp.async.bulk, 1-D) through an MFIT_STAGES-deep mbarrier ring that runs across item boundaries, and is read back
+// Work decomposition: one work item = one warp-block (MFIT_WB = 64 chains, two chains per lane) x one segment of
+// the data (tiles_per_seg tiles of MFIT_TILE points).  Persistent CTAs; each of their warps takes items from a
+// global counter on its own, chain-block fastest.  The data tile is moved global -> shared by the TMA engine
+// (cp.async.bulk, 1-D) through a per-warp mbarrier ring that runs across item boundaries, and is read back
 // as warp-uniform (broadcast) 128-bit LDS; theta lives in registers, so the FP64 pipe sees no cross-lane traffic.
 //
 // Why two chains per thread: a broadcast LDS.128 still returns 512 bytes to the register file and the shared-memory
@@ -33,16 +33,23 @@
 #define MFIT_TILE 128    /* points per shared-memory stage */
 #endif
 #ifndef MFIT_STAGES
-#define MFIT_STAGES 4    /* TMA ring depth */
+#define MFIT_STAGES 3    /* per-warp TMA ring depth (the host lowers it when shared memory is short, MfitMultiArgs::stages) */
 #endif
 #define MFIT_MAX_SEG 1024 /* segments (= work items per chain-block, = partial sums per chain) a data set is cut into at most */
-#define MFIT_THREADS 128 /* threads per CTA */
-#define MFIT_CB 256      /* chains per CTA: two per thread (thread t: chains t and t + MFIT_THREADS of the block) */
+#ifndef MFIT_WARPS
+#define MFIT_WARPS 4     /* warps per CTA.  Small CTAs: a CTA leaves the SM as soon as ITS warps find no more items, and a CTA
+                            of the next launch (the next chain group's, on another stream) takes the slot -- with one
+                            12-warp CTA per SM the hand-over waits for the slowest of twelve (0.4615 against 0.4411 ms per
+                            C2 step, profiles/r02_kernel_shapes.md) */
+#endif
+#define MFIT_THREADS (32 * MFIT_WARPS) /* threads per CTA */
+#define MFIT_WB 64       /* chains per work item: two per lane (lane l: chains l and l + 32 of the warp-block) */
+#define MFIT_CB 256      /* granule of the chain dimension on the host: strides, chain groups (a multiple of MFIT_WB) */
 #ifndef MFIT_MIN_CTAS
-#define MFIT_MIN_CTAS 3   /* CTAs per SM the register allocation is bounded for */
+#define MFIT_MIN_CTAS 3   /* CTAs per SM the register allocation is bounded for: 3 x 128 threads x 168 registers */
 #endif
 #define MFIT_PC_THREADS 256 /* threads per CTA of the per-walker-data kernel (one warp per chain) */
-#define MFIT_QN 8        /* ring of item ids handed from the producer thread to the CTA */
+#define MFIT_QN 8        /* per-warp ring of item ids handed from the producer side of the warp to its consumer side */
 #define MFIT_MAXK 16     /* parameters a built-in family may gather */
 
 #define MFITK_NORMAL 0
@@ -82,6 +89,7 @@ struct MfitEvalArgs {
 #define MFIT_MAX_FUSED 8
 struct MfitMultiArgs {
   int n_ds;
+  int stages;                         /* depth of every warp's TMA ring (>= 1; 2 or more to overlap fetch and arithmetic) */
   int item_start[MFIT_MAX_FUSED + 1]; /* items [item_start[k], item_start[k+1]) belong to d[k]; chain-block fastest inside */
   int* sched;                         /* [2] zero between launches: next item to hand out, CTAs that have finished */
   MfitEvalArgs d[MFIT_MAX_FUSED];
@@ -172,7 +180,8 @@ struct MfitTerm<MFITK_POISSON> {
 // only to redo a tile in which a fast routine met an argument outside its domain (see mfit_math.cuh); G = MfitGuard
 // records such arguments, MfitNoGuard is for chains whose Model::safe() has ruled them out.
 #ifndef MFIT_UNROLL_PAIRS
-#define MFIT_UNROLL_PAIRS 2
+#define MFIT_UNROLL_PAIRS 4   /* 16 evaluations per iteration: same instruction count per point as 2, but the scheduler sees
+                                 more independent work across the loop's back edge (C2 step 0.4201 -> 0.4116 ms) */
 #endif
 // f(x_i) for a model whose x is a number (eval) or a sequence of Model::XDIMS components (evalv; the component arrays
 // of a stage lie MFIT_TILE apart)
@@ -242,14 +251,26 @@ __device__ __forceinline__ void mfit_tile_pass(const Model* m, const double* xs,
   }
 }
 
-// fast pass with whatever protection the chains of this warp need; a tripped guard redoes the tile with libdevice
+// fast pass with whatever protection the chains of this warp need (warp-uniform `mode`): MFIT_MODE_FREE = none
+// (Model::safe holds for every chain), MFIT_MODE_CLAMP = in-place clamps only (Model::CLAMP_ONLY and Model::tame),
+// MFIT_MODE_GUARD = recording guard; a tripped guard redoes the tile with libdevice
+#define MFIT_MODE_FREE 0
+#define MFIT_MODE_CLAMP 1
+#define MFIT_MODE_GUARD 2
+#define MFIT_MODE_FUSED 3   /* MFIT_MODE_FREE and Model::fusable for every chain (Model::FUSABLE) */
 template <class Model, int LL, int NC>
-__device__ __forceinline__ void mfit_tile(const Model* m, bool unguarded, const double* xs, const double* ys,
+__device__ __forceinline__ void mfit_tile(const Model* m, int mode, const double* xs, const double* ys,
                                           const double* ws, const double* cs, int cnt, double* acc) {
   constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
-  if (!GUARDED || unguarded) {
+  if (Model::FUSABLE && mode == MFIT_MODE_FUSED) {
+    MfitFusedNoGuard fg[NC];
+    mfit_tile_pass<Model, LL, false, NC>(m, xs, ys, ws, cs, cnt, acc, fg);
+  } else if (!GUARDED || mode == MFIT_MODE_FREE) {
     MfitNoGuard ng[NC];
     mfit_tile_pass<Model, LL, false, NC>(m, xs, ys, ws, cs, cnt, acc, ng);
+  } else if (Model::CLAMP_ONLY && MfitTerm<LL>::USES == 0 && mode == MFIT_MODE_CLAMP) {
+    MfitClampGuard cg[NC];
+    mfit_tile_pass<Model, LL, false, NC>(m, xs, ys, ws, cs, cnt, acc, cg);
   } else {
     double save[2 * NC];
 #pragma unroll
@@ -274,13 +295,17 @@ __device__ __forceinline__ void mfit_tile(const Model* m, bool unguarded, const 
 }
 
 // ---------------------------------------------------------------- the kernel body
-// Persistent CTAs: the grid is sized to what is resident at once (occupancy x SM count) and every CTA takes work
-// items (segment, chain-block) -- chain-block fastest -- from a.sched[0] until they run out, so there is no wave
-// quantisation, no tail longer than one item, and the prologue (mbarriers, math tables) is paid once per CTA.
-// Thread 0 is the producer: it draws the next item while the tiles of the current one are still being consumed, keeps
-// MFIT_STAGES tiles in flight across item boundaries and publishes item ids through a small ring in shared memory
-// (the warps of a CTA are coupled by the mbarriers of the tile ring only, never by a CTA-wide barrier);
-// the parameters of the next item are loaded into registers one item ahead.
+// Persistent CTAs (MFIT_MIN_CTAS per SM); every WARP is an independent worker.  A warp draws work items -- (segment, block of
+// MFIT_WB = 64 chains), chain-block fastest -- from a.sched[0] until they run out, streams the item's data tiles
+// through ITS OWN TMA ring (cp.async.bulk 1-D into per-warp shared memory, one mbarrier per stage, lane 0 issues) and
+// keeps two chains per lane in registers.  Nothing couples the warps of a CTA after the prologue (math tables): no
+// CTA-wide barrier, no shared producer.  (The first version of this kernel had one producer thread per 4-warp CTA: the
+// producer's warp could not run ahead of the CTA's slowest warp, all three producers of an SM sat on the same
+// scheduler, and the kernel ran at the pace of that scheduler -- 9 % below the bare loop, tools/probe/loop_probe.cu.)
+// The data set is L2-resident and tiny next to the arithmetic (3 KB per 128 points x 64 chains x ~30 FP64 instructions),
+// so fetching a tile once per warp instead of once per CTA costs nothing measurable.
+// The ring runs across item boundaries: the next item is drawn (atomicAdd) one tile before its first tile is requested,
+// its parameters are loaded one item ahead, so neither latency is exposed.
 // MULTI = false: one data set, whose arguments are then compile-time-addressed kernel parameters (constant-bank
 // operands); with MULTI the per-item data set index makes them indexed loads, which costs the one-data-set case 5 %.
 template <class Model, int LL, bool MULTI>
@@ -289,15 +314,16 @@ __device__ __forceinline__ void mfit_eval_body_t(const MfitMultiArgs& ma) {
   constexpr int LNARR = MfitTerm<LL>::NARR;          // x, y, [w, [c]] as the likelihood term counts them
   constexpr int NARR = LNARR + XD - 1;               // arrays per stage: XD of x, then y, w, c
   constexpr unsigned STAGE_BYTES = NARR * MFIT_TILE * 8u;
+  constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char mfit_smem[];
-  double* buf = reinterpret_cast<double*>(mfit_smem);
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(mfit_smem + MFIT_STAGES * STAGE_BYTES);
-  unsigned long long* empty = full + MFIT_STAGES;
-  volatile int* q_items = reinterpret_cast<volatile int*>(empty + MFIT_STAGES);
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, nwarp = blockDim.x >> 5;
+  const int S = ma.stages;
+  double* buf = reinterpret_cast<double*>(mfit_smem + (size_t)wib * S * STAGE_BYTES);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(mfit_smem + (size_t)nwarp * S * STAGE_BYTES) + wib * S;
+  volatile int* q_items = reinterpret_cast<volatile int*>(mfit_smem + (size_t)nwarp * S * (STAGE_BYTES + 8)) + wib * MFIT_QN;
 
-  const int tid = threadIdx.x;
   const int total = ma.item_start[ma.n_ds];
-  // item id -> data set and its (segment, chain-block) item
+  // item id -> data set and its (segment, warp-block) item
   auto ds_of = [&](int item) -> int {
     if (!MULTI) return 0;
     int k = 0;
@@ -312,125 +338,143 @@ __device__ __forceinline__ void mfit_eval_body_t(const MfitMultiArgs& ma) {
     return (int)(t1 - t0);
   };
 
-  mfit_math_stage(Model::USES | MfitTerm<LL>::USES, tid, MFIT_THREADS);  // exp/log tables -> shared memory
-  if (tid == 0) {
-    for (int s = 0; s < MFIT_STAGES; s++) {
-      mfit_mbar_init(&full[s], 1);
-      mfit_mbar_init(&empty[s], MFIT_THREADS / 32);
-    }
+  mfit_math_stage(Model::USES | MfitTerm<LL>::USES, tid, (int)blockDim.x);  // exp/log tables -> shared memory
+  if (lane == 0) {
+    for (int s = 0; s < S; s++) mfit_mbar_init(&full[s], 1);
     mfit_fence_mbar_init();
   }
+  __syncthreads();  // tables staged (the only CTA-wide barrier before the epilogue)
 
-  // producer cursor (thread 0 only): next tile to request = tile p_k of item p_item; `issued` counts requests
-  int p_item = 0, p_k = 0, p_nt = 0, p_seq = 0, p_ds = 0, p_seg = 0;
+  // ---- producer side of the warp (all values warp-uniform; lane 0 talks to the TMA engine) ----
+  // cursor: next tile to request = tile p_k of item p_item (segment p_seg of data set p_ds); p_raw = the item id drawn
+  // for after it (lane 0 only until it is broadcast), p_seq = items published so far
+  int p_item = -1, p_k = 0, p_nt = 0, p_seq = 0, p_ds = 0, p_seg = 0, p_raw = 0;
   bool p_done = false;
-  unsigned issued = 0;
-  auto fetch_item = [&]() {
-    p_item = atomicAdd(ma.sched, 1);
+  int p_stage = 0;          // ring slot the next request goes to
+  long long p_off = 0;      // its first point (index into the data arrays)
+  auto draw = [&]() {  // ask for the next item id; the answer is first used one tile later (next_item)
+    if (lane == 0) p_raw = atomicAdd(ma.sched, 1);
+  };
+  auto next_item = [&]() {  // move the cursor to the item drawn last and publish its id to the consumer side
+    p_item = __shfl_sync(FULL, p_raw, 0);
     if (p_item >= total) {
       p_item = -1;
       p_done = true;
     } else {
       p_ds = ds_of(p_item);
       const MfitEvalArgs& a = ma.d[MULTI ? p_ds : 0];
-      p_seg = (p_item - start_of(p_ds)) / a.n_cb;
+      p_seg = (p_item - start_of(p_ds)) / (a.n_cb * (MFIT_CB / MFIT_WB));
       p_k = 0;
       p_nt = tiles_of(a, p_seg);
+      p_off = (long long)p_seg * a.tiles_per_seg * (long long)MFIT_TILE;
     }
-    q_items[(p_seq + 1) % MFIT_QN] = -2;  // "not drawn yet": a reader running ahead must never see a stale id
-    __threadfence_block();
-    q_items[p_seq % MFIT_QN] = p_item;
+    if (lane == 0) q_items[p_seq % MFIT_QN] = p_item;
     p_seq++;
+    __syncwarp();
   };
-  auto issue_next = [&]() {
-    const MfitEvalArgs& a = ma.d[MULTI ? p_ds : 0];
-    const int s = (int)(issued % MFIT_STAGES);
-    const long long off = ((long long)p_seg * a.tiles_per_seg + p_k) * (long long)MFIT_TILE;
-    double* dst = buf + (size_t)s * NARR * MFIT_TILE;
-    mfit_mbar_expect_tx(&full[s], STAGE_BYTES);
+  auto issue_next = [&]() {  // request one tile (if any is left), one stage ahead of the ring's oldest free slot
+    if (p_done) return;
+    if (p_k == p_nt) {
+      next_item();
+      if (p_done) return;
+    }
+    if (lane == 0) {
+      const MfitEvalArgs& a = ma.d[MULTI ? p_ds : 0];
+      const int s = p_stage;
+      const long long off = p_off;
+      double* dst = buf + (size_t)s * NARR * MFIT_TILE;
+      mfit_mbar_expect_tx(&full[s], STAGE_BYTES);
 #pragma unroll
-    for (int d = 0; d < XD; d++) mfit_tma_load_1d(dst + d * MFIT_TILE, a.x + d * a.xd_stride + off, MFIT_TILE * 8u, &full[s]);
-    mfit_tma_load_1d(dst + XD * MFIT_TILE, (LL == MFITK_NORMAL ? a.yw : a.y) + off, MFIT_TILE * 8u, &full[s]);
-    if (LNARR > 2) mfit_tma_load_1d(dst + (XD + 1) * MFIT_TILE, a.w + off, MFIT_TILE * 8u, &full[s]);
-    if (LNARR > 3) mfit_tma_load_1d(dst + (XD + 2) * MFIT_TILE, a.c + off, MFIT_TILE * 8u, &full[s]);
-    issued++;
-    if (++p_k == p_nt) fetch_item();
+      for (int d = 0; d < XD; d++) mfit_tma_load_1d(dst + d * MFIT_TILE, a.x + d * a.xd_stride + off, MFIT_TILE * 8u, &full[s]);
+      mfit_tma_load_1d(dst + XD * MFIT_TILE, (LL == MFITK_NORMAL ? a.yw : a.y) + off, MFIT_TILE * 8u, &full[s]);
+      if (LNARR > 2) mfit_tma_load_1d(dst + (XD + 1) * MFIT_TILE, a.w + off, MFIT_TILE * 8u, &full[s]);
+      if (LNARR > 3) mfit_tma_load_1d(dst + (XD + 2) * MFIT_TILE, a.c + off, MFIT_TILE * 8u, &full[s]);
+    }
+    p_off += MFIT_TILE;
+    if (++p_stage == S) p_stage = 0;
+    if (++p_k == p_nt) draw();
   };
-  __syncthreads();  // mbarriers initialised, tables staged
-  if (tid == 0) {
-    fetch_item();
-    for (int s = 0; s < MFIT_STAGES && !p_done; s++) issue_next();
-  }
-  __syncthreads();  // q_items[0] published
+  draw();
+  next_item();
+  for (int s = 0; s + 1 < S; s++) issue_next();  // S - 1 tiles ahead of the one being evaluated
 
+  // ---- consumer side ----
   Model m_next[2];
-  auto load_params = [&](int it) {
+  bool live_next[2] = {false, false};
+  auto load_item = [&](int it) {  // parameters and finished-flags of the warp's chains for item `it`
     const int k = ds_of(it);
     const MfitEvalArgs& a = ma.d[MULTI ? k : 0];
-    const long long c0 = (long long)(a.cb0 + (it - start_of(k)) % a.n_cb) * MFIT_CB + tid;
+    const long long c0 = ((long long)a.cb0 * (MFIT_CB / MFIT_WB) + (it - start_of(k)) % (a.n_cb * (MFIT_CB / MFIT_WB))) * MFIT_WB + lane;
     const long long last = (long long)a.W - 1;
-    m_next[0].load(a, c0 < a.W ? c0 : last);
-    m_next[1].load(a, c0 + MFIT_THREADS < a.W ? c0 + MFIT_THREADS : last);
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const long long ch = c0 + 32 * c;
+      const long long cl = ch < a.W ? ch : last;
+      m_next[c].load(a, cl);
+      live_next[c] = ch < a.W && !(a.skip != nullptr && a.skip[cl] != 0);
+    }
   };
-  bool have_params = false;
-  unsigned consumed = 0;
+  bool have_next = false;
+  int c_stage = 0;          // ring slot of the tile evaluated next, and the parity its mbarrier completes with
+  unsigned c_phase = 0;
   for (int seq = 0;; seq++) {
-    // No CTA-wide barrier per item: the id of item seq is published by thread 0 right after it has requested the last
-    // tile of item seq - 1 (which every warp had to wait for), and the slot reads -2 until then.
-    int item;
-    do { item = q_items[seq % MFIT_QN]; } while (item == -2);
+    const int item = q_items[seq % MFIT_QN];  // published by this warp's own producer side before the item's first tile was requested
     if (item < 0) break;
     const int ds = ds_of(item);
     const MfitEvalArgs& a = ma.d[MULTI ? ds : 0];
     const int local = item - start_of(ds);
-    const int seg = local / a.n_cb;
-    const long long cb0 = (long long)(a.cb0 + local % a.n_cb) * MFIT_CB;
-    const long long chain[2] = {cb0 + tid, cb0 + MFIT_THREADS + tid};
-    bool live[2];
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-      const long long cl = chain[c] < a.W ? chain[c] : (long long)a.W - 1;
-      live[c] = chain[c] < a.W && !(a.skip != nullptr && a.skip[cl] != 0);
-    }
-    const bool any_live = __any_sync(0xffffffffu, (live[0] || live[1]) ? 1 : 0) != 0;  // a finished warp only drains its tiles
-    const bool two = cb0 + MFIT_THREADS < a.W;                                  // CTA-uniform: second half of the block holds chains
-    if (!have_params) load_params(item);
+    const int n_wb = a.n_cb * (MFIT_CB / MFIT_WB);
+    const int seg = local / n_wb;
+    const long long cb0 = ((long long)a.cb0 * (MFIT_CB / MFIT_WB) + local % n_wb) * MFIT_WB;
+    const long long chain[2] = {cb0 + lane, cb0 + 32 + lane};
+    if (!have_next) load_item(item);
     Model m[2] = {m_next[0], m_next[1]};
-    {
-      // parameters of the next item one item ahead, if the producer has drawn it already (-2: not yet, -1: none)
-      const int nxt = q_items[(seq + 1) % MFIT_QN];
-      have_params = nxt >= 0;
-      if (have_params) load_params(nxt);
-    }
+    const bool live[2] = {live_next[0], live_next[1]};
+    const bool any_live = __any_sync(FULL, (live[0] || live[1]) ? 1 : 0) != 0;  // a finished warp-block only drains its tiles
+    const bool two = cb0 + 32 < a.W;                                           // warp-uniform: the second half holds chains
     m[0].setup();  // theta-only subexpressions
     m[1].setup();
     // warp-uniform: every chain of this warp stays inside the fast domain over the whole x range of the data set
-    const bool unguarded =
-        MfitTerm<LL>::USES == 0 && __all_sync(0xffffffffu, (m[0].safe(a) && (!two || m[1].safe(a))) ? 1 : 0) != 0;
-    const int nt = tiles_of(a, seg);
-    const long long t0 = (long long)seg * a.tiles_per_seg;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = 0; k < nt; k++, consumed++) {
-      const int s = (int)(consumed % MFIT_STAGES);
-      // refill the stage freed one tile ago (gives the other warps a tile of slack)
-      if (tid == 0 && consumed >= 1 && !p_done) {
-        const unsigned c1 = consumed - 1;
-        mfit_mbar_wait(&empty[c1 % MFIT_STAGES], (c1 / MFIT_STAGES) & 1u);
-        issue_next();
+    // (no guard at all), or at least has finite parameters where the model's fast routines clamp in place
+    int mode = MFIT_MODE_GUARD;
+    if (MfitTerm<LL>::USES == 0) {
+      if (__all_sync(FULL, (m[0].safe(a) && (!two || m[1].safe(a))) ? 1 : 0) != 0) {
+        mode = MFIT_MODE_FREE;
+#ifndef MFIT_NO_FUSE   /* A/B aid: tools/build_variant.sh nofuse -DMFIT_NO_FUSE */
+        if constexpr (Model::FUSABLE) {
+          if (__all_sync(FULL, (m[0].fusable(a) && (!two || m[1].fusable(a))) ? 1 : 0) != 0) mode = MFIT_MODE_FUSED;
+        }
+#endif
+      } else if constexpr (Model::CLAMP_ONLY) {
+        if (__all_sync(FULL, (m[0].tame(a) && (!two || m[1].tame(a))) ? 1 : 0) != 0) mode = MFIT_MODE_CLAMP;
       }
-      mfit_mbar_wait(&full[s], (consumed / MFIT_STAGES) & 1u);
+    }
+    const int nt = tiles_of(a, seg);
+    long long rem_ll = a.n - (long long)seg * a.tiles_per_seg * (long long)MFIT_TILE;  // points from the segment's first one on
+    int rem = rem_ll < (long long)nt * MFIT_TILE ? (int)rem_ll : nt * MFIT_TILE;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    have_next = false;
+    for (int k = 0; k < nt; k++) {
+      const int s = c_stage;
+      issue_next();  // into the stage evaluated one tile ago (every lane has passed the __syncwarp that ended it)
+      if (!have_next && p_seq > seq + 1) {
+        // the next item is known: its parameters travel while this item is evaluated
+        const int nxt = q_items[(seq + 1) % MFIT_QN];
+        if (nxt >= 0) { load_item(nxt); have_next = true; }
+      }
+      mfit_mbar_wait(&full[s], c_phase);
+      if (++c_stage == S) { c_stage = 0; c_phase ^= 1u; }
+      const int cnt = rem < MFIT_TILE ? rem : MFIT_TILE;
+      rem -= MFIT_TILE;
       if (any_live) {
         const double* xs = buf + (size_t)s * NARR * MFIT_TILE;
         const double* ys = xs + XD * MFIT_TILE;
         const double* ws = xs + (LNARR > 2 ? XD + 1 : 0) * MFIT_TILE;
         const double* cs = xs + (LNARR > 3 ? XD + 2 : 0) * MFIT_TILE;
-        long long rem = a.n - (t0 + k) * (long long)MFIT_TILE;
-        const int cnt = rem < MFIT_TILE ? (int)rem : MFIT_TILE;
-        if (two) mfit_tile<Model, LL, 2>(m, unguarded, xs, ys, ws, cs, cnt, acc);
-        else mfit_tile<Model, LL, 1>(m, unguarded, xs, ys, ws, cs, cnt, acc);
+        if (two) mfit_tile<Model, LL, 2>(m, mode, xs, ys, ws, cs, cnt, acc);
+        else mfit_tile<Model, LL, 1>(m, mode, xs, ys, ws, cs, cnt, acc);
       }
-      __syncwarp();
-      if ((tid & 31) == 0) mfit_mbar_arrive(&empty[s]);
+      __syncwarp();  // every lane is done with stage s
     }
     if (live[0]) a.partial[(size_t)seg * a.stride + chain[0]] = acc[0] + acc[1];
     if (live[1]) a.partial[(size_t)seg * a.stride + chain[1]] = acc[2] + acc[3];

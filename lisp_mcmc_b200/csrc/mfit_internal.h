@@ -12,7 +12,7 @@
 // eval_builtin.cu
 const void* mfit_builtin_eval_kernel(int family, int degree, int ll);
 int mfit_family_nparams(int family, int degree);
-size_t mfit_eval_smem_bytes(int ll, int x_dims);
+size_t mfit_eval_smem_bytes(int ll, int x_dims, int warps, int stages);
 // eval_perchain.cu
 const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int staged);
 

@@ -65,7 +65,9 @@ __device__ __forceinline__ void mfit_math_stage(int uses, int tid, int nthreads)
 
 // sticky record of the most extreme argument each fast routine has seen since reset()
 struct MfitGuard {
-  static constexpr bool ON = true;
+  static constexpr bool FUSED = false;
+  static constexpr bool ON = true;     // records arguments (see_*), checked once per tile
+  static constexpr bool CLAMP = true;  // in-place clamps of the routines that have one (mfit_gauss_reduce)
   unsigned e, g, l, s, d;
   __device__ __forceinline__ void reset() { e = 0u; g = 0u; l = 0u; s = 0u; d = 0u; }
   __device__ __forceinline__ void see_exp(unsigned v) { e = mfit_umax(e, v); }
@@ -90,6 +92,8 @@ struct MfitGuard {
 // (two to three integer-pipe slots per call) then disappear from the loop.
 struct MfitNoGuard {
   static constexpr bool ON = false;
+  static constexpr bool CLAMP = false;
+  static constexpr bool FUSED = false;  // see MfitFusedNoGuard
   __device__ __forceinline__ void reset() {}
   __device__ __forceinline__ void see_exp(unsigned) {}
   __device__ __forceinline__ void see_gauss(unsigned) {}
@@ -100,6 +104,21 @@ struct MfitNoGuard {
   __device__ __forceinline__ bool log_of_negative() const { return false; }
 };
 
+// In between: the clamps stay, nothing is recorded.  For a model all of whose fast routines clamp in place (the
+// Gaussian) and whose parameters are finite (Model::tame) no argument can produce anything but the right value, so
+// there is nothing to check per tile -- one integer min per call instead of three integer instructions and a redo
+// path.  This is what the wild proposals of the reference's start-up phase run on (its first l-matrix is diag(theta)).
+struct MfitClampGuard : MfitNoGuard {
+  static constexpr bool CLAMP = true;
+};
+
+// No guard, and the model may contract its argument arithmetic where Model::fusable() has shown that to be harmless
+// (the Gaussian forms (x - mu)/s as one FMA when |mu| is not large next to s: the rounding of the hoisted product then
+// acts like a change of mu in its last place or two).
+struct MfitFusedNoGuard : MfitNoGuard {
+  static constexpr bool FUSED = true;
+};
+
 /* 1.5 * 2^52 + 2^31: adding it rounds to an integer k held in the low mantissa word.  The 2^31 bias keeps the low
  * word free of borrows for |k| < 2^31 and vanishes from every use of k below (k & 63, k << 14, n & 3 are all taken
  * modulo a power of two that divides 2^31). */
@@ -107,15 +126,22 @@ struct MfitNoGuard {
 
 // 2^(k/256) for the integer k held (biased) in the low word of tmp = q + MAGIC: table entry (k & 255), exponent
 // k >> 8 added on the integer pipe (the table entries are pre-biased so that a plain k << 12 does both jobs).
-// Three integer instructions and one conflict-free LDS.64.  256 entries (32 KB replicated) instead of 64 buy one
+// Two integer instructions and one conflict-free LDS.64.  256 entries (32 KB replicated) instead of 64 buy one
 // polynomial degree, i.e. one FP64 instruction per call -- the pipe this code is bound by.
 __device__ __forceinline__ double mfit_exp2_256th(double tmp) {
   const int k = mfit_lo(tmp);
 #ifdef MFIT_HOST_TEST
   const unsigned long long t = mfit_c_exp2[k & 255];
 #else
-  const char* base = reinterpret_cast<const char*>(mfit_s_exp2) + ((threadIdx.x & 15u) << 3);
-  const unsigned long long t = *reinterpret_cast<const unsigned long long*>(base + ((k & 255) << 7));
+  // address = table + 8 (lane mod 16) + 128 (k & 255) in ONE instruction: an integer dot product of the bytes of k
+  // with (128, 0, 0, 0) masks, scales and adds the base at once (IDP.4A).  Left to itself the compiler shifts,
+  // masks-and-merges and adds (three instructions); a mask + multiply-add is two.  This loop is short of issue slots, not
+  // of integer throughput: C2 step 0.4411 (three) -> 0.4308 (two) -> 0.4049 ms (one, with the other changes of round 2;
+  // profiles/r02_kernel_shapes.md).
+  const unsigned base = (unsigned)__cvta_generic_to_shared(mfit_s_exp2) + ((threadIdx.x & 15u) << 3);
+  unsigned long long t;
+  const unsigned addr = __dp4a((unsigned)k, 0x80u, base);
+  asm("ld.shared.u64 %0, [%1];" : "=l"(t) : "r"(addr));
 #endif
   return mfit_mk((int)(t >> 32) + (k << 12), (int)t);
 }
@@ -140,14 +166,17 @@ __device__ __forceinline__ double mfit_exp_t(double x, G& gd) {
 // argument and, through one FMA each, its rounding to 1/256 octaves and the exact remainder r.  Three FP64
 // instructions here; the caller runs the polynomial (coefficients MFIT_K_EXS1..4, which it may pre-multiply by its
 // amplitude) and folds s:  f = fma(s, a (1 + r q), rest).
+// zs must not be negative (callers pass |d| |1/s|: the absolute values are operand modifiers of the multiply, free).
 template <class G>
 __device__ __forceinline__ void mfit_gauss_reduce(double zs, double* s, double* r, G& gd) {
-  if (G::ON) {
-    // |zs| is clamped on the integer pipe at 511.75 (exp(-z^2/2) ~ 2^-1023, which the arithmetic below turns into
+  if (G::CLAMP) {
+    // zs is clamped on the integer pipe at 511.75 (exp(-z^2/2) ~ 2^-1023, which the arithmetic below turns into
     // a subnormal-sized number, i.e. zero next to any amplitude): wild proposals underflow all the time during the
     // reference's start-up phase (its first l-matrix is diag(theta)), so that case must not leave the fast path.
-    const unsigned ah = (unsigned)mfit_hi(zs) & 0x7fffffffu;
-    gd.see_gauss(ah);
+    // One unsigned min on the high word: +inf clamps too, a NaN (0x7ff8...) would as well -- which is why the
+    // recording guard looks at the word first and Model::tame() rules NaN out for the clamp-only guard.
+    const unsigned ah = (unsigned)mfit_hi(zs);
+    if (G::ON) gd.see_gauss(ah);
     zs = mfit_mk((int)min(ah, 0x407ffc00u), mfit_lo(zs));
   }
   const double tmp = fma(-zs, zs, MFIT_MAGIC);

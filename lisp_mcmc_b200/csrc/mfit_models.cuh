@@ -17,6 +17,9 @@
 //                    (NaN parameters make every comparison false -> not safe -> guarded path -> libdevice redo)
 //   eval<SLOW>(x,gd) the model function
 //   GUARDED          whether eval uses a fast routine with a restricted domain at all
+//   FUSABLE          the model has a shorter evaluation for MfitFusedNoGuard, valid for chains with fusable(a) (and safe(a))
+//   CLAMP_ONLY       every such routine clamps in place (MfitClampGuard): chains with tame() parameters need no per-tile
+//                    check even where safe() cannot be proved; tame(a) is only called when CLAMP_ONLY
 //   XDIMS, XVEC      components of x the model reads; XVEC: x is a sequence and the model provides evalv(xv[XDIMS], gd)
 //                    instead of eval (lowered user models only, csrc/lower.cpp)
 
@@ -29,6 +32,8 @@ struct MfitPoly {
   static constexpr int XDIMS = 1;
   static constexpr bool XVEC = false;
   static constexpr bool GUARDED = false;
+  static constexpr bool CLAMP_ONLY = false;
+  static constexpr bool FUSABLE = false;
   double c[D + 1];
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
 #pragma unroll
@@ -51,6 +56,8 @@ struct MfitExpo {
   static constexpr int XDIMS = 1;
   static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
+  static constexpr bool CLAMP_ONLY = false;
+  static constexpr bool FUSABLE = false;
   double a_, b_, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     a_ = MFIT_TH(0); b_ = MFIT_TH(1); c_ = MFIT_TH(2);
@@ -67,6 +74,8 @@ struct MfitSinus {
   static constexpr int XDIMS = 1;
   static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
+  static constexpr bool CLAMP_ONLY = false;
+  static constexpr bool FUSABLE = false;
   double a_, om, ph, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     a_ = MFIT_TH(0); om = MFIT_TH(1); ph = MFIT_TH(2); c_ = MFIT_TH(3);
@@ -86,6 +95,8 @@ struct MfitLorentz {
   static constexpr int XDIMS = 1;
   static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
+  static constexpr bool CLAMP_ONLY = false;
+  static constexpr bool FUSABLE = false;
   double ag2, x0, g2, c_;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     ag2 = MFIT_TH(0); x0 = MFIT_TH(1); g2 = MFIT_TH(2); c_ = MFIT_TH(3);
@@ -117,13 +128,31 @@ struct MfitGaussLin {
   static constexpr int XDIMS = 1;
   static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
+  static constexpr bool CLAMP_ONLY = true;
+  static constexpr bool FUSABLE = true;
   double a_, mu, isq, b0, b1;  // load() leaves s in isq
+  double nmi;                  // -mu isq (fused form)
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     a_ = MFIT_TH(0); mu = MFIT_TH(1); isq = MFIT_TH(2); b0 = MFIT_TH(3); b1 = MFIT_TH(4);
   }
-  __device__ __forceinline__ void setup() { isq = (1.0 / isq) * MFIT_GAUSS_ZSCALE; }
+  __device__ __forceinline__ void setup() {
+    isq = fabs(1.0 / isq) * MFIT_GAUSS_ZSCALE;  // only its square matters
+    nmi = -mu * isq;
+  }
   __device__ __forceinline__ bool safe(const MfitEvalArgs& a) const {
-    return mfit_absmax(a.xmin - mu, a.xmax - mu) * fabs(isq) < MFIT_GAUSS_ZLIMIT && fabs(a_) < 1.0e300;
+    return mfit_absmax(a.xmin - mu, a.xmax - mu) * isq < MFIT_GAUSS_ZLIMIT && fabs(a_) < 1.0e300;
+  }
+  // zs = fma(x, isq, -mu isq) instead of (x - mu) isq saves one of 14 FP64 instructions per point.  The hoisted product is
+  // rounded once, which shifts every argument by up to |mu isq| 2^-53 -- exactly what a change of mu by |mu| 2^-53 would
+  // do, i.e. the result is the exact model of a parameter vector within half an ulp of the given one.  That is invisible
+  // as long as the log-likelihood is not steeper in mu than ~1e3 per unit of relative change, guaranteed here by
+  // |mu| <= 8 |s| (tests/test_gpu_parity.py::test_gauss_far_from_origin is the counter-example: |mu / s| up to 9500, 1.4e-11).
+  __device__ __forceinline__ bool fusable(const MfitEvalArgs&) const { return fabs(nmi) <= 8.0 * MFIT_GAUSS_ZSCALE; }
+  // finite parameters and data: zs = |x - mu| |1/s| ZSCALE is then a number or +inf, never NaN, and the clamp of
+  // mfit_gauss_reduce turns everything beyond 511.75 into an amplitude of a 2^-1023 (below 1e-28 for |a| < 1e280)
+  __device__ __forceinline__ bool tame(const MfitEvalArgs& a) const {
+    return fabs(a_) < 1.0e280 && fabs(mu) < 1.0e300 && isq < 1.0e300 && fabs(b0) < 1.0e300 && fabs(b1) < 1.0e300 &&
+           a.xmin > -1.0e300 && a.xmax < 1.0e300;
   }
   template <bool SLOW, class G>
   __device__ __forceinline__ double eval(double x, G& gd) const {
@@ -134,7 +163,8 @@ struct MfitGaussLin {
       return fma(a_, exp(-0.5 * (z * z)), lin);
     }
     double s, p;
-    mfit_gauss_parts(d * isq, &s, &p, gd);
+    if (G::FUSED) mfit_gauss_parts(fma(x, isq, nmi), &s, &p, gd);   // sign-free: only MfitFusedNoGuard (no clamp) comes here
+    else mfit_gauss_parts(fabs(d) * isq, &s, &p, gd);
     return fma(a_ * s, p, lin);
   }
 };
@@ -147,6 +177,8 @@ struct MfitNvMulti {
   static constexpr int XDIMS = 1;
   static constexpr bool XVEC = false;
   static constexpr bool GUARDED = true;
+  static constexpr bool CLAMP_ONLY = false;
+  static constexpr bool FUSABLE = false;
   double sg[K], mu[K], g2, bg0;
   __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {
     g2 = MFIT_TH(2 * K);
