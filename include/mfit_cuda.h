@@ -260,6 +260,10 @@ int mfit_set_timing(mfit_ctx* ctx, int on);
 /* device time of the eval kernels of the last run / eval call, seconds (CUDA events on the ctx stream),
  * and how many eval launches it covered */
 int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches);
+/* 128-point tiles the likelihood kernels evaluated, per loop variant, since the last call while timing was on:
+ * [0] guard-free, [1] in-place clamps only, [2] recording guard, [3] guard-free with fused argument arithmetic
+ * (csrc/mfit_eval.cuh MFIT_MODE_*).  bench.py weights the FP64 instruction count of the roofline with it. */
+int mfit_eval_mode_tiles(mfit_ctx* ctx, int64_t* tiles4);
 /* A run advances the chains as up to four groups on separate streams when there are enough of them, so that one group's
  * per-chain kernels overlap the others' likelihood kernels (results do not depend on it).  0 = automatic (3, 2 or 1 by
  * chain count), 1 = one group (also what mfit_set_timing(1) implies: an overlapped kernel cannot be timed with events),

@@ -13,6 +13,7 @@
 // "how many chains are still active" (auto-stop) and the stop flag (mfit-walker-estop :860).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <thread>
@@ -22,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -52,7 +54,9 @@ struct Dataset {
   double *x = nullptr, *y = nullptr, *yw = nullptr, *w = nullptr, *c = nullptr;
   double xmin = 0.0, xmax = 0.0;  // -inf / +inf when some x is not finite
   double cst_normal = 0.0, cst_poisson = 0.0;
-  bool poisson_ok = false;
+  bool poisson_ok = false;     // every y is a count (non-negative integer-valued, <= 5e6)
+  bool poisson_ready = false;  // cst_poisson / cst_poisson_pc hold -sum log y_i!
+  double ymax = 0.0;
   // walker set with per-walker data: W_pc chains, chain w owns row w of y / yw / w / c (and of x unless x_shared)
   long long W_pc = 0;
   bool x_shared = false, sigma_shared = false;
@@ -89,6 +93,31 @@ struct EventPair { cudaEvent_t a, b; };
 // launch shape of a shared-data likelihood kernel (mfit_eval.cuh): persistent CTAs of `warps` independent warps
 struct EvalShape { int warps = 0, stages = 0, ctas = 0; size_t smem = 0; };
 
+// What every context on a device can share, made once per process: the fixed cost of a context (walker-create is called
+// per fit) was dominated by things that do not depend on it -- cudaGetDeviceProperties (~1 ms), two 16 MB pinned bounce
+// buffers (~10 ms each to pin, again to unpin), kernel attribute / occupancy queries, streams and events for the chain
+// groups.  Contexts borrow them; a mutex serialises the borrowers of the bounce buffers and stream sets.
+struct StreamSet { cudaStream_t g[3]; cudaEvent_t fork_ev, join_ev[3], poll_ev[4], stage_ev[2]; int* pinned_ints; };
+struct DeviceShared {
+  std::mutex mu;
+  bool probed = false;
+  int cc_major = 0, cc_minor = 0, sms = 0, smem_optin = 0, smem_sm = 0;
+  char* stage[2] = {nullptr, nullptr};      // pinned bounce buffers for large device -> host reads
+  std::mutex stage_mu;
+  std::vector<cudaEvent_t> slice_ev;        // one per 1 MB slice of a small read (d2h_staged)
+  std::vector<StreamSet*> free_sets;        // stream / event sets not in use by a context
+  std::map<const void*, int> resident;      // per-walker eval kernel -> CTAs resident on the whole device
+  std::map<const void*, EvalShape> shape;   // shared-data eval kernel -> launch shape (built-in kernels only)
+};
+DeviceShared* device_shared(int device) {
+  static std::mutex mu;
+  static std::map<int, DeviceShared*> all;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = all.find(device);
+  if (it == all.end()) it = all.emplace(device, new DeviceShared()).first;
+  return it->second;
+}
+
 }  // namespace
 
 struct mfit_ctx {
@@ -100,13 +129,16 @@ struct mfit_ctx {
   int D = 0, P = 0;
   std::vector<Dataset> ds;
   int seg_tiles_override = 0;
-  std::map<const void*, int> resident;  // per-walker eval kernel -> CTAs resident on the whole device
-  std::map<const void*, EvalShape> shape;  // shared-data eval kernel -> launch shape
+  std::map<const void*, int> resident;  // per-walker eval kernel -> CTAs resident on the whole device (NVRTC kernels of this context)
+  std::map<const void*, EvalShape> shape;  // shared-data eval kernel -> launch shape (NVRTC kernels of this context)
+  unsigned long long* mode_dev = nullptr;  // [4] tiles per kernel mode, counted while timing is on (mfit_eval_mode_tiles)
   int* sched_dev = nullptr;             // [2 per group] work-item counter / finished-CTA counter of the eval kernels (zero between launches)
   // A run splits the chains into two or three groups that advance on separate streams: the per-chain kernels of one
   // group (segment reduction, accept/adapt, next proposal -- latency-bound, one warp per SM) and the tail of its
   // likelihood kernel then overlap the likelihood kernels of the others.  Chains never interact: results are unchanged.
   static constexpr int kMaxGroups = 4;
+  DeviceShared* shared = nullptr;
+  StreamSet* set = nullptr;             // borrowed from `shared` for the life of the context
   cudaStream_t gstream[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};  // [0] is `stream`
   cudaEvent_t fork_ev = nullptr, join_ev[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
   int n_groups = 1;
@@ -155,7 +187,7 @@ struct mfit_ctx {
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   // pinned bounce buffers for large device -> host reads (traces): pageable destinations are filled from here
-  char* stage[2] = {nullptr, nullptr};
+  char* stage[2] = {nullptr, nullptr};   // = shared->stage while a read is in progress
   cudaEvent_t stage_ev[2];
 };
 
@@ -185,7 +217,7 @@ long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 void free_dev(void* p) { if (p) cudaFree(p); }
 
 void dataset_free_data(Dataset& d) {
-  free_dev(d.x); free_dev(d.y); free_dev(d.yw); free_dev(d.w); free_dev(d.c);
+  free_dev(d.x);  // x, y, yw, w, c are one allocation (mfit_dataset_upload_xd)
   free_dev(d.cst_normal_pc); free_dev(d.cst_poisson_pc);
   d.x = d.y = d.yw = d.w = d.c = nullptr;
   d.cst_normal_pc = d.cst_poisson_pc = nullptr;
@@ -316,6 +348,48 @@ int workspace_make(mfit_ctx* ctx, Workspace& w, long long W) {
   return 0;
 }
 
+// -sum_i log y_i! of a data set (of every row of a walker set): the table of log-factorial :379-380 -- (reduce (lambda (x y)
+// (+ x (log y))) (up-to n)), accumulated in single-float -- is built on the host up to the largest count and looked up on
+// the device (prep_kernels.cu).  Done when a log-poisson likelihood first needs it.
+int ensure_poisson_const(mfit_ctx* ctx, Dataset& s) {
+  CU(cudaSetDevice(ctx->device));
+  g_alloc_stream = ctx->stream;
+  std::vector<float> memo;
+  log_factorial_ref((long long)s.ymax, memo);
+  std::vector<double> table(memo.begin(), memo.end());
+  if (table.empty()) table.push_back(0.0);
+  const size_t rows = s.W_pc > 0 ? (size_t)s.W_pc : 1;
+  const int blocks = rows > 1 ? (int)(rows < 2048 ? rows : 2048)
+                              : (int)std::max<long long>(1, std::min<long long>(592, (s.n_pad + MFIT_PREP_THREADS - 1) / MFIT_PREP_THREADS));
+  const size_t n_res = rows > 1 ? rows : (size_t)blocks;
+  double* tab_dev = nullptr;
+  MfitPrepBlock* dev = nullptr;
+  CU(cudaMalloc(&tab_dev, sizeof(double) * table.size()));
+  CU(cudaMalloc(&dev, sizeof(MfitPrepBlock) * n_res));
+  std::vector<MfitPrepBlock> res(n_res);
+  cudaError_t e = cudaMemcpyAsync(tab_dev, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    mfit_launch_poisson_const(s.y, tab_dev, s.n, s.n_pad, (long long)rows, dev, blocks, ctx->stream);
+    ctx->launches++;
+    e = cudaMemcpyAsync(res.data(), dev, sizeof(MfitPrepBlock) * n_res, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(tab_dev); cudaFree(dev);
+  if (e != cudaSuccess) return fail(ctx, MFIT_ERR_CUDA, "log-factorial constants: %s", cudaGetErrorString(e));
+  if (rows > 1) {
+    std::vector<double> pc(rows);
+    for (size_t r = 0; r < rows; r++) pc[r] = res[r].sum + res[r].err;
+    CU(cudaMemcpyAsync(s.cst_poisson_pc, pc.data(), sizeof(double) * rows, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  } else {
+    CompSum t;
+    for (const MfitPrepBlock& b : res) { t.add(b.sum); t.c += b.err; }
+    s.cst_poisson = t.value();
+  }
+  s.poisson_ready = true;
+  return 0;
+}
+
 int check_problem_ready(mfit_ctx* ctx) {
   if (ctx->D <= 0) return fail(ctx, MFIT_ERR_STATE, "mfit_problem_define has not been called");
   for (int d = 0; d < ctx->D; d++) {
@@ -325,6 +399,10 @@ int check_problem_ready(mfit_ctx* ctx) {
     if (s.family < 0) return fail(ctx, MFIT_ERR_STATE, "dataset %d has no model (:function)", d);
     if (s.ll_kind == MFIT_LL_POISSON && !s.poisson_ok)
       return fail(ctx, MFIT_ERR_ARG, "dataset %d: log-poisson needs non-negative integer-valued y (log-factorial :379-380)", d);
+    if (s.ll_kind == MFIT_LL_POISSON && !s.poisson_ready) {
+      int rc = ensure_poisson_const(ctx, s);
+      if (rc) return rc;
+    }
     // the reference would signal a type error inside the model (a sequence used as a number, or the reverse)
     if (s.x_dims > 1 && s.model_xdims == 0)
       return fail(ctx, MFIT_ERR_ARG, "dataset %d: x has %d components but the model takes x as a number", d, s.x_dims);
@@ -397,8 +475,13 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
   const void* fpc = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_pc[s.ll_kind + (staged ? 3 : 0)]
                                               : mfit_builtin_perchain_kernel(s.family, s.degree, s.ll_kind, staged);
   if (!fpc) return fail(ctx, MFIT_ERR_STATE, "no per-walker kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
-  auto itp = ctx->resident.find(fpc);
-  if (itp == ctx->resident.end()) {
+  // built-in kernels are the same symbols for every context of the process: their attributes are set once per device
+  std::unique_lock<std::mutex> shared_lock(ctx->shared->mu, std::defer_lock);
+  const bool user_pc = s.family == MFIT_FAM_SEXPR;
+  if (!user_pc) shared_lock.lock();
+  std::map<const void*, int>& resident = user_pc ? ctx->resident : ctx->shared->resident;
+  auto itp = resident.find(fpc);
+  if (itp == resident.end()) {
     const size_t smem_max = 112 * 1024;
     CU(cudaFuncSetAttribute(fpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CU(cudaFuncSetAttribute(fpc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -406,11 +489,13 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc, MFIT_PC_THREADS, smem_pc));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     if (per_sm < 1) per_sm = 1;
-    itp = ctx->resident.emplace(fpc, per_sm * sms).first;
+    itp = resident.emplace(fpc, per_sm * sms).first;
   }
+  const int resident_ctas = itp->second;
+  if (!user_pc) shared_lock.unlock();
   const long long chains = (long long)a.n_cb * MFIT_CB;
   const long long need = (chains + MFIT_PC_THREADS / 32 - 1) / (MFIT_PC_THREADS / 32);
-  const unsigned gridp = (unsigned)(need < itp->second ? need : itp->second);
+  const unsigned gridp = (unsigned)(need < resident_ctas ? need : resident_ctas);
   void* argsp[] = {&a};
   CU(cudaLaunchKernel(fpc, dim3(gridp > 0 ? gridp : 1), dim3(MFIT_PC_THREADS), argsp, smem_pc, st));
   ctx->launches++;
@@ -431,6 +516,7 @@ int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, c
   memset(&ma, 0, sizeof ma);
   ma.n_ds = n;
   ma.sched = ctx->sched_dev + 2 * group;
+  ma.mode_tiles = ctx->timing ? ctx->mode_dev : nullptr;
   long long items = 0;
   for (int k = 0; k < n; k++) {
     fill_eval_args(ma.d[k], ctx->ds[ds[k]], w, ds[k], theta, skip, cb0, n_cb);
@@ -443,8 +529,12 @@ int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, c
   Dataset& s = ctx->ds[ds[0]];
   const void* fn = shared_data_kernel(s);
   if (!fn) return fail(ctx, MFIT_ERR_STATE, "no kernel for dataset %d (family %d degree %d)", ds[0], s.family, s.degree);
-  auto it = ctx->shape.find(fn);
-  if (it == ctx->shape.end()) {
+  std::unique_lock<std::mutex> shared_lock(ctx->shared->mu, std::defer_lock);
+  const bool user_k = s.family == MFIT_FAM_SEXPR;
+  if (!user_k) shared_lock.lock();
+  std::map<const void*, EvalShape>& shapes = user_k ? ctx->shape : ctx->shared->shape;
+  auto it = shapes.find(fn);
+  if (it == shapes.end()) {
     // Persistent CTAs of MFIT_WARPS independent warps, MFIT_MIN_CTAS per SM, a three-stage TMA ring per warp.  The
     // shape is fixed once per kernel; when the stages of a wide data set (many x components, the cutoff constants) do
     // not fit next to the math tables, first a shallower ring, then fewer warps.
@@ -483,9 +573,10 @@ int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, c
     // the kernel's __launch_bounds__ say how many CTAs per SM its registers are allotted for (MFIT_MIN_CTAS)
     if (per_sm > MFIT_MIN_CTAS) per_sm = MFIT_MIN_CTAS;
     sh.ctas = per_sm * sms;
-    it = ctx->shape.emplace(fn, sh).first;
+    it = shapes.emplace(fn, sh).first;
   }
-  const EvalShape& sh = it->second;
+  const EvalShape sh = it->second;
+  if (!user_k) shared_lock.unlock();
   ma.stages = sh.stages;
   void* args[] = {&ma};
   const long long need = (items + sh.warps - 1) / sh.warps;
@@ -608,18 +699,54 @@ void copy_out(char* dst, const char* src, size_t bytes) {
   memcpy(dst, src, per < bytes ? per : bytes);
   for (auto& t : th) if (t.joinable()) t.join();
 }
+// MFIT_DEBUG_TIMING=1: wall-clock marks of the set-up path on stderr (each mark synchronises the stream first)
+struct PhaseClock {
+  bool on; double t0; cudaStream_t st;
+  explicit PhaseClock(cudaStream_t s);
+  void mark(const char* what);
+};
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+PhaseClock::PhaseClock(cudaStream_t s) : on(getenv("MFIT_DEBUG_TIMING") != nullptr), t0(now_ms()), st(s) {}
+void PhaseClock::mark(const char* what) {
+  if (!on) return;
+  cudaStreamSynchronize(st);
+  const double t = now_ms();
+  fprintf(stderr, "  [mfit] %-28s %8.3f ms\n", what, t - t0);
+  t0 = t;
+}
 int d2h_staged(mfit_ctx* ctx, void* dst, const void* src, size_t bytes) {
-  if (bytes < ((size_t)1 << 20)) {
+  if (bytes < ((size_t)512 << 10)) {
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
   }
-  for (int i = 0; i < 2; i++)
-    if (!ctx->stage[i]) {
-      CU(cudaMallocHost(&ctx->stage[i], kStageBytes));
-      CU(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+  std::lock_guard<std::mutex> stage_lock(ctx->shared->stage_mu);  // the bounce buffers belong to the device, not to the context
+  for (int i = 0; i < 2; i++) {
+    if (!ctx->shared->stage[i]) CU(cudaMallocHost(&ctx->shared->stage[i], kStageBytes));
+    ctx->stage[i] = ctx->shared->stage[i];
+  }
+  if (bytes <= kStageBytes) {
+    // A few MB (the trace of a short run): one DMA per 1 MB slice into the first bounce buffer, all enqueued at once, and the
+    // CPU copies slice i out -- mostly page faults of the caller's fresh pages -- while the later ones are still in flight.
+    const size_t slice = (size_t)1 << 20, n = (bytes + slice - 1) / slice;
+    std::vector<cudaEvent_t>& evs = ctx->shared->slice_ev;
+    while (evs.size() < n) {
+      cudaEvent_t ev;
+      CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      evs.push_back(ev);
     }
+    for (size_t i = 0; i < n; i++) {
+      const size_t len = i + 1 < n ? slice : bytes - i * slice;
+      CU(cudaMemcpyAsync(ctx->stage[0] + i * slice, (const char*)src + i * slice, len, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaEventRecord(evs[i], ctx->stream));
+    }
+    for (size_t i = 0; i < n; i++) {
+      const size_t len = i + 1 < n ? slice : bytes - i * slice;
+      CU(cudaEventSynchronize(evs[i]));
+      memcpy((char*)dst + i * slice, ctx->stage[0] + i * slice, len);
+    }
+    return 0;
+  }
   const size_t n_chunks = (bytes + kStageBytes - 1) / kStageBytes;
   auto chunk_len = [&](size_t i) { return i + 1 < n_chunks ? kStageBytes : bytes - i * kStageBytes; };
   for (size_t i = 0; i <= n_chunks; i++) {
@@ -711,12 +838,7 @@ int run_begin(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long lon
   mfit_launch_pre(c, r, ctx->stream);    // proposals of chains that keep their l-matrix
   mfit_launch_reest(c, r, ctx->stream);  // chains resuming a long walk re-estimate first (:897-901)
   ctx->launches += 3;
-  if (!ctx->poll_ev_made) {
-    for (auto& e : ctx->poll_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CU(cudaMallocHost(&ctx->active_host, sizeof(int) * 4));
-    CU(cudaMalloc(&ctx->active_dev, sizeof(int) * 4));
-    ctx->poll_ev_made = true;
-  }
+  if (!ctx->active_dev) CU(cudaMalloc(&ctx->active_dev, sizeof(int) * 4));
   ctx->run_cfg = r;
   ctx->run_t = 0;
   ctx->run_max = max_steps;
@@ -810,7 +932,8 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
       const int R = ctx->n_ranks;
       if (!ctx->xflag_dev) {
         CU(cudaMalloc(&ctx->xflag_dev, sizeof(int) * 2 * R));
-        CU(cudaMallocHost(&ctx->xflag_host, sizeof(int) * 2 * R));
+        if (2 * R > 56) return fail(ctx, MFIT_ERR_ARG, "more than 28 ranks");
+        ctx->xflag_host = ctx->active_host + 8;  // the context's pinned words: [0,4) active counts, [8, 8 + 2R) these flags
       }
       mfit_launch_count_active(c, ctx->xflag_dev + 2 * ctx->rank, ctx->stream);
       ctx->launches++;
@@ -887,23 +1010,51 @@ int mfit_ctx_create(int device, void* stream, mfit_ctx** out) {
   if (device < 0 || device >= n) return fail(nullptr, MFIT_ERR_ARG, "device %d out of range (have %d)", device, n);
   e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail(nullptr, MFIT_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
-  cudaDeviceProp prop;
-  cudaGetDeviceProperties(&prop, device);
-  if (prop.major != 10)
-    return fail(nullptr, MFIT_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
-                prop.minor);
+  DeviceShared* sh = device_shared(device);
+  StreamSet* set = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(sh->mu);
+    if (!sh->probed) {
+      cudaDeviceGetAttribute(&sh->cc_major, cudaDevAttrComputeCapabilityMajor, device);
+      cudaDeviceGetAttribute(&sh->cc_minor, cudaDevAttrComputeCapabilityMinor, device);
+      cudaDeviceGetAttribute(&sh->sms, cudaDevAttrMultiProcessorCount, device);
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = 16ull << 30;  // freed blocks stay cached up to 16 GB; beyond that they go back to the driver
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      sh->probed = true;
+    }
+    if (sh->cc_major != 10)
+      return fail(nullptr, MFIT_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, sh->cc_major,
+                  sh->cc_minor);
+    if (!sh->free_sets.empty()) { set = sh->free_sets.back(); sh->free_sets.pop_back(); }
+  }
+  if (!set) {  // streams of the chain groups, their fork / join events, the poll and bounce-buffer events, a pinned word or two
+    set = new StreamSet();
+    bool ok = true;
+    for (auto& g : set->g) ok = ok && cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&set->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& ev : set->join_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& ev : set->poll_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& ev : set->stage_ev) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost(&set->pinned_ints, 64 * sizeof(int)) == cudaSuccess;
+    if (!ok) return fail(nullptr, MFIT_ERR_CUDA, "stream / event set: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   mfit_ctx* c = new mfit_ctx();
   c->device = device;
+  c->shared = sh;
+  c->set = set;
+  for (int g = 1; g < mfit_ctx::kMaxGroups; g++) { c->gstream[g] = set->g[g - 1]; c->join_ev[g] = set->join_ev[g - 1]; }
+  c->fork_ev = set->fork_ev;
+  for (int k = 0; k < 4; k++) c->poll_ev[k] = set->poll_ev[k];
+  for (int k = 0; k < 2; k++) c->stage_ev[k] = set->stage_ev[k];
+  c->active_host = set->pinned_ints;
   if (stream) c->stream = (cudaStream_t)stream;
   else {
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(nullptr, MFIT_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     c->own_stream = true;
-  }
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    unsigned long long keep = 16ull << 30;  // freed blocks stay cached up to 16 GB; beyond that they go back to the driver
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   *out = c;
   return 0;
@@ -917,19 +1068,15 @@ void mfit_ctx_destroy(mfit_ctx* ctx) {
   chains_free(ctx);
   for (auto& d : ctx->ds) { dataset_free_data(d); dataset_free_prior(d); dataset_free_model(d); }
   free_dev(ctx->temps_dev); free_dev(ctx->z_dev); free_dev(ctx->u_dev); free_dev(ctx->lshared_dev);
-  free_dev(ctx->active_dev); free_dev(ctx->flush_buf); free_dev(ctx->sched_dev);
-  if (ctx->active_host) cudaFreeHost(ctx->active_host);
+  free_dev(ctx->active_dev); free_dev(ctx->flush_buf); free_dev(ctx->sched_dev); free_dev(ctx->mode_dev);
   free_dev(ctx->xflag_dev);
-  if (ctx->xflag_host) cudaFreeHost(ctx->xflag_host);
-  for (int i = 0; i < 2; i++)
-    if (ctx->stage[i]) { cudaFreeHost(ctx->stage[i]); cudaEventDestroy(ctx->stage_ev[i]); }
-  if (ctx->poll_ev_made) for (auto& e : ctx->poll_ev) cudaEventDestroy(e);
   for (auto& p : ctx->ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
-  if (ctx->comm) mfit_nccl_comm_destroy(ctx->comm);
   cudaStreamSynchronize(ctx->stream);  // the stream-ordered frees above
-  for (int g = 1; g < mfit_ctx::kMaxGroups; g++)
-    if (ctx->gstream[g]) { cudaStreamDestroy(ctx->gstream[g]); cudaEventDestroy(ctx->join_ev[g]); }
-  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  for (int g = 1; g < mfit_ctx::kMaxGroups; g++) cudaStreamSynchronize(ctx->gstream[g]);
+  {  // the stream / event set goes back to the device's pool
+    std::lock_guard<std::mutex> lock(ctx->shared->mu);
+    ctx->shared->free_sets.push_back(ctx->set);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -973,6 +1120,35 @@ int mfit_dataset_upload(mfit_ctx* ctx, int d, const double* x, const double* y, 
   return mfit_dataset_upload_xd(ctx, d, x, 0, y, sigma, n);
 }
 
+// host -> device rows of n doubles laid down n_pad apart, the padding of every row zeroed
+static int upload_rows(mfit_ctx* ctx, double* dst, const double* src, size_t n, size_t n_pad, size_t rows) {
+  if (n > 0 && rows > 0)
+    CU(cudaMemcpy2DAsync(dst, n_pad * sizeof(double), src, n * sizeof(double), n * sizeof(double), rows, cudaMemcpyHostToDevice,
+                         ctx->stream));
+  if (n_pad > n && rows > 0)
+    CU(cudaMemset2DAsync(dst + n, n_pad * sizeof(double), 0, (n_pad - n) * sizeof(double), rows, ctx->stream));
+  return 0;
+}
+
+// the upload pass (prep_kernels.cu) over a data set already in device memory (sigma in s.c), and its small results
+static int prepare_dataset(mfit_ctx* ctx, Dataset& s, size_t rows, size_t x_rows, size_t sig_rows, bool have_sigma,
+                           std::vector<MfitPrepBlock>& res) {
+  const int blocks = rows > 1 ? (int)(rows < 2048 ? rows : 2048)
+                              : (int)std::max<long long>(1, std::min<long long>(592, (s.n_pad + MFIT_PREP_THREADS - 1) / MFIT_PREP_THREADS));
+  const size_t n_res = rows > 1 ? rows : (size_t)blocks;
+  MfitPrepBlock* dev = nullptr;
+  CU(cudaMalloc(&dev, sizeof(MfitPrepBlock) * n_res));
+  mfit_launch_prepare(s.x, s.y, s.yw, s.w, s.c, s.n, s.n_pad, (long long)rows, (long long)x_rows, (long long)sig_rows,
+                      have_sigma ? 1 : 0, dev, blocks, ctx->stream);
+  ctx->launches += (rows > 1 && sig_rows == 1) ? 2 : 1;
+  res.resize(n_res);
+  cudaError_t e = cudaMemcpyAsync(res.data(), dev, sizeof(MfitPrepBlock) * n_res, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // also: the caller's arrays are free to go
+  cudaFree(dev);
+  if (e != cudaSuccess) return fail(ctx, MFIT_ERR_CUDA, "dataset upload: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // x_dims = 0: every x is a number; x_dims >= 1: every x is a sequence of x_dims numbers, component k of point i at
 // x[k * n + i]
 int mfit_dataset_upload_xd(mfit_ctx* ctx, int d, const double* x, int x_dims, const double* y, const double* sigma, int64_t n) {
@@ -986,51 +1162,39 @@ int mfit_dataset_upload_xd(mfit_ctx* ctx, int d, const double* x, int x_dims, co
   s.n_pad = round_up(n > 0 ? n : 1, MFIT_TILE);
   s.x_is_sequence = x_dims > 0;
   s.x_dims = x_dims > 0 ? x_dims : 1;
-  std::vector<double> w((size_t)s.n_pad, 0.0), cc((size_t)s.n_pad, 0.0), xx((size_t)s.n_pad * s.x_dims, 0.0), yy((size_t)s.n_pad, 0.0),
-      yw((size_t)s.n_pad, 0.0);
-  for (int k = 1; k < s.x_dims; k++)
-    for (long long i = 0; i < n; i++) xx[(size_t)k * s.n_pad + i] = x[(size_t)k * n + i];
-  double xmin = INFINITY, xmax = -INFINITY;
-  bool x_finite = true;
-  const double a = -0.5 * std::log(2.0 * 3.141592653589793);  // (* -1/2 (log (* 2 pi))) :377
-  CompSum cst, pcst;
-  bool pois_ok = true;
-  std::vector<float> memo;
-  for (long long i = 0; i < n; i++) {
-    const double sg = sigma ? sigma[i] : 1.0;  // (if data-error data-error 1) :1144
-    xx[i] = x[i];
-    yy[i] = y[i];
-    w[i] = 1.0 / sg;
-    yw[i] = y[i] * w[i];
-    if (!std::isfinite(x[i])) x_finite = false;
-    if (x[i] < xmin) xmin = x[i];
-    if (x[i] > xmax) xmax = x[i];
-    const double ci = a + (-1.0 * std::log(sg));
-    cc[i] = ci;
-    cst.add(ci);
-    const double k = y[i];
-    if (pois_ok) {
-      if (!(k >= 0.0) || k != std::floor(k) || k > 5e6) pois_ok = false;
-      else pcst.add(-log_factorial_ref((long long)k, memo));
-    }
+  const size_t np = (size_t)s.n_pad, bytes = sizeof(double) * np;
+  PhaseClock pc(ctx->stream);
+  // one allocation: [x_0 .. x_{dims-1}][y][y/sigma][1/sigma][c]
+  double* block = nullptr;
+  CU(cudaMalloc(&block, bytes * (s.x_dims + 4)));
+  s.x = block; s.y = block + np * s.x_dims; s.yw = s.y + np; s.w = s.yw + np; s.c = s.w + np;
+  int rc = upload_rows(ctx, s.x, x, (size_t)n, np, (size_t)s.x_dims);
+  if (!rc) rc = upload_rows(ctx, s.y, y, (size_t)n, np, 1);
+  if (!rc && sigma) rc = upload_rows(ctx, s.c, sigma, (size_t)n, np, 1);
+  pc.mark("upload: alloc + H2D");
+  std::vector<MfitPrepBlock> res;
+  if (!rc) rc = prepare_dataset(ctx, s, 1, 1, 1, sigma != nullptr, res);
+  pc.mark("upload: prepare pass");
+  if (rc) { dataset_free_data(s); return rc; }
+  CompSum cst;
+  double xmin = INFINITY, xmax = -INFINITY, ymax = 0.0;
+  bool x_finite = true, pois_ok = true;
+  for (const MfitPrepBlock& b : res) {  // block order
+    cst.add(b.sum);
+    cst.c += b.err;
+    if (b.xmin < xmin) xmin = b.xmin;
+    if (b.xmax > xmax) xmax = b.xmax;
+    if (b.ymax > ymax) ymax = b.ymax;
+    if (b.bad_x) x_finite = false;
+    if (b.bad_pois) pois_ok = false;
   }
   s.xmin = x_finite && n > 0 && !s.x_is_sequence ? xmin : -INFINITY;
   s.xmax = x_finite && n > 0 && !s.x_is_sequence ? xmax : INFINITY;
   s.cst_normal = cst.value();
-  s.cst_poisson = pcst.value();
+  s.cst_poisson = 0.0;
   s.poisson_ok = pois_ok;
-  const size_t bytes = sizeof(double) * (size_t)s.n_pad;
-  CU(cudaMalloc(&s.x, bytes * s.x_dims));
-  if (s.x_dims > 1)
-    CU(cudaMemcpyAsync(s.x + s.n_pad, xx.data() + s.n_pad, bytes * (s.x_dims - 1), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMalloc(&s.y, bytes)); CU(cudaMalloc(&s.yw, bytes)); CU(cudaMalloc(&s.w, bytes));
-  CU(cudaMalloc(&s.c, bytes));
-  CU(cudaMemcpyAsync(s.x, xx.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.y, yy.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.yw, yw.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.w, w.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.c, cc.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  s.poisson_ready = false;   // -sum log y_i! is formed when a log-poisson likelihood first needs it (ensure_poisson_const)
+  s.ymax = ymax;
   if (ctx->have_chains) chains_free(ctx);  // segment geometry changed: chains must be re-initialised
   return 0;
 }
@@ -1051,55 +1215,38 @@ int mfit_dataset_upload_per_walker(mfit_ctx* ctx, int d, const double* x, const 
   s.x_shared = x_shared != 0;
   s.sigma_shared = sigma_shared != 0 || sigma == nullptr;
   const size_t np = (size_t)s.n_pad, rows = (size_t)W, xrows = x_shared ? 1 : rows, wrows = s.sigma_shared ? 1 : rows;
-  std::vector<double> xx(np * xrows, 0.0), yy(np * rows, 0.0), yw(np * rows, 0.0), w(np * wrows, 0.0), cc(np * wrows, 0.0);
-  std::vector<double> cst(rows, 0.0), pcst(rows, 0.0);
-  const double a = -0.5 * std::log(2.0 * 3.141592653589793);  // (* -1/2 (log (* 2 pi))) :377
-  double xmin = INFINITY, xmax = -INFINITY;
+  // one allocation: [x rows][y rows][y/sigma rows][1/sigma rows][c rows]
+  double* block = nullptr;
+  CU(cudaMalloc(&block, sizeof(double) * np * (xrows + 2 * rows + 2 * wrows)));
+  s.x = block; s.y = s.x + np * xrows; s.yw = s.y + np * rows; s.w = s.yw + np * rows; s.c = s.w + np * wrows;
+  int rc = upload_rows(ctx, s.x, x, (size_t)n, np, xrows);
+  if (!rc) rc = upload_rows(ctx, s.y, y, (size_t)n, np, rows);
+  if (!rc && sigma) rc = upload_rows(ctx, s.c, sigma, (size_t)n, np, wrows);
+  std::vector<MfitPrepBlock> res;
+  if (!rc) rc = prepare_dataset(ctx, s, rows, xrows, wrows, sigma != nullptr, res);
+  if (rc) { dataset_free_data(s); return rc; }
+  std::vector<double> cst(rows);
+  double xmin = INFINITY, xmax = -INFINITY, ymax = 0.0;
   bool x_finite = true, pois_ok = true;
-  std::vector<float> memo;
-  for (size_t r = 0; r < xrows; r++)
-    for (long long i = 0; i < n; i++) {
-      const double v = x[r * (size_t)n + i];
-      xx[r * np + i] = v;
-      if (!std::isfinite(v)) x_finite = false;
-      if (v < xmin) xmin = v;
-      if (v > xmax) xmax = v;
-    }
   for (size_t r = 0; r < rows; r++) {
-    CompSum c0, p0;
-    for (long long i = 0; i < n; i++) {
-      const double sg = sigma ? sigma[(sigma_shared ? 0 : r * (size_t)n) + i] : 1.0;  // (if data-error data-error 1) :1144
-      const double yv = y[r * (size_t)n + i];
-      const size_t o = r * np + i, ow = (s.sigma_shared ? 0 : r * np) + i;
-      yy[o] = yv;
-      w[ow] = 1.0 / sg;
-      yw[o] = yv * w[ow];
-      const double ci = a + (-1.0 * std::log(sg));
-      cc[ow] = ci;
-      c0.add(ci);
-      if (pois_ok) {
-        if (!(yv >= 0.0) || yv != std::floor(yv) || yv > 5e6) pois_ok = false;
-        else p0.add(-log_factorial_ref((long long)yv, memo));
-      }
-    }
-    cst[r] = c0.value();
-    pcst[r] = p0.value();
+    const MfitPrepBlock& b = res[r];
+    cst[r] = b.sum + b.err;
+    if (b.xmin < xmin) xmin = b.xmin;
+    if (b.xmax > xmax) xmax = b.xmax;
+    if (b.ymax > ymax) ymax = b.ymax;
+    if (b.bad_x) x_finite = false;
+    if (b.bad_pois) pois_ok = false;
   }
   s.xmin = x_finite && n > 0 ? xmin : -INFINITY;
   s.xmax = x_finite && n > 0 ? xmax : INFINITY;
   s.cst_normal = s.cst_poisson = 0.0;
   s.poisson_ok = pois_ok;
-  const size_t bytes = sizeof(double) * np * rows, xbytes = sizeof(double) * np * xrows, cb = sizeof(double) * rows;
-  const size_t wbytes = sizeof(double) * np * wrows;
-  CU(cudaMalloc(&s.x, xbytes)); CU(cudaMalloc(&s.y, bytes)); CU(cudaMalloc(&s.yw, bytes)); CU(cudaMalloc(&s.w, wbytes));
-  CU(cudaMalloc(&s.c, wbytes)); CU(cudaMalloc(&s.cst_normal_pc, cb)); CU(cudaMalloc(&s.cst_poisson_pc, cb));
-  CU(cudaMemcpyAsync(s.x, xx.data(), xbytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.y, yy.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.yw, yw.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.w, w.data(), wbytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.c, cc.data(), wbytes, cudaMemcpyHostToDevice, ctx->stream));
+  s.poisson_ready = false;
+  s.ymax = ymax;
+  const size_t cb = sizeof(double) * rows;
+  CU(cudaMalloc(&s.cst_normal_pc, cb)); CU(cudaMalloc(&s.cst_poisson_pc, cb));
   CU(cudaMemcpyAsync(s.cst_normal_pc, cst.data(), cb, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(s.cst_poisson_pc, pcst.data(), cb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(s.cst_poisson_pc, 0, cb, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (ctx->have_chains) chains_free(ctx);
   return 0;
@@ -1297,18 +1444,32 @@ int mfit_chains_init(mfit_ctx* ctx, const double* theta0, int64_t W, uint64_t se
   int rc = check_problem_ready(ctx);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  PhaseClock pc(ctx->stream);
   chains_free(ctx);
   rc = workspace_make(ctx, ctx->ws, W);
   if (rc) return rc;
+  pc.mark("chains_init: workspace");
   const int P = ctx->P, D = ctx->D;
   MfitChains& c = ctx->ch;
   c = view_of(ctx, ctx->ws);
   const size_t st = (size_t)c.stride;
-#define CA(field, count) if ((rc = chain_alloc(ctx, &c.field, (count))) != 0) { chains_free(ctx); return rc; }
+  // every per-chain array out of ONE zeroed allocation (seventeen allocations and memsets cost more than the first step)
+  struct Slot { void** p; size_t bytes; };
+  std::vector<Slot> slots;
+  size_t total = 0;
+#define CA(field, count)                                                            \
+  slots.push_back({(void**)&c.field, (sizeof(*c.field) * (size_t)(count) + 255) & ~(size_t)255}); \
+  total += slots.back().bytes;
   CA(cur_theta, P * st) CA(cur_prob, st) CA(prop_theta, P * st) CA(best_theta, P * st) CA(best_prob, st)
   CA(L, (size_t)P * P * st) CA(loop_i, st) CA(shutting, st) CA(done, st) CA(need_reest, st) CA(temperature, st)
   CA(length, st) CA(age, st) CA(rows, st) CA(reset_index, st) CA(steps_run, st) CA(l_updates, st)
+#undef CA
   (void)D;
+  {
+    char* base = nullptr;
+    if ((rc = chain_alloc(ctx, &base, total)) != 0) { chains_free(ctx); return rc; }
+    for (const Slot& sl : slots) { *sl.p = base; base += sl.bytes; }
+  }
   long long cap = trace_capacity;
   ctx->cap_fixed = trace_capacity > 0;
   const long long mincap = min_trace_cap(P);
@@ -1316,7 +1477,7 @@ int mfit_chains_init(mfit_ctx* ctx, const double* theta0, int64_t W, uint64_t se
   c.cap = cap;
   if ((rc = chain_alloc(ctx, &c.trace_theta, (size_t)cap * P * st, false)) != 0) { chains_free(ctx); return rc; }
   if ((rc = chain_alloc(ctx, &c.trace_prob, (size_t)cap * st, false)) != 0) { chains_free(ctx); return rc; }
-#undef CA
+  pc.mark("chains_init: chain arrays");
   ctx->seed = seed;
   ctx->chain_base = chain_id_base;
   ctx->have_chains = true;
@@ -1333,6 +1494,7 @@ int mfit_chains_init(mfit_ctx* ctx, const double* theta0, int64_t W, uint64_t se
   ctx->launches++;
   rc = exchange(ctx, ctx->ws);
   if (rc) { cudaFree(th_rm); return rc; }
+  pc.mark("chains_init: first eval");
   mfit_launch_first_step(c, ctx->stream);
   ctx->rows_upper = 1;
   ctx->launches++;
@@ -1358,15 +1520,26 @@ static int make_cfg(mfit_ctx* ctx, const mfit_adapt_cfg* cfg, MfitRunCfg& r) {
   r.greedy = cfg->greedy;
   r.temperature0 = cfg->temperature;
   // temps :878  (max 1 (* (cos (* x pi (+ 1 (* 2 (floor temp-steps 5000))) (/ (* 2 temp-steps)))) temperature))
-  std::vector<double> temps((size_t)r.Tn);
-  const double pi = 3.141592653589793;
-  const double k = (double)(1 + 2 * (r.Tn / 5000));
-  const double inv = 1.0 / (double)(2 * r.Tn);
-  for (long long x = 0; x < r.Tn; x++) {
-    const double a = (((double)x * pi) * k) * inv;
-    const double t = std::cos(a) * cfg->temperature;
-    temps[(size_t)x] = t > 1.0 ? t : 1.0;
+  // 30000 cosines are half a millisecond of host time per run: the last table is kept per process
+  static std::mutex temps_mu;
+  static std::vector<double> temps_cache;
+  static long long temps_cache_Tn = -1;
+  static double temps_cache_T = 0.0;
+  std::lock_guard<std::mutex> lock(temps_mu);
+  if (temps_cache_Tn != r.Tn || temps_cache_T != cfg->temperature) {
+    temps_cache.resize((size_t)r.Tn);
+    const double pi = 3.141592653589793;
+    const double k = (double)(1 + 2 * (r.Tn / 5000));
+    const double inv = 1.0 / (double)(2 * r.Tn);
+    for (long long x = 0; x < r.Tn; x++) {
+      const double a = (((double)x * pi) * k) * inv;
+      const double t = std::cos(a) * cfg->temperature;
+      temps_cache[(size_t)x] = t > 1.0 ? t : 1.0;
+    }
+    temps_cache_Tn = r.Tn;
+    temps_cache_T = cfg->temperature;
   }
+  const std::vector<double>& temps = temps_cache;
   if (ctx->temps_len < r.Tn) {
     free_dev(ctx->temps_dev);
     ctx->temps_dev = nullptr;
@@ -1845,10 +2018,23 @@ int mfit_nccl_unique_id(void* id_out) {
 int mfit_nccl_attach(mfit_ctx* ctx, const void* unique_id, int rank, int n_ranks) {
   if (!ctx || !unique_id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return MFIT_ERR_ARG;
   CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
-  if (ctx->comm) { mfit_nccl_comm_destroy(ctx->comm); ctx->comm = nullptr; }
-  std::string e;
-  int rc = mfit_nccl_comm_init(&ctx->comm, n_ranks, unique_id, rank, e);
-  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  // One communicator per (unique id, rank) and process, shared by every context that attaches with it: bringing a
+  // communicator up costs tens of milliseconds (ncclCommInitRank is a collective with a bootstrap network round), which a
+  // program that builds walker set after walker set must not pay each time.  It lives until the process ends.
+  static std::mutex mu;
+  static std::map<std::string, void*> comms;
+  std::string key((const char*)unique_id, 128);
+  key += "/" + std::to_string(rank) + "/" + std::to_string(n_ranks) + "/" + std::to_string(ctx->device);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = comms.find(key);
+  if (it == comms.end()) {
+    void* comm = nullptr;
+    std::string e;
+    int rc = mfit_nccl_comm_init(&comm, n_ranks, unique_id, rank, e);
+    if (rc) return fail(ctx, rc, "%s", e.c_str());
+    it = comms.emplace(key, comm).first;
+  }
+  ctx->comm = it->second;
   ctx->rank = rank;
   ctx->n_ranks = n_ranks;
   return 0;
@@ -1912,10 +2098,27 @@ int mfit_set_timing(mfit_ctx* ctx, int on) {
   if (!ctx) return MFIT_ERR_ARG;
   CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
   ctx->timing = on != 0;
+  if (ctx->timing && !ctx->mode_dev) {
+    CU(cudaMalloc(&ctx->mode_dev, 4 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ctx->mode_dev, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  }
   if (ctx->timing && ctx->ev.empty()) {
     ctx->ev.resize(4096);
     for (auto& p : ctx->ev) { CU(cudaEventCreate(&p.a)); CU(cudaEventCreate(&p.b)); }
   }
+  return 0;
+}
+
+int mfit_eval_mode_tiles(mfit_ctx* ctx, int64_t* tiles4) {
+  if (!ctx || !tiles4) return MFIT_ERR_ARG;
+  for (int k = 0; k < 4; k++) tiles4[k] = 0;
+  if (!ctx->mode_dev) return 0;
+  CU(cudaSetDevice(ctx->device));
+  unsigned long long h[4];
+  CU(cudaMemcpyAsync(h, ctx->mode_dev, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 4; k++) tiles4[k] = (int64_t)h[k];
+  CU(cudaMemsetAsync(ctx->mode_dev, 0, sizeof h, ctx->stream));
   return 0;
 }
 

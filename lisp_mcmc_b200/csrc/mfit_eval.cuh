@@ -92,6 +92,7 @@ struct MfitMultiArgs {
   int stages;                         /* depth of every warp's TMA ring (>= 1; 2 or more to overlap fetch and arithmetic) */
   int item_start[MFIT_MAX_FUSED + 1]; /* items [item_start[k], item_start[k+1]) belong to d[k]; chain-block fastest inside */
   int* sched;                         /* [2] zero between launches: next item to hand out, CTAs that have finished */
+  unsigned long long* mode_tiles;     /* [4] or null: tiles evaluated per MFIT_MODE_* (measurement: which loop ran how often) */
   MfitEvalArgs d[MFIT_MAX_FUSED];
 };
 
@@ -450,6 +451,7 @@ __device__ __forceinline__ void mfit_eval_body_t(const MfitMultiArgs& ma) {
       }
     }
     const int nt = tiles_of(a, seg);
+    if (ma.mode_tiles != nullptr && lane == 0 && any_live) atomicAdd(ma.mode_tiles + mode, (unsigned long long)nt);
     long long rem_ll = a.n - (long long)seg * a.tiles_per_seg * (long long)MFIT_TILE;  // points from the segment's first one on
     int rem = rem_ll < (long long)nt * MFIT_TILE ? (int)rem_ll : nt * MFIT_TILE;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};

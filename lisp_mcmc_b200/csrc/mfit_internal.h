@@ -5,6 +5,14 @@
 #include <stdint.h>
 #include "../../include/mfit_cuda.h"
 
+// prep_kernels.cu: per-block (shared data) or per-row (walker sets) results of the upload pass
+#define MFIT_PREP_THREADS 256
+struct MfitPrepBlock {
+  double sum, err;      /* compensated sum of the block's terms and the collected rounding errors */
+  double xmin, xmax, ymax;
+  int bad_x, bad_pois;  /* some x not finite / some y not a count */
+};
+
 #ifdef __cplusplus
 #include <string>
 #include <vector>
@@ -18,6 +26,14 @@ const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int sta
 
 // eval_fit.cu
 const void* mfit_builtin_fit_kernel(int family, int degree);
+
+#ifdef __CUDACC__
+void mfit_launch_prepare(const double* x, const double* y, double* yw, double* w, double* c, long long n, long long n_pad,
+                         long long rows, long long x_rows, long long sig_rows, int have_sigma, MfitPrepBlock* out, int blocks,
+                         cudaStream_t st);
+void mfit_launch_poisson_const(const double* y, const double* table, long long n, long long n_pad, long long rows,
+                               MfitPrepBlock* out, int blocks, cudaStream_t st);
+#endif
 
 // lower.cpp
 // x_dims (may be null): 0 when the model uses x as a number, else the number of components of x it reads

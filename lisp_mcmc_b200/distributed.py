@@ -71,6 +71,22 @@ def broadcast_nccl_unique_id():
     return C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
 
 
+_PROCESS_UID = None
+
+
+def process_comm(rank=None, world=None):
+    """(unique id, rank, world) for Walker(nccl=...): ONE ncclUniqueId per process and job -- made on rank 0 and broadcast
+    the first time, reused afterwards -- so that every walker set of this process attaches to the same communicator
+    (libmfit_cuda.so keeps one per id; ncclCommInitRank is a collective that costs tens of milliseconds)."""
+    global _PROCESS_UID
+    r, _, w = env_ranks()
+    rank = r if rank is None else rank
+    world = w if world is None else world
+    if _PROCESS_UID is None:
+        _PROCESS_UID = broadcast_nccl_unique_id()
+    return _PROCESS_UID, rank, world
+
+
 def chain_shard(W):
     """(first global chain id, count) of this rank"""
     dist = _dist()
@@ -168,5 +184,4 @@ def walker_create_sharded(cfg, mode="chains", **gpu):
         raise ValueError("mode must be 'chains' or 'datasets'")
     if world == 1:
         return workloads.make_walker(cfg, **gpu)
-    uid = broadcast_nccl_unique_id()
-    return workloads.make_walker(cfg, nccl=(uid, rank, world), dataset_owners=dataset_owners(len(cfg["function"])), **gpu)
+    return workloads.make_walker(cfg, nccl=process_comm(rank, world), dataset_owners=dataset_owners(len(cfg["function"])), **gpu)

@@ -43,7 +43,8 @@ def c2(W=4096, N=100000):
     keys = ["a", "mu", "s", "b0", "b1"]
     return dict(name="C2", function=[builtin("gauss_lin", keys)], data=[[x, y]], data_error=[sig], keys=keys,
                 theta_star=th, theta0=_jitter(th, W, 0.05, 2002), log_liklihood="log-liklihood-normal",
-                log_prior="log-prior-flat", steps=2000, flop_per_point=12, transc_per_point={"exp": 1}, fp64_instr_per_point=14)
+                log_prior="log-prior-flat", steps=2000, flop_per_point=12, transc_per_point={"exp": 1}, fp64_instr_per_point=14,
+                fp64_instr_by_mode=[14, 14, 14, 13])   # guard-free, clamp-only, guarded, fused argument (profiles/r02_sass_gauss_lin.txt)
 
 
 def c3(W=16384, N=1000000):
