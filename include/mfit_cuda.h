@@ -52,7 +52,8 @@ enum { MFIT_FAM_POLY = 0, MFIT_FAM_EXPO = 1, MFIT_FAM_SINUS = 2, MFIT_FAM_LORENT
 /* :log-liklihood slot values.  NORMAL = log-liklihood-normal :393-400, NORMAL_CUTOFF =
  * log-liklihood-normal-cutoff :419-427, POISSON = (create-log-liklihood-function
  * (lambda (y model error) (log-poisson model y))) :402-417 with log-poisson :382-383. */
-enum { MFIT_LL_NORMAL = 0, MFIT_LL_NORMAL_CUTOFF = 1, MFIT_LL_POISSON = 2 };
+enum { MFIT_LL_NORMAL = 0, MFIT_LL_NORMAL_CUTOFF = 1, MFIT_LL_POISSON = 2,
+       MFIT_LL_USER = 3 /* set by mfit_likelihood_sexpr only */ };
 
 enum { MFIT_AUTO_NONE = 0, MFIT_AUTO_PROB_SETTLE = 1 };      /* :auto, :862 */
 enum { MFIT_OPT_COVARIANCE = 0, MFIT_OPT_BEST_VALUE = 1 };   /* :sampling-optimization, :862 */
@@ -119,6 +120,15 @@ int mfit_model_builtin(mfit_ctx* ctx, int d, int family, int degree, const int32
  * key_names are the P keys of the :params plist in order.  Lowered to CUDA C, NVRTC -> sm_100a. */
 int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* const* key_names, int n_keys);
 int mfit_likelihood_set(mfit_ctx* ctx, int d, int kind);
+/* :log-liklihood = (create-log-liklihood-function <lambda>) :402-417 with any per-point (lambda (y model error) ...):
+ * the text is lowered to CUDA C (csrc/lower.cpp, kind 2) and compiled by NVRTC into the same likelihood kernel, together
+ * with the data set's :function (built-in family or lowered lambda).  The kernel sums g(y_i, f(x_i; theta), error) in
+ * data order; nothing is hoisted.  As in the reference (:416) `error` is the data set's WHOLE stddev list, not the
+ * point's: (elt error k) / (first error) ... with a literal k < 16 read it (a per-data-set constant).  The reference's
+ * own densities may be called: (log-normal x mu sigma), (log-poisson lambda y), (log-factorial y) -- the latter two
+ * with the lambda's y only (a table built at upload, single-float accumulation :379-380).
+ * (lambda (y model error) (log-poisson model y)) is recognised and becomes MFIT_LL_POISSON itself. */
+int mfit_likelihood_sexpr(mfit_ctx* ctx, int d, const char* lambda_text);
 /* :log-prior slot.  flat = log-prior-flat :340-343; bounds = (prior-bounds-let ((k lo hi)...) bounds-total)
  * :346-369 with constant bounds (idx<0 means the key is absent: getf default 0d0); sexpr = any
  * (lambda (params data) ...) body, prior-bounds-let included. */
@@ -127,7 +137,8 @@ int mfit_prior_bounds(mfit_ctx* ctx, int d, int n, const int32_t* idx, const dou
 int mfit_prior_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* const* key_names, int n_keys);
 
 /* s-expression -> CUDA C lowering, exposed so it can be inspected and tested without a GPU.
- * kind 0 = model lambda, 1 = prior lambda.  Returns bytes needed (incl. NUL) or a negative status. */
+ * kind 0 = model lambda, 1 = prior lambda, 2 = per-point likelihood lambda (key_names unused).
+ * Returns bytes needed (incl. NUL) or a negative status. */
 int mfit_lower_sexpr(const char* lambda_text, const char* const* key_names, int n_keys, int kind,
                      char* out, int out_len, char* err, int err_len);
 

@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("MFIT_LIB") or os.path.join(_HERE, "libmfit_cuda.so") 
 
 OK, ERR_ARG, ERR_CUDA, ERR_SEXPR, ERR_NVRTC, ERR_STATE, ERR_STREAM, ERR_NCCL, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6, -7, -8
 FAM_POLY, FAM_EXPO, FAM_SINUS, FAM_LORENTZ, FAM_GAUSS_LIN, FAM_NV_MULTI, FAM_SEXPR = 0, 1, 2, 3, 4, 5, 100
-LL_NORMAL, LL_NORMAL_CUTOFF, LL_POISSON = 0, 1, 2
+LL_NORMAL, LL_NORMAL_CUTOFF, LL_POISSON, LL_USER = 0, 1, 2, 3
 AUTO_NONE, AUTO_PROB_SETTLE = 0, 1
 OPT_COVARIANCE, OPT_BEST_VALUE = 0, 1
 FIT_MOST_LIKELY, FIT_MEDIAN = 0, 1
@@ -49,6 +49,7 @@ SIGNATURES = {
     "mfit_model_builtin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_int]),
     "mfit_model_sexpr": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, _cpp, C.c_int]),
     "mfit_likelihood_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mfit_likelihood_sexpr": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
     "mfit_prior_flat": (C.c_int, [C.c_void_p, C.c_int]),
     "mfit_prior_bounds": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _ip, _dp, _dp]),
     "mfit_prior_sexpr": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, _cpp, C.c_int]),

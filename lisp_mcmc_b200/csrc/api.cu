@@ -69,6 +69,14 @@ struct Dataset {
   int nb = 0;
   int* b_idx = nullptr;
   double *b_lo = nullptr, *b_hi = nullptr;
+  // :log-liklihood given as a per-point lambda (mfit_likelihood_sexpr): compiled with the model when first needed
+  std::string ll_text, model_code;     // the lambda; the lowered MfitUser struct of a user :function
+  cudaLibrary_t lib_term = nullptr;
+  cudaKernel_t k_term = nullptr;
+  int term_narr = 2;                   // arrays the term reads per point: 2 (x, y) or 4 (+ the log-factorial table in the c slot)
+  double* lf = nullptr;                // [n_pad] log y_i! (single-float accumulation) for such a term
+  double err_head[16];                 // first elements of the stddev list ((elt error k) in the lambda)
+  int n_err_head = 0;
   cudaLibrary_t lib_model = nullptr, lib_prior = nullptr;
   cudaKernel_t k_user[3] = {nullptr, nullptr, nullptr};
   cudaKernel_t k_user_fit = nullptr;
@@ -216,7 +224,9 @@ long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
 void free_dev(void* p) { if (p) cudaFree(p); }
 
+void dataset_free_term(Dataset& d);
 void dataset_free_data(Dataset& d) {
+  dataset_free_term(d);
   free_dev(d.x);  // x, y, yw, w, c are one allocation (mfit_dataset_upload_xd)
   free_dev(d.cst_normal_pc); free_dev(d.cst_poisson_pc);
   d.x = d.y = d.yw = d.w = d.c = nullptr;
@@ -231,7 +241,15 @@ void dataset_free_prior(Dataset& d) {
   d.nb = 0;
   if (d.lib_prior) { cudaLibraryUnload(d.lib_prior); d.lib_prior = nullptr; d.k_prior = nullptr; }
 }
+void dataset_free_term(Dataset& d) {  // the compiled likelihood term depends on the model and on the data (error list, y table)
+  if (d.lib_term) { cudaLibraryUnload(d.lib_term); d.lib_term = nullptr; }
+  d.k_term = nullptr;
+  free_dev(d.lf);
+  d.lf = nullptr;
+}
 void dataset_free_model(Dataset& d) {
+  dataset_free_term(d);
+  d.model_code.clear();
   if (d.lib_model) { cudaLibraryUnload(d.lib_model); d.lib_model = nullptr; }
   d.k_user[0] = d.k_user[1] = d.k_user[2] = nullptr;
   for (auto& k : d.k_user_pc) k = nullptr;
@@ -390,6 +408,48 @@ int ensure_poisson_const(mfit_ctx* ctx, Dataset& s) {
   return 0;
 }
 
+// compile the data set's likelihood lambda together with its model (NVRTC) and build the log-factorial table if it reads one
+int ensure_user_term(mfit_ctx* ctx, Dataset& s, int d) {
+  CU(cudaSetDevice(ctx->device));
+  g_alloc_stream = ctx->stream;
+  std::string code, e;
+  int n_err = 0;
+  int rc = mfit_lower_to_string(s.ll_text.c_str(), nullptr, 0, 2, code, e, &n_err);
+  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  if (n_err > s.n_err_head)
+    return fail(ctx, MFIT_ERR_ARG, "dataset %d: the likelihood lambda reads element %d of an error list of %d", d, n_err - 1, s.n_err_head);
+  s.term_narr = code.find("NARR = 4") != std::string::npos ? 4 : 2;
+  const std::string type = s.family == MFIT_FAM_SEXPR ? std::string("MfitUser") : mfit_builtin_model_type(s.family, s.degree);
+  if (type.empty()) return fail(ctx, MFIT_ERR_STATE, "dataset %d has no model (:function)", d);
+  std::vector<char> cubin;
+  rc = mfit_nvrtc_compile(mfit_user_term_source(s.family == MFIT_FAM_SEXPR ? s.model_code : std::string(), type, code, s.err_head,
+                                                s.n_err_head), cubin, e);
+  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  dataset_free_term(s);
+  CU(cudaLibraryLoadData(&s.lib_term, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+  CU(cudaLibraryGetKernel(&s.k_term, s.lib_term, "mfit_user_eval_term"));
+  if (s.term_narr == 4) {  // log y_i! per point
+    if (!s.poisson_ok)
+      return fail(ctx, MFIT_ERR_ARG, "dataset %d: log-factorial / log-poisson need non-negative integer-valued y (:379-380)", d);
+    std::vector<float> memo;
+    log_factorial_ref((long long)s.ymax, memo);
+    std::vector<double> table(memo.begin(), memo.end());
+    if (table.empty()) table.push_back(0.0);
+    double* tab_dev = nullptr;
+    CU(cudaMalloc(&tab_dev, sizeof(double) * table.size()));
+    CU(cudaMalloc(&s.lf, sizeof(double) * (size_t)s.n_pad));
+    cudaError_t ce = cudaMemcpyAsync(tab_dev, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess) {
+      mfit_launch_logfact_fill(s.y, tab_dev, s.lf, s.n, s.n_pad, ctx->stream);
+      ctx->launches++;
+      ce = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(tab_dev);
+    if (ce != cudaSuccess) return fail(ctx, MFIT_ERR_CUDA, "log-factorial table: %s", cudaGetErrorString(ce));
+  }
+  return 0;
+}
+
 int check_problem_ready(mfit_ctx* ctx) {
   if (ctx->D <= 0) return fail(ctx, MFIT_ERR_STATE, "mfit_problem_define has not been called");
   for (int d = 0; d < ctx->D; d++) {
@@ -399,6 +459,13 @@ int check_problem_ready(mfit_ctx* ctx) {
     if (s.family < 0) return fail(ctx, MFIT_ERR_STATE, "dataset %d has no model (:function)", d);
     if (s.ll_kind == MFIT_LL_POISSON && !s.poisson_ok)
       return fail(ctx, MFIT_ERR_ARG, "dataset %d: log-poisson needs non-negative integer-valued y (log-factorial :379-380)", d);
+    if (s.ll_kind == MFIT_LL_USER) {
+      if (s.W_pc > 0) return fail(ctx, MFIT_ERR_ARG, "dataset %d: a likelihood lambda is not supported for walker sets with per-walker data", d);
+      if (!s.k_term) {
+        int rc = ensure_user_term(ctx, s, d);
+        if (rc) return rc;
+      }
+    }
     if (s.ll_kind == MFIT_LL_POISSON && !s.poisson_ready) {
       int rc = ensure_poisson_const(ctx, s);
       if (rc) return rc;
@@ -419,7 +486,8 @@ int check_problem_ready(mfit_ctx* ctx) {
 void fill_eval_args(MfitEvalArgs& a, const Dataset& s, const Workspace& w, int d, const double* theta, const unsigned char* skip,
                     int cb0, int n_cb) {
   memset(&a, 0, sizeof a);
-  a.x = s.x; a.y = s.y; a.yw = s.yw; a.w = s.w; a.c = s.c;
+  a.x = s.x; a.y = s.y; a.yw = s.yw; a.w = s.w;
+  a.c = s.ll_kind == MFIT_LL_USER ? s.lf : s.c;   // a user term reads the log-factorial table in that slot
   a.n = s.n;
   a.xd_stride = s.n_pad;
   a.xmin = s.xmin;
@@ -503,6 +571,7 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
 }
 
 const void* shared_data_kernel(const Dataset& s) {
+  if (s.ll_kind == MFIT_LL_USER) return (const void*)s.k_term;
   return s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user[s.ll_kind] : mfit_builtin_eval_kernel(s.family, s.degree, s.ll_kind);
 }
 
@@ -530,7 +599,7 @@ int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, c
   const void* fn = shared_data_kernel(s);
   if (!fn) return fail(ctx, MFIT_ERR_STATE, "no kernel for dataset %d (family %d degree %d)", ds[0], s.family, s.degree);
   std::unique_lock<std::mutex> shared_lock(ctx->shared->mu, std::defer_lock);
-  const bool user_k = s.family == MFIT_FAM_SEXPR;
+  const bool user_k = s.family == MFIT_FAM_SEXPR || s.ll_kind == MFIT_LL_USER;
   if (!user_k) shared_lock.lock();
   std::map<const void*, EvalShape>& shapes = user_k ? ctx->shape : ctx->shared->shape;
   auto it = shapes.find(fn);
@@ -545,6 +614,8 @@ int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, c
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     const long long room = (long long)max_optin - (long long)fa.sharedSizeBytes;
     const int xd = s.model_xdims > 0 ? s.model_xdims : 1;
+    // arrays per stage as mfit_eval_smem_bytes counts them by likelihood kind: a user term reads 2 (like poisson) or 4 (like cutoff)
+    const int ll_smem = s.ll_kind == MFIT_LL_USER ? (s.term_narr == 4 ? MFIT_LL_NORMAL_CUTOFF : MFIT_LL_POISSON) : s.ll_kind;
     EvalShape sh;
     sh.warps = 0;
     int max_warps = MFIT_WARPS;
@@ -559,12 +630,12 @@ int launch_eval_fused(mfit_ctx* ctx, const int* ds, int n, const Workspace& w, c
     const long long fit = per_cta < room ? per_cta : room;
     for (int w = max_warps; w >= 1 && sh.warps == 0; w = w > 4 ? w - 4 : w - 1)
       for (int st = want_stages; st >= 2 && sh.warps == 0; st--)
-        if ((long long)mfit_eval_smem_bytes(s.ll_kind, xd, w, st) <= fit) { sh.warps = w; sh.stages = st; }
+        if ((long long)mfit_eval_smem_bytes(ll_smem, xd, w, st) <= fit) { sh.warps = w; sh.stages = st; }
     if (sh.warps == 0)  // fewer CTAs per SM rather than none
       for (int w = max_warps; w >= 1 && sh.warps == 0; w--)
-        if ((long long)mfit_eval_smem_bytes(s.ll_kind, xd, w, 2) <= room) { sh.warps = w; sh.stages = 2; }
+        if ((long long)mfit_eval_smem_bytes(ll_smem, xd, w, 2) <= room) { sh.warps = w; sh.stages = 2; }
     if (sh.warps == 0) return fail(ctx, MFIT_ERR_ARG, "dataset %d: a tile of its %d arrays does not fit in shared memory", ds[0], xd + 3);
-    sh.smem = mfit_eval_smem_bytes(s.ll_kind, xd, sh.warps, sh.stages);
+    sh.smem = mfit_eval_smem_bytes(ll_smem, xd, sh.warps, sh.stages);
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
@@ -1195,6 +1266,8 @@ int mfit_dataset_upload_xd(mfit_ctx* ctx, int d, const double* x, int x_dims, co
   s.poisson_ok = pois_ok;
   s.poisson_ready = false;   // -sum log y_i! is formed when a log-poisson likelihood first needs it (ensure_poisson_const)
   s.ymax = ymax;
+  s.n_err_head = (int)std::min<int64_t>(n, 16);
+  for (int k = 0; k < s.n_err_head; k++) s.err_head[k] = sigma ? sigma[k] : 1.0;
   if (ctx->have_chains) chains_free(ctx);  // segment geometry changed: chains must be re-initialised
   return 0;
 }
@@ -1303,6 +1376,7 @@ int mfit_model_sexpr(mfit_ctx* ctx, int d, const char* lambda_text, const char* 
   s.family = MFIT_FAM_SEXPR;
   s.degree = 0;
   s.model_xdims = model_xdims;
+  s.model_code = code;
   return 0;
 }
 
@@ -1310,7 +1384,25 @@ int mfit_likelihood_set(mfit_ctx* ctx, int d, int kind) {
   NEED_DS(d);
   if (kind < 0 || kind > 2) return fail(ctx, MFIT_ERR_ARG, "unknown likelihood kind %d", kind);
   if (ctx->ds[d].ll_kind != kind && ctx->have_chains) chains_free(ctx);
+  if (ctx->ds[d].ll_kind == MFIT_LL_USER) { CU(cudaSetDevice(ctx->device)); dataset_free_term(ctx->ds[d]); }
   ctx->ds[d].ll_kind = kind;
+  return 0;
+}
+
+int mfit_likelihood_sexpr(mfit_ctx* ctx, int d, const char* lambda_text) {
+  NEED_DS(d);
+  if (!lambda_text) return fail(ctx, MFIT_ERR_ARG, "need the lambda text");
+  const int canon = mfit_ll_canonical_kind(lambda_text);
+  if (canon >= 0) return mfit_likelihood_set(ctx, d, canon);
+  std::string code, e;
+  int rc = mfit_lower_to_string(lambda_text, nullptr, 0, 2, code, e);   // syntax errors now, compilation when the model is known
+  if (rc) return fail(ctx, rc, "%s", e.c_str());
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  if (ctx->have_chains) chains_free(ctx);
+  Dataset& s = ctx->ds[d];
+  dataset_free_term(s);
+  s.ll_text = lambda_text;
+  s.ll_kind = MFIT_LL_USER;
   return 0;
 }
 

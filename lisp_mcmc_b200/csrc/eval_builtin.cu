@@ -37,6 +37,18 @@ const void* mfit_builtin_eval_kernel(int family, int degree, int ll) {
   return nullptr;
 }
 
+std::string mfit_builtin_model_type(int family, int degree) {
+  switch (family) {
+    case MFIT_FAM_POLY: return (degree >= 0 && degree <= 7) ? "MfitPoly<" + std::to_string(degree) + ">" : "";
+    case MFIT_FAM_EXPO: return "MfitExpo";
+    case MFIT_FAM_SINUS: return "MfitSinus";
+    case MFIT_FAM_LORENTZ: return "MfitLorentz";
+    case MFIT_FAM_GAUSS_LIN: return "MfitGaussLin";
+    case MFIT_FAM_NV_MULTI: return (degree >= 1 && degree <= 4) ? "MfitNvMulti<" + std::to_string(degree) + ">" : "";
+  }
+  return "";
+}
+
 int mfit_family_nparams(int family, int degree) {
   switch (family) {
     case MFIT_FAM_POLY: return degree + 1;

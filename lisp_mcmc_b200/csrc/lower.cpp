@@ -271,6 +271,11 @@ struct Lower {
   std::string x_name;      // the model's positional argument
   int x_dims = 0;          // > 0: x is a sequence and components 0 .. x_dims - 1 are read (elt / aref / nth / first ...)
   bool x_scalar = false;   // x is used as a number
+  // likelihood lambdas (kind 2): (lambda (y model error) ...) of create-log-liklihood-function :402-417
+  bool is_ll = false;
+  std::string y_name, err_name;
+  bool uses_logfact = false;   // (log-factorial y) / (log-poisson . y): the per-point table value `lf`
+  int err_max = -1;            // highest index of the stddev list read
 
   std::string fresh(const char* stem) { return std::string(stem) + std::to_string(tmp++); }
 
@@ -650,7 +655,22 @@ struct Lower {
         if (f == a.name) {
           const bool fixed = a.fixed >= 0;
           need(fixed ? 1 : 2, fixed ? 1 : 2);
-          if (!is_x(s.kids[a.fixed == -2 ? 2 : 1])) throw Err(f + ": only the model's positional argument can be indexed");
+          const Sx& seq = s.kids[a.fixed == -2 ? 2 : 1];
+          if (is_ll) {
+            // `error` is the data set's whole stddev LIST (:416), the lambda has no index of the point it is called for:
+            // only a literal position can be read -- a per-data-set constant, spliced into the kernel as MFIT_ERR(k)
+            if (seq.t != Sx::SYM || seq.sym != err_name) throw Err(f + ": only the error list can be indexed in a likelihood lambda");
+            i64 idx = a.fixed;
+            if (!fixed) {
+              const Sx& ix = s.kids[a.fixed == -2 ? 1 : 2];
+              if (ix.t != Sx::NUM || ix.nk != 0 || ix.den != 1 || ix.num < 0) throw Err(f + ": the index must be a literal non-negative integer");
+              idx = ix.num;
+            }
+            if (idx >= 16) throw Err(f + ": only the first 16 elements of the error list can be read");
+            if ((int)idx > err_max) err_max = (int)idx;
+            return mk(T_DBL, "MFIT_ERR(" + std::to_string(idx) + ")");
+          }
+          if (!is_x(seq)) throw Err(f + ": only the model's positional argument can be indexed");
           i64 idx = a.fixed;
           if (!fixed) {
             const Sx& ix = s.kids[a.fixed == -2 ? 1 : 2];
@@ -662,6 +682,24 @@ struct Lower {
           if ((int)idx + 1 > x_dims) x_dims = (int)idx + 1;
           return mk(T_DBL, "xv[" + std::to_string(idx) + "]");
         }
+    }
+    if (f == "LOG-NORMAL") {  // :372-377
+      need(3, 3);
+      Ex a = lower(s.kids[1]), b = lower(s.kids[2]), c = lower(s.kids[3]);
+      if (a.ty == T_BOOL || b.ty == T_BOOL || c.ty == T_BOOL) throw Err("log-normal of a non-number (the error LIST itself is not a number: use (elt error k))");
+      return mk(T_DBL, "mfit_u_log_normal(" + as_code(a, T_DBL) + ", " + as_code(b, T_DBL) + ", " + as_code(c, T_DBL) + ")");
+    }
+    if (f == "LOG-FACTORIAL" || f == "LOG-POISSON") {  // :379-383; the factorial of the DATUM only (a table built at upload)
+      const bool pois = f == "LOG-POISSON";
+      need(pois ? 2 : 1, pois ? 2 : 1);
+      const Sx& k = s.kids[pois ? 2 : 1];
+      if (!is_ll || k.t != Sx::SYM || k.sym != y_name)
+        throw Err(f + ": the count must be the likelihood lambda's y (log-factorial of anything else is not supported)");
+      uses_logfact = true;
+      if (!pois) return mk(T_SGL, "((float)lf)");   // (log-factorial n) is a single-float
+      Ex lam = lower(s.kids[1]);
+      if (lam.ty == T_BOOL) throw Err("log-poisson of a non-number");
+      return mk(T_DBL, "mfit_u_log_poisson(" + as_code(lam, T_DBL) + ", y, lf)");
     }
     if (f == "DECLARE") return mk_bool(false);
     if (f == "PROGN") return body(s, 1);
@@ -902,6 +940,14 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
     xe.xk = 1;
     xe.A = "1.0";
     L.bind(positional[0], xe);
+  } else if (kind == 2) {
+    if (positional.size() != 3 || in_key) throw Err("a likelihood lambda takes (y model error)");
+    L.is_ll = true;
+    L.y_name = positional[0];
+    L.err_name = positional[2];
+    L.bind(positional[0], mk(T_DBL, "y"));
+    L.bind(positional[1], mk(T_DBL, "f"));
+    L.bind(positional[2], mk_bool(true));   // a list is no number: using it as one is a type error in the reference too
   } else {
     if (positional.size() != 2) throw Err("a prior lambda takes (params data)");
   }
@@ -924,7 +970,16 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
   }
   std::string stmts;
   for (auto& sline : pre) stmts += "    " + sline + "\n";
-  if (x_dims_out) *x_dims_out = kind == 0 ? L.x_dims : 0;
+  if (x_dims_out) *x_dims_out = kind == 0 ? L.x_dims : kind == 2 ? L.err_max + 1 : 0;
+  if (kind == 2) {
+    // the per-point term of create-log-liklihood-function (:410-417): acc + g(y, model, error), summed by the kernel in
+    // data order.  NARR = 4 when the log-factorial table of y is read (it travels in the slot of the cutoff constants).
+    out += "template <>\nstruct MfitTerm<MFITK_USER> {\n";
+    out += std::string("  static constexpr int NARR = ") + (L.uses_logfact ? "4" : "2") + ";\n  static constexpr int USES = 0;\n";
+    out += "  template <bool SLOW, class G>\n  __device__ __forceinline__ static double add(double acc, double f, double y, double, double lf, G&) {\n";
+    out += "    (void)f; (void)y; (void)lf;\n" + stmts + "    return acc + (" + ret + ");\n  }\n};\n";
+    return out;
+  }
   if (kind == 0) {
     // a user model carries no proof about its arguments (safe() is false): its fast routines always run guarded
     out += "struct MfitUser {\n  static constexpr int USES = " + std::to_string(L.uses) + ";\n";
@@ -983,7 +1038,7 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
 
 extern "C" int mfit_lower_sexpr(const char* lambda_text, const char* const* key_names, int n_keys, int kind, char* out,
                                 int out_len, char* err, int err_len) {
-  if (!lambda_text || n_keys < 0 || (n_keys > 0 && !key_names) || (kind != 0 && kind != 1)) {
+  if (!lambda_text || n_keys < 0 || (n_keys > 0 && !key_names) || kind < 0 || kind > 2) {
     if (err && err_len > 0) snprintf(err, err_len, "bad argument");
     return MFIT_ERR_ARG;
   }
@@ -997,6 +1052,31 @@ extern "C" int mfit_lower_sexpr(const char* lambda_text, const char* const* key_
     if (err && err_len > 0) snprintf(err, err_len, "%s", e.what());
     return MFIT_ERR_SEXPR;
   }
+}
+
+// (lambda (y model error) (log-poisson model y)) -- the way the reference spells a Poisson likelihood (:402-417 with
+// :382-383) -- is the built-in kind: same kernel, same hoisted constant, bit for bit.
+int mfit_ll_canonical_kind(const char* text) {
+  try {
+    Reader rd{text};
+    Sx top = rd.read();
+    if (top.t != Sx::LIST || top.kids.size() < 3 || top.kids[0].t != Sx::SYM || top.kids[0].sym != "LAMBDA") return -1;
+    const Sx& ll = top.kids[1];
+    if (ll.t != Sx::LIST || ll.kids.size() != 3) return -1;
+    for (auto& a : ll.kids) if (a.t != Sx::SYM || a.sym[0] == '&') return -1;
+    const Sx* body = nullptr;
+    for (size_t i = 2; i < top.kids.size(); i++) {
+      if (Lower::is_declare(top.kids[i])) continue;
+      if (body) return -1;
+      body = &top.kids[i];
+    }
+    if (!body || body->t != Sx::LIST || body->kids.size() != 3 || body->kids[0].t != Sx::SYM) return -1;
+    if (body->kids[0].sym == "LOG-POISSON" && body->kids[1].t == Sx::SYM && body->kids[1].sym == ll.kids[1].sym &&
+        body->kids[2].t == Sx::SYM && body->kids[2].sym == ll.kids[0].sym)
+      return MFIT_LL_POISSON;
+  } catch (...) {
+  }
+  return -1;
 }
 
 // C++ face used by api.cu

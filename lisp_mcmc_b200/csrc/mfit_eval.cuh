@@ -55,6 +55,7 @@
 #define MFITK_NORMAL 0
 #define MFITK_CUTOFF 1
 #define MFITK_POISSON 2
+#define MFITK_USER 3     /* a lowered (lambda (y model error) ...): MfitTerm<MFITK_USER> is generated text (csrc/lower.cpp kind 2) */
 
 struct MfitEvalArgs {
   const double* x;      /* [n_pad]; multi-dimensional inputs: component k at x + k * xd_stride */

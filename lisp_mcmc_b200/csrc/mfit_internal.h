@@ -31,6 +31,7 @@ const void* mfit_builtin_fit_kernel(int family, int degree);
 void mfit_launch_prepare(const double* x, const double* y, double* yw, double* w, double* c, long long n, long long n_pad,
                          long long rows, long long x_rows, long long sig_rows, int have_sigma, MfitPrepBlock* out, int blocks,
                          cudaStream_t st);
+void mfit_launch_logfact_fill(const double* y, const double* table, double* lf, long long n, long long n_pad, cudaStream_t st);
 void mfit_launch_poisson_const(const double* y, const double* table, long long n, long long n_pad, long long rows,
                                MfitPrepBlock* out, int blocks, cudaStream_t st);
 #endif
@@ -42,6 +43,13 @@ int mfit_lower_to_string(const char* text, const char* const* keys, int n_keys, 
 // nvrtc_glue.cpp
 std::string mfit_user_model_source(const std::string& model_struct);
 std::string mfit_user_prior_source(const std::string& prior_fn);
+std::string mfit_user_term_source(const std::string& model_struct, const std::string& model_type, const std::string& term_code,
+                                  const double* err_head, int n_err);
+// lower.cpp: MFIT_LL_* when the likelihood lambda is one of the built-in kinds spelled out, e.g.
+// (lambda (y model error) (log-poisson model y)); -1 otherwise
+int mfit_ll_canonical_kind(const char* text);
+// eval_builtin.cu: C++ type of a built-in family ("MfitGaussLin", "MfitPoly<3>" ...), empty if unknown
+std::string mfit_builtin_model_type(int family, int degree);
 int mfit_nvrtc_compile(const std::string& src, std::vector<char>& cubin, std::string& err);
 
 // nccl_glue.cpp (libnccl is dlopen'ed on first use)

@@ -144,7 +144,17 @@ k_poisson_const(const double* y, const double* table, long long n, long long n_p
   }
 }
 
+// log y_i! per point from the host-built table (a likelihood lambda that calls log-factorial / log-poisson)
+__global__ void k_logfact_fill(const double* y, const double* table, double* lf, long long n, long long n_pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) lf[i] = i < n ? table[(long long)y[i]] : 0.0;
+}
+
 }  // namespace
+
+void mfit_launch_logfact_fill(const double* y, const double* table, double* lf, long long n, long long n_pad, cudaStream_t st) {
+  k_logfact_fill<<<(unsigned)((n_pad + 255) / 256), 256, 0, st>>>(y, table, lf, n, n_pad);
+}
 
 void mfit_launch_prepare(const double* x, const double* y, double* yw, double* w, double* c, long long n, long long n_pad,
                          long long rows, long long x_rows, long long sig_rows, int have_sigma, MfitPrepBlock* out, int blocks,

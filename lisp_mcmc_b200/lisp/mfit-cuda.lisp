@@ -10,6 +10,8 @@
 ;;;;                                                                               ; lowered to CUDA C -> NVRTC -> sm_100a
 ;;;;                   (gpu-builtin :gauss-lin '(:a :mu :s :b0 :b1))               ; hand-written FP64 family
 ;;;;   :log-liklihood  :log-liklihood-normal | :log-liklihood-normal-cutoff | :log-poisson
+;;;;                   | (create-log-liklihood-function (gpu-lambda (y model error) (log-poisson model y)))  ; :402-417, any
+;;;;                                                        ; per-point lambda; ERROR is the whole stddev list as in :416
 ;;;;   :log-prior      :log-prior-flat | ((:key lo hi) ...)  ; = (prior-bounds-let (...) bounds-total)
 ;;;;                   | (gpu-lambda (params data) (prior-bounds-let (...) (+ bounds-total ...)))
 ;;;;
@@ -26,7 +28,7 @@
 
 (defpackage :mfit-cuda
   (:use :cl)
-  (:export #:gpu-lambda #:gpu-builtin #:gpu-walker #:walker-create #:walker-adaptive-steps
+  (:export #:gpu-lambda #:gpu-builtin #:gpu-walker #:create-log-liklihood-function #:walker-create #:walker-adaptive-steps
            #:walker-adaptive-steps-full #:walker-many-steps #:walker-sample-region #:walker-force-take-step
            #:walker-get #:walker-get-data-and-fit #:walker-save #:walker-load #:walker-modify #:walker-set-get #:walker-free #:mcmc-fit #:mfit-walker-estop #:lower-to-cuda #:walker-set-create))
 (in-package :mfit-cuda)
@@ -59,6 +61,7 @@
 (cffi:defcfun ("mfit_model_sexpr" %model-sexpr) :int
   (ctx :pointer) (d :int) (lambda-text :string) (key-names :pointer) (n-keys :int))
 (cffi:defcfun ("mfit_likelihood_set" %likelihood-set) :int (ctx :pointer) (d :int) (kind :int))
+(cffi:defcfun ("mfit_likelihood_sexpr" %likelihood-sexpr) :int (ctx :pointer) (d :int) (lambda-text :string))
 (cffi:defcfun ("mfit_prior_flat" %prior-flat) :int (ctx :pointer) (d :int))
 (cffi:defcfun ("mfit_prior_bounds" %prior-bounds) :int
   (ctx :pointer) (d :int) (n :int) (idx :pointer) (lo :pointer) (hi :pointer))
@@ -215,6 +218,19 @@ translates it to CUDA C and NVRTC compiles it for sm_100a; it never runs in Lisp
   (ecase (or x :log-liklihood-normal)
     (:log-liklihood-normal 0) (:log-liklihood-normal-cutoff 1) (:log-poisson 2)))
 
+(defun create-log-liklihood-function (log-liklihood-function)
+  "create-log-liklihood-function :402-417 for the GPU path: LOG-LIKLIHOOD-FUNCTION is a per-point
+(gpu-lambda (y model error) ...); the result goes into :log-liklihood.  The lambda is lowered to CUDA C and compiled into
+the likelihood kernel together with the data set's :function; as in the reference (:416) ERROR is the data set's whole
+stddev list -- read it with (elt error k), k a literal."
+  (check-type log-liklihood-function gpu-fn)
+  log-liklihood-function)
+
+(defun set-likelihood (ctx d ll)
+  (if (gpu-fn-p ll)
+      (chk ctx (%likelihood-sexpr ctx d (gpu-fn-text ll)))
+      (chk ctx (%likelihood-set ctx d (likelihood-kind ll)))))
+
 (defun set-function (ctx d f keys)
   (etypecase f
     (gpu-family
@@ -271,7 +287,7 @@ lists in :params order) gives each chain its own start; SEED keys the Philox str
                            (%dataset-upload-xd ctx d x x-dims y s (length (second set)))
                            (%dataset-upload ctx d x y s (length (second set)))))))))
       (set-function ctx d f keys)
-      (chk ctx (%likelihood-set ctx d (likelihood-kind (nth d ll))))
+      (set-likelihood ctx d (nth d ll))
       (set-prior ctx d (nth d lp) keys))
     (with-doubles (t0 (apply #'append theta0))               ; W x P row-major
       (chk ctx (%chains-init ctx t0 w seed 0 trace-capacity)))

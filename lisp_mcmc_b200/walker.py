@@ -13,6 +13,7 @@ exactly one reference walker.
 Plugin slot values are descriptors instead of closures (nothing calls back into the host):
   :function       `builtin("gauss_lin", keys)` | Lisp lambda text (lowered to CUDA C, compiled by NVRTC)
   :log-liklihood  "log-liklihood-normal" | "log-liklihood-normal-cutoff" | "log-poisson"
+                  | create_log_liklihood_function("(lambda (y model error) ...)") -- any per-point Lisp lambda (lowered, NVRTC)
   :log-prior      "log-prior-flat" | [(key, lo, hi), ...] (prior-bounds-let with body bounds-total)
                   | Lisp lambda text `(lambda (params data) ...)`
 """
@@ -161,6 +162,22 @@ def plist(params):
     return keys, np.array([float(v) for _, v in items], dtype=np.float64)
 
 
+def create_log_liklihood_function(log_liklihood_function):
+    """create-log-liklihood-function :402-417: wraps a per-point (lambda (y model error) ...) into a data-set likelihood.
+    Here the lambda is Lisp text and so is the result (a "(create-log-liklihood-function <lambda>)" wrapper is unwrapped):
+    pass it as :log-liklihood.  `error` is the data set's whole stddev list, as in the reference (:416)."""
+    t = log_liklihood_function.strip()
+    low = t.lower()
+    if low.startswith("(create-log-liklihood-function"):
+        t = t[len("(create-log-liklihood-function"):].rstrip()
+        if not t.endswith(")"):
+            raise ValueError("unbalanced create-log-liklihood-function form")
+        t = t[:-1].strip()
+    if not t.lower().startswith("(lambda"):
+        raise ValueError("create-log-liklihood-function takes a (lambda (y model error) ...)")
+    return t
+
+
 # ------------------------------------------------------------------ sharding plans (one process per GPU)
 def shard_chains(W, rank, world):
     """Contiguous, balanced partition of W chains over `world` ranks -> (first global chain id, count)."""
@@ -243,10 +260,15 @@ class Walker:
                 else:
                     self._chk(L.mfit_dataset_upload(h, d, _ptr(x), _ptr(y), _ptr(e), len(x)))
             self._set_function(d, self.function[d])
-            kind = _LL.get(self.log_liklihood[d])
-            if kind is None:
-                raise ValueError("unknown :log-liklihood %r" % (self.log_liklihood[d],))
-            self._chk(L.mfit_likelihood_set(h, d, kind))
+            ll_d = self.log_liklihood[d]
+            if isinstance(ll_d, str) and ll_d.lstrip().startswith("("):
+                # (create-log-liklihood-function (lambda (y model error) ...)) :402-417: the per-point lambda as text
+                self._chk(L.mfit_likelihood_sexpr(h, d, create_log_liklihood_function(ll_d).encode()))
+            else:
+                kind = _LL.get(ll_d)
+                if kind is None:
+                    raise ValueError("unknown :log-liklihood %r" % (ll_d,))
+                self._chk(L.mfit_likelihood_set(h, d, kind))
             self._set_prior(d, self.log_prior[d])
 
         if theta0 is None:

@@ -26,7 +26,7 @@ extern "C" {
 /* model families (defined by this build); ids shared with include/mfit_cuda.h */
 enum { ORC_FAM_POLY = 0, ORC_FAM_EXPO = 1, ORC_FAM_SINUS = 2, ORC_FAM_LORENTZ = 3,
        ORC_FAM_GAUSS_LIN = 4, ORC_FAM_NV_MULTI = 5, ORC_FAM_SEXPR = 100 };
-enum { ORC_LL_NORMAL = 0, ORC_LL_NORMAL_CUTOFF = 1, ORC_LL_POISSON = 2 };
+enum { ORC_LL_NORMAL = 0, ORC_LL_NORMAL_CUTOFF = 1, ORC_LL_POISSON = 2, ORC_LL_USER = 3 };
 enum { ORC_AUTO_NONE = 0, ORC_AUTO_PROB_SETTLE = 1 };
 enum { ORC_OPT_COVARIANCE = 0, ORC_OPT_BEST_VALUE = 1 };
 enum { ORC_SUM_REFERENCE = 0, ORC_SUM_COMPENSATED = 1 };
@@ -70,6 +70,9 @@ int orc_walker_dataset_xd(orc_walker* w, int d, const double* x, int xd, const d
 int orc_walker_model_builtin(orc_walker* w, int d, int family, int degree, const int* idx, int n_idx);
 int orc_walker_model_sexpr(orc_walker* w, int d, const char* text, const char* const* keys);
 int orc_walker_likelihood(orc_walker* w, int d, int kind);
+/* :log-liklihood = (create-log-liklihood-function (lambda (y model error) ...)), mcmc-fitting.lisp:402-417; `error` is the
+ * data set's whole stddev list (:416): (elt error k) and friends with a literal index */
+int orc_walker_likelihood_sexpr(orc_walker* w, int d, const char* text);
 int orc_walker_prior_flat(orc_walker* w, int d);
 int orc_walker_prior_bounds(orc_walker* w, int d, int n, const int* idx, const double* lo, const double* hi);
 int orc_walker_prior_sexpr(orc_walker* w, int d, const char* text, const char* const* keys);

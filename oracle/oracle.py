@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 FAM_POLY, FAM_EXPO, FAM_SINUS, FAM_LORENTZ, FAM_GAUSS_LIN, FAM_NV_MULTI, FAM_SEXPR = 0, 1, 2, 3, 4, 5, 100
-LL_NORMAL, LL_NORMAL_CUTOFF, LL_POISSON = 0, 1, 2
+LL_NORMAL, LL_NORMAL_CUTOFF, LL_POISSON, LL_USER = 0, 1, 2, 3
 AUTO_NONE, AUTO_PROB_SETTLE = 0, 1
 OPT_COVARIANCE, OPT_BEST_VALUE = 0, 1
 SUM_REFERENCE, SUM_COMPENSATED = 0, 1
@@ -85,6 +85,7 @@ def lib():
         L.orc_walker_model_builtin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_int]
         L.orc_walker_model_sexpr.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_char_p)]
         L.orc_walker_likelihood.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_walker_likelihood_sexpr.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         L.orc_walker_prior_flat.argtypes = [C.c_void_p, C.c_int]
         L.orc_walker_prior_bounds.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _dp, _dp]
         L.orc_walker_prior_sexpr.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_char_p)]
@@ -270,6 +271,10 @@ class Walker:
 
     def likelihood(self, d, kind):
         self._chk(lib().orc_walker_likelihood(self.h, d, kind))
+
+    def likelihood_sexpr(self, d, text):
+        """:log-liklihood = (create-log-liklihood-function <text>), text = "(lambda (y model error) ...)" (:402-417)"""
+        self._chk(lib().orc_walker_likelihood_sexpr(self.h, d, text.encode()))
 
     def prior_flat(self, d):
         self._chk(lib().orc_walker_prior_flat(self.h, d))

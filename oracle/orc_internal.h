@@ -26,6 +26,7 @@ Fn* fn_parse(const char* text, const std::vector<std::string>& keys);
 double fn_call_model(Fn* f, double x, const double* theta);
 double fn_call_model_v(Fn* f, const double* x, int xdim, const double* theta);
 double fn_call_prior(Fn* f, const double* theta);
+double fn_call_ll(Fn* f, double y, double model, const double* err, int n_err);
 void fn_free(Fn* f);
 
 }  // namespace orc

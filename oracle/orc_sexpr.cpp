@@ -19,6 +19,10 @@
 #include <memory>
 #include <stdexcept>
 
+extern "C" double orc_log_normal(double x, double mu, double sigma);
+extern "C" double orc_log_factorial(double n);
+extern "C" double orc_log_poisson(double lambda, double k);
+
 namespace orc {
 
 // ---------------------------------------------------------------- reader
@@ -243,7 +247,8 @@ static Val irrational(fn1 f, const Val& a) {
 enum Op {
   O_CONST, O_VAR, O_ADD, O_SUB, O_MUL, O_DIV, O_INC, O_DEC, O_EXP, O_LOG, O_SIN, O_COS, O_TAN, O_ASIN,
   O_ACOS, O_ATAN, O_SINH, O_COSH, O_TANH, O_SQRT, O_EXPT, O_ABS, O_MIN, O_MAX, O_SIGNUM, O_IF, O_AND,
-  O_OR, O_NOT, O_LT, O_GT, O_LE, O_GE, O_EQ, O_NE, O_LET, O_PROGN, O_FLOAT, O_XELT
+  O_OR, O_NOT, O_LT, O_GT, O_LE, O_GE, O_EQ, O_NE, O_LET, O_PROGN, O_FLOAT, O_XELT,
+  O_LOGNORMAL, O_LOGPOISSON, O_LOGFACT   // the reference's own per-point densities, callable from a likelihood lambda (:372-383)
 };
 
 struct Node {
@@ -260,6 +265,8 @@ struct Fn {
   int nslots = 0;
   int P = 0;
   bool is_prior = false;
+  bool is_ll = false;              // (lambda (y model error) ...) of create-log-liklihood-function :402-417
+  int y_slot = -1, model_slot = -1; // its first two arguments; the third (the whole stddev LIST, :416) is the sequence x_slot
   int x_slot = -1;
   std::vector<int> theta_slot;     // per theta index -> slot (or -1)
   std::vector<std::pair<int, Val>> defaults;  // slot, default for keys not in the plist
@@ -403,7 +410,7 @@ struct Compiler {
         {"TANH", O_TANH}, {"SQRT", O_SQRT}, {"EXPT", O_EXPT}, {"ABS", O_ABS}, {"MIN", O_MIN},
         {"MAX", O_MAX}, {"SIGNUM", O_SIGNUM}, {"AND", O_AND}, {"OR", O_OR}, {"NOT", O_NOT},
         {"<", O_LT}, {">", O_GT}, {"<=", O_LE}, {">=", O_GE}, {"=", O_EQ}, {"/=", O_NE},
-        {"FLOAT", O_FLOAT}};
+        {"FLOAT", O_FLOAT}, {"LOG-NORMAL", O_LOGNORMAL}, {"LOG-POISSON", O_LOGPOISSON}, {"LOG-FACTORIAL", O_LOGFACT}};
     for (auto& e : table)
       if (f == e.name) return call(e.op, args());
     throw std::runtime_error("unsupported operator " + f);
@@ -553,6 +560,24 @@ static Val eval(const Node& n, Val* env) {
       if (a.k == Val::SGL) return Val::sgl(c == 0 ? a.f : (float)c);
       return Val::dbl(c == 0 ? a.d : (double)c);
     }
+    case O_LOGNORMAL: {  // (log-normal x mu sigma) :372-377
+      if (n.kids.size() != 3) throw std::runtime_error("log-normal takes (x mu sigma)");
+      const Val a = eval(n.kids[0], env), b = eval(n.kids[1], env), c = eval(n.kids[2], env);
+      if (a.k == Val::BOOL || b.k == Val::BOOL || c.k == Val::BOOL) throw std::runtime_error("log-normal of a non-number");
+      return Val::dbl(orc_log_normal(a.as_double(), b.as_double(), c.as_double()));
+    }
+    case O_LOGPOISSON: {  // (log-poisson lambda k) :382-383
+      if (n.kids.size() != 2) throw std::runtime_error("log-poisson takes (lambda k)");
+      const Val a = eval(n.kids[0], env), b = eval(n.kids[1], env);
+      if (a.k == Val::BOOL || b.k == Val::BOOL) throw std::runtime_error("log-poisson of a non-number");
+      return Val::dbl(orc_log_poisson(a.as_double(), b.as_double()));
+    }
+    case O_LOGFACT: {  // (log-factorial n) :379-380: a single-float
+      if (n.kids.size() != 1) throw std::runtime_error("log-factorial takes (n)");
+      const Val a = eval(n.kids[0], env);
+      if (a.k == Val::BOOL) throw std::runtime_error("log-factorial of a non-number");
+      return Val::sgl((float)orc_log_factorial(a.as_double()));
+    }
     case O_FLOAT: {
       Val a = eval(n.kids.at(0), env);
       if (n.kids.size() == 2) {
@@ -653,7 +678,12 @@ Fn* fn_parse(const char* text, const std::vector<std::string>& keys_in) {
     }
   }
   fn->is_prior = !seen_key_marker && positional.size() == 2;
-  if (!fn->is_prior) {
+  fn->is_ll = !seen_key_marker && positional.size() == 3;
+  if (fn->is_ll) {
+    fn->y_slot = c.new_slot(positional[0]);
+    fn->model_slot = c.new_slot(positional[1]);
+    fn->x_slot = c.new_slot(positional[2]);   // `error` is a sequence: (elt error k) etc. go through the same accessors as a sequence x
+  } else if (!fn->is_prior) {
     if (positional.size() != 1) throw std::runtime_error("model lambda must take exactly one positional argument");
     fn->x_slot = c.new_slot(positional[0]);
   }
@@ -692,6 +722,24 @@ double fn_call_model_v(Fn* f, const double* x, int xdim, const double* theta) {
   return run(f, std::numeric_limits<double>::quiet_NaN(), theta, true);
 }
 double fn_call_prior(Fn* f, const double* theta) { return run(f, 0.0, theta); }
+// (funcall ll-fn y (apply fn x params) stddev) :416 -- stddev is the data set's whole error list
+double fn_call_ll(Fn* f, double y, double model, const double* err, int n_err) {
+  if (!f->is_ll) throw std::runtime_error("not a (lambda (y model error) ...)");
+  struct Bind {
+    Bind(const double* x, int d) { t_xvec = x; t_xdim = d; }
+    ~Bind() { t_xvec = nullptr; t_xdim = 0; }
+  } bind(err, n_err);
+  Val envbuf[256];
+  std::vector<Val> big;
+  Val* env = envbuf;
+  if (f->nslots > 256) { big.resize(f->nslots); env = big.data(); }
+  env[f->y_slot] = Val::dbl(y);
+  env[f->model_slot] = Val::dbl(model);
+  env[f->x_slot] = Val::boolean(true);  // a list is no number
+  Val v = eval(f->body, env);
+  if (v.k == Val::BOOL) throw std::runtime_error("likelihood lambda returned a non-number");
+  return v.as_double();
+}
 void fn_free(Fn* f) { delete f; }
 
 }  // namespace orc

@@ -168,6 +168,7 @@ struct Dataset {
   std::vector<int> idx;
   orc::Fn* fn = nullptr;        // model s-expression
   int ll_kind = ORC_LL_NORMAL;
+  orc::Fn* ll_fn = nullptr;     // ORC_LL_USER: the per-point (lambda (y model error) ...) of create-log-liklihood-function
   int prior_kind = 0;           // 0 flat, 1 bounds, 2 s-expression
   std::vector<int> b_idx;
   std::vector<double> b_lo, b_hi;
@@ -192,7 +193,7 @@ struct orc_walker {
   std::mt19937_64 rng{12345};
   std::vector<std::vector<std::string>> keep_keys;
   ~orc_walker() {
-    for (auto& d : ds) { if (d.fn) orc::fn_free(d.fn); if (d.prior_fn) orc::fn_free(d.prior_fn); }
+    for (auto& d : ds) { if (d.fn) orc::fn_free(d.fn); if (d.prior_fn) orc::fn_free(d.prior_fn); if (d.ll_fn) orc::fn_free(d.ll_fn); }
   }
 };
 
@@ -237,6 +238,7 @@ double dataset_ll(const Dataset& d, const double* theta, int mode) {
         t = (v > -5000.0) ? v : (v != v ? v : -5000.0);  // (max -5000d0 v)
         break;
       }
+      case ORC_LL_USER: t = orc::fn_call_ll(d.ll_fn, d.y[i], f, d.sigma.data(), (int)d.sigma.size()); break;  // :416
       default: t = orc_log_poisson(f, d.y[i]); break;
     }
     sum.add(t);
@@ -511,6 +513,20 @@ int orc_walker_likelihood(orc_walker* w, int d, int kind) {
   if (d < 0 || d >= w->D) return -1;
   w->ds[d].ll_kind = kind;
   return 0;
+}
+// :log-liklihood = (create-log-liklihood-function (lambda (y model error) ...)) :402-417
+int orc_walker_likelihood_sexpr(orc_walker* w, int d, const char* text) {
+  if (d < 0 || d >= w->D) return -1;
+  try {
+    orc::Fn* f = orc::fn_parse(text, std::vector<std::string>());
+    if (w->ds[d].ll_fn) orc::fn_free(w->ds[d].ll_fn);
+    w->ds[d].ll_fn = f;
+    w->ds[d].ll_kind = ORC_LL_USER;
+    return 0;
+  } catch (std::exception& e) {
+    w->err = e.what();
+    return -2;
+  }
 }
 int orc_walker_prior_flat(orc_walker* w, int d) { w->ds[d].prior_kind = 0; return 0; }
 int orc_walker_prior_bounds(orc_walker* w, int d, int n, const int* idx, const double* lo, const double* hi) {

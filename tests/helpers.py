@@ -31,7 +31,10 @@ def oracle_walker(orc, cfg, use_builtin_formula=False):
                 ow.model_sexpr(d, f.lisp_text())
         else:
             ow.model_sexpr(d, f)
-        ow.likelihood(d, _LL[lls[d]])
+        if isinstance(lls[d], str) and lls[d].lstrip().startswith("("):
+            ow.likelihood_sexpr(d, lls[d])      # (create-log-liklihood-function (lambda (y model error) ...)) :402-417
+        else:
+            ow.likelihood(d, _LL[lls[d]])
         p = lps[d]
         if p in (None, "log-prior-flat"):
             ow.prior_flat(d)

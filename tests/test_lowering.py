@@ -203,3 +203,43 @@ def test_lowered_model_proves_its_fast_math_arguments_safe():
               "(lambda (x &key a b k &allow-other-keys) (+ a b (exp (* k (sin x)))))"]:
         assert "safe(const MfitEvalArgs&) const { return false; }" in _lib.lower_sexpr(t, keys, 0)
     assert "fabs(s0b) < 700.0" in _lib.lower_sexpr(workloads.USER_POLY5_EXP, ["c0", "c1", "c2", "c3", "c4", "c5", "k"], 0)
+
+
+def test_likelihood_lambda_lowers_and_compiles():
+    """create-log-liklihood-function :402-417: a per-point (lambda (y model error) ...) becomes MfitTerm<MFITK_USER>;
+    `error` is a LIST (:416) -- indexable with a literal, never a number; log-factorial only of y"""
+    from lisp_mcmc_b200 import _lib
+    code = _lib.lower_sexpr("(lambda (y model error) (- (log (+ 1 (expt (/ (- y model) 0.5d0) 2)))))", [], 2)
+    assert "struct MfitTerm<MFITK_USER>" in code and "NARR = 2" in code and "return acc + (" in code
+    code = _lib.lower_sexpr("(lambda (y model error) (log-normal y model (second error)))", [], 2)
+    assert "mfit_u_log_normal(y, f, MFIT_ERR(1))" in code
+    code = _lib.lower_sexpr("(lambda (y model error) (+ (log-poisson model y) 0))", [], 2)
+    assert "NARR = 4" in code and "mfit_u_log_poisson(f, y, lf)" in code
+    assert _lib.compile_sexpr("(lambda (y model error) (log-normal y model (elt error 0)))", [], 2) > 1000
+    for bad in ("(lambda (y model error) (log-normal y model error))",       # the list used as a number
+                "(lambda (y model) (- y model))",                             # wrong arity
+                "(lambda (y model error) (log-factorial model))",             # factorial of something that is not the datum
+                "(lambda (y model error) (elt error 16))"):
+        with pytest.raises(_lib.MfitError):
+            _lib.lower_sexpr(bad, [], 2)
+
+
+def test_oracle_likelihood_lambda_equals_builtin_kinds():
+    """the oracle's evaluator on (lambda (y model error) ...) reproduces its own built-in kinds exactly"""
+    import numpy as np
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    x = np.linspace(0, 1, 200)
+    y = rng.poisson(5 + 3 * x).astype(float)
+    ow = orc.Walker(["a", "b"], 1)
+    ow.dataset(0, x, y, np.full(200, 0.3))
+    ow.model_sexpr(0, "(lambda (x &key a b &allow-other-keys) (+ a (* b x)))")
+    ow.prior_flat(0)
+    ow.likelihood(0, orc.LL_POISSON)
+    p_pois = ow.logp([5.0, 3.0])[0]
+    ow.likelihood_sexpr(0, "(lambda (y model error) (log-poisson model y))")
+    assert ow.logp([5.0, 3.0])[0] == p_pois
+    ow.likelihood(0, orc.LL_NORMAL)
+    p_norm = ow.logp([5.0, 3.0])[0]
+    ow.likelihood_sexpr(0, "(lambda (y model error) (log-normal y model (elt error 0)))")
+    assert ow.logp([5.0, 3.0])[0] == p_norm
