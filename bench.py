@@ -381,7 +381,8 @@ def main():
     if by_dataset:
         from lisp_mcmc_b200 import distributed as Dist
         owners = Dist.shard_datasets(len(base["function"]), world)
-        make = lambda cfg_, **kw_: workloads.make_walker(cfg_, nccl=Dist.process_comm(rank, world), dataset_owners=owners, **kw_)
+        make = lambda cfg_, **kw_: workloads.make_walker(cfg_, nccl=Dist.process_comm(rank, world), peers=Dist.peer_exchange(rank, world),
+                                                         dataset_owners=owners, **kw_)
         n_owned = sum(len(d[0]) for d, o in zip(base["data"], owners) if o == rank)
     kw0 = {} if walker_set else {"theta0": theta0}
     # rows the ring must hold: warm-up + the repeated blocks (bounded by MAX_BLOCKS and by the run's 30000 steps)
@@ -525,14 +526,17 @@ def main():
             try:
                 c4 = workloads.c4()
                 owners = Dist.shard_datasets(len(c4["function"]), world)
-                w4 = workloads.make_walker(c4, nccl=Dist.process_comm(rank, world), dataset_owners=owners, seed=5,
+                w4 = workloads.make_walker(c4, nccl=Dist.process_comm(rank, world), peers=Dist.peer_exchange(rank, world),
+                                           dataset_owners=owners, seed=5,
                                            device=local_rank, trace_capacity=1300, stream=dev.stream)
                 r4 = device_run(dev, L, _lib, w4, 20, 3, 0.0, kernel_steps=10)
                 w4.close()
                 ms4 = float(np.median(r4["block_ms"]))
                 N4 = sum(len(d[0]) for d in c4["data"])
                 extra["c4_datasets"] = {"workload": "C4 global fit, %d data sets over %d GPUs, every rank holds all %d chains; "
-                                        "per-step exchange of the per-data-set terms" % (len(owners), world, c4["theta0"].shape[0]),
+                                        "per-step exchange of the per-data-set terms (%s)" % (
+                                            len(owners), world, c4["theta0"].shape[0],
+                                            "peer stores over NVLink + flags" if Dist.peer_exchange(rank, world) else "NCCL all-gather"),
                                         "scaling": "strong", "steps": 20, "ms_per_step": ms4 / 20,
                                         "value": c4["theta0"].shape[0] * 20 * N4 / (ms4 * 1e-3), "unit": UNIT,
                                         "kernel_ms": r4["kernel_s"] / max(r4["kernel_launches"], 1) * 1e3, "gpu_launches": r4["launches"]}

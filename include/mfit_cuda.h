@@ -256,7 +256,17 @@ int mfit_philox_stream(mfit_ctx* ctx, uint64_t seed, int64_t chain_id_base, int6
  * ll/lp every step with ncclAllGather and sum them in dataset order on every rank. */
 int mfit_nccl_unique_id(void* id_out /* 128 bytes */);
 int mfit_nccl_attach(mfit_ctx* ctx, const void* unique_id, int rank, int n_ranks);
-/* owner[d] = rank that evaluates dataset d (others skip it). Requires mfit_nccl_attach. */
+/* Peer exchange: the same sharding without a collective call on the step path.  Every rank reserves an exchange block
+ * (mfit_peer_setup: plain device memory, exported as a CUDA IPC handle), the 128-byte handles of all ranks are passed to
+ * every rank in rank order (mfit_peer_attach maps them: IPC between processes, direct peer access inside one), and from
+ * then on the kernel that reduces a rank's data sets stores the per-chain terms straight into every peer's block over
+ * NVLink and raises a flag there; the accept kernel of the other GPUs waits for the flags.  Needs all ranks on one box
+ * with peer access (NVSwitch).  max_chains / max_datasets_per_rank bound the chains of a walker set and the data sets a
+ * rank may own.  With a communicator attached as well (mfit_nccl_attach) only the rare stop test uses it. */
+#define MFIT_PEER_HANDLE_BYTES 128
+int mfit_peer_setup(mfit_ctx* ctx, int rank, int n_ranks, int64_t max_chains, int max_datasets_per_rank, void* handle_out);
+int mfit_peer_attach(mfit_ctx* ctx, const void* handles /* n_ranks x MFIT_PEER_HANDLE_BYTES */);
+/* owner[d] = rank that evaluates dataset d (others skip it). Requires mfit_nccl_attach or mfit_peer_attach. */
 int mfit_dataset_owners(mfit_ctx* ctx, const int32_t* owner);
 /* gather chain-sharded traces on every rank: local (W_local x take x (P+1)) -> out (n_ranks x ...) */
 int mfit_nccl_allgather_f64(mfit_ctx* ctx, const double* local_host, int64_t count, double* out_host);

@@ -79,6 +79,8 @@ SIGNATURES = {
     "mfit_philox_stream": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _dp, _dp]),
     "mfit_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mfit_nccl_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "mfit_peer_setup": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "mfit_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mfit_dataset_owners": (C.c_int, [C.c_void_p, _ip]),
     "mfit_nccl_allgather_f64": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp]),
     "mfit_measure_fp64": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp]),

@@ -12,6 +12,7 @@
 // The host never looks at chain state inside a run except for a lagging, non-blocking poll of
 // "how many chains are still active" (auto-stop) and the stop flag (mfit-walker-estop :860).
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -94,7 +95,26 @@ struct Workspace {
   MfitDsDev* ds_dev = nullptr;
   double* xch = nullptr;
   int xslots = 0;
+  bool peer = false;   // xch is the context's peer-mapped exchange buffer (not owned by the workspace)
 };
+
+// Peer exchange state of a context whose data sets are sharded over GPUs (mfit_peer_setup / mfit_peer_attach): one plain
+// cudaMalloc block [flags 512 B][done, err 512 B][two halves of the exchange buffer], mapped into every peer.
+struct Peers {
+  bool ready = false;
+  int rank = 0, n = 0;
+  long long max_stride = 0;
+  int max_slots = 0;
+  char* base = nullptr;
+  double* xch = nullptr;
+  unsigned long long* flags = nullptr;
+  int *xdone = nullptr, *xerr = nullptr;
+  double* xpeer[8] = {nullptr};
+  unsigned long long* flag_peer[8] = {nullptr};
+  void* opened[8] = {nullptr};        // IPC mappings to close
+  unsigned long long epoch = 0;       // exchanges completed (all ranks make the same calls, so it agrees everywhere)
+};
+constexpr size_t kPeerHeader = 1024;
 
 struct EventPair { cudaEvent_t a, b; };
 
@@ -174,12 +194,14 @@ struct mfit_ctx {
   bool poll_ev_made = false;
 
   // multi-GPU
+  Peers peers;
   void* comm = nullptr;
   int rank = 0, n_ranks = 1;
   bool sharded = false;
   int xslots = 0;
 
   std::atomic<int> stop{0};
+  std::atomic<long long>* stop_at = nullptr;   // several ranks in one process: the poll boundary at which all of them stop
 
   // an open run (mfit_run_begin ... mfit_run_advance)
   bool run_open = false;
@@ -258,7 +280,8 @@ void dataset_free_model(Dataset& d) {
 }
 
 void workspace_free(Workspace& w) {
-  free_dev(w.lld); free_dev(w.lpd); free_dev(w.ds_dev); free_dev(w.xch);
+  free_dev(w.lld); free_dev(w.lpd); free_dev(w.ds_dev);
+  if (!w.peer) free_dev(w.xch);
   for (double* p : w.partial) free_dev(p);
   w = Workspace();
 }
@@ -332,8 +355,15 @@ int workspace_make(mfit_ctx* ctx, Workspace& w, long long W) {
   if (ctx->sharded) {
     w.xslots = ctx->xslots;
     const size_t cnt = (size_t)ctx->n_ranks * w.xslots * 2 * w.stride;
-    CU(cudaMalloc(&w.xch, sizeof(double) * cnt));
-    CU(cudaMemsetAsync(w.xch, 0, sizeof(double) * cnt, ctx->stream));
+    if (ctx->peers.ready) {
+      if (w.stride > ctx->peers.max_stride || w.xslots > ctx->peers.max_slots)
+        return fail(ctx, MFIT_ERR_ARG, "%lld chains / %d data sets per rank exceed what mfit_peer_setup reserved", (long long)W, w.xslots);
+      w.xch = ctx->peers.xch;
+      w.peer = true;
+    } else {
+      CU(cudaMalloc(&w.xch, sizeof(double) * cnt));
+      CU(cudaMemsetAsync(w.xch, 0, sizeof(double) * cnt, ctx->stream));
+    }
   }
   std::vector<MfitDsDev> host(D);
   for (int d = 0; d < D; d++) {
@@ -697,7 +727,8 @@ int eval_all(mfit_ctx* ctx, Workspace& w, const MfitChains& view, const double* 
   for (int d = 0; d < ctx->D; d++) {
     Dataset& s = ctx->ds[d];
     if (!s.owned || s.prior_kind != 2) continue;
-    double* out = view.xch ? const_cast<double*>(view.xch) + ((size_t)(s.owner * view.xslots + s.xslot) * 2 + 1) * view.stride
+    double* out = view.xch ? const_cast<double*>(view.xch) + (size_t)view.xpar * view.xpar_stride +
+                                 ((size_t)(s.owner * view.xslots + s.xslot) * 2 + 1) * view.stride
                            : view.lpd + (size_t)d * view.stride;
     // the user prior kernel indexes chains from 0: a group passes pointers advanced to its first chain
     const long long w_lo = (long long)cb0 * MFIT_CB;
@@ -715,8 +746,24 @@ int eval_all(mfit_ctx* ctx, Workspace& w, const MfitChains& view, const double* 
   return 0;
 }
 
-int exchange(mfit_ctx* ctx, Workspace& w) {
+// the view's exchange fields follow the context's exchange counter (peer exchange only)
+void sync_epoch(mfit_ctx* ctx, MfitChains& v) {
+  if (v.xranks > 0) {
+    v.xepoch = ctx->peers.epoch;
+    v.xpar = (int)(ctx->peers.epoch & 1);
+  }
+}
+
+// After k_finalize: make the other ranks' per-data-set terms available to the kernel enqueued next.  Host-side collective
+// (NCCL all-gather of every rank's rows), or -- peer exchange -- nothing to launch: k_finalize has pushed this rank's rows
+// into the peers' buffers, k_post waits for theirs itself, any other consumer is preceded by a wait kernel.
+int exchange(mfit_ctx* ctx, Workspace& w, const MfitChains* v = nullptr, bool consumer_waits = false) {
   if (!ctx->sharded) return 0;
+  if (w.peer) {
+    if (!consumer_waits && v) { mfit_launch_peer_wait(*v, ctx->stream); ctx->launches++; }
+    return 0;
+  }
+  if (!ctx->comm) return fail(ctx, MFIT_ERR_STATE, "data sets are sharded but neither NCCL nor peers are attached");
   const size_t per_rank = sizeof(double) * (size_t)w.xslots * 2 * w.stride;
   std::string e;
   int rc = mfit_nccl_allgather_bytes(ctx->comm, (const char*)w.xch + per_rank * ctx->rank, w.xch, per_rank, ctx->stream, e);
@@ -740,6 +787,17 @@ MfitChains view_of(mfit_ctx* ctx, Workspace& w) {
   v.lpd = w.lpd;
   v.xch = w.xch;
   v.xslots = w.xslots;
+  if (w.peer) {
+    const Peers& p = ctx->peers;
+    v.xpar_stride = (long long)p.n * w.xslots * 2 * w.stride;
+    v.xrank = p.rank;
+    v.xranks = p.n;
+    for (int q = 0; q < p.n; q++) { v.xpeer[q] = p.xpeer[q]; v.xflag_peer[q] = p.flag_peer[q]; }
+    v.xflag = p.flags;
+    v.xdone = p.xdone;
+    v.xerr = p.xerr;
+    sync_epoch(ctx, v);
+  }
   v.ds = w.ds_dev;
   return v;
 }
@@ -886,6 +944,19 @@ int upload_opt(mfit_ctx* ctx, const double* host, size_t count, double** dev, si
   return 0;
 }
 
+// a peer-exchange wait that ran out of time (a rank died or fell out of step) left a mark: report it once
+int peer_check(mfit_ctx* ctx) {
+  if (!ctx->peers.ready) return 0;
+  int err = 0;
+  CU(cudaMemcpyAsync(&err, ctx->peers.xerr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (err) {
+    CU(cudaMemsetAsync(ctx->peers.xerr, 0, sizeof(int), ctx->stream));
+    return fail(ctx, MFIT_ERR_NCCL, "peer exchange timed out: a rank did not deliver its data sets' terms");
+  }
+  return 0;
+}
+
 // set-up of a run (:866-901): driver state per chain, first proposals
 int run_begin(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long long max_steps) {
   MfitChains& c = ctx->ch;
@@ -905,6 +976,7 @@ int run_begin(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long lon
   r.seed = ctx->seed;
   r.chain_base = ctx->chain_base;
   r.t = 0;
+  sync_epoch(ctx, c);   // the first proposals' priors belong to the exchange of the first step
   mfit_launch_init_run(c, r, l_dev, ctx->stream);
   mfit_launch_pre(c, r, ctx->stream);    // proposals of chains that keep their l-matrix
   mfit_launch_reest(c, r, ctx->stream);  // chains resuming a long walk re-estimate first (:897-901)
@@ -976,6 +1048,7 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
     // leave the loop at the same t: the flag is then only looked at -- all-gathered -- at the poll boundaries below.
     if (!ctx->sharded && ctx->stop.load()) break;
     r.t = t;
+    sync_epoch(ctx, c);
     for (int g = 0; g < n_groups; g++) {
       const Group& G = grp[g];
       if (G.w1 <= G.w0) continue;
@@ -985,17 +1058,20 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
       rc = eval_all(ctx, ctx->ws, c, c.prop_theta, c.done, g, G.cb0, G.n_cb, G.st);
       if (rc) return rc;
       if (ctx->sharded) {
-        mfit_launch_finalize(c, ctx->stream);
+        mfit_launch_finalize(c, ctx->stream);   // peer exchange: also stores this rank's rows into the peers' buffers
         ctx->launches++;
-        rc = exchange(ctx, ctx->ws);
+        rc = exchange(ctx, ctx->ws, &c, true);  // k_post waits for the peers' rows itself
         if (rc) return rc;
       }
       mfit_launch_post(cg, r, true, G.st);  // accept/push/adapt of step t, proposal of step t+1
       MfitRunCfg rn = r;
       rn.t = t + 1;
-      mfit_launch_reest(cg, rn, G.st);
+      MfitChains cn = cg;
+      if (cn.xpar_stride != 0) cn.xpar ^= 1;   // a re-estimated chain's next proposal: priors of the NEXT exchange
+      mfit_launch_reest(cn, rn, G.st);
       ctx->launches += 2;
     }
+    if (ctx->ws.peer) ctx->peers.epoch++;
     if (ctx->sharded && (t + 1) % poll_every == 0) {
       // Collective, deterministic stop test: every rank holds the same chains (so the same active count) but its own
       // stop flag and its own host timing.  (active, stop) of all ranks are all-gathered and read back with a blocking
@@ -1006,19 +1082,40 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
         if (2 * R > 56) return fail(ctx, MFIT_ERR_ARG, "more than 28 ranks");
         ctx->xflag_host = ctx->active_host + 8;  // the context's pinned words: [0,4) active counts, [8, 8 + 2R) these flags
       }
-      mfit_launch_count_active(c, ctx->xflag_dev + 2 * ctx->rank, ctx->stream);
       ctx->launches++;
-      ctx->xflag_host[2 * ctx->rank + 1] = ctx->stop.load();
-      CU(cudaMemcpyAsync(ctx->xflag_dev + 2 * ctx->rank + 1, ctx->xflag_host + 2 * ctx->rank + 1, sizeof(int),
-                         cudaMemcpyHostToDevice, ctx->stream));
-      std::string er;
-      rc = mfit_nccl_allgather_bytes(ctx->comm, ctx->xflag_dev + 2 * ctx->rank, ctx->xflag_dev, 2 * sizeof(int), ctx->stream, er);
-      if (rc) return fail(ctx, rc, "%s", er.c_str());
+      if (ctx->comm) {
+        mfit_launch_count_active(c, ctx->xflag_dev + 2 * ctx->rank, ctx->stream);
+        ctx->xflag_host[2 * ctx->rank + 1] = ctx->stop.load();
+        CU(cudaMemcpyAsync(ctx->xflag_dev + 2 * ctx->rank + 1, ctx->xflag_host + 2 * ctx->rank + 1, sizeof(int),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        std::string er;
+        rc = mfit_nccl_allgather_bytes(ctx->comm, ctx->xflag_dev + 2 * ctx->rank, ctx->xflag_dev, 2 * sizeof(int), ctx->stream, er);
+        if (rc) return fail(ctx, rc, "%s", er.c_str());
+      } else {
+        // peers without a communicator (all ranks in one process, mfit_multi_*): the active count is the same on every
+        // rank by construction; a stop request is agreed on through the owner's shared word, one boundary ahead
+        CU(cudaMemsetAsync(ctx->xflag_dev, 0xff, sizeof(int) * 2 * R, ctx->stream));   // "-1": other ranks neither done nor stopping
+        mfit_launch_count_active(c, ctx->xflag_dev + 2 * ctx->rank, ctx->stream);
+        const long long boundary = (t + 1) / poll_every;
+        int stop_now = 0;
+        if (ctx->stop_at) {
+          long long at = ctx->stop_at->load();
+          if (at < 0 && ctx->rank == 0 && ctx->stop.load()) {
+            long long want = boundary + 1;
+            ctx->stop_at->compare_exchange_strong(at, want);
+            at = ctx->stop_at->load();
+          }
+          stop_now = at >= 0 && boundary >= at;
+        }
+        ctx->xflag_host[2 * ctx->rank + 1] = stop_now;
+        CU(cudaMemcpyAsync(ctx->xflag_dev + 2 * ctx->rank + 1, ctx->xflag_host + 2 * ctx->rank + 1, sizeof(int),
+                           cudaMemcpyHostToDevice, ctx->stream));
+      }
       CU(cudaMemcpyAsync(ctx->xflag_host, ctx->xflag_dev, sizeof(int) * 2 * R, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
       for (int k = 0; k < R; k++) {
         if (ctx->xflag_host[2 * k] == 0) all_done = true;
-        if (ctx->xflag_host[2 * k + 1] != 0) stop_seen = true;
+        if (ctx->xflag_host[2 * k + 1] > 0) stop_seen = true;
       }
       if (stop_seen) { t++; break; }
     } else if ((t + 1) % poll_every == 0) {
@@ -1043,6 +1140,7 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
   if ((rc = join_groups()) != 0) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
+  if ((rc = peer_check(ctx)) != 0) return rc;
   collect_timing(ctx);
   ctx->rows_upper += t - ctx->run_t;
   if (steps_done) *steps_done = t - ctx->run_t;
@@ -1141,6 +1239,8 @@ void mfit_ctx_destroy(mfit_ctx* ctx) {
   free_dev(ctx->temps_dev); free_dev(ctx->z_dev); free_dev(ctx->u_dev); free_dev(ctx->lshared_dev);
   free_dev(ctx->active_dev); free_dev(ctx->flush_buf); free_dev(ctx->sched_dev); free_dev(ctx->mode_dev);
   free_dev(ctx->xflag_dev);
+  for (void* m : ctx->peers.opened) if (m) cudaIpcCloseMemHandle(m);
+  if (ctx->peers.base) (cudaFree)(ctx->peers.base);
   for (auto& p : ctx->ev) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   cudaStreamSynchronize(ctx->stream);  // the stream-ordered frees above
   for (int g = 1; g < mfit_ctx::kMaxGroups; g++) cudaStreamSynchronize(ctx->gstream[g]);
@@ -1502,6 +1602,7 @@ int mfit_eval_logp(mfit_ctx* ctx, const double* theta, int64_t W, double* prob, 
   CUX(cudaMalloc(&o_lp, sizeof(double) * W * D));
   CUX(cudaMemcpyAsync(th_rm, theta, sizeof(double) * W * P, cudaMemcpyHostToDevice, ctx->stream));
   mfit_launch_transpose_in(th_rm, th, W, P, w.stride, ctx->stream);
+  if (w.peer && ctx->run_open) { cleanup(); return fail(ctx, MFIT_ERR_STATE, "a run is open: its pending terms live in the peer exchange buffer"); }
   MfitChains v = view_of(ctx, w);
   mfit_launch_priors(v, th, ctx->stream);
   ctx->launches += 2;
@@ -1512,10 +1613,11 @@ int mfit_eval_logp(mfit_ctx* ctx, const double* theta, int64_t W, double* prob, 
   if (rc) { cleanup(); return rc; }
   mfit_launch_finalize(v, ctx->stream);
   ctx->launches++;
-  rc = exchange(ctx, w);
+  rc = exchange(ctx, w, &v);
   if (rc) { cleanup(); return rc; }
   mfit_launch_eval_finalize(v, o_prob, o_ll, o_lp, ctx->stream);
   ctx->launches++;
+  if (w.peer) ctx->peers.epoch++;
   if (prob) CUX(cudaMemcpyAsync(prob, o_prob, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
   if (ll) CUX(cudaMemcpyAsync(ll, o_ll, sizeof(double) * W * D, cudaMemcpyDeviceToHost, ctx->stream));
   if (lp) CUX(cudaMemcpyAsync(lp, o_lp, sizeof(double) * W * D, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1578,16 +1680,18 @@ int mfit_chains_init(mfit_ctx* ctx, const double* theta0, int64_t W, uint64_t se
   CU(cudaMalloc(&th_rm, sizeof(double) * W * P));
   CU(cudaMemcpyAsync(th_rm, theta0, sizeof(double) * W * P, cudaMemcpyHostToDevice, ctx->stream));
   mfit_launch_transpose_in(th_rm, c.prop_theta, W, P, c.stride, ctx->stream);
+  sync_epoch(ctx, c);
   mfit_launch_priors(c, c.prop_theta, ctx->stream);
   ctx->launches += 2;
   rc = eval_all(ctx, ctx->ws, c, c.prop_theta, nullptr);
   if (rc) { cudaFree(th_rm); return rc; }
   mfit_launch_finalize(c, ctx->stream);
   ctx->launches++;
-  rc = exchange(ctx, ctx->ws);
+  rc = exchange(ctx, ctx->ws, &c);
   if (rc) { cudaFree(th_rm); return rc; }
   pc.mark("chains_init: first eval");
   mfit_launch_first_step(c, ctx->stream);
+  if (ctx->ws.peer) ctx->peers.epoch++;
   ctx->rows_upper = 1;
   ctx->launches++;
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -1762,15 +1866,17 @@ int mfit_force_take_step(mfit_ctx* ctx) {
   int rc = grow_trace(ctx, ctx->rows_upper + 2);
   if (rc) return rc;
   ctx->rows_upper += 1;
+  sync_epoch(ctx, c);
   mfit_launch_priors(c, c.cur_theta, ctx->stream);
   ctx->launches++;
   rc = eval_all(ctx, ctx->ws, c, c.cur_theta, nullptr);
   if (rc) return rc;
   mfit_launch_finalize(c, ctx->stream);
   ctx->launches++;
-  rc = exchange(ctx, ctx->ws);
+  rc = exchange(ctx, ctx->ws, &c);
   if (rc) return rc;
   mfit_launch_force_step(c, ctx->stream);
+  if (ctx->ws.peer) ctx->peers.epoch++;
   ctx->launches++;
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
@@ -2132,10 +2238,92 @@ int mfit_nccl_attach(mfit_ctx* ctx, const void* unique_id, int rank, int n_ranks
   return 0;
 }
 
+// ---- peer exchange: data sets sharded over the GPUs of one box without a collective call on the step path
+struct PeerHandle {   // MFIT_PEER_HANDLE_BYTES
+  cudaIpcMemHandle_t ipc;        // 64 bytes
+  unsigned long long ptr;        // the block's address in the exporting process
+  long long pid;
+  int device, rank, n_ranks, max_slots;
+  long long max_stride;
+};
+static_assert(sizeof(PeerHandle) <= MFIT_PEER_HANDLE_BYTES, "PeerHandle does not fit");
+
+int mfit_peer_setup(mfit_ctx* ctx, int rank, int n_ranks, int64_t max_chains, int max_datasets_per_rank, void* handle_out) {
+  if (!ctx || !handle_out || n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks || max_chains < 1 || max_datasets_per_rank < 1)
+    return ctx ? fail(ctx, MFIT_ERR_ARG, "peer exchange: 1..8 ranks, rank in range, chains and data sets per rank >= 1") : MFIT_ERR_ARG;
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  Peers& p = ctx->peers;
+  if (p.base) return fail(ctx, MFIT_ERR_STATE, "mfit_peer_setup has been called already");
+  p.rank = rank;
+  p.n = n_ranks;
+  p.max_stride = round_up(max_chains, MFIT_CB);
+  p.max_slots = max_datasets_per_rank;
+  const size_t half = sizeof(double) * (size_t)n_ranks * p.max_slots * 2 * (size_t)p.max_stride;
+  // plain cudaMalloc: memory of the stream-ordered pool cannot be exported to other processes
+  CU((cudaMalloc)((void**)&p.base, kPeerHeader + 2 * half));
+  CU(cudaMemsetAsync(p.base, 0, kPeerHeader + 2 * half, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  p.flags = reinterpret_cast<unsigned long long*>(p.base);
+  p.xdone = reinterpret_cast<int*>(p.base + 512);
+  p.xerr = p.xdone + 1;
+  p.xch = reinterpret_cast<double*>(p.base + kPeerHeader);
+  PeerHandle h;
+  memset(&h, 0, sizeof h);
+  CU(cudaIpcGetMemHandle(&h.ipc, p.base));
+  h.ptr = (unsigned long long)(uintptr_t)p.base;
+  h.pid = (long long)getpid();
+  h.device = ctx->device;
+  h.rank = rank;
+  h.n_ranks = n_ranks;
+  h.max_slots = p.max_slots;
+  h.max_stride = p.max_stride;
+  memset(handle_out, 0, MFIT_PEER_HANDLE_BYTES);
+  memcpy(handle_out, &h, sizeof h);
+  ctx->rank = rank;
+  ctx->n_ranks = n_ranks;
+  return 0;
+}
+
+int mfit_peer_attach(mfit_ctx* ctx, const void* handles) {
+  if (!ctx || !handles) return MFIT_ERR_ARG;
+  Peers& p = ctx->peers;
+  if (!p.base) return fail(ctx, MFIT_ERR_STATE, "mfit_peer_setup has not been called");
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  for (int q = 0; q < p.n; q++) {
+    PeerHandle h;
+    memcpy(&h, (const char*)handles + (size_t)q * MFIT_PEER_HANDLE_BYTES, sizeof h);
+    if (h.rank != q || h.n_ranks != p.n || h.max_stride != p.max_stride || h.max_slots != p.max_slots)
+      return fail(ctx, MFIT_ERR_ARG, "peer handle %d does not match this context's mfit_peer_setup", q);
+    char* base = nullptr;
+    if (q == p.rank) base = p.base;
+    else if (h.pid == (long long)getpid()) {   // the peer lives in this process: its pointer is valid here once peer access is on
+      if (h.device != ctx->device) {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
+        if (!can) return fail(ctx, MFIT_ERR_CUDA, "device %d cannot access device %d", ctx->device, h.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, MFIT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+      }
+      base = reinterpret_cast<char*>((uintptr_t)h.ptr);
+    } else {
+      void* m = nullptr;
+      CU(cudaIpcOpenMemHandle(&m, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+      p.opened[q] = m;
+      base = (char*)m;
+    }
+    p.flag_peer[q] = reinterpret_cast<unsigned long long*>(base);
+    p.xpeer[q] = reinterpret_cast<double*>(base + kPeerHeader);
+  }
+  p.ready = true;
+  if (ctx->have_chains) chains_free(ctx);
+  return 0;
+}
+
 int mfit_dataset_owners(mfit_ctx* ctx, const int32_t* owner) {
   if (!ctx || !owner) return MFIT_ERR_ARG;
   if (ctx->D <= 0) return fail(ctx, MFIT_ERR_STATE, "mfit_problem_define has not been called");
-  if (!ctx->comm) return fail(ctx, MFIT_ERR_STATE, "mfit_nccl_attach has not been called");
+  if (!ctx->comm && !ctx->peers.ready) return fail(ctx, MFIT_ERR_STATE, "neither mfit_nccl_attach nor mfit_peer_attach has been called");
   g_alloc_stream = ctx->stream;
   std::vector<int> per_rank(ctx->n_ranks, 0);
   for (int d = 0; d < ctx->D; d++) {

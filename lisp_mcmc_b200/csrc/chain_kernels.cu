@@ -122,16 +122,71 @@ __device__ bool stable_probs(const MfitChains& c, long long w, long long S) {
 __device__ __forceinline__ double* ll_ptr(const MfitChains& c, int d) {
   if (c.xch) {
     const MfitDsDev& s = c.ds[d];
-    return const_cast<double*>(c.xch) + ((size_t)(s.xrank * c.xslots + s.xslot) * 2 + 0) * c.stride;
+    return const_cast<double*>(c.xch) + (size_t)c.xpar * c.xpar_stride + ((size_t)(s.xrank * c.xslots + s.xslot) * 2 + 0) * c.stride;
   }
   return c.lld + (size_t)d * c.stride;
 }
 __device__ __forceinline__ double* lp_ptr(const MfitChains& c, int d) {
   if (c.xch) {
     const MfitDsDev& s = c.ds[d];
-    return const_cast<double*>(c.xch) + ((size_t)(s.xrank * c.xslots + s.xslot) * 2 + 1) * c.stride;
+    return const_cast<double*>(c.xch) + (size_t)c.xpar * c.xpar_stride + ((size_t)(s.xrank * c.xslots + s.xslot) * 2 + 1) * c.stride;
   }
   return c.lpd + (size_t)d * c.stride;
+}
+// Per-data-set terms are read through L2 (never a stale L1 line): with the peer exchange other GPUs write them.
+__device__ __forceinline__ double term_load(const double* p) { return __ldcg(p); }
+
+// ------------------------------------------------------------------ peer exchange (data sets sharded over GPUs)
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const volatile unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// every block, before it reads terms other ranks own: wait until all of them have delivered exchange c.xepoch.
+// Bounded (a few seconds): a peer that never delivers must not hang the GPU; the host reports it.
+__device__ void peer_wait(const MfitChains& c) {
+  if (c.xranks > 0) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      for (int r = 0; r < c.xranks; r++) {
+        if (r == c.xrank) continue;
+        while (ld_acquire_sys(c.xflag + r) < c.xepoch + 1) {
+          if (clock64() - t0 > 20000000000LL) { *c.xerr = 1; break; }
+          __nanosleep(200);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+// this rank's rows (ll and lp of every data set it owns, chains [w_lo, w_hi) of this block) -> every peer's buffer
+__device__ void peer_push(const MfitChains& c, long long w, bool valid) {
+  if (c.xranks <= 0) return;
+  if (valid)
+    for (int d = 0; d < c.D; d++) {
+      const MfitDsDev& s = c.ds[d];
+      if (!s.owned) continue;
+      const size_t off = (size_t)c.xpar * c.xpar_stride + ((size_t)(s.xrank * c.xslots + s.xslot) * 2) * c.stride + w;
+      const double ll = c.xch[off], lp = c.xch[off + c.stride];
+      for (int q = 0; q < c.xranks; q++) {
+        if (q == c.xrank) continue;
+        c.xpeer[q][off] = ll;
+        c.xpeer[q][off + c.stride] = lp;
+      }
+    }
+  __threadfence_system();   // this thread's remote stores are visible system-wide ...
+  __syncthreads();
+  if (threadIdx.x == 0) {   // ... before the last block to get here tells the peers
+    if (atomicAdd(c.xdone, 1) == (int)gridDim.x - 1) {
+      *c.xdone = 0;
+      __threadfence_system();
+      for (int q = 0; q < c.xranks; q++)
+        if (q != c.xrank) st_release_sys(c.xflag_peer[q] + c.xrank, c.xepoch + 1);
+    }
+  }
 }
 
 // per-segment partial sums -> dataset log-likelihood.  The likelihood kernel cuts a data set into up to 1024
@@ -256,11 +311,11 @@ __device__ void post_body(const MfitChains& c, const MfitRunCfg& r, long long w)
   // walker-make-step :1067-1070
   double ll = 0.0, lp = 0.0;
   for (int d = 0; d < c.D; d++) {
-    double v = ll_ptr(c, d)[w];
+    double v = term_load(ll_ptr(c, d) + w);
     ll = d == 0 ? v : ll + v;
   }
   for (int d = 0; d < c.D; d++) {
-    double v = lp_ptr(c, d)[w];
+    double v = term_load(lp_ptr(c, d) + w);
     lp = d == 0 ? v : lp + v;
   }
   const double p1 = ll + lp;
@@ -363,13 +418,20 @@ __global__ void k_post(const MfitChains c, MfitRunCfg r) {
       if (slice == 0 && w < c.w1) ll_ptr(c, d)[w] = v;
     }
     if (slice != 0) return;
-  } else
+  } else {
+    peer_wait(c);   // the other ranks' terms of this step have arrived (no-op with a host-side collective)
     w = c.w0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  }
   if (w >= c.w1) return;
   post_body(c, r, w);
   if (FUSE) {
     r.t += 1;
-    pre_body(c, r, w);
+    if (c.xpar_stride != 0) {   // the next proposal's priors belong to the next exchange: the other half of the buffer
+      MfitChains cn = c;
+      cn.xpar ^= 1;
+      pre_body(cn, r, w);
+    } else
+      pre_body(c, r, w);
   }
 }
 __global__ void k_finalize(const MfitChains c) {
@@ -381,7 +443,10 @@ __global__ void k_finalize(const MfitChains c) {
     const double v = reduce_ll<MFIT_RED_S>(c, d, w, slice, red);
     if (slice == 0 && w < c.W) ll_ptr(c, d)[w] = v;
   }
+  peer_push(c, w, slice == 0 && w < c.W);   // the threads of slice 0 wrote the rows; every thread takes part in the barrier
 }
+// kernels that read the exchanged terms outside k_post (first step, force-take-step, eval_logp's read-out) are preceded by this
+__global__ void k_peer_wait(const MfitChains c) { peer_wait(c); }
 
 // ------------------------------------------------------------------ run set-up (:866-901)
 __global__ void k_init_run(const MfitChains c, const MfitRunCfg r, const double* l_shared) {
@@ -543,8 +608,8 @@ __global__ void k_first_step(const MfitChains c) {  // :1148-1162; prop_theta = 
   if (w >= c.W) return;
   const int P = c.P;
   double ll = 0.0, lp = 0.0;
-  for (int d = 0; d < c.D; d++) { double v = ll_ptr(c, d)[w]; ll = d == 0 ? v : ll + v; }
-  for (int d = 0; d < c.D; d++) { double v = lp_ptr(c, d)[w]; lp = d == 0 ? v : lp + v; }
+  for (int d = 0; d < c.D; d++) { double v = term_load(ll_ptr(c, d) + w); ll = d == 0 ? v : ll + v; }
+  for (int d = 0; d < c.D; d++) { double v = term_load(lp_ptr(c, d) + w); lp = d == 0 ? v : lp + v; }
   const double p = ll + lp;
   for (int i = 0; i < P; i++) {
     double v = c.prop_theta[(size_t)i * c.stride + w];
@@ -572,8 +637,8 @@ __global__ void k_force_step(const MfitChains c) {  // :1124-1129; prop_theta = 
   if (w >= c.W) return;
   const int P = c.P;
   double ll = 0.0, lp = 0.0;
-  for (int d = 0; d < c.D; d++) { double v = ll_ptr(c, d)[w]; ll = d == 0 ? v : ll + v; }
-  for (int d = 0; d < c.D; d++) { double v = lp_ptr(c, d)[w]; lp = d == 0 ? v : lp + v; }
+  for (int d = 0; d < c.D; d++) { double v = term_load(ll_ptr(c, d) + w); ll = d == 0 ? v : ll + v; }
+  for (int d = 0; d < c.D; d++) { double v = term_load(lp_ptr(c, d) + w); lp = d == 0 ? v : lp + v; }
   const double p = ll + lp;
   c.cur_prob[w] = p;
   if (p > c.best_prob[w]) {
@@ -602,12 +667,12 @@ __global__ void k_eval_finalize(const MfitChains c, double* prob, double* ll_out
   if (w >= c.W) return;
   double ll = 0.0, lp = 0.0;
   for (int d = 0; d < c.D; d++) {
-    double v = ll_ptr(c, d)[w];
+    double v = term_load(ll_ptr(c, d) + w);
     if (ll_out) ll_out[(size_t)w * c.D + d] = v;
     ll = d == 0 ? v : ll + v;
   }
   for (int d = 0; d < c.D; d++) {
-    double v = lp_ptr(c, d)[w];
+    double v = term_load(lp_ptr(c, d) + w);
     if (lp_out) lp_out[(size_t)w * c.D + d] = v;
     lp = d == 0 ? v : lp + v;
   }
@@ -1079,6 +1144,9 @@ void mfit_launch_post(const MfitChains& c, const MfitRunCfg& r, bool fuse_pre, c
 }
 void mfit_launch_finalize(const MfitChains& c, cudaStream_t st) {
   k_finalize<<<blocks_for(c.W, 32), MFIT_RED_T, 0, st>>>(c);
+}
+void mfit_launch_peer_wait(const MfitChains& c, cudaStream_t st) {
+  if (c.xranks > 0) k_peer_wait<<<1, 32, 0, st>>>(c);
 }
 void mfit_launch_first_step(const MfitChains& c, cudaStream_t st) {
   k_first_step<<<blocks_for(c.W, 128), 128, 0, st>>>(c);

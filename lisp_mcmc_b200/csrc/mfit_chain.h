@@ -54,6 +54,19 @@ struct MfitChains {
   double* lpd;          // [D][stride] per-dataset log-prior of the proposal
   const double* xch;    // exchange buffer [R][slots][2][stride] when datasets are sharded (else null)
   int xslots;
+  // Peer exchange (data sets sharded over GPUs, no collective call on the step path): the buffer is doubled -- xch +
+  // xpar * xpar_stride is the half in use for the exchange in progress -- and every rank's k_finalize stores its own rows
+  // straight into the buffers of all peers over NVLink (xpeer[q], mapped peer memory), then raises xflag_peer[q][xrank] to
+  // xepoch + 1; the kernels that read the terms first wait until xflag[r] has got there for every r.
+  int xpar;                         // 0 / 1
+  long long xpar_stride;            // elements between the halves (0: not doubled, host-side collective)
+  int xrank, xranks;                // this GPU's rank among the owners; 0 ranks = no peer exchange
+  unsigned long long xepoch;        // exchanges completed before this one
+  double* xpeer[8];                 // every rank's exchange buffer as seen from this GPU ([xrank] = xch)
+  unsigned long long* xflag_peer[8];  // every rank's flag array [xranks] as seen from this GPU
+  volatile unsigned long long* xflag;  // this GPU's flags
+  int* xdone;                       // blocks of k_finalize that have pushed their rows (reset by the last one)
+  int* xerr;                        // set when a wait timed out (a peer died): the host turns it into MFIT_ERR_NCCL
   const MfitDsDev* ds;  // [D] device array
 };
 
@@ -78,6 +91,7 @@ void mfit_launch_reest(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st
 void mfit_launch_pre(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st);
 void mfit_launch_post(const MfitChains& c, const MfitRunCfg& r, bool fuse_pre, cudaStream_t st);
 void mfit_launch_finalize(const MfitChains& c, cudaStream_t st);
+void mfit_launch_peer_wait(const MfitChains& c, cudaStream_t st);
 void mfit_launch_first_step(const MfitChains& c, cudaStream_t st);
 void mfit_launch_force_step(const MfitChains& c, cudaStream_t st);
 void mfit_launch_priors(const MfitChains& c, const double* theta, cudaStream_t st);

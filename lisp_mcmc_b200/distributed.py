@@ -87,6 +87,31 @@ def process_comm(rank=None, world=None):
     return _PROCESS_UID, rank, world
 
 
+def gather_peer_handles(handle_bytes):
+    """all ranks' 128-byte peer-exchange handles (mfit_peer_setup), concatenated in rank order -- the `gather` of
+    Walker(peers=(rank, world, gather))"""
+    import torch
+    dist = _dist()
+    if dist is None:
+        return bytes(handle_bytes)
+    mine = torch.frombuffer(bytearray(handle_bytes), dtype=torch.uint8).clone().to(_device())
+    parts = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    return b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+
+
+def peer_exchange(rank=None, world=None):
+    """Walker(peers=...) argument for this job, or None when the peer exchange cannot be used (one rank, more than 8,
+    MFIT_NO_PEERS set, or no GPUs): then the per-step exchange is the NCCL all-gather."""
+    r, _, w = env_ranks()
+    rank = r if rank is None else rank
+    world = w if world is None else world
+    dist = _dist()
+    if world < 2 or world > 8 or os.environ.get("MFIT_NO_PEERS") or dist is None or dist.get_backend() != "nccl":
+        return None
+    return rank, world, gather_peer_handles
+
+
 def chain_shard(W):
     """(first global chain id, count) of this rank"""
     dist = _dist()
@@ -184,4 +209,5 @@ def walker_create_sharded(cfg, mode="chains", **gpu):
         raise ValueError("mode must be 'chains' or 'datasets'")
     if world == 1:
         return workloads.make_walker(cfg, **gpu)
-    return workloads.make_walker(cfg, nccl=process_comm(rank, world), dataset_owners=dataset_owners(len(cfg["function"])), **gpu)
+    return workloads.make_walker(cfg, nccl=process_comm(rank, world), peers=peer_exchange(rank, world),
+                                 dataset_owners=dataset_owners(len(cfg["function"])), **gpu)

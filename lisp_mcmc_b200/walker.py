@@ -196,7 +196,7 @@ class Walker:
 
     def __init__(self, function, data, params, data_error=None, log_liklihood=None, log_prior=None,
                  n_walkers=None, theta0=None, seed=0, device=0, chain_id_base=0, trace_capacity=0,
-                 nccl=None, dataset_owners=None, stream=None, per_walker=None):
+                 nccl=None, dataset_owners=None, stream=None, per_walker=None, peers=None):
         L = _lib.lib()
         self._L = L
         self.function = force_list(function)                        # :1142
@@ -240,6 +240,19 @@ class Walker:
             self.rank, self.world = rank, world
         else:
             self.rank, self.world = 0, 1
+        if peers is not None:
+            # peer exchange for data sets sharded over the GPUs of one box (mfit_peer_setup / mfit_peer_attach):
+            # peers = (rank, world, gather) with gather(bytes) -> the handles of all ranks concatenated in rank order
+            prank, pworld, gather = peers
+            n_chains = int(per_walker["y"].shape[0]) if per_walker is not None else \
+                (int(np.shape(theta0)[0]) if theta0 is not None and np.ndim(theta0) == 2 else int(n_walkers or 1))
+            handle = C.create_string_buffer(128)
+            self._chk(L.mfit_peer_setup(h, prank, pworld, n_chains, -(-D // pworld), handle))
+            allh = gather(handle.raw)
+            if len(allh) != 128 * pworld:
+                raise ValueError("peer handle exchange returned %d bytes for %d ranks" % (len(allh), pworld))
+            self._chk(L.mfit_peer_attach(h, C.create_string_buffer(allh, len(allh))))
+            self.rank, self.world = prank, pworld
         self.dataset_owners = None
         if dataset_owners is not None:
             own = np.ascontiguousarray(dataset_owners, dtype=np.int32)

@@ -2,8 +2,11 @@
    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mgpu/mgpu_check.py
 1. chain sharding: W chains split over N ranks give, after the gather, bit for bit the trace rank 0 gets from all W
    chains on its own GPU (Philox keyed by global chain id).
-2. dataset sharding: a D-data-set global fit with data sets spread over the ranks (per-step NCCL all-gather inside
-   libmfit_cuda.so, ordered sum) gives bit for bit the trace of the same fit on one GPU.
+2. dataset sharding: a D-data-set global fit with data sets spread over the ranks gives bit for bit the trace of the same
+   fit on one GPU -- with the peer exchange (every rank's k_finalize stores its terms into the peers' buffers over NVLink,
+   k_post waits on flags) and with the NCCL all-gather (MFIT_NO_PEERS), ordered sum either way.
+3. the same fit with :auto :prob-settle (chains stop on their own, the host loop must end at the same step on every rank)
+   and with a stop request raised on ONE rank only: no rank hangs, all leave the loop after the same number of steps.
 Prints MGPU_OK on rank 0."""
 import os
 import sys
@@ -54,6 +57,51 @@ def main():
         m = int(nv1.max())
         ok2 = np.array_equal(nvg, nv1) and np.array_equal(thg[:, :m], th1[:, :m]) and np.array_equal(prg[:, :m], pr1[:, :m])
         print("dataset sharding (%d data sets over %d ranks): %s" % (Dn, world, "bit-identical" if ok2 else "MISMATCH"))
+    # 2b. the same through the NCCL all-gather instead of the peer exchange
+    os.environ["MFIT_NO_PEERS"] = "1"
+    wn = D.walker_create_sharded(g, "datasets", seed=5)
+    wn.adaptive_steps_full(n=300, temperature=10, auto=None)
+    thn, prn, nvn = wn.trace(2001)
+    wn.close()
+    del os.environ["MFIT_NO_PEERS"]
+    ok2b = np.array_equal(thn, thg) and np.array_equal(prn, prg, equal_nan=True)
+    if rank == 0:
+        print("NCCL all-gather and peer exchange agree: %s" % ok2b)
+    ok2 = ok2 and ok2b
+
+    # 3. auto stop and a one-sided stop request on the sharded fit
+    import ctypes as C
+    from lisp_mcmc_b200 import _lib
+    wa = D.walker_create_sharded(g, "datasets", seed=6)
+    wa.adaptive_steps(n=5000)                       # :auto :prob-settle, temperature 10
+    tha, pra, nva = wa.trace(7001)
+    wa.close()
+    ok4 = True
+    if rank == 0:
+        w2 = workloads.make_walker(g, seed=6, device=local_rank)
+        w2.adaptive_steps(n=5000)
+        th2, pr2, nv2 = w2.trace(7001)
+        w2.close()
+        ok4 = np.array_equal(nva, nv2) and np.array_equal(tha, th2, equal_nan=True)
+        print("sharded :prob-settle run equals the one-GPU run: %s (steps per chain %d..%d)" % (ok4, nva.min(), nva.max()))
+    ws = D.walker_create_sharded(g, "datasets", seed=7)
+    L = _lib.lib()
+    cfgc = _lib.AdaptCfg(30000, 10.0, _lib.AUTO_NONE, _lib.OPT_COVARIANCE, 0, 0, 0)
+    ws._chk(L.mfit_run_begin(ws._h, C.byref(cfgc), None, None, None, 0))
+    done, fin = C.c_int64(), C.c_int()
+    ws._chk(L.mfit_run_advance(ws._h, 100, C.byref(done), C.byref(fin)))
+    if rank == world - 1:
+        ws.request_stop()                           # (setf mfit-walker-estop t) on one rank only
+    ws._chk(L.mfit_run_advance(ws._h, 5000, C.byref(done), C.byref(fin)))
+    steps = torch.tensor([done.value, fin.value], dtype=torch.int64).cuda()
+    allsteps = [torch.empty_like(steps) for _ in range(world)]
+    dist.all_gather(allsteps, steps)
+    ok5 = all(torch.equal(allsteps[0], p) for p in allsteps) and int(allsteps[0][0]) < 5000 and int(allsteps[0][1]) == 1
+    ws.close()
+    if rank == 0:
+        print("one-sided stop request: every rank left after %d more steps, finished=%d: %s" % (int(allsteps[0][0]), int(allsteps[0][1]), ok5))
+    ok2 = ok2 and ok4 and ok5
+
     # every rank must hold the same chains after a dataset-sharded run
     t = torch.from_numpy(prg[:, 0].copy()).cuda()
     parts = [torch.empty_like(t) for _ in range(world)]
