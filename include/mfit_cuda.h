@@ -290,6 +290,11 @@ int mfit_eval_mode_tiles(mfit_ctx* ctx, int64_t* tiles4);
  * chain count), 1 = one group (also what mfit_set_timing(1) implies: an overlapped kernel cannot be timed with events),
  * 2..4 = that many whenever possible. */
 int mfit_set_groups(mfit_ctx* ctx, int n_groups);
+/* Small problems (one walker or a few, up to a few thousand points, built-in families and priors -- the reference's own
+ * mcmc-fit use, test.lisp:14-24) advance many steps per kernel launch, one CTA per chain, instead of three launches per
+ * step.  0 = automatic (by size), 1 = never, 2 = whenever the problem qualifies (any size).  Results agree with the
+ * three-launch path to rounding (the likelihood sum is formed in another fixed order), not bit for bit. */
+int mfit_set_small_path(mfit_ctx* ctx, int mode);
 /* write > L2 bytes on the ctx stream (bench hygiene between timed steps) */
 int mfit_flush_l2(mfit_ctx* ctx);
 /* the cudaStream_t the context enqueues on */

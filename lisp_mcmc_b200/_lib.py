@@ -87,6 +87,7 @@ SIGNATURES = {
     "mfit_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "mfit_eval_kernel_time": (C.c_int, [C.c_void_p, _dp, _lp]),
     "mfit_eval_mode_tiles": (C.c_int, [C.c_void_p, _lp]),
+    "mfit_set_small_path": (C.c_int, [C.c_void_p, C.c_int]),
     "mfit_set_groups": (C.c_int, [C.c_void_p, C.c_int]),
     "mfit_flush_l2": (C.c_int, [C.c_void_p]),
     "mfit_stream_handle": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

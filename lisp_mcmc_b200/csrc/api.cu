@@ -171,6 +171,7 @@ struct mfit_ctx {
   cudaEvent_t fork_ev = nullptr, join_ev[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
   int n_groups = 1;
   int groups_override = 0;              // mfit_set_groups: 0 = automatic
+  int small_mode = 0;                   // mfit_set_small_path: 0 = automatic, 1 = never, 2 = whenever the problem qualifies
 
   // chains
   bool have_chains = false;
@@ -989,6 +990,32 @@ int run_begin(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long lon
   return 0;
 }
 
+// Small problems (the reference's own: one walker, a thousand points) are launch-bound on the three-launch step: when every
+// data set is shared data with a built-in family and a built-in prior, and a step is only a few microseconds of
+// arithmetic, the chains advance many steps per launch, one CTA per chain (chain_kernels.cu k_run_small).
+bool small_path(mfit_ctx* ctx, MfitSmallArgs& a) {
+  if (ctx->small_mode == 1 || ctx->sharded || ctx->timing || ctx->D > MFIT_SMALL_MAX_DS) return false;
+  if (const char* e = getenv("MFIT_SMALL_PATH")) { if (atoi(e) == 0) return false; }
+  long long n_total = 0;
+  memset(&a, 0, sizeof a);
+  a.n_ds = ctx->D;
+  for (int d = 0; d < ctx->D; d++) {
+    const Dataset& s = ctx->ds[d];
+    if (!s.owned || s.W_pc > 0 || s.family == MFIT_FAM_SEXPR || s.family < 0 || s.ll_kind > MFIT_LL_POISSON || s.prior_kind == 2 ||
+        s.x_dims != 1 || s.x_is_sequence)
+      return false;
+    MfitSmallDs& o = a.d[d];
+    o.x = s.x; o.y = s.y; o.yw = s.yw; o.w = s.w; o.c = s.c;
+    o.n = s.n;
+    o.family = s.family; o.degree = s.degree; o.ll_kind = s.ll_kind;
+    for (int k = 0; k < 16; k++) o.idx[k] = s.idx[k];
+    n_total += s.n;
+  }
+  if (ctx->small_mode == 2) return true;
+  // a CTA of 128 threads per chain: worth it while the large kernel's step (three launches, ~25 us) is mostly latency
+  return n_total <= 4096 && (long long)ctx->ch.W * n_total <= (1LL << 24) && ctx->ch.W <= 8192;
+}
+
 // up to `budget` more MH steps of the open run; returns when they have completed on the device
 int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* finished) {
   MfitChains& c = ctx->ch;
@@ -1043,6 +1070,23 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
     if (grp[g].w0 > c.W) grp[g].w0 = c.W;
   }
   bool stop_seen = false;
+  MfitSmallArgs small_args;
+  if (small_path(ctx, small_args)) {
+    // many steps per launch; between launches the host looks at the stop flag and (blocking, it is cheap here) at the chains left
+    const long long chunk = 512;
+    while (t < t_end && !all_done) {
+      if (ctx->stop.load()) break;  // mfit-walker-estop, :904
+      const long long k = t_end - t < chunk ? t_end - t : chunk;
+      r.t = t;
+      mfit_launch_run_small(c, r, small_args, k, ctx->stream);
+      mfit_launch_count_active(c, ctx->active_dev, ctx->stream);
+      ctx->launches += 2;
+      CU(cudaMemcpyAsync(ctx->active_host, ctx->active_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      t += k;
+      if (ctx->active_host[0] == 0) all_done = true;
+    }
+  } else
   for (; t < t_end && !all_done; t++) {
     // mfit-walker-estop, :904.  With the data sets sharded over ranks every step holds a collective, so all ranks must
     // leave the loop at the same t: the flag is then only looked at -- all-gathered -- at the poll boundaries below.
@@ -1055,6 +1099,7 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
       MfitChains cg = c;
       cg.w0 = G.w0;
       cg.w1 = G.w1;
+      cg.group = g;
       rc = eval_all(ctx, ctx->ws, c, c.prop_theta, c.done, g, G.cb0, G.n_cb, G.st);
       if (rc) return rc;
       if (ctx->sharded) {
@@ -1657,6 +1702,7 @@ int mfit_chains_init(mfit_ctx* ctx, const double* theta0, int64_t W, uint64_t se
   CA(cur_theta, P * st) CA(cur_prob, st) CA(prop_theta, P * st) CA(best_theta, P * st) CA(best_prob, st)
   CA(L, (size_t)P * P * st) CA(loop_i, st) CA(shutting, st) CA(done, st) CA(need_reest, st) CA(temperature, st)
   CA(length, st) CA(age, st) CA(rows, st) CA(reset_index, st) CA(steps_run, st) CA(l_updates, st)
+  CA(reest_list, st) CA(reest_count, 8)
 #undef CA
   (void)D;
   {
@@ -2406,6 +2452,12 @@ int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches) {
   if (!ctx) return MFIT_ERR_ARG;
   if (seconds) *seconds = ctx->eval_seconds;
   if (launches) *launches = ctx->eval_launches;
+  return 0;
+}
+
+int mfit_set_small_path(mfit_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 2) return MFIT_ERR_ARG;
+  ctx->small_mode = mode;
   return 0;
 }
 

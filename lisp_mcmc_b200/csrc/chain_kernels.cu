@@ -266,6 +266,15 @@ __device__ void scale_L(const MfitChains& c, long long w, double s) {  // scale-
   }
 }
 
+// a chain that needs its l-matrix re-estimated goes on its group's work list: k_reest is launched with a small fixed grid
+// that walks the list (a CTA per chain of the whole set, nearly all of which return at once, cost 50 us per step at 131072 chains)
+__device__ __forceinline__ void flag_reest(const MfitChains& c, long long w) {
+  c.need_reest[w] = 1;
+  if (c.group < 0) return;   // k_run_small re-estimates in place
+  const int k = atomicAdd(c.reest_count + c.group, 1);
+  c.reest_list[c.w0 + k] = (int)w;
+}
+
 // ------------------------------------------------------------------ top of loop iteration: shutdown test + proposal
 // Chains flagged need_reest are skipped here: k_reest rebuilds their l-matrix first and then runs this body itself.
 __device__ void pre_body(const MfitChains& c, const MfitRunCfg& r, long long w) {
@@ -369,7 +378,7 @@ __device__ void post_body(const MfitChains& c, const MfitRunCfg& r, long long w)
       if (enter) {
         if (!have) acc_window(c, w, 200, &cnt, &len);
         if (acc_gt(cnt, len, 0.2f) && acc_lt(cnt, len, 0.4f))
-          c.need_reest[w] = 1;
+          flag_reest(c, w);
         else if (acc_lt(cnt, len, 0.2f)) {
           scale_L(c, w, 0.1);
           c.l_updates[w] += 1;
@@ -471,7 +480,7 @@ __global__ void k_init_run(const MfitChains c, const MfitRunCfg r, const double*
       }
       long long cnt, len;
       acc_window(c, w, 100, &cnt, &len);
-      if (!(c.length[w] < r.S || acc_lt(cnt, len, 0.1f))) c.need_reest[w] = 1;  // :897-901
+      if (!(c.length[w] < r.S || acc_lt(cnt, len, 0.1f))) flag_reest(c, w);  // :897-901
     }
   } else if (r.mode == MFIT_MODE_MANY) {
     c.loop_i[w] = 0;
@@ -577,15 +586,128 @@ __device__ int reest_body(const MfitChains& c, const MfitRunCfg& r, long long w,
 
 // r.t is the take-step index of the step that FOLLOWS the re-estimate; the chain's proposal for it is made here
 __global__ void k_reest(const MfitChains c, const MfitRunCfg r) {
-  const long long w = c.w0 + blockIdx.x;
-  if (w >= c.w1 || !c.need_reest[w]) return;
   extern __shared__ __align__(16) unsigned char sm[];
-  const int upd = reest_body(c, r, w, sm);
-  __syncthreads();  // l-matrix writes of every thread are visible to thread 0
-  if (threadIdx.x == 0) {
-    c.need_reest[w] = 0;
-    c.l_updates[w] += upd;
-    pre_body(c, r, w);
+  const int n = *(volatile int*)(c.reest_count + c.group);
+  for (int k = blockIdx.x; k < n; k += gridDim.x) {   // the order of the list does not matter: chains do not interact
+    const long long w = c.reest_list[c.w0 + k];
+    const int upd = reest_body(c, r, w, sm);
+    __syncthreads();  // l-matrix writes of every thread are visible to thread 0
+    if (threadIdx.x == 0) {
+      c.need_reest[w] = 0;
+      c.l_updates[w] += upd;
+      pre_body(c, r, w);
+    }
+    __syncthreads();  // shared memory is reused by the next chain
+  }
+  if (threadIdx.x == 0) {  // the last CTA out empties the list for the next step
+    __threadfence();
+    if (atomicAdd(c.reest_count + 4 + c.group, 1) == (int)gridDim.x - 1) {
+      c.reest_count[c.group] = 0;
+      c.reest_count[4 + c.group] = 0;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ small problems: many steps per launch
+// The reference's own use (mcmc-fit: ONE walker, a few hundred to a few thousand points, test.lisp:14-24) is three kernel
+// launches per step on the path above -- launch latency, not arithmetic.  Here a CTA owns a chain for `steps` steps: its
+// threads stride over the points of every data set (built-in families, libdevice math, explicit fma as in the likelihood
+// kernels), a fixed-shape tree adds the per-thread sums, thread 0 runs the very same post_body / pre_body as the three-launch
+// path and the CTA the same reest_body.  Only the order of the likelihood sum differs from the large kernel's (thread-strided
+// instead of segment-wise): within 1e-12 of the oracle like it, not bit-identical to it.
+__device__ double small_model(const MfitSmallDs& s, const double* th, double x) {
+  switch (s.family) {
+    case MFIT_FAM_POLY: {
+      double r = th[s.idx[s.degree]];
+      for (int k = s.degree - 1; k >= 0; k--) r = fma(x, r, th[s.idx[k]]);
+      return r;
+    }
+    case MFIT_FAM_EXPO: return fma(th[s.idx[0]], exp(th[s.idx[1]] * x), th[s.idx[2]]);
+    case MFIT_FAM_SINUS: return fma(th[s.idx[0]], sin(fma(th[s.idx[1]], x, th[s.idx[2]])), th[s.idx[3]]);
+    case MFIT_FAM_LORENTZ: {
+      const double g2 = th[s.idx[2]] * th[s.idx[2]], d = x - th[s.idx[1]];
+      return (th[s.idx[0]] * g2) / fma(d, d, g2) + th[s.idx[3]];
+    }
+    case MFIT_FAM_GAUSS_LIN: {
+      const double z = (x - th[s.idx[1]]) * (1.0 / th[s.idx[2]]);
+      return fma(th[s.idx[0]], exp(-0.5 * (z * z)), fma(th[s.idx[4]], x, th[s.idx[3]]));
+    }
+    default: {  // MFIT_FAM_NV_MULTI, degree = K dips: scale_1..K mu_1..K sigma bg0
+      const int K = s.degree;
+      const double g2 = th[s.idx[2 * K]] * th[s.idx[2 * K]];
+      double r = th[s.idx[2 * K + 1]];
+      for (int k = 0; k < K; k++) {
+        const double d = x - th[s.idx[K + k]];
+        r -= (th[s.idx[k]] * g2) / fma(d, d, g2);
+      }
+      return r;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MFIT_SMALL_THREADS)
+k_run_small(MfitChains c, MfitRunCfg r, const __grid_constant__ MfitSmallArgs a, long long steps) {
+  extern __shared__ __align__(16) unsigned char sm[];   // reest_body's scratch
+  __shared__ double s_th[MFIT_MAX_P];
+  __shared__ double s_red[MFIT_SMALL_THREADS];
+  __shared__ int s_go;
+  const long long w = c.w0 + blockIdx.x;
+  if (w >= c.w1) return;
+  const int tid = threadIdx.x;
+  c.group = -1;   // re-estimates are done right here: no work list
+  for (long long s = 0; s < steps; s++, r.t++) {
+    if (tid == 0) s_go = c.done[w] ? 0 : 1;
+    for (int i = tid; i < c.P; i += MFIT_SMALL_THREADS) s_th[i] = c.prop_theta[(size_t)i * c.stride + w];
+    __syncthreads();
+    if (!s_go) break;
+    // walker-make-step :1067-1070 for the proposal: every data set's log-likelihood
+    for (int d = 0; d < a.n_ds; d++) {
+      const MfitSmallDs& ds = a.d[d];
+      double acc = 0.0;
+      for (long long i = tid; i < ds.n; i += MFIT_SMALL_THREADS) {
+        const double f = small_model(ds, s_th, ds.x[i]);
+        if (ds.ll_kind == MFIT_LL_NORMAL) {
+          const double rr = fma(-f, ds.w[i], ds.yw[i]);
+          acc = fma(rr, rr, acc);
+        } else if (ds.ll_kind == MFIT_LL_NORMAL_CUTOFF) {
+          const double rr = (ds.y[i] - f) * ds.w[i];
+          double t = fma(-0.5 * rr, rr, ds.c[i]);
+          t = (t > -5000.0) ? t : ((t != t) ? t : -5000.0);
+          acc = acc + t;
+        } else
+          acc = acc + fma(ds.y[i], log(f), -f);
+      }
+      s_red[tid] = acc;
+      __syncthreads();
+      for (int h = MFIT_SMALL_THREADS / 2; h > 0; h >>= 1) {  // fixed-shape tree
+        if (tid < h) s_red[tid] = s_red[tid] + s_red[tid + h];
+        __syncthreads();
+      }
+      if (tid == 0) {
+        const MfitDsDev& dd = c.ds[d];
+        const double sum = s_red[0];
+        ll_ptr(c, d)[w] = ds.n == 0 ? 0.0 : dd.ll_kind == MFIT_LL_NORMAL ? dd.cst + (-0.5 * sum) : dd.ll_kind == MFIT_LL_NORMAL_CUTOFF ? sum : dd.cst + sum;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      __threadfence_block();
+      post_body(c, r, w);   // accept / push / adapt of this step (may flag a re-estimate)
+    }
+    __syncthreads();
+    MfitRunCfg rn = r;
+    rn.t = r.t + 1;
+    if (c.need_reest[w]) {  // CTA-uniform: written by thread 0 before the barrier
+      const int upd = reest_body(c, rn, w, sm);
+      __syncthreads();
+      if (tid == 0) {
+        c.need_reest[w] = 0;
+        c.l_updates[w] += upd;
+      }
+    }
+    if (tid == 0) pre_body(c, rn, w);   // shutdown test + proposal of the next step
+    __syncthreads();
   }
 }
 
@@ -1112,6 +1234,16 @@ inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) /
 void mfit_launch_init_run(const MfitChains& c, const MfitRunCfg& r, const double* l_shared, cudaStream_t st) {
   k_init_run<<<blocks_for(c.W, 128), 128, 0, st>>>(c, r, l_shared);
 }
+void mfit_launch_run_small(const MfitChains& c, const MfitRunCfg& r, const MfitSmallArgs& a, long long steps, cudaStream_t st) {
+  const int P = c.P;
+  size_t smem = sizeof(double) * (P + 2 * (size_t)P * P) + sizeof(int) * (size_t)(r.S + 1);
+  static size_t configured = 0;
+  if (smem > 40 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(k_run_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  k_run_small<<<(unsigned)(c.w1 - c.w0), MFIT_SMALL_THREADS, smem, st>>>(c, r, a, steps);
+}
 void mfit_launch_reest(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st) {
   const int P = c.P;
   size_t smem = sizeof(double) * (P + 2 * (size_t)P * P) + sizeof(int) * (size_t)(r.S + 1);
@@ -1120,7 +1252,8 @@ void mfit_launch_reest(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st
     cudaFuncSetAttribute(k_reest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  k_reest<<<(unsigned)(c.w1 - c.w0), 128, smem, st>>>(c, r);
+  const long long chains = c.w1 - c.w0;
+  k_reest<<<(unsigned)(chains < 296 ? (chains > 0 ? chains : 1) : 296), 128, smem, st>>>(c, r);
 }
 void mfit_launch_pre(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st) {
   k_pre<<<blocks_for(c.W, 128), 128, 0, st>>>(c, r);

@@ -40,6 +40,9 @@ struct MfitChains {
   unsigned char* shutting;
   unsigned char* done;  // also the eval kernel's skip mask
   unsigned char* need_reest;
+  int* reest_list;      // [stride] chains flagged for a re-estimate, the launch range [w0, w1) fills its own stretch from w0 on
+  int* reest_count;     // [4 + 4] per chain group: entries in its stretch; finished CTAs of its k_reest launch
+  int group;            // chain group of this launch (0 when the chains advance as one)
   double* temperature;
   long long* length;    // walker-length
   long long* age;       // walker-age
@@ -85,7 +88,22 @@ struct MfitRunCfg {
   double sr_scale;      // sample-region initial scale
 };
 
+// ---- small problems: K Metropolis-Hastings steps per launch, one CTA per chain (chain_kernels.cu k_run_small)
+#define MFIT_SMALL_MAX_DS 8
+#define MFIT_SMALL_THREADS 128
+struct MfitSmallDs {       // one shared-data set with a built-in family
+  const double *x, *y, *yw, *w, *c;
+  long long n;
+  int family, degree, ll_kind;
+  int idx[16];             // family slot -> shared parameter index
+};
+struct MfitSmallArgs {
+  int n_ds;
+  MfitSmallDs d[MFIT_SMALL_MAX_DS];
+};
+
 #ifdef __CUDACC__
+void mfit_launch_run_small(const MfitChains& c, const MfitRunCfg& r, const MfitSmallArgs& a, long long steps, cudaStream_t st);
 void mfit_launch_init_run(const MfitChains& c, const MfitRunCfg& r, const double* l_shared, cudaStream_t st);
 void mfit_launch_reest(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st);
 void mfit_launch_pre(const MfitChains& c, const MfitRunCfg& r, cudaStream_t st);

@@ -425,6 +425,10 @@ class Walker:
         self._chk(self._L.mfit_segment_geometry(self._h, int(d), C.byref(t), C.byref(n)))
         return t.value, n.value
 
+    def set_small_path(self, mode):
+        """0 = automatic, 1 = never, 2 = whenever the problem qualifies: many steps per launch for small problems (mfit_set_small_path)"""
+        self._chk(self._L.mfit_set_small_path(self._h, int(mode)))
+
     def set_groups(self, n_groups):
         """0 = automatic, 1 / 2 = advance the chains as one / two groups on separate streams (mfit_set_groups)"""
         self._chk(self._L.mfit_set_groups(self._h, int(n_groups)))

@@ -268,7 +268,16 @@ def _compare_chain(orc, cfg, w, z, u, run_oracle, chains, bit_exact=True):
     return compared
 
 
-def test_many_steps_injected_stream_identical_to_oracle(orc):
+@pytest.fixture(params=["many-steps-per-launch", "three-launch"])
+def step_path(request, monkeypatch):
+    """Small problems advance many steps per launch, one CTA per chain (k_run_small); MFIT_SMALL_PATH=0 keeps them on the
+    three-launch step of the large path.  The tests that take this fixture hold both against the oracle."""
+    if request.param == "three-launch":
+        monkeypatch.setenv("MFIT_SMALL_PATH", "0")
+    return request.param
+
+
+def test_many_steps_injected_stream_identical_to_oracle(orc, step_path):
     cfg = workloads.c2(W=40, N=1500)
     w = workloads.make_walker(cfg)
     n = 400
@@ -282,7 +291,7 @@ def test_many_steps_injected_stream_identical_to_oracle(orc):
 
 
 @pytest.mark.parametrize("auto", [None, "prob-settle"])
-def test_adaptive_steps_full_injected_stream_identical_to_oracle(orc, auto):
+def test_adaptive_steps_full_injected_stream_identical_to_oracle(orc, auto, step_path):
     """walker-adaptive-steps-full end to end: temperature schedule, 200-step acceptance windows, x0.1 / x1.9 rescales,
     forward-step covariance + Cholesky re-estimates, shutdown tail and (auto) the :prob-settle stop."""
     cfg = workloads.c2(W=12, N=400)
@@ -299,7 +308,7 @@ def test_adaptive_steps_full_injected_stream_identical_to_oracle(orc, auto):
     w.close()
 
 
-def test_adaptive_with_bounds_prior_lorentzian_c1(orc):
+def test_adaptive_with_bounds_prior_lorentzian_c1(orc, step_path):
     cfg = workloads.c1(W=3)
     cfg["theta0"] = cfg["theta0"] * np.array([[1.0], [1.02], [0.97]])
     w = workloads.make_walker(cfg)
@@ -312,7 +321,7 @@ def test_adaptive_with_bounds_prior_lorentzian_c1(orc):
     w.close()
 
 
-def test_sample_region_and_force_take_step(orc):
+def test_sample_region_and_force_take_step(orc, step_path):
     cfg = workloads.c2(W=5, N=300)
     w = workloads.make_walker(cfg)
     rng = np.random.default_rng(14)
@@ -330,7 +339,7 @@ def test_sample_region_and_force_take_step(orc):
     w.close()
 
 
-def test_resume_reestimates_l_matrix_from_existing_walk(orc):
+def test_resume_reestimates_l_matrix_from_existing_walk(orc, step_path):
     """calling walker-adaptive-steps again on a long walk derives the l-matrix from it (:896-901)"""
     cfg = workloads.c2(W=4, N=300)
     w = workloads.make_walker(cfg)
@@ -352,7 +361,7 @@ def test_resume_reestimates_l_matrix_from_existing_walk(orc):
     w.close()
 
 
-def test_philox_run_replays_through_oracle(orc):
+def test_philox_run_replays_through_oracle(orc, step_path):
     """on-device Philox4x32-10 proposals: export the stream the device drew and replay it through the oracle"""
     cfg = workloads.c2(W=6, N=500)
     w = workloads.make_walker(cfg, seed=1234, chain_id_base=77)
@@ -1018,3 +1027,42 @@ def test_log_poisson_spelled_as_a_lambda_is_the_builtin_kind(orc):
     ow = oracle_walker(orc, cfg2)
     assert rel_err(p2, np.array([ow.logp(t)[0] for t in cfg["theta0"]])) < TOL
     w1.close(); w2.close()
+
+
+@pytest.mark.parametrize("name,degree,ll", [("poly", 3, "log-liklihood-normal-cutoff"), ("sinus", 0, "log-poisson"),
+                                            ("expo", 0, "log-liklihood-normal"), ("nv_multi", 2, "log-liklihood-normal"),
+                                            ("lorentz", 0, "log-liklihood-normal")])
+def test_small_path_every_family_identical_to_oracle(orc, name, degree, ll):
+    """k_run_small (many steps per launch, one CTA per chain) for each built-in family and likelihood kind, bounds prior
+    included: parameter traces bit-identical to the oracle under injected streams, log p within tolerance"""
+    cfg = _family_cfg(name, 700, 9, ll, degree, seed=5)
+    if name == "sinus":
+        cfg["theta0"][:, 3] = np.abs(cfg["theta0"][:, 3]) + 25.0
+    k0 = cfg["keys"][0]
+    cfg["log_prior"] = [[(k0, -1e3, 1e3)]]
+    w = workloads.make_walker(cfg)
+    w.set_small_path(2)
+    n = 700
+    rng = np.random.default_rng(41)
+    z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    w.adaptive_steps_full(n=n, temperature=10, auto=None, z=z, u=u, max_steps=n)
+    _compare_chain(orc, cfg, w, z, u,
+                   lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_NONE, z=zz, u=uu, max_steps=n),
+                   range(9), bit_exact=False)
+    assert np.all(w.stats()["steps_this_run"] == n)
+    w.close()
+
+
+def test_small_path_global_fit_and_auto_stop(orc):
+    """two data sets sharing a parameter, :auto :prob-settle: the chains leave the loop on their own, at the oracle's step"""
+    cfg = workloads.c4(W=6, D=2, N=500)
+    cfg["log_prior"] = [[("sigma", 9.0, 20.0)], "log-prior-flat"]
+    w = workloads.make_walker(cfg)
+    w.set_small_path(2)
+    n = 6000
+    rng = np.random.default_rng(43)
+    z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    w.adaptive_steps_full(n=n, temperature=10, auto="prob-settle", z=z, u=u)
+    _compare_chain(orc, cfg, w, z, u,
+                   lambda ow, zz, uu: ow.adaptive_steps_full(n=n, temperature=10, auto=orc.AUTO_PROB_SETTLE, z=zz, u=uu), range(6))
+    w.close()
