@@ -595,7 +595,6 @@ __device__ __forceinline__ void mfit_ring_row(const Model& m, const double* xs, 
 template <class Model, int LL>
 __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double* smem, long long n_pad) {
   constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
-  constexpr int NARR = MfitTerm<LL>::NARR;
   const int S = a.ring_stages;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   double* ring = smem + 3 * n_pad + (size_t)wib * S * n_pad;
