@@ -271,6 +271,45 @@ int mfit_dataset_owners(mfit_ctx* ctx, const int32_t* owner);
 /* gather chain-sharded traces on every rank: local (W_local x take x (P+1)) -> out (n_ranks x ...) */
 int mfit_nccl_allgather_f64(mfit_ctx* ctx, const double* local_host, int64_t count, double* out_host);
 
+/* ---- several GPUs behind ONE handle (one host thread per GPU inside the library; no Python, no MPI) -----------------
+ * What the Lisp host's :devices uses.  The walker set is sharded over the listed devices of this box either by CHAINS
+ * (MFIT_SHARD_CHAINS: W chains split contiguously, every data set on every GPU, Philox streams keyed by global chain id,
+ * nothing crosses GPUs during a run) or by DATA SETS (MFIT_SHARD_DATASETS: data set d lives on GPU d mod n, every GPU holds
+ * all chains, the per-data-set terms travel through the peer exchange above).  Either way results are bit-identical to one
+ * GPU.  Calls mirror the single-GPU ones; per-chain outputs come back in global chain order. */
+typedef struct mfit_multi mfit_multi;
+enum { MFIT_SHARD_CHAINS = 0, MFIT_SHARD_DATASETS = 1 };
+int mfit_multi_create(int n_gpus, const int* dev_ids, int shard_mode, mfit_multi** out);
+void mfit_multi_destroy(mfit_multi* m);
+const char* mfit_multi_last_error(mfit_multi* m);
+int mfit_multi_size(mfit_multi* m);
+mfit_ctx* mfit_multi_ctx(mfit_multi* m, int rank);          /* the per-GPU context (read-only uses: launch counts, stats) */
+int64_t mfit_multi_launch_count(mfit_multi* m);             /* kernels launched by all of its contexts */
+/* MFIT_SHARD_DATASETS: chains the exchange blocks are sized for (default 131072; 32 bytes x chains x data sets per GPU x
+ * GPUs on every GPU).  Before mfit_multi_problem_define. */
+int mfit_multi_reserve(mfit_multi* m, int64_t max_chains);
+int mfit_multi_problem_define(mfit_multi* m, int n_datasets, int n_params);
+int mfit_multi_dataset_upload(mfit_multi* m, int d, const double* x, int x_dims, const double* y, const double* sigma, int64_t n);
+int mfit_multi_model_builtin(mfit_multi* m, int d, int family, int degree, const int32_t* param_index, int n_idx);
+int mfit_multi_model_sexpr(mfit_multi* m, int d, const char* lambda_text, const char* const* key_names, int n_keys);
+int mfit_multi_likelihood_set(mfit_multi* m, int d, int kind);
+int mfit_multi_likelihood_sexpr(mfit_multi* m, int d, const char* lambda_text);
+int mfit_multi_prior_flat(mfit_multi* m, int d);
+int mfit_multi_prior_bounds(mfit_multi* m, int d, int n, const int32_t* idx, const double* lo, const double* hi);
+int mfit_multi_prior_sexpr(mfit_multi* m, int d, const char* lambda_text, const char* const* key_names, int n_keys);
+int mfit_multi_eval_logp(mfit_multi* m, const double* theta, int64_t W, double* prob, double* ll, double* lp);
+int mfit_multi_chains_init(mfit_multi* m, const double* theta0, int64_t W, uint64_t seed, int64_t trace_capacity);
+int mfit_multi_run_adaptive(mfit_multi* m, const mfit_adapt_cfg* cfg, const double* l_matrix, int64_t* steps_launched);
+int mfit_multi_run_begin(mfit_multi* m, const mfit_adapt_cfg* cfg, const double* l_matrix);
+int mfit_multi_run_advance(mfit_multi* m, int64_t max_steps, int64_t* steps_done, int* finished);
+int mfit_multi_run_many_steps(mfit_multi* m, int64_t n, const double* l_matrix);
+int mfit_multi_request_stop(mfit_multi* m);
+int mfit_multi_trace_read(mfit_multi* m, int64_t take, double* theta, double* prob, int64_t* n_valid);
+int mfit_multi_stats_read(mfit_multi* m, mfit_chain_stats* stats /* W */);
+int mfit_multi_best_read(mfit_multi* m, double* theta, double* prob);
+int mfit_multi_last_read(mfit_multi* m, double* theta, double* prob);
+int mfit_multi_l_matrix_read(mfit_multi* m, double* l /* W x P x P */);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------
  * FP64 DFMA issue peak of the device this ctx is bound to, measured live (FLOP/s, 2 per DFMA), and the
  * DFMA-equivalent cost of the FP64 transcendentals used by the model families. */

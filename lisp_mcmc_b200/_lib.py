@@ -13,6 +13,7 @@ LL_NORMAL, LL_NORMAL_CUTOFF, LL_POISSON, LL_USER = 0, 1, 2, 3
 AUTO_NONE, AUTO_PROB_SETTLE = 0, 1
 OPT_COVARIANCE, OPT_BEST_VALUE = 0, 1
 FIT_MOST_LIKELY, FIT_MEDIAN = 0, 1
+SHARD_CHAINS, SHARD_DATASETS = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -83,6 +84,34 @@ SIGNATURES = {
     "mfit_peer_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mfit_dataset_owners": (C.c_int, [C.c_void_p, _ip]),
     "mfit_nccl_allgather_f64": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp]),
+    "mfit_multi_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "mfit_multi_destroy": (None, [C.c_void_p]),
+    "mfit_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "mfit_multi_size": (C.c_int, [C.c_void_p]),
+    "mfit_multi_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "mfit_multi_launch_count": (C.c_int64, [C.c_void_p]),
+    "mfit_multi_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
+    "mfit_multi_problem_define": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mfit_multi_dataset_upload": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int64]),
+    "mfit_multi_model_builtin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_int]),
+    "mfit_multi_model_sexpr": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, _cpp, C.c_int]),
+    "mfit_multi_likelihood_set": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "mfit_multi_likelihood_sexpr": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "mfit_multi_prior_flat": (C.c_int, [C.c_void_p, C.c_int]),
+    "mfit_multi_prior_bounds": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _ip, _dp, _dp]),
+    "mfit_multi_prior_sexpr": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, _cpp, C.c_int]),
+    "mfit_multi_eval_logp": (C.c_int, [C.c_void_p, _dp, C.c_int64, _dp, _dp, _dp]),
+    "mfit_multi_chains_init": (C.c_int, [C.c_void_p, _dp, C.c_int64, C.c_uint64, C.c_int64]),
+    "mfit_multi_run_adaptive": (C.c_int, [C.c_void_p, C.POINTER(AdaptCfg), _dp, _lp]),
+    "mfit_multi_run_begin": (C.c_int, [C.c_void_p, C.POINTER(AdaptCfg), _dp]),
+    "mfit_multi_run_advance": (C.c_int, [C.c_void_p, C.c_int64, _lp, C.POINTER(C.c_int)]),
+    "mfit_multi_run_many_steps": (C.c_int, [C.c_void_p, C.c_int64, _dp]),
+    "mfit_multi_request_stop": (C.c_int, [C.c_void_p]),
+    "mfit_multi_trace_read": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _lp]),
+    "mfit_multi_stats_read": (C.c_int, [C.c_void_p, C.POINTER(ChainStats)]),
+    "mfit_multi_best_read": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "mfit_multi_last_read": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "mfit_multi_l_matrix_read": (C.c_int, [C.c_void_p, _dp]),
     "mfit_measure_fp64": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp]),
     "mfit_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "mfit_eval_kernel_time": (C.c_int, [C.c_void_p, _dp, _lp]),

@@ -1138,7 +1138,10 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
         if (rc) return fail(ctx, rc, "%s", er.c_str());
       } else {
         // peers without a communicator (all ranks in one process, mfit_multi_*): the active count is the same on every
-        // rank by construction; a stop request is agreed on through the owner's shared word, one boundary ahead
+        // rank by construction; a stop request is agreed on through the owner's shared word, TWO boundaries ahead: a peer's
+        // host may already have passed its test of boundary b + 1 when rank 0 writes at boundary b (its blocking read of
+        // boundary b needs only the GPU work rank 0 enqueued BEFORE this test), but it cannot have reached boundary b + 2,
+        // whose predecessor's read waits for steps rank 0 enqueues after the write
         CU(cudaMemsetAsync(ctx->xflag_dev, 0xff, sizeof(int) * 2 * R, ctx->stream));   // "-1": other ranks neither done nor stopping
         mfit_launch_count_active(c, ctx->xflag_dev + 2 * ctx->rank, ctx->stream);
         const long long boundary = (t + 1) / poll_every;
@@ -1146,7 +1149,7 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
         if (ctx->stop_at) {
           long long at = ctx->stop_at->load();
           if (at < 0 && ctx->rank == 0 && ctx->stop.load()) {
-            long long want = boundary + 1;
+            long long want = boundary + 2;
             ctx->stop_at->compare_exchange_strong(at, want);
             at = ctx->stop_at->load();
           }
@@ -1207,6 +1210,9 @@ int run_loop(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long long
 }
 
 }  // namespace
+
+// multi.cpp: the word through which the contexts of one process agree on the step at which a stop request takes effect
+void mfit_internal_stop_word(mfit_ctx* ctx, std::atomic<long long>* word) { if (ctx) ctx->stop_at = word; }
 
 // =================================================================================== C ABI
 extern "C" {

@@ -14,8 +14,12 @@ struct MfitPrepBlock {
 };
 
 #ifdef __cplusplus
+#include <atomic>
 #include <string>
 #include <vector>
+
+// api.cu, for multi.cpp
+void mfit_internal_stop_word(mfit_ctx* ctx, std::atomic<long long>* word);
 
 // eval_builtin.cu
 const void* mfit_builtin_eval_kernel(int family, int degree, int ll);

@@ -15,6 +15,10 @@
 ;;;;   :log-prior      :log-prior-flat | ((:key lo hi) ...)  ; = (prior-bounds-let (...) bounds-total)
 ;;;;                   | (gpu-lambda (params data) (prior-bounds-let (...) (+ bounds-total ...)))
 ;;;;
+;;;; Several GPUs: (walker-create ... :devices '(0 1 2 3) :shard :chains) shards the W chains over the listed GPUs of this
+;;;; box, :shard :datasets puts data set d of a global fit on GPU d mod n; both inside the library (mfit_multi_*, one host
+;;;; thread per GPU), bit-identical to one GPU.  The reference has one worker (`mapc`, nv-specific.lisp:58-66).
+;;;;
 ;;;; A gpu-walker holds W independent chains (a "walker set", nv-specific.lisp:58-66) that share
 ;;;; :function / :data / :log-liklihood / :log-prior; W = 1 is exactly one reference walker.
 ;;;;
@@ -103,6 +107,48 @@
   (ctx :pointer) (d :int) (take :int64) (which-solution :int) (x-fit :pointer) (n-fit :int) (y-fit :pointer)
   (y-max :pointer) (y-min :pointer) (params :pointer) (n-distinct :pointer))
 
+;;; several GPUs behind one handle (csrc/multi.cpp): the twins of the calls above
+(cffi:defcfun ("mfit_multi_create" %multi-create) :int (n-gpus :int) (dev-ids :pointer) (shard-mode :int) (out :pointer))
+(cffi:defcfun ("mfit_multi_destroy" %multi-destroy) :void (m :pointer))
+(cffi:defcfun ("mfit_multi_last_error" %multi-last-error) :string (m :pointer))
+(cffi:defcfun ("mfit_multi_reserve" %multi-reserve) :int (m :pointer) (max-chains :int64))
+(cffi:defcfun ("mfit_multi_problem_define" %multi-problem-define) :int (m :pointer) (n-datasets :int) (n-params :int))
+(cffi:defcfun ("mfit_multi_dataset_upload" %multi-dataset-upload) :int
+  (m :pointer) (d :int) (x :pointer) (x-dims :int) (y :pointer) (sigma :pointer) (n :int64))
+(cffi:defcfun ("mfit_multi_model_builtin" %multi-model-builtin) :int
+  (m :pointer) (d :int) (family :int) (degree :int) (param-index :pointer) (n-idx :int))
+(cffi:defcfun ("mfit_multi_model_sexpr" %multi-model-sexpr) :int
+  (m :pointer) (d :int) (lambda-text :string) (key-names :pointer) (n-keys :int))
+(cffi:defcfun ("mfit_multi_likelihood_set" %multi-likelihood-set) :int (m :pointer) (d :int) (kind :int))
+(cffi:defcfun ("mfit_multi_likelihood_sexpr" %multi-likelihood-sexpr) :int (m :pointer) (d :int) (lambda-text :string))
+(cffi:defcfun ("mfit_multi_prior_flat" %multi-prior-flat) :int (m :pointer) (d :int))
+(cffi:defcfun ("mfit_multi_prior_bounds" %multi-prior-bounds) :int
+  (m :pointer) (d :int) (n :int) (idx :pointer) (lo :pointer) (hi :pointer))
+(cffi:defcfun ("mfit_multi_prior_sexpr" %multi-prior-sexpr) :int
+  (m :pointer) (d :int) (lambda-text :string) (key-names :pointer) (n-keys :int))
+(cffi:defcfun ("mfit_multi_chains_init" %multi-chains-init) :int
+  (m :pointer) (theta0 :pointer) (w :int64) (seed :uint64) (trace-capacity :int64))
+(cffi:defcfun ("mfit_multi_run_begin" %multi-run-begin) :int (m :pointer) (cfg :pointer) (l-matrix :pointer))
+(cffi:defcfun ("mfit_multi_run_advance" %multi-run-advance) :int
+  (m :pointer) (max-steps :int64) (steps-done :pointer) (finished :pointer))
+(cffi:defcfun ("mfit_multi_run_many_steps" %multi-run-many-steps) :int (m :pointer) (n :int64) (l-matrix :pointer))
+(cffi:defcfun ("mfit_multi_request_stop" %multi-request-stop) :int (m :pointer))
+(cffi:defcfun ("mfit_multi_trace_read" %multi-trace-read) :int
+  (m :pointer) (take :int64) (theta :pointer) (prob :pointer) (n-valid :pointer))
+(cffi:defcfun ("mfit_multi_stats_read" %multi-stats-read) :int (m :pointer) (stats :pointer))
+(cffi:defcfun ("mfit_multi_best_read" %multi-best-read) :int (m :pointer) (theta :pointer) (prob :pointer))
+(cffi:defcfun ("mfit_multi_last_read" %multi-last-read) :int (m :pointer) (theta :pointer) (prob :pointer))
+
+(defvar *multi* nil "True while the handle in use is an mfit_multi (a walker made with :devices).")
+(defmacro api (single multi handle &rest args)
+  "Call SINGLE on a one-GPU context or its twin MULTI on a several-GPU handle."
+  `(if *multi* (,multi ,handle ,@args) (,single ,handle ,@args)))
+(defmacro with-walker-api ((walker) &body body)
+  `(let ((*multi* (gpu-walker-multi ,walker))) ,@body))
+(defun one-gpu-only (walker what)
+  (when (gpu-walker-multi walker)
+    (error "~a reads or edits the walk on one GPU; create the walker with :device for it" what)))
+
 (defmacro with-traps-masked (&body body)
   #+sbcl `(sb-int:with-float-traps-masked (:invalid :divide-by-zero :overflow :inexact :underflow) ,@body)
   #-sbcl `(progn ,@body))
@@ -115,7 +161,7 @@
   "Signal a Lisp error for a negative mfit_status (the reference signals `error` in clean-data :819,:825)."
   (let ((rc (gensym)))
     `(let ((,rc (with-traps-masked ,form)))
-       (unless (zerop ,rc) (error 'mfit-error :code ,rc :message (%last-error ,ctx)))
+       (unless (zerop ,rc) (error 'mfit-error :code ,rc :message (api %last-error %multi-last-error ,ctx)))
        ,rc)))
 
 ;;; ---------------------------------------------------------------------------------- plugin-slot descriptors
@@ -189,7 +235,7 @@ translates it to CUDA C and NVRTC compiles it for sm_100a; it never runs in Lisp
           (cffi:foreign-string-to-lisp out))))))
 
 ;;; ---------------------------------------------------------------------------------- walker
-(defstruct gpu-walker ctx function param-keys n-walkers n-params data data-error log-liklihood log-prior)
+(defstruct gpu-walker ctx multi function param-keys n-walkers n-params data data-error log-liklihood log-prior)
 
 (defvar mfit-walker-estop nil "Set to T (e.g. from another thread) to stop a run between launches, :860.")
 
@@ -228,8 +274,8 @@ stddev list -- read it with (elt error k), k a literal."
 
 (defun set-likelihood (ctx d ll)
   (if (gpu-fn-p ll)
-      (chk ctx (%likelihood-sexpr ctx d (gpu-fn-text ll)))
-      (chk ctx (%likelihood-set ctx d (likelihood-kind ll)))))
+      (chk ctx (api %likelihood-sexpr %multi-likelihood-sexpr ctx d (gpu-fn-text ll)))
+      (chk ctx (api %likelihood-set %multi-likelihood-set ctx d (likelihood-kind ll)))))
 
 (defun set-function (ctx d f keys)
   (etypecase f
@@ -238,25 +284,28 @@ stddev list -- read it with (elt error k), k a literal."
                         (gpu-family-keys f))))
        (cffi:with-foreign-object (ip :int32 (max 1 (length idx)))
          (loop for v in idx for i from 0 do (setf (cffi:mem-aref ip :int32 i) v))
-         (chk ctx (%model-builtin ctx d (cdr (assoc (gpu-family-name f) *families*)) (gpu-family-degree f) ip (length idx))))))
-    (gpu-fn (with-key-names (kp keys) (chk ctx (%model-sexpr ctx d (gpu-fn-text f) kp (length keys)))))))
+         (chk ctx (api %model-builtin %multi-model-builtin ctx d (cdr (assoc (gpu-family-name f) *families*)) (gpu-family-degree f) ip (length idx))))))
+    (gpu-fn (with-key-names (kp keys) (chk ctx (api %model-sexpr %multi-model-sexpr ctx d (gpu-fn-text f) kp (length keys)))))))
 
 (defun set-prior (ctx d p keys)
-  (cond ((or (null p) (eq p :log-prior-flat)) (chk ctx (%prior-flat ctx d)))
-        ((gpu-fn-p p) (with-key-names (kp keys) (chk ctx (%prior-sexpr ctx d (gpu-fn-text p) kp (length keys)))))
+  (cond ((or (null p) (eq p :log-prior-flat)) (chk ctx (api %prior-flat %multi-prior-flat ctx d)))
+        ((gpu-fn-p p) (with-key-names (kp keys) (chk ctx (api %prior-sexpr %multi-prior-sexpr ctx d (gpu-fn-text p) kp (length keys)))))
         (t (let ((n (length p)))                   ; ((:key lo hi) ...), a missing key reads 0d0 like getf :353
              (cffi:with-foreign-object (ip :int32 (max 1 n))
                (loop for (k) in p for i from 0 do (setf (cffi:mem-aref ip :int32 i) (or (position k keys) -1)))
                (with-doubles (lo (mapcar #'second p))
                  (with-doubles (hi (mapcar #'third p))
-                   (chk ctx (%prior-bounds ctx d n ip lo hi)))))))))
+                   (chk ctx (api %prior-bounds %multi-prior-bounds ctx d n ip lo hi)))))))))
 
 (defun walker-create (&key function data params data-error log-liklihood log-prior param-bounds
-                        (n-walkers 1) theta0 (seed 0) (device 0) (trace-capacity 0))
+                        (n-walkers 1) theta0 (seed 0) (device 0) devices (shard :chains) (trace-capacity 0))
   "walker-create :1132-1163.  GPU-side extras: N-WALKERS chains start at PARAMS, or THETA0 (a list of W value
-lists in :params order) gives each chain its own start; SEED keys the Philox streams."
+lists in :params order) gives each chain its own start; SEED keys the Philox streams.  DEVICES (a list of GPU ordinals)
+shards the walker set over several GPUs of this box inside the library: SHARD :chains splits the chains, :datasets puts
+data set d of a global fit on GPU d mod n; results are bit-identical to one GPU."
   (declare (ignorable param-bounds))
-  (let* ((function (force-list function))
+  (let* ((*multi* (and devices t))
+         (function (force-list function))
          (d-count (length function))
          (data (clean-data data d-count))
          (data-error (clean-data-error (if data-error data-error 1) data))
@@ -268,11 +317,17 @@ lists in :params order) gives each chain its own start; SEED keys the Philox str
          (theta0 (or theta0 (make-list n-walkers :initial-element (plist-values params))))
          (w (length theta0))
          ctx)
-    (cffi:with-foreign-object (out :pointer)
-      (let ((rc (with-traps-masked (%ctx-create device (cffi:null-pointer) out))))
-        (unless (zerop rc) (error 'mfit-error :code rc :message (%last-error (cffi:null-pointer)))))
+    (cffi:with-foreign-objects ((out :pointer) (ids :int (max 1 (length devices))))
+      (loop for g in devices for i from 0 do (setf (cffi:mem-aref ids :int i) g))
+      (let ((rc (with-traps-masked
+                  (if *multi*
+                      (%multi-create (length devices) ids (ecase shard (:chains 0) (:datasets 1)) out)
+                      (%ctx-create device (cffi:null-pointer) out)))))
+        (unless (zerop rc)
+          (error 'mfit-error :code rc :message (api %last-error %multi-last-error (cffi:null-pointer)))))
       (setf ctx (cffi:mem-ref out :pointer)))
-    (chk ctx (%problem-define ctx d-count p))
+    (when (and *multi* (eq shard :datasets)) (chk ctx (%multi-reserve ctx (max w 4096))))
+    (chk ctx (api %problem-define %multi-problem-define ctx d-count p))
     (loop for d from 0 for f in function for set in data for e in data-error do
       (let* ((xs (first set))
              ;; multi-dimensional inputs (:1137): every x is itself a sequence -> component-major for the device
@@ -283,15 +338,17 @@ lists in :params order) gives each chain its own start; SEED keys the Philox str
         (with-doubles (x flat)
           (with-doubles (y (second set))
             (with-doubles (s e)
-              (chk ctx (if (plusp x-dims)
-                           (%dataset-upload-xd ctx d x x-dims y s (length (second set)))
-                           (%dataset-upload ctx d x y s (length (second set)))))))))
+              (chk ctx (cond (*multi* (%multi-dataset-upload ctx d x x-dims y s (length (second set))))
+                             ((plusp x-dims) (%dataset-upload-xd ctx d x x-dims y s (length (second set))))
+                             (t (%dataset-upload ctx d x y s (length (second set))))))))))
       (set-function ctx d f keys)
       (set-likelihood ctx d (nth d ll))
       (set-prior ctx d (nth d lp) keys))
     (with-doubles (t0 (apply #'append theta0))               ; W x P row-major
-      (chk ctx (%chains-init ctx t0 w seed 0 trace-capacity)))
-    (make-gpu-walker :ctx ctx :function function :param-keys keys :n-walkers w :n-params p :data data
+      (chk ctx (if *multi*
+                   (%multi-chains-init ctx t0 w seed trace-capacity)
+                   (%chains-init ctx t0 w seed 0 trace-capacity))))
+    (make-gpu-walker :ctx ctx :multi *multi* :function function :param-keys keys :n-walkers w :n-params p :data data
                      :data-error data-error :log-liklihood ll :log-prior lp)))
 
 (defun walker-set-create (&key function x ys params data-error log-liklihood log-prior (seed 0) (device 0) (trace-capacity 0))
@@ -319,7 +376,9 @@ a number or one list as long as X.  The walkers advance together on the GPU, one
                      :data (list x ys) :data-error sigma :log-liklihood (list log-liklihood) :log-prior (list log-prior))))
 
 (defun walker-free (walker)
-  (when (gpu-walker-ctx walker) (%ctx-destroy (gpu-walker-ctx walker)) (setf (gpu-walker-ctx walker) nil)))
+  (when (gpu-walker-ctx walker)
+    (if (gpu-walker-multi walker) (%multi-destroy (gpu-walker-ctx walker)) (%ctx-destroy (gpu-walker-ctx walker)))
+    (setf (gpu-walker-ctx walker) nil)))
 
 (defun walker-adaptive-steps-full (walker &key (n 100000) (temperature 1d3) (auto :prob-settle)
                                             (sampling-optimization :covariance) max-walker-length l-matrix
@@ -327,7 +386,7 @@ a number or one list as long as X.  The walkers advance together on the GPU, one
   "walker-adaptive-steps-full :862-942, all chains advanced together on the GPU.  The run is issued in slices of
 POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slope-settle is not supported."
   (setf mfit-walker-estop nil)
-  (let ((ctx (gpu-walker-ctx walker)) (p (gpu-walker-n-params walker)))
+  (let ((ctx (gpu-walker-ctx walker)) (p (gpu-walker-n-params walker)) (*multi* (gpu-walker-multi walker)))
     (cffi:with-foreign-objects ((cfg '(:struct adapt-cfg)) (done :int64) (fin :int))
       (cffi:with-foreign-slots ((n temperature auto-mode sampling-optimization max-walker-length greedy reserved)
                                 cfg (:struct adapt-cfg))
@@ -336,10 +395,12 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
               sampling-optimization (ecase sampling-optimization (:covariance 0) (:best-value 1))
               max-walker-length (if max-walker-length (floor max-walker-length) 0) greedy 0 reserved 0))
       (with-doubles (lm (when l-matrix (loop for i below p append (loop for j below p collect (aref l-matrix i j)))))
-        (chk ctx (%run-begin ctx cfg lm (cffi:null-pointer) (cffi:null-pointer) 0)))
+        (chk ctx (if *multi*
+                     (%multi-run-begin ctx cfg lm)
+                     (%run-begin ctx cfg lm (cffi:null-pointer) (cffi:null-pointer) 0))))
       (loop
-        (when mfit-walker-estop (%request-stop ctx))
-        (chk ctx (%run-advance ctx poll-every done fin))
+        (when mfit-walker-estop (api %request-stop %multi-request-stop ctx))
+        (chk ctx (api %run-advance %multi-run-advance ctx poll-every done fin))
         (unless (zerop (cffi:mem-ref fin :int)) (return)))))
   walker)
 
@@ -347,22 +408,27 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
   (walker-adaptive-steps-full walker :n n :temperature 10 :auto :prob-settle))
 
 (defun walker-many-steps (walker n l-matrix)                                            ; :849-853
-  (let ((ctx (gpu-walker-ctx walker)) (p (gpu-walker-n-params walker)))
+  (let ((ctx (gpu-walker-ctx walker)) (p (gpu-walker-n-params walker)) (*multi* (gpu-walker-multi walker)))
     (with-doubles (lm (loop for i below p append (loop for j below p collect (aref l-matrix i j))))
-      (chk ctx (%run-many-steps ctx n lm (cffi:null-pointer) (cffi:null-pointer) 0))))
+      (chk ctx (if *multi*
+                   (%multi-run-many-steps ctx n lm)
+                   (%run-many-steps ctx n lm (cffi:null-pointer) (cffi:null-pointer) 0)))))
   walker)
 
 (defun walker-sample-region (walker &optional (initial-scale 1d-3))                     ; :949-969
+  (one-gpu-only walker "walker-sample-region")
   (chk (gpu-walker-ctx walker)
        (%run-sample-region (gpu-walker-ctx walker) (coerce initial-scale 'double-float) (cffi:null-pointer) 0))
   walker)
 
 (defun walker-force-take-step (walker)                                                  ; :1124-1129
+  (one-gpu-only walker "walker-force-take-step")
   (chk (gpu-walker-ctx walker) (%force-take-step (gpu-walker-ctx walker)))
   walker)
 
 (defun read-step (walker reader chain)
-  (let* ((ctx (gpu-walker-ctx walker)) (w (gpu-walker-n-walkers walker)) (p (gpu-walker-n-params walker)))
+  (let* ((ctx (gpu-walker-ctx walker)) (w (gpu-walker-n-walkers walker)) (p (gpu-walker-n-params walker))
+         (*multi* (gpu-walker-multi walker)))
     (cffi:with-foreign-objects ((th :double (* w p)) (pr :double w))
       (chk ctx (funcall reader ctx th pr))
       (values (loop for k in (gpu-walker-param-keys walker) for i from 0
@@ -372,12 +438,15 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
 (defun walker-get (walker &key (get :steps) take param (chain 0))
   "walker-get :487-543 for the modes that read the trace of one CHAIN, newest first."
   (let* ((ctx (gpu-walker-ctx walker)) (w (gpu-walker-n-walkers walker)) (p (gpu-walker-n-params walker))
-         (keys (gpu-walker-param-keys walker)))
+         (keys (gpu-walker-param-keys walker)) (*multi* (gpu-walker-multi walker))
+         (best-reader (if *multi* #'%multi-best-read #'%best-read))
+         (last-reader (if *multi* #'%multi-last-read #'%last-read)))
     (ecase get
-      (:most-likely-params (values (read-step walker #'%best-read chain)))
-      (:most-likely-step (read-step walker #'%best-read chain))
-      (:last-step (read-step walker #'%last-read chain))
+      (:most-likely-params (values (read-step walker best-reader chain)))
+      (:most-likely-step (read-step walker best-reader chain))
+      (:last-step (read-step walker last-reader chain))
       ((:median-params :stddev-params :covariance-matrix :l-matrix)      ; :516-543, computed on the device for all chains
+       (one-gpu-only walker "walker-get's trace analytics")
        (let ((take (or take 1000000000)) (null (cffi:null-pointer)))
          (cffi:with-foreign-objects ((med :double (* w p)) (mat :double (* w p p)))
            (ecase get
@@ -394,11 +463,11 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
                   (dotimes (i p a) (dotimes (j p) (setf (aref a i j) (mat-at i j)))))))))))
       ((:steps :params :param :log-liklihoods :acceptance)
        (let ((take (or take (cffi:with-foreign-object (st '(:struct chain-stats) w)
-                              (chk ctx (%stats-read ctx st))
+                              (chk ctx (api %stats-read %multi-stats-read ctx st))
                               (cffi:foreign-slot-value (cffi:mem-aptr st '(:struct chain-stats) chain)
                                                        '(:struct chain-stats) 'length)))))
          (cffi:with-foreign-objects ((th :double (* w take p)) (pr :double (* w take)) (nv :int64 w))
-           (chk ctx (%trace-read ctx take th pr nv))
+           (chk ctx (api %trace-read %multi-trace-read ctx take th pr nv))
            (let* ((m (cffi:mem-aref nv :int64 chain))
                   (probs (loop for r below m collect (cffi:mem-aref pr :double (+ (* chain take) r))))
                   (rows (loop for r below m
@@ -415,6 +484,7 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
                                           (which-solution :most-likely) x-shift y-shift (chain 0))
   "walker-get-data-and-fit :1231-1255 for one CHAIN -> (x-fit max-ys min-ys y-fit x-data y-data params).  The fit
 curve and the envelope over the best 66 % of the walk are evaluated on the device for every chain at once."
+  (one-gpu-only walker "walker-get-data-and-fit")
   (let* ((ctx (gpu-walker-ctx walker)) (w (gpu-walker-n-walkers walker)) (p (gpu-walker-n-params walker))
          (data (elt (gpu-walker-data walker) fn-number))
          (x-data (elt data x-column)) (y-data (elt data y-column))
@@ -486,6 +556,7 @@ curve and the envelope over the best 66 % of the walk are evaluated on the devic
 
 (defun walker-modify (walker &key (modify :keep-walks) burn-number keep-number)
   "walker-modify :546-580 on the device, every chain: :burn-walks :keep-walks :reset :reset-to-most-likely."
+  (one-gpu-only walker "walker-modify")
   (let ((ctx (gpu-walker-ctx walker)))
     (chk ctx (ecase modify
                (:burn-walks (%walker-modify ctx 1 burn-number))

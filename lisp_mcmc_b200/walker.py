@@ -191,13 +191,57 @@ def shard_datasets(D, world):
     return [d % world for d in range(D)]
 
 
+class _MultiABI:
+    """The single-GPU entry points a Walker calls, answered by their mfit_multi_* twins (csrc/multi.cpp): the handle is an
+    mfit_multi*, the walker set is sharded over the GPUs of this box inside the library (one host thread per GPU), per-chain
+    results come back in global chain order.  Calls without a twin (analytics, envelope, restore, injected streams) raise."""
+
+    def __init__(self, L):
+        self._lib = L
+
+    def __getattr__(self, name):
+        L = self._lib
+        if name == "mfit_ctx_destroy":
+            return L.mfit_multi_destroy
+        if name == "mfit_last_error":
+            return L.mfit_multi_last_error
+        if name in ("mfit_dataset_upload",):
+            return lambda h, d, x, y, s, n: L.mfit_multi_dataset_upload(h, d, x, 0, y, s, n)
+        if name == "mfit_dataset_upload_xd":
+            return L.mfit_multi_dataset_upload
+        if name == "mfit_chains_init":
+            return lambda h, th, W, seed, base, cap: L.mfit_multi_chains_init(h, th, W, seed, cap)
+
+        def no_streams(z, u):
+            if z is not None or u is not None:
+                raise NotImplementedError("injected z/u streams are a single-GPU test facility")
+        if name == "mfit_run_adaptive":
+            return lambda h, cfg, lm, z, u, ns, out: (no_streams(z, u), L.mfit_multi_run_adaptive(h, cfg, lm, out))[1]
+        if name == "mfit_run_begin":
+            return lambda h, cfg, lm, z, u, ns: (no_streams(z, u), L.mfit_multi_run_begin(h, cfg, lm))[1]
+        if name == "mfit_run_many_steps":
+            return lambda h, n, lm, z, u, ns: (no_streams(z, u), L.mfit_multi_run_many_steps(h, n, lm))[1]
+        twin = "mfit_multi_" + name[len("mfit_"):]
+        if name.startswith("mfit_") and twin in _lib.SIGNATURES:
+            return getattr(L, twin)
+        raise NotImplementedError("%s has no multi-GPU twin: use one GPU (device=) for it" % name)
+
+
 class Walker:
-    """W chains on one GPU behind the reference's walker interface."""
+    """W chains on one GPU -- or, with devices=[...], sharded over several GPUs of this box behind one handle -- behind
+    the reference's walker interface."""
 
     def __init__(self, function, data, params, data_error=None, log_liklihood=None, log_prior=None,
                  n_walkers=None, theta0=None, seed=0, device=0, chain_id_base=0, trace_capacity=0,
-                 nccl=None, dataset_owners=None, stream=None, per_walker=None, peers=None):
+                 nccl=None, dataset_owners=None, stream=None, per_walker=None, peers=None, devices=None, shard="chains"):
         L = _lib.lib()
+        self.devices = list(devices) if devices is not None else None
+        if self.devices is not None:
+            if nccl is not None or peers is not None or dataset_owners is not None or per_walker is not None or chain_id_base:
+                raise ValueError("devices=[...] shards inside the library: nccl / peers / dataset_owners / per_walker / chain_id_base do not apply")
+            if shard not in ("chains", "datasets"):
+                raise ValueError("shard must be 'chains' or 'datasets'")
+            L = _MultiABI(L)
         self._L = L
         self.function = force_list(function)                        # :1142
         D = len(self.function)
@@ -229,7 +273,12 @@ class Walker:
         self._keys_c = _lib.keys_array(self.param_keys)
 
         h = C.c_void_p()
-        rc = L.mfit_ctx_create(device, stream, C.byref(h))
+        if self.devices is not None:
+            ids = (C.c_int * len(self.devices))(*self.devices)
+            rc = _lib.lib().mfit_multi_create(len(self.devices), ids, _lib.SHARD_DATASETS if shard == "datasets" else _lib.SHARD_CHAINS,
+                                              C.byref(h))
+        else:
+            rc = L.mfit_ctx_create(device, stream, C.byref(h))
         if rc != 0:
             raise _lib.MfitError(rc, L.mfit_last_error(None).decode())
         self._h = h

@@ -453,6 +453,46 @@ def test_multi_gpu_sharding_is_bit_identical():
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_one_handle_multi_gpu_is_bit_identical():
+    """mfit_multi_* (several GPUs behind one handle, one host thread per GPU inside the library; what the Lisp host's
+    :devices uses): chains / data sets sharded over every GPU of the box equal the one-GPU traces bit for bit, :prob-settle
+    and an in-flight stop request end on the same step everywhere (tests/mgpu/multi_check.py); skipped on a one-GPU box"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "mgpu", "multi_check.py"), str(min(n, 8))],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_one_handle_on_one_gpu_equals_the_plain_context():
+    """the same fan-out with a single device listed (worker thread, offsets, twins of every call) == mfit_ctx calls"""
+    cfg = workloads.c2(W=11, N=700)
+    wm = workloads.make_walker(cfg, seed=4, devices=[0], shard="chains")
+    w0 = workloads.make_walker(cfg, seed=4)
+    for w in (wm, w0):
+        w.adaptive_steps_full(n=250, temperature=10, auto=None)
+    for a, b in zip(wm.trace(300), w0.trace(300)):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(wm.l_matrix(), w0.l_matrix())
+    sm, s0 = wm.stats(), w0.stats()
+    assert all(np.array_equal(sm[k], s0[k]) for k in sm.dtype.names)
+    with pytest.raises(NotImplementedError):
+        wm.analytics(100)
+    g = workloads.c4(W=6, D=3, N=500)
+    gm = workloads.make_walker(g, seed=2, devices=[0], shard="datasets")
+    g0 = workloads.make_walker(g, seed=2)
+    for a, b in zip(gm.make_step(g["theta0"]), g0.make_step(g["theta0"])):
+        assert np.array_equal(a, b, equal_nan=True)
+    for w in (wm, w0, gm, g0):
+        w.close()
+
+
 def _nth_percentile(n, seq):
     """nth-percentile :1493-1504 restated: position n (len-1)/100; a fractional position gives the MEAN of its two
     neighbours (not an interpolation)"""
