@@ -560,7 +560,26 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
   // ... and the chains' own y rows go through a per-warp TMA ring when two CTAs per SM still fit with at least two
   // stages (mfit_perchain_ring): rows of up to ~800 points; longer ones are read straight into registers
   a.ring_stages = 0;
-  if (staged && a.n > 0 && getenv("MFIT_NO_PC_RING") == nullptr) {
+  // Rows of up to 512 points (the reference's spectra have a few hundred, nv-specific.lisp:50-66), built-in family, no
+  // cutoff constants: the register form (mfit_reg_row) -- four-warp CTAs, three per SM, every lane keeps the x and 1/sigma
+  // of its points in registers across all the chains its warp evaluates.
+  int reg_form = 0;       // 0 = no, 2 = rows up to 256 points, 3 = up to 512
+  int threads = MFIT_PC_THREADS;
+  if (staged && a.n > 0 && a.n <= 512 && s.family != MFIT_FAM_SEXPR && s.ll_kind != MFIT_LL_NORMAL_CUTOFF && s.ll_kind != MFIT_LL_USER &&
+      getenv("MFIT_NO_PC_RING") == nullptr && getenv("MFIT_NO_PC_REG") == nullptr) {
+    reg_form = a.n <= 256 ? 2 : 3;
+    threads = MFIT_PCR_THREADS;
+    const size_t warps = MFIT_PCR_THREADS / 32, slot = reg_form == 2 ? 256 : 512, budget = 74 * 1024;  // three CTAs per SM
+    for (int S = 4; S >= 2 && a.ring_stages == 0; S--) {
+      const size_t need = smem_pc + warps * S * slot * sizeof(double) + warps * S * sizeof(unsigned long long);
+      if (need <= budget) {
+        a.ring_stages = S;
+        smem_pc = need;
+      }
+    }
+    if (a.ring_stages == 0) { reg_form = 0; threads = MFIT_PC_THREADS; }
+  }
+  if (!reg_form && staged && a.n > 0 && getenv("MFIT_NO_PC_RING") == nullptr) {
     const char* bk = getenv("MFIT_PC_RING_BUDGET_KB");  // experiments: shared memory one CTA may take (default: two CTAs per SM)
     const size_t warps = MFIT_PC_THREADS / 32, budget = (bk ? (size_t)atoi(bk) : 110) * 1024;
     for (int S = 3; S >= 2 && a.ring_stages == 0; S--) {
@@ -572,7 +591,7 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
     }
   }
   const void* fpc = s.family == MFIT_FAM_SEXPR ? (const void*)s.k_user_pc[s.ll_kind + (staged ? 3 : 0)]
-                                              : mfit_builtin_perchain_kernel(s.family, s.degree, s.ll_kind, staged);
+                                              : mfit_builtin_perchain_kernel(s.family, s.degree, s.ll_kind, reg_form ? reg_form : (int)staged);
   if (!fpc) return fail(ctx, MFIT_ERR_STATE, "no per-walker kernel for dataset %d (family %d degree %d)", d, s.family, s.degree);
   // built-in kernels are the same symbols for every context of the process: their attributes are set once per device
   std::unique_lock<std::mutex> shared_lock(ctx->shared->mu, std::defer_lock);
@@ -585,7 +604,7 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
     CU(cudaFuncSetAttribute(fpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CU(cudaFuncSetAttribute(fpc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0, sms = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc, MFIT_PC_THREADS, smem_pc));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fpc, threads, smem_pc));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     if (per_sm < 1) per_sm = 1;
     itp = resident.emplace(fpc, per_sm * sms).first;
@@ -593,10 +612,10 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
   const int resident_ctas = itp->second;
   if (!user_pc) shared_lock.unlock();
   const long long chains = (long long)a.n_cb * MFIT_CB;
-  const long long need = (chains + MFIT_PC_THREADS / 32 - 1) / (MFIT_PC_THREADS / 32);
+  const long long need = (chains + threads / 32 - 1) / (threads / 32);
   const unsigned gridp = (unsigned)(need < resident_ctas ? need : resident_ctas);
   void* argsp[] = {&a};
-  CU(cudaLaunchKernel(fpc, dim3(gridp > 0 ? gridp : 1), dim3(MFIT_PC_THREADS), argsp, smem_pc, st));
+  CU(cudaLaunchKernel(fpc, dim3(gridp > 0 ? gridp : 1), dim3(threads), argsp, smem_pc, st));
   ctx->launches++;
   return 0;
 }

@@ -28,8 +28,11 @@ static const void* const k_gauss[6] = MFIT_ROW(MfitGaussLin);
 static const void* const k_nv[][6] = {MFIT_ROW(MfitNvMulti<1>), MFIT_ROW(MfitNvMulti<2>), MFIT_ROW(MfitNvMulti<3>),
                                       MFIT_ROW(MfitNvMulti<4>)};
 
+// staged: 0 = rows read straight from global memory, 1 = shared x / sigma staged in shared memory, 2 / 3 = staged with the
+// register form for rows of up to 256 / 512 points (normal and poisson likelihoods only)
 const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int staged) {
   if (ll < 0 || ll > 2) return nullptr;
+  if (staged >= 2) return mfit_builtin_perchain_reg_kernel(family, degree, ll, staged == 2 ? 8 : 16);
   ll += staged ? 3 : 0;
   switch (family) {
     case MFIT_FAM_POLY: return (degree >= 0 && degree <= 7) ? k_poly[degree][ll] : nullptr;

@@ -515,6 +515,8 @@ __device__ __forceinline__ void mfit_eval_body(const MfitMultiArgs& ma) {
 #define MFIT_PC_STAGED_CTAS 2 /* min CTAs per SM the staged per-walker kernel is register-bounded for (3 or 4: 80 / 64 registers with spills, 20-35 % slower; 1: the compiler takes 200+ registers, one CTA per SM, 60 % slower) */
 #endif
 #define MFIT_PC_STAGE_MAX 2048 /* points up to which shared x / sigma vectors are staged in shared memory */
+#define MFIT_PCR_THREADS 128   /* threads per CTA of the register form of the staged kernel (mfit_reg_row): four warps, one per scheduler */
+#define MFIT_PCR_CTAS 3        /* its CTAs per SM (register bound: 168) */
 // STAGED: x and 1/sigma (and the cutoff constants) are one vector for all chains and sit in shared memory (xs, ws, cs
 // point there), so only the chain's own y values are streamed.
 template <class Model, int LL, bool SLOW, bool STAGED, class G>
@@ -583,6 +585,25 @@ __device__ __forceinline__ void mfit_ring_row(const Model& m, const double* xs, 
 #undef MFIT_RING_TERM
 }
 
+// The same row with the chain-invariant operands in REGISTERS: lane l of a warp always evaluates points l, l + 32, ...,
+// l + 32 (NPT - 1) of whatever chain the warp is on, so their x and 1/sigma are loaded once per warp (xr, wr) instead of
+// once per chain, and only y comes out of the ring: one LDS per evaluation instead of three (the shared-memory version
+// issued 46 warp-instructions per warp-point for 16 FP64 ones and ran at the pace of the issue ports, ncu
+// profiles/r02_perchain_kernel_ncu_raw.csv).  Fully unrolled and branch-free: NPT independent evaluations per lane;
+// slots beyond the row (bit u of `valid` clear) are evaluated at a real abscissa and dropped by a select.  Same
+// accumulator per row and same arithmetic as mfit_ring_row: the sums are bit-identical.
+template <class Model, int LL, int NPT, class G>
+__device__ __forceinline__ void mfit_reg_row(const Model& m, const double* xr, const double* wr, unsigned valid,
+                                             const double* row, int lane, double* acc, G& g) {
+#pragma unroll
+  for (int u = 0; u < NPT; u++) {
+    const double y = row[lane + 32 * u];
+    const double f = mfit_model_scalar<Model, false>(m, xr[u], g);
+    const double t = MfitTerm<LL>::template add<false>(acc[u & 3], f, y, wr[MfitTerm<LL>::NARR > 2 ? u : 0], 0.0, g);
+    acc[u & 3] = ((valid >> u) & 1u) ? t : acc[u & 3];
+  }
+}
+
 // STAGED with a ring (a.ring_stages = S >= 2): the chain's own y row -- the only per-chain data here -- is fetched by the
 // TMA engine (cp.async.bulk, one request per row) into a per-warp ring of S rows in shared memory, S - 1 rows ahead of the
 // one being evaluated.  A warp that reads its rows straight into registers alternates between waiting for memory and
@@ -592,13 +613,16 @@ __device__ __forceinline__ void mfit_ring_row(const Model& m, const double* xs, 
 // Shared memory: [x][1/sigma][c] (3 n_pad doubles, as for the register path), then [warp][stage][n_pad] doubles, then
 // [warp][stage] mbarriers.  Sums are formed exactly as in the register path (same four accumulators per lane, same
 // shuffle tree), so the two are bit-identical.
-template <class Model, int LL>
+// NPT > 0: the register form of the row (mfit_reg_row; rows of up to 32 NPT points, likelihoods without the cutoff
+// constants); ring slots are then 32 NPT doubles apart so that the unrolled reads stay inside the ring.
+template <class Model, int LL, int NPT = 0>
 __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double* smem, long long n_pad) {
   constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
   const int S = a.ring_stages;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  double* ring = smem + 3 * n_pad + (size_t)wib * S * n_pad;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 3 * n_pad + (size_t)nwarp * S * n_pad) + wib * S;
+  const long long slot_len = NPT > 0 ? 32 * NPT : n_pad;   // doubles per ring slot
+  double* ring = smem + 3 * n_pad + (size_t)wib * S * slot_len;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + 3 * n_pad + (size_t)nwarp * S * slot_len) + wib * S;
   const double* xs = smem;
   const double* ws = smem + n_pad;
   const double* cs = smem + 2 * n_pad;
@@ -614,16 +638,29 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       const long long ch = first + (long long)s * warps;
       if (ch < w_hi) {
         mfit_mbar_expect_tx(&bars[s], row_bytes);
-        mfit_tma_load_1d(ring + (size_t)s * n_pad, ybase + ch * a.pc_stride, row_bytes, &bars[s]);
+        mfit_tma_load_1d(ring + (size_t)s * slot_len, ybase + ch * a.pc_stride, row_bytes, &bars[s]);
       }
     }
+  const int n = (int)a.n;
+  double xr[NPT > 0 ? NPT : 1], wr[NPT > 0 ? NPT : 1];
+  unsigned valid = 0u;
+  if constexpr (NPT > 0) {
+#pragma unroll
+    for (int u = 0; u < NPT; u++) {
+      const int j = lane + 32 * u;
+      const bool ok = j < n;
+      const int jj = ok ? j : lane % n;   // a real abscissa for the slots beyond the row (their terms are dropped)
+      xr[u] = xs[jj];
+      wr[u] = MfitTerm<LL>::NARR > 2 ? ws[jj] : 0.0;
+      valid |= (ok ? 1u : 0u) << u;
+    }
+  }
   Model m_next;
   bool skip_next = false;
   if (first < w_hi) {
     m_next.load(a, first);
     skip_next = a.skip != nullptr && a.skip[first] != 0;
   }
-  const int n = (int)a.n;
   long long k = 0;
   for (long long chain = first; chain < w_hi; chain += warps, k++) {
     const int slot = (int)(k % S);
@@ -636,7 +673,7 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
     m.setup();
     const bool unguarded = !GUARDED || (MfitTerm<LL>::USES == 0 && m.safe(a));  // theta is warp-uniform
     mfit_mbar_wait(&bars[slot], (unsigned)((k / S) & 1));
-    const double* row = ring + (size_t)slot * n_pad;
+    const double* row = ring + (size_t)slot * slot_len;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     double sum = 0.0;
     bool redo = false;
@@ -644,8 +681,13 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       MfitGuard gd;
       gd.reset();
       MfitNoGuard ng;
-      if (unguarded) mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, ng);
-      else mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, gd);
+      if constexpr (NPT > 0) {
+        if (unguarded) mfit_reg_row<Model, LL, NPT>(m, xr, wr, valid, row, lane, acc, ng);
+        else mfit_reg_row<Model, LL, NPT>(m, xr, wr, valid, row, lane, acc, gd);
+      } else {
+        if (unguarded) mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, ng);
+        else mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, gd);
+      }
       redo = !unguarded && __any_sync(0xffffffffu, gd.tripped() ? 1 : 0) != 0;
       if (redo) sum = mfit_perchain_pass<Model, LL, true, true>(m, xs, row, ws, cs, a.n, lane, gd);  // rare: libdevice
     }
@@ -654,7 +696,7 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       const long long nxt = chain + (long long)S * warps;
       if (nxt < w_hi) {
         mfit_mbar_expect_tx(&bars[slot], row_bytes);
-        mfit_tma_load_1d(ring + (size_t)slot * n_pad, ybase + nxt * a.pc_stride, row_bytes, &bars[slot]);
+        mfit_tma_load_1d(ring + (size_t)slot * slot_len, ybase + nxt * a.pc_stride, row_bytes, &bars[slot]);
       }
     }
     if (!skip) {
@@ -668,7 +710,7 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
   }
 }
 
-template <class Model, int LL, bool STAGED>
+template <class Model, int LL, bool STAGED, int NPT = 0>
 __device__ __forceinline__ void mfit_eval_perchain_body_t(const MfitEvalArgs& a) {
   constexpr bool GUARDED = Model::GUARDED || MfitTerm<LL>::USES != 0;
   constexpr int NARR = MfitTerm<LL>::NARR;
@@ -684,13 +726,13 @@ __device__ __forceinline__ void mfit_eval_perchain_body_t(const MfitEvalArgs& a)
   if (STAGED && a.ring_stages > 0) {
     if ((threadIdx.x & 31) == 0) {  // every warp owns the mbarriers of its own ring
       unsigned long long* bars = reinterpret_cast<unsigned long long*>(
-                                     mfit_pc_smem + 3 * n_pad + (size_t)(blockDim.x >> 5) * a.ring_stages * n_pad) +
+                                     mfit_pc_smem + 3 * n_pad + (size_t)(blockDim.x >> 5) * a.ring_stages * (NPT > 0 ? 32 * NPT : n_pad)) +
                                  (threadIdx.x >> 5) * a.ring_stages;
       for (int s_ = 0; s_ < a.ring_stages; s_++) mfit_mbar_init(&bars[s_], 1);
       mfit_fence_mbar_init();
     }
     __syncthreads();
-    mfit_perchain_ring<Model, LL>(a, mfit_pc_smem, n_pad);
+    mfit_perchain_ring<Model, LL, NPT>(a, mfit_pc_smem, n_pad);
     return;
   }
   __syncthreads();

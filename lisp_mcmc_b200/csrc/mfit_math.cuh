@@ -4,7 +4,7 @@
 // pipe (ncu: profiles/), so what matters is the number of FP64 instructions per call, and that the other
 // instructions (integer, LDS, select) stay below one per FP64 instruction so that they hide in the pipe's shadow.
 // CUDA's libdevice spends 22 / 46 / 32 DFMA issue slots on exp / log / sin (measured, mfit_measure_fp64); these
-// spend 9 / 13 / 15 FP64 instructions: table-driven range reduction (Tang) with the tables staged in shared
+// spend 9 / 12 / 15 FP64 instructions: table-driven range reduction (Tang) with the tables staged in shared
 // memory, short polynomials with coefficients taken straight from constant memory, exponent arithmetic on the
 // integer pipe.  Accuracy is <= 2.4 ulp (tools/check_math.cpp measures it against long double), far inside the
 // 1e-12 relative tolerance on log-likelihoods.
@@ -31,6 +31,12 @@ static inline double mfit_mk(int hi, int lo) {
 }
 static inline unsigned mfit_umax(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+#ifndef MFIT_EXP_BITS
+#define MFIT_EXP_BITS 8
+#endif
+#ifndef MFIT_GAUSS_DEG
+#define MFIT_GAUSS_DEG 3
+#endif
 #else
 __device__ __forceinline__ int mfit_hi(double x) { return __double2hiint(x); }
 __device__ __forceinline__ int mfit_lo(double x) { return __double2loint(x); }
@@ -41,7 +47,23 @@ __device__ __forceinline__ unsigned mfit_umax(unsigned a, unsigned b) { return m
 // crossbar ran at 62 % next to a 68 % FP64 pipe).  Each table is therefore replicated so that every lane of a
 // crossbar phase reads its own banks: 16 copies of the 8-byte exp entries (a 64-bit load is served in two phases of
 // 16 lanes), 8 copies of the 16-byte log entries (four phases of 8 lanes).  Entry j of copy c sits at [j][c].
-__shared__ __align__(16) unsigned long long mfit_s_exp2[256 * 16];
+#ifndef MFIT_EXP_BITS
+#define MFIT_EXP_BITS 8     /* the exp table holds 2^(j / 2^B): 8 or 9 (mfit_math_tables.inc has both; 10 needs gen_math_tables.py to emit it) */
+#endif
+#ifndef MFIT_EXP_COPIES
+#define MFIT_EXP_COPIES 16  /* replication in shared memory: 16 = conflict-free */
+#endif
+#ifndef MFIT_GAUSS_DEG
+#define MFIT_GAUSS_DEG 3    /* degree of the Gaussian's polynomial in the reduced argument: 4 (< 1e-17) or 3.  3 with the 256-entry table
+                               is the shipped setting: every evaluation is one FP64 instruction shorter (C2 step 0.4115 -> 0.3921 ms,
+                               profiles/r02_ab_deg.txt) and the Gaussian factor -- a number in (0, 1] that is added to a background --
+                               carries a relative error of at most 5.6e-14 whose MEAN over the reduced argument is zero
+                               (tools/gen_math_tables.py: a biased fit adds up coherently over a peak).  On log-likelihoods that is
+                               far inside the 1e-12 they are held to and of the size of the reference's own summation error (2e-14 at
+                               C2's 100 000 points, profiles/r02_fullsize_parity.json).  Larger tables cost more in bank conflicts /
+                               shared memory than the lower degree buys (same file). */
+#endif
+__shared__ __align__(16) unsigned long long mfit_s_exp2[(1 << MFIT_EXP_BITS) * MFIT_EXP_COPIES];
 __shared__ __align__(16) double mfit_s_log[128 * 8 * 2];
 #endif
 
@@ -54,7 +76,7 @@ __shared__ __align__(16) double mfit_s_log[128 * 8 * 2];
 // every thread of the CTA calls this before the first __syncthreads of the kernel
 __device__ __forceinline__ void mfit_math_stage(int uses, int tid, int nthreads) {
   if (uses & MFIT_USES_EXP)
-    for (int i = tid; i < 256 * 16; i += nthreads) mfit_s_exp2[i] = mfit_c_exp2[i >> 4];
+    for (int i = tid; i < (1 << MFIT_EXP_BITS) * MFIT_EXP_COPIES; i += nthreads) mfit_s_exp2[i] = mfit_c_exp2[i / MFIT_EXP_COPIES];
   if (uses & MFIT_USES_LOG)
     for (int i = tid; i < 128 * 8; i += nthreads) {
       mfit_s_log[2 * i] = mfit_c_log[2 * (i >> 3)];
@@ -131,7 +153,13 @@ struct MfitFusedNoGuard : MfitNoGuard {
 __device__ __forceinline__ double mfit_exp2_256th(double tmp) {
   const int k = mfit_lo(tmp);
 #ifdef MFIT_HOST_TEST
-  const unsigned long long t = mfit_c_exp2[k & 255];
+  const unsigned long long t = mfit_c_exp2[k & ((1 << MFIT_EXP_BITS) - 1)];
+#elif MFIT_EXP_BITS != 8 || MFIT_EXP_COPIES != 16
+  // other table shapes (experiments): mask, then one multiply-add
+  const unsigned base = (unsigned)__cvta_generic_to_shared(mfit_s_exp2) + ((threadIdx.x & (MFIT_EXP_COPIES - 1u)) << 3);
+  unsigned long long t;
+  const unsigned addr = ((unsigned)k & ((1u << MFIT_EXP_BITS) - 1u)) * (8u * MFIT_EXP_COPIES) + base;
+  asm("ld.shared.u64 %0, [%1];" : "=l"(t) : "r"(addr));
 #else
   // address = table + 8 (lane mod 16) + 128 (k & 255) in ONE instruction: an integer dot product of the bytes of k
   // with (128, 0, 0, 0) masks, scales and adds the base at once (IDP.4A).  Left to itself the compiler shifts,
@@ -143,7 +171,7 @@ __device__ __forceinline__ double mfit_exp2_256th(double tmp) {
   const unsigned addr = __dp4a((unsigned)k, 0x80u, base);
   asm("ld.shared.u64 %0, [%1];" : "=l"(t) : "r"(addr));
 #endif
-  return mfit_mk((int)(t >> 32) + (k << 12), (int)t);
+  return mfit_mk((int)(t >> 32) + (k << (20 - MFIT_EXP_BITS)), (int)t);
 }
 
 // exp(x): 9 FP64 instructions
@@ -151,16 +179,32 @@ template <bool SLOW, class G>
 __device__ __forceinline__ double mfit_exp_t(double x, G& gd) {
   if (SLOW) return exp(x);
   if (G::ON) gd.see_exp((unsigned)mfit_hi(x) & 0x7fffffffu);
-  const double tmp = fma(x, MFIT_K_L2E256, MFIT_MAGIC);  // x 256/ln2
+  const double tmp = fma(x, MFIT_K_L2E256 * (double)(1 << (MFIT_EXP_BITS - 8)), MFIT_MAGIC);  // x 2^B/ln2
   const double kd = tmp - MFIT_MAGIC;
-  double r = fma(kd, -0x1.62e42fef00000p-9, x);          // ln2/256 in two pieces (Cody-Waite); the first is a 32-bit constant
-  r = fma(kd, -0x1.473de6af278edp-42, r);
+  double r = fma(kd, -0x1.62e42fef00000p-9 / (double)(1 << (MFIT_EXP_BITS - 8)), x);  // ln2/2^B in two pieces (Cody-Waite); the first is a 32-bit constant
+  r = fma(kd, -0x1.473de6af278edp-42 / (double)(1 << (MFIT_EXP_BITS - 8)), r);
   double p = fma(r, MFIT_K_EXN4, MFIT_K_EXN3);           // |r| <= ln2/512: degree 4 is good to 4e-17
   p = fma(r, p, 0.5);
   p = fma(r, p, 1.0);
   p = fma(r, p, 1.0);
   return mfit_exp2_256th(tmp) * p;
 }
+
+/* zs = z sqrt(2^(B-1)/ln2); |zs| beyond ZLIMIT (zs^2 = 1023 2^B: exp(-z^2/2) = 2^-1023) needs the clamp of the guarded form,
+ * whose bound is the high word of a double just below it */
+#if MFIT_EXP_BITS == 8
+#define MFIT_GAUSS_ZLIMIT 511.75
+#define MFIT_GAUSS_ZCLAMP_HI 0x407ffc00u
+#define MFIT_GAUSS_ZSCALE 0x1.b2da4e9808a53p+3 /* sqrt(128/ln2) */
+#elif MFIT_EXP_BITS == 9
+#define MFIT_GAUSS_ZLIMIT 723.5
+#define MFIT_GAUSS_ZCLAMP_HI 0x40869c00u
+#define MFIT_GAUSS_ZSCALE (0x1.b2da4e9808a53p+3 * 0x1.6a09e667f3bcdp+0)
+#else
+#define MFIT_GAUSS_ZLIMIT 1023.375
+#define MFIT_GAUSS_ZCLAMP_HI 0x408ffb00u
+#define MFIT_GAUSS_ZSCALE 0x1.b2da4e9808a53p+4
+#endif
 
 // exp(-zs^2 ln2/256) = s * (1 + r q)  (zs = z sqrt(128/ln2) turns exp(-z^2/2) into this form): the square is both the
 // argument and, through one FMA each, its rounding to 1/256 octaves and the exact remainder r.  Three FP64
@@ -177,7 +221,7 @@ __device__ __forceinline__ void mfit_gauss_reduce(double zs, double* s, double* 
     // recording guard looks at the word first and Model::tame() rules NaN out for the clamp-only guard.
     const unsigned ah = (unsigned)mfit_hi(zs);
     if (G::ON) gd.see_gauss(ah);
-    zs = mfit_mk((int)min(ah, 0x407ffc00u), mfit_lo(zs));
+    zs = mfit_mk((int)min(ah, MFIT_GAUSS_ZCLAMP_HI), mfit_lo(zs));
   }
   const double tmp = fma(-zs, zs, MFIT_MAGIC);
   const double kd = tmp - MFIT_MAGIC;
@@ -189,15 +233,23 @@ template <class G>
 __device__ __forceinline__ void mfit_gauss_parts(double zs, double* s, double* p, G& gd) {
   double r;
   mfit_gauss_reduce(zs, s, &r, gd);
+#if MFIT_EXP_BITS == 8 && MFIT_GAUSS_DEG == 4
   double q = fma(r, MFIT_K_EXS4, MFIT_K_EXS3);
   q = fma(r, q, MFIT_K_EXS2);
   q = fma(r, q, MFIT_K_EXS1);
+#elif MFIT_GAUSS_DEG == 4
+  double q = fma(r, mfit_kg[MFIT_EXP_BITS - 8][1][3], mfit_kg[MFIT_EXP_BITS - 8][1][2]);
+  q = fma(r, q, mfit_kg[MFIT_EXP_BITS - 8][1][1]);
+  q = fma(r, q, mfit_kg[MFIT_EXP_BITS - 8][1][0]);
+#else
+  double q = fma(r, mfit_kg[MFIT_EXP_BITS - 8][0][2], mfit_kg[MFIT_EXP_BITS - 8][0][1]);
+  q = fma(r, q, mfit_kg[MFIT_EXP_BITS - 8][0][0]);
+#endif
   *p = fma(r, q, 1.0);
 }
-#define MFIT_GAUSS_ZLIMIT 511.75 /* |zs| beyond this needs the clamp of the guarded form */
-#define MFIT_GAUSS_ZSCALE 0x1.b2da4e9808a53p+3 /* sqrt(128/ln2) */
 
-// log(x): 13 FP64 instructions.  x = 2^e m with m in [0.707, 1.414); r = m c_i - 1 (one FMA, exact before rounding),
+
+// log(x): 12 FP64 instructions.  x = 2^e m with m in [0.707, 1.414); r = m c_i - 1 (one FMA, exact before rounding),
 // log x = e ln2 + L_i + log1p(r); the table intervals next to 1 have c = 1 (1/2) and L = 0 exactly, which keeps full
 // relative accuracy around x = 1.
 template <bool SLOW, class G>
@@ -218,8 +270,7 @@ __device__ __forceinline__ double mfit_log_t(double x, G& gd) {
   const double r = fma(m, c, -1.0);
   const double ed = mfit_mk(0x43300000, e ^ 0x80000000) - 0x1.0000080000000p+52;  // int -> double via the exponent trick
   const double r2 = r * r;
-  double q = fma(r, MFIT_K_LG8, MFIT_K_LG7);
-  q = fma(r, q, MFIT_K_LG6);
+  double q = fma(r, MFIT_K_LG7, MFIT_K_LG6);             // |r| < 2^-7.9: the r^8 term of log1p is below 2e-18 of the result
   q = fma(r, q, MFIT_K_LG5);
   q = fma(r, q, -0.25);
   q = fma(r, q, MFIT_K_LG3);

@@ -43,8 +43,8 @@ def c2(W=4096, N=100000):
     keys = ["a", "mu", "s", "b0", "b1"]
     return dict(name="C2", function=[builtin("gauss_lin", keys)], data=[[x, y]], data_error=[sig], keys=keys,
                 theta_star=th, theta0=_jitter(th, W, 0.05, 2002), log_liklihood="log-liklihood-normal",
-                log_prior="log-prior-flat", steps=2000, flop_per_point=12, transc_per_point={"exp": 1}, fp64_instr_per_point=14,
-                fp64_instr_by_mode=[14, 14, 14, 13])   # guard-free, clamp-only, guarded, fused argument (profiles/r02_sass_gauss_lin.txt)
+                log_prior="log-prior-flat", steps=2000, flop_per_point=12, transc_per_point={"exp": 1}, fp64_instr_per_point=13,
+                fp64_instr_by_mode=[13, 13, 13, 12])   # guard-free, clamp-only, guarded, fused argument (profiles/r02_sass_gauss_lin.txt)
 
 
 def c3(W=16384, N=1000000):
@@ -57,7 +57,7 @@ def c3(W=16384, N=1000000):
     keys = ["a", "omega", "phi", "c"]
     return dict(name="C3", function=[builtin("sinus", keys)], data=[[x, y]], data_error=1.0, keys=keys,
                 theta_star=th, theta0=_jitter(th, W, 0.02, 2003), log_liklihood="log-poisson",
-                log_prior="log-prior-flat", steps=200, flop_per_point=7, transc_per_point={"sin": 1, "log": 1}, fp64_instr_per_point=32)
+                log_prior="log-prior-flat", steps=200, flop_per_point=7, transc_per_point={"sin": 1, "log": 1}, fp64_instr_per_point=31)
 
 
 def c4(W=1024, D=8, N=1000000):

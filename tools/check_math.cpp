@@ -37,7 +37,7 @@ int main() {
     double z = U(-37, 37), zs = std::fabs(z) * MFIT_GAUSS_ZSCALE, s, p;   // the routine takes |zs| (mfit_gauss_reduce)
     mfit_gauss_parts(zs, &s, &p, G);
     // reference for what the routine promises: exp(-zs^2 ln2/256) of the rounded zs
-    long double ref = expl(-(long double)zs * zs * (logl(2.0L) / 256));
+    long double ref = expl(-(long double)zs * zs * (logl(2.0L) / (1 << MFIT_EXP_BITS)));
     worst = std::fmax(worst, ulp_err(s * p, ref));
   }
   printf("gauss max ulp %.3f\n", worst);
