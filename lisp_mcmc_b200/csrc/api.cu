@@ -534,6 +534,7 @@ void fill_eval_args(MfitEvalArgs& a, const Dataset& s, const Workspace& w, int d
   a.partial = w.partial[d];
   for (int k = 0; k < MFIT_MAXK; k++) a.idx[k] = s.idx[k];
   a.degree = s.degree;
+  a.diag = 0;
 }
 
 int ensure_sched(mfit_ctx* ctx) {
@@ -560,6 +561,7 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
   // ... and the chains' own y rows go through a per-warp TMA ring when two CTAs per SM still fit with at least two
   // stages (mfit_perchain_ring): rows of up to ~800 points; longer ones are read straight into registers
   a.ring_stages = 0;
+  { const char* dg = getenv("MFIT_PC_DIAG"); a.diag = dg ? atoi(dg) : 0; }
   // Rows of up to 512 points (the reference's spectra have a few hundred, nv-specific.lisp:50-66), built-in family, no
   // cutoff constants: the register form (mfit_reg_row) -- four-warp CTAs, three per SM, every lane keeps the x and 1/sigma
   // of its points in registers across all the chains its warp evaluates.

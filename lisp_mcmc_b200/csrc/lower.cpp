@@ -294,6 +294,31 @@ struct Lower {
       if (keys[i] == k) return (int)i;
     return -1;
   }
+  // :single-item parameter style (mcmc-fitting.lisp:8-14, :1078-1088, :1153-1155): ONE key whose value is a list, a vector
+  // or an n x 1 array of numbers -- (lambda (x &key params &allow-other-keys) (+ (elt params 0) (* (elt params 1) x))).
+  // The hosts flatten it: the key names arrive as NAME[0] .. NAME[n-1], element k of the sequence is parameter NAME[k].
+  std::set<std::string> seq_vars;        // &key variables bound to such a sequence
+  int seq_key_count(const std::string& name) const {
+    int n = 0;
+    while (key_index(name + "[" + std::to_string(n) + "]") >= 0) n++;
+    return n;
+  }
+  // the sequence-valued key a form denotes: the &key variable itself, or (getf params :NAME) in a prior lambda
+  bool seq_key_of(const Sx& seq, std::string& name) const {
+    if (seq.t == Sx::SYM) {
+      if (!seq_vars.count(seq.sym)) return false;
+      name = seq.sym;
+      return true;
+    }
+    if (seq.t == Sx::LIST && seq.kids.size() >= 3 && seq.kids[0].t == Sx::SYM && seq.kids[0].sym == "GETF" && seq.kids[2].t == Sx::SYM) {
+      std::string k = seq.kids[2].sym;
+      if (!k.empty() && k[0] == ':') k = k.substr(1);
+      if (seq_key_count(k) == 0) return false;
+      name = k;
+      return true;
+    }
+    return false;
+  }
   void bind(const std::string& name, const Ex& e) { scope[name].push_back(e); }
   void unbind(const std::string& name) { scope[name].pop_back(); }
 
@@ -654,6 +679,28 @@ struct Lower {
       for (auto& a : acc)
         if (f == a.name) {
           const bool fixed = a.fixed >= 0;
+          if (!is_ll && na >= 1 && (a.fixed != -2 || na >= 2)) {
+            // element k of a sequence-valued parameter (:single-item style): (elt params k), (aref params k), (aref params k 0)
+            std::string sk;
+            if (seq_key_of(s.kids[a.fixed == -2 ? 2 : 1], sk)) {
+              i64 idx = a.fixed;
+              if (!fixed) {
+                if (na < 2 || na > (f == "AREF" ? 3u : 2u)) throw Err("wrong number of arguments to " + f);
+                const Sx& ix = s.kids[a.fixed == -2 ? 1 : 2];
+                if (ix.t != Sx::NUM || ix.nk != 0 || ix.den != 1 || ix.num < 0) throw Err(f + ": the index must be a literal non-negative integer");
+                idx = ix.num;
+                if (na == 3) {  // an n x 1 array: the column index is 0
+                  const Sx& jx = s.kids[3];
+                  if (jx.t != Sx::NUM || jx.nk != 0 || jx.den != 1 || jx.num != 0) throw Err("aref: the parameter array is n x 1, its second index must be 0");
+                }
+              } else {
+                need(1, 1);
+              }
+              const int ti = key_index(sk + "[" + std::to_string(idx) + "]");
+              if (ti < 0) throw Err(f + ": index " + std::to_string(idx) + " is beyond the parameter sequence " + sk);
+              return theta(ti);
+            }
+          }
           need(fixed ? 1 : 2, fixed ? 1 : 2);
           const Sx& seq = s.kids[a.fixed == -2 ? 2 : 1];
           if (is_ll) {
@@ -929,7 +976,10 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
     if (name.empty()) throw Err("malformed &key argument");
     int i = L.key_index(name);
     if (i >= 0) L.bind(name, L.theta(i));
-    else if (a.t == Sx::LIST && a.kids.size() > 1) L.bind(name, L.lower(a.kids[1]));  // default value form
+    else if (L.seq_key_count(name) > 0) {   // :single-item style: the key's value is a sequence, read with elt / aref ...
+      L.seq_vars.insert(name);
+      L.bind(name, mk_bool(true));          // a sequence is no number: using it as one is a type error in the reference too
+    } else if (a.t == Sx::LIST && a.kids.size() > 1) L.bind(name, L.lower(a.kids[1]));  // default value form
     else L.bind(name, mk_bool(false));                                                 // nil
   }
   std::string out;

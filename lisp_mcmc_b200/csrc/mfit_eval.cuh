@@ -82,6 +82,8 @@ struct MfitEvalArgs {
   long long xd_stride;  /* distance between the component arrays of a multi-dimensional x (n_pad) */
   int idx[MFIT_MAXK];   /* built-in families: family slot -> shared parameter index */
   int degree;
+  int diag;             /* measurement aid of the walker-set ring kernels (MFIT_PC_DIAG): 1 = rows are fetched, nothing is
+                           evaluated; 2 = everything is evaluated, nothing is fetched (results are then meaningless) */
 };
 
 // One launch of the shared-data kernel evaluates up to MFIT_MAX_FUSED data sets that use the same model family and
@@ -633,7 +635,7 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
   const long long first = w_lo + (long long)blockIdx.x * nwarp + wib;
   const double* ybase = LL == MFITK_NORMAL ? a.yw : a.y;
   const unsigned row_bytes = (unsigned)(n_pad * 8);
-  if (lane == 0)
+  if (lane == 0 && a.diag != 2)
     for (int s = 0; s < S; s++) {
       const long long ch = first + (long long)s * warps;
       if (ch < w_hi) {
@@ -672,12 +674,12 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
     }
     m.setup();
     const bool unguarded = !GUARDED || (MfitTerm<LL>::USES == 0 && m.safe(a));  // theta is warp-uniform
-    mfit_mbar_wait(&bars[slot], (unsigned)((k / S) & 1));
+    if (a.diag != 2) mfit_mbar_wait(&bars[slot], (unsigned)((k / S) & 1));
     const double* row = ring + (size_t)slot * slot_len;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     double sum = 0.0;
     bool redo = false;
-    if (!skip) {
+    if (!skip && a.diag != 1) {
       MfitGuard gd;
       gd.reset();
       MfitNoGuard ng;
@@ -692,7 +694,7 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       if (redo) sum = mfit_perchain_pass<Model, LL, true, true>(m, xs, row, ws, cs, a.n, lane, gd);  // rare: libdevice
     }
     __syncwarp();  // every lane is done with the row: its slot goes back to the TMA engine before the sums are combined
-    if (lane == 0) {
+    if (lane == 0 && a.diag != 2) {
       const long long nxt = chain + (long long)S * warps;
       if (nxt < w_hi) {
         mfit_mbar_expect_tx(&bars[slot], row_bytes);

@@ -235,13 +235,36 @@ translates it to CUDA C and NVRTC compiles it for sm_100a; it never runs in Lisp
           (cffi:foreign-string-to-lisp out))))))
 
 ;;; ---------------------------------------------------------------------------------- walker
-(defstruct gpu-walker ctx multi function param-keys n-walkers n-params data data-error log-liklihood log-prior)
+(defstruct gpu-walker ctx multi param-style single-key function param-keys n-walkers n-params data data-error log-liklihood log-prior)
 
 (defvar mfit-walker-estop nil "Set to T (e.g. from another thread) to stop a run between launches, :860.")
 
 (defun force-list (x) (if (listp x) x (list x)))          ; :755-759
 (defun plist-keys (p) (loop for k in p by #'cddr collect k))
 (defun plist-values (p) (loop for v in (cdr p) by #'cddr collect v))
+
+;;; :single-item parameter style (:8-14, :1078-1088, :1153-1155): ONE key whose value is a list, a vector or an n x 1 array.
+;;; The device sees it flattened -- element k is the parameter named NAME[k], which the lowering resolves from
+;;; (elt NAME k) / (aref NAME k) / (aref NAME k 0) / (nth k NAME) in the :function text.
+(defun single-item-p (params)
+  (and (= (length params) 2) (second params) (typep (second params) '(and (or list vector array) (not string)))))
+(defun sequence-values (v)
+  (etypecase v
+    (list v)
+    (vector (coerce v 'list))
+    (array (loop for i below (array-dimension v 0) collect (aref v i 0)))))
+(defun flat-param-keys (params)
+  (if (single-item-p params)
+      (loop for k below (length (sequence-values (second params)))
+            collect (intern (format nil "~a[~d]" (symbol-name (first params)) k) :keyword))
+      (plist-keys params)))
+(defun flat-param-values (params)
+  (if (single-item-p params) (sequence-values (second params)) (plist-values params)))
+(defun shape-params (walker plist)
+  "A flat (key value ...) list as the device returns it -> the reference's shape: (:name (v0 v1 ...)) for :single-item."
+  (if (eq (gpu-walker-param-style walker) :single-item)
+      (list (gpu-walker-single-key walker) (plist-values plist))
+      plist))
 
 (defun clean-data (data n-functions)
   "clean-data :807-825: one (x y) set, or a list of them, one per function."
@@ -309,12 +332,12 @@ data set d of a global fit on GPU d mod n; results are bit-identical to one GPU.
          (d-count (length function))
          (data (clean-data data d-count))
          (data-error (clean-data-error (if data-error data-error 1) data))
-         (keys (plist-keys params))
+         (keys (flat-param-keys params))
          (p (length keys))
          (ll (if (consp log-liklihood) log-liklihood (make-list d-count :initial-element log-liklihood)))
          (lp (if (and (consp log-prior) (= (length log-prior) d-count) (not (keywordp (first (first log-prior)))))
                  log-prior (make-list d-count :initial-element log-prior)))
-         (theta0 (or theta0 (make-list n-walkers :initial-element (plist-values params))))
+         (theta0 (or theta0 (make-list n-walkers :initial-element (flat-param-values params))))
          (w (length theta0))
          ctx)
     (cffi:with-foreign-objects ((out :pointer) (ids :int (max 1 (length devices))))
@@ -348,7 +371,8 @@ data set d of a global fit on GPU d mod n; results are bit-identical to one GPU.
       (chk ctx (if *multi*
                    (%multi-chains-init ctx t0 w seed trace-capacity)
                    (%chains-init ctx t0 w seed 0 trace-capacity))))
-    (make-gpu-walker :ctx ctx :multi *multi* :function function :param-keys keys :n-walkers w :n-params p :data data
+    (make-gpu-walker :ctx ctx :multi *multi* :param-style (if (single-item-p params) :single-item :multiple-kwargs)
+                     :single-key (first params) :function function :param-keys keys :n-walkers w :n-params p :data data
                      :data-error data-error :log-liklihood ll :log-prior lp)))
 
 (defun walker-set-create (&key function x ys params data-error log-liklihood log-prior (seed 0) (device 0) (trace-capacity 0))
@@ -431,8 +455,8 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
          (*multi* (gpu-walker-multi walker)))
     (cffi:with-foreign-objects ((th :double (* w p)) (pr :double w))
       (chk ctx (funcall reader ctx th pr))
-      (values (loop for k in (gpu-walker-param-keys walker) for i from 0
-                    append (list k (cffi:mem-aref th :double (+ (* chain p) i))))
+      (values (shape-params walker (loop for k in (gpu-walker-param-keys walker) for i from 0
+                                         append (list k (cffi:mem-aref th :double (+ (* chain p) i)))))
               (cffi:mem-aref pr :double chain)))))
 
 (defun walker-get (walker &key (get :steps) take param (chain 0))
@@ -474,8 +498,8 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
                               collect (loop for k in keys for i from 0
                                             append (list k (cffi:mem-aref th :double (+ (* (+ (* chain take) r) p) i)))))))
              (ecase get
-               (:steps (mapcar #'cons probs rows))
-               (:params rows)
+               (:steps (mapcar #'cons probs (mapcar (lambda (row) (shape-params walker row)) rows)))
+               (:params (mapcar (lambda (row) (shape-params walker row)) rows))
                (:param (mapcar (lambda (row) (getf row param)) rows))
                (:log-liklihoods probs)
                (:acceptance (/ (1+ (loop for (a b) on probs while b count (/= a b))) m))))))))))   ; :506-508

@@ -159,6 +159,16 @@ def plist(params):
     keys = [str(k).lstrip(":").lower() for k, _ in items]
     if len(set(keys)) != len(keys):
         raise ValueError("duplicate parameter keys")
+    if len(items) == 1 and np.ndim(items[0][1]) >= 1:
+        # :single-item style (:8-14; walker-create :1153-1155 looks at (elt params 1)): ONE key whose value is a list, a
+        # vector or an n x 1 array.  Flattened for the device: element k becomes parameter NAME[k], which the lowering
+        # resolves from (elt NAME k) / (aref NAME k) / (aref NAME k 0) / (nth k NAME) ... in the :function text.
+        v = np.asarray(items[0][1], dtype=np.float64)
+        if v.ndim == 2 and v.shape[1] == 1:
+            v = v[:, 0]
+        if v.ndim != 1 or v.size == 0:
+            raise ValueError("a single-item :params value must be a list, a vector or an n x 1 array of numbers")
+        return ["%s[%d]" % (keys[0], k) for k in range(v.size)], v.copy()
     return keys, np.array([float(v) for _, v in items], dtype=np.float64)
 
 
@@ -268,7 +278,7 @@ class Walker:
         self.log_prior = [x if x is not None else "log-prior-flat" for x in lp]
         if len(self.log_liklihood) != D or len(self.log_prior) != D:
             raise ValueError(":log-liklihood / :log-prior lists must match the :function list")
-        self.param_style = "multiple-kwargs"
+        self.param_style = "single-item" if len(self.param_keys) and self.param_keys[0].endswith("[0]") else "multiple-kwargs"
         self.device, self.seed, self.chain_id_base = device, int(seed), int(chain_id_base)
         self._keys_c = _lib.keys_array(self.param_keys)
 

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <set>
 #include <stdexcept>
 
 extern "C" double orc_log_normal(double x, double mu, double sigma);
@@ -285,6 +286,27 @@ struct Compiler {
   Fn* fn;
   Scope sc;
   std::vector<std::string> keys;  // upper-case, without ':'
+  std::set<std::string> seq_vars;  // &key variables whose value is a sequence (:single-item style; keys NAME[0] .. NAME[n-1])
+  bool has_seq_key(const std::string& name) const {
+    for (auto& k : keys)
+      if (k == name + "[0]") return true;
+    return false;
+  }
+  bool seq_key_of(const Sx& seq, std::string& name) const {
+    if (seq.t == Sx::SYM) {
+      if (!seq_vars.count(seq.sym)) return false;
+      name = seq.sym;
+      return true;
+    }
+    if (seq.t == Sx::LIST && seq.kids.size() >= 3 && seq.kids[0].t == Sx::SYM && seq.kids[0].sym == "GETF" && seq.kids[2].t == Sx::SYM) {
+      std::string k = seq.kids[2].sym;
+      if (!k.empty() && k[0] == ':') k = k.substr(1);
+      if (!has_seq_key(k)) return false;
+      name = k;
+      return true;
+    }
+    return false;
+  }
   int new_slot(const std::string& name) {
     int s = fn->nslots++;
     sc.names.push_back({name, s});
@@ -323,6 +345,32 @@ struct Compiler {
       for (auto& a : acc)
         if (f == a.name) {
           const bool fixed = a.fixed >= 0;
+          if (s.kids.size() >= 2 && (a.fixed != -2 || s.kids.size() >= 3)) {
+            // :single-item parameter style (:8-14, :1078-1088): the key's value is a list / vector / n x 1 array whose
+            // element k is parameter NAME[k] of the flattened key list
+            std::string sk;
+            if (seq_key_of(s.kids[a.fixed == -2 ? 2 : 1], sk)) {
+              long long idx = a.fixed;
+              if (!fixed) {
+                if (s.kids.size() < 3 || s.kids.size() > (f == "AREF" ? 4u : 3u)) throw std::runtime_error("wrong number of arguments to " + f);
+                const Sx& ix = s.kids[a.fixed == -2 ? 1 : 2];
+                if (ix.t != Sx::NUM || ix.num.k != Val::RAT || ix.num.den != 1 || ix.num.num < 0)
+                  throw std::runtime_error(f + ": the index must be a literal non-negative integer");
+                idx = ix.num.num;
+                if (s.kids.size() == 4) {
+                  const Sx& jx = s.kids[3];
+                  if (jx.t != Sx::NUM || jx.num.k != Val::RAT || jx.num.den != 1 || jx.num.num != 0)
+                    throw std::runtime_error("aref: the parameter array is n x 1, its second index must be 0");
+                }
+              } else if (s.kids.size() != 2) {
+                throw std::runtime_error("wrong number of arguments to " + f);
+              }
+              const std::string want = sk + "[" + std::to_string(idx) + "]";
+              for (size_t i = 0; i < keys.size(); i++)
+                if (keys[i] == want) return var(theta_var((int)i));
+              throw std::runtime_error(f + ": index beyond the parameter sequence " + sk);
+            }
+          }
           if (s.kids.size() != (fixed ? 2u : 3u)) throw std::runtime_error("wrong number of arguments to " + f);
           const Sx& seq = s.kids[a.fixed == -2 ? 2 : 1];
           if (seq.t != Sx::SYM || fn->x_slot < 0 || sc.find(seq.sym) != fn->x_slot)
@@ -667,6 +715,10 @@ Fn* fn_parse(const char* text, const std::vector<std::string>& keys_in) {
     if (idx >= 0) {
       int slot = c.theta_var(idx);
       c.sc.names.push_back({name, slot});
+    } else if (c.has_seq_key(name)) {
+      c.seq_vars.insert(name);
+      int slot = c.new_slot(name);
+      fn->defaults.push_back({slot, Val::boolean(true)});   // a sequence is no number
     } else {
       int slot = c.new_slot(name);
       Val dv = Val::boolean(false);

@@ -179,6 +179,41 @@ def test_user_sexpr_model_matches_builtin_and_oracle(orc):
     w1.close(); w2.close()
 
 
+def test_single_item_parameter_style_equals_keyword_parameters(orc):
+    """:params '(:params (-1 2)) with (lambda (x &key params ...) (+ (elt params 0) (* (elt params 1) x))) -- the reference's
+    "single param list fit" (mcmc-fitting.lisp:8, :1078-1088, :1153-1155) -- runs the same chains, bit for bit, as the
+    same line written with two keyword parameters, and its log-probs agree with the oracle's evaluation of the
+    single-item lambda; a vector and an n x 1 array start value behave like the list"""
+    rng = np.random.default_rng(8)
+    x = np.linspace(-4.0, 10.0, 700)
+    y = 1.0 + 0.9 * x + 0.2 * rng.standard_normal(x.size)
+    single = "(lambda (x &key params &allow-other-keys) (+ (elt params 0) (* (elt params 1) x)))"
+    array = "(lambda (x &key params &allow-other-keys) (+ (aref params 0 0) (* (aref params 1 0) x)))"
+    multi = "(lambda (x &key b m &allow-other-keys) (+ b (* m x)))"
+    kw = dict(data=[x, y], data_error=0.2, n_walkers=5, seed=3)
+    w_s = walker_create(function=single, params=[":params", [-1.0, 2.0]], **kw)
+    w_v = walker_create(function=single, params=[":params", np.array([-1.0, 2.0])], **kw)
+    w_a = walker_create(function=array, params=[":params", np.array([[-1.0], [2.0]])], **kw)
+    w_m = walker_create(function=multi, params=[":b", -1.0, ":m", 2.0], **kw)
+    assert w_s.param_style == "single-item" and w_m.param_style == "multiple-kwargs" and w_s.param_keys == ["params[0]", "params[1]"]
+    for w in (w_s, w_v, w_a, w_m):
+        w.adaptive_steps_full(n=600, temperature=10, auto=None)
+    ref = w_m.trace(700)
+    for w in (w_s, w_v, w_a):
+        for a, b in zip(w.trace(700), ref):
+            assert np.array_equal(a, b, equal_nan=True)
+    th, pr, nv = w_s.trace(50)
+    ow = orc.Walker(["params[0]", "params[1]"], 1)
+    ow.dataset(0, x, y, np.full(x.size, 0.2))
+    ow.model_sexpr(0, single)
+    ow.likelihood(0, 0)
+    ow.prior_flat(0)
+    want = np.array([ow.logp(t)[0] for t in th[0, :20]])
+    assert rel_err(pr[0, :20], want) < TOL
+    for w in (w_s, w_v, w_a, w_m):
+        w.close()
+
+
 def test_c5_user_model_poly5_times_exp(orc):
     cfg = workloads.c5(W=50, N=3000)
     w = workloads.make_walker(cfg)

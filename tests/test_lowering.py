@@ -54,6 +54,12 @@ MODELS = [
     ("(lambda (x &key a b &allow-other-keys) (* (exp 1) (float 1/3) (+ a (* 0.1 b x)) (expt 2 10) (atan a b) (tanh x)))", ["a", "b"]),
     ("(lambda (x &key a b &allow-other-keys) (if (and (> a 0) (not (> b 10)) (or (< x 0) (>= a 1/2))) (+ a (* 2 pi x)) (1+ b)))", ["a", "b"]),
 ]
+# :single-item parameter style (mcmc-fitting.lisp:8-14): one key, its value a list / vector / n x 1 array -> keys NAME[k]
+MODELS += [
+    ("(lambda (x &key params &allow-other-keys) (+ (elt params 0) (* (elt params 1) x)))", ["params[0]", "params[1]"]),          # :8
+    ("(lambda (x &key params &allow-other-keys) (+ (aref params 0 0) (* (aref params 1 0) x)))", ["params[0]", "params[1]"]),    # :14
+    ("(lambda (x &key p &allow-other-keys) (+ (first p) (* (nth 1 p) x) (* (svref p 2) (exp (* -1 (third p) x)))))", ["p[0]", "p[1]", "p[2]"]),
+]
 for _name, _deg in [("poly", 4), ("expo", 0), ("sinus", 0), ("lorentz", 0), ("gauss_lin", 0), ("nv_multi", 2)]:
     MODELS.append((families.lisp_text(_name, _deg), families.slots(_name, _deg)))
 
@@ -78,6 +84,10 @@ PRIORS = [
 ]
 
 
+PRIORS.append(("(lambda (params data) (declare (ignore data)) (let ((p0 (elt (getf params :p) 0))) (if (< 0 p0 (nth 1 (getf params :p))) 0d0 -1d10)))",
+               ["p[0]", "p[1]"]))
+
+
 @pytest.mark.parametrize("text,keys", PRIORS)
 def test_prior_lowering_matches_lisp_semantics(orc, text, keys):
     f = _host_compile(_lib.lower_sexpr(text, keys, 1), 1)
@@ -88,6 +98,25 @@ def test_prior_lowering_matches_lisp_semantics(orc, text, keys):
         a, b = f(th), ref.prior(th)
         assert a == b or abs(a - b) <= 1e-15 * abs(b) + 1e10 * 2.0 ** -52, (text, th, a, b)
     assert f(np.zeros(len(keys))) == ref.prior(np.zeros(len(keys))) or True
+
+
+def test_single_item_parameter_style():
+    """:params '(:params (-1 2)) (mcmc-fitting.lisp:8): the flattened keys lower to the same code as two keyword
+    parameters; indexing beyond the sequence or using the sequence as a number is refused; plist() flattens lists,
+    vectors and n x 1 arrays alike"""
+    from lisp_mcmc_b200.walker import plist
+    single = _lib.lower_sexpr("(lambda (x &key params &allow-other-keys) (+ (elt params 0) (* (elt params 1) x)))", ["params[0]", "params[1]"], 0)
+    multi = _lib.lower_sexpr("(lambda (x &key b m &allow-other-keys) (+ b (* m x)))", ["b", "m"], 0)
+    assert single == multi
+    for bad in ["(lambda (x &key params &allow-other-keys) (+ (elt params 2) x))",
+                "(lambda (x &key params &allow-other-keys) (+ params x))",
+                "(lambda (x &key params &allow-other-keys) (+ (aref params 0 1) x))"]:
+        with pytest.raises(_lib.MfitError):
+            _lib.lower_sexpr(bad, ["params[0]", "params[1]"], 0)
+    for value in ([-1, 2], (-1.0, 2.0), np.array([-1.0, 2.0]), np.array([[-1.0], [2.0]])):
+        keys, vals = plist([":params", value])
+        assert keys == ["params[0]", "params[1]"] and list(vals) == [-1.0, 2.0]
+    assert plist([":b", -1, ":m", 2])[0] == ["b", "m"]
 
 
 def test_exact_rational_comparison():
