@@ -179,6 +179,10 @@ int mfit_run_advance(mfit_ctx* ctx, int64_t max_steps, int64_t* steps_done, int*
 /* walker-many-steps :849-853: n steps, constant l-matrix (required), temperature 1 */
 int mfit_run_many_steps(mfit_ctx* ctx, int64_t n, const double* l_matrix, const double* z, const double* u,
                         int64_t nstream);
+/* the same with one l-matrix per chain (W x P x P): walker-many-steps' default, (diagonal-covariance (scale-plist 1e-2
+ * median-params)) :851, is made per walker, and a walker set holds W of them */
+int mfit_run_many_steps_per_chain(mfit_ctx* ctx, int64_t n, const double* l_matrices, const double* z, const double* u,
+                                  int64_t nstream);
 /* walker-sample-region :949-969 */
 int mfit_run_sample_region(mfit_ctx* ctx, double initial_scale, const double* z, int64_t nstream);
 /* walker-force-take-step :1124-1129 */

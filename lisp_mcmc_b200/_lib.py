@@ -64,6 +64,7 @@ SIGNATURES = {
     "mfit_run_begin": (C.c_int, [C.c_void_p, C.POINTER(AdaptCfg), _dp, _dp, _dp, C.c_int64]),
     "mfit_run_advance": (C.c_int, [C.c_void_p, C.c_int64, _lp, C.POINTER(C.c_int)]),
     "mfit_run_many_steps": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _dp, C.c_int64]),
+    "mfit_run_many_steps_per_chain": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _dp, C.c_int64]),
     "mfit_run_sample_region": (C.c_int, [C.c_void_p, C.c_double, _dp, C.c_int64]),
     "mfit_force_take_step": (C.c_int, [C.c_void_p]),
     "mfit_request_stop": (C.c_int, [C.c_void_p]),

@@ -990,7 +990,12 @@ int run_begin(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long lon
   rc = grow_trace(ctx, ctx->rows_upper + max_steps + 1);
   if (rc) return rc;
   const double* l_dev = nullptr;
-  if (l_shared_host) {
+  double* l_tmp = nullptr;
+  if (l_shared_host && r.l_per_chain) {   // W x P x P, used by k_init_run only
+    CU(cudaMalloc(&l_tmp, sizeof(double) * (size_t)c.W * c.P * c.P));
+    CU(cudaMemcpyAsync(l_tmp, l_shared_host, sizeof(double) * (size_t)c.W * c.P * c.P, cudaMemcpyHostToDevice, ctx->stream));
+    l_dev = l_tmp;
+  } else if (l_shared_host) {
     if (!ctx->lshared_dev) CU(cudaMalloc(&ctx->lshared_dev, sizeof(double) * MFIT_MAX_P * MFIT_MAX_P));
     CU(cudaMemcpyAsync(ctx->lshared_dev, l_shared_host, sizeof(double) * c.P * c.P, cudaMemcpyHostToDevice, ctx->stream));
     l_dev = ctx->lshared_dev;
@@ -1000,6 +1005,7 @@ int run_begin(mfit_ctx* ctx, MfitRunCfg r, const double* l_shared_host, long lon
   r.t = 0;
   sync_epoch(ctx, c);   // the first proposals' priors belong to the exchange of the first step
   mfit_launch_init_run(c, r, l_dev, ctx->stream);
+  free_dev(l_tmp);                       // stream-ordered: after k_init_run has read it
   mfit_launch_pre(c, r, ctx->stream);    // proposals of chains that keep their l-matrix
   mfit_launch_reest(c, r, ctx->stream);  // chains resuming a long walk re-estimate first (:897-901)
   ctx->launches += 3;
@@ -1912,6 +1918,25 @@ int mfit_run_many_steps(mfit_ctx* ctx, int64_t n, const double* l_matrix, const 
   int rc = attach_streams(ctx, r, z, u, nstream, n, true);
   if (rc) return rc;
   return run_loop(ctx, r, l_matrix, n, nullptr);
+}
+
+int mfit_run_many_steps_per_chain(mfit_ctx* ctx, int64_t n, const double* l_matrices, const double* z, const double* u,
+                                  int64_t nstream) {
+  if (!ctx) return MFIT_ERR_ARG;
+  if (!ctx->have_chains) return fail(ctx, MFIT_ERR_STATE, "mfit_chains_init has not been called");
+  if (!l_matrices) return fail(ctx, MFIT_ERR_ARG, "l_matrices is NULL");
+  if (n < 0) return fail(ctx, MFIT_ERR_ARG, "n < 0");
+  CU(cudaSetDevice(ctx->device)); g_alloc_stream = ctx->stream;
+  MfitRunCfg r;
+  memset(&r, 0, sizeof r);
+  r.mode = MFIT_MODE_MANY;
+  r.n = n;
+  r.S = 10LL * (ctx->P > 50 ? ctx->P : 50);
+  r.temperature0 = 1.0;
+  r.l_per_chain = 1;
+  int rc = attach_streams(ctx, r, z, u, nstream, n, true);
+  if (rc) return rc;
+  return run_loop(ctx, r, l_matrices, n, nullptr);
 }
 
 int mfit_run_sample_region(mfit_ctx* ctx, double initial_scale, const double* z, int64_t nstream) {

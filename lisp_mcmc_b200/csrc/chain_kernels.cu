@@ -486,7 +486,8 @@ __global__ void k_init_run(const MfitChains c, const MfitRunCfg r, const double*
     c.loop_i[w] = 0;
     c.done[w] = (0 >= r.n) ? 1 : 0;
     c.temperature[w] = 1.0;
-    for (int e = 0; e < PP; e++) c.L[(size_t)e * c.stride + w] = l_shared[e];
+    const double* lw = l_shared + (r.l_per_chain ? (size_t)w * PP : 0);   // :851 makes the default l-matrix per walker
+    for (int e = 0; e < PP; e++) c.L[(size_t)e * c.stride + w] = lw[e];
   } else {
     c.loop_i[w] = 1;
     c.done[w] = 0;

@@ -86,6 +86,7 @@ struct MfitRunCfg {
   unsigned long long seed;
   long long chain_base;
   double sr_scale;      // sample-region initial scale
+  int l_per_chain;      // the l-matrix handed to the run is W x P x P (one per chain) instead of one shared P x P
 };
 
 // ---- small problems: K Metropolis-Hastings steps per launch, one CTA per chain (chain_kernels.cu k_run_small)

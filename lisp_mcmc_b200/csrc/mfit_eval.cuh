@@ -592,17 +592,17 @@ __device__ __forceinline__ void mfit_ring_row(const Model& m, const double* xs, 
 // once per chain, and only y comes out of the ring: one LDS per evaluation instead of three (the shared-memory version
 // issued 46 warp-instructions per warp-point for 16 FP64 ones and ran at the pace of the issue ports, ncu
 // profiles/r02_perchain_kernel_ncu_raw.csv).  Fully unrolled and branch-free: NPT independent evaluations per lane;
-// slots beyond the row (bit u of `valid` clear) are evaluated at a real abscissa and dropped by a select.  Same
+// slots beyond the row are evaluated at a real abscissa and dropped by a select.  Same
 // accumulator per row and same arithmetic as mfit_ring_row: the sums are bit-identical.
 template <class Model, int LL, int NPT, class G>
-__device__ __forceinline__ void mfit_reg_row(const Model& m, const double* xr, const double* wr, unsigned valid,
+__device__ __forceinline__ void mfit_reg_row(const Model& m, const double* xr, const double* wr, int n_lane,
                                              const double* row, int lane, double* acc, G& g) {
 #pragma unroll
   for (int u = 0; u < NPT; u++) {
     const double y = row[lane + 32 * u];
     const double f = mfit_model_scalar<Model, false>(m, xr[u], g);
     const double t = MfitTerm<LL>::template add<false>(acc[u & 3], f, y, wr[MfitTerm<LL>::NARR > 2 ? u : 0], 0.0, g);
-    acc[u & 3] = ((valid >> u) & 1u) ? t : acc[u & 3];
+    acc[u & 3] = (32 * u < n_lane) ? t : acc[u & 3];   // n_lane = n - lane: point lane + 32 u exists (one compare with an immediate)
   }
 }
 
@@ -645,7 +645,7 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
     }
   const int n = (int)a.n;
   double xr[NPT > 0 ? NPT : 1], wr[NPT > 0 ? NPT : 1];
-  unsigned valid = 0u;
+  const int n_lane = n - lane;
   if constexpr (NPT > 0) {
 #pragma unroll
     for (int u = 0; u < NPT; u++) {
@@ -654,7 +654,6 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       const int jj = ok ? j : lane % n;   // a real abscissa for the slots beyond the row (their terms are dropped)
       xr[u] = xs[jj];
       wr[u] = MfitTerm<LL>::NARR > 2 ? ws[jj] : 0.0;
-      valid |= (ok ? 1u : 0u) << u;
     }
   }
   Model m_next;
@@ -663,9 +662,9 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
     m_next.load(a, first);
     skip_next = a.skip != nullptr && a.skip[first] != 0;
   }
-  long long k = 0;
-  for (long long chain = first; chain < w_hi; chain += warps, k++) {
-    const int slot = (int)(k % S);
+  int slot = 0;            // ring slot of this chain's row and the parity its mbarrier completes with (no division per chain)
+  unsigned phase = 0u;
+  for (long long chain = first; chain < w_hi; chain += warps) {
     Model m = m_next;
     const bool skip = skip_next;
     if (chain + warps < w_hi) {  // the next chain's parameters and its finished flag, one chain ahead
@@ -674,7 +673,7 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
     }
     m.setup();
     const bool unguarded = !GUARDED || (MfitTerm<LL>::USES == 0 && m.safe(a));  // theta is warp-uniform
-    if (a.diag != 2) mfit_mbar_wait(&bars[slot], (unsigned)((k / S) & 1));
+    if (a.diag != 2) mfit_mbar_wait(&bars[slot], phase);
     const double* row = ring + (size_t)slot * slot_len;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     double sum = 0.0;
@@ -684,8 +683,8 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       gd.reset();
       MfitNoGuard ng;
       if constexpr (NPT > 0) {
-        if (unguarded) mfit_reg_row<Model, LL, NPT>(m, xr, wr, valid, row, lane, acc, ng);
-        else mfit_reg_row<Model, LL, NPT>(m, xr, wr, valid, row, lane, acc, gd);
+        if (unguarded) mfit_reg_row<Model, LL, NPT>(m, xr, wr, n_lane, row, lane, acc, ng);
+        else mfit_reg_row<Model, LL, NPT>(m, xr, wr, n_lane, row, lane, acc, gd);
       } else {
         if (unguarded) mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, ng);
         else mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, gd);
@@ -709,6 +708,7 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       }
       if (lane == 0) a.partial[chain] = sum;  // one segment
     }
+    if (++slot == S) { slot = 0; phase ^= 1u; }
   }
 }
 

@@ -90,18 +90,20 @@ struct MfitGuard {
   static constexpr bool FUSED = false;
   static constexpr bool ON = true;     // records arguments (see_*), checked once per tile
   static constexpr bool CLAMP = true;  // in-place clamps of the routines that have one (mfit_gauss_reduce)
-  unsigned e, g, l, s, d;
-  __device__ __forceinline__ void reset() { e = 0u; g = 0u; l = 0u; s = 0u; d = 0u; }
+  unsigned e, g, l, s, d, b;
+  __device__ __forceinline__ void reset() { e = 0u; g = 0u; l = 0u; s = 0u; d = 0u; b = 0u; }
   __device__ __forceinline__ void see_exp(unsigned v) { e = mfit_umax(e, v); }
   __device__ __forceinline__ void see_gauss(unsigned v) { g = mfit_umax(g, v); }
   __device__ __forceinline__ void see_log(unsigned v) { l = mfit_umax(l, v); }
   __device__ __forceinline__ void see_sin(unsigned v) { s = mfit_umax(s, v); }
   __device__ __forceinline__ void see_div(unsigned v) { d = mfit_umax(d, v); }
+  __device__ __forceinline__ void see_big(unsigned v) { b = mfit_umax(b, v); }
   __device__ __forceinline__ bool tripped() const {
     return e >= 0x40862000u      // exp: |x| >= 708 (overflow / underflow), inf, nan
         || g > 0x7ff00000u       // gauss: nan (underflow and +-inf are clamped in place, see mfit_gauss_parts)
         || l >= 0x7fe00000u      // log: x <= 0, subnormal, inf, nan   (l tracks hi(x) - 0x00100000 as unsigned)
         || s >= 0x40f86a00u      // sin/cos: |x| >= 1e5, inf, nan
+        || b >= 0x7fe00000u      // an intermediate product at or beyond 2^1023, inf, nan (MfitNvMulti's paired numerator)
         || d >= 0x7fb00000u;     // rcp: |x| outside [2^-1021, 2^1022), zero, inf, nan   (d tracks |hi(x)| - 0x00200000)
   }
   // some log argument was a negative normal number (hi(x) in [0x80100000, 0xffefffff]): that term is NaN, hence so
@@ -122,6 +124,7 @@ struct MfitNoGuard {
   __device__ __forceinline__ void see_log(unsigned) {}
   __device__ __forceinline__ void see_sin(unsigned) {}
   __device__ __forceinline__ void see_div(unsigned) {}
+  __device__ __forceinline__ void see_big(unsigned) {}
   __device__ __forceinline__ bool tripped() const { return false; }
   __device__ __forceinline__ bool log_of_negative() const { return false; }
 };

@@ -84,6 +84,8 @@
   (ctx :pointer) (max-steps :int64) (steps-done :pointer) (finished :pointer))
 (cffi:defcfun ("mfit_run_many_steps" %run-many-steps) :int
   (ctx :pointer) (n :int64) (l-matrix :pointer) (z :pointer) (u :pointer) (nstream :int64))
+(cffi:defcfun ("mfit_run_many_steps_per_chain" %run-many-steps-per-chain) :int
+  (ctx :pointer) (n :int64) (l-matrices :pointer) (z :pointer) (u :pointer) (nstream :int64))
 (cffi:defcfun ("mfit_run_sample_region" %run-sample-region) :int
   (ctx :pointer) (initial-scale :double) (z :pointer) (nstream :int64))
 (cffi:defcfun ("mfit_force_take_step" %force-take-step) :int (ctx :pointer))
@@ -431,12 +433,27 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
 (defun walker-adaptive-steps (walker &optional (n 30000))                               ; :946-947
   (walker-adaptive-steps-full walker :n n :temperature 10 :auto :prob-settle))
 
-(defun walker-many-steps (walker n l-matrix)                                            ; :849-853
-  (let ((ctx (gpu-walker-ctx walker)) (p (gpu-walker-n-params walker)) (*multi* (gpu-walker-multi walker)))
-    (with-doubles (lm (loop for i below p append (loop for j below p collect (aref l-matrix i j))))
-      (chk ctx (if *multi*
-                   (%multi-run-many-steps ctx n lm)
-                   (%run-many-steps ctx n lm (cffi:null-pointer) (cffi:null-pointer) 0)))))
+(defun walker-many-steps (walker n &optional l-matrix)                                  ; :849-853
+  "walker-many-steps :849-853.  Without L-MATRIX every chain gets the reference's default (:851),
+(diagonal-covariance (scale-plist 1e-2 median-params)), from its own walk (medians computed on the device)."
+  (let ((ctx (gpu-walker-ctx walker)) (p (gpu-walker-n-params walker)) (w (gpu-walker-n-walkers walker))
+        (*multi* (gpu-walker-multi walker)))
+    (if l-matrix
+        (with-doubles (lm (loop for i below p append (loop for j below p collect (aref l-matrix i j))))
+          (chk ctx (if *multi*
+                       (%multi-run-many-steps ctx n lm)
+                       (%run-many-steps ctx n lm (cffi:null-pointer) (cffi:null-pointer) 0))))
+        (progn
+          (one-gpu-only walker "walker-many-steps without an l-matrix")
+          (cffi:with-foreign-objects ((med :double (* w p)) (lms :double (* w p p)))
+            (let ((null (cffi:null-pointer)))
+              (chk ctx (%trace-analytics ctx 1000000000 null null med null null null))
+              (dotimes (c w)
+                (dotimes (i p)
+                  (dotimes (j p)
+                    (setf (cffi:mem-aref lms :double (+ (* c p p) (* i p) j))
+                          (if (= i j) (* (coerce 1e-2 'double-float) (cffi:mem-aref med :double (+ (* c p) i))) 0d0)))))
+              (chk ctx (%run-many-steps-per-chain ctx n lms null null 0)))))))
   walker)
 
 (defun walker-sample-region (walker &optional (initial-scale 1d-3))                     ; :949-969

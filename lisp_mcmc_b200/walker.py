@@ -460,7 +460,12 @@ class Walker:
         """walker-many-steps :849-853 (the :median-params default l-matrix is host post-processing: pass one)"""
         z, u, nstream = self._streams(z, u)
         lm = _f64(l_matrix)
-        self._chk(self._L.mfit_run_many_steps(self._h, int(n), _ptr(lm), _ptr(z), _ptr(u), nstream))
+        if lm.shape == (self.W, self.P, self.P):     # one l-matrix per chain
+            self._chk(self._L.mfit_run_many_steps_per_chain(self._h, int(n), _ptr(lm), _ptr(z), _ptr(u), nstream))
+        elif lm.shape == (self.P, self.P):
+            self._chk(self._L.mfit_run_many_steps(self._h, int(n), _ptr(lm), _ptr(z), _ptr(u), nstream))
+        else:
+            raise ValueError("l-matrix must be P x P, or W x P x P with one per chain")
         return self
 
     def sample_region(self, initial_scale=1e-3, z=None):
@@ -764,10 +769,8 @@ def walker_adaptive_steps(walker, n=30000):
 
 def walker_many_steps(walker, n, l_matrix=None):
     if l_matrix is None:   # :851 (diagonal-covariance (scale-plist 1e-2 median-params)); 1e-2 is a single-float literal
-        med = walker.get("median-params")
-        if not np.allclose(med, med[0]):
-            raise ValueError("chains disagree on :median-params; pass an l-matrix")
-        l_matrix = np.diag(np.float64(np.float32(1e-2)) * med[0])
+        med = walker.get("median-params")             # per chain, as the reference makes it per walker
+        l_matrix = np.float64(np.float32(1e-2)) * med[:, :, None] * np.eye(walker.P)[None, :, :]
     return walker.many_steps(n, l_matrix)
 
 

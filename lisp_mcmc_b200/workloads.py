@@ -85,7 +85,7 @@ def c4(W=1024, D=8, N=1000000):
         priors.append(families.log_prior_nv_text(sfx))
     return dict(name="C4", function=fns, data=data, data_error=1e-7, keys=keys, theta_star=th,
                 theta0=_jitter(th, W, 1e-4, 2004), log_liklihood="log-liklihood-normal", log_prior=priors,
-                steps=200, flop_per_point=14, transc_per_point={"div": 2}, fp64_instr_per_point=16)
+                steps=200, flop_per_point=14, transc_per_point={"div": 2}, fp64_instr_per_point=14)
 
 
 def c5(W=65536, N=10000000):
@@ -114,7 +114,7 @@ def nvset(W=131072, N=500):
     Y = f + 1e-7 * rng.standard_normal((W, N))
     return dict(name="NVSET", function=[builtin("nv_multi", keys, degree=2)], data=(x, Y), data_error=1e-7, keys=keys,
                 theta_star=th, theta0=thk * (1.0 + 1e-4 * rng.standard_normal((W, 6))), log_liklihood="log-liklihood-normal",
-                log_prior=families.log_prior_nv_text(), steps=200, fp64_instr_per_point=16, bytes_per_point=8, flop_per_point=14, transc_per_point={"div": 2})
+                log_prior=families.log_prior_nv_text(), steps=200, fp64_instr_per_point=14, bytes_per_point=8, flop_per_point=14, transc_per_point={"div": 2})
 
 
 def make_walker_set(cfg, **gpu):

@@ -325,6 +325,39 @@ def test_many_steps_injected_stream_identical_to_oracle(orc, step_path):
     w.close()
 
 
+def test_many_steps_with_one_l_matrix_per_chain(orc, step_path):
+    """walker-many-steps makes its default l-matrix per walker (:851: from that walker's :median-params); on a walker set
+    every chain therefore steps with its own (mfit_run_many_steps_per_chain, W x P x P) -- each chain against an oracle
+    walker that was handed the same matrix, injected streams, bit-identical traces.  The host's default reproduces :851."""
+    from lisp_mcmc_b200 import walker_many_steps
+    cfg = workloads.c2(W=7, N=900)
+    w = workloads.make_walker(cfg)
+    n = 300
+    rng = np.random.default_rng(12)
+    z, u = rng.standard_normal((w.W, n, w.P)), rng.uniform(size=(w.W, n))
+    Ls = np.stack([np.diag((0.002 + 0.001 * c) * np.abs(cfg["theta0"][c])) + 1e-4 * c * np.tril(np.ones((w.P, w.P)), -1)
+                   for c in range(w.W)])
+    w.many_steps(n, Ls, z=z, u=u)
+    th, pr, nv = w.trace(n + 1)
+    scale = ll_scale(cfg)
+    for c in range(w.W):
+        ow = oracle_walker(orc, cfg)
+        ow.init(cfg["theta0"][c])
+        ow.many_steps(n, Ls[c], z=z[c], u=u[c])
+        oth, opr = ow.trace(0)
+        assert nv[c] == len(opr) and np.array_equal(th[c, :nv[c]], oth)
+        assert rel_err(pr[c, :nv[c]], opr, scale) < TOL
+    med = w.get("median-params")
+    before = w.stats()["length"].copy()
+    walker_many_steps(w, 50)                       # default l-matrix: diag(1e-2 (single-float) x this chain's medians)
+    assert np.array_equal(w.stats()["length"], before + 50)
+    want = np.float64(np.float32(1e-2)) * med[:, :, None] * np.eye(w.P)[None]
+    assert np.array_equal(w.l_matrix(), want)
+    with pytest.raises(ValueError):
+        w.many_steps(5, np.zeros((3, w.P, w.P)))
+    w.close()
+
+
 @pytest.mark.parametrize("auto", [None, "prob-settle"])
 def test_adaptive_steps_full_injected_stream_identical_to_oracle(orc, auto, step_path):
     """walker-adaptive-steps-full end to end: temperature schedule, 200-step acceptance windows, x0.1 / x1.9 rescales,
