@@ -573,7 +573,8 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
     threads = MFIT_PCR_THREADS;
     const size_t warps = MFIT_PCR_THREADS / 32, slot = reg_form == 2 ? 256 : 512, budget = 74 * 1024;  // three CTAs per SM
     for (int S = 4; S >= 2 && a.ring_stages == 0; S--) {
-      const size_t need = smem_pc + warps * S * slot * sizeof(double) + warps * S * sizeof(unsigned long long);
+      const size_t need = smem_pc + warps * S * slot * sizeof(double) + warps * S * sizeof(unsigned long long) +
+                          warps * MFIT_PCR_BATCH * 33 * sizeof(double);   // ring, its mbarriers, the parked per-lane sums
       if (need <= budget) {
         a.ring_stages = S;
         smem_pc = need;

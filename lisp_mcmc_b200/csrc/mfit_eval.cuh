@@ -519,6 +519,7 @@ __device__ __forceinline__ void mfit_eval_body(const MfitMultiArgs& ma) {
 #define MFIT_PC_STAGE_MAX 2048 /* points up to which shared x / sigma vectors are staged in shared memory */
 #define MFIT_PCR_THREADS 128   /* threads per CTA of the register form of the staged kernel (mfit_reg_row): four warps, one per scheduler */
 #define MFIT_PCR_CTAS 3        /* its CTAs per SM (register bound: 168) */
+#define MFIT_PCR_BATCH 8       /* chains whose 32 per-lane sums wait in shared memory and are combined together (register form) */
 // STAGED: x and 1/sigma (and the cutoff constants) are one vector for all chains and sit in shared memory (xs, ws, cs
 // point there), so only the chain's own y values are streamed.
 template <class Model, int LL, bool SLOW, bool STAGED, class G>
@@ -628,7 +629,35 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
   const double* xs = smem;
   const double* ws = smem + n_pad;
   const double* cs = smem + 2 * n_pad;
+  // Register form: the 32 per-lane sums of a chain are not combined by a shuffle tree per chain (five dependent
+  // shuffle + add levels, ~200 cycles in which the warp issues nothing else: 29 % of the kernel's samples, ncu) but parked
+  // in shared memory, [chain of the batch][lane] with rows 33 apart; after MFIT_PCR_BATCH chains lane b adds up chain b's
+  // row IN THE TREE'S ORDER (s_i + s_{i+16}, then + 8, 4, 2, 1), so the sums are the same bits.
+  double* red = reinterpret_cast<double*>(reinterpret_cast<unsigned long long*>(smem + 3 * n_pad + (size_t)nwarp * S * slot_len) + (size_t)nwarp * S) +
+                (size_t)wib * MFIT_PCR_BATCH * 33;
+  int batch_n = 0;               // chains parked
+  unsigned batch_live = 0u;      // bit b: chain b of the batch has a sum to write
+  long long batch_first = 0;     // its first chain; chain b = batch_first + b * warps
   const long long warps = (long long)gridDim.x * nwarp;
+  auto flush = [&]() {
+    __syncwarp();
+    if (lane < batch_n && ((batch_live >> lane) & 1u)) {
+      const double* v = red + lane * 33;
+      double t16[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) t16[i] = v[i] + v[i + 16];
+#pragma unroll
+      for (int i = 0; i < 8; i++) t16[i] = t16[i] + t16[i + 8];
+#pragma unroll
+      for (int i = 0; i < 4; i++) t16[i] = t16[i] + t16[i + 4];
+      t16[0] = t16[0] + t16[2];
+      t16[1] = t16[1] + t16[3];
+      a.partial[batch_first + (long long)lane * warps] = t16[0] + t16[1];
+    }
+    __syncwarp();
+    batch_n = 0;
+    batch_live = 0u;
+  };
   const long long w_lo = (long long)a.cb0 * MFIT_CB;
   long long w_hi = w_lo + (long long)a.n_cb * MFIT_CB;
   if (w_hi > a.W) w_hi = a.W;
@@ -700,7 +729,16 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
         mfit_tma_load_1d(ring + (size_t)slot * slot_len, ybase + nxt * a.pc_stride, row_bytes, &bars[slot]);
       }
     }
-    if (!skip) {
+    if constexpr (NPT > 0) {
+      if (batch_n == 0) batch_first = chain;
+      if (!skip && !redo) {
+        red[batch_n * 33 + lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        batch_live |= 1u << batch_n;
+      } else if (!skip && lane == 0) {
+        a.partial[chain] = sum;  // the libdevice pass has combined its lanes already
+      }
+      if (++batch_n == MFIT_PCR_BATCH) flush();
+    } else if (!skip) {
       if (!redo) {
         sum = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 #pragma unroll
@@ -709,6 +747,9 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       if (lane == 0) a.partial[chain] = sum;  // one segment
     }
     if (++slot == S) { slot = 0; phase ^= 1u; }
+  }
+  if constexpr (NPT > 0) {
+    if (batch_n > 0) flush();
   }
 }
 
