@@ -272,7 +272,7 @@ def extra_record(dev, L, _lib, workloads, name, dfma, costs, local_rank, steps, 
         per_launch_s = run["kernel_s"] / max(run["kernel_launches"], 1)
         by = float(cfg["bytes_per_point"]) * W * N
         rec["roofline"] = {"bound": "hbm", "achieved": by / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                           "frac": by / per_launch_s / 1e9 / hbm_peak, "kernel": "mfit_eval_perchain_kernel",
+                           "frac": by / per_launch_s / 1e9 / hbm_peak, "kernel": "mfit_eval_perchain_reg_kernel",
                            "kernel_ms": per_launch_s * 1e3, "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % hbm_src,
                            "fp64_frac": r["frac"]}
     else:
@@ -477,7 +477,7 @@ def main():
                          "frac": by / per_launch_s / 1e9 / hbm_peak, "traffic": None,
                          "what": "algorithmic bytes (%g per point-eval: y/sigma; x and 1/sigma are shared vectors) / kernel time, "
                                  "against the measured copy bandwidth (%s)" % (base["bytes_per_point"], hbm_src)})
-            roof["kernel"] = "mfit_eval_perchain_kernel"
+            roof["kernel"] = "mfit_eval_perchain_reg_kernel"
             roof["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (%s)" % hbm_src
             roof.pop("hbm", None)
             roof.pop("survey_8d", None)
