@@ -1063,6 +1063,10 @@ int run_advance(mfit_ctx* ctx, long long budget, long long* steps_done, int* fin
   // (an overlapped kernel's event interval includes its wait for SM slots)
   const long long n_cb_all = c.stride / MFIT_CB;
   int n_groups = (ctx->sharded || ctx->timing) ? 1 : n_cb_all >= 12 ? 3 : n_cb_all >= 8 ? 2 : 1;
+  // walker sets with per-walker data: their likelihood kernel takes one pass over the rows, comparable to the chain kernels
+  // of a group; two groups overlap them best (NVSET step 0.182 / 0.173 / 0.181 ms with one / two / three groups)
+  for (const Dataset& s : ctx->ds)
+    if (s.W_pc > 0 && n_groups > 2) n_groups = 2;
   if (const char* e = getenv("MFIT_GROUPS")) { if (atoi(e) > 0 && !ctx->timing) n_groups = atoi(e); }  // tuning aid
   if (ctx->groups_override > 0) n_groups = ctx->groups_override;
   if (n_groups > mfit_ctx::kMaxGroups) n_groups = mfit_ctx::kMaxGroups;
