@@ -61,6 +61,7 @@ struct Dataset {
   // walker set with per-walker data: W_pc chains, chain w owns row w of y / yw / w / c (and of x unless x_shared)
   long long W_pc = 0;
   bool x_shared = false, sigma_shared = false;
+  bool sigma_uniform = false;   // one number for every point of every walker (or no :data-error at all)
   double *cst_normal_pc = nullptr, *cst_poisson_pc = nullptr;  // [W_pc] device
   cudaKernel_t k_user_pc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [kind + 3 * staged]
   int family = -1, degree = 0;
@@ -255,7 +256,7 @@ void dataset_free_data(Dataset& d) {
   d.x = d.y = d.yw = d.w = d.c = nullptr;
   d.cst_normal_pc = d.cst_poisson_pc = nullptr;
   d.W_pc = 0;
-  d.x_shared = d.sigma_shared = false;
+  d.x_shared = d.sigma_shared = d.sigma_uniform = false;
   d.n = -1;
 }
 void dataset_free_prior(Dataset& d) {
@@ -568,10 +569,11 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
   int reg_form = 0;       // 0 = no, 2 = rows up to 256 points, 3 = up to 512
   int threads = MFIT_PC_THREADS;
   if (staged && a.n > 0 && a.n <= 512 && s.family != MFIT_FAM_SEXPR && s.ll_kind != MFIT_LL_NORMAL_CUTOFF && s.ll_kind != MFIT_LL_USER &&
-      getenv("MFIT_NO_PC_RING") == nullptr && getenv("MFIT_NO_PC_REG") == nullptr) {
+      (s.sigma_uniform || s.ll_kind == MFIT_LL_POISSON) && getenv("MFIT_NO_PC_RING") == nullptr && getenv("MFIT_NO_PC_REG") == nullptr) {
     reg_form = a.n <= 256 ? 2 : 3;
     threads = MFIT_PCR_THREADS;
-    const size_t warps = MFIT_PCR_THREADS / 32, slot = reg_form == 2 ? 256 : 512, budget = 74 * 1024;  // three CTAs per SM
+    const size_t warps = MFIT_PCR_THREADS / 32, slot = reg_form == 2 ? 256 : 512,
+                 budget = (MFIT_PCR_CTAS >= 4 ? 55 : 74) * 1024;  // MFIT_PCR_CTAS CTAs per SM
     for (int S = 4; S >= 2 && a.ring_stages == 0; S--) {
       const size_t need = smem_pc + warps * S * slot * sizeof(double) + warps * S * sizeof(unsigned long long) +
                           warps * MFIT_PCR_BATCH * 33 * sizeof(double);   // ring, its mbarriers, the parked per-lane sums
@@ -1470,6 +1472,11 @@ int mfit_dataset_upload_per_walker(mfit_ctx* ctx, int d, const double* x, const 
   s.W_pc = W;
   s.x_shared = x_shared != 0;
   s.sigma_shared = sigma_shared != 0 || sigma == nullptr;
+  s.sigma_uniform = sigma == nullptr;
+  if (sigma && s.sigma_shared) {
+    s.sigma_uniform = true;
+    for (int64_t i = 1; i < n; i++) if (sigma[i] != sigma[0]) { s.sigma_uniform = false; break; }
+  }
   const size_t np = (size_t)s.n_pad, rows = (size_t)W, xrows = x_shared ? 1 : rows, wrows = s.sigma_shared ? 1 : rows;
   // one allocation: [x rows][y rows][y/sigma rows][1/sigma rows][c rows]
   double* block = nullptr;

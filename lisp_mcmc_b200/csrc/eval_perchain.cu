@@ -32,7 +32,10 @@ static const void* const k_nv[][6] = {MFIT_ROW(MfitNvMulti<1>), MFIT_ROW(MfitNvM
 // register form for rows of up to 256 / 512 points (normal and poisson likelihoods only)
 const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int staged) {
   if (ll < 0 || ll > 2) return nullptr;
-  if (staged >= 2) return mfit_builtin_perchain_reg_kernel(family, degree, ll, staged == 2 ? 8 : 16);
+  if (staged >= 2)
+    return ll == MFITK_NORMAL    ? mfit_builtin_perchain_reg_kernel_normal(family, degree, staged == 2 ? 8 : 16)
+           : ll == MFITK_POISSON ? mfit_builtin_perchain_reg_kernel_poisson(family, degree, staged == 2 ? 8 : 16)
+                                 : nullptr;
   ll += staged ? 3 : 0;
   switch (family) {
     case MFIT_FAM_POLY: return (degree >= 0 && degree <= 7) ? k_poly[degree][ll] : nullptr;

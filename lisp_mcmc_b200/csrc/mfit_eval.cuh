@@ -518,7 +518,10 @@ __device__ __forceinline__ void mfit_eval_body(const MfitMultiArgs& ma) {
 #endif
 #define MFIT_PC_STAGE_MAX 2048 /* points up to which shared x / sigma vectors are staged in shared memory */
 #define MFIT_PCR_THREADS 128   /* threads per CTA of the register form of the staged kernel (mfit_reg_row): four warps, one per scheduler */
-#define MFIT_PCR_CTAS 3        /* its CTAs per SM (register bound: 168) */
+#ifndef MFIT_PCR_CTAS
+#define MFIT_PCR_CTAS 3        /* its CTAs per SM (register bound: 168).  4 (128 registers, a two-row ring) was measured: kernel
+                                  0.125 against 0.118 ms, MH step of the set 0.155 against 0.158 ms -- occupancy is not what it lacks */
+#endif
 #define MFIT_PCR_BATCH 8       /* chains whose 32 per-lane sums wait in shared memory and are combined together (register form) */
 // STAGED: x and 1/sigma (and the cutoff constants) are one vector for all chains and sit in shared memory (xs, ws, cs
 // point there), so only the chain's own y values are streamed.
@@ -589,21 +592,25 @@ __device__ __forceinline__ void mfit_ring_row(const Model& m, const double* xs, 
 }
 
 // The same row with the chain-invariant operands in REGISTERS: lane l of a warp always evaluates points l, l + 32, ...,
-// l + 32 (NPT - 1) of whatever chain the warp is on, so their x and 1/sigma are loaded once per warp (xr, wr) instead of
-// once per chain, and only y comes out of the ring: one LDS per evaluation instead of three (the shared-memory version
+// l + 32 (NPT - 1) of whatever chain the warp is on, so their x are loaded once per warp (xr) instead of once per chain,
+// 1/sigma is ONE number (the host takes this form only when the set's sigma is uniform -- the reference's NV use passes a
+// number, nv-specific.lisp -- which spares sixteen registers), and only y comes out of the ring: one LDS per evaluation instead of three (the shared-memory version
 // issued 46 warp-instructions per warp-point for 16 FP64 ones and ran at the pace of the issue ports, ncu
 // profiles/r02_perchain_kernel_ncu_raw.csv).  Fully unrolled and branch-free: NPT independent evaluations per lane;
 // slots beyond the row are evaluated at a real abscissa and dropped by a select.  Same
 // accumulator per row and same arithmetic as mfit_ring_row: the sums are bit-identical.
-template <class Model, int LL, int NPT, class G>
-__device__ __forceinline__ void mfit_reg_row(const Model& m, const double* xr, const double* wr, int n_lane,
+// LASTONLY: the row is longer than 32 (NPT - 1) points, i.e. only the last slot can lie beyond it and only that one is
+// selected (a compare and two selects per slot are 8 % of the per-chain instructions otherwise).
+template <class Model, int LL, int NPT, bool LASTONLY, class G>
+__device__ __forceinline__ void mfit_reg_row(const Model& m, const double* xr, double w0, int n_lane,
                                              const double* row, int lane, double* acc, G& g) {
 #pragma unroll
   for (int u = 0; u < NPT; u++) {
     const double y = row[lane + 32 * u];
     const double f = mfit_model_scalar<Model, false>(m, xr[u], g);
-    const double t = MfitTerm<LL>::template add<false>(acc[u & 3], f, y, wr[MfitTerm<LL>::NARR > 2 ? u : 0], 0.0, g);
-    acc[u & 3] = (32 * u < n_lane) ? t : acc[u & 3];   // n_lane = n - lane: point lane + 32 u exists (one compare with an immediate)
+    const double t = MfitTerm<LL>::template add<false>(acc[u & 3], f, y, w0, 0.0, g);
+    if (LASTONLY && u < NPT - 1) acc[u & 3] = t;
+    else acc[u & 3] = (32 * u < n_lane) ? t : acc[u & 3];   // n_lane = n - lane: point lane + 32 u exists (one compare with an immediate)
   }
 }
 
@@ -673,7 +680,8 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       }
     }
   const int n = (int)a.n;
-  double xr[NPT > 0 ? NPT : 1], wr[NPT > 0 ? NPT : 1];
+  double xr[NPT > 0 ? NPT : 1];
+  const double w0 = (NPT > 0 && MfitTerm<LL>::NARR > 2) ? ws[0] : 0.0;   // register form: sigma is uniform over the set
   const int n_lane = n - lane;
   if constexpr (NPT > 0) {
 #pragma unroll
@@ -682,7 +690,6 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       const bool ok = j < n;
       const int jj = ok ? j : lane % n;   // a real abscissa for the slots beyond the row (their terms are dropped)
       xr[u] = xs[jj];
-      wr[u] = MfitTerm<LL>::NARR > 2 ? ws[jj] : 0.0;
     }
   }
   Model m_next;
@@ -712,8 +719,13 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       gd.reset();
       MfitNoGuard ng;
       if constexpr (NPT > 0) {
-        if (unguarded) mfit_reg_row<Model, LL, NPT>(m, xr, wr, n_lane, row, lane, acc, ng);
-        else mfit_reg_row<Model, LL, NPT>(m, xr, wr, n_lane, row, lane, acc, gd);
+        if (n > 32 * (NPT - 1)) {   // kernel-uniform
+          if (unguarded) mfit_reg_row<Model, LL, NPT, true>(m, xr, w0, n_lane, row, lane, acc, ng);
+          else mfit_reg_row<Model, LL, NPT, true>(m, xr, w0, n_lane, row, lane, acc, gd);
+        } else {
+          if (unguarded) mfit_reg_row<Model, LL, NPT, false>(m, xr, w0, n_lane, row, lane, acc, ng);
+          else mfit_reg_row<Model, LL, NPT, false>(m, xr, w0, n_lane, row, lane, acc, gd);
+        }
       } else {
         if (unguarded) mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, ng);
         else mfit_ring_row<Model, LL>(m, xs, ws, cs, row, n, lane, acc, gd);

@@ -28,7 +28,8 @@ size_t mfit_eval_smem_bytes(int ll, int x_dims, int warps, int stages);
 // eval_perchain.cu
 const void* mfit_builtin_perchain_kernel(int family, int degree, int ll, int staged);
 // eval_perchain_reg.cu
-const void* mfit_builtin_perchain_reg_kernel(int family, int degree, int ll, int npt);
+const void* mfit_builtin_perchain_reg_kernel_normal(int family, int degree, int npt);
+const void* mfit_builtin_perchain_reg_kernel_poisson(int family, int degree, int npt);
 
 // eval_fit.cu
 const void* mfit_builtin_fit_kernel(int family, int degree);

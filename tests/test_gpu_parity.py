@@ -561,6 +561,28 @@ def test_one_handle_on_one_gpu_equals_the_plain_context():
         w.close()
 
 
+def test_one_handle_error_paths():
+    """mfit_multi_*: bad device lists and call order are status codes with a message, not crashes; a failing call on one GPU
+    names that GPU"""
+    import ctypes as C
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.mfit_multi_create(0, None, 0, C.byref(h)) == _lib.ERR_ARG
+    assert L.mfit_multi_create(2, (C.c_int * 2)(0, 0), 0, C.byref(h)) == _lib.ERR_ARG and b"twice" in L.mfit_multi_last_error(None)
+    assert L.mfit_multi_create(1, (C.c_int * 1)(99), 0, C.byref(h)) == _lib.ERR_ARG and b"GPU 99" in L.mfit_multi_last_error(None)
+    assert L.mfit_multi_create(1, (C.c_int * 1)(0), 7, C.byref(h)) == _lib.ERR_ARG
+    assert L.mfit_multi_create(1, (C.c_int * 1)(0), _lib.SHARD_CHAINS, C.byref(h)) == 0 and h.value
+    assert L.mfit_multi_size(h) == 1 and L.mfit_multi_ctx(h, 0) and not L.mfit_multi_ctx(h, 1)
+    done, fin = C.c_int64(), C.c_int()
+    assert L.mfit_multi_run_advance(h, 10, C.byref(done), C.byref(fin)) == _lib.ERR_STATE     # no chains yet
+    assert L.mfit_multi_trace_read(h, 10, None, None, None) == _lib.ERR_STATE
+    assert L.mfit_multi_problem_define(h, 1, 2) == 0
+    th = np.zeros((3, 2))
+    rc = L.mfit_multi_chains_init(h, th.ctypes.data_as(C.POINTER(C.c_double)), 3, 1, 0)    # no data / model yet
+    assert rc < 0 and b"GPU 0 (rank 0)" in L.mfit_multi_last_error(h)
+    L.mfit_multi_destroy(h)
+
+
 def _nth_percentile(n, seq):
     """nth-percentile :1493-1504 restated: position n (len-1)/100; a fractional position gives the MEAN of its two
     neighbours (not an interpolation)"""
@@ -937,6 +959,26 @@ def test_walker_set_tma_ring_matches_register_path_and_oracle(orc, W, n):
     finally:
         del os.environ["MFIT_NO_PC_RING"]
     assert np.array_equal(p_ring, p_reg)
+    # rows of up to 512 points with a uniform sigma take the register form of the ring kernel (x in registers, lane sums of
+    # eight chains combined together); MFIT_NO_PC_REG keeps them on the shared-memory form: the same bits
+    os.environ["MFIT_NO_PC_REG"] = "1"
+    try:
+        p_smem = w.make_step(th0)[0]
+    finally:
+        del os.environ["MFIT_NO_PC_REG"]
+    assert np.array_equal(p_ring, p_smem)
+    if W == 300:   # a sigma VECTOR shared by the walkers (not uniform): shared-memory form, against the register-reading path
+        ns2 = dict(ns)
+        ns2["data_error"] = 1e-7 * (1.0 + 0.3 * np.sin(np.arange(n)))
+        w3 = workloads.make_walker_set(ns2, seed=3)
+        p_a = w3.make_step(th0)[0]
+        os.environ["MFIT_NO_PC_RING"] = "1"
+        try:
+            p_b = w3.make_step(th0)[0]
+        finally:
+            del os.environ["MFIT_NO_PC_RING"]
+        assert np.array_equal(p_a, p_b) and not np.array_equal(p_a, p_ring)
+        w3.close()
     x, Y = ns["data"]
     for k in sorted({0, W // 2, W - 1}):
         cfgk = dict(function=ns["function"], data=[[x, Y[k]]], data_error=ns["data_error"], keys=ns["keys"],

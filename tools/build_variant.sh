@@ -14,6 +14,6 @@ $NV "$@" -c -o $out/$name/api.o $src/api.cu &
 $NV "$@" -Xptxas -v -c -o $out/$name/eval_builtin.o $src/eval_builtin.cu 2> $out/$name/ptxas.log &
 wait
 objs=""
-for o in eval_perchain eval_perchain_reg eval_fit chain_kernels prep_kernels measure lower nvrtc_glue nccl_glue multi eval_src models_src; do objs="$objs $src/build/$o.o"; done
+for o in eval_perchain eval_perchain_reg_normal eval_perchain_reg_poisson eval_fit chain_kernels prep_kernels measure lower nvrtc_glue nccl_glue multi eval_src models_src; do objs="$objs $src/build/$o.o"; done
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o $out/libmfit_$name.so $out/$name/api.o $out/$name/eval_builtin.o $objs -ldl -lpthread
 grep -A2 "GaussLinLi0EEv13MfitMultiArgs" $out/$name/ptxas.log | grep -o "Used [0-9]* registers\|[0-9]* bytes spill stores" | tr '\n' ' '; echo " -> $out/libmfit_$name.so"
