@@ -313,6 +313,16 @@ int mfit_multi_stats_read(mfit_multi* m, mfit_chain_stats* stats /* W */);
 int mfit_multi_best_read(mfit_multi* m, double* theta, double* prob);
 int mfit_multi_last_read(mfit_multi* m, double* theta, double* prob);
 int mfit_multi_l_matrix_read(mfit_multi* m, double* l /* W x P x P */);
+/* the trace consumers and editors (mfit_trace_analytics, mfit_fit_envelope, mfit_walker_modify, mfit_keep_walks,
+ * mfit_chains_restore) on a sharded walker set: same arguments, global chain order */
+int mfit_multi_trace_analytics(mfit_multi* m, int64_t take, double* most_likely_theta, double* most_likely_prob, double* median,
+                               double* acceptance, double* covariance, double* l_matrix);
+int mfit_multi_fit_envelope(mfit_multi* m, int d, int64_t take, int which_solution, const double* x_fit, int n_fit, double* y_fit,
+                            double* y_max, double* y_min, double* params, int64_t* n_distinct);
+int mfit_multi_walker_modify(mfit_multi* m, int mode, int64_t number);
+int mfit_multi_keep_walks(mfit_multi* m, int64_t keep);
+int mfit_multi_chains_restore(mfit_multi* m, int64_t rows, const double* theta, const double* prob, const int64_t* n_valid,
+                              const int64_t* age, const double* best_theta, const double* best_prob);
 
 /* ---- measurement helpers ----------------------------------------------------------------------------
  * FP64 DFMA issue peak of the device this ctx is bound to, measured live (FLOP/s, 2 per DFMA), and the

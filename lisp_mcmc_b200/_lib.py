@@ -113,6 +113,11 @@ SIGNATURES = {
     "mfit_multi_best_read": (C.c_int, [C.c_void_p, _dp, _dp]),
     "mfit_multi_last_read": (C.c_int, [C.c_void_p, _dp, _dp]),
     "mfit_multi_l_matrix_read": (C.c_int, [C.c_void_p, _dp]),
+    "mfit_multi_trace_analytics": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "mfit_multi_fit_envelope": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, _lp]),
+    "mfit_multi_walker_modify": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
+    "mfit_multi_keep_walks": (C.c_int, [C.c_void_p, C.c_int64]),
+    "mfit_multi_chains_restore": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, _lp, _lp, _dp, _dp]),
     "mfit_measure_fp64": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp]),
     "mfit_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "mfit_eval_kernel_time": (C.c_int, [C.c_void_p, _dp, _lp]),

@@ -213,13 +213,15 @@ struct MfitNvMulti {
       }
       return r;
     }
+    if constexpr (K >= 2) {
 #pragma unroll
-    for (int k = 0; k + 1 < K; k += 2) {
-      const double d0 = x - mu[k], d1 = x - mu[k + 1];
-      const double q0 = fma(d0, d0, g2), q1 = fma(d1, d1, g2);
-      const double num = fma(sg[k], q1, sg[k + 1] * q0);
-      if (G::ON) gd.see_big((unsigned)mfit_hi(num) & 0x7fffffffu);
-      r = fma(-num, mfit_rcp_t<false>(q0 * q1, gd), r);
+      for (int k = 0; k + 1 < K; k += 2) {
+        const double d0 = x - mu[k], d1 = x - mu[k + 1];
+        const double q0 = fma(d0, d0, g2), q1 = fma(d1, d1, g2);
+        const double num = fma(sg[k], q1, sg[k + 1] * q0);
+        if (G::ON) gd.see_big((unsigned)mfit_hi(num) & 0x7fffffffu);
+        r = fma(-num, mfit_rcp_t<false>(q0 * q1, gd), r);
+      }
     }
     if (K & 1) {
       const double d = x - mu[K - 1];

@@ -423,3 +423,71 @@ int64_t mfit_multi_launch_count(mfit_multi* m) {
 }
 
 }  // extern "C"
+
+// ---- the trace consumers and editors: per-chain work, so chain shards are served in place at their offsets;
+// with sharded data sets every GPU holds all chains (and must edit them alike), and rank 0 -- for the fit envelope the
+// owner of the data set -- answers
+extern "C" {
+
+int mfit_multi_trace_analytics(mfit_multi* m, int64_t take, double* most_likely_theta, double* most_likely_prob, double* median,
+                               double* acceptance, double* covariance, double* l_matrix) {
+  int rc = need_chains(m);
+  if (rc) return rc;
+  const int P = m->P;
+  if (m->mode == MFIT_SHARD_DATASETS)
+    return run_on(m, {0}, [=](int r) {
+      return mfit_trace_analytics(m->ctx[r], take, most_likely_theta, most_likely_prob, median, acceptance, covariance, l_matrix);
+    });
+  return run_on(m, chain_ranks(m), [=](int r) {
+    const int64_t o = m->lo[r];
+    return mfit_trace_analytics(m->ctx[r], take, most_likely_theta ? most_likely_theta + o * P : nullptr,
+                                most_likely_prob ? most_likely_prob + o : nullptr, median ? median + o * P : nullptr,
+                                acceptance ? acceptance + o : nullptr, covariance ? covariance + o * P * P : nullptr,
+                                l_matrix ? l_matrix + o * P * P : nullptr);
+  });
+}
+
+int mfit_multi_fit_envelope(mfit_multi* m, int d, int64_t take, int which_solution, const double* x_fit, int n_fit, double* y_fit,
+                            double* y_max, double* y_min, double* params, int64_t* n_distinct) {
+  int rc = need_chains(m);
+  if (rc) return rc;
+  if (d < 0 || d >= m->D) return mfail(m, MFIT_ERR_ARG, "data set %d out of range", d);
+  const int P = m->P;
+  if (m->mode == MFIT_SHARD_DATASETS)
+    return run_on(m, {m->n > 1 ? d % m->n : 0}, [=](int r) {
+      return mfit_fit_envelope(m->ctx[r], d, take, which_solution, x_fit, n_fit, y_fit, y_max, y_min, params, n_distinct);
+    });
+  return run_on(m, chain_ranks(m), [=](int r) {
+    const int64_t o = m->lo[r];
+    return mfit_fit_envelope(m->ctx[r], d, take, which_solution, x_fit, n_fit, y_fit ? y_fit + o * n_fit : nullptr,
+                             y_max ? y_max + o * n_fit : nullptr, y_min ? y_min + o * n_fit : nullptr,
+                             params ? params + o * P : nullptr, n_distinct ? n_distinct + o : nullptr);
+  });
+}
+
+int mfit_multi_walker_modify(mfit_multi* m, int mode, int64_t number) {
+  int rc = need_chains(m);
+  if (rc) return rc;
+  return run_on(m, chain_ranks(m), [=](int r) { return mfit_walker_modify(m->ctx[r], mode, number); });
+}
+
+int mfit_multi_keep_walks(mfit_multi* m, int64_t keep) {
+  int rc = need_chains(m);
+  if (rc) return rc;
+  return run_on(m, chain_ranks(m), [=](int r) { return mfit_keep_walks(m->ctx[r], keep); });
+}
+
+int mfit_multi_chains_restore(mfit_multi* m, int64_t rows, const double* theta, const double* prob, const int64_t* n_valid,
+                              const int64_t* age, const double* best_theta, const double* best_prob) {
+  int rc = need_chains(m);
+  if (rc) return rc;
+  const int P = m->P;
+  return run_on(m, chain_ranks(m), [=](int r) {
+    const int64_t o = m->lo[r];   // 0 when every GPU holds all chains
+    return mfit_chains_restore(m->ctx[r], rows, theta ? theta + o * rows * P : nullptr, prob ? prob + o * rows : nullptr,
+                               n_valid ? n_valid + o : nullptr, age ? age + o : nullptr,
+                               best_theta ? best_theta + o * P : nullptr, best_prob ? best_prob + o : nullptr);
+  });
+}
+
+}  // extern "C"

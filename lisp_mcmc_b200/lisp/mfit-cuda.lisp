@@ -141,6 +141,14 @@
 (cffi:defcfun ("mfit_multi_best_read" %multi-best-read) :int (m :pointer) (theta :pointer) (prob :pointer))
 (cffi:defcfun ("mfit_multi_last_read" %multi-last-read) :int (m :pointer) (theta :pointer) (prob :pointer))
 
+(cffi:defcfun ("mfit_multi_trace_analytics" %multi-trace-analytics) :int
+  (m :pointer) (take :int64) (most-likely-theta :pointer) (most-likely-prob :pointer) (median :pointer)
+  (acceptance :pointer) (covariance :pointer) (l-matrix :pointer))
+(cffi:defcfun ("mfit_multi_fit_envelope" %multi-fit-envelope) :int
+  (m :pointer) (d :int) (take :int64) (which-solution :int) (x-fit :pointer) (n-fit :int) (y-fit :pointer)
+  (y-max :pointer) (y-min :pointer) (params :pointer) (n-distinct :pointer))
+(cffi:defcfun ("mfit_multi_walker_modify" %multi-walker-modify) :int (m :pointer) (mode :int) (number :int64))
+
 (defvar *multi* nil "True while the handle in use is an mfit_multi (a walker made with :devices).")
 (defmacro api (single multi handle &rest args)
   "Call SINGLE on a one-GPU context or its twin MULTI on a several-GPU handle."
@@ -444,10 +452,9 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
                        (%multi-run-many-steps ctx n lm)
                        (%run-many-steps ctx n lm (cffi:null-pointer) (cffi:null-pointer) 0))))
         (progn
-          (one-gpu-only walker "walker-many-steps without an l-matrix")
           (cffi:with-foreign-objects ((med :double (* w p)) (lms :double (* w p p)))
             (let ((null (cffi:null-pointer)))
-              (chk ctx (%trace-analytics ctx 1000000000 null null med null null null))
+              (chk ctx (api %trace-analytics %multi-trace-analytics ctx 1000000000 null null med null null null))
               (dotimes (c w)
                 (dotimes (i p)
                   (dotimes (j p)
@@ -487,13 +494,12 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
       (:most-likely-step (read-step walker best-reader chain))
       (:last-step (read-step walker last-reader chain))
       ((:median-params :stddev-params :covariance-matrix :l-matrix)      ; :516-543, computed on the device for all chains
-       (one-gpu-only walker "walker-get's trace analytics")
        (let ((take (or take 1000000000)) (null (cffi:null-pointer)))
          (cffi:with-foreign-objects ((med :double (* w p)) (mat :double (* w p p)))
            (ecase get
-             (:median-params (chk ctx (%trace-analytics ctx take null null med null null null)))
-             (:covariance-matrix (chk ctx (%trace-analytics ctx take null null null null mat null)))
-             ((:l-matrix :stddev-params) (chk ctx (%trace-analytics ctx take null null null null null mat))))
+             (:median-params (chk ctx (api %trace-analytics %multi-trace-analytics ctx take null null med null null null)))
+             (:covariance-matrix (chk ctx (api %trace-analytics %multi-trace-analytics ctx take null null null null mat null)))
+             ((:l-matrix :stddev-params) (chk ctx (api %trace-analytics %multi-trace-analytics ctx take null null null null null mat))))
            (flet ((mat-at (i j) (cffi:mem-aref mat :double (+ (* chain p p) (* i p) j))))
              (ecase get
                (:median-params (loop for k in keys for i from 0
@@ -525,8 +531,8 @@ POLL-EVERY steps so that mfit-walker-estop (:860, :904) is honoured.  :auto :slo
                                           (which-solution :most-likely) x-shift y-shift (chain 0))
   "walker-get-data-and-fit :1231-1255 for one CHAIN -> (x-fit max-ys min-ys y-fit x-data y-data params).  The fit
 curve and the envelope over the best 66 % of the walk are evaluated on the device for every chain at once."
-  (one-gpu-only walker "walker-get-data-and-fit")
   (let* ((ctx (gpu-walker-ctx walker)) (w (gpu-walker-n-walkers walker)) (p (gpu-walker-n-params walker))
+         (*multi* (gpu-walker-multi walker))
          (data (elt (gpu-walker-data walker) fn-number))
          (x-data (elt data x-column)) (y-data (elt data y-column))
          (x-fit (let* ((lo (reduce #'min x-data)) (hi (reduce #'max x-data))           ; linspace :235-247, :len 1000
@@ -538,8 +544,8 @@ curve and the envelope over the best 66 % of the walk are evaluated on the devic
                                 (ymin :double (* w n-fit)) (par :double (* w p)))
       (loop for x in x-fit for i from 0 do (setf (cffi:mem-aref xf :double i) (coerce x 'double-float)))
       (with-traps-masked
-        (chk ctx (%fit-envelope ctx fn-number take (if (eq which-solution :most-likely) 0 1) xf n-fit yf ymax ymin par
-                                (cffi:null-pointer))))
+        (chk ctx (api %fit-envelope %multi-fit-envelope ctx fn-number take (if (eq which-solution :most-likely) 0 1) xf n-fit
+                      yf ymax ymin par (cffi:null-pointer))))
       (flet ((row (ptr) (loop for i below n-fit collect (cffi:mem-aref ptr :double (+ (* chain n-fit) i)))))
         (list (funcall shift x-shift x-fit)
               (funcall shift y-shift (row ymax))
@@ -597,13 +603,12 @@ curve and the envelope over the best 66 % of the walk are evaluated on the devic
 
 (defun walker-modify (walker &key (modify :keep-walks) burn-number keep-number)
   "walker-modify :546-580 on the device, every chain: :burn-walks :keep-walks :reset :reset-to-most-likely."
-  (one-gpu-only walker "walker-modify")
-  (let ((ctx (gpu-walker-ctx walker)))
+  (let ((ctx (gpu-walker-ctx walker)) (*multi* (gpu-walker-multi walker)))
     (chk ctx (ecase modify
-               (:burn-walks (%walker-modify ctx 1 burn-number))
-               (:keep-walks (%walker-modify ctx 2 keep-number))
-               (:reset (%walker-modify ctx 3 0))
-               (:reset-to-most-likely (%walker-modify ctx 4 0))))
+               (:burn-walks (api %walker-modify %multi-walker-modify ctx 1 burn-number))
+               (:keep-walks (api %walker-modify %multi-walker-modify ctx 2 keep-number))
+               (:reset (api %walker-modify %multi-walker-modify ctx 3 0))
+               (:reset-to-most-likely (api %walker-modify %multi-walker-modify ctx 4 0))))
     walker))
 
 (defun mcmc-fit (&rest args &key function data params data-error log-liklihood log-prior param-bounds &allow-other-keys)

@@ -204,7 +204,7 @@ def shard_datasets(D, world):
 class _MultiABI:
     """The single-GPU entry points a Walker calls, answered by their mfit_multi_* twins (csrc/multi.cpp): the handle is an
     mfit_multi*, the walker set is sharded over the GPUs of this box inside the library (one host thread per GPU), per-chain
-    results come back in global chain order.  Calls without a twin (analytics, envelope, restore, injected streams) raise."""
+    results come back in global chain order.  Calls without a twin (sample-region, force-take-step, injected streams) raise."""
 
     def __init__(self, L):
         self._lib = L

@@ -44,6 +44,11 @@ def main():
     ok1 = ok1 and all(np.array_equal(a, b) for a, b in zip(wm.most_likely(), w0.most_likely()))
     ok1 = ok1 and all(np.array_equal(a, b) for a, b in zip(wm.last_step(), w0.last_step()))
     ok1 = ok1 and np.array_equal(wm.l_matrix(), w0.l_matrix())
+    am, a0 = wm.analytics(300), w0.analytics(300)          # walker-get's trace analytics, the fit envelope, list surgery
+    ok1 = ok1 and all(np.array_equal(am[k], a0[k], equal_nan=True) for k in a0)
+    ok1 = ok1 and all(np.array_equal(u, v, equal_nan=True) for u, v in zip(wm.data_and_fit(take=200), w0.data_and_fit(take=200)))
+    wm.modify("burn-walks", burn_number=50); w0.modify("burn-walks", burn_number=50)
+    ok1 = ok1 and all(np.array_equal(u, v, equal_nan=True) for u, v in zip(wm.trace(2001), w0.trace(2001)))
     theta = cfg["theta0"] * (1 + 0.01 * np.arange(W)[:, None])
     ok1 = ok1 and all(np.array_equal(a, b, equal_nan=True) for a, b in zip(wm.make_step(theta), w0.make_step(theta)))
     print("chains over %d GPUs behind one handle: %s (%d chains x %d rows)" % (n, "bit-identical" if ok1 else "MISMATCH", W, int(nv0.max())))
@@ -69,6 +74,11 @@ def main():
     for w in (gm, g0):
         w.adaptive_steps_full(n=300, temperature=10, auto=None)
     ok2 = ok2 and all(np.array_equal(a, b, equal_nan=True) for a, b in zip(gm.trace(2001), g0.trace(2001)))
+    ag, a0 = gm.analytics(200), g0.analytics(200)
+    ok2 = ok2 and all(np.array_equal(ag[k], a0[k], equal_nan=True) for k in a0)
+    for d in (0, Dn - 1):      # the fit envelope of a data set is evaluated on the GPU that owns it
+        ok2 = ok2 and all(np.array_equal(u, v, equal_nan=True)
+                          for u, v in zip(gm.data_and_fit(take=150, fn_number=d), g0.data_and_fit(take=150, fn_number=d)))
     print("data sets (%d over %d GPUs) behind one handle: %s" % (Dn, n, "bit-identical" if ok2 else "MISMATCH"))
     gm.close(); g0.close()
     ok = ok and ok2

@@ -550,8 +550,14 @@ def test_one_handle_on_one_gpu_equals_the_plain_context():
     assert np.array_equal(wm.l_matrix(), w0.l_matrix())
     sm, s0 = wm.stats(), w0.stats()
     assert all(np.array_equal(sm[k], s0[k]) for k in sm.dtype.names)
+    am, a0 = wm.analytics(200), w0.analytics(200)
+    assert all(np.array_equal(am[k], a0[k], equal_nan=True) for k in a0)
+    for u, v in zip(wm.data_and_fit(take=150), w0.data_and_fit(take=150)):
+        assert np.array_equal(u, v, equal_nan=True)
     with pytest.raises(NotImplementedError):
-        wm.analytics(100)
+        wm.sample_region()
+    wm.modify("burn-walks", burn_number=40); w0.modify("burn-walks", burn_number=40)
+    assert np.array_equal(wm.stats()["length"], w0.stats()["length"])
     g = workloads.c4(W=6, D=3, N=500)
     gm = workloads.make_walker(g, seed=2, devices=[0], shard="datasets")
     g0 = workloads.make_walker(g, seed=2)
