@@ -52,6 +52,7 @@ struct mfit_multi {
   std::vector<char> open;              // run_begin made, not finished (per rank)
   std::atomic<long long> stop_at{-1};  // datasets mode: the poll boundary at which all ranks leave the step loop
   bool peers_ready = false;
+  int reserved_slots = 0;              // data sets per GPU the exchange blocks were sized for
 };
 
 namespace {
@@ -213,6 +214,9 @@ int mfit_multi_problem_define(mfit_multi* m, int n_datasets, int n_params) {
   m->W = 0;
   if (m->mode == MFIT_SHARD_DATASETS && m->n > 1) {
     const int slots = (n_datasets + m->n - 1) / m->n;
+    if (m->peers_ready && slots > m->reserved_slots)
+      return mfail(m, MFIT_ERR_ARG, "%d data sets need %d exchange slots per GPU, the blocks of this handle hold %d: make a new handle",
+                   n_datasets, slots, m->reserved_slots);
     if (!m->peers_ready) {
       std::vector<char> handles((size_t)m->n * MFIT_PEER_HANDLE_BYTES);
       rc = run_all(m, [&](int r) {
@@ -225,6 +229,7 @@ int mfit_multi_problem_define(mfit_multi* m, int n_datasets, int n_params) {
       });
       if (rc) return rc;
       m->peers_ready = true;
+      m->reserved_slots = slots > 0 ? slots : 1;
     }
     std::vector<int32_t> owner(n_datasets);
     for (int d = 0; d < n_datasets; d++) owner[d] = d % m->n;
