@@ -1035,6 +1035,7 @@ std::string lower_text(const char* text, const char* const* key_names, int n_key
     out += "struct MfitUser {\n  static constexpr int USES = " + std::to_string(L.uses) + ";\n";
     out += std::string("  static constexpr bool GUARDED = ") + (L.guarded ? "true" : "false") + ";\n";
     out += "  static constexpr bool CLAMP_ONLY = false;\n  static constexpr bool FUSABLE = false;\n";
+    out += "  __device__ __forceinline__ bool positive(const MfitEvalArgs&) const { return false; }\n";
     out += "  static constexpr int XDIMS = " + std::to_string(L.x_dims > 0 ? L.x_dims : 1) + ";\n";
     out += std::string("  static constexpr bool XVEC = ") + (L.x_dims > 0 ? "true" : "false") + ";\n" + decls;
     out += "  __device__ __forceinline__ void load(const MfitEvalArgs& a, long long chain) {\n";

@@ -441,7 +441,11 @@ __device__ __forceinline__ void mfit_eval_body_t(const MfitMultiArgs& ma) {
     // warp-uniform: every chain of this warp stays inside the fast domain over the whole x range of the data set
     // (no guard at all), or at least has finite parameters where the model's fast routines clamp in place
     int mode = MFIT_MODE_GUARD;
-    if (MfitTerm<LL>::USES == 0) {
+    // a term that takes log f (log-poisson) is as safe as the model when the model also proves f positive and normal
+    bool term_safe = MfitTerm<LL>::USES == 0;
+    if constexpr (LL == MFITK_POISSON)
+      term_safe = __all_sync(FULL, (m[0].positive(a) && (!two || m[1].positive(a))) ? 1 : 0) != 0;
+    if (term_safe) {
       if (__all_sync(FULL, (m[0].safe(a) && (!two || m[1].safe(a))) ? 1 : 0) != 0) {
         mode = MFIT_MODE_FREE;
 #ifndef MFIT_NO_FUSE   /* A/B aid: tools/build_variant.sh nofuse -DMFIT_NO_FUSE */
@@ -708,7 +712,7 @@ __device__ __forceinline__ void mfit_perchain_ring(const MfitEvalArgs& a, double
       skip_next = a.skip != nullptr && a.skip[chain + warps] != 0;
     }
     m.setup();
-    const bool unguarded = !GUARDED || (MfitTerm<LL>::USES == 0 && m.safe(a));  // theta is warp-uniform
+    const bool unguarded = !GUARDED || ((MfitTerm<LL>::USES == 0 || (LL == MFITK_POISSON && m.positive(a))) && m.safe(a));  // theta is warp-uniform
     if (a.diag != 2) mfit_mbar_wait(&bars[slot], phase);
     const double* row = ring + (size_t)slot * slot_len;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -824,7 +828,7 @@ __device__ __forceinline__ void mfit_eval_perchain_body_t(const MfitEvalArgs& a)
     const double* cs = STAGED ? mfit_pc_smem + 2 * n_pad : a.c + chain * a.w_stride;
     double sum;
     // theta is warp-uniform here, so is the model's verdict on its arguments
-    const bool unguarded = !GUARDED || (MfitTerm<LL>::USES == 0 && m.safe(a));
+    const bool unguarded = !GUARDED || ((MfitTerm<LL>::USES == 0 || (LL == MFITK_POISSON && m.positive(a))) && m.safe(a));
     if (STAGED) {
       // Software pipeline over 256-point blocks, across chain boundaries: the y values of the NEXT block (of this chain,
       // or the first block of this warp's next chain) are requested before the current block is evaluated, so a warp

@@ -16,6 +16,8 @@
 //   safe(a)          true when no argument of a fast math routine can leave its domain for any x in [a.xmin, a.xmax]
 //                    (NaN parameters make every comparison false -> not safe -> guarded path -> libdevice redo)
 //   eval<SLOW>(x,gd) the model function
+//   positive(a)      true when f(x) is a positive normal number for every x in [a.xmin, a.xmax] (called after setup, only
+//                    together with safe): a likelihood term that takes log f -- log-poisson -- then needs no guard either
 //   GUARDED          whether eval uses a fast routine with a restricted domain at all
 //   FUSABLE          the model has a shorter evaluation for MfitFusedNoGuard, valid for chains with fusable(a) (and safe(a))
 //   CLAMP_ONLY       every such routine clamps in place (MfitClampGuard): chains with tame() parameters need no per-tile
@@ -41,6 +43,7 @@ struct MfitPoly {
   }
   __device__ __forceinline__ void setup() {}
   __device__ __forceinline__ bool safe(const MfitEvalArgs&) const { return true; }
+  __device__ __forceinline__ bool positive(const MfitEvalArgs&) const { return D == 0 && c[0] > 1e-300 && c[0] < 1e300; }
   template <bool SLOW, class G>
   __device__ __forceinline__ double eval(double x, G& gd) const {
     double r = c[D];
@@ -64,6 +67,10 @@ struct MfitExpo {
   }
   __device__ __forceinline__ void setup() {}
   __device__ __forceinline__ bool safe(const MfitEvalArgs& a) const { return fabs(b_) * mfit_absmax(a.xmin, a.xmax) < 700.0; }
+  // a >= 0, c > 0: f >= c; |b x| < 600 keeps a exp(b x) below 1e291
+  __device__ __forceinline__ bool positive(const MfitEvalArgs& a) const {
+    return a_ >= 0.0 && a_ < 1e30 && c_ > 1e-300 && c_ < 1e290 && fabs(b_) * mfit_absmax(a.xmin, a.xmax) < 600.0;
+  }
   template <bool SLOW, class G>
   __device__ __forceinline__ double eval(double x, G& gd) const { return fma(a_, mfit_exp_t<SLOW>(b_ * x, gd), c_); }
 };
@@ -84,6 +91,8 @@ struct MfitSinus {
   __device__ __forceinline__ bool safe(const MfitEvalArgs& a) const {
     return fabs(om) * mfit_absmax(a.xmin, a.xmax) + fabs(ph) < 9.0e4;
   }
+  // f lies in [c - |a|, c + |a|]
+  __device__ __forceinline__ bool positive(const MfitEvalArgs&) const { return c_ - fabs(a_) > 1e-300 && c_ + fabs(a_) < 1e300; }
   template <bool SLOW, class G>
   __device__ __forceinline__ double eval(double x, G& gd) const { return fma(a_, mfit_sin_t<SLOW>(fma(om, x, ph), gd), c_); }
 };
@@ -108,6 +117,10 @@ struct MfitLorentz {
   __device__ __forceinline__ bool safe(const MfitEvalArgs& a) const {
     const double dm = mfit_absmax(a.xmin - x0, a.xmax - x0);
     return g2 > 1e-290 && fma(dm, dm, g2) < 1e290;
+  }
+  // after setup: ag2 = a gamma^2 >= 0 and c > 0 give c <= f <= c + ag2 / g2
+  __device__ __forceinline__ bool positive(const MfitEvalArgs&) const {
+    return ag2 >= 0.0 && ag2 < 1e150 && g2 > 1e-140 && c_ > 1e-300 && c_ < 1e290;
   }
   template <bool SLOW, class G>
   __device__ __forceinline__ double eval(double x, G& gd) const {
@@ -148,6 +161,11 @@ struct MfitGaussLin {
   // as long as the log-likelihood is not steeper in mu than ~1e3 per unit of relative change, guaranteed here by
   // |mu| <= 8 |s| (tests/test_gpu_parity.py::test_gauss_far_from_origin is the counter-example: |mu / s| up to 9500, 1.4e-11).
   __device__ __forceinline__ bool fusable(const MfitEvalArgs&) const { return fabs(nmi) <= 8.0 * MFIT_GAUSS_ZSCALE; }
+  // a >= 0 and a background that is positive at both ends of the x range (it is linear in between)
+  __device__ __forceinline__ bool positive(const MfitEvalArgs& a) const {
+    const double l0 = fma(b1, a.xmin, b0), l1 = fma(b1, a.xmax, b0);
+    return a_ >= 0.0 && a_ < 1e290 && l0 > 1e-300 && l1 > 1e-300 && l0 < 1e290 && l1 < 1e290;
+  }
   // finite parameters and data: zs = |x - mu| |1/s| ZSCALE is then a number or +inf, never NaN, and the clamp of
   // mfit_gauss_reduce turns everything beyond 511.75 into an amplitude of a 2^-1023 (below 1e-28 for |a| < 1e280)
   __device__ __forceinline__ bool tame(const MfitEvalArgs& a) const {
@@ -201,6 +219,13 @@ struct MfitNvMulti {
 #pragma unroll
     for (int k = 0; k < K; k++) ok = ok && fabs(mu[k]) < 1e69 && fabs(sg[k]) < 1e140;
     return ok;
+  }
+  // after setup sg[k] = scale_k sigma^2: a dip is at most sg[k] / g2 deep (at its centre)
+  __device__ __forceinline__ bool positive(const MfitEvalArgs&) const {
+    double down = 0.0, up = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; k++) { down += fmax(sg[k], 0.0); up += fmax(-sg[k], 0.0); }
+    return g2 > 1e-140 && bg0 - down / g2 > 1e-300 && bg0 + up / g2 < 1e290;
   }
   template <bool SLOW, class G>
   __device__ __forceinline__ double eval(double x, G& gd) const {
