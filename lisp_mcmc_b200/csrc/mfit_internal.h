@@ -23,6 +23,10 @@ void mfit_internal_stop_word(mfit_ctx* ctx, std::atomic<long long>* word);
 
 // eval_builtin.cu
 const void* mfit_builtin_eval_kernel(int family, int degree, int ll);
+// eval_builtin_ll.cu, one object per likelihood kind
+const void* mfit_builtin_eval_kernel_normal(int family, int degree);
+const void* mfit_builtin_eval_kernel_cutoff(int family, int degree);
+const void* mfit_builtin_eval_kernel_poisson(int family, int degree);
 int mfit_family_nparams(int family, int degree);
 size_t mfit_eval_smem_bytes(int ll, int x_dims, int warps, int stages);
 // eval_perchain.cu

@@ -1,7 +1,7 @@
 """SASS evidence for a likelihood kernel: TMA / mbarrier instruction counts, the instruction mix of every innermost
 evaluation loop, and the full text of the loop with the fewest FP64 instructions per evaluation (what adapted chains run).
 
-  python tools/sass_listing.py lisp_mcmc_b200/csrc/build/eval_builtin.o _Z16mfit_eval_kernelI12MfitGaussLinLi0EEv13MfitMultiArgs \
+  python tools/sass_listing.py lisp_mcmc_b200/csrc/build/eval_builtin_normal.o _Z16mfit_eval_kernelI12MfitGaussLinLi0EEv13MfitMultiArgs \
       "mfit_eval_kernel<MfitGaussLin, log-normal>" 16 > profiles/r02_sass_gauss_lin.txt
 (last argument: evaluations per loop iteration, to turn FP64 counts into FP64 instructions per evaluation)"""
 import re
