@@ -340,7 +340,7 @@ int mfit_eval_kernel_time(mfit_ctx* ctx, double* seconds, int64_t* launches);
 int mfit_eval_mode_tiles(mfit_ctx* ctx, int64_t* tiles4);
 /* A run advances the chains as up to four groups on separate streams when there are enough of them, so that one group's
  * per-chain kernels overlap the others' likelihood kernels (results do not depend on it).  0 = automatic (3, 2 or 1 by
- * chain count), 1 = one group (also what mfit_set_timing(1) implies: an overlapped kernel cannot be timed with events),
+ * chain count; 2 at most for walker sets with per-walker data), 1 = one group (also what mfit_set_timing(1) implies: an overlapped kernel cannot be timed with events),
  * 2..4 = that many whenever possible. */
 int mfit_set_groups(mfit_ctx* ctx, int n_groups);
 /* Small problems (one walker or a few, up to a few thousand points, built-in families and priors -- the reference's own
