@@ -568,7 +568,8 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
   // of its points in registers across all the chains its warp evaluates.
   int reg_form = 0;       // 0 = no, 2 = rows up to 256 points, 3 = up to 512
   int threads = MFIT_PC_THREADS;
-  if (staged && a.n > 0 && a.n <= 512 && s.family != MFIT_FAM_SEXPR && s.ll_kind != MFIT_LL_NORMAL_CUTOFF && s.ll_kind != MFIT_LL_USER &&
+  const bool ring_ok = (long long)ctx->P * w.stride < (1LL << 31);   // mfit_perchain_ring forms idx[k] * stride in 32 bits
+  if (ring_ok && staged && a.n > 0 && a.n <= 512 && s.family != MFIT_FAM_SEXPR && s.ll_kind != MFIT_LL_NORMAL_CUTOFF && s.ll_kind != MFIT_LL_USER &&
       (s.sigma_uniform || s.ll_kind == MFIT_LL_POISSON) && getenv("MFIT_NO_PC_RING") == nullptr && getenv("MFIT_NO_PC_REG") == nullptr) {
     reg_form = a.n <= 256 ? 2 : 3;
     threads = MFIT_PCR_THREADS;
@@ -584,7 +585,7 @@ int launch_eval_per_walker(mfit_ctx* ctx, Dataset& s, const Workspace& w, int d,
     }
     if (a.ring_stages == 0) { reg_form = 0; threads = MFIT_PC_THREADS; }
   }
-  if (!reg_form && staged && a.n > 0 && getenv("MFIT_NO_PC_RING") == nullptr) {
+  if (!reg_form && ring_ok && staged && a.n > 0 && getenv("MFIT_NO_PC_RING") == nullptr) {
     const char* bk = getenv("MFIT_PC_RING_BUDGET_KB");  // experiments: shared memory one CTA may take (default: two CTAs per SM)
     const size_t warps = MFIT_PC_THREADS / 32, budget = (bk ? (size_t)atoi(bk) : 110) * 1024;
     for (int S = 3; S >= 2 && a.ring_stages == 0; S--) {
